@@ -1,0 +1,112 @@
+"""TEST INFRASTRUCTURE ONLY -- generates tests/golden/*.npz by running the reference's OWN, unmodified
+Python hot path (imported from /root/reference through oracle/ref_shim.py) on CPU, with the pybind op
+woord_query_grid_point_index served by oracle/query_oracle.c.  Run in the build container:
+
+    python -m oracle.make_golden
+
+The fixtures pin (a) oracle/shade_oracle.py + oracle/pipeline.py (tests/test_oracle_*.py, CPU) and
+(b) the CUDA path (tests/test_gpu_*.py) against numbers the reference code itself produced.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from oracle import ref_shim, query_oracle  # noqa: E402
+from pointnerf_b200 import scene  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+
+
+def build_reference_net(cfg, alpha_bias, SR=24, is_train=False):
+    ref_shim.install()
+    from models.neural_points_volumetric_model import NeuralPointsRayMarching
+    from models.neural_points.neural_points import NeuralPoints
+    from models.aggregators.point_aggregators import PointAggregator
+    from models.rendering.diff_render_func import find_render_function, find_blend_function, find_tone_map
+    vs = str(cfg.vsize)
+    opt = ref_shim.make_opt(["--vsize", vs, vs, vs, "--P", str(cfg.P), "--SR", str(SR), "--K", str(cfg.K),
+                             "--kernel_size"] + [str(cfg.kernel_size)] * 3 + ["--query_size"] + [str(cfg.query_size)] * 3 +
+                            ["--ranges"] + [str(v) for v in scene.ranges_for(cfg)], is_train=is_train)
+    pts = scene.make_points(cfg)
+    torch.manual_seed(0)
+    agg = PointAggregator(opt)
+    with torch.no_grad():
+        agg.alpha_branch[0].bias += alpha_bias
+    npts = NeuralPoints(32, 8192, opt, torch.device("cpu"))
+    npts.querier.device = "cpu"   # point_query.py:31 hard-codes "cuda"; instance attribute only, source untouched
+    npts.set_points(pts["xyz"], pts["embedding"], points_color=pts["color"], points_dir=pts["dir"],
+                    points_conf=pts["conf"], parameter=True)
+    net = NeuralPointsRayMarching(tonemap_func=find_tone_map("off"), render_func=find_render_function("radiance"),
+                                  blend_func=find_blend_function("alpha"), aggregator=agg, neural_points=npts, opt=opt,
+                                  num_pos_freqs=10, num_viewdir_freqs=4)
+    return net, agg, npts, pts, opt
+
+
+def golden_case(name, cfg, pixels, alpha_bias, SR=24):
+    net, agg, npts, pts, opt = build_reference_net(cfg, alpha_bias, SR=SR)
+    rays = scene.make_rays(cfg, pixels)
+    out = net(rays["campos"], rays["raydir"], bg_color=rays["bg_color"], camrotc2w=rays["camrotc2w"],
+              pixel_idx=rays["pixel_idx"], near=rays["near"], far=rays["far"], h=rays["h"], w=rays["w"],
+              intrinsic=rays["intrinsic"])
+    # what the querier returned (recompute through the reference class to capture intermediates)
+    q = npts.querier
+    rng_t, vsz, sdim = q.get_hyperparameters(opt.vsize, npts.xyz[None], ranges=opt.ranges)
+    qp = q.query_points(rays["pixel_idx"].to(torch.int32), npts.w2pers(npts.xyz, rays["camrotc2w"], rays["campos"]),
+                        npts.xyz[None], torch.tensor([npts.xyz.shape[0]], dtype=torch.int32), 0, 0, None,
+                        np.float32(cfg.near), np.float32(cfg.far), rays["raydir"], rays["campos"], rays["camrotc2w"])
+    loss = (out["coarse_raycolor"] ** 2).sum() + 1e-3 * out["conf_coefficient"].sum()
+    loss.backward()
+    g = {n: p.grad for n, p in net.named_parameters() if p.grad is not None}
+    fx = dict(
+        alpha_bias=np.float32(alpha_bias), SR=np.int32(SR), pixels=np.asarray(pixels, np.float32),
+        ranges6=rng_t.detach().numpy(), scaled_vdim=sdim, counters=np.array([query_oracle.last_counters[k] for k in query_oracle.COUNTER_NAMES], np.int32),
+        ray_mask=out["ray_mask"][0].numpy(), sample_pidx=qp[0][0].numpy(), sample_loc=qp[1][0].detach().numpy(),
+        sample_loc_w=qp[2][0].numpy(),
+        coarse_raycolor=out["coarse_raycolor"][0].detach().numpy(),
+        coarse_point_opacity=out["coarse_point_opacity"][0].detach().numpy(),
+        coarse_is_background=out["coarse_is_background"][0].detach().numpy(),
+        weight=out["weight"][0].numpy(), conf_coefficient=out["conf_coefficient"][0].detach().numpy(),
+        blend_weight=out["blend_weight"][0].numpy(),
+        grad_embedding=g["neural_points.points_embeding"].numpy(), grad_color=g["neural_points.points_color"].numpy(),
+        grad_dir=g["neural_points.points_dir"].numpy(), grad_conf=g["neural_points.points_conf"].numpy(),
+    )
+    for k, v in agg.state_dict().items():
+        fx["mlp." + k] = v.detach().numpy()
+        fx["gradmlp." + k] = g["aggregator." + k].numpy()
+    os.makedirs(OUT, exist_ok=True)
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **fx)
+    print(name, "R'=%d" % fx["sample_pidx"].shape[0], "bgT mean %.3f" % fx["coarse_is_background"].mean(),
+          {k: query_oracle.last_counters[k] for k in ("n_occ", "max_pts", "n_valid_samples", "n_valid_pairs")})
+
+
+def golden_hyper():
+    """get_hyperparameters of the reference class for every BASELINE config (cheap, a few ints/floats each)."""
+    ref_shim.install()
+    fx = {}
+    for name in ("chair_plumbing", "lego_render", "tiny"):
+        cfg = scene.CONFIGS[name]
+        net, agg, npts, pts, opt = build_reference_net(cfg, 0.0)
+        rng_t, vsz, sdim = npts.querier.get_hyperparameters(opt.vsize, npts.xyz[None], ranges=opt.ranges)
+        fx[name + ".ranges6"] = rng_t.detach().numpy()
+        fx[name + ".scaled_vdim"] = sdim
+        fx[name + ".scaled_vsize"] = npts.querier.scaled_vsize_np
+        fx[name + ".radius_limit"] = npts.querier.radius_limit_np
+    from models.rendering.diff_ray_marching import near_far_linear_ray_generation
+    for (near, far, D) in ((2.0, 6.0, 400), (0.0, 3.5, 400), (0.1, 8.0, 400), (2.0, 6.0, 37)):
+        _, _, _, ts = near_far_linear_ray_generation(torch.zeros(1, 3), torch.ones(1, 1, 3), D, near=near, far=far, jitter=0.)
+        fx["t_%g_%g_%d" % (near, far, D)] = ts.reshape(-1).numpy()
+    np.savez_compressed(os.path.join(OUT, "hyper.npz"), **fx)
+    print("hyper", {k: v.tolist() for k, v in fx.items() if k.endswith("scaled_vdim")})
+
+
+if __name__ == "__main__":
+    assert ref_shim.available(), "needs /root/reference"
+    tiny = scene.CONFIGS["tiny"]
+    golden_case("tiny_opaque", tiny, scene.centre_patch(tiny, 40), alpha_bias=4.0)
+    golden_case("tiny_thin_sr8", tiny, scene.centre_patch(tiny, 40), alpha_bias=0.0, SR=8)
+    golden_hyper()

@@ -1,0 +1,235 @@
+"""Host-side mirror of the reference's hot-path modules on top of libpnb200.so:
+
+  PointAggregator        parameter container with the reference's names/shapes
+                         (/root/reference/models/aggregators/point_aggregators.py:276-348:
+                         block1.{0,2}, block3.{0,2}, alpha_branch.0, color_branch.{0,2,4,6})
+  NeuralPoints           parameter container (xyz, points_embeding, points_conf, points_dir, points_color,
+                         Rw2c) + querier (/root/reference/models/neural_points/neural_points.py:231-344)
+  NeuralPointsRayMarching.forward(campos, raydir, ...)  -> the reference's output dict
+                         (/root/reference/models/neural_points_volumetric_model.py:252-364)
+  render_full(...)       the same computation with full-R outputs (fill_invalid already applied,
+                         :87-123) and NO host synchronisation -- what bench.py times.
+
+Only the shipped hot-path configuration (SURVEY.md section 8 head) is implemented; any other option
+value raises NotImplementedError (no silent fallback).
+"""
+import math
+
+import torch
+import torch.nn as nn
+
+from . import lib as _lib
+from .point_query import lighting_fast_querier, make_cam_opts
+
+MLP_KEYS = ("block1.0", "block1.2", "block3.0", "block3.2", "alpha_branch.0",
+            "color_branch.0", "color_branch.2", "color_branch.4", "color_branch.6")
+MLP_SHAPES = ((256, 284), (256, 256), (256, 263), (256, 256), (1, 256), (128, 280), (128, 128), (128, 128), (3, 128))
+MLP_KPAD = (288, 256, 272, 256, 256, 280, 128, 128, 128)  # rows of the W^T buffers handed to the kernels
+
+_REQUIRED = dict(
+    agg_dist_pers=20, agg_distance_kernel="linear", agg_intrp_order=2, apply_pnt_mask=1, num_feat_freqs=3,
+    dist_xyz_freq=5, dist_xyz_deno=0, num_viewdir_freqs=4, view_ori=0, shading_feature_mlp_layer1=2,
+    shading_feature_mlp_layer2=0, shading_feature_mlp_layer3=2, shading_alpha_mlp_layer=1,
+    shading_color_mlp_layer=4, shading_feature_num=256, act_type="LeakyReLU", act_super=1,
+    point_features_dim=32, agg_feat_xyz_mode="None", agg_alpha_xyz_mode="None", agg_color_xyz_mode="None",
+    which_agg_model="viewmlp", agg_weight_norm=1, point_conf_mode="1", point_dir_mode="1", point_color_mode="1",
+)
+_DEFAULTS = dict(view_ori=0, act_super=1, agg_weight_norm=1, apply_pnt_mask=1, which_agg_model="viewmlp",
+                 dist_xyz_deno=0, agg_feat_xyz_mode="None", agg_alpha_xyz_mode="None", agg_color_xyz_mode="None",
+                 shading_feature_mlp_layer2=0)
+
+
+def check_opt(opt):
+    """Reject (loudly) every option value outside the implemented configuration."""
+    for k, want in _REQUIRED.items():
+        have = getattr(opt, k, _DEFAULTS.get(k, want))
+        if isinstance(want, (int, float)) and not isinstance(want, bool):
+            ok = float(have) == float(want)
+        else:
+            ok = str(have) == str(want)
+        if not ok:
+            raise NotImplementedError("pnb200: option %s=%r is outside the implemented hot path (needs %r)" % (k, have, want))
+    aw = getattr(opt, "agg_axis_weight", None)
+    if aw is not None and any(float(a) != 1.0 for a in aw):
+        raise NotImplementedError("pnb200: agg_axis_weight must be None or 1 1 1")
+    if getattr(opt, "prob", 0) != 0:
+        raise NotImplementedError("pnb200: opt.prob == 1 (probe outputs) is a 'next' row (SURVEY 8f)")
+
+
+def _to_list(x):
+    if isinstance(x, torch.Tensor):
+        return x.detach().reshape(-1).cpu().tolist()
+    import numpy as np
+    return [float(v) for v in np.asarray(x, dtype=np.float64).reshape(-1)]
+
+
+class PointAggregator(nn.Module):
+    """Parameters of the reference aggregator for the shipped viewmlp configuration; same state-dict keys."""
+
+    def __init__(self, opt=None, seed=0):
+        super().__init__()
+        if opt is not None:
+            check_opt(opt)
+        self.opt = opt
+        act = lambda: nn.LeakyReLU(inplace=True)
+        self.block1 = nn.Sequential(nn.Linear(284, 256), act(), nn.Linear(256, 256), act())
+        self.block3 = nn.Sequential(nn.Linear(263, 256), act(), nn.Linear(256, 256), act())
+        self.alpha_branch = nn.Sequential(nn.Linear(256, 1))
+        self.color_branch = nn.Sequential(nn.Linear(280, 128), act(), nn.Linear(128, 128), act(),
+                                          nn.Linear(128, 128), act(), nn.Linear(128, 3))
+        g = torch.Generator().manual_seed(seed)
+        with torch.no_grad():
+            for m in self.modules():
+                if isinstance(m, nn.Linear):  # xavier-uniform, zero bias (helpers/networks.py:120-141)
+                    bound = math.sqrt(6.0 / (m.in_features + m.out_features))
+                    m.weight.copy_((torch.rand(m.weight.shape, generator=g) * 2 - 1) * bound)
+                    m.bias.zero_()
+
+    def mlp_dict(self):
+        sd = self.state_dict()
+        return {k: sd[k] for k in sd}
+
+
+class MlpPack:
+    """W^T (zero padded) buffers for the kernels, refreshed when any parameter's version changes."""
+
+    def __init__(self):
+        self.key = None
+        self.wt = None
+        self.bias = None
+        self.desc = None
+
+    def get(self, agg):
+        sd = {k: v for k, v in agg.named_parameters()}
+        ws = [sd[k + ".weight"] for k in MLP_KEYS]
+        bs = [sd[k + ".bias"] for k in MLP_KEYS]
+        key = tuple((t.data_ptr(), t._version) for t in ws + bs)
+        if key != self.key:
+            self.wt, self.bias = [], []
+            for w, b, shp, kp in zip(ws, bs, MLP_SHAPES, MLP_KPAD):
+                assert tuple(w.shape) == shp, "MLP tensor shape %s != %s" % (tuple(w.shape), shp)
+                wt = torch.zeros((kp, shp[0]), dtype=torch.float32, device=w.device)
+                wt[:shp[1]].copy_(w.detach().t())
+                self.wt.append(wt.contiguous())
+                self.bias.append(b.detach().contiguous().float())
+            d = _lib.Mlp()
+            for i in range(9):
+                d.w[i] = self.wt[i].data_ptr()
+                d.b[i] = self.bias[i].data_ptr()
+            self.desc = d
+            self.key = key
+        return self.desc
+
+
+class NeuralPoints(nn.Module):
+    """Parameter container + querier with the reference's attribute names (neural_points.py:231-344)."""
+
+    def __init__(self, opt, device):
+        super().__init__()
+        self.opt = opt
+        self.device = device
+        self.xyz = None
+        self.points_embeding = self.points_conf = self.points_dir = self.points_color = None
+        self.Rw2c = torch.eye(3)
+        self.querier = lighting_fast_querier(device, opt)
+
+    def set_points(self, points_xyz, points_embeding, points_color=None, points_dir=None, points_conf=None,
+                   parameter=True, Rw2c=None, **_):
+        mk = (lambda t, g: nn.Parameter(t.contiguous(), requires_grad=g)) if parameter else (lambda t, g: t.contiguous())
+        o = self.opt
+        self.xyz = mk(points_xyz, getattr(o, "xyz_grad", 0) > 0)
+        self.points_embeding = mk(points_embeding, getattr(o, "feat_grad", 1) > 0)
+        self.points_color = mk(points_color, getattr(o, "color_grad", 1) > 0)
+        self.points_dir = mk(points_dir, getattr(o, "dir_grad", 1) > 0)
+        self.points_conf = mk(points_conf, getattr(o, "conf_grad", 1) > 0)
+        self.Rw2c = torch.eye(3, device=points_xyz.device) if Rw2c is None else Rw2c
+        self._Rw2c_host = _to_list(self.Rw2c) if self.Rw2c.dim() == 2 else None
+        self.querier.clean_up()
+
+    def reset_querier(self):
+        self.querier.clean_up()
+
+    def points_desc(self):
+        if self.Rw2c.dim() != 2:
+            raise NotImplementedError("pnb200: per-point Rw2c is not part of the implemented hot path")
+        p = _lib.Points()
+        p.xyz = self.xyz.data_ptr(); p.emb = self.points_embeding.data_ptr(); p.color = self.points_color.data_ptr()
+        p.dir = self.points_dir.data_ptr(); p.conf = self.points_conf.data_ptr(); p.N = self.xyz.shape[0]
+        for t in (self.xyz, self.points_embeding, self.points_color, self.points_dir, self.points_conf):
+            assert t.is_cuda and t.is_contiguous() and t.dtype == torch.float32
+        assert self.points_embeding.shape[-1] == 32
+        return p
+
+
+class NeuralPointsRayMarching(nn.Module):
+    """forward() keeps the reference's signature and output dict (neural_points_volumetric_model.py:252-364)."""
+
+    def __init__(self, aggregator=None, neural_points=None, opt=None, **kwargs):
+        super().__init__()
+        check_opt(opt)
+        for k, want in (("which_render_func", "radiance"), ("which_blend_func", "alpha"), ("which_tonemap_func", "off")):
+            if getattr(opt, k, want) != want:
+                raise NotImplementedError("pnb200: %s=%r unsupported (needs %r)" % (k, getattr(opt, k), want))
+        self.aggregator = aggregator
+        self.neural_points = neural_points
+        self.opt = opt
+        self._mlp = MlpPack()
+        self._sigma_rgb = None
+        self.last = None
+
+    # -------------------------------------------------------------------------------------------------
+    def _run(self, campos, raydir, camrotc2w, near, far, bg_color, want_counters, t=None):
+        lib = _lib.load()
+        npnts, opt = self.neural_points, self.opt
+        raydir = raydir[0].contiguous() if raydir.dim() == 3 else raydir.contiguous()
+        # camera scalars go to the kernels by value: host lists / CPU tensors cost nothing, device tensors
+        # cost one small D2H copy (the reference does the same with near/far/intrinsic, neural_points.py:704)
+        cp, rt, bg = _to_list(campos)[:3], _to_list(camrotc2w)[:9], _to_list(bg_color)[:3]
+        q = npnts.querier.run_query(npnts.xyz.detach(), raydir, cp, float(near), float(far), t=t, want_counters=want_counters)
+        o = make_cam_opts(cp, rt, Rw2c=npnts._Rw2c_host,
+                          vsize_z=float(opt.vsize[2]), bg_color=bg, raydist_mode_unit=int(getattr(opt, "raydist_mode_unit", 0)))
+        cap = q.desc.cap_samples
+        if self._sigma_rgb is None or self._sigma_rgb.shape[0] < cap or self._sigma_rgb.device != raydir.device:
+            self._sigma_rgb = torch.empty((cap, 4), dtype=torch.float32, device=raydir.device)
+        mlp = self._mlp.get(self.aggregator)
+        pts = npnts.points_desc()
+        stream = torch.cuda.current_stream(raydir.device).cuda_stream
+        _lib.check(lib.pnb_shade_forward(_lib.C.byref(q.desc), _lib.C.byref(pts), _lib.C.byref(mlp), _lib.C.byref(o),
+                                         self._sigma_rgb.data_ptr(), None, 0, stream), "pnb_shade_forward")
+        R, SR = q.R, q.SR
+        dev = raydir.device
+        ray_color = torch.empty((R, 3), dtype=torch.float32, device=dev)
+        opacity = torch.empty((R, SR), dtype=torch.float32, device=dev)
+        bg_T = torch.empty((R,), dtype=torch.float32, device=dev)
+        ray_mask = torch.empty((R,), dtype=torch.int8, device=dev)
+        _lib.check(lib.pnb_composite_forward(_lib.C.byref(q.desc), _lib.C.byref(o), self._sigma_rgb.data_ptr(),
+                                             ray_color.data_ptr(), opacity.data_ptr(), bg_T.data_ptr(),
+                                             ray_mask.data_ptr(), stream), "pnb_composite_forward")
+        self.last = q
+        return q, ray_color, opacity, bg_T, ray_mask
+
+    def render_full(self, campos, raydir, camrotc2w, near, far, bg_color, t=None):
+        """Full-R outputs, fill_invalid semantics, no host sync: dict(coarse_raycolor [1,R,3],
+        coarse_point_opacity [1,R,SR], coarse_is_background [1,R,1], ray_mask [1,R])."""
+        q, ray_color, opacity, bg_T, ray_mask = self._run(campos, raydir, camrotc2w, near, far, bg_color, False, t=t)
+        return dict(coarse_raycolor=ray_color[None], coarse_point_opacity=opacity[None],
+                    coarse_is_background=bg_T[None, :, None], ray_mask=ray_mask[None])
+
+    def forward(self, campos, raydir, gt_image=None, bg_color=None, camrotc2w=None, pixel_idx=None, near=None,
+                far=None, focal=None, h=None, w=None, intrinsic=None, **kargs):
+        if "bg_ray" in kargs:
+            raise NotImplementedError("pnb200: bg_ray input is not part of the implemented hot path")
+        near_f = float(torch.min(near)) if isinstance(near, torch.Tensor) else float(near)
+        far_f = float(torch.max(far)) if isinstance(far, torch.Tensor) else float(far)
+        q, ray_color, opacity, bg_T, ray_mask = self._run(campos, raydir, camrotc2w, near_f, far_f,
+                                                          bg_color if bg_color is not None else torch.zeros(3), True)
+        # compact to the R' rays the reference returns (one host sync already paid for the counters)
+        inds = torch.nonzero(ray_mask)[:, 0]
+        out = {}
+        out["coarse_raycolor"] = ray_color[inds][None]
+        out["coarse_point_opacity"] = opacity[inds][None]
+        out["coarse_is_background"] = bg_T[inds][None, :, None]
+        # queried_shading: 1 where no sample of the ray is valid (:290) -- rays in R' always have one
+        out["queried_shading"] = torch.zeros((1, inds.shape[0], 3), dtype=torch.float32, device=ray_color.device)
+        out["ray_mask"] = ray_mask[None]
+        return out

@@ -175,6 +175,12 @@ int pnb_composite_forward(const pnb_query_t* q, const pnb_shade_opts_t* opts, co
                           float* d_ray_color, float* d_opacity, float* d_bg_T, int8_t* d_ray_mask,
                           pnb_stream_t stream);
 
+/* ---- diagnostics ---- */
+/* One-CTA tcgen05 self-test: D[128,N] = A[128,K] * W[N,K]^T with the BF16x3 split used by the fused kernel.
+ * layout: 0 = interleaved core matrices, 4 = 64-byte swizzle.  d_err: device int, non-zero on a pipeline timeout. */
+int pnb_umma_selftest(const float* d_A, const float* d_W, float* d_D, int K, int N, int layout, int* d_err,
+                      pnb_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -21,7 +21,7 @@ namespace pnb {
 constexpr int TS = 8;             // samples per tile
 constexpr int TR = TS * PNB_MAX_K;  // 64 pair rows
 constexpr int XS = 292;           // X row stride (floats): 284 inputs padded to 288, +4 against bank conflicts
-constexpr int HS = 276;           // H row stride: 263 padded to 272, +4
+constexpr int HS = 284;           // H row stride: holds 280 colour-branch inputs (256 + 24) and 272 block3 inputs
 constexpr int KC = 16;            // weight rows per pipeline stage
 constexpr int NTHREADS = 256;
 constexpr float LEAKY = 0.01f;

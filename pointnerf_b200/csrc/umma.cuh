@@ -1,0 +1,151 @@
+// tcgen05 / TMEM / mbarrier / bulk-copy building blocks for sm_100a (inline PTX, no CUTLASS).
+// Encodings follow the PTX ISA "tcgen05" chapter; field layouts cross-checked against the CuTe headers
+// vendored in the image (cute/arch/mma_sm100_desc.hpp: SmemDescriptor, InstrDescriptor).
+#pragma once
+#include <cuda_bf16.h>
+#include <stdint.h>
+
+namespace pnb {
+namespace umma {
+
+// ---- shared-memory operand layouts (K-major, 16-bit elements) -------------------------------------------------
+// An operand tile is [rows][BK] with BK = 32 elements (64 bytes of K per row).  Two layouts are implemented:
+//   LAYOUT_NONE  "interleaved" 8x16B core matrices:  byte(r, k) = (r/8)*SBO + (k/8)*LBO + (r%8)*16 + (k%8)*2
+//                with LBO = 128, SBO = 512  -> 64 bytes per row on average, no swizzle, conflict-free 16B stores
+//   LAYOUT_SW64  64B rows, 16B chunks XOR-swizzled with bits (r/2)%4 (Swizzle<2,4,3>); 8-row group = 512 B
+enum { LAYOUT_NONE = 0, LAYOUT_SW64 = 4, LAYOUT_SW128 = 2 };
+constexpr int BK = 32;  // K elements per operand block
+
+template <int LAYOUT>
+__host__ __device__ __forceinline__ uint32_t tile_offset_bytes(int r, int k) {  // k in [0, BK) (or [0,64) for SW128)
+    if (LAYOUT == LAYOUT_NONE) return (uint32_t)((r >> 3) * 512 + (k >> 3) * 128 + (r & 7) * 16 + (k & 7) * 2);
+    if (LAYOUT == LAYOUT_SW64) return (uint32_t)(r * 64 + ((((k >> 3) ^ (r >> 1)) & 3) * 16) + (k & 7) * 2);
+    return (uint32_t)(r * 128 + ((((k >> 3) ^ r) & 7) * 16) + (k & 7) * 2);  // SW128: 64 k per row
+}
+
+// 64-bit shared-memory matrix descriptor (SmemDescriptor): start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46),
+// version=1 [46,48), layout type [61,64).
+template <int LAYOUT>
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3fff);
+    uint32_t lbo, sbo;
+    if (LAYOUT == LAYOUT_NONE) { lbo = 128; sbo = 512; }
+    else if (LAYOUT == LAYOUT_SW64) { lbo = 16; sbo = 512; }   // LBO unused for swizzled K-major (encode 1)
+    else { lbo = 16; sbo = 1024; }
+    d |= (uint64_t)((lbo >> 4) & 0x3fff) << 16;
+    d |= (uint64_t)((sbo >> 4) & 0x3fff) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)LAYOUT << 61;
+    return d;
+}
+// byte advance of the start address for the k-th UMMA_K(=16 elements) step inside a block
+template <int LAYOUT>
+__device__ __forceinline__ uint32_t kstep_advance_bytes(int ks) {
+    return LAYOUT == LAYOUT_NONE ? (uint32_t)ks * 256u : (uint32_t)ks * 32u;
+}
+
+// 32-bit instruction descriptor, kind::f16, BF16 x BF16 -> F32, both operands K-major.
+__host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
+    return (1u << 4)                      // c_format = F32
+           | (1u << 7)                    // a_format = BF16
+           | (1u << 10)                   // b_format = BF16
+           | ((uint32_t)(N >> 3) << 17)   // n_dim
+           | ((uint32_t)(M >> 4) << 24);  // m_dim
+}
+
+// ---- mbarrier ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// Bounded wait: a protocol bug must surface as an error flag, never as a hung GPU.
+__device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity, int* err_flag, int code) {
+    for (uint32_t it = 0; it < (1u << 22); ++it)
+        if (mbar_try_wait(bar, parity)) return true;
+    if (err_flag) atomicExch(err_flag, code);
+    return false;
+}
+
+// ---- 1-D bulk async copy global -> shared (TMA engine, UBLKCP in SASS), completes on an mbarrier -------------------
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)),
+                 "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// ---- TMEM ---------------------------------------------------------------------------------------------------------
+template <int NCOLS>
+__device__ __forceinline__ void tmem_alloc(uint32_t* smem_result) {  // whole warp
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_result)), "n"(NCOLS));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+}
+template <int NCOLS>
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr) {  // whole warp
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(NCOLS));
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// D[tmem] (+)= A[smem] * B[smem], single thread issues.
+__device__ __forceinline__ void mma_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// all previously issued MMAs of this thread -> arrive(1) on the mbarrier when complete
+__device__ __forceinline__ void mma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// 32 lanes x 32 consecutive columns (fp32 / b32) -> 32 registers per thread (thread = lane of the warp's quadrant)
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// ---- fp32 -> (hi, lo) bf16 split: x ~= hi + lo with |x - hi - lo| <= 2^-17 |x| ------------------------------------
+__device__ __forceinline__ void split_bf16(float x, __nv_bfloat16& hi, __nv_bfloat16& lo) {
+    hi = __float2bfloat16_rn(x);
+    lo = __float2bfloat16_rn(x - __bfloat162float(hi));
+}
+// two floats -> packed hi pair / lo pair (element 0 in the low half)
+__device__ __forceinline__ void split_bf16x2(float a, float b, uint32_t& hi, uint32_t& lo) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    float ra = a - __low2float(h), rb = b - __high2float(h);
+    __nv_bfloat162 l = __floats2bfloat162_rn(ra, rb);
+    hi = *reinterpret_cast<uint32_t*>(&h);
+    lo = *reinterpret_cast<uint32_t*>(&l);
+}
+
+}  // namespace umma
+}  // namespace pnb

@@ -1,0 +1,121 @@
+// Self-test of the tcgen05 building blocks used by the fused shading kernel: one CTA computes
+//   D[128 x N] = A[128 x K] * W[N x K]^T    with the BF16x3 error-compensated split
+//   (A_hi*W_hi + A_lo*W_hi + A_hi*W_lo, fp32 accumulation in TMEM)
+// from fp32 inputs, operands staged in shared memory in the selected K-major layout.  tests/test_gpu_umma.py
+// compares D against an fp32/fp64 matmul: this pins descriptors, layouts, TMEM addressing and the split
+// accuracy on the real hardware before the big kernel depends on them.
+#include "common.cuh"
+#include "umma.cuh"
+
+namespace pnb {
+using namespace umma;
+
+template <int LAYOUT>
+__global__ void __launch_bounds__(128, 1) k_umma_selftest(const float* __restrict__ A, const float* __restrict__ W,
+                                                          float* __restrict__ D, int K, int N, int* err) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // swizzle atoms need 1 KB alignment
+    // A_hi | A_lo : nkb blocks of [128 x 32] (8 KB each);  B_hi | B_lo : one block of [N x 32] (N*64 B each)
+    const int nkb = (K + BK - 1) / BK;
+    unsigned char* a_hi = smem;
+    unsigned char* a_lo = a_hi + nkb * 8192;
+    unsigned char* b_hi = a_lo + nkb * 8192;
+    unsigned char* b_lo = b_hi + 256 * 64;
+    __shared__ uint64_t bar;
+    __shared__ uint32_t tmem_base;
+    const int tid = threadIdx.x, warp = tid >> 5;
+
+    if (tid == 0) { mbar_init(&bar, 1); mbar_fence_init(); }
+    if (warp == 0) tmem_alloc<256>(&tmem_base);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tacc = tmem_base;
+
+    // stage A (all K blocks)
+    for (int i = tid; i < 128 * nkb * BK; i += 128) {
+        int r = i / (nkb * BK), k = i - r * (nkb * BK);
+        float v = k < K ? A[(size_t)r * K + k] : 0.f;
+        __nv_bfloat16 h, l;
+        split_bf16(v, h, l);
+        uint32_t off = (uint32_t)(k / BK) * 8192u + tile_offset_bytes<LAYOUT>(r, k % BK);
+        *(__nv_bfloat16*)(a_hi + off) = h;
+        *(__nv_bfloat16*)(a_lo + off) = l;
+    }
+    const uint32_t idesc = make_idesc_bf16(128, N);
+    uint32_t phase = 0;
+    for (int kb = 0; kb < nkb; ++kb) {
+        for (int i = tid; i < N * BK; i += 128) {
+            int n = i / BK, k = i - n * BK;
+            int kg = kb * BK + k;
+            float v = kg < K ? W[(size_t)n * K + kg] : 0.f;
+            __nv_bfloat16 h, l;
+            split_bf16(v, h, l);
+            uint32_t off = tile_offset_bytes<LAYOUT>(n, k);
+            *(__nv_bfloat16*)(b_hi + off) = h;
+            *(__nv_bfloat16*)(b_lo + off) = l;
+        }
+        fence_proxy_async();
+        __syncthreads();
+        if (tid == 0) {
+            tc_fence_after();
+            const int nks = (min(K - kb * BK, BK) + 15) / 16;
+            for (int ks = 0; ks < nks; ++ks) {
+                uint32_t adv = kstep_advance_bytes<LAYOUT>(ks);
+                uint64_t dah = make_smem_desc<LAYOUT>(smem_u32(a_hi + kb * 8192) + adv);
+                uint64_t dal = make_smem_desc<LAYOUT>(smem_u32(a_lo + kb * 8192) + adv);
+                uint64_t dbh = make_smem_desc<LAYOUT>(smem_u32(b_hi) + adv);
+                uint64_t dbl = make_smem_desc<LAYOUT>(smem_u32(b_lo) + adv);
+                mma_ss(tacc, dah, dbh, idesc, (kb | ks) ? 1u : 0u);
+                mma_ss(tacc, dal, dbh, idesc, 1u);
+                mma_ss(tacc, dah, dbl, idesc, 1u);
+            }
+            mma_commit(&bar);
+        }
+        // everyone waits for the MMAs of this block before B is overwritten
+        if (!mbar_wait(&bar, phase, err, 100 + kb)) break;
+        phase ^= 1;
+        tc_fence_after();
+        __syncthreads();
+    }
+    // epilogue: warp w reads TMEM lanes 32w..32w+31
+    {
+        const int row = warp * 32 + (tid & 31);
+        for (int c0 = 0; c0 < N; c0 += 32) {
+            uint32_t v[32];
+            tmem_ld32(tacc + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+                if (c0 + j < N) D[(size_t)row * N + c0 + j] = __uint_as_float(v[j]);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc<256>(tacc);
+}
+
+}  // namespace pnb
+
+using namespace pnb;
+
+// layout: 0 = interleaved (no swizzle), 4 = 64B swizzle.  N multiple of 16 in [16,256], K <= 288.
+extern "C" int pnb_umma_selftest(const float* d_A, const float* d_W, float* d_D, int K, int N, int layout, int* d_err,
+                                 pnb_stream_t stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    PNB_REQUIRE(d_A && d_W && d_D && d_err, PNB_ERR_INVALID, "pnb_umma_selftest: null argument");
+    PNB_REQUIRE(K >= 1 && K <= 288 && N >= 16 && N <= 256 && N % 16 == 0, PNB_ERR_INVALID, "pnb_umma_selftest: bad K/N");
+    const int nkb = (K + 31) / 32;
+    size_t smem = (size_t)nkb * 8192 * 2 + 256 * 64 * 2 + 1024;
+    if (layout == umma::LAYOUT_NONE) {
+        PNB_CHECK_CUDA(cudaFuncSetAttribute(k_umma_selftest<umma::LAYOUT_NONE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_umma_selftest<umma::LAYOUT_NONE><<<1, 128, smem, stream>>>(d_A, d_W, d_D, K, N, d_err);
+    } else if (layout == umma::LAYOUT_SW64) {
+        PNB_CHECK_CUDA(cudaFuncSetAttribute(k_umma_selftest<umma::LAYOUT_SW64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_umma_selftest<umma::LAYOUT_SW64><<<1, 128, smem, stream>>>(d_A, d_W, d_D, K, N, d_err);
+    } else {
+        PNB_REQUIRE(false, PNB_ERR_INVALID, "pnb_umma_selftest: layout %d not supported", layout);
+    }
+    PNB_CHECK_CUDA(cudaGetLastError());
+    return PNB_OK;
+}

@@ -1,0 +1,36 @@
+"""GPU: tcgen05 building blocks (descriptors, operand layouts, TMEM, BF16x3 split) against a plain fp64 matmul."""
+import pytest
+import torch
+
+from pointnerf_b200 import lib as _lib
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _run(A, W, layout):
+    l = _lib.load()
+    K, N = A.shape[1], W.shape[0]
+    D = torch.full((128, N), float("nan"), device=DEV)
+    err = torch.zeros(1, dtype=torch.int32, device=DEV)
+    _lib.check(l.pnb_umma_selftest(A.data_ptr(), W.data_ptr(), D.data_ptr(), K, N, layout, err.data_ptr(),
+                                   torch.cuda.current_stream().cuda_stream), "pnb_umma_selftest")
+    torch.cuda.synchronize()
+    return D, int(err.item())
+
+
+@pytest.mark.parametrize("layout", [0, 4])
+@pytest.mark.parametrize("K,N", [(16, 16), (32, 256), (64, 128), (288, 256), (272, 256), (256, 256), (100, 64)])
+def test_umma_bf16x3_matches_matmul(layout, K, N):
+    g = torch.Generator(device=DEV).manual_seed(K * 1000 + N)
+    A = torch.randn(128, K, device=DEV, generator=g)
+    W = torch.randn(N, K, device=DEV, generator=g) / K ** 0.5
+    D, err = _run(A.contiguous(), W.contiguous(), layout)
+    assert err == 0, "pipeline timeout code %d" % err
+    ref = (A.double() @ W.double().t())
+    d = (D.double() - ref).abs().max().item()
+    scale = ref.abs().max().item()
+    assert d <= 2e-5 * max(scale, 1.0), "layout %d K=%d N=%d: max abs err %.3e (scale %.2f)" % (layout, K, N, d, scale)
+    # the split must beat a single bf16 pass by orders of magnitude
+    single = (A.bfloat16().double() @ W.bfloat16().double().t() - ref).abs().max().item()
+    assert d < single / 50

@@ -1,0 +1,617 @@
+// Fused per-pair shading on the 5th-generation tensor cores (tcgen05 + TMEM), sm_100a.
+//
+//   gather + weights + positional encoding  ->  block1 (284->256->256)  ->  cat extras  ->  block3 (263->256->256)
+//   ->  alpha branch + K-reduction  (reference: /root/reference/models/aggregators/point_aggregators.py:488-628,
+//   727-814; gather /root/reference/models/neural_points/neural_points.py:706-717)
+//
+// One persistent CTA per SM; a tile is 16 valid samples x 8 neighbour slots = 128 (sample,k) pair rows = UMMA M.
+// Every layer is D[128x256] = A[128xK] * W[256xK]^T on tcgen05.mma (kind::f16, BF16 operands, FP32 accumulate in
+// TMEM).  The reference computes these layers in fp32 (cuBLAS SGEMM, TF32 off) and the parity bar is 1e-4 on the
+// rendered radiance, which a single BF16/TF32 pass misses -> error-compensated split:
+//   A = A_hi + A_lo, W = W_hi + W_lo (bf16 each);   D = A_hi*W_hi + A_lo*W_hi + A_hi*W_lo    (3 MMAs per k-step)
+// Warp roles (320 threads):
+//   warps 0-7  workers : build the layer-1 operand (gather, PE, split) and run the epilogues
+//                        (tcgen05.ld -> bias -> LeakyReLU -> split -> next layer's A operand in shared memory)
+//   warp  8    loader  : streams the pre-packed weight images (16 KB each, already in the UMMA operand layout)
+//                        L2 -> shared memory with cp.async.bulk (TMA engine) through a 4-deep mbarrier ring
+//   warp  9    issuer  : one elected thread issues tcgen05.mma and commits to mbarriers
+// A-operand: 9 K-blocks of [128 x 32] bf16 (hi and lo), interleaved core-matrix layout (see umma.cuh).
+#include "common.cuh"
+#include "umma.cuh"
+
+namespace pnb {
+using namespace umma;
+
+namespace tc {
+constexpr int LAYOUT = LAYOUT_NONE;
+constexpr int TM = 128;                 // pair rows per tile
+constexpr int TSAMP = TM / PNB_MAX_K;   // 16 samples per tile
+constexpr int NWORK = 256;              // worker threads
+constexpr int NTHR = 320;
+constexpr int NSTAGE = 4;
+constexpr int IMG = 256 * 64;           // bytes of one weight image ([256 x 32] bf16)
+constexpr int ABLK = 128 * 64;          // bytes of one A block ([128 x 32] bf16)
+constexpr int NKB_MAX = 9;
+__host__ __device__ constexpr int nkb_of(int l) { return (l == 0 || l == 2) ? 9 : 8; }
+__host__ __device__ constexpr int img_base(int l) { return l == 0 ? 0 : l == 1 ? 9 : l == 2 ? 17 : 26; }  // in blocks
+constexpr int NBLK_TOTAL = 34;
+constexpr int IMGS_PER_TILE = 2 * NBLK_TOTAL;
+constexpr float LEAKY = 0.01f;
+
+struct Smem {
+    unsigned char a_hi[NKB_MAX * ABLK];
+    unsigned char a_lo[NKB_MAX * ABLK];
+    unsigned char b[NSTAGE][IMG];
+    float bias[4][256];
+    float wa[256];
+    float E[TM][8];
+    float wc[TM];
+    float alpha_part[2][TM];
+    uint32_t samp[TSAMP];
+    uint64_t bar_full[NSTAGE], bar_empty[NSTAGE], bar_a_ready, bar_acc_full;
+    uint32_t tmem_base;
+    int abort;
+};
+}  // namespace tc
+
+struct ShadeTcParams {
+    pnb_query_t q;
+    pnb_points_t pts;
+    pnb_shade_opts_t o;
+    const unsigned char* wimg;   // packed weight images
+    const float* bias[4];
+    const float* wa;             // alpha_branch.0 weight [256]
+    float ba;
+    float* hbar;                 // [n_valid][256]
+    float* sigma;                // [n_valid]
+    int hbar_cap;
+    int* err;
+};
+
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+__device__ __forceinline__ void rot3t(const float* M, float x, float y, float z, float& ox, float& oy, float& oz) {
+    ox = x * M[0] + y * M[1] + z * M[2];
+    oy = x * M[3] + y * M[4] + z * M[5];
+    oz = x * M[6] + y * M[7] + z * M[8];
+}
+__device__ __forceinline__ void w2pers_t(const pnb_shade_opts_t& o, float px, float py, float pz, float& xp, float& yp, float& zp) {
+    float sx = px - o.campos[0], sy = py - o.campos[1], sz = pz - o.campos[2];
+    const float* M = o.camrotc2w;
+    float xc = sx * M[0] + sy * M[3] + sz * M[6];
+    float yc = sx * M[1] + sy * M[4] + sz * M[7];
+    float zc = sx * M[2] + sy * M[5] + sz * M[8];
+    xp = xc / zc; yp = yc / zc; zp = zc;
+}
+
+// 8 consecutive K elements (one 16-byte chunk) of row r, block kb, starting at k8 (multiple of 8) -> hi / lo buffers
+__device__ __forceinline__ void store_chunk8(tc::Smem& sm, int r, int kb, int k8, const float* v) {
+    uint32_t h[4], l[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) split_bf16x2(v[2 * i], v[2 * i + 1], h[i], l[i]);
+    uint32_t off = (uint32_t)kb * tc::ABLK + tile_offset_bytes<tc::LAYOUT>(r, k8);
+    *reinterpret_cast<uint4*>(sm.a_hi + off) = make_uint4(h[0], h[1], h[2], h[3]);
+    *reinterpret_cast<uint4*>(sm.a_lo + off) = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
+__global__ void __launch_bounds__(tc::NTHR, 1) k_shade_tc(ShadeTcParams p) {
+    using namespace tc;
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    Smem& sm = *reinterpret_cast<Smem*>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const pnb_query_t& q = p.q;
+    const int n_valid = min(q.counters[PNB_QC_N_VALID], p.hbar_cap);
+    const int n_tiles = (n_valid + TSAMP - 1) / TSAMP;
+    const int my_tiles = n_tiles > (int)blockIdx.x ? (n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+
+    // ---------------------------------------------------------------- one-time setup
+    if (tid == 0) {
+        for (int s = 0; s < NSTAGE; ++s) { mbar_init(&sm.bar_full[s], 1); mbar_init(&sm.bar_empty[s], 1); }
+        mbar_init(&sm.bar_a_ready, NWORK);
+        mbar_init(&sm.bar_acc_full, 1);
+        sm.abort = 0;
+        mbar_fence_init();
+    }
+    if (warp == 9) tmem_alloc<256>(&sm.tmem_base);
+    for (int i = tid; i < 4 * 256; i += NTHR) sm.bias[i >> 8][i & 255] = p.bias[i >> 8][i & 255];
+    for (int i = tid; i < 256; i += NTHR) sm.wa[i] = p.wa[i];
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tacc = sm.tmem_base;
+
+    if (warp == 8) {
+        // ============================================================ loader
+        if (lane == 0) {
+            const uint32_t total = (uint32_t)my_tiles * IMGS_PER_TILE;
+            for (uint32_t n = 0; n < total; ++n) {
+                const uint32_t s = n % NSTAGE, ph = (n / NSTAGE) & 1u;
+                if (!mbar_wait(&sm.bar_empty[s], ph ^ 1u, p.err, 1)) break;
+                mbar_arrive_expect_tx(&sm.bar_full[s], IMG);
+                bulk_g2s(sm.b[s], p.wimg + (size_t)(n % IMGS_PER_TILE) * IMG, IMG, &sm.bar_full[s]);
+            }
+        }
+    } else if (warp == 9) {
+        // ============================================================ MMA issuer
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc_bf16(128, 256);
+            uint32_t n = 0, lyr = 0;
+            bool ok = true;
+            for (int t = 0; t < my_tiles && ok; ++t) {
+                for (int l = 0; l < 4 && ok; ++l, ++lyr) {
+                    if (!mbar_wait(&sm.bar_a_ready, lyr & 1u, p.err, 2)) { ok = false; break; }
+                    tc_fence_after();
+                    const int nkb = nkb_of(l);
+                    for (int kb = 0; kb < nkb && ok; ++kb) {
+                        const int nks = (l == 2 && kb == 8) ? 1 : 2;   // block3 input: 263 -> 272 columns used
+                        {   // W_hi image: A_hi*W_hi + A_lo*W_hi
+                            const uint32_t s = n % NSTAGE, ph = (n / NSTAGE) & 1u;
+                            if (!mbar_wait(&sm.bar_full[s], ph, p.err, 3)) { ok = false; break; }
+                            tc_fence_after();
+                            for (int ks = 0; ks < nks; ++ks) {
+                                const uint32_t adv = kstep_advance_bytes<LAYOUT>(ks);
+                                const uint64_t db = make_smem_desc<LAYOUT>(smem_u32(sm.b[s]) + adv);
+                                mma_ss(tacc, make_smem_desc<LAYOUT>(smem_u32(sm.a_hi + kb * ABLK) + adv), db, idesc, (kb | ks) ? 1u : 0u);
+                                mma_ss(tacc, make_smem_desc<LAYOUT>(smem_u32(sm.a_lo + kb * ABLK) + adv), db, idesc, 1u);
+                            }
+                            mma_commit(&sm.bar_empty[s]);
+                            ++n;
+                        }
+                        {   // W_lo image: A_hi*W_lo
+                            const uint32_t s = n % NSTAGE, ph = (n / NSTAGE) & 1u;
+                            if (!mbar_wait(&sm.bar_full[s], ph, p.err, 4)) { ok = false; break; }
+                            tc_fence_after();
+                            for (int ks = 0; ks < nks; ++ks) {
+                                const uint32_t adv = kstep_advance_bytes<LAYOUT>(ks);
+                                mma_ss(tacc, make_smem_desc<LAYOUT>(smem_u32(sm.a_hi + kb * ABLK) + adv),
+                                       make_smem_desc<LAYOUT>(smem_u32(sm.b[s]) + adv), idesc, 1u);
+                            }
+                            mma_commit(&sm.bar_empty[s]);
+                            ++n;
+                        }
+                    }
+                    mma_commit(&sm.bar_acc_full);
+                }
+            }
+        }
+    } else {
+        // ============================================================ workers (warps 0..7)
+        const int quad = warp & 3, half = warp >> 2;
+        const int erow = quad * 32 + lane;                 // epilogue row = TMEM lane
+        const uint32_t tlane = (uint32_t)(quad * 32) << 16;
+        uint32_t lyr = 0;
+        bool ok = true;
+        for (int t = 0; t < my_tiles && ok; ++t) {
+            const int tile = (int)blockIdx.x + t * (int)gridDim.x;
+            // ------------------------------------------------ build the block1 operand: 2 threads per pair row
+            {
+                const int row = warp * 16 + (lane >> 1), hf = lane & 1;
+                const int si = row >> 3, k = row & 7;
+                const int vi = tile * TSAMP + si;
+                uint32_t s = 0xffffffffu;
+                int pidx = -1;
+                float lx = 0.f, ly = 0.f, lz = 0.f, vx = 0.f, vy = 0.f, vz = 0.f;
+                if (vi < n_valid) {
+                    s = q.valid_list[vi];
+                    uint32_t pk = q.samp_ray[s];
+                    int r = (int)(pk >> 7), j = (int)(pk & 127u);
+                    int d = q.steps[(size_t)r * q.SR + j];
+                    float tt = q.t[(size_t)r * q.t_ray_stride + d];
+                    vx = q.raydir[3 * r]; vy = q.raydir[3 * r + 1]; vz = q.raydir[3 * r + 2];
+                    lx = raypos1(q.campos[0], vx, tt); ly = raypos1(q.campos[1], vy, tt); lz = raypos1(q.campos[2], vz, tt);
+                    if (k < q.K) pidx = q.cand_pidx[(size_t)s * q.K + k];
+                }
+                if ((lane & 15) == 0) sm.samp[si] = s;
+                const bool valid = pidx >= 0;
+                const int pi = valid ? pidx : 0;
+                float ovx, ovy, ovz;
+                rot3t(p.o.Rw2c, vx, vy, vz, ovx, ovy, ovz);
+                float px = __ldg(&p.pts.xyz[3 * pi]), py = __ldg(&p.pts.xyz[3 * pi + 1]), pz = __ldg(&p.pts.xyz[3 * pi + 2]);
+                float dist[6];
+                dist[0] = px - lx; dist[1] = py - ly; dist[2] = pz - lz;
+                float xpp, ypp, zpp, xsp, ysp, zsp;
+                w2pers_t(p.o, px, py, pz, xpp, ypp, zpp);
+                w2pers_t(p.o, lx, ly, lz, xsp, ysp, zsp);
+                dist[3] = xpp * zpp - xsp * zsp;
+                dist[4] = ypp * zpp - ysp * zsp;
+                dist[5] = zpp - zsp;
+                float nrm = sqrtf(dist[0] * dist[0] + dist[1] * dist[1] + dist[2] * dist[2]);
+                float w = valid ? 1.0f / fmaxf(nrm, 1e-6f) : 0.f;
+                float wsum = hf == 0 ? w : 0.f;   // the 16 lanes of one sample: sum over its 8 rows
+                wsum += __shfl_xor_sync(0xffffffffu, wsum, 1);
+                wsum += __shfl_xor_sync(0xffffffffu, wsum, 2);
+                wsum += __shfl_xor_sync(0xffffffffu, wsum, 4);
+                wsum += __shfl_xor_sync(0xffffffffu, wsum, 8);
+                w = w / fmaxf(wsum, 1e-8f);
+                float cf = __ldg(&p.pts.conf[pi]);
+                float cc = fminf(fmaxf(cf, 1e-4f), 1.0f);
+                if (hf == 0) sm.wc[row] = valid ? w * cc : 0.f;
+                float d0, d1, d2;
+                rot3t(p.o.Rw2c, dist[0], dist[1], dist[2], d0, d1, d2);
+                dist[0] = d0; dist[1] = d1; dist[2] = d2;
+                if (valid) {
+                    // raw features hf*16 .. +15 -> columns hf*16.. ; their PE -> columns 32 + 96*hf .. +95
+                    const float4* ep = (const float4*)&p.pts.emb[(size_t)pi * PNB_FEAT + hf * 16];
+                    float f[16];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        float4 v = __ldg(ep + i);
+                        f[4 * i] = v.x; f[4 * i + 1] = v.y; f[4 * i + 2] = v.z; f[4 * i + 3] = v.w;
+                    }
+                    store_chunk8(sm, row, 0, hf * 16, f);
+                    store_chunk8(sm, row, 0, hf * 16 + 8, f + 8);
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) {      // 4 features -> 24 PE values -> 3 chunks
+                        float pe[24];
+#pragma unroll
+                        for (int e = 0; e < 4; ++e)
+#pragma unroll
+                            for (int j = 0; j < 3; ++j) {
+                                float sn, cs;
+                                sincosf(f[g * 4 + e] * (float)(1 << j), &sn, &cs);
+                                pe[(e * 3 + j) * 2] = sn;
+                                pe[(e * 3 + j) * 2 + 1] = cs;
+                            }
+                        const int col = 32 + 96 * hf + 24 * g;    // multiple of 8
+#pragma unroll
+                        for (int c = 0; c < 3; ++c) {
+                            int cc0 = col + 8 * c;
+                            store_chunk8(sm, row, cc0 >> 5, cc0 & 31, pe + 8 * c);
+                        }
+                    }
+                    // distance PE: index i = d*5 + j -> columns 224 + 2i ; this thread: i in [16*hf, 16*hf + 16)
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        float pe[8];
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            int i = 16 * hf + 4 * c + e;
+                            float sn = 0.f, cs = 0.f;
+                            if (i < 30) {
+                                int dd = i / 5, jj = i - dd * 5;
+                                sincosf(dist[dd] * (float)(1 << jj), &sn, &cs);
+                            }
+                            pe[2 * e] = sn; pe[2 * e + 1] = cs;
+                        }
+                        int cc0 = 224 + 32 * hf + 8 * c;
+                        store_chunk8(sm, row, cc0 >> 5, cc0 & 31, pe);
+                    }
+                    if (hf == 1) {
+                        float cr = __ldg(&p.pts.color[3 * pi]), cg = __ldg(&p.pts.color[3 * pi + 1]), cb = __ldg(&p.pts.color[3 * pi + 2]);
+                        float ddx, ddy, ddz;
+                        rot3t(p.o.Rw2c, __ldg(&p.pts.dir[3 * pi]), __ldg(&p.pts.dir[3 * pi + 1]), __ldg(&p.pts.dir[3 * pi + 2]), ddx, ddy, ddz);
+                        sm.E[row][0] = cr; sm.E[row][1] = cg; sm.E[row][2] = cb;
+                        sm.E[row][3] = ddx - ovx; sm.E[row][4] = ddy - ovy; sm.E[row][5] = ddz - ovz;
+                        sm.E[row][6] = ddx * ovx + ddy * ovy + ddz * ovz;
+                        sm.E[row][7] = 0.f;
+                    }
+                } else {
+                    float z8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                    for (int c = hf; c < 36; c += 2) store_chunk8(sm, row, c >> 2, (c & 3) * 8, z8);   // 288 columns
+                    if (hf == 1)
+                        for (int e = 0; e < 8; ++e) sm.E[row][e] = 0.f;
+                }
+            }
+            fence_proxy_async();
+            mbar_arrive(&sm.bar_a_ready);
+
+            // ------------------------------------------------ 4 layers: epilogues
+            for (int l = 0; l < 4 && ok; ++l, ++lyr) {
+                if (!mbar_wait(&sm.bar_acc_full, lyr & 1u, p.err, 5)) { ok = false; break; }
+                tc_fence_after();
+                float apart = 0.f;
+                if (l < 3) {
+#pragma unroll 1
+                    for (int ch = 0; ch < 4; ++ch) {
+                        const int c0 = half * 128 + ch * 32;
+                        uint32_t v[32];
+                        tmem_ld32(tacc + tlane + (uint32_t)c0, v);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int g = 0; g < 4; ++g) {
+                            float x[8];
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) {
+                                float y = __uint_as_float(v[g * 8 + e]) + sm.bias[l][c0 + g * 8 + e];
+                                x[e] = y > 0.f ? y : LEAKY * y;
+                            }
+                            store_chunk8(sm, erow, c0 >> 5, g * 8, x);
+                        }
+                    }
+                    if (l == 1 && half == 0) {   // block3 extras -> columns 256..271 (zero padded)
+                        float e0[8], e1[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) e0[e] = sm.E[erow][e];
+                        store_chunk8(sm, erow, 8, 0, e0);
+                        store_chunk8(sm, erow, 8, 8, e1);
+                    }
+                    tc_fence_before();
+                    fence_proxy_async();
+                    mbar_arrive(&sm.bar_a_ready);
+                } else {
+                    // last layer: h stays in registers; alpha branch + weighted K-reduction
+                    const float wrow = sm.wc[erow];
+                    const int sidx = tile * TSAMP + (erow >> 3);
+                    const bool swrite = sidx < n_valid;
+#pragma unroll 1
+                    for (int ch = 0; ch < 4; ++ch) {
+                        const int c0 = half * 128 + ch * 32;
+                        uint32_t v[32];
+                        tmem_ld32(tacc + tlane + (uint32_t)c0, v);
+                        tmem_ld_wait();
+                        float mine[4];
+#pragma unroll
+                        for (int e = 0; e < 32; ++e) {
+                            float y = __uint_as_float(v[e]) + sm.bias[3][c0 + e];
+                            y = y > 0.f ? y : LEAKY * y;
+                            apart = fmaf(y, sm.wa[c0 + e], apart);
+                            float z = y * wrow;
+                            z += __shfl_xor_sync(0xffffffffu, z, 1);
+                            z += __shfl_xor_sync(0xffffffffu, z, 2);
+                            z += __shfl_xor_sync(0xffffffffu, z, 4);
+                            if ((e & 7) == (lane & 7)) mine[e >> 3] = z;
+                        }
+                        if (swrite) {
+                            float* dst = p.hbar + (size_t)sidx * 256 + c0 + (lane & 7);
+#pragma unroll
+                            for (int g = 0; g < 4; ++g) dst[8 * g] = mine[g];
+                        }
+                    }
+                    tc_fence_before();
+                    sm.alpha_part[half][erow] = apart;
+                    named_bar_sync(1, NWORK);
+                    if (half == 0) {
+                        float a = sm.alpha_part[0][erow] + sm.alpha_part[1][erow] + p.ba - 1.0f;
+                        float sp = a > 20.f ? a : log1pf(expf(a));
+                        float z = sp * wrow;
+                        z += __shfl_xor_sync(0xffffffffu, z, 1);
+                        z += __shfl_xor_sync(0xffffffffu, z, 2);
+                        z += __shfl_xor_sync(0xffffffffu, z, 4);
+                        if ((lane & 7) == 0 && swrite) p.sigma[sidx] = z;
+                    }
+                    named_bar_sync(1, NWORK);   // alpha_part / wc / E are reused by the next tile's build
+                }
+            }
+        }
+    }
+    // ---------------------------------------------------------------- teardown
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 9) tmem_dealloc<256>(tacc);
+}
+
+// ------------------------------------------------------------------------------------------ weight packing
+// W^T fp32 [Kpad][256] (rows >= K are zero) -> per K-block: hi image then lo image, each [256 x 32] bf16 in the
+// UMMA operand layout.
+__global__ void __launch_bounds__(256) k_pack_weights(const float* __restrict__ wt, int Kpad, int nkb, unsigned char* __restrict__ out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;   // (kb, n, k)
+    if (i >= nkb * 256 * BK) return;
+    int kb = i / (256 * BK), rem = i - kb * 256 * BK;
+    int n = rem / BK, k = rem - n * BK;
+    int kg = kb * BK + k;
+    float v = kg < Kpad ? wt[(size_t)kg * 256 + n] : 0.f;
+    __nv_bfloat16 h, l;
+    split_bf16(v, h, l);
+    uint32_t off = tile_offset_bytes<tc::LAYOUT>(n, k);
+    *(__nv_bfloat16*)(out + (size_t)(2 * kb) * tc::IMG + off) = h;
+    *(__nv_bfloat16*)(out + (size_t)(2 * kb + 1) * tc::IMG + off) = l;
+}
+
+// ------------------------------------------------------------------------------------------ colour branch
+// Per valid sample: [hbar(256), PE4(view)(24)] -> 128 -> 128 -> 128 -> 3, sigmoid*1.002-0.001 ; fp32 CUDA cores.
+// (reference: point_aggregators.py:631-637, 269-273).  Tile = 64 samples.
+namespace cb {
+constexpr int TR = 64, XS = 292, KC = 16, NTHREADS = 256;
+struct Smem {
+    float X[TR * XS];
+    float Y[TR * 132];
+    float W[2][KC * 128];
+};
+}  // namespace cb
+
+__device__ __forceinline__ void cp16(void* smem, const void* gmem) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(smem_u32(smem)), "l"(gmem));
+}
+
+// C[64 x 128] = act(A[64 x Kp] * Wt[Kp x 128] + b); thread (ty,tx): rows ty*4..+3, cols tx*4 + 64*j (j=0,1)
+__device__ __forceinline__ void gemm64x128(const float* __restrict__ A, int sa, float* __restrict__ C, int sc,
+                                           const float* __restrict__ Wt, const float* __restrict__ bias, int Kp,
+                                           float (*Wst)[cb::KC * 128]) {
+    using namespace cb;
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    float acc[4][8];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+    const int nchunk = Kp / KC;
+    {
+        const float4* src = (const float4*)Wt;
+#pragma unroll
+        for (int i = 0; i < 2; ++i) cp16(&Wst[0][(tid + i * NTHREADS) * 4], src + tid + i * NTHREADS);
+        asm volatile("cp.async.commit_group;\n" ::);
+    }
+    for (int c = 0; c < nchunk; ++c) {
+        if (c + 1 < nchunk) {
+            const float4* src = (const float4*)(Wt + (size_t)(c + 1) * KC * 128);
+#pragma unroll
+            for (int i = 0; i < 2; ++i) cp16(&Wst[(c + 1) & 1][(tid + i * NTHREADS) * 4], src + tid + i * NTHREADS);
+            asm volatile("cp.async.commit_group;\n" ::);
+            asm volatile("cp.async.wait_group 1;\n" ::);
+        } else {
+            asm volatile("cp.async.wait_group 0;\n" ::);
+        }
+        __syncthreads();
+        const float* Wc = Wst[c & 1];
+#pragma unroll
+        for (int k4 = 0; k4 < KC; k4 += 4) {
+            float4 a[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) a[i] = *(const float4*)&A[(ty * 4 + i) * sa + c * KC + k4];
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+                float4 w0 = *(const float4*)&Wc[(k4 + kk) * 128 + tx * 4];
+                float4 w1 = *(const float4*)&Wc[(k4 + kk) * 128 + tx * 4 + 64];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    float av = kk == 0 ? a[i].x : kk == 1 ? a[i].y : kk == 2 ? a[i].z : a[i].w;
+                    acc[i][0] = fmaf(av, w0.x, acc[i][0]); acc[i][1] = fmaf(av, w0.y, acc[i][1]);
+                    acc[i][2] = fmaf(av, w0.z, acc[i][2]); acc[i][3] = fmaf(av, w0.w, acc[i][3]);
+                    acc[i][4] = fmaf(av, w1.x, acc[i][4]); acc[i][5] = fmaf(av, w1.y, acc[i][5]);
+                    acc[i][6] = fmaf(av, w1.z, acc[i][6]); acc[i][7] = fmaf(av, w1.w, acc[i][7]);
+                }
+            }
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+        float4 b = *(const float4*)&bias[tx * 4 + 64 * j];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            float4 v;
+            v.x = acc[i][j * 4 + 0] + b.x; v.y = acc[i][j * 4 + 1] + b.y;
+            v.z = acc[i][j * 4 + 2] + b.z; v.w = acc[i][j * 4 + 3] + b.w;
+            v.x = v.x > 0.f ? v.x : tc::LEAKY * v.x; v.y = v.y > 0.f ? v.y : tc::LEAKY * v.y;
+            v.z = v.z > 0.f ? v.z : tc::LEAKY * v.z; v.w = v.w > 0.f ? v.w : tc::LEAKY * v.w;
+            *(float4*)&C[(ty * 4 + i) * sc + tx * 4 + 64 * j] = v;
+        }
+    }
+    __syncthreads();
+}
+
+struct ColorParams {
+    pnb_query_t q;
+    pnb_shade_opts_t o;
+    const float* w[4];   // W^T: [288][128] (rows >= 280 zero), [128][128], [128][128], [128][3]
+    const float* b[4];
+    const float* hbar;
+    const float* sigma;
+    int hbar_cap;
+    float4* sigma_rgb;
+};
+
+__global__ void __launch_bounds__(cb::NTHREADS, 1) k_color_branch(ColorParams p) {
+    using namespace cb;
+    extern __shared__ __align__(16) unsigned char smem_raw2[];
+    Smem& sm = *reinterpret_cast<Smem*>(smem_raw2);
+    const int tid = threadIdx.x;
+    const pnb_query_t& q = p.q;
+    const int n_valid = min(q.counters[PNB_QC_N_VALID], p.hbar_cap);
+    const int n_tiles = (n_valid + TR - 1) / TR;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        // inputs: 4 threads per sample row
+        {
+            const int row = tid >> 2, part = tid & 3;
+            const int vi = tile * TR + row;
+            float* xr = &sm.X[row * XS];
+            if (vi < n_valid) {
+                const float4* src = (const float4*)(p.hbar + (size_t)vi * 256 + part * 64);
+#pragma unroll
+                for (int i = 0; i < 16; ++i) *(float4*)&xr[part * 64 + 4 * i] = __ldg(src + i);
+                uint32_t s = q.valid_list[vi];
+                int r = (int)(q.samp_ray[s] >> 7);
+                float ovx, ovy, ovz;
+                rot3t(p.o.Rw2c, q.raydir[3 * r], q.raydir[3 * r + 1], q.raydir[3 * r + 2], ovx, ovy, ovz);
+                // PE4(view), ori=True layout: sin block (12) then cos block (12), index d*4 + j ; 3 (d,j) per thread
+#pragma unroll
+                for (int e = 0; e < 3; ++e) {
+                    int i = part * 3 + e, dd = i >> 2, jj = i & 3;
+                    float sn, cs;
+                    sincosf((dd == 0 ? ovx : dd == 1 ? ovy : ovz) * (float)(1 << jj), &sn, &cs);
+                    xr[256 + i] = sn;
+                    xr[268 + i] = cs;
+                }
+                if (part == 0) { xr[280] = 0.f; xr[281] = 0.f; xr[282] = 0.f; xr[283] = 0.f; xr[284] = 0.f; xr[285] = 0.f; xr[286] = 0.f; xr[287] = 0.f; }
+            } else {
+                for (int c = part; c < 288; c += 4) xr[c] = 0.f;
+            }
+        }
+        __syncthreads();
+        gemm64x128(sm.X, XS, sm.Y, 132, p.w[0], p.b[0], 288, sm.W);
+        gemm64x128(sm.Y, 132, sm.X, XS, p.w[1], p.b[1], 128, sm.W);
+        gemm64x128(sm.X, XS, sm.Y, 132, p.w[2], p.b[2], 128, sm.W);
+        if (tid < TR * 3) {
+            const int row = tid / 3, c = tid - row * 3;
+            const int vi = tile * TR + row;
+            if (vi < n_valid) {
+                float a = __ldg(&p.b[3][c]);
+                const float* wl = p.w[3];
+                for (int k = 0; k < 128; ++k) a = fmaf(sm.Y[row * 132 + k], __ldg(&wl[k * 3 + c]), a);
+                float rgb = 1.0f / (1.0f + expf(-a)) * (1.0f + 2.0f * 0.001f) - 0.001f;
+                uint32_t s = q.valid_list[vi];
+                float* dst = (float*)&p.sigma_rgb[s];
+                dst[1 + c] = rgb;
+                if (c == 0) dst[0] = p.sigma[vi];
+            }
+        }
+        __syncthreads();
+    }
+}
+
+}  // namespace pnb
+
+using namespace pnb;
+
+extern "C" size_t pnb_mlp_pack_bytes(void) { return (size_t)tc::NBLK_TOTAL * 2 * tc::IMG; }
+
+// Packs block1/block3 weights (pnb_mlp_t W^T buffers, fp32) into tcgen05 operand images.  Call once per weight version.
+extern "C" int pnb_mlp_pack(const pnb_mlp_t* mlp, void* d_out, size_t out_bytes, pnb_stream_t stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    PNB_REQUIRE(mlp && d_out, PNB_ERR_INVALID, "pnb_mlp_pack: null argument");
+    PNB_REQUIRE(out_bytes >= pnb_mlp_pack_bytes(), PNB_ERR_WORKSPACE, "pnb_mlp_pack: buffer too small");
+    const int kpad[4] = {288, 256, 272, 256};
+    for (int l = 0; l < 4; ++l) {
+        int nkb = tc::nkb_of(l);
+        int n = nkb * 256 * umma::BK;
+        k_pack_weights<<<(n + 255) / 256, 256, 0, stream>>>(mlp->w[l], kpad[l], nkb, (unsigned char*)d_out + (size_t)tc::img_base(l) * 2 * tc::IMG);
+    }
+    PNB_CHECK_CUDA(cudaGetLastError());
+    return PNB_OK;
+}
+
+extern "C" size_t pnb_shade_tc_bytes(int max_valid_samples) {
+    return align_up((size_t)max_valid_samples * 256 * sizeof(float)) + align_up((size_t)max_valid_samples * sizeof(float)) + 256;
+}
+
+// Tensor-core forward: per-pair MLPs on tcgen05 (BF16x3), colour branch on CUDA cores.  ws: >= pnb_shade_tc_bytes.
+// d_err: device int32, set non-zero if the in-kernel pipeline timed out (results invalid).
+extern "C" int pnb_shade_forward_tc(const pnb_query_t* q, const pnb_points_t* pts, const pnb_mlp_t* mlp, const void* d_packed,
+                                    const pnb_shade_opts_t* opts, float* d_sigma_rgb, void* ws, size_t ws_bytes,
+                                    int max_valid_samples, int* d_err, pnb_stream_t stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    PNB_REQUIRE(q && pts && mlp && d_packed && opts && d_sigma_rgb && ws && d_err, PNB_ERR_INVALID, "pnb_shade_forward_tc: null argument");
+    PNB_REQUIRE(q->K >= 1 && q->K <= PNB_MAX_K, PNB_ERR_UNSUPPORTED, "pnb_shade_forward_tc: K=%d unsupported", q->K);
+    PNB_REQUIRE(ws_bytes >= pnb_shade_tc_bytes(max_valid_samples), PNB_ERR_WORKSPACE, "pnb_shade_forward_tc: workspace too small");
+    static int configured = 0, n_sm = 0;
+    const size_t smem_tc = sizeof(tc::Smem) + 1024, smem_cb = sizeof(cb::Smem);
+    if (!configured) {
+        PNB_CHECK_CUDA(cudaFuncSetAttribute(k_shade_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tc));
+        PNB_CHECK_CUDA(cudaFuncSetAttribute(k_color_branch, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cb));
+        int dev = 0;
+        PNB_CHECK_CUDA(cudaGetDevice(&dev));
+        PNB_CHECK_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+        configured = 1;
+    }
+    Carver c(ws, ws_bytes);
+    float* hbar = c.take<float>((size_t)max_valid_samples * 256);
+    float* sigma = c.take<float>((size_t)max_valid_samples);
+    ShadeTcParams p;
+    p.q = *q; p.pts = *pts; p.o = *opts; p.wimg = (const unsigned char*)d_packed;
+    for (int l = 0; l < 4; ++l) p.bias[l] = mlp->b[l];
+    p.wa = mlp->w[4];
+    p.ba = 0.f;
+    PNB_CHECK_CUDA(cudaMemcpyAsync(&p.ba, mlp->b[4], sizeof(float), cudaMemcpyDeviceToHost, stream));
+    PNB_CHECK_CUDA(cudaStreamSynchronize(stream));
+    p.hbar = hbar; p.sigma = sigma; p.hbar_cap = max_valid_samples; p.err = d_err;
+    k_shade_tc<<<n_sm, tc::NTHR, smem_tc, stream>>>(p);
+    ColorParams cp;
+    cp.q = *q; cp.o = *opts;
+    for (int i = 0; i < 4; ++i) { cp.w[i] = mlp->w[5 + i]; cp.b[i] = mlp->b[5 + i]; }
+    cp.hbar = hbar; cp.sigma = sigma; cp.hbar_cap = max_valid_samples; cp.sigma_rgb = (float4*)d_sigma_rgb;
+    k_color_branch<<<n_sm * 2, cb::NTHREADS, smem_cb, stream>>>(cp);
+    PNB_CHECK_CUDA(cudaGetLastError());
+    return PNB_OK;
+}

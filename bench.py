@@ -159,6 +159,7 @@ def main():
     ap.add_argument("--impl", type=str, default="pnb200")
     ap.add_argument("--sr", type=int, default=24)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--precision", type=str, default="bf16x3", help="bf16x3 (tcgen05, default) | fp32 (CUDA cores)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
@@ -177,7 +178,7 @@ def main():
 
     cfg = scene.CONFIGS["lego_render"]
     cfg.SR = args.sr
-    net, pts, opt = harness.build_model(cfg, dev, seed=0, alpha_bias=3.0)
+    net, pts, opt = harness.build_model(cfg, dev, seed=0, alpha_bias=3.0, pnb_precision=args.precision)
     full = scene.make_rays(cfg)
     R_img = full["raydir"].shape[1]
     # global batch = `world` images; ray i of the global batch belongs to rank i % world (interleaved)
@@ -253,17 +254,36 @@ def main():
                       raydist_mode_unit=opt.raydist_mode_unit)
     stream = torch.cuda.current_stream(dev).cuda_stream
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    shade_ms = []
-    for i in range(args.steps + 1):
-        flush.fill_(1)
-        e0.record()
-        _lib.check(l.pnb_shade_forward(_lib.C.byref(q.desc), _lib.C.byref(ptsd), _lib.C.byref(mlp), _lib.C.byref(o),
-                                       net._sigma_rgb.data_ptr(), None, 0, stream), "pnb_shade_forward")
-        e1.record()
-        torch.cuda.synchronize(dev)
-        if i > 0:
-            shade_ms.append(e0.elapsed_time(e1))
-    shade_avg = float(np.mean(shade_ms))
+
+    def time_kernel(launch):
+        ms = []
+        for i in range(args.steps + 1):
+            flush.fill_(1)
+            e0.record()
+            launch()
+            e1.record()
+            torch.cuda.synchronize(dev)
+            if i > 0:
+                ms.append(e0.elapsed_time(e1))
+        return float(np.mean(ms))
+
+    if args.precision == "fp32":
+        shade_avg = time_kernel(lambda: _lib.check(l.pnb_shade_forward(
+            _lib.C.byref(q.desc), _lib.C.byref(ptsd), _lib.C.byref(mlp), _lib.C.byref(o), net._sigma_rgb.data_ptr(), None, 0, stream),
+            "pnb_shade_forward"))
+        color_avg = None
+        kname = "k_shade_fwd (fp32 CUDA-core kernel: pair MLPs + colour branch)"
+        kflops = FLOPS_PER_PAIR * qc["n_pairs"] + FLOPS_PER_SAMPLE * qc["n_valid"]
+    else:
+        def tc(mask):
+            _lib.check(l.pnb_shade_forward_tc(_lib.C.byref(q.desc), _lib.C.byref(ptsd), _lib.C.byref(mlp), net._mlp.packed.data_ptr(),
+                                              _lib.C.byref(o), net._sigma_rgb.data_ptr(), net._tc_ws.data_ptr(), net._tc_ws.numel(),
+                                              net._max_valid, mask, net._err.data_ptr(), stream), "pnb_shade_forward_tc")
+        shade_avg = time_kernel(lambda: tc(1))
+        color_avg = time_kernel(lambda: tc(2))
+        kname = "k_shade_tc (tcgen05 BF16x3 pair MLPs 284-256-256 | 263-256-256 + alpha + K-reduction)"
+        kflops = FLOPS_PER_PAIR * qc["n_pairs"]
+        net.check_errors()
 
     for _ in range(2):
         step_e2e()
@@ -273,7 +293,7 @@ def main():
     value = total_rays / (ms_res * 1e-3) / 1e6
     e2e_val = total_rays / (ms_e2e * 1e-3) / 1e6
     pk = peaks()
-    flops = FLOPS_PER_PAIR * qc["n_pairs"] + FLOPS_PER_SAMPLE * qc["n_valid"]
+    flops = kflops
     achieved = flops / (shade_avg * 1e-3) / 1e12
     peak = pk["bf16_tflops"]
     cpu = None
@@ -282,7 +302,7 @@ def main():
     if rank == 0:
         line = dict(
             metric=METRIC, value=value, unit="Mrays/s", n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3),
-            ms_per_step=ms_res / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32",
+            ms_per_step=ms_res / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None, dtype=("f32 (bf16x3 split on tcgen05, fp32 accumulate)" if args.precision != "fp32" else "f32"),
             data="synthetic",
             config=dict(workload="lego_render: 800x800 image per GPU, K=8, N=400000 points, SR=%d, D=400, P=16, vsize 0.004 x vscale 2" % args.sr,
                         rays_per_step_per_gpu=R, parallelism="rays interleave-sharded x%d, points replicated%s" % (world, ", all-gather of colours" if world > 1 else ""),
@@ -291,12 +311,15 @@ def main():
                                                candidate_samples=qc["n_cand"], occupied_voxels=gc["n_occ"], max_pts_per_voxel=gc["max_pts"])),
             e2e=dict(value=e2e_val, unit="Mrays/s", h2d_bytes_per_step=int(mine_host.numel() * 4 * world),
                      d2h_bytes_per_step=int(out_host.numel() * 4 * world), ms_per_step=ms_e2e / args.steps),
-            gpu_launches=LAUNCHES_PER_STEP * args.steps,
+            gpu_launches=(LAUNCHES_PER_STEP + (1 if args.precision != "fp32" else 0)) * args.steps,
             clocks=clocks,
-            roofline=dict(bound="tensor", kernel="k_shade_fwd (fp32 CUDA-core v1)", achieved=achieved, peak=peak, unit="TFLOP/s",
+            roofline=dict(bound="tensor", kernel=kname, achieved=achieved, peak=peak, unit="TFLOP/s",
                           frac=achieved / peak, traffic=None, peak_source="%s bf16 cuBLAS burst (MEASURED_PEAKS.json)" % pk["source"],
                           algorithmic_flops_per_launch=flops, kernel_ms=shade_avg,
-                          kernel_share_of_step=shade_avg / (ms_res / args.steps)),
+                          kernel_share_of_step=shade_avg / (ms_res / args.steps),
+                          issued_mma_flops_per_launch=(3 * flops if args.precision != "fp32" else None),
+                          tensor_pipe_frac_issued=(3 * achieved / peak if args.precision != "fp32" else None),
+                          colour_branch_kernel_ms=color_avg),
             cpu_baseline=cpu,
         )
         print(json.dumps(line))

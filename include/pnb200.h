@@ -175,6 +175,21 @@ int pnb_composite_forward(const pnb_query_t* q, const pnb_shade_opts_t* opts, co
                           float* d_ray_color, float* d_opacity, float* d_bg_T, int8_t* d_ray_mask,
                           pnb_stream_t stream);
 
+/* ---- shading forward on the tensor cores (tcgen05 / TMEM, BF16x3 error-compensated split) ---- */
+/* Packs block1 / block3 weights of a pnb_mlp_t (fp32 W^T buffers) into tcgen05 operand images (hi/lo bf16, UMMA
+ * shared-memory layout).  Call once per weight version.  d_out: >= pnb_mlp_pack_bytes() bytes. */
+size_t pnb_mlp_pack_bytes(void);
+int pnb_mlp_pack(const pnb_mlp_t* mlp, void* d_out, size_t out_bytes, pnb_stream_t stream);
+/* Same contract as pnb_shade_forward; per-pair MLPs run as tcgen05.mma tiles, colour branch on CUDA cores.
+ * mlp->w[5] must be zero padded to 288 rows.  ws >= pnb_shade_tc_bytes(max_valid_samples).  d_err: device int32,
+ * 0 on success, 9 if the query produced more valid samples than max_valid_samples, 1..5 on an internal pipeline
+ * time-out (results invalid in both cases). */
+size_t pnb_shade_tc_bytes(int max_valid_samples);
+int pnb_shade_forward_tc(const pnb_query_t* q, const pnb_points_t* pts, const pnb_mlp_t* mlp, const void* d_packed,
+                         const pnb_shade_opts_t* opts, float* d_sigma_rgb, void* ws, size_t ws_bytes,
+                         int max_valid_samples, int stage_mask /* 1 pair MLPs, 2 colour branch, 3 both */,
+                         int* d_err, pnb_stream_t stream);
+
 /* ---- diagnostics ---- */
 /* One-CTA tcgen05 self-test: D[128,N] = A[128,K] * W[N,K]^T with the BF16x3 split used by the fused kernel.
  * layout: 0 = interleaved core matrices, 4 = 64-byte swizzle.  d_err: device int, non-zero on a pipeline timeout. */

@@ -61,7 +61,7 @@ struct ShadeTcParams {
     const unsigned char* wimg;   // packed weight images
     const float* bias[4];
     const float* wa;             // alpha_branch.0 weight [256]
-    float ba;
+    const float* ba;             // alpha_branch.0 bias [1]
     float* hbar;                 // [n_valid][256]
     float* sigma;                // [n_valid]
     int hbar_cap;
@@ -113,6 +113,7 @@ __global__ void __launch_bounds__(tc::NTHR, 1) k_shade_tc(ShadeTcParams p) {
         mbar_init(&sm.bar_acc_full, 1);
         sm.abort = 0;
         mbar_fence_init();
+        if (blockIdx.x == 0 && q.counters[PNB_QC_N_VALID] > p.hbar_cap) atomicExch(p.err, 9);   // capacity exceeded
     }
     if (warp == 9) tmem_alloc<256>(&sm.tmem_base);
     for (int i = tid; i < 4 * 256; i += NTHR) sm.bias[i >> 8][i & 255] = p.bias[i >> 8][i & 255];
@@ -363,7 +364,7 @@ __global__ void __launch_bounds__(tc::NTHR, 1) k_shade_tc(ShadeTcParams p) {
                     sm.alpha_part[half][erow] = apart;
                     named_bar_sync(1, NWORK);
                     if (half == 0) {
-                        float a = sm.alpha_part[0][erow] + sm.alpha_part[1][erow] + p.ba - 1.0f;
+                        float a = sm.alpha_part[0][erow] + sm.alpha_part[1][erow] + __ldg(p.ba) - 1.0f;
                         float sp = a > 20.f ? a : log1pf(expf(a));
                         float z = sp * wrow;
                         z += __shfl_xor_sync(0xffffffffu, z, 1);
@@ -580,7 +581,7 @@ extern "C" size_t pnb_shade_tc_bytes(int max_valid_samples) {
 // d_err: device int32, set non-zero if the in-kernel pipeline timed out (results invalid).
 extern "C" int pnb_shade_forward_tc(const pnb_query_t* q, const pnb_points_t* pts, const pnb_mlp_t* mlp, const void* d_packed,
                                     const pnb_shade_opts_t* opts, float* d_sigma_rgb, void* ws, size_t ws_bytes,
-                                    int max_valid_samples, int* d_err, pnb_stream_t stream_) {
+                                    int max_valid_samples, int stage_mask, int* d_err, pnb_stream_t stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     PNB_REQUIRE(q && pts && mlp && d_packed && opts && d_sigma_rgb && ws && d_err, PNB_ERR_INVALID, "pnb_shade_forward_tc: null argument");
     PNB_REQUIRE(q->K >= 1 && q->K <= PNB_MAX_K, PNB_ERR_UNSUPPORTED, "pnb_shade_forward_tc: K=%d unsupported", q->K);
@@ -602,16 +603,14 @@ extern "C" int pnb_shade_forward_tc(const pnb_query_t* q, const pnb_points_t* pt
     p.q = *q; p.pts = *pts; p.o = *opts; p.wimg = (const unsigned char*)d_packed;
     for (int l = 0; l < 4; ++l) p.bias[l] = mlp->b[l];
     p.wa = mlp->w[4];
-    p.ba = 0.f;
-    PNB_CHECK_CUDA(cudaMemcpyAsync(&p.ba, mlp->b[4], sizeof(float), cudaMemcpyDeviceToHost, stream));
-    PNB_CHECK_CUDA(cudaStreamSynchronize(stream));
+    p.ba = mlp->b[4];
     p.hbar = hbar; p.sigma = sigma; p.hbar_cap = max_valid_samples; p.err = d_err;
-    k_shade_tc<<<n_sm, tc::NTHR, smem_tc, stream>>>(p);
+    if (stage_mask & 1) k_shade_tc<<<n_sm, tc::NTHR, smem_tc, stream>>>(p);
     ColorParams cp;
     cp.q = *q; cp.o = *opts;
     for (int i = 0; i < 4; ++i) { cp.w[i] = mlp->w[5 + i]; cp.b[i] = mlp->b[5 + i]; }
     cp.hbar = hbar; cp.sigma = sigma; cp.hbar_cap = max_valid_samples; cp.sigma_rgb = (float4*)d_sigma_rgb;
-    k_color_branch<<<n_sm * 2, cb::NTHREADS, smem_cb, stream>>>(cp);
+    if (stage_mask & 2) k_color_branch<<<n_sm * 2, cb::NTHREADS, smem_cb, stream>>>(cp);
     PNB_CHECK_CUDA(cudaGetLastError());
     return PNB_OK;
 }

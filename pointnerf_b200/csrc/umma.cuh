@@ -71,16 +71,25 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
     uint32_t ok;
     asm volatile(
-        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity)
+        : "r"(smem_u32(bar)), "r"(parity), "r"(20000u)   // suspend-time hint (ns)
         : "memory");
     return ok != 0;
 }
-// Bounded wait: a protocol bug must surface as an error flag, never as a hung GPU.
+__device__ __forceinline__ uint64_t globaltimer_ns() {
+    uint64_t t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+// Bounded wait (2 s wall clock): a protocol bug must surface as an error flag, never as a hung GPU.
 __device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity, int* err_flag, int code) {
-    for (uint32_t it = 0; it < (1u << 22); ++it)
+    if (mbar_try_wait(bar, parity)) return true;
+    const uint64_t t0 = globaltimer_ns();
+    for (;;) {
         if (mbar_try_wait(bar, parity)) return true;
+        if (globaltimer_ns() - t0 > 2000000000ull) break;
+    }
     if (err_flag) atomicExch(err_flag, code);
     return false;
 }

@@ -24,7 +24,7 @@ from .point_query import lighting_fast_querier, make_cam_opts
 MLP_KEYS = ("block1.0", "block1.2", "block3.0", "block3.2", "alpha_branch.0",
             "color_branch.0", "color_branch.2", "color_branch.4", "color_branch.6")
 MLP_SHAPES = ((256, 284), (256, 256), (256, 263), (256, 256), (1, 256), (128, 280), (128, 128), (128, 128), (3, 128))
-MLP_KPAD = (288, 256, 272, 256, 256, 280, 128, 128, 128)  # rows of the W^T buffers handed to the kernels
+MLP_KPAD = (288, 256, 272, 256, 256, 288, 128, 128, 128)  # rows of the W^T buffers handed to the kernels
 
 _REQUIRED = dict(
     agg_dist_pers=20, agg_distance_kernel="linear", agg_intrp_order=2, apply_pnt_mask=1, num_feat_freqs=3,
@@ -98,6 +98,7 @@ class MlpPack:
         self.wt = None
         self.bias = None
         self.desc = None
+        self.packed = None   # tcgen05 operand images of block1/block3 (hi/lo bf16)
 
     def get(self, agg):
         sd = {k: v for k, v in agg.named_parameters()}
@@ -118,6 +119,12 @@ class MlpPack:
                 d.b[i] = self.bias[i].data_ptr()
             self.desc = d
             self.key = key
+            lib = _lib.load()
+            nb = lib.pnb_mlp_pack_bytes()
+            if self.packed is None or self.packed.device != ws[0].device:
+                self.packed = torch.empty(nb, dtype=torch.uint8, device=ws[0].device)
+            _lib.check(lib.pnb_mlp_pack(_lib.C.byref(d), self.packed.data_ptr(), nb,
+                                        torch.cuda.current_stream(ws[0].device).cuda_stream), "pnb_mlp_pack")
         return self.desc
 
 
@@ -175,6 +182,13 @@ class NeuralPointsRayMarching(nn.Module):
         self.opt = opt
         self._mlp = MlpPack()
         self._sigma_rgb = None
+        self._tc_ws = None
+        self._err = None
+        # "bf16x3": per-pair MLPs on tcgen05 tensor cores with the error-compensated split (default);
+        # "fp32": the exact-fp32 CUDA-core kernel.
+        self.precision = getattr(opt, "pnb_precision", "bf16x3")
+        if self.precision not in ("bf16x3", "fp32"):
+            raise NotImplementedError("pnb200: pnb_precision=%r (bf16x3 | fp32)" % self.precision)
         self.last = None
 
     # -------------------------------------------------------------------------------------------------
@@ -194,8 +208,22 @@ class NeuralPointsRayMarching(nn.Module):
         mlp = self._mlp.get(self.aggregator)
         pts = npnts.points_desc()
         stream = torch.cuda.current_stream(raydir.device).cuda_stream
-        _lib.check(lib.pnb_shade_forward(_lib.C.byref(q.desc), _lib.C.byref(pts), _lib.C.byref(mlp), _lib.C.byref(o),
-                                         self._sigma_rgb.data_ptr(), None, 0, stream), "pnb_shade_forward")
+        if self.precision == "fp32":
+            _lib.check(lib.pnb_shade_forward(_lib.C.byref(q.desc), _lib.C.byref(pts), _lib.C.byref(mlp), _lib.C.byref(o),
+                                             self._sigma_rgb.data_ptr(), None, 0, stream), "pnb_shade_forward")
+        else:
+            per_ray = int(getattr(opt, "pnb_max_valid_per_ray", 10))
+            max_valid = int(min(q.R * q.SR, max(1 << 20, q.R * per_ray)))
+            self._max_valid = max_valid
+            nb = lib.pnb_shade_tc_bytes(max_valid)
+            if self._tc_ws is None or self._tc_ws.numel() < nb or self._tc_ws.device != raydir.device:
+                self._tc_ws = torch.empty(nb, dtype=torch.uint8, device=raydir.device)
+            if self._err is None or self._err.device != raydir.device:
+                self._err = torch.zeros(1, dtype=torch.int32, device=raydir.device)
+            _lib.check(lib.pnb_shade_forward_tc(_lib.C.byref(q.desc), _lib.C.byref(pts), _lib.C.byref(mlp),
+                                                self._mlp.packed.data_ptr(), _lib.C.byref(o), self._sigma_rgb.data_ptr(),
+                                                self._tc_ws.data_ptr(), self._tc_ws.numel(), max_valid, 3,
+                                                self._err.data_ptr(), stream), "pnb_shade_forward_tc")
         R, SR = q.R, q.SR
         dev = raydir.device
         ray_color = torch.empty((R, 3), dtype=torch.float32, device=dev)
@@ -207,6 +235,15 @@ class NeuralPointsRayMarching(nn.Module):
                                              ray_mask.data_ptr(), stream), "pnb_composite_forward")
         self.last = q
         return q, ray_color, opacity, bg_T, ray_mask
+
+    def check_errors(self):
+        """Synchronising check of the device-side error flag of the tensor-core path (raises on failure)."""
+        if self._err is not None:
+            code = int(self._err.item())
+            if code == 9:
+                raise _lib.PnbError("pnb200: more valid samples than the shading workspace holds; raise opt.pnb_max_valid_per_ray")
+            if code != 0:
+                raise _lib.PnbError("pnb200: tcgen05 pipeline time-out (code %d)" % code)
 
     def render_full(self, campos, raydir, camrotc2w, near, far, bg_color, t=None):
         """Full-R outputs, fill_invalid semantics, no host sync: dict(coarse_raycolor [1,R,3],
@@ -223,6 +260,7 @@ class NeuralPointsRayMarching(nn.Module):
         far_f = float(torch.max(far)) if isinstance(far, torch.Tensor) else float(far)
         q, ray_color, opacity, bg_T, ray_mask = self._run(campos, raydir, camrotc2w, near_f, far_f,
                                                           bg_color if bg_color is not None else torch.zeros(3), True)
+        self.check_errors()
         # compact to the R' rays the reference returns (one host sync already paid for the counters)
         inds = torch.nonzero(ray_mask)[:, 0]
         out = {}

@@ -250,7 +250,7 @@ def main():
     mlp = net._mlp.get(net.aggregator)
     ptsd = net.neural_points.points_desc()
     from pointnerf_b200.point_query import make_cam_opts
-    o = make_cam_opts(cam[0], cam[1], Rw2c=net.neural_points._Rw2c_host, vsize_z=float(opt.vsize[2]), bg_color=cam[4],
+    o = make_cam_opts(cam[0], cam[1], Rw2c=None, vsize_z=float(opt.vsize[2]), bg_color=cam[4],
                       raydist_mode_unit=opt.raydist_mode_unit)
     stream = torch.cuda.current_stream(dev).cuda_stream
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

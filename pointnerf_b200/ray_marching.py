@@ -128,6 +128,37 @@ class MlpPack:
         return self.desc
 
 
+def points_desc_of(npnts):
+    """pnb_points_t over the parameter tensors of a NeuralPoints-like module (ours or the reference's)."""
+    if npnts.Rw2c is not None and npnts.Rw2c.dim() != 2:
+        raise NotImplementedError("pnb200: per-point Rw2c is not part of the implemented hot path")
+    for name in ("points_embeding", "points_color", "points_dir", "points_conf"):
+        if getattr(npnts, name, None) is None:
+            raise NotImplementedError("pnb200: neural_points.%s is None; the hot path needs point_{conf,dir,color}_mode=1" % name)
+    p = _lib.Points()
+    tens = (npnts.xyz, npnts.points_embeding, npnts.points_color, npnts.points_dir, npnts.points_conf)
+    for t in tens:
+        if not (t.is_cuda and t.is_contiguous() and t.dtype == torch.float32):
+            raise _lib.PnbError("pnb200: point tensors must be contiguous fp32 CUDA tensors")
+    if npnts.points_embeding.shape[-1] != 32:
+        raise NotImplementedError("pnb200: point_features_dim must be 32")
+    p.xyz, p.emb, p.color, p.dir, p.conf = (t.data_ptr() for t in tens)
+    p.N = npnts.xyz.shape[0]
+    return p
+
+
+def rw2c_host_of(npnts):
+    """Rw2c as 9 host floats, cached on the module per tensor version (one tiny D2H copy when it changes)."""
+    R = npnts.Rw2c
+    if R is None:
+        return None
+    key = (R.data_ptr(), R._version)
+    if getattr(npnts, "_pnb_rw2c_key", None) != key:
+        npnts._pnb_rw2c_host = _to_list(R)
+        npnts._pnb_rw2c_key = key
+    return npnts._pnb_rw2c_host
+
+
 class NeuralPoints(nn.Module):
     """Parameter container + querier with the reference's attribute names (neural_points.py:231-344)."""
 
@@ -150,22 +181,51 @@ class NeuralPoints(nn.Module):
         self.points_dir = mk(points_dir, getattr(o, "dir_grad", 1) > 0)
         self.points_conf = mk(points_conf, getattr(o, "conf_grad", 1) > 0)
         self.Rw2c = torch.eye(3, device=points_xyz.device) if Rw2c is None else Rw2c
-        self._Rw2c_host = _to_list(self.Rw2c) if self.Rw2c.dim() == 2 else None
         self.querier.clean_up()
 
     def reset_querier(self):
         self.querier.clean_up()
 
     def points_desc(self):
-        if self.Rw2c.dim() != 2:
-            raise NotImplementedError("pnb200: per-point Rw2c is not part of the implemented hot path")
-        p = _lib.Points()
-        p.xyz = self.xyz.data_ptr(); p.emb = self.points_embeding.data_ptr(); p.color = self.points_color.data_ptr()
-        p.dir = self.points_dir.data_ptr(); p.conf = self.points_conf.data_ptr(); p.N = self.xyz.shape[0]
-        for t in (self.xyz, self.points_embeding, self.points_color, self.points_dir, self.points_conf):
-            assert t.is_cuda and t.is_contiguous() and t.dtype == torch.float32
-        assert self.points_embeding.shape[-1] == 32
-        return p
+        return points_desc_of(self)
+
+
+def _init_state(mod):
+    """Per-module launch state (weight packs, workspaces).  Works on our module and on the reference's
+    NeuralPointsRayMarching after install_into()."""
+    opt = mod.opt
+    check_opt(opt)
+    for k, want in (("which_render_func", "radiance"), ("which_blend_func", "alpha"), ("which_tonemap_func", "off")):
+        if getattr(opt, k, want) != want:
+            raise NotImplementedError("pnb200: %s=%r unsupported (needs %r)" % (k, getattr(opt, k), want))
+    mod._mlp = MlpPack()
+    mod._sigma_rgb = None
+    mod._tc_ws = None
+    mod._err = None
+    # "bf16x3": per-pair MLPs on tcgen05 tensor cores with the error-compensated split (default);
+    # "fp32": the exact-fp32 CUDA-core kernel.
+    mod.precision = getattr(opt, "pnb_precision", "bf16x3")
+    if mod.precision not in ("bf16x3", "fp32"):
+        raise NotImplementedError("pnb200: pnb_precision=%r (bf16x3 | fp32)" % mod.precision)
+    mod.last = None
+    mod._pnb_ready = True
+
+
+def install_into(reference_cls):
+    """Patch the reference's models.neural_points_volumetric_model.NeuralPointsRayMarching class in place: its
+    instances keep their own parameters (self.neural_points.*, self.aggregator.*) and gain the fused forward
+    (seam B).  self.neural_points.querier must be pointnerf_b200's lighting_fast_querier (seam A)."""
+    for name in ("forward", "_run", "check_errors", "render_full"):
+        setattr(reference_cls, name, getattr(NeuralPointsRayMarching, name))
+    return reference_cls
+
+
+def reference_forward(self, *args, **kwargs):
+    """Function form of the patched forward (bind it as NeuralPointsRayMarching.forward of the reference)."""
+    for name in ("_run", "check_errors", "render_full"):
+        if not hasattr(type(self), name):
+            setattr(type(self), name, getattr(NeuralPointsRayMarching, name))
+    return NeuralPointsRayMarching.forward(self, *args, **kwargs)
 
 
 class NeuralPointsRayMarching(nn.Module):
@@ -173,26 +233,15 @@ class NeuralPointsRayMarching(nn.Module):
 
     def __init__(self, aggregator=None, neural_points=None, opt=None, **kwargs):
         super().__init__()
-        check_opt(opt)
-        for k, want in (("which_render_func", "radiance"), ("which_blend_func", "alpha"), ("which_tonemap_func", "off")):
-            if getattr(opt, k, want) != want:
-                raise NotImplementedError("pnb200: %s=%r unsupported (needs %r)" % (k, getattr(opt, k), want))
         self.aggregator = aggregator
         self.neural_points = neural_points
         self.opt = opt
-        self._mlp = MlpPack()
-        self._sigma_rgb = None
-        self._tc_ws = None
-        self._err = None
-        # "bf16x3": per-pair MLPs on tcgen05 tensor cores with the error-compensated split (default);
-        # "fp32": the exact-fp32 CUDA-core kernel.
-        self.precision = getattr(opt, "pnb_precision", "bf16x3")
-        if self.precision not in ("bf16x3", "fp32"):
-            raise NotImplementedError("pnb200: pnb_precision=%r (bf16x3 | fp32)" % self.precision)
-        self.last = None
+        _init_state(self)
 
     # -------------------------------------------------------------------------------------------------
     def _run(self, campos, raydir, camrotc2w, near, far, bg_color, want_counters, t=None):
+        if not getattr(self, "_pnb_ready", False):
+            _init_state(self)           # reference module patched by install_into(): state is created lazily
         lib = _lib.load()
         npnts, opt = self.neural_points, self.opt
         raydir = raydir[0].contiguous() if raydir.dim() == 3 else raydir.contiguous()
@@ -200,13 +249,13 @@ class NeuralPointsRayMarching(nn.Module):
         # cost one small D2H copy (the reference does the same with near/far/intrinsic, neural_points.py:704)
         cp, rt, bg = _to_list(campos)[:3], _to_list(camrotc2w)[:9], _to_list(bg_color)[:3]
         q = npnts.querier.run_query(npnts.xyz.detach(), raydir, cp, float(near), float(far), t=t, want_counters=want_counters)
-        o = make_cam_opts(cp, rt, Rw2c=npnts._Rw2c_host,
+        o = make_cam_opts(cp, rt, Rw2c=rw2c_host_of(npnts),
                           vsize_z=float(opt.vsize[2]), bg_color=bg, raydist_mode_unit=int(getattr(opt, "raydist_mode_unit", 0)))
         cap = q.desc.cap_samples
         if self._sigma_rgb is None or self._sigma_rgb.shape[0] < cap or self._sigma_rgb.device != raydir.device:
             self._sigma_rgb = torch.empty((cap, 4), dtype=torch.float32, device=raydir.device)
         mlp = self._mlp.get(self.aggregator)
-        pts = npnts.points_desc()
+        pts = points_desc_of(npnts)
         stream = torch.cuda.current_stream(raydir.device).cuda_stream
         if self.precision == "fp32":
             _lib.check(lib.pnb_shade_forward(_lib.C.byref(q.desc), _lib.C.byref(pts), _lib.C.byref(mlp), _lib.C.byref(o),

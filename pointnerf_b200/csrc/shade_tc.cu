@@ -86,6 +86,21 @@ __device__ __forceinline__ void w2pers_t(const pnb_shade_opts_t& o, float px, fl
     xp = xc / zc; yp = yc / zc; zp = zc;
 }
 
+// sin/cos of x*2^j, j = 0..NF-1: one accurate sincosf + angle doubling (abs error < 1e-6 after 4 doublings; the
+// fp32 kernel keeps NF independent sincosf calls).  out[2j] = sin, out[2j+1] = cos  (networks.py:175-190 layout).
+template <int NF>
+__device__ __forceinline__ void pe_doubling(float x, float* out) {
+    float s, c;
+    sincosf(x, &s, &c);
+    out[0] = s; out[1] = c;
+#pragma unroll
+    for (int j = 1; j < NF; ++j) {
+        float s2 = 2.0f * s * c, c2 = fmaf(c, c, -s * s);
+        s = s2; c = c2;
+        out[2 * j] = s; out[2 * j + 1] = c;
+    }
+}
+
 // 8 consecutive K elements (one 16-byte chunk) of row r, block kb, starting at k8 (multiple of 8) -> hi / lo buffers
 __device__ __forceinline__ void store_chunk8(tc::Smem& sm, int r, int kb, int k8, const float* v) {
     uint32_t h[4], l[4];
@@ -247,14 +262,7 @@ __global__ void __launch_bounds__(tc::NTHR, 1) k_shade_tc(ShadeTcParams p) {
                     for (int g = 0; g < 4; ++g) {      // 4 features -> 24 PE values -> 3 chunks
                         float pe[24];
 #pragma unroll
-                        for (int e = 0; e < 4; ++e)
-#pragma unroll
-                            for (int j = 0; j < 3; ++j) {
-                                float sn, cs;
-                                sincosf(f[g * 4 + e] * (float)(1 << j), &sn, &cs);
-                                pe[(e * 3 + j) * 2] = sn;
-                                pe[(e * 3 + j) * 2 + 1] = cs;
-                            }
+                        for (int e = 0; e < 4; ++e) pe_doubling<3>(f[g * 4 + e], pe + e * 6);
                         const int col = 32 + 96 * hf + 24 * g;    // multiple of 8
 #pragma unroll
                         for (int c = 0; c < 3; ++c) {
@@ -262,22 +270,31 @@ __global__ void __launch_bounds__(tc::NTHR, 1) k_shade_tc(ShadeTcParams p) {
                             store_chunk8(sm, row, cc0 >> 5, cc0 & 31, pe + 8 * c);
                         }
                     }
-                    // distance PE: index i = d*5 + j -> columns 224 + 2i ; this thread: i in [16*hf, 16*hf + 16)
+                    // distance PE: index i = d*5 + j -> columns 224 + 2i ; thread hf covers i in [16*hf, 16*hf+16):
+                    // hf 0: d = 0,1,2 (+ d=3, j=0) ; hf 1: d = 3 (j>=1), 4, 5 ; 32 values each (4 zeros pad hf 1)
+                    {
+                        float dp[30];   // 3 distances x 10 values
+                        const int dbase = hf * 3;
 #pragma unroll
-                    for (int c = 0; c < 4; ++c) {
-                        float pe[8];
+                        for (int e = 0; e < 3; ++e) pe_doubling<5>(dist[dbase + e], dp + 10 * e);
+                        float vals[32];
+                        if (hf == 0) {
 #pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            int i = 16 * hf + 4 * c + e;
-                            float sn = 0.f, cs = 0.f;
-                            if (i < 30) {
-                                int dd = i / 5, jj = i - dd * 5;
-                                sincosf(dist[dd] * (float)(1 << jj), &sn, &cs);
-                            }
-                            pe[2 * e] = sn; pe[2 * e + 1] = cs;
+                            for (int i = 0; i < 30; ++i) vals[i] = dp[i];
+                            float sn, cs;
+                            sincosf(dist[3], &sn, &cs);
+                            vals[30] = sn; vals[31] = cs;
+                        } else {
+                            // i = 16..29 -> (d=3, j=1..4), (d=4, j=0..4), (d=5, j=0..4): dp holds d=3,4,5
+#pragma unroll
+                            for (int i = 0; i < 28; ++i) vals[i] = dp[2 + i];
+                            vals[28] = 0.f; vals[29] = 0.f; vals[30] = 0.f; vals[31] = 0.f;
                         }
-                        int cc0 = 224 + 32 * hf + 8 * c;
-                        store_chunk8(sm, row, cc0 >> 5, cc0 & 31, pe);
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) {
+                            int cc0 = 224 + 32 * hf + 8 * c;
+                            store_chunk8(sm, row, cc0 >> 5, cc0 & 31, vals + 8 * c);
+                        }
                     }
                     if (hf == 1) {
                         float cr = __ldg(&p.pts.color[3 * pi]), cg = __ldg(&p.pts.color[3 * pi + 1]), cb = __ldg(&p.pts.color[3 * pi + 2]);
@@ -316,7 +333,7 @@ __global__ void __launch_bounds__(tc::NTHR, 1) k_shade_tc(ShadeTcParams p) {
 #pragma unroll
                             for (int e = 0; e < 8; ++e) {
                                 float y = __uint_as_float(v[g * 8 + e]) + sm.bias[l][c0 + g * 8 + e];
-                                x[e] = y > 0.f ? y : LEAKY * y;
+                                x[e] = fmaxf(y, LEAKY * y);
                             }
                             store_chunk8(sm, erow, c0 >> 5, g * 8, x);
                         }
@@ -346,7 +363,7 @@ __global__ void __launch_bounds__(tc::NTHR, 1) k_shade_tc(ShadeTcParams p) {
 #pragma unroll
                         for (int e = 0; e < 32; ++e) {
                             float y = __uint_as_float(v[e]) + sm.bias[3][c0 + e];
-                            y = y > 0.f ? y : LEAKY * y;
+                            y = fmaxf(y, LEAKY * y);
                             apart = fmaf(y, sm.wa[c0 + e], apart);
                             float z = y * wrow;
                             z += __shfl_xor_sync(0xffffffffu, z, 1);

@@ -95,6 +95,119 @@ __global__ void __launch_bounds__(128, 1) k_umma_selftest(const float* __restric
     if (warp == 0) tmem_dealloc<256>(tacc);
 }
 
+// Same product with the A operand in TENSOR MEMORY (tcgen05.mma "TS" form): A_hi at columns 256.., A_lo at 384..
+// (two bf16 per 32-bit column, element 2c in the low half), written with tcgen05.st; the last 16 K columns can be
+// routed through shared memory instead (ss_tail = 1) to pin mixing TS and SS MMAs on one accumulator.
+template <int LAYOUT>
+__global__ void __launch_bounds__(128, 1) k_umma_selftest_ts(const float* __restrict__ A, const float* __restrict__ W,
+                                                             float* __restrict__ D, int K, int N, int ss_tail, int* err) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    unsigned char* b_hi = smem;
+    unsigned char* b_lo = b_hi + 256 * 64;
+    unsigned char* t_hi = b_lo + 256 * 64;   // [128 x 32] tail block (only 16 columns used)
+    unsigned char* t_lo = t_hi + 8192;
+    __shared__ uint64_t bar;
+    __shared__ uint32_t tmem_base;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int nkb = (K + BK - 1) / BK;
+    const int Kts = ss_tail ? K - 16 : K;    // K columns served from TMEM
+
+    if (tid == 0) { mbar_init(&bar, 1); mbar_fence_init(); }
+    if (warp == 0) tmem_alloc<512>(&tmem_base);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tacc = tmem_base;
+    const uint32_t tlane = (uint32_t)(warp * 32) << 16;
+    // A -> TMEM: thread = row, 16 K elements (8 packed columns) per store
+    {
+        const int row = warp * 32 + lane;
+        for (int k0 = 0; k0 < 256; k0 += 16) {
+            uint32_t h[8], l[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                int k = k0 + 2 * i;
+                float a = k < Kts ? A[(size_t)row * K + k] : 0.f, b = k + 1 < Kts ? A[(size_t)row * K + k + 1] : 0.f;
+                split_bf16x2(a, b, h[i], l[i]);
+            }
+            tmem_st8(tacc + tlane + 256u + (uint32_t)(k0 >> 1), h);
+            tmem_st8(tacc + tlane + 384u + (uint32_t)(k0 >> 1), l);
+        }
+        tmem_st_wait();
+        if (ss_tail) {
+            for (int k = 0; k < 32; ++k) {
+                int kg = Kts + k;
+                float v = (k < 16 && kg < K) ? A[(size_t)row * K + kg] : 0.f;
+                __nv_bfloat16 hh, ll;
+                split_bf16(v, hh, ll);
+                uint32_t off = tile_offset_bytes<LAYOUT>(row, k);
+                *(__nv_bfloat16*)(t_hi + off) = hh;
+                *(__nv_bfloat16*)(t_lo + off) = ll;
+            }
+        }
+    }
+    tc_fence_before();
+    const uint32_t idesc = make_idesc_bf16(128, N);
+    uint32_t phase = 0;
+    for (int kb = 0; kb < nkb; ++kb) {
+        for (int i = tid; i < N * BK; i += 128) {
+            int n = i / BK, k = i - n * BK;
+            int kg = kb * BK + k;
+            float v = kg < K ? W[(size_t)n * K + kg] : 0.f;
+            __nv_bfloat16 h, l;
+            split_bf16(v, h, l);
+            uint32_t off = tile_offset_bytes<LAYOUT>(n, k);
+            *(__nv_bfloat16*)(b_hi + off) = h;
+            *(__nv_bfloat16*)(b_lo + off) = l;
+        }
+        fence_proxy_async();
+        __syncthreads();
+        if (tid == 0) {
+            tc_fence_after();
+            const int nks = (min(K - kb * BK, BK) + 15) / 16;
+            for (int ks = 0; ks < nks; ++ks) {
+                const int kcol = kb * BK + ks * 16;
+                uint32_t adv = kstep_advance_bytes<LAYOUT>(ks);
+                uint64_t dbh = make_smem_desc<LAYOUT>(smem_u32(b_hi) + adv);
+                uint64_t dbl = make_smem_desc<LAYOUT>(smem_u32(b_lo) + adv);
+                uint32_t acc_flag = (kb | ks) ? 1u : 0u;
+                if (kcol < Kts) {
+                    uint32_t ah = tacc + 256u + (uint32_t)(kcol >> 1), al = tacc + 384u + (uint32_t)(kcol >> 1);
+                    mma_ts(tacc, ah, dbh, idesc, acc_flag);
+                    mma_ts(tacc, al, dbh, idesc, 1u);
+                    mma_ts(tacc, ah, dbl, idesc, 1u);
+                } else {
+                    uint64_t dah = make_smem_desc<LAYOUT>(smem_u32(t_hi));
+                    uint64_t dal = make_smem_desc<LAYOUT>(smem_u32(t_lo));
+                    mma_ss(tacc, dah, dbh, idesc, acc_flag);
+                    mma_ss(tacc, dal, dbh, idesc, 1u);
+                    mma_ss(tacc, dah, dbl, idesc, 1u);
+                }
+            }
+            mma_commit(&bar);
+        }
+        if (!mbar_wait(&bar, phase, err, 200 + kb)) break;
+        phase ^= 1;
+        tc_fence_after();
+        __syncthreads();
+    }
+    {
+        const int row = warp * 32 + lane;
+        for (int c0 = 0; c0 < N; c0 += 32) {
+            uint32_t v[32];
+            tmem_ld32(tacc + tlane + (uint32_t)c0, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+                if (c0 + j < N) D[(size_t)row * N + c0 + j] = __uint_as_float(v[j]);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc<512>(tacc);
+}
+
 }  // namespace pnb
 
 using namespace pnb;
@@ -113,6 +226,12 @@ extern "C" int pnb_umma_selftest(const float* d_A, const float* d_W, float* d_D,
     } else if (layout == umma::LAYOUT_SW64) {
         PNB_CHECK_CUDA(cudaFuncSetAttribute(k_umma_selftest<umma::LAYOUT_SW64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         k_umma_selftest<umma::LAYOUT_SW64><<<1, 128, smem, stream>>>(d_A, d_W, d_D, K, N, d_err);
+    } else if (layout == 100 || layout == 101) {   // A operand in tensor memory (TS form); 101: last 16 K columns via SS
+        PNB_REQUIRE(K % 16 == 0 && K <= 272 && (layout == 101 || K <= 256) && (layout == 100 || K >= 32), PNB_ERR_INVALID,
+                    "pnb_umma_selftest: TS mode needs K %% 16 == 0 and K <= 256 (+16 with the SS tail)");
+        size_t smem_ts = 256 * 64 * 2 + 8192 * 2 + 1024;
+        PNB_CHECK_CUDA(cudaFuncSetAttribute(k_umma_selftest_ts<umma::LAYOUT_NONE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_ts));
+        k_umma_selftest_ts<umma::LAYOUT_NONE><<<1, 128, smem_ts, stream>>>(d_A, d_W, d_D, K, N, layout == 101 ? 1 : 0, d_err);
     } else {
         PNB_REQUIRE(false, PNB_ERR_INVALID, "pnb_umma_selftest: layout %d not supported", layout);
     }

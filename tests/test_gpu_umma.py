@@ -34,3 +34,16 @@ def test_umma_bf16x3_matches_matmul(layout, K, N):
     # the split must beat a single bf16 pass by orders of magnitude
     single = (A.bfloat16().double() @ W.bfloat16().double().t() - ref).abs().max().item()
     assert d < single / 50
+
+
+@pytest.mark.parametrize("layout,K,N", [(100, 16, 16), (100, 64, 256), (100, 256, 256), (101, 32, 256), (101, 272, 256)])
+def test_umma_a_operand_in_tensor_memory(layout, K, N):
+    """TS form (A in TMEM, written with tcgen05.st), optionally mixed with one SS k-step on the same accumulator."""
+    g = torch.Generator(device=DEV).manual_seed(K * 7 + N)
+    A = torch.randn(128, K, device=DEV, generator=g)
+    W = torch.randn(N, K, device=DEV, generator=g) / K ** 0.5
+    D, err = _run(A.contiguous(), W.contiguous(), layout)
+    assert err == 0, "pipeline timeout code %d" % err
+    ref = (A.double() @ W.double().t())
+    d = (D.double() - ref).abs().max().item()
+    assert d <= 2e-5 * max(ref.abs().max().item(), 1.0), "mode %d K=%d N=%d: max abs err %.3e" % (layout, K, N, d)

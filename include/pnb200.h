@@ -190,6 +190,19 @@ int pnb_shade_forward_tc(const pnb_query_t* q, const pnb_points_t* pts, const pn
                          int max_valid_samples, int stage_mask /* 1 pair MLPs, 2 colour branch, 3 both */,
                          int* d_err, pnb_stream_t stream);
 
+/* ---- backward (per-scene optimisation batches) ----
+ * Replaces loss.backward() through the reference's eager autograd graph
+ * (models/mvs_points_volumetric_model.py:98-118): given d(loss)/d(ray_color) [R,3] (full-R layout of
+ * pnb_composite_forward) accumulates gradients of points_embeding [N,32], points_color [N,3], points_dir [N,3],
+ * points_conf [N] (any may be NULL) and of the 9 MLP layers in the layout of pnb_mlp_t (W^T [K_pad][N] and bias; the
+ * caller zero-initialises all accumulators).  d_sigma_rgb_fwd: the forward's per-candidate (sigma, rgb) buffer.
+ * n_valid: host copy of counters[PNB_QC_N_VALID].  Activations are recomputed in fp32.  ws >= pnb_backward_bytes. */
+size_t pnb_backward_bytes(int n_valid, int cap_samples);
+int pnb_shade_backward(const pnb_query_t* q, const pnb_points_t* pts, const pnb_mlp_t* mlp, const pnb_shade_opts_t* opts,
+                       const float* d_sigma_rgb_fwd, const float* d_ray_color, int n_valid, float* d_emb, float* d_color,
+                       float* d_dir, float* d_conf, float* const* d_mlp_w, float* const* d_mlp_b, void* ws,
+                       size_t ws_bytes, pnb_stream_t stream);
+
 /* ---- diagnostics ---- */
 /* One-CTA tcgen05 self-test: D[128,N] = A[128,K] * W[N,K]^T with the BF16x3 split used by the fused kernel.
  * layout: 0 = interleaved core matrices, 4 = 64-byte swizzle.  d_err: device int, non-zero on a pipeline timeout. */

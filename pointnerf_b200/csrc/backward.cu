@@ -1,0 +1,601 @@
+// Backward of the shading + compositing path for per-scene optimisation batches (run/train_ft.py: 3600 rays/step).
+//
+// Reference: loss.backward() through autograd (/root/reference/models/mvs_points_volumetric_model.py:98-118) over
+//   ray_march        /root/reference/models/rendering/diff_ray_marching.py:508-554
+//   viewmlp          /root/reference/models/aggregators/point_aggregators.py:488-644
+//   index_select     /root/reference/models/neural_points/neural_points.py:706-717 (backward = index_add into [1,N,.])
+// Gradients produced: points_embeding [N,32], points_color [N,3], points_dir [N,3], points_conf [N] (through
+// weight*conf_coefficient, straight-through clamp :722-724), and the 18 MLP tensors (in the W^T layout of pnb_mlp_t).
+// xyz receives no gradient (xyz_grad = 0 in every shipped script).
+//
+// Training batches are small (~2e4 valid samples), so the per-layer activations are recomputed in fp32 into an HBM
+// workspace and the layer gradients are plain GEMMs (hand-written fp32 tiles; the tcgen05 backward is a later round).
+#include "common.cuh"
+
+namespace pnb {
+namespace bw {
+
+constexpr float LEAKY = 0.01f;
+
+// ------------------------------------------------------------------------------------------ generic fp32 GEMM
+// C[M x N] (+)= sum_k Aeff[m][k] * Beff[k][n],  Aeff[m][k] = A[m*sam + k*sak],  Beff[k][n] = B[k*sbk + n*sbn].
+// 64 x 64 tile, 256 threads, 4 x 4 outputs per thread.  blockIdx.z splits the reduction (ATOMIC accumulation).
+template <bool ATOMIC>
+__global__ void __launch_bounds__(256) k_gemm(const float* __restrict__ A, long sam, long sak, const float* __restrict__ B,
+                                              long sbk, long sbn, float* __restrict__ C, long ldc, int M, int N, int K,
+                                              int kchunk, const float* __restrict__ bias, int act) {
+    __shared__ float As[16][68];
+    __shared__ float Bs[16][68];
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
+    const int kbeg = blockIdx.z * kchunk, kend = min(K, kbeg + kchunk);
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    for (int k0 = kbeg; k0 < kend; k0 += 16) {
+        // load tiles: choose the thread->element map along the unit-stride direction
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            int idx = tid + e * 256;           // 0..1023
+            int am, ak;
+            if (sak == 1) { ak = idx & 15; am = idx >> 4; } else { am = idx & 63; ak = idx >> 6; }
+            int gm = m0 + am, gk = k0 + ak;
+            As[ak][am] = (gm < M && gk < kend) ? A[gm * sam + gk * sak] : 0.f;
+            int bn, bk;
+            if (sbn == 1) { bn = idx & 63; bk = idx >> 6; } else { bk = idx & 15; bn = idx >> 4; }
+            int gn = n0 + bn, gk2 = k0 + bk;
+            Bs[bk][bn] = (gn < N && gk2 < kend) ? B[gk2 * sbk + gn * sbn] : 0.f;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            float a[4], b[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) a[i] = As[k][ty * 4 + i];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) b[j] = Bs[k][tx * 4 + j];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        int gm = m0 + ty * 4 + i;
+        if (gm >= M) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            int gn = n0 + tx * 4 + j;
+            if (gn >= N) continue;
+            float v = acc[i][j];
+            if (ATOMIC) {
+                atomicAdd(&C[gm * ldc + gn], v);
+            } else {
+                if (bias) v += bias[gn];
+                if (act) v = v > 0.f ? v : LEAKY * v;
+                C[gm * ldc + gn] = v;
+            }
+        }
+    }
+}
+
+static int gemm_nn(const float* A, long lda, const float* Bt, long ldb, float* C, long ldc, int M, int N, int K,
+                   const float* bias, int act, cudaStream_t st) {
+    if (M <= 0) return PNB_OK;
+    dim3 g((N + 63) / 64, (M + 63) / 64, 1);
+    k_gemm<false><<<g, 256, 0, st>>>(A, lda, 1, Bt, ldb, 1, C, ldc, M, N, K, K, bias, act);
+    return PNB_OK;
+}
+// dX[M x Kin] = dZ[M x Nout] * Wt[Kin x Nout]^T
+static int gemm_nt(const float* dZ, long ldz, const float* Wt, long ldw, float* dX, long ldx, int M, int Kin, int Nout,
+                   cudaStream_t st) {
+    if (M <= 0) return PNB_OK;
+    dim3 g((Kin + 63) / 64, (M + 63) / 64, 1);
+    k_gemm<false><<<g, 256, 0, st>>>(dZ, ldz, 1, Wt, 1, ldw, dX, ldx, M, Kin, Nout, Nout, nullptr, 0);
+    return PNB_OK;
+}
+// dWt[Kin x Nout] += X[M x Kin]^T * dZ[M x Nout]   (reduction over M split into chunks, atomics)
+static int gemm_tn_acc(const float* X, long ldx, const float* dZ, long ldz, float* dWt, long ldw, int M, int Kin, int Nout,
+                       cudaStream_t st) {
+    if (M <= 0) return PNB_OK;
+    const int chunk = 2048;
+    dim3 g((Nout + 63) / 64, (Kin + 63) / 64, (M + chunk - 1) / chunk);
+    k_gemm<true><<<g, 256, 0, st>>>(X, 1, ldx, dZ, ldz, 1, dWt, ldw, Kin, Nout, M, chunk, nullptr, 0);
+    return PNB_OK;
+}
+
+__global__ void __launch_bounds__(256) k_lrelu_bwd(float* __restrict__ dY, const float* __restrict__ Y, long ldy, long ldd, int M, int N) {
+    long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long)M * N) return;
+    int m = (int)(i / N), n = (int)(i - (long)m * N);
+    float y = Y[m * ldy + n];
+    dY[m * ldd + n] *= (y > 0.f ? 1.0f : LEAKY);
+}
+
+// db[n] += sum_m dZ[m][n]
+__global__ void __launch_bounds__(256) k_colsum(const float* __restrict__ dZ, long ld, int M, int N, float* __restrict__ db) {
+    int n = blockIdx.x * 32 + (threadIdx.x & 31);
+    int r0 = blockIdx.y * 2048 + (threadIdx.x >> 5);
+    float s = 0.f;
+    if (n < N)
+        for (int m = r0; m < min(M, (int)(blockIdx.y + 1) * 2048); m += 8) s += dZ[(long)m * ld + n];
+    __shared__ float red[8][33];
+    red[threadIdx.x >> 5][threadIdx.x & 31] = s;
+    __syncthreads();
+    if (threadIdx.x < 32 && n < N) {
+        float t = 0.f;
+        for (int w = 0; w < 8; ++w) t += red[w][threadIdx.x];
+        atomicAdd(&db[n], t);
+    }
+}
+
+// ------------------------------------------------------------------------------------------ path-specific kernels
+struct BwdParams {
+    pnb_query_t q;
+    pnb_points_t pts;
+    pnb_shade_opts_t o;
+    int n_valid;        // S
+    // forward recompute buffers
+    float* X1;          // [P x 288]
+    float* H1;          // [P x 256]
+    float* X3;          // [P x 272]  (H2 | extras | 0)
+    float* H3;          // [P x 256]
+    float* H4;          // [P x 256]
+    float* wc;          // [P]   weight * conf_coefficient
+    float* wn;          // [P]   normalised distance weight (no conf)
+    float* sp;          // [P]   softplus(alpha_raw - 1)
+    float* sg;          // [P]   sigmoid(alpha_raw - 1)   (= d softplus)
+    int* pidx;          // [P]   point index or -1
+    float* CX;          // [S x 288]  (hbar | PE(view) | 0)
+    float* C1; float* C2; float* C3;   // [S x 128]
+    float* O3;          // [S x 4]   raw colour outputs (3 used)
+    // gradient buffers
+    float* G1;          // [P x 288]
+    float* G2;          // [P x 272]
+    float* G3;          // [P x 256]
+    float* GS1;         // [S x 288]
+    float* GS2;         // [S x 128]
+    float* GS3;         // [S x 128]
+    float* dO3;         // [S x 4]
+    float* dsig;        // [S]
+    const float4* d_sigma_rgb;   // per candidate (from k_composite_bwd)
+    const float* wa; const float* ba;
+};
+
+__device__ __forceinline__ void rot3b(const float* M, float x, float y, float z, float& ox, float& oy, float& oz) {
+    ox = x * M[0] + y * M[1] + z * M[2];
+    oy = x * M[3] + y * M[4] + z * M[5];
+    oz = x * M[6] + y * M[7] + z * M[8];
+}
+__device__ __forceinline__ void rot3bT(const float* M, float x, float y, float z, float& ox, float& oy, float& oz) {
+    ox = x * M[0] + y * M[3] + z * M[6];
+    oy = x * M[1] + y * M[4] + z * M[7];
+    oz = x * M[2] + y * M[5] + z * M[8];
+}
+__device__ __forceinline__ void w2persb(const pnb_shade_opts_t& o, float px, float py, float pz, float& xp, float& yp, float& zp) {
+    float sx = px - o.campos[0], sy = py - o.campos[1], sz = pz - o.campos[2];
+    const float* M = o.camrotc2w;
+    float xc = sx * M[0] + sy * M[3] + sz * M[6];
+    float yc = sx * M[1] + sy * M[4] + sz * M[7];
+    float zc = sx * M[2] + sy * M[5] + sz * M[8];
+    xp = xc / zc; yp = yc / zc; zp = zc;
+}
+
+// One warp per valid sample, 4 lanes per pair row (same mapping as the fp32 forward kernel): dense block1 input.
+__global__ void __launch_bounds__(256) k_bwd_build(BwdParams p) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= p.n_valid) return;
+    const pnb_query_t& q = p.q;
+    const int vi = warp, k = lane >> 2, part = lane & 3;
+    const long row = (long)vi * PNB_MAX_K + k;
+    uint32_t s = q.valid_list[vi];
+    uint32_t pk = q.samp_ray[s];
+    int r = (int)(pk >> 7), j = (int)(pk & 127u);
+    int d = q.steps[(size_t)r * q.SR + j];
+    float t = q.t[(size_t)r * q.t_ray_stride + d];
+    float vx = q.raydir[3 * r], vy = q.raydir[3 * r + 1], vz = q.raydir[3 * r + 2];
+    float lx = raypos1(q.campos[0], vx, t), ly = raypos1(q.campos[1], vy, t), lz = raypos1(q.campos[2], vz, t);
+    int pidx = k < q.K ? q.cand_pidx[(size_t)s * q.K + k] : -1;
+    const bool valid = pidx >= 0;
+    const int pi = valid ? pidx : 0;
+    float ovx, ovy, ovz;
+    rot3b(p.o.Rw2c, vx, vy, vz, ovx, ovy, ovz);
+    float* cx = p.CX + (long)vi * 288;
+    if (lane < 12) {
+        int dd = lane >> 2, jj = lane & 3;
+        float sn, cs;
+        sincosf((dd == 0 ? ovx : dd == 1 ? ovy : ovz) * (float)(1 << jj), &sn, &cs);
+        cx[256 + lane] = sn;
+        cx[268 + lane] = cs;
+    }
+    if (lane < 8) cx[280 + lane] = 0.f;
+    float px = __ldg(&p.pts.xyz[3 * pi]), py = __ldg(&p.pts.xyz[3 * pi + 1]), pz = __ldg(&p.pts.xyz[3 * pi + 2]);
+    float dist[6];
+    dist[0] = px - lx; dist[1] = py - ly; dist[2] = pz - lz;
+    float xpp, ypp, zpp, xsp, ysp, zsp;
+    w2persb(p.o, px, py, pz, xpp, ypp, zpp);
+    w2persb(p.o, lx, ly, lz, xsp, ysp, zsp);
+    dist[3] = xpp * zpp - xsp * zsp; dist[4] = ypp * zpp - ysp * zsp; dist[5] = zpp - zsp;
+    float nrm = sqrtf(dist[0] * dist[0] + dist[1] * dist[1] + dist[2] * dist[2]);
+    float w = valid ? 1.0f / fmaxf(nrm, 1e-6f) : 0.f;
+    float wsum = part == 0 ? w : 0.f;
+    for (int o = 16; o > 0; o >>= 1) wsum += __shfl_xor_sync(0xffffffffu, wsum, o);
+    w = w / fmaxf(wsum, 1e-8f);
+    float cf = __ldg(&p.pts.conf[pi]);
+    float cc = fminf(fmaxf(cf, 1e-4f), 1.0f);
+    if (part == 0) { p.wc[row] = valid ? w * cc : 0.f; p.wn[row] = valid ? w : 0.f; p.pidx[row] = pidx; }
+    float d0, d1, d2;
+    rot3b(p.o.Rw2c, dist[0], dist[1], dist[2], d0, d1, d2);
+    dist[0] = d0; dist[1] = d1; dist[2] = d2;
+    float* xr = p.X1 + row * 288;
+    float* er = p.X3 + row * 272 + 256;
+    if (valid) {
+        const float4* ep = (const float4*)&p.pts.emb[(size_t)pi * PNB_FEAT + part * 8];
+        float4 f0 = __ldg(ep), f1 = __ldg(ep + 1);
+        float f[8] = {f0.x, f0.y, f0.z, f0.w, f1.x, f1.y, f1.z, f1.w};
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            int c = part * 8 + e;
+            xr[c] = f[e];
+#pragma unroll
+            for (int jj = 0; jj < 3; ++jj) {
+                float sn, cs;
+                sincosf(f[e] * (float)(1 << jj), &sn, &cs);
+                xr[32 + (c * 3 + jj) * 2] = sn;
+                xr[32 + (c * 3 + jj) * 2 + 1] = cs;
+            }
+        }
+        for (int i = part; i < 30; i += 4) {
+            int dd = i / 5, jj = i - dd * 5;
+            float sn, cs;
+            sincosf(dist[dd] * (float)(1 << jj), &sn, &cs);
+            xr[224 + i * 2] = sn;
+            xr[224 + i * 2 + 1] = cs;
+        }
+        if (part == 0) { xr[284] = 0.f; xr[285] = 0.f; xr[286] = 0.f; xr[287] = 0.f; }
+        if (part == 1) {
+            float ddx, ddy, ddz;
+            rot3b(p.o.Rw2c, __ldg(&p.pts.dir[3 * pi]), __ldg(&p.pts.dir[3 * pi + 1]), __ldg(&p.pts.dir[3 * pi + 2]), ddx, ddy, ddz);
+            er[0] = __ldg(&p.pts.color[3 * pi]); er[1] = __ldg(&p.pts.color[3 * pi + 1]); er[2] = __ldg(&p.pts.color[3 * pi + 2]);
+            er[3] = ddx - ovx; er[4] = ddy - ovy; er[5] = ddz - ovz;
+            er[6] = ddx * ovx + ddy * ovy + ddz * ovz;
+            for (int e = 7; e < 16; ++e) er[e] = 0.f;
+        }
+    } else {
+        for (int c = part; c < 288; c += 4) xr[c] = 0.f;
+        if (part == 1)
+            for (int e = 0; e < 16; ++e) er[e] = 0.f;
+    }
+}
+
+// alpha branch + K-reduction forward (dense): one warp per sample.
+__global__ void __launch_bounds__(256) k_bwd_reduce_fwd(BwdParams p) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= p.n_valid) return;
+    const long r0 = (long)warp * PNB_MAX_K;
+    float hb[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) hb[c] = 0.f;
+    for (int k = 0; k < PNB_MAX_K; ++k) {
+        const float* h = p.H4 + (r0 + k) * 256;
+        float wck = p.wc[r0 + k];
+        float a = 0.f;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            float v = h[lane + 32 * c];
+            a = fmaf(v, __ldg(&p.wa[lane + 32 * c]), a);
+            hb[c] = fmaf(v, wck, hb[c]);
+        }
+        for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+        if (lane == 0) {
+            float x = a + __ldg(p.ba) - 1.0f;
+            p.sp[r0 + k] = x > 20.f ? x : log1pf(expf(x));
+            p.sg[r0 + k] = 1.0f / (1.0f + expf(-x));
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < 8; ++c) p.CX[(long)warp * 288 + lane + 32 * c] = hb[c];
+}
+
+// colour head: O3 raw -> d(raw) ; sigma gradient per valid sample
+__global__ void __launch_bounds__(256) k_bwd_head(BwdParams p) {
+    int vi = blockIdx.x * blockDim.x + threadIdx.x;
+    if (vi >= p.n_valid) return;
+    uint32_t s = p.q.valid_list[vi];
+    float4 g = p.d_sigma_rgb[s];
+    p.dsig[vi] = g.x;
+    float gr[3] = {g.y, g.z, g.w};
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        float sgm = 1.0f / (1.0f + expf(-p.O3[(long)vi * 4 + c]));
+        p.dO3[(long)vi * 4 + c] = gr[c] * (1.0f + 2.0f * 0.001f) * sgm * (1.0f - sgm);
+    }
+    p.dO3[(long)vi * 4 + 3] = 0.f;
+}
+
+// dH4[p][c] = wc[p] * dhbar[s][c] + dalpha_raw[p] * wa[c] ;  dwc[p] = <dhbar[s], H4[p]> + dsigma[s] * sp[p]
+// output dH4 in G3 (then lrelu' applied separately), dwc into G1[row*288] scratch column 0 (consumed by k_bwd_scatter)
+__global__ void __launch_bounds__(256) k_bwd_reduce_bwd(BwdParams p, float* __restrict__ dwc) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= p.n_valid) return;
+    const long r0 = (long)warp * PNB_MAX_K;
+    float dh[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) dh[c] = p.GS1[(long)warp * 288 + lane + 32 * c];
+    const float ds = p.dsig[warp];
+    for (int k = 0; k < PNB_MAX_K; ++k) {
+        const long row = r0 + k;
+        const float wck = p.wc[row];
+        const float dar = ds * wck * p.sg[row];     // d alpha_raw
+        const float* h = p.H4 + row * 256;
+        float dot = 0.f;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            dot = fmaf(dh[c], h[lane + 32 * c], dot);
+            p.G3[row * 256 + lane + 32 * c] = wck * dh[c] + dar * __ldg(&p.wa[lane + 32 * c]);
+        }
+        for (int o = 16; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+        if (lane == 0) dwc[row] = dot + ds * p.sp[row];
+    }
+}
+
+// alpha-branch parameter gradients: dwa[c] += sum_p dalpha_raw[p] * H4[p][c] ; dba += sum_p dalpha_raw[p]
+__global__ void __launch_bounds__(256) k_bwd_alpha_params(BwdParams p, float* __restrict__ dwa, float* __restrict__ dba) {
+    const int c = threadIdx.x;
+    const long P = (long)p.n_valid * PNB_MAX_K;
+    const long r0 = (long)blockIdx.x * 1024, r1 = min(P, r0 + 1024);
+    float acc = 0.f, accb = 0.f;
+    for (long row = r0; row < r1; ++row) {
+        float dar = p.dsig[row >> 3] * p.wc[row] * p.sg[row];
+        acc = fmaf(dar, p.H4[row * 256 + c], acc);
+        accb += dar;
+    }
+    atomicAdd(&dwa[c], acc);
+    if (c == 0) atomicAdd(dba, accb);
+}
+
+// Scatter to the points: embedding (through PE), colour, dir, conf.  4 lanes per pair row.
+__global__ void __launch_bounds__(256) k_bwd_scatter(BwdParams p, const float* __restrict__ dwc, float* __restrict__ d_emb,
+                                                     float* __restrict__ d_color, float* __restrict__ d_dir, float* __restrict__ d_conf) {
+    const long gt = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long row = gt >> 2;
+    const int part = (int)(gt & 3);
+    const long P = (long)p.n_valid * PNB_MAX_K;
+    if (row >= P) return;
+    const int pi = p.pidx[row];
+    if (pi < 0) return;
+    const float* x = p.X1 + row * 288;
+    const float* g = p.G1 + row * 288;
+    if (d_emb) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            int c = part * 8 + e;
+            float acc = g[c];
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+                float sn = x[32 + (c * 3 + j) * 2], cs = x[32 + (c * 3 + j) * 2 + 1];
+                float gs = g[32 + (c * 3 + j) * 2], gc = g[32 + (c * 3 + j) * 2 + 1];
+                acc = fmaf((float)(1 << j), cs * gs - sn * gc, acc);
+            }
+            atomicAdd(&d_emb[(size_t)pi * PNB_FEAT + c], acc);
+        }
+    }
+    if (part == 0) {
+        const float* ge = p.G2 + row * 272 + 256;
+        if (d_color) { atomicAdd(&d_color[3 * pi], ge[0]); atomicAdd(&d_color[3 * pi + 1], ge[1]); atomicAdd(&d_color[3 * pi + 2], ge[2]); }
+        if (d_dir) {
+            // extras: (dir' - view')[3], <dir', view'>  with dir' = Rw2c * dir  ->  d dir = Rw2c^T (g[3:6] + g[6] * view')
+            uint32_t s = p.q.valid_list[row >> 3];
+            int r = (int)(p.q.samp_ray[s] >> 7);
+            float ovx, ovy, ovz;
+            rot3b(p.o.Rw2c, p.q.raydir[3 * r], p.q.raydir[3 * r + 1], p.q.raydir[3 * r + 2], ovx, ovy, ovz);
+            float gx = ge[3] + ge[6] * ovx, gy = ge[4] + ge[6] * ovy, gz = ge[5] + ge[6] * ovz;
+            float ox, oy, oz;
+            rot3bT(p.o.Rw2c, gx, gy, gz, ox, oy, oz);
+            atomicAdd(&d_dir[3 * pi], ox); atomicAdd(&d_dir[3 * pi + 1], oy); atomicAdd(&d_dir[3 * pi + 2], oz);
+        }
+        if (d_conf) atomicAdd(&d_conf[pi], dwc[row] * p.wn[row]);   // straight-through clamp (gradiant_clamp :722-724)
+    }
+}
+
+// Composite backward: per ray, d ray_color -> d(sigma, rgb) of each of its candidate samples.
+struct CompBwdParams {
+    pnb_query_t q;
+    pnb_shade_opts_t o;
+    const float4* sigma_rgb;
+    const float* d_ray_color;   // [R,3]
+    float4* d_sigma_rgb;        // [cap]
+};
+
+__global__ void __launch_bounds__(128) k_composite_bwd(CompBwdParams p) {
+    int r = blockIdx.x * blockDim.x + threadIdx.x;
+    const pnb_query_t& q = p.q;
+    if (r >= q.R) return;
+    const int n = q.nsamp[r];
+    const uint32_t s0 = q.samp_off[r];
+    if (n == 0) return;
+    if (!q.ray_hit[r]) {
+        for (int j = 0; j < n; ++j) p.d_sigma_rgb[s0 + j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        return;
+    }
+    const int SR = q.SR;
+    const float dx = q.raydir[3 * r], dy = q.raydir[3 * r + 1], dz = q.raydir[3 * r + 2];
+    const float* tr = q.t + (size_t)r * q.t_ray_stride;
+    const float* M = p.o.camrotc2w;
+    auto zcam = [&](float x, float y, float z) {
+        float sx = x - p.o.campos[0], sy = y - p.o.campos[1], sz = z - p.o.campos[2];
+        return sx * M[2] + sy * M[5] + sz * M[8];
+    };
+    auto zslot = [&](int j) {
+        if (j < n) {
+            float t = tr[q.steps[(size_t)r * SR + j]];
+            return zcam(raypos1(q.campos[0], dx, t), raypos1(q.campos[1], dy, t), raypos1(q.campos[2], dz, t));
+        }
+        return zcam(0.f, 0.f, 0.f);
+    };
+    const float vz = p.o.vsize_z;
+    const float gR = p.d_ray_color[3 * r], gG = p.d_ray_color[3 * r + 1], gB = p.d_ray_color[3 * r + 2];
+    // pass 1: Full = sum_j g.rgb_j o_j T_j + g.bg T_end
+    float full = 0.f;
+    {
+        float cm = zslot(0), T = 1.0f;
+        for (int j = 0; j < n; ++j) {
+            float rd;
+            if (j + 1 < SR) { float zn = zslot(j + 1); float cmn = fmaxf(cm, zn); rd = cmn - cm; cm = cmn; } else rd = vz;
+            bool m = rd < 1e-8f;
+            if (p.o.raydist_mode_unit > 0) m = m || (rd > 2.0f * vz);
+            if (m) rd = vz;
+            if (q.samp_nvalid[s0 + j] > 0) {
+                float4 v = p.sigma_rgb[s0 + j];
+                float o1 = 1.0f - expf(-v.x * rd);
+                full += (gR * v.y + gG * v.z + gB * v.w) * o1 * T;
+                T = T * (1.0f - o1 + 1e-10f);
+            }
+        }
+        full += (gR * p.o.bg_color[0] + gG * p.o.bg_color[1] + gB * p.o.bg_color[2]) * T;
+    }
+    // pass 2
+    float cm = zslot(0), T = 1.0f, prefix = 0.f;
+    for (int j = 0; j < n; ++j) {
+        float rd;
+        if (j + 1 < SR) { float zn = zslot(j + 1); float cmn = fmaxf(cm, zn); rd = cmn - cm; cm = cmn; } else rd = vz;
+        bool m = rd < 1e-8f;
+        if (p.o.raydist_mode_unit > 0) m = m || (rd > 2.0f * vz);
+        if (m) rd = vz;
+        float4 out = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (q.samp_nvalid[s0 + j] > 0) {
+            float4 v = p.sigma_rgb[s0 + j];
+            float ex = expf(-v.x * rd);
+            float o1 = 1.0f - ex;
+            float gdot = gR * v.y + gG * v.z + gB * v.w;
+            float bw = o1 * T;
+            prefix += gdot * bw;
+            float suffix = full - prefix;                     // contributions of everything behind sample j
+            float d_o = gdot * T - suffix / (1.0f - o1 + 1e-10f);
+            out.x = d_o * rd * ex;
+            out.y = gR * bw; out.z = gG * bw; out.w = gB * bw;
+            T = T * (1.0f - o1 + 1e-10f);
+        }
+        p.d_sigma_rgb[s0 + j] = out;
+    }
+}
+
+struct Layout {
+    float *X1, *H1, *X3, *H3, *H4, *wc, *wn, *sp, *sg, *CX, *C1, *C2, *C3, *O3, *G1, *G2, *G3, *GS1, *GS2, *GS3, *dO3, *dsig, *dwc;
+    int* pidx;
+    float4* d_sigma_rgb;
+    size_t bytes;
+};
+static Layout carve(void* ws, size_t cap, int max_valid, int cap_samples) {
+    Carver c(ws, cap);
+    Layout L;
+    size_t S = (size_t)(max_valid > 0 ? max_valid : 1), P = S * PNB_MAX_K;
+    L.X1 = c.take<float>(P * 288); L.H1 = c.take<float>(P * 256); L.X3 = c.take<float>(P * 272);
+    L.H3 = c.take<float>(P * 256); L.H4 = c.take<float>(P * 256);
+    L.wc = c.take<float>(P); L.wn = c.take<float>(P); L.sp = c.take<float>(P); L.sg = c.take<float>(P); L.dwc = c.take<float>(P);
+    L.pidx = c.take<int>(P);
+    L.CX = c.take<float>(S * 288); L.C1 = c.take<float>(S * 128); L.C2 = c.take<float>(S * 128); L.C3 = c.take<float>(S * 128);
+    L.O3 = c.take<float>(S * 4);
+    L.G1 = c.take<float>(P * 288); L.G2 = c.take<float>(P * 272); L.G3 = c.take<float>(P * 256);
+    L.GS1 = c.take<float>(S * 288); L.GS2 = c.take<float>(S * 128); L.GS3 = c.take<float>(S * 128);
+    L.dO3 = c.take<float>(S * 4); L.dsig = c.take<float>(S);
+    L.d_sigma_rgb = c.take<float4>((size_t)(cap_samples > 0 ? cap_samples : 1));
+    L.bytes = align_up(c.off);
+    return L;
+}
+
+}  // namespace bw
+}  // namespace pnb
+
+using namespace pnb;
+using namespace pnb::bw;
+
+extern "C" size_t pnb_backward_bytes(int n_valid, int cap_samples) { return carve(nullptr, 0, n_valid, cap_samples).bytes; }
+
+// d_mlp_w[i] / d_mlp_b[i]: gradient accumulators in the layout of pnb_mlp_t (W^T [K_pad][N], bias [N]); the caller
+// zero-initialises them.  Point gradients are accumulated (atomicAdd) into d_emb/d_color/d_dir/d_conf (caller zeroes);
+// any of them may be NULL.  n_valid: host copy of counters[PNB_QC_N_VALID] of the query.
+extern "C" int pnb_shade_backward(const pnb_query_t* q, const pnb_points_t* pts, const pnb_mlp_t* mlp,
+                                  const pnb_shade_opts_t* opts, const float* d_sigma_rgb_fwd, const float* d_ray_color,
+                                  int n_valid, float* d_emb, float* d_color, float* d_dir, float* d_conf,
+                                  float* const* d_mlp_w, float* const* d_mlp_b, void* ws, size_t ws_bytes,
+                                  pnb_stream_t stream_) {
+    cudaStream_t st = (cudaStream_t)stream_;
+    PNB_REQUIRE(q && pts && mlp && opts && d_sigma_rgb_fwd && d_ray_color && d_mlp_w && d_mlp_b && ws, PNB_ERR_INVALID,
+                "pnb_shade_backward: null argument");
+    Layout L = carve(ws, ws_bytes, n_valid, q->cap_samples);
+    PNB_REQUIRE(L.bytes <= ws_bytes, PNB_ERR_WORKSPACE, "pnb_shade_backward: workspace %zu < required %zu", ws_bytes, L.bytes);
+    // composite backward first (also covers n_valid == 0)
+    CompBwdParams cp;
+    cp.q = *q; cp.o = *opts; cp.sigma_rgb = (const float4*)d_sigma_rgb_fwd; cp.d_ray_color = d_ray_color; cp.d_sigma_rgb = L.d_sigma_rgb;
+    k_composite_bwd<<<(q->R + 127) / 128, 128, 0, st>>>(cp);
+    if (n_valid <= 0) { PNB_CHECK_CUDA(cudaGetLastError()); return PNB_OK; }
+    const int S = n_valid, P = n_valid * PNB_MAX_K;
+    BwdParams p;
+    p.q = *q; p.pts = *pts; p.o = *opts; p.n_valid = n_valid;
+    p.X1 = L.X1; p.H1 = L.H1; p.X3 = L.X3; p.H3 = L.H3; p.H4 = L.H4; p.wc = L.wc; p.wn = L.wn; p.sp = L.sp; p.sg = L.sg; p.pidx = L.pidx;
+    p.CX = L.CX; p.C1 = L.C1; p.C2 = L.C2; p.C3 = L.C3; p.O3 = L.O3; p.G1 = L.G1; p.G2 = L.G2; p.G3 = L.G3;
+    p.GS1 = L.GS1; p.GS2 = L.GS2; p.GS3 = L.GS3; p.dO3 = L.dO3; p.dsig = L.dsig; p.d_sigma_rgb = L.d_sigma_rgb;
+    p.wa = mlp->w[4]; p.ba = mlp->b[4];
+    const int wb = (S * 32 + 255) / 256;   // one warp per sample
+    // ---------------- forward recompute (fp32) ----------------
+    k_bwd_build<<<wb, 256, 0, st>>>(p);
+    gemm_nn(L.X1, 288, mlp->w[0], 256, L.H1, 256, P, 256, 288, mlp->b[0], 1, st);
+    gemm_nn(L.H1, 256, mlp->w[1], 256, L.X3, 272, P, 256, 256, mlp->b[1], 1, st);   // H2 into X3[:, :256]
+    gemm_nn(L.X3, 272, mlp->w[2], 256, L.H3, 256, P, 256, 272, mlp->b[2], 1, st);
+    gemm_nn(L.H3, 256, mlp->w[3], 256, L.H4, 256, P, 256, 256, mlp->b[3], 1, st);
+    k_bwd_reduce_fwd<<<wb, 256, 0, st>>>(p);
+    gemm_nn(L.CX, 288, mlp->w[5], 128, L.C1, 128, S, 128, 288, mlp->b[5], 1, st);
+    gemm_nn(L.C1, 128, mlp->w[6], 128, L.C2, 128, S, 128, 128, mlp->b[6], 1, st);
+    gemm_nn(L.C2, 128, mlp->w[7], 128, L.C3, 128, S, 128, 128, mlp->b[7], 1, st);
+    gemm_nn(L.C3, 128, mlp->w[8], 3, L.O3, 4, S, 3, 128, mlp->b[8], 0, st);
+    // ---------------- backward ----------------
+    k_bwd_head<<<(S + 255) / 256, 256, 0, st>>>(p);
+    // colour branch
+    gemm_tn_acc(L.C3, 128, L.dO3, 4, d_mlp_w[8], 3, S, 128, 3, st);
+    k_colsum<<<dim3(1, (S + 2047) / 2048), 256, 0, st>>>(L.dO3, 4, S, 3, d_mlp_b[8]);
+    gemm_nt(L.dO3, 4, mlp->w[8], 3, L.GS3, 128, S, 128, 3, st);                      // dC3
+    k_lrelu_bwd<<<(int)(((long)S * 128 + 255) / 256), 256, 0, st>>>(L.GS3, L.C3, 128, 128, S, 128);
+    gemm_tn_acc(L.C2, 128, L.GS3, 128, d_mlp_w[7], 128, S, 128, 128, st);
+    k_colsum<<<dim3(4, (S + 2047) / 2048), 256, 0, st>>>(L.GS3, 128, S, 128, d_mlp_b[7]);
+    gemm_nt(L.GS3, 128, mlp->w[7], 128, L.GS2, 128, S, 128, 128, st);                // dC2
+    k_lrelu_bwd<<<(int)(((long)S * 128 + 255) / 256), 256, 0, st>>>(L.GS2, L.C2, 128, 128, S, 128);
+    gemm_tn_acc(L.C1, 128, L.GS2, 128, d_mlp_w[6], 128, S, 128, 128, st);
+    k_colsum<<<dim3(4, (S + 2047) / 2048), 256, 0, st>>>(L.GS2, 128, S, 128, d_mlp_b[6]);
+    gemm_nt(L.GS2, 128, mlp->w[6], 128, L.GS3, 128, S, 128, 128, st);                // dC1 (reuse GS3)
+    k_lrelu_bwd<<<(int)(((long)S * 128 + 255) / 256), 256, 0, st>>>(L.GS3, L.C1, 128, 128, S, 128);
+    gemm_tn_acc(L.CX, 288, L.GS3, 128, d_mlp_w[5], 128, S, 288, 128, st);
+    k_colsum<<<dim3(4, (S + 2047) / 2048), 256, 0, st>>>(L.GS3, 128, S, 128, d_mlp_b[5]);
+    gemm_nt(L.GS3, 128, mlp->w[5], 128, L.GS1, 288, S, 288, 128, st);                // d(hbar | view PE)
+    // K-reduction + alpha branch
+    k_bwd_reduce_bwd<<<wb, 256, 0, st>>>(p, L.dwc);
+    k_bwd_alpha_params<<<(P + 1023) / 1024, 256, 0, st>>>(p, d_mlp_w[4], d_mlp_b[4]);
+    // block3.2
+    k_lrelu_bwd<<<(int)(((long)P * 256 + 255) / 256), 256, 0, st>>>(L.G3, L.H4, 256, 256, P, 256);
+    gemm_tn_acc(L.H3, 256, L.G3, 256, d_mlp_w[3], 256, P, 256, 256, st);
+    k_colsum<<<dim3(8, (P + 2047) / 2048), 256, 0, st>>>(L.G3, 256, P, 256, d_mlp_b[3]);
+    gemm_nt(L.G3, 256, mlp->w[3], 256, L.G1, 288, P, 256, 256, st);                  // dH3 in G1[:, :256] (ld 288)
+    k_lrelu_bwd<<<(int)(((long)P * 256 + 255) / 256), 256, 0, st>>>(L.G1, L.H3, 256, 288, P, 256);
+    // block3.0
+    gemm_tn_acc(L.X3, 272, L.G1, 288, d_mlp_w[2], 256, P, 272, 256, st);
+    k_colsum<<<dim3(8, (P + 2047) / 2048), 256, 0, st>>>(L.G1, 288, P, 256, d_mlp_b[2]);
+    gemm_nt(L.G1, 288, mlp->w[2], 256, L.G2, 272, P, 272, 256, st);                  // dX3 = (dH2 | d extras)
+    k_lrelu_bwd<<<(int)(((long)P * 256 + 255) / 256), 256, 0, st>>>(L.G2, L.X3, 272, 272, P, 256);
+    // block1.2
+    gemm_tn_acc(L.H1, 256, L.G2, 272, d_mlp_w[1], 256, P, 256, 256, st);
+    k_colsum<<<dim3(8, (P + 2047) / 2048), 256, 0, st>>>(L.G2, 272, P, 256, d_mlp_b[1]);
+    gemm_nt(L.G2, 272, mlp->w[1], 256, L.G3, 256, P, 256, 256, st);                  // dH1 in G3
+    k_lrelu_bwd<<<(int)(((long)P * 256 + 255) / 256), 256, 0, st>>>(L.G3, L.H1, 256, 256, P, 256);
+    // block1.0
+    gemm_tn_acc(L.X1, 288, L.G3, 256, d_mlp_w[0], 256, P, 288, 256, st);
+    k_colsum<<<dim3(8, (P + 2047) / 2048), 256, 0, st>>>(L.G3, 256, P, 256, d_mlp_b[0]);
+    gemm_nt(L.G3, 256, mlp->w[0], 256, L.G1, 288, P, 288, 256, st);                  // dX1
+    // scatter to the points
+    k_bwd_scatter<<<(int)(((long)P * 4 + 255) / 256), 256, 0, st>>>(p, L.dwc, d_emb, d_color, d_dir, d_conf);
+    PNB_CHECK_CUDA(cudaGetLastError());
+    return PNB_OK;
+}

@@ -53,7 +53,8 @@ QC = dict(n_cand=0, n_valid=1, n_pairs=2, R1=3, R2=4, overflow=5)
 # every symbol include/pnb200.h declares (tests check that the .so exports all of them)
 SYMBOLS = ["pnb_version", "pnb_last_error", "pnb_struct_size", "pnb_grid_bytes", "pnb_grid_build", "pnb_query_bytes", "pnb_query",
            "pnb_query_export", "pnb_shade_bytes", "pnb_shade_forward", "pnb_composite_forward", "pnb_umma_selftest",
-           "pnb_mlp_pack_bytes", "pnb_mlp_pack", "pnb_shade_tc_bytes", "pnb_shade_forward_tc"]
+           "pnb_mlp_pack_bytes", "pnb_mlp_pack", "pnb_shade_tc_bytes", "pnb_shade_forward_tc",
+           "pnb_backward_bytes", "pnb_shade_backward"]
 
 _lib = None
 
@@ -108,6 +109,12 @@ def load():
     lib.pnb_shade_forward_tc.restype = C.c_int
     lib.pnb_shade_forward_tc.argtypes = [C.POINTER(Query), C.POINTER(Points), C.POINTER(Mlp), C.c_void_p, C.POINTER(ShadeOpts),
                                          C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    lib.pnb_backward_bytes.restype = C.c_size_t
+    lib.pnb_backward_bytes.argtypes = [C.c_int, C.c_int]
+    lib.pnb_shade_backward.restype = C.c_int
+    lib.pnb_shade_backward.argtypes = [C.POINTER(Query), C.POINTER(Points), C.POINTER(Mlp), C.POINTER(ShadeOpts), C.c_void_p,
+                                       C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                       C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_void_p, C.c_size_t, C.c_void_p]
     lib.pnb_umma_selftest.restype = C.c_int
     lib.pnb_umma_selftest.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
     _lib = lib

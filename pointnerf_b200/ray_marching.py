@@ -190,6 +190,56 @@ class NeuralPoints(nn.Module):
         return points_desc_of(self)
 
 
+class _RenderFn(torch.autograd.Function):
+    """Differentiable face of the fused path: ray_color[R,3] = f(points_embeding, points_color, points_dir,
+    points_conf, 18 MLP tensors).  Backward = pnb_shade_backward (recompute in fp32, hand-written GEMM tiles)."""
+
+    @staticmethod
+    def forward(ctx, mod, run_args, emb, color, pdir, conf, *mlp_params):
+        q, ray_color, opacity, bg_T, ray_mask = mod._run(*run_args)
+        ctx.mod = mod
+        ctx.q = q
+        ctx.o = mod._last_opts
+        ctx.n_valid = q.counters["n_valid"]
+        ctx.sigma_rgb = mod._sigma_rgb          # forward (sigma, rgb) per candidate; valid until the next _run
+        ctx.needs = [t.requires_grad for t in (emb, color, pdir, conf)]
+        ctx.mlp_shapes = [tuple(t.shape) for t in mlp_params]
+        ctx.mark_non_differentiable(opacity, bg_T, ray_mask)
+        return ray_color, opacity, bg_T, ray_mask
+
+    @staticmethod
+    def backward(ctx, g_color, g_op, g_bg, g_mask):
+        lib = _lib.load()
+        mod, q = ctx.mod, ctx.q
+        npnts = mod.neural_points
+        dev = g_color.device
+        g_color = g_color.contiguous().float()
+        N = npnts.xyz.shape[0]
+        outs = []
+        for need, shape in zip(ctx.needs, ((1, N, 32), (1, N, 3), (1, N, 3), (1, N, 1))):
+            outs.append(torch.zeros(shape, dtype=torch.float32, device=dev) if need else None)
+        dwt = [torch.zeros_like(w) for w in mod._mlp.wt]
+        dbs = [torch.zeros_like(b) for b in mod._mlp.bias]
+        nb = lib.pnb_backward_bytes(max(ctx.n_valid, 1), q.desc.cap_samples)
+        if getattr(mod, "_bwd_ws", None) is None or mod._bwd_ws.numel() < nb:
+            mod._bwd_ws = torch.empty(nb, dtype=torch.uint8, device=dev)
+        wp = (_lib.C.c_void_p * 9)(*[t.data_ptr() for t in dwt])
+        bp = (_lib.C.c_void_p * 9)(*[t.data_ptr() for t in dbs])
+        pts = points_desc_of(npnts)
+        mlp = mod._mlp.get(mod.aggregator)
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        ptr = lambda t: t.data_ptr() if t is not None else None
+        _lib.check(lib.pnb_shade_backward(_lib.C.byref(q.desc), _lib.C.byref(pts), _lib.C.byref(mlp), _lib.C.byref(ctx.o),
+                                          ctx.sigma_rgb.data_ptr(), g_color.data_ptr(), int(ctx.n_valid), ptr(outs[0]),
+                                          ptr(outs[1]), ptr(outs[2]), ptr(outs[3]), wp, bp, mod._bwd_ws.data_ptr(),
+                                          mod._bwd_ws.numel(), stream), "pnb_shade_backward")
+        grads = []
+        for i, shp in enumerate(MLP_SHAPES):                 # W^T [K_pad, N] -> nn.Linear weight [N, K]
+            grads.append(dwt[i][:shp[1]].t().contiguous().view(ctx.mlp_shapes[2 * i]))
+            grads.append(dbs[i].view(ctx.mlp_shapes[2 * i + 1]))
+        return (None, None, outs[0], outs[1], outs[2], outs[3], *grads)
+
+
 def _init_state(mod):
     """Per-module launch state (weight packs, workspaces).  Works on our module and on the reference's
     NeuralPointsRayMarching after install_into()."""
@@ -283,6 +333,7 @@ class NeuralPointsRayMarching(nn.Module):
                                              ray_color.data_ptr(), opacity.data_ptr(), bg_T.data_ptr(),
                                              ray_mask.data_ptr(), stream), "pnb_composite_forward")
         self.last = q
+        self._last_opts = o
         return q, ray_color, opacity, bg_T, ray_mask
 
     def check_errors(self):
@@ -307,8 +358,22 @@ class NeuralPointsRayMarching(nn.Module):
             raise NotImplementedError("pnb200: bg_ray input is not part of the implemented hot path")
         near_f = float(torch.min(near)) if isinstance(near, torch.Tensor) else float(near)
         far_f = float(torch.max(far)) if isinstance(far, torch.Tensor) else float(far)
-        q, ray_color, opacity, bg_T, ray_mask = self._run(campos, raydir, camrotc2w, near_f, far_f,
-                                                          bg_color if bg_color is not None else torch.zeros(3), True)
+        bg = bg_color if bg_color is not None else torch.zeros(3)
+        run_args = (campos, raydir, camrotc2w, near_f, far_f, bg, True)
+        npnts, agg = self.neural_points, self.aggregator
+        train = torch.is_grad_enabled() and any(
+            t is not None and t.requires_grad for t in
+            [npnts.points_embeding, npnts.points_color, npnts.points_dir, npnts.points_conf] + list(agg.parameters()))
+        if train:
+            sd = dict(agg.named_parameters())
+            mlp_params = []
+            for k in MLP_KEYS:
+                mlp_params += [sd[k + ".weight"], sd[k + ".bias"]]
+            ray_color, opacity, bg_T, ray_mask = _RenderFn.apply(self, run_args, npnts.points_embeding, npnts.points_color,
+                                                                 npnts.points_dir, npnts.points_conf, *mlp_params)
+            q = self.last
+        else:
+            q, ray_color, opacity, bg_T, ray_mask = self._run(*run_args)
         self.check_errors()
         # compact to the R' rays the reference returns (one host sync already paid for the counters)
         inds = torch.nonzero(ray_mask)[:, 0]
@@ -319,4 +384,25 @@ class NeuralPointsRayMarching(nn.Module):
         # queried_shading: 1 where no sample of the ray is valid (:290) -- rays in R' always have one
         out["queried_shading"] = torch.zeros((1, inds.shape[0], 3), dtype=torch.float32, device=ray_color.device)
         out["ray_mask"] = ray_mask[None]
+        opt = self.opt
+        want_aux = (getattr(opt, "sparse_loss_weight", 0) > 0) or ("conf_coefficient" in getattr(opt, "zero_one_loss_items", [])) \
+            or getattr(opt, "prob", 0) != 0                       # point_aggregators.py:812-813
+        if want_aux and inds.shape[0] > 0:
+            # weight / conf_coefficient / blend_weight of the reference dict (:325-329): cheap torch ops on the dense export
+            cam = make_cam_opts(_to_list(campos)[:3], _to_list(camrotc2w)[:9])
+            ex = q.export(cam, want_pers=False, want_dirs=False)
+            pidx = ex["sample_pidx"]
+            mask = pidx >= 0
+            idx = pidx.clamp(min=0).long()
+            d = npnts.xyz.detach()[idx] - ex["sample_loc_w"][:, :, None, :]
+            wgt = mask * (1.0 / torch.clamp(torch.norm(d, dim=-1), min=1e-6))
+            wgt = wgt / torch.clamp(torch.sum(wgt, dim=-1, keepdim=True), min=1e-8)
+            c0 = npnts.points_conf[0, :, 0][idx]
+            conf_coefficient = c0 - (c0 - torch.clamp(c0, min=0.0001, max=1)).detach()
+            op = out["coarse_point_opacity"][0].detach()
+            acc = torch.cumprod(1. - op + 1e-10, dim=-1)
+            acc_T = torch.cat([torch.ones_like(acc[:, :1]), acc[:, :-1]], dim=-1)
+            out["weight"] = wgt[None].detach()
+            out["blend_weight"] = (op * acc_T)[None, ..., None]
+            out["conf_coefficient"] = conf_coefficient[None]
         return out

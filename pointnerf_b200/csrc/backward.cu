@@ -439,8 +439,9 @@ __global__ void __launch_bounds__(128) k_composite_bwd(CompBwdParams p) {
     };
     const float vz = p.o.vsize_z;
     const float gR = p.d_ray_color[3 * r], gG = p.d_ray_color[3 * r + 1], gB = p.d_ray_color[3 * r + 2];
-    // pass 1: Full = sum_j g.rgb_j o_j T_j + g.bg T_end
-    float full = 0.f;
+    // pass 1 (front to back): opacity, ray distance and transmittance of every candidate (local arrays, SR <= 128)
+    float o_[PNB_MAX_SR], rd_[PNB_MAX_SR], T_[PNB_MAX_SR];
+    float Tend;
     {
         float cm = zslot(0), T = 1.0f;
         for (int j = 0; j < n; ++j) {
@@ -449,36 +450,26 @@ __global__ void __launch_bounds__(128) k_composite_bwd(CompBwdParams p) {
             bool m = rd < 1e-8f;
             if (p.o.raydist_mode_unit > 0) m = m || (rd > 2.0f * vz);
             if (m) rd = vz;
-            if (q.samp_nvalid[s0 + j] > 0) {
-                float4 v = p.sigma_rgb[s0 + j];
-                float o1 = 1.0f - expf(-v.x * rd);
-                full += (gR * v.y + gG * v.z + gB * v.w) * o1 * T;
-                T = T * (1.0f - o1 + 1e-10f);
-            }
+            float o1 = 0.f;
+            if (q.samp_nvalid[s0 + j] > 0) o1 = 1.0f - expf(-p.sigma_rgb[s0 + j].x * rd);
+            o_[j] = o1; rd_[j] = rd; T_[j] = T;
+            T = T * (1.0f - o1 + 1e-10f);
         }
-        full += (gR * p.o.bg_color[0] + gG * p.o.bg_color[1] + gB * p.o.bg_color[2]) * T;
+        Tend = T;
     }
-    // pass 2
-    float cm = zslot(0), T = 1.0f, prefix = 0.f;
-    for (int j = 0; j < n; ++j) {
-        float rd;
-        if (j + 1 < SR) { float zn = zslot(j + 1); float cmn = fmaxf(cm, zn); rd = cmn - cm; cm = cmn; } else rd = vz;
-        bool m = rd < 1e-8f;
-        if (p.o.raydist_mode_unit > 0) m = m || (rd > 2.0f * vz);
-        if (m) rd = vz;
+    // pass 2 (back to front): suffix_j = g.bg T_end + sum_{i>j} g.rgb_i o_i T_i   (no cancellation)
+    float suffix = (gR * p.o.bg_color[0] + gG * p.o.bg_color[1] + gB * p.o.bg_color[2]) * Tend;
+    for (int j = n - 1; j >= 0; --j) {
         float4 out = make_float4(0.f, 0.f, 0.f, 0.f);
         if (q.samp_nvalid[s0 + j] > 0) {
             float4 v = p.sigma_rgb[s0 + j];
-            float ex = expf(-v.x * rd);
-            float o1 = 1.0f - ex;
+            float o1 = o_[j], T = T_[j];
             float gdot = gR * v.y + gG * v.z + gB * v.w;
             float bw = o1 * T;
-            prefix += gdot * bw;
-            float suffix = full - prefix;                     // contributions of everything behind sample j
             float d_o = gdot * T - suffix / (1.0f - o1 + 1e-10f);
-            out.x = d_o * rd * ex;
+            out.x = d_o * rd_[j] * (1.0f - o1);              // d o / d sigma = rd * exp(-sigma rd)
             out.y = gR * bw; out.z = gG * bw; out.w = gB * bw;
-            T = T * (1.0f - o1 + 1e-10f);
+            suffix += gdot * bw;
         }
         p.d_sigma_rgb[s0 + j] = out;
     }

@@ -400,21 +400,335 @@ __global__ void __launch_bounds__(tc::NTHR, 1) k_shade_tc(ShadeTcParams p) {
     if (warp == 9) tmem_dealloc<256>(tacc);
 }
 
+// =====================================================================================================================
+// v3: layers 2-4 read their A operand from TENSOR MEMORY (tcgen05.mma TS form) so the shared-memory operand buffer
+// is only needed by layer 1 -> dedicated builder warps construct the NEXT tile's layer-1 operand while the tensor
+// core runs layers 2-4 of the current tile.  TMEM: accumulator cols 0..255, A_hi 256..383, A_lo 384..511 (two bf16
+// per 32-bit column).  Warp roles (448 threads): 0-7 epilogue (TMEM -> bias/LeakyReLU/split -> TMEM), 8-11 builders,
+// 12 loader, 13 issuer.  The 7 block3 extras go through a small [128 x 16] shared-memory operand (one SS k-step).
+namespace tc3 {
+constexpr int NEPI = 256, NBUILD = 128, NTHR = 448;
+constexpr int NSTAGE = 4;
+constexpr int XE = 128 * 32;            // bytes of one [128 x 16] bf16 extras operand (SBO = 256)
+struct Smem {
+    unsigned char a_hi[tc::NKB_MAX * tc::ABLK];
+    unsigned char a_lo[tc::NKB_MAX * tc::ABLK];
+    unsigned char b[NSTAGE][tc::IMG];
+    unsigned char xe_hi[2][XE];
+    unsigned char xe_lo[2][XE];
+    float wc[2][tc::TM];
+    float alpha_part[2][tc::TM];
+    uint64_t bar_full[NSTAGE], bar_empty[NSTAGE], bar_a1_ready, bar_a1_free, bar_acc_full, bar_at_ready;
+    uint32_t tmem_base;
+};
+__device__ __forceinline__ uint32_t xe_offset(int r, int k) { return (uint32_t)((r >> 3) * 256 + (k >> 3) * 128 + (r & 7) * 16 + (k & 7) * 2); }
+__device__ __forceinline__ uint64_t xe_desc(uint32_t addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((addr >> 4) & 0x3fff);
+    d |= (uint64_t)(128 >> 4) << 16;    // LBO: next 8-column chunk
+    d |= (uint64_t)(256 >> 4) << 32;    // SBO: next 8-row group
+    d |= (uint64_t)1 << 46;
+    return d;                           // layout type 0 (interleaved)
+}
+}  // namespace tc3
+
+__device__ __forceinline__ void store_chunk8_a1(tc3::Smem& sm, int r, int kb, int k8, const float* v) {
+    uint32_t h[4], l[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) split_bf16x2(v[2 * i], v[2 * i + 1], h[i], l[i]);
+    uint32_t off = (uint32_t)kb * tc::ABLK + tile_offset_bytes<tc::LAYOUT>(r, k8);
+    *reinterpret_cast<uint4*>(sm.a_hi + off) = make_uint4(h[0], h[1], h[2], h[3]);
+    *reinterpret_cast<uint4*>(sm.a_lo + off) = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
+__global__ void __launch_bounds__(tc3::NTHR, 1) k_shade_tc3(ShadeTcParams p) {
+    using namespace tc;
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    tc3::Smem& sm = *reinterpret_cast<tc3::Smem*>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const pnb_query_t& q = p.q;
+    const int n_valid = min(q.counters[PNB_QC_N_VALID], p.hbar_cap);
+    const int n_tiles = (n_valid + TSAMP - 1) / TSAMP;
+    const int my_tiles = n_tiles > (int)blockIdx.x ? (n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+
+    if (tid == 0) {
+        for (int s = 0; s < tc3::NSTAGE; ++s) { mbar_init(&sm.bar_full[s], 1); mbar_init(&sm.bar_empty[s], 1); }
+        mbar_init(&sm.bar_a1_ready, tc3::NBUILD);
+        mbar_init(&sm.bar_a1_free, 1);
+        mbar_init(&sm.bar_acc_full, 1);
+        mbar_init(&sm.bar_at_ready, tc3::NEPI);
+        mbar_fence_init();
+        if (blockIdx.x == 0 && q.counters[PNB_QC_N_VALID] > p.hbar_cap) atomicExch(p.err, 9);
+    }
+    if (warp == 13) tmem_alloc<512>(&sm.tmem_base);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tacc = sm.tmem_base;
+    const uint32_t t_ahi = tacc + 256u, t_alo = tacc + 384u;
+
+    if (warp == 12) {
+        // ============================================================ loader
+        if (lane == 0) {
+            const uint32_t total = (uint32_t)my_tiles * IMGS_PER_TILE;
+            for (uint32_t n = 0; n < total; ++n) {
+                const uint32_t s = n % tc3::NSTAGE, ph = (n / tc3::NSTAGE) & 1u;
+                if (!mbar_wait(&sm.bar_empty[s], ph ^ 1u, p.err, 11)) break;
+                mbar_arrive_expect_tx(&sm.bar_full[s], IMG);
+                bulk_g2s(sm.b[s], p.wimg + (size_t)(n % IMGS_PER_TILE) * IMG, IMG, &sm.bar_full[s]);
+            }
+        }
+    } else if (warp == 13) {
+        // ============================================================ MMA issuer
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc_bf16(128, 256);
+            uint32_t n = 0, n_at = 0;
+            bool ok = true;
+            for (int t = 0; t < my_tiles && ok; ++t) {
+                for (int l = 0; l < 4 && ok; ++l) {
+                    if (l == 0) {
+                        if (!mbar_wait(&sm.bar_a1_ready, (uint32_t)t & 1u, p.err, 12)) { ok = false; break; }
+                        if (t > 0) { if (!mbar_wait(&sm.bar_at_ready, n_at & 1u, p.err, 13)) { ok = false; break; } ++n_at; }
+                    } else {
+                        if (!mbar_wait(&sm.bar_at_ready, n_at & 1u, p.err, 14)) { ok = false; break; }
+                        ++n_at;
+                    }
+                    tc_fence_after();
+                    const int nkb = nkb_of(l);
+                    for (int kb = 0; kb < nkb && ok; ++kb) {
+                        const int nks = (l == 2 && kb == 8) ? 1 : 2;
+                        const bool ss = (l == 0) || (kb == 8);           // layer 1 and the extras block read smem
+                        for (int part = 0; part < 2 && ok; ++part) {      // 0: W_hi image, 1: W_lo image
+                            const uint32_t s = n % tc3::NSTAGE, ph = (n / tc3::NSTAGE) & 1u;
+                            if (!mbar_wait(&sm.bar_full[s], ph, p.err, 15)) { ok = false; break; }
+                            tc_fence_after();
+                            for (int ks = 0; ks < nks; ++ks) {
+                                const uint32_t adv = kstep_advance_bytes<LAYOUT>(ks);
+                                const uint64_t db = make_smem_desc<LAYOUT>(smem_u32(sm.b[s]) + adv);
+                                const uint32_t accf = (kb | ks | part) ? 1u : 0u;
+                                if (l == 0) {
+                                    mma_ss(tacc, make_smem_desc<LAYOUT>(smem_u32(sm.a_hi + kb * ABLK) + adv), db, idesc, accf);
+                                    if (part == 0) mma_ss(tacc, make_smem_desc<LAYOUT>(smem_u32(sm.a_lo + kb * ABLK) + adv), db, idesc, 1u);
+                                } else if (ss) {
+                                    mma_ss(tacc, tc3::xe_desc(smem_u32(sm.xe_hi[t & 1])), db, idesc, 1u);
+                                    if (part == 0) mma_ss(tacc, tc3::xe_desc(smem_u32(sm.xe_lo[t & 1])), db, idesc, 1u);
+                                } else {
+                                    const uint32_t col = (uint32_t)(kb * 16 + ks * 8);
+                                    mma_ts(tacc, t_ahi + col, db, idesc, accf);
+                                    if (part == 0) mma_ts(tacc, t_alo + col, db, idesc, 1u);
+                                }
+                            }
+                            mma_commit(&sm.bar_empty[s]);
+                            ++n;
+                        }
+                    }
+                    mma_commit(&sm.bar_acc_full);
+                    if (l == 0) mma_commit(&sm.bar_a1_free);
+                }
+            }
+        }
+    } else if (warp >= 8) {
+        // ============================================================ builders: one thread per pair row
+        const int row = (warp - 8) * 32 + lane;
+        const int si = row >> 3, k = row & 7;
+        bool ok = true;
+        for (int t = 0; t < my_tiles && ok; ++t) {
+            const int tile = (int)blockIdx.x + t * (int)gridDim.x;
+            if (t > 0 && !mbar_wait(&sm.bar_a1_free, (uint32_t)(t - 1) & 1u, p.err, 16)) { ok = false; break; }
+            const int vi = tile * TSAMP + si;
+            int pidx = -1;
+            float lx = 0.f, ly = 0.f, lz = 0.f, vx = 0.f, vy = 0.f, vz = 0.f;
+            if (vi < n_valid) {
+                uint32_t s = q.valid_list[vi];
+                uint32_t pk = q.samp_ray[s];
+                int r = (int)(pk >> 7), j = (int)(pk & 127u);
+                int d = q.steps[(size_t)r * q.SR + j];
+                float tt = q.t[(size_t)r * q.t_ray_stride + d];
+                vx = q.raydir[3 * r]; vy = q.raydir[3 * r + 1]; vz = q.raydir[3 * r + 2];
+                lx = raypos1(q.campos[0], vx, tt); ly = raypos1(q.campos[1], vy, tt); lz = raypos1(q.campos[2], vz, tt);
+                if (k < q.K) pidx = q.cand_pidx[(size_t)s * q.K + k];
+            }
+            const bool valid = pidx >= 0;
+            const int pi = valid ? pidx : 0;
+            float ovx, ovy, ovz;
+            rot3t(p.o.Rw2c, vx, vy, vz, ovx, ovy, ovz);
+            float px = __ldg(&p.pts.xyz[3 * pi]), py = __ldg(&p.pts.xyz[3 * pi + 1]), pz = __ldg(&p.pts.xyz[3 * pi + 2]);
+            float dist[6];
+            dist[0] = px - lx; dist[1] = py - ly; dist[2] = pz - lz;
+            float xpp, ypp, zpp, xsp, ysp, zsp;
+            w2pers_t(p.o, px, py, pz, xpp, ypp, zpp);
+            w2pers_t(p.o, lx, ly, lz, xsp, ysp, zsp);
+            dist[3] = xpp * zpp - xsp * zsp; dist[4] = ypp * zpp - ysp * zsp; dist[5] = zpp - zsp;
+            float nrm = sqrtf(dist[0] * dist[0] + dist[1] * dist[1] + dist[2] * dist[2]);
+            float w = valid ? 1.0f / fmaxf(nrm, 1e-6f) : 0.f;
+            float wsum = w;                        // 8 consecutive lanes = the 8 rows of one sample
+            wsum += __shfl_xor_sync(0xffffffffu, wsum, 1);
+            wsum += __shfl_xor_sync(0xffffffffu, wsum, 2);
+            wsum += __shfl_xor_sync(0xffffffffu, wsum, 4);
+            w = w / fmaxf(wsum, 1e-8f);
+            float cf = __ldg(&p.pts.conf[pi]);
+            sm.wc[t & 1][row] = valid ? w * fminf(fmaxf(cf, 1e-4f), 1.0f) : 0.f;
+            {
+                float d0, d1, d2;
+                rot3t(p.o.Rw2c, dist[0], dist[1], dist[2], d0, d1, d2);
+                dist[0] = d0; dist[1] = d1; dist[2] = d2;
+            }
+            float ex[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            if (valid) {
+                const float4* ep = (const float4*)&p.pts.emb[(size_t)pi * PNB_FEAT];
+#pragma unroll
+                for (int g = 0; g < 8; ++g) {          // 4 features per step
+                    float4 fv = __ldg(ep + g);
+                    float f[4] = {fv.x, fv.y, fv.z, fv.w};
+                    float pe[24];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) pe_doubling<3>(f[e], pe + e * 6);
+                    // (the raw features themselves are stored 8 per chunk in the loop below)
+                    const int col = 32 + 24 * g;
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) store_chunk8_a1(sm, row, (col + 8 * c) >> 5, (col + 8 * c) & 31, pe + 8 * c);
+                }
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {          // raw features, 8 per chunk (re-read: L1 hit)
+                    float4 a = __ldg(ep + 2 * g), b = __ldg(ep + 2 * g + 1);
+                    float f8[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+                    store_chunk8_a1(sm, row, 0, 8 * g, f8);
+                }
+                float dp[60];
+#pragma unroll
+                for (int e = 0; e < 6; ++e) pe_doubling<5>(dist[e], dp + 10 * e);
+                float z4[8] = {dp[56], dp[57], dp[58], dp[59], 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                for (int c = 0; c < 7; ++c) store_chunk8_a1(sm, row, (224 + 8 * c) >> 5, (224 + 8 * c) & 31, dp + 8 * c);
+                store_chunk8_a1(sm, row, 8, 24, z4);
+                float ddx, ddy, ddz;
+                rot3t(p.o.Rw2c, __ldg(&p.pts.dir[3 * pi]), __ldg(&p.pts.dir[3 * pi + 1]), __ldg(&p.pts.dir[3 * pi + 2]), ddx, ddy, ddz);
+                ex[0] = __ldg(&p.pts.color[3 * pi]); ex[1] = __ldg(&p.pts.color[3 * pi + 1]); ex[2] = __ldg(&p.pts.color[3 * pi + 2]);
+                ex[3] = ddx - ovx; ex[4] = ddy - ovy; ex[5] = ddz - ovz;
+                ex[6] = ddx * ovx + ddy * ovy + ddz * ovz;
+            } else {
+                float z8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                for (int c = 0; c < 36; ++c) store_chunk8_a1(sm, row, c >> 2, (c & 3) * 8, z8);
+            }
+            {   // block3 extras operand [128 x 16]: chunk 0 = extras, chunk 1 = 0
+                uint32_t h[4], l[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) split_bf16x2(ex[2 * i], ex[2 * i + 1], h[i], l[i]);
+                uint32_t off = tc3::xe_offset(row, 0);
+                *reinterpret_cast<uint4*>(sm.xe_hi[t & 1] + off) = make_uint4(h[0], h[1], h[2], h[3]);
+                *reinterpret_cast<uint4*>(sm.xe_lo[t & 1] + off) = make_uint4(l[0], l[1], l[2], l[3]);
+                *reinterpret_cast<uint4*>(sm.xe_hi[t & 1] + off + 128) = make_uint4(0u, 0u, 0u, 0u);
+                *reinterpret_cast<uint4*>(sm.xe_lo[t & 1] + off + 128) = make_uint4(0u, 0u, 0u, 0u);
+            }
+            fence_proxy_async();
+            mbar_arrive(&sm.bar_a1_ready);
+        }
+    } else {
+        // ============================================================ epilogue warps 0..7
+        const int quad = warp & 3, half = warp >> 2;
+        const int erow = quad * 32 + lane;
+        const uint32_t tlane = (uint32_t)(quad * 32) << 16;
+        uint32_t n_acc = 0;
+        bool ok = true;
+        for (int t = 0; t < my_tiles && ok; ++t) {
+            const int tile = (int)blockIdx.x + t * (int)gridDim.x;
+            for (int l = 0; l < 4 && ok; ++l, ++n_acc) {
+                if (!mbar_wait(&sm.bar_acc_full, n_acc & 1u, p.err, 17)) { ok = false; break; }
+                tc_fence_after();
+                if (l < 3) {
+                    const float* bias = p.bias[l];
+#pragma unroll 1
+                    for (int ch = 0; ch < 4; ++ch) {
+                        const int c0 = half * 128 + ch * 32;
+                        uint32_t v[32];
+                        tmem_ld32(tacc + tlane + (uint32_t)c0, v);
+                        tmem_ld_wait();
+                        uint32_t hh[16], ll[16];
+#pragma unroll
+                        for (int e = 0; e < 16; ++e) {
+                            float2 bb = __ldg(reinterpret_cast<const float2*>(bias + c0) + e);
+                            float y0 = __uint_as_float(v[2 * e]) + bb.x, y1 = __uint_as_float(v[2 * e + 1]) + bb.y;
+                            y0 = fmaxf(y0, LEAKY * y0); y1 = fmaxf(y1, LEAKY * y1);
+                            split_bf16x2(y0, y1, hh[e], ll[e]);
+                        }
+                        const uint32_t colp = (uint32_t)(c0 >> 1);
+                        tmem_st8(t_ahi + tlane + colp, hh);
+                        tmem_st8(t_ahi + tlane + colp + 8u, hh + 8);
+                        tmem_st8(t_alo + tlane + colp, ll);
+                        tmem_st8(t_alo + tlane + colp + 8u, ll + 8);
+                    }
+                    tmem_st_wait();
+                    tc_fence_before();
+                    mbar_arrive(&sm.bar_at_ready);
+                } else {
+                    const float wrow = sm.wc[t & 1][erow];
+                    const int sidx = tile * TSAMP + (erow >> 3);
+                    const bool swrite = sidx < n_valid;
+                    const float* bias = p.bias[3];
+                    float apart = 0.f;
+#pragma unroll 1
+                    for (int ch = 0; ch < 4; ++ch) {
+                        const int c0 = half * 128 + ch * 32;
+                        uint32_t v[32];
+                        tmem_ld32(tacc + tlane + (uint32_t)c0, v);
+                        tmem_ld_wait();
+                        float mine[4];
+#pragma unroll
+                        for (int e = 0; e < 32; ++e) {
+                            float y = __uint_as_float(v[e]) + __ldg(bias + c0 + e);
+                            y = fmaxf(y, LEAKY * y);
+                            apart = fmaf(y, __ldg(p.wa + c0 + e), apart);
+                            float z = y * wrow;
+                            z += __shfl_xor_sync(0xffffffffu, z, 1);
+                            z += __shfl_xor_sync(0xffffffffu, z, 2);
+                            z += __shfl_xor_sync(0xffffffffu, z, 4);
+                            if ((e & 7) == (lane & 7)) mine[e >> 3] = z;
+                        }
+                        if (swrite) {
+                            float* dst = p.hbar + (size_t)sidx * 256 + c0 + (lane & 7);
+#pragma unroll
+                            for (int g = 0; g < 4; ++g) dst[8 * g] = mine[g];
+                        }
+                    }
+                    tc_fence_before();
+                    mbar_arrive(&sm.bar_at_ready);          // accumulator drained: the next tile's layer 1 may start
+                    sm.alpha_part[half][erow] = apart;
+                    named_bar_sync(1, tc3::NEPI);
+                    if (half == 0) {
+                        float a = sm.alpha_part[0][erow] + sm.alpha_part[1][erow] + __ldg(p.ba) - 1.0f;
+                        float sp = a > 20.f ? a : log1pf(expf(a));
+                        float z = sp * wrow;
+                        z += __shfl_xor_sync(0xffffffffu, z, 1);
+                        z += __shfl_xor_sync(0xffffffffu, z, 2);
+                        z += __shfl_xor_sync(0xffffffffu, z, 4);
+                        if ((lane & 7) == 0 && swrite) p.sigma[sidx] = z;
+                    }
+                    named_bar_sync(1, tc3::NEPI);
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 13) tmem_dealloc<512>(tacc);
+}
+
 // ------------------------------------------------------------------------------------------ weight packing
 // W^T fp32 [Kpad][256] (rows >= K are zero) -> per K-block: hi image then lo image, each [256 x 32] bf16 in the
 // UMMA operand layout.
-__global__ void __launch_bounds__(256) k_pack_weights(const float* __restrict__ wt, int Kpad, int nkb, unsigned char* __restrict__ out) {
+__global__ void __launch_bounds__(256) k_pack_weights(const float* __restrict__ wt, int Kpad, int nkb, int N, unsigned char* __restrict__ out) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;   // (kb, n, k)
-    if (i >= nkb * 256 * BK) return;
-    int kb = i / (256 * BK), rem = i - kb * 256 * BK;
+    if (i >= nkb * N * BK) return;
+    int kb = i / (N * BK), rem = i - kb * N * BK;
     int n = rem / BK, k = rem - n * BK;
     int kg = kb * BK + k;
-    float v = kg < Kpad ? wt[(size_t)kg * 256 + n] : 0.f;
+    float v = kg < Kpad ? wt[(size_t)kg * N + n] : 0.f;
     __nv_bfloat16 h, l;
     split_bf16(v, h, l);
     uint32_t off = tile_offset_bytes<tc::LAYOUT>(n, k);
-    *(__nv_bfloat16*)(out + (size_t)(2 * kb) * tc::IMG + off) = h;
-    *(__nv_bfloat16*)(out + (size_t)(2 * kb + 1) * tc::IMG + off) = l;
+    const size_t img = (size_t)N * 64;
+    *(__nv_bfloat16*)(out + (size_t)(2 * kb) * img + off) = h;
+    *(__nv_bfloat16*)(out + (size_t)(2 * kb + 1) * img + off) = l;
 }
 
 // ------------------------------------------------------------------------------------------ colour branch
@@ -569,11 +883,249 @@ __global__ void __launch_bounds__(cb::NTHREADS, 1) k_color_branch(ColorParams p)
     }
 }
 
+// =====================================================================================================================
+// Colour branch on the tensor cores: per 128 valid samples  [hbar(256) | PE4(view)(24)] -> 128 -> 128 -> 128 (tcgen05,
+// BF16x3) -> 3 (CUDA cores) -> sigmoid*1.002-0.001   (reference: point_aggregators.py:631-637, 269-273).
+// Layer 1 reads its operand from shared memory (SS), layers 2-3 from tensor memory (TS).  TMEM: accumulator cols
+// 0..127, A_hi 128..191, A_lo 192..255.  320 threads: 8 worker warps (build + epilogues), loader, issuer.
+namespace ctc {
+constexpr int NTHR = 320, NWORK = 256, NSTAGE = 4;
+constexpr int IMG = 128 * 64;                 // [128 x 32] bf16 weight image
+constexpr int NBLK = 9 + 4 + 4;               // K blocks of the three layers
+constexpr int IMGS_PER_TILE = 2 * NBLK;
+__host__ __device__ constexpr int nkb_of(int l) { return l == 0 ? 9 : 4; }
+__host__ __device__ constexpr int img_base(int l) { return l == 0 ? 0 : l == 1 ? 9 : 13; }
+struct Smem {
+    unsigned char a_hi[9 * tc::ABLK];
+    unsigned char a_lo[9 * tc::ABLK];
+    unsigned char b[NSTAGE][IMG];
+    float part[2][128][4];
+    uint32_t samp[128];
+    uint64_t bar_full[NSTAGE], bar_empty[NSTAGE], bar_a_ready, bar_acc_full;
+    uint32_t tmem_base;
+};
+}  // namespace ctc
+
+struct ColorTcParams {
+    pnb_query_t q;
+    pnb_shade_opts_t o;
+    const unsigned char* wimg;      // packed colour_branch.{0,2,4} images
+    const float* bias[3];
+    const float* w3t;               // colour_branch.6 W^T [128][3]
+    const float* b3;
+    const float* hbar;
+    const float* sigma;
+    int hbar_cap;
+    float4* sigma_rgb;
+    int* err;
+};
+
+__global__ void __launch_bounds__(ctc::NTHR, 1) k_color_tc(ColorTcParams p) {
+    using namespace ctc;
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    Smem& sm = *reinterpret_cast<Smem*>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const pnb_query_t& q = p.q;
+    const int n_valid = min(q.counters[PNB_QC_N_VALID], p.hbar_cap);
+    const int n_tiles = (n_valid + 127) / 128;
+    const int my_tiles = n_tiles > (int)blockIdx.x ? (n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+
+    if (tid == 0) {
+        for (int s = 0; s < NSTAGE; ++s) { mbar_init(&sm.bar_full[s], 1); mbar_init(&sm.bar_empty[s], 1); }
+        mbar_init(&sm.bar_a_ready, NWORK);
+        mbar_init(&sm.bar_acc_full, 1);
+        mbar_fence_init();
+    }
+    if (warp == 9) tmem_alloc<256>(&sm.tmem_base);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tacc = sm.tmem_base, t_ahi = tacc + 128u, t_alo = tacc + 192u;
+
+    if (warp == 8) {
+        if (lane == 0) {
+            const uint32_t total = (uint32_t)my_tiles * IMGS_PER_TILE;
+            for (uint32_t n = 0; n < total; ++n) {
+                const uint32_t s = n % NSTAGE, ph = (n / NSTAGE) & 1u;
+                if (!mbar_wait(&sm.bar_empty[s], ph ^ 1u, p.err, 21)) break;
+                mbar_arrive_expect_tx(&sm.bar_full[s], IMG);
+                bulk_g2s(sm.b[s], p.wimg + (size_t)(n % IMGS_PER_TILE) * IMG, IMG, &sm.bar_full[s]);
+            }
+        }
+    } else if (warp == 9) {
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc_bf16(128, 128);
+            uint32_t n = 0, lyr = 0;
+            bool ok = true;
+            for (int t = 0; t < my_tiles && ok; ++t) {
+                for (int l = 0; l < 3 && ok; ++l, ++lyr) {
+                    if (!mbar_wait(&sm.bar_a_ready, lyr & 1u, p.err, 22)) { ok = false; break; }
+                    tc_fence_after();
+                    const int nkb = nkb_of(l);
+                    for (int kb = 0; kb < nkb && ok; ++kb) {
+                        for (int part = 0; part < 2 && ok; ++part) {
+                            const uint32_t s = n % NSTAGE, ph = (n / NSTAGE) & 1u;
+                            if (!mbar_wait(&sm.bar_full[s], ph, p.err, 23)) { ok = false; break; }
+                            tc_fence_after();
+                            for (int ks = 0; ks < 2; ++ks) {
+                                const uint32_t adv = kstep_advance_bytes<tc::LAYOUT>(ks);
+                                const uint64_t db = make_smem_desc<tc::LAYOUT>(smem_u32(sm.b[s]) + adv);
+                                const uint32_t accf = (kb | ks | part) ? 1u : 0u;
+                                if (l == 0) {
+                                    mma_ss(tacc, make_smem_desc<tc::LAYOUT>(smem_u32(sm.a_hi + kb * tc::ABLK) + adv), db, idesc, accf);
+                                    if (part == 0) mma_ss(tacc, make_smem_desc<tc::LAYOUT>(smem_u32(sm.a_lo + kb * tc::ABLK) + adv), db, idesc, 1u);
+                                } else {
+                                    const uint32_t col = (uint32_t)(kb * 16 + ks * 8);
+                                    mma_ts(tacc, t_ahi + col, db, idesc, accf);
+                                    if (part == 0) mma_ts(tacc, t_alo + col, db, idesc, 1u);
+                                }
+                            }
+                            mma_commit(&sm.bar_empty[s]);
+                            ++n;
+                        }
+                    }
+                    mma_commit(&sm.bar_acc_full);
+                }
+            }
+        }
+    } else {
+        const int quad = warp & 3, half = warp >> 2;
+        const int erow = quad * 32 + lane;
+        const uint32_t tlane = (uint32_t)(quad * 32) << 16;
+        uint32_t lyr = 0;
+        bool ok = true;
+        for (int t = 0; t < my_tiles && ok; ++t) {
+            const int tile = (int)blockIdx.x + t * (int)gridDim.x;
+            {   // ---- build: 2 threads per sample row
+                const int row = warp * 16 + (lane >> 1), hf = lane & 1;
+                const int vi = tile * 128 + row;
+                uint32_t s = 0xffffffffu;
+                if (vi < n_valid) {
+                    s = q.valid_list[vi];
+                    const float4* src = (const float4*)(p.hbar + (size_t)vi * 256 + hf * 128);
+#pragma unroll 4
+                    for (int c = 0; c < 16; ++c) {
+                        float4 a = __ldg(src + 2 * c), b = __ldg(src + 2 * c + 1);
+                        float f8[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+                        int col = hf * 128 + 8 * c;
+                        uint32_t h[4], l[4];
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) split_bf16x2(f8[2 * i], f8[2 * i + 1], h[i], l[i]);
+                        uint32_t off = (uint32_t)(col >> 5) * tc::ABLK + tile_offset_bytes<tc::LAYOUT>(row, col & 31);
+                        *reinterpret_cast<uint4*>(sm.a_hi + off) = make_uint4(h[0], h[1], h[2], h[3]);
+                        *reinterpret_cast<uint4*>(sm.a_lo + off) = make_uint4(l[0], l[1], l[2], l[3]);
+                    }
+                } else {
+                    for (int c = 0; c < 16; ++c) {
+                        int col = hf * 128 + 8 * c;
+                        uint32_t off = (uint32_t)(col >> 5) * tc::ABLK + tile_offset_bytes<tc::LAYOUT>(row, col & 31);
+                        *reinterpret_cast<uint4*>(sm.a_hi + off) = make_uint4(0u, 0u, 0u, 0u);
+                        *reinterpret_cast<uint4*>(sm.a_lo + off) = make_uint4(0u, 0u, 0u, 0u);
+                    }
+                }
+                if (hf == 0) {
+                    sm.samp[row] = s;
+                    float pe[32];
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) pe[i] = 0.f;
+                    if (s != 0xffffffffu) {
+                        int r = (int)(q.samp_ray[s] >> 7);
+                        float ov[3];
+                        rot3t(p.o.Rw2c, q.raydir[3 * r], q.raydir[3 * r + 1], q.raydir[3 * r + 2], ov[0], ov[1], ov[2]);
+#pragma unroll
+                        for (int d = 0; d < 3; ++d) {     // ori=True layout: sin block (d*4+j) then cos block
+                            float sc[8];
+                            pe_doubling<4>(ov[d], sc);
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) { pe[d * 4 + j] = sc[2 * j]; pe[12 + d * 4 + j] = sc[2 * j + 1]; }
+                        }
+                    }
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        uint32_t h[4], l[4];
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) split_bf16x2(pe[8 * c + 2 * i], pe[8 * c + 2 * i + 1], h[i], l[i]);
+                        uint32_t off = 8u * tc::ABLK + tile_offset_bytes<tc::LAYOUT>(row, 8 * c);
+                        *reinterpret_cast<uint4*>(sm.a_hi + off) = make_uint4(h[0], h[1], h[2], h[3]);
+                        *reinterpret_cast<uint4*>(sm.a_lo + off) = make_uint4(l[0], l[1], l[2], l[3]);
+                    }
+                }
+            }
+            fence_proxy_async();
+            mbar_arrive(&sm.bar_a_ready);
+            for (int l = 0; l < 3 && ok; ++l, ++lyr) {
+                if (!mbar_wait(&sm.bar_acc_full, lyr & 1u, p.err, 24)) { ok = false; break; }
+                tc_fence_after();
+                const float* bias = p.bias[l];
+                float d0 = 0.f, d1 = 0.f, d2 = 0.f;
+#pragma unroll 1
+                for (int ch = 0; ch < 2; ++ch) {
+                    const int c0 = half * 64 + ch * 32;
+                    uint32_t v[32];
+                    tmem_ld32(tacc + tlane + (uint32_t)c0, v);
+                    tmem_ld_wait();
+                    if (l < 2) {
+                        uint32_t hh[16], ll[16];
+#pragma unroll
+                        for (int e = 0; e < 16; ++e) {
+                            float2 bb = __ldg(reinterpret_cast<const float2*>(bias + c0) + e);
+                            float y0 = __uint_as_float(v[2 * e]) + bb.x, y1 = __uint_as_float(v[2 * e + 1]) + bb.y;
+                            y0 = fmaxf(y0, tc::LEAKY * y0); y1 = fmaxf(y1, tc::LEAKY * y1);
+                            split_bf16x2(y0, y1, hh[e], ll[e]);
+                        }
+                        const uint32_t colp = (uint32_t)(c0 >> 1);
+                        tmem_st8(t_ahi + tlane + colp, hh);
+                        tmem_st8(t_ahi + tlane + colp + 8u, hh + 8);
+                        tmem_st8(t_alo + tlane + colp, ll);
+                        tmem_st8(t_alo + tlane + colp + 8u, ll + 8);
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < 32; ++e) {
+                            float y = __uint_as_float(v[e]) + __ldg(bias + c0 + e);
+                            y = fmaxf(y, tc::LEAKY * y);
+                            const float* wr = p.w3t + (c0 + e) * 3;
+                            d0 = fmaf(y, __ldg(wr), d0); d1 = fmaf(y, __ldg(wr + 1), d1); d2 = fmaf(y, __ldg(wr + 2), d2);
+                        }
+                    }
+                }
+                if (l < 2) {
+                    tmem_st_wait();
+                    tc_fence_before();
+                    mbar_arrive(&sm.bar_a_ready);
+                } else {
+                    tc_fence_before();
+                    sm.part[half][erow][0] = d0; sm.part[half][erow][1] = d1; sm.part[half][erow][2] = d2;
+                    named_bar_sync(1, NWORK);
+                    if (half == 0) {
+                        uint32_t s = sm.samp[erow];
+                        if (s != 0xffffffffu) {
+                            float4 o4;
+                            o4.x = p.sigma[tile * 128 + erow];
+                            float r0 = sm.part[0][erow][0] + sm.part[1][erow][0] + __ldg(p.b3);
+                            float r1 = sm.part[0][erow][1] + sm.part[1][erow][1] + __ldg(p.b3 + 1);
+                            float r2 = sm.part[0][erow][2] + sm.part[1][erow][2] + __ldg(p.b3 + 2);
+                            o4.y = 1.0f / (1.0f + expf(-r0)) * (1.0f + 2.0f * 0.001f) - 0.001f;
+                            o4.z = 1.0f / (1.0f + expf(-r1)) * (1.0f + 2.0f * 0.001f) - 0.001f;
+                            o4.w = 1.0f / (1.0f + expf(-r2)) * (1.0f + 2.0f * 0.001f) - 0.001f;
+                            p.sigma_rgb[s] = o4;
+                        }
+                    }
+                    named_bar_sync(1, NWORK);
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 9) tmem_dealloc<256>(tacc);
+}
+
 }  // namespace pnb
 
 using namespace pnb;
 
-extern "C" size_t pnb_mlp_pack_bytes(void) { return (size_t)tc::NBLK_TOTAL * 2 * tc::IMG; }
+static size_t pack_pairs_bytes() { return (size_t)tc::NBLK_TOTAL * 2 * tc::IMG; }
+extern "C" size_t pnb_mlp_pack_bytes(void) { return pack_pairs_bytes() + (size_t)ctc::NBLK * 2 * ctc::IMG; }
 
 // Packs block1/block3 weights (pnb_mlp_t W^T buffers, fp32) into tcgen05 operand images.  Call once per weight version.
 extern "C" int pnb_mlp_pack(const pnb_mlp_t* mlp, void* d_out, size_t out_bytes, pnb_stream_t stream_) {
@@ -584,7 +1136,14 @@ extern "C" int pnb_mlp_pack(const pnb_mlp_t* mlp, void* d_out, size_t out_bytes,
     for (int l = 0; l < 4; ++l) {
         int nkb = tc::nkb_of(l);
         int n = nkb * 256 * umma::BK;
-        k_pack_weights<<<(n + 255) / 256, 256, 0, stream>>>(mlp->w[l], kpad[l], nkb, (unsigned char*)d_out + (size_t)tc::img_base(l) * 2 * tc::IMG);
+        k_pack_weights<<<(n + 255) / 256, 256, 0, stream>>>(mlp->w[l], kpad[l], nkb, 256, (unsigned char*)d_out + (size_t)tc::img_base(l) * 2 * tc::IMG);
+    }
+    const int ckpad[3] = {288, 128, 128};   // colour_branch.{0,2,4}: W^T [K_pad][128]
+    for (int l = 0; l < 3; ++l) {
+        int nkb = ctc::nkb_of(l);
+        int n = nkb * 128 * umma::BK;
+        k_pack_weights<<<(n + 255) / 256, 256, 0, stream>>>(mlp->w[5 + l], ckpad[l], nkb, 128,
+                                                            (unsigned char*)d_out + pack_pairs_bytes() + (size_t)ctc::img_base(l) * 2 * ctc::IMG);
     }
     PNB_CHECK_CUDA(cudaGetLastError());
     return PNB_OK;
@@ -604,9 +1163,12 @@ extern "C" int pnb_shade_forward_tc(const pnb_query_t* q, const pnb_points_t* pt
     PNB_REQUIRE(q->K >= 1 && q->K <= PNB_MAX_K, PNB_ERR_UNSUPPORTED, "pnb_shade_forward_tc: K=%d unsupported", q->K);
     PNB_REQUIRE(ws_bytes >= pnb_shade_tc_bytes(max_valid_samples), PNB_ERR_WORKSPACE, "pnb_shade_forward_tc: workspace too small");
     static int configured = 0, n_sm = 0;
-    const size_t smem_tc = sizeof(tc::Smem) + 1024, smem_cb = sizeof(cb::Smem);
+    const size_t smem_tc = sizeof(tc::Smem) + 1024, smem_tc3 = sizeof(tc3::Smem) + 1024, smem_cb = sizeof(cb::Smem),
+                 smem_ctc = sizeof(ctc::Smem) + 1024;
     if (!configured) {
         PNB_CHECK_CUDA(cudaFuncSetAttribute(k_shade_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tc));
+        PNB_CHECK_CUDA(cudaFuncSetAttribute(k_shade_tc3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tc3));
+        PNB_CHECK_CUDA(cudaFuncSetAttribute(k_color_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_ctc));
         PNB_CHECK_CUDA(cudaFuncSetAttribute(k_color_branch, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cb));
         int dev = 0;
         PNB_CHECK_CUDA(cudaGetDevice(&dev));
@@ -622,12 +1184,24 @@ extern "C" int pnb_shade_forward_tc(const pnb_query_t* q, const pnb_points_t* pt
     p.wa = mlp->w[4];
     p.ba = mlp->b[4];
     p.hbar = hbar; p.sigma = sigma; p.hbar_cap = max_valid_samples; p.err = d_err;
-    if (stage_mask & 1) k_shade_tc<<<n_sm, tc::NTHR, smem_tc, stream>>>(p);
+    if (stage_mask & 1) {
+        if (stage_mask & 4) k_shade_tc3<<<n_sm, tc3::NTHR, smem_tc3, stream>>>(p);   // TS-form pipeline (A in tensor memory)
+        else k_shade_tc<<<n_sm, tc::NTHR, smem_tc, stream>>>(p);
+    }
     ColorParams cp;
     cp.q = *q; cp.o = *opts;
     for (int i = 0; i < 4; ++i) { cp.w[i] = mlp->w[5 + i]; cp.b[i] = mlp->b[5 + i]; }
     cp.hbar = hbar; cp.sigma = sigma; cp.hbar_cap = max_valid_samples; cp.sigma_rgb = (float4*)d_sigma_rgb;
-    if (stage_mask & 2) k_color_branch<<<n_sm * 2, cb::NTHREADS, smem_cb, stream>>>(cp);
+    if ((stage_mask & 2) && (stage_mask & 8)) {          // colour branch on tcgen05
+        ColorTcParams ct;
+        ct.q = *q; ct.o = *opts; ct.wimg = (const unsigned char*)d_packed + pack_pairs_bytes();
+        for (int i = 0; i < 3; ++i) ct.bias[i] = mlp->b[5 + i];
+        ct.w3t = mlp->w[8]; ct.b3 = mlp->b[8];
+        ct.hbar = hbar; ct.sigma = sigma; ct.hbar_cap = max_valid_samples; ct.sigma_rgb = (float4*)d_sigma_rgb; ct.err = d_err;
+        k_color_tc<<<n_sm, ctc::NTHR, smem_ctc, stream>>>(ct);
+    } else if (stage_mask & 2) {
+        k_color_branch<<<n_sm * 2, cb::NTHREADS, smem_cb, stream>>>(cp);
+    }
     PNB_CHECK_CUDA(cudaGetLastError());
     return PNB_OK;
 }

@@ -257,6 +257,9 @@ def _init_state(mod):
     mod.precision = getattr(opt, "pnb_precision", "bf16x3")
     if mod.precision not in ("bf16x3", "fp32"):
         raise NotImplementedError("pnb200: pnb_precision=%r (bf16x3 | fp32)" % mod.precision)
+    # tcgen05 pipeline variant: 3 = A operand of layers 2-4 in tensor memory + overlapped operand builders (default),
+    # 2 = serialized shared-memory pipeline
+    mod.tc_mask = 3 | (12 if int(getattr(opt, "pnb_tc_version", 3)) == 3 else 0)
     mod.last = None
     mod._pnb_ready = True
 
@@ -321,7 +324,7 @@ class NeuralPointsRayMarching(nn.Module):
                 self._err = torch.zeros(1, dtype=torch.int32, device=raydir.device)
             _lib.check(lib.pnb_shade_forward_tc(_lib.C.byref(q.desc), _lib.C.byref(pts), _lib.C.byref(mlp),
                                                 self._mlp.packed.data_ptr(), _lib.C.byref(o), self._sigma_rgb.data_ptr(),
-                                                self._tc_ws.data_ptr(), self._tc_ws.numel(), max_valid, 3,
+                                                self._tc_ws.data_ptr(), self._tc_ws.numel(), max_valid, self.tc_mask,
                                                 self._err.data_ptr(), stream), "pnb_shade_forward_tc")
         R, SR = q.R, q.SR
         dev = raydir.device

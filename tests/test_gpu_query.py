@@ -155,3 +155,17 @@ def test_query_lego_scale_chunk_and_properties():
     for sel_hit, pidx in rows:
         assert torch.equal(pidx_full[row_of[sel_hit]], pidx)
     assert 0.3 < cnt_full["R2"] / R < 0.6 and cnt_full["n_pairs"] <= cnt_full["n_valid"] * opt.K
+
+
+@pytest.mark.parametrize("name,side", [("truck_8gpu", 40), ("scannet_8gpu", 32)])
+def test_query_large_configs_chunk(name, side):
+    """BASELINE configs 4/5 sizes (N=2M with kernel_size 5 / N=5M box with P=30): a reference-sized chunk vs oracle."""
+    cfg = scene.CONFIGS[name]
+    net, pts, opt = harness.build_model(cfg, DEV)
+    rays = scene.make_rays(cfg, scene.centre_patch(cfg, side))
+    out = _query_points(net, rays)
+    o = _oracle(cfg, opt, pts, rays["raydir"][0])
+    _assert_same(out, o)
+    gc, oc = net.neural_points.querier.last_grid_counters, o["counters"]
+    assert gc["n_occ"] == oc["n_occ"] and gc["max_pts"] == oc["max_pts"] and gc["overflow_p"] == oc["overflow_p"]
+    assert o["counters"]["R2"] > 0

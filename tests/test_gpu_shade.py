@@ -15,6 +15,12 @@ DEV = "cuda:0"
 TOL = 1e-4
 
 
+def _prec(precision):
+    if precision == "bf16x3-v2":
+        return dict(pnb_precision="bf16x3", pnb_tc_version=2)
+    return dict(pnb_precision=precision)
+
+
 def _oracle_render(cfg, opt, pts, agg, raydir):
     return pipeline.render(pts, harness.mlp_cpu(agg), raydir, cfg.campos, np.eye(3, dtype=np.float32), cfg.near, cfg.far,
                            opt.vsize, opt.vscale, opt.kernel_size, opt.query_size, opt.ranges, opt.SR, opt.K, opt.P,
@@ -26,14 +32,14 @@ def _render_full(net, cfg, rays):
         return net.render_full(list(cfg.campos), rays["raydir"].to(DEV), torch.eye(3), cfg.near, cfg.far, [1., 1., 1.])
 
 
-@pytest.mark.parametrize("precision", ["bf16x3", "fp32"])
+@pytest.mark.parametrize("precision", ["bf16x3", "bf16x3-v2", "fp32"])
 @pytest.mark.parametrize("name,side,alpha_bias,over", [
     ("tiny", 64, 4.0, {}), ("tiny", 64, 0.0, {}), ("tiny", 40, 8.0, dict(SR=8)), ("tiny", 40, 4.0, dict(K=3)),
     ("chair_plumbing", 16, 4.0, {}), ("chair_plumbing", 64, 2.0, dict(SR=80)),
 ])
 def test_render_matches_oracle(name, side, alpha_bias, over, precision):
     cfg = scene.CONFIGS[name]
-    net, pts, opt = harness.build_model(cfg, DEV, alpha_bias=alpha_bias, pnb_precision=precision, **over)
+    net, pts, opt = harness.build_model(cfg, DEV, alpha_bias=alpha_bias, **_prec(precision), **over)
     rays = scene.make_rays(cfg, scene.centre_patch(cfg, side))
     out = _render_full(net, cfg, rays)
     ref = _oracle_render(cfg, opt, pts, net.aggregator, rays["raydir"][0])
@@ -45,13 +51,13 @@ def test_render_matches_oracle(name, side, alpha_bias, over, precision):
     net.check_errors()
 
 
-@pytest.mark.parametrize("precision", ["bf16x3", "fp32"])
+@pytest.mark.parametrize("precision", ["bf16x3", "bf16x3-v2", "fp32"])
 @pytest.mark.parametrize("name", ["tiny_opaque", "tiny_thin_sr8"])
 def test_forward_matches_reference_fixture(name, golden_dir, precision):
     """The drop-in NeuralPointsRayMarching.forward() output dict vs what the reference module itself returned."""
     fx = np.load(os.path.join(golden_dir, name + ".npz"))
     cfg = scene.CONFIGS["tiny"]
-    net, pts, opt = harness.build_model(cfg, DEV, SR=int(fx["SR"]), max_o=100000, pnb_precision=precision)
+    net, pts, opt = harness.build_model(cfg, DEV, SR=int(fx["SR"]), max_o=100000, **_prec(precision))
     sd = {k[4:]: torch.from_numpy(fx[k]) for k in fx.files if k.startswith("mlp.")}
     net.aggregator.load_state_dict(sd)
     rays = scene.make_rays(cfg, fx["pixels"])
@@ -66,12 +72,12 @@ def test_forward_matches_reference_fixture(name, golden_dir, precision):
     assert out["queried_shading"].shape == (1, fx["sample_pidx"].shape[0], 3)
 
 
-@pytest.mark.parametrize("precision", ["bf16x3", "fp32"])
+@pytest.mark.parametrize("precision", ["bf16x3", "bf16x3-v2", "fp32"])
 def test_render_lego_scale(precision):
     """BASELINE config 2 size: a reference-sized chunk against the oracle; full-frame determinism and
     sharding invariance (bit-exact: a ray's colour does not depend on which rays share the call)."""
     cfg = scene.CONFIGS["lego_render"]
-    net, pts, opt = harness.build_model(cfg, DEV, alpha_bias=3.0, pnb_precision=precision)
+    net, pts, opt = harness.build_model(cfg, DEV, alpha_bias=3.0, **_prec(precision))
     chunk = scene.make_rays(cfg, scene.centre_patch(cfg, 40))
     out = _render_full(net, cfg, chunk)
     ref = _oracle_render(cfg, opt, pts, net.aggregator, chunk["raydir"][0])
@@ -93,4 +99,19 @@ def test_render_lego_scale(precision):
     hit = (a["ray_mask"][0] > 0)
     assert torch.all(col_a[0][~hit] == 1.0) and torch.all(op_a[0][~hit] == 0)
     assert torch.isfinite(col_a).all() and col_a.min() >= -0.002 and col_a.max() <= 1.002
+    net.check_errors()
+
+
+@pytest.mark.parametrize("name,side", [("truck_8gpu", 24), ("scannet_8gpu", 16)])
+def test_render_large_configs_chunk(name, side):
+    """BASELINE configs 4/5 sizes: rendered radiance of a chunk vs the oracle (default tcgen05 path)."""
+    cfg = scene.CONFIGS[name]
+    net, pts, opt = harness.build_model(cfg, DEV, alpha_bias=3.0)
+    rays = scene.make_rays(cfg, scene.centre_patch(cfg, side))
+    out = _render_full(net, cfg, rays)
+    ref = _oracle_render(cfg, opt, pts, net.aggregator, rays["raydir"][0])
+    assert np.array_equal(out["ray_mask"][0].cpu().numpy(), ref["ray_mask"])
+    for a in ("coarse_raycolor", "coarse_point_opacity", "coarse_is_background"):
+        d = (out[a][0].cpu() - ref[a]).abs().max().item()
+        assert d <= TOL, "%s max abs diff %.3e" % (a, d)
     net.check_errors()

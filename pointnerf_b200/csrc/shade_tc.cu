@@ -114,7 +114,7 @@ __device__ __forceinline__ void store_chunk8(tc::Smem& sm, int r, int kb, int k8
 __global__ void __launch_bounds__(tc::NTHR, 1) k_shade_tc(ShadeTcParams p) {
     using namespace tc;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
-    Smem& sm = *reinterpret_cast<Smem*>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
+    Smem& sm = *reinterpret_cast<Smem*>(smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u));
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const pnb_query_t& q = p.q;
     const int n_valid = min(q.counters[PNB_QC_N_VALID], p.hbar_cap);
@@ -444,7 +444,7 @@ __device__ __forceinline__ void store_chunk8_a1(tc3::Smem& sm, int r, int kb, in
 __global__ void __launch_bounds__(tc3::NTHR, 1) k_shade_tc3(ShadeTcParams p) {
     using namespace tc;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
-    tc3::Smem& sm = *reinterpret_cast<tc3::Smem*>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
+    tc3::Smem& sm = *reinterpret_cast<tc3::Smem*>(smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u));
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const pnb_query_t& q = p.q;
     const int n_valid = min(q.counters[PNB_QC_N_VALID], p.hbar_cap);
@@ -923,7 +923,7 @@ struct ColorTcParams {
 __global__ void __launch_bounds__(ctc::NTHR, 1) k_color_tc(ColorTcParams p) {
     using namespace ctc;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
-    Smem& sm = *reinterpret_cast<Smem*>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
+    Smem& sm = *reinterpret_cast<Smem*>(smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u));
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const pnb_query_t& q = p.q;
     const int n_valid = min(q.counters[PNB_QC_N_VALID], p.hbar_cap);
@@ -1163,8 +1163,12 @@ extern "C" int pnb_shade_forward_tc(const pnb_query_t* q, const pnb_points_t* pt
     PNB_REQUIRE(q->K >= 1 && q->K <= PNB_MAX_K, PNB_ERR_UNSUPPORTED, "pnb_shade_forward_tc: K=%d unsupported", q->K);
     PNB_REQUIRE(ws_bytes >= pnb_shade_tc_bytes(max_valid_samples), PNB_ERR_WORKSPACE, "pnb_shade_forward_tc: workspace too small");
     static int configured = 0, n_sm = 0;
-    const size_t smem_tc = sizeof(tc::Smem) + 1024, smem_tc3 = sizeof(tc3::Smem) + 1024, smem_cb = sizeof(cb::Smem),
-                 smem_ctc = sizeof(ctc::Smem) + 1024;
+    // interleaved (non-swizzled) operand layout: 128-byte alignment of the carve-out is sufficient
+    constexpr size_t kSmemMax = 232448;   // 227 KB opt-in limit per block on sm_100
+    const size_t smem_tc = sizeof(tc::Smem) + 128, smem_tc3 = sizeof(tc3::Smem) + 128, smem_cb = sizeof(cb::Smem),
+                 smem_ctc = sizeof(ctc::Smem) + 128;
+    static_assert(sizeof(tc::Smem) + 128 <= kSmemMax && sizeof(tc3::Smem) + 128 <= kSmemMax && sizeof(ctc::Smem) + 128 <= kSmemMax &&
+                  sizeof(cb::Smem) <= kSmemMax, "shared-memory carve-out exceeds the sm_100 per-block limit");
     if (!configured) {
         PNB_CHECK_CUDA(cudaFuncSetAttribute(k_shade_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tc));
         PNB_CHECK_CUDA(cudaFuncSetAttribute(k_shade_tc3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tc3));

@@ -84,6 +84,25 @@ def golden_case(name, cfg, pixels, alpha_bias, SR=24):
           {k: query_oracle.last_counters[k] for k in ("n_occ", "max_pts", "n_valid_samples", "n_valid_pairs")})
 
 
+def golden_probe(name, cfg, pixels, alpha_bias):
+    """opt.prob == 1 outputs (neural_points_volumetric_model.py:331-351) of the reference module; same MLP weights as
+    golden_case(..., alpha_bias) (seed 0), so the fixture stores outputs only."""
+    net, agg, npts, pts, opt = build_reference_net(cfg, alpha_bias)
+    opt.prob = 1
+    rays = scene.make_rays(cfg, pixels)
+    with torch.no_grad():
+        out = net(rays["campos"], rays["raydir"], bg_color=rays["bg_color"], camrotc2w=rays["camrotc2w"],
+                  pixel_idx=rays["pixel_idx"], near=rays["near"], far=rays["far"], h=rays["h"], w=rays["w"],
+                  intrinsic=rays["intrinsic"])
+    keys = ["ray_max_shading_opacity", "ray_max_sample_loc_w", "ray_max_far_dist", "shading_avg_color", "shading_avg_dir",
+            "shading_avg_conf", "shading_avg_embedding"]
+    fx = {k: out[k][0].numpy() for k in keys}
+    fx["pixels"] = np.asarray(pixels, np.float32)
+    fx["alpha_bias"] = np.float32(alpha_bias)
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **fx)
+    print(name, {k: fx[k].shape for k in keys})
+
+
 def golden_hyper():
     """get_hyperparameters of the reference class for every BASELINE config (cheap, a few ints/floats each)."""
     ref_shim.install()
@@ -109,4 +128,5 @@ if __name__ == "__main__":
     tiny = scene.CONFIGS["tiny"]
     golden_case("tiny_opaque", tiny, scene.centre_patch(tiny, 40), alpha_bias=4.0)
     golden_case("tiny_thin_sr8", tiny, scene.centre_patch(tiny, 40), alpha_bias=0.0, SR=8)
+    golden_probe("tiny_probe", tiny, scene.centre_patch(tiny, 40), alpha_bias=4.0)
     golden_hyper()

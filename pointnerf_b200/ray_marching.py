@@ -52,8 +52,8 @@ def check_opt(opt):
     aw = getattr(opt, "agg_axis_weight", None)
     if aw is not None and any(float(a) != 1.0 for a in aw):
         raise NotImplementedError("pnb200: agg_axis_weight must be None or 1 1 1")
-    if getattr(opt, "prob", 0) != 0:
-        raise NotImplementedError("pnb200: opt.prob == 1 (probe outputs) is a 'next' row (SURVEY 8f)")
+    if getattr(opt, "prob", 0) not in (0, 1):
+        raise NotImplementedError("pnb200: opt.prob must be 0 or 1")
 
 
 def _to_list(x):
@@ -184,6 +184,35 @@ class NeuralPoints(nn.Module):
         self.querier.clean_up()
 
     def reset_querier(self):
+        self.querier.clean_up()
+
+    def _wrap(self, t, grad_flag):
+        t = nn.Parameter(t.contiguous())
+        t.requires_grad = grad_flag
+        return t
+
+    def prune(self, thresh):
+        """/root/reference/models/neural_points/neural_points.py:347-370: keep points with conf >= thresh.
+        Parameters are re-created (the caller rebuilds its optimisers, run/train_ft.py:834-842); the cached voxel
+        grid is invalidated."""
+        o = self.opt
+        mask = self.points_conf[0, ..., 0] >= thresh
+        self.xyz = self._wrap(self.xyz[mask, :], getattr(o, "xyz_grad", 0) > 0)
+        self.points_embeding = self._wrap(self.points_embeding[:, mask, :], getattr(o, "feat_grad", 1) > 0)
+        self.points_conf = self._wrap(self.points_conf[:, mask, :], getattr(o, "conf_grad", 1) > 0)
+        self.points_dir = self._wrap(self.points_dir[:, mask, :], getattr(o, "dir_grad", 1) > 0)
+        self.points_color = self._wrap(self.points_color[:, mask, :], getattr(o, "color_grad", 1) > 0)
+        self.querier.clean_up()
+        return int((~mask).sum())
+
+    def grow_points(self, add_xyz, add_embedding, add_color, add_dir, add_conf, add_eulers=None, add_Rw2c=None):
+        """/root/reference/models/neural_points/neural_points.py:373-399: append points (new parameters)."""
+        o = self.opt
+        self.xyz = self._wrap(torch.cat([self.xyz, add_xyz], dim=0), getattr(o, "xyz_grad", 0) > 0)
+        self.points_embeding = self._wrap(torch.cat([self.points_embeding, add_embedding[None, ...]], dim=1), getattr(o, "feat_grad", 1) > 0)
+        self.points_conf = self._wrap(torch.cat([self.points_conf, add_conf[None, ...]], dim=1), getattr(o, "conf_grad", 1) > 0)
+        self.points_dir = self._wrap(torch.cat([self.points_dir, add_dir[None, ...]], dim=1), getattr(o, "dir_grad", 1) > 0)
+        self.points_color = self._wrap(torch.cat([self.points_color, add_color[None, ...]], dim=1), getattr(o, "color_grad", 1) > 0)
         self.querier.clean_up()
 
     def points_desc(self):
@@ -408,4 +437,28 @@ class NeuralPointsRayMarching(nn.Module):
             out["weight"] = wgt[None].detach()
             out["blend_weight"] = (op * acc_T)[None, ..., None]
             out["conf_coefficient"] = conf_coefficient[None]
+            if getattr(opt, "prob", 0) == 1:
+                # probe outputs for point growing (neural_points_volumetric_model.py:331-351), same torch ops on the
+                # dense export: arg-max-opacity sample of every ray and the weighted average of its neighbours
+                K = pidx.shape[-1]
+                omax, oind = torch.max(out["coarse_point_opacity"], dim=-1, keepdim=True)          # [1,R',1]
+                out["ray_max_shading_opacity"] = omax
+                oi = oind[0, :, 0]
+                rows = torch.arange(pidx.shape[0], device=pidx.device)
+                loc_max = ex["sample_loc_w"][rows, oi]                                                # [R',3]
+                out["ray_max_sample_loc_w"] = loc_max[None]
+                wsel = (wgt * conf_coefficient.detach())[rows, oi][..., None]                         # [R',K,1]
+                idx_max = idx[rows, oi]                                                               # [R',K] (clamped, :707)
+                xyz_max = npnts.xyz.detach()[idx_max]
+                out["ray_max_far_dist"] = torch.min(torch.norm(xyz_max - loc_max[:, None, :], dim=-1), dim=-1, keepdim=True)[0][None]
+                out["shading_avg_color"] = torch.sum(npnts.points_color.detach()[0][idx_max] * wsel, dim=-2)[None]
+                out["shading_avg_dir"] = torch.sum(npnts.points_dir.detach()[0][idx_max] * wsel, dim=-2)[None]
+                out["shading_avg_conf"] = torch.sum(npnts.points_conf.detach()[0][idx_max] * wsel, dim=-2)[None]
+                out["shading_avg_embedding"] = torch.sum(npnts.points_embeding.detach()[0][idx_max] * wsel, dim=-2)[None]
+        elif getattr(opt, "prob", 0) == 1:
+            dev = ray_color.device                                                                    # :352-361
+            out.update({"ray_max_shading_opacity": torch.zeros([0, 0, 1, 1], device=dev), "ray_max_sample_loc_w": torch.zeros([0, 0, 3], device=dev),
+                        "ray_max_far_dist": torch.zeros([0, 0, 1], device=dev), "shading_avg_color": torch.zeros([0, 0, 3], device=dev),
+                        "shading_avg_dir": torch.zeros([0, 0, 3], device=dev), "shading_avg_conf": torch.zeros([0, 0, 1], device=dev),
+                        "shading_avg_embedding": torch.zeros([0, 0, 32], device=dev)})
         return out

@@ -115,3 +115,27 @@ def test_render_large_configs_chunk(name, side):
         d = (out[a][0].cpu() - ref[a]).abs().max().item()
         assert d <= TOL, "%s max abs diff %.3e" % (a, d)
     net.check_errors()
+
+
+def test_probe_outputs_match_reference_fixture(golden_dir):
+    """opt.prob == 1 (point-growing probe, run/train_ft.py:417-530): the extra per-ray outputs of the drop-in forward
+    vs what the reference module returned (neural_points_volumetric_model.py:331-351)."""
+    fx = np.load(os.path.join(golden_dir, "tiny_probe.npz"))
+    wfx = np.load(os.path.join(golden_dir, "tiny_opaque.npz"))
+    cfg = scene.CONFIGS["tiny"]
+    net, pts, opt = harness.build_model(cfg, DEV, max_o=100000, prob=1)
+    net.aggregator.load_state_dict({k[4:]: torch.from_numpy(wfx[k]) for k in wfx.files if k.startswith("mlp.")})
+    rays = scene.make_rays(cfg, fx["pixels"])
+    r = {k: v.to(DEV) for k, v in rays.items()}
+    with torch.no_grad():
+        out = net(r["campos"], r["raydir"], bg_color=r["bg_color"], camrotc2w=r["camrotc2w"], pixel_idx=r["pixel_idx"],
+                  near=r["near"], far=r["far"], h=r["h"], w=r["w"], intrinsic=r["intrinsic"])
+    # rays whose arg-max opacity is (numerically) tied between two samples may pick the other sample: compare where
+    # the selected sample location agrees, and require that to be (almost) everywhere
+    loc = out["ray_max_sample_loc_w"][0].cpu().numpy()
+    same = np.abs(loc - fx["ray_max_sample_loc_w"]).max(-1) == 0
+    assert same.mean() > 0.98
+    for k, tol in (("ray_max_shading_opacity", 1e-4), ("ray_max_far_dist", 1e-6), ("shading_avg_color", 1e-5),
+                   ("shading_avg_dir", 1e-5), ("shading_avg_conf", 1e-5), ("shading_avg_embedding", 1e-5)):
+        a = out[k][0].cpu().numpy().reshape(fx[k].shape)
+        assert np.abs(a - fx[k])[same].max() <= tol, k

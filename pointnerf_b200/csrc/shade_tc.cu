@@ -406,6 +406,12 @@ __global__ void __launch_bounds__(tc::NTHR, 1) k_shade_tc(ShadeTcParams p) {
 // core runs layers 2-4 of the current tile.  TMEM: accumulator cols 0..255, A_hi 256..383, A_lo 384..511 (two bf16
 // per 32-bit column).  Warp roles (448 threads): 0-7 epilogue (TMEM -> bias/LeakyReLU/split -> TMEM), 8-11 builders,
 // 12 loader, 13 issuer.  The 7 block3 extras go through a small [128 x 16] shared-memory operand (one SS k-step).
+// Optional in-kernel cycle accounting (block 0 only): err[2 + 2*i], 64-bit counters, see tools/tc_profile.py
+__device__ __forceinline__ void prof_add(int* err, int slot, long long cyc) {
+    if (blockIdx.x == 0) atomicAdd(reinterpret_cast<unsigned long long*>(err) + 1 + slot, (unsigned long long)cyc);
+}
+#define PNB_TIMED_WAIT(slot, expr) [&]() { long long _t0 = clock64(); bool _r = (expr); prof_add(p.err, slot, clock64() - _t0); return _r; }()
+
 namespace tc3 {
 constexpr int NEPI = 256, NBUILD = 128, NTHR = 448;
 constexpr int NSTAGE = 4;
@@ -466,6 +472,7 @@ __global__ void __launch_bounds__(tc3::NTHR, 1) k_shade_tc3(ShadeTcParams p) {
     tc_fence_after();
     const uint32_t tacc = sm.tmem_base;
     const uint32_t t_ahi = tacc + 256u, t_alo = tacc + 384u;
+    const long long _tk0 = clock64();
 
     if (warp == 12) {
         // ============================================================ loader
@@ -473,7 +480,7 @@ __global__ void __launch_bounds__(tc3::NTHR, 1) k_shade_tc3(ShadeTcParams p) {
             const uint32_t total = (uint32_t)my_tiles * IMGS_PER_TILE;
             for (uint32_t n = 0; n < total; ++n) {
                 const uint32_t s = n % tc3::NSTAGE, ph = (n / tc3::NSTAGE) & 1u;
-                if (!mbar_wait(&sm.bar_empty[s], ph ^ 1u, p.err, 11)) break;
+                if (!PNB_TIMED_WAIT(0, mbar_wait(&sm.bar_empty[s], ph ^ 1u, p.err, 11))) break;
                 mbar_arrive_expect_tx(&sm.bar_full[s], IMG);
                 bulk_g2s(sm.b[s], p.wimg + (size_t)(n % IMGS_PER_TILE) * IMG, IMG, &sm.bar_full[s]);
             }
@@ -487,10 +494,10 @@ __global__ void __launch_bounds__(tc3::NTHR, 1) k_shade_tc3(ShadeTcParams p) {
             for (int t = 0; t < my_tiles && ok; ++t) {
                 for (int l = 0; l < 4 && ok; ++l) {
                     if (l == 0) {
-                        if (!mbar_wait(&sm.bar_a1_ready, (uint32_t)t & 1u, p.err, 12)) { ok = false; break; }
-                        if (t > 0) { if (!mbar_wait(&sm.bar_at_ready, n_at & 1u, p.err, 13)) { ok = false; break; } ++n_at; }
+                        if (!PNB_TIMED_WAIT(1, mbar_wait(&sm.bar_a1_ready, (uint32_t)t & 1u, p.err, 12))) { ok = false; break; }
+                        if (t > 0) { if (!PNB_TIMED_WAIT(2, mbar_wait(&sm.bar_at_ready, n_at & 1u, p.err, 13))) { ok = false; break; } ++n_at; }
                     } else {
-                        if (!mbar_wait(&sm.bar_at_ready, n_at & 1u, p.err, 14)) { ok = false; break; }
+                        if (!PNB_TIMED_WAIT(2, mbar_wait(&sm.bar_at_ready, n_at & 1u, p.err, 14))) { ok = false; break; }
                         ++n_at;
                     }
                     tc_fence_after();
@@ -500,7 +507,7 @@ __global__ void __launch_bounds__(tc3::NTHR, 1) k_shade_tc3(ShadeTcParams p) {
                         const bool ss = (l == 0) || (kb == 8);           // layer 1 and the extras block read smem
                         for (int part = 0; part < 2 && ok; ++part) {      // 0: W_hi image, 1: W_lo image
                             const uint32_t s = n % tc3::NSTAGE, ph = (n / tc3::NSTAGE) & 1u;
-                            if (!mbar_wait(&sm.bar_full[s], ph, p.err, 15)) { ok = false; break; }
+                            if (!PNB_TIMED_WAIT(3, mbar_wait(&sm.bar_full[s], ph, p.err, 15))) { ok = false; break; }
                             tc_fence_after();
                             for (int ks = 0; ks < nks; ++ks) {
                                 const uint32_t adv = kstep_advance_bytes<LAYOUT>(ks);
@@ -534,7 +541,8 @@ __global__ void __launch_bounds__(tc3::NTHR, 1) k_shade_tc3(ShadeTcParams p) {
         bool ok = true;
         for (int t = 0; t < my_tiles && ok; ++t) {
             const int tile = (int)blockIdx.x + t * (int)gridDim.x;
-            if (t > 0 && !mbar_wait(&sm.bar_a1_free, (uint32_t)(t - 1) & 1u, p.err, 16)) { ok = false; break; }
+            if (t > 0 && !(lane == 0 && warp == 8 ? PNB_TIMED_WAIT(4, mbar_wait(&sm.bar_a1_free, (uint32_t)(t - 1) & 1u, p.err, 16)) : mbar_wait(&sm.bar_a1_free, (uint32_t)(t - 1) & 1u, p.err, 16))) { ok = false; break; }
+            const long long _tb0 = clock64();
             const int vi = tile * TSAMP + si;
             int pidx = -1;
             float lx = 0.f, ly = 0.f, lz = 0.f, vx = 0.f, vy = 0.f, vz = 0.f;
@@ -622,6 +630,7 @@ __global__ void __launch_bounds__(tc3::NTHR, 1) k_shade_tc3(ShadeTcParams p) {
             }
             fence_proxy_async();
             mbar_arrive(&sm.bar_a1_ready);
+            if (lane == 0 && warp == 8) prof_add(p.err, 5, clock64() - _tb0);
         }
     } else {
         // ============================================================ epilogue warps 0..7
@@ -633,7 +642,8 @@ __global__ void __launch_bounds__(tc3::NTHR, 1) k_shade_tc3(ShadeTcParams p) {
         for (int t = 0; t < my_tiles && ok; ++t) {
             const int tile = (int)blockIdx.x + t * (int)gridDim.x;
             for (int l = 0; l < 4 && ok; ++l, ++n_acc) {
-                if (!mbar_wait(&sm.bar_acc_full, n_acc & 1u, p.err, 17)) { ok = false; break; }
+                if (!(tid == 0 ? PNB_TIMED_WAIT(6, mbar_wait(&sm.bar_acc_full, n_acc & 1u, p.err, 17)) : mbar_wait(&sm.bar_acc_full, n_acc & 1u, p.err, 17))) { ok = false; break; }
+                const long long _te0 = clock64();
                 tc_fence_after();
                 if (l < 3) {
                     const float* bias = p.bias[l];
@@ -660,6 +670,7 @@ __global__ void __launch_bounds__(tc3::NTHR, 1) k_shade_tc3(ShadeTcParams p) {
                     tmem_st_wait();
                     tc_fence_before();
                     mbar_arrive(&sm.bar_at_ready);
+                    if (tid == 0) prof_add(p.err, 7, clock64() - _te0);
                 } else {
                     const float wrow = sm.wc[t & 1][erow];
                     const int sidx = tile * TSAMP + (erow >> 3);
@@ -692,6 +703,7 @@ __global__ void __launch_bounds__(tc3::NTHR, 1) k_shade_tc3(ShadeTcParams p) {
                     }
                     tc_fence_before();
                     mbar_arrive(&sm.bar_at_ready);          // accumulator drained: the next tile's layer 1 may start
+                    if (tid == 0) prof_add(p.err, 8, clock64() - _te0);
                     sm.alpha_part[half][erow] = apart;
                     named_bar_sync(1, tc3::NEPI);
                     if (half == 0) {
@@ -708,6 +720,7 @@ __global__ void __launch_bounds__(tc3::NTHR, 1) k_shade_tc3(ShadeTcParams p) {
             }
         }
     }
+    if (tid == 0) prof_add(p.err, 9, clock64() - _tk0);
     tc_fence_before();
     __syncthreads();
     if (warp == 13) tmem_dealloc<512>(tacc);

@@ -350,7 +350,7 @@ class NeuralPointsRayMarching(nn.Module):
             if self._tc_ws is None or self._tc_ws.numel() < nb or self._tc_ws.device != raydir.device:
                 self._tc_ws = torch.empty(nb, dtype=torch.uint8, device=raydir.device)
             if self._err is None or self._err.device != raydir.device:
-                self._err = torch.zeros(1, dtype=torch.int32, device=raydir.device)
+                self._err = torch.zeros(64, dtype=torch.int32, device=raydir.device)   # [0] status, [2:] cycle counters
             _lib.check(lib.pnb_shade_forward_tc(_lib.C.byref(q.desc), _lib.C.byref(pts), _lib.C.byref(mlp),
                                                 self._mlp.packed.data_ptr(), _lib.C.byref(o), self._sigma_rgb.data_ptr(),
                                                 self._tc_ws.data_ptr(), self._tc_ws.numel(), max_valid, self.tc_mask,
@@ -371,7 +371,7 @@ class NeuralPointsRayMarching(nn.Module):
     def check_errors(self):
         """Synchronising check of the device-side error flag of the tensor-core path (raises on failure)."""
         if self._err is not None:
-            code = int(self._err.item())
+            code = int(self._err[0].item())
             if code == 9:
                 raise _lib.PnbError("pnb200: more valid samples than the shading workspace holds; raise opt.pnb_max_valid_per_ray")
             if code != 0:

@@ -1,0 +1,26 @@
+"""Run on the GPU box: in-kernel cycle accounting of k_shade_tc3 (block 0), lego_render frame."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from pointnerf_b200 import harness, scene
+dev = torch.device("cuda:0")
+cfg = scene.CONFIGS["lego_render"]
+net, pts, opt = harness.build_model(cfg, dev, alpha_bias=3.0)
+rays = scene.make_rays(cfg)
+rd = rays["raydir"].to(dev)
+for i in range(3):
+    with torch.no_grad():
+        net.render_full(list(cfg.campos), rd, torch.eye(3), cfg.near, cfg.far, [1., 1., 1.])
+torch.cuda.synchronize()
+net._err.zero_()
+with torch.no_grad():
+    net.render_full(list(cfg.campos), rd, torch.eye(3), cfg.near, cfg.far, [1., 1., 1.])
+torch.cuda.synchronize()
+c = net._err.cpu().view(torch.int64)[1:11].tolist()
+names = ["loader wait empty", "issuer wait a1_ready", "issuer wait at_ready", "issuer wait full(weights)", "builder wait a1_free",
+         "builder busy", "epilogue wait acc_full", "epilogue busy (l<3)", "epilogue busy (l==3)", "kernel total (thread 0)"]
+ntiles = (net.last.counters["n_valid"] if net.last.counters else 3472901) if False else None
+tot = c[9]
+print("status", int(net._err[0]))
+for n, v in zip(names, c):
+    print("%-28s %12d cycles  %5.1f%% of kernel" % (n, v, 100.0 * v / max(tot, 1)))

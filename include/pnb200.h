@@ -210,6 +210,10 @@ int pnb_shade_backward(const pnb_query_t* q, const pnb_points_t* pts, const pnb_
 int pnb_umma_selftest(const float* d_A, const float* d_W, float* d_D, int K, int N, int layout, int* d_err,
                       pnb_stream_t stream);
 
+/* Micro-benchmark of the tcgen05.mma issue rate (M=128,N=256,K=16 bf16) on resident operands; d_out int64[2]. */
+int pnb_umma_bench(int layout, int mode, int iters, int bulk, const void* d_src, long long* d_out, int* d_err,
+                   pnb_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -208,6 +208,58 @@ __global__ void __launch_bounds__(128, 1) k_umma_selftest_ts(const float* __rest
     if (warp == 0) tmem_dealloc<512>(tacc);
 }
 
+// Micro-benchmark: cycles per tcgen05.mma (M=128, N=256, K=16, bf16) issued back to back on resident operands.
+// mode 0: A and B in shared memory (SS), mode 1: A in tensor memory (TS).  bulk = 1 adds a concurrent stream of
+// 16 KB cp.async.bulk copies into a second shared buffer (the weight-streaming traffic of the fused kernel).
+template <int LAYOUT>
+__global__ void __launch_bounds__(128, 1) k_umma_bench(int mode, int iters, int bulk, const unsigned char* __restrict__ gsrc,
+                                                       long long* __restrict__ out, int* err) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    unsigned char* a = smem;                 // [128 x 32]
+    unsigned char* b = smem + 8192;          // [256 x 32]
+    unsigned char* sink = smem + 8192 + 16384;   // 2 x 16 KB landing zone for bulk copies
+    __shared__ uint64_t bar, bbar[2];
+    __shared__ uint32_t tmem_base;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    for (int i = tid; i < (8192 + 16384) / 4; i += 128) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;
+    if (tid == 0) { mbar_init(&bar, 1); mbar_init(&bbar[0], 1); mbar_init(&bbar[1], 1); mbar_fence_init(); }
+    if (warp == 0) tmem_alloc<512>(&tmem_base);
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tacc = tmem_base;
+    if (tid == 32 && bulk) {       // concurrent weight-like stream
+        for (int i = 0; i < iters / 3 + 2; ++i) {
+            int s = i & 1;
+            if (i >= 2 && !mbar_wait(&bbar[s], ((i >> 1) - 1) & 1, err, 301)) break;
+            mbar_arrive_expect_tx(&bbar[s], 16384);
+            bulk_g2s(sink + s * 16384, gsrc + (size_t)(i % 64) * 16384, 16384, &bbar[s]);
+        }
+    }
+    if (tid == 0) {
+        const uint32_t idesc = make_idesc_bf16(128, 256);
+        const uint64_t da = make_smem_desc<LAYOUT>(smem_u32(a)), db = make_smem_desc<LAYOUT>(smem_u32(b));
+        long long t0 = clock64();
+        for (int i = 0; i < iters; ++i) {
+            if (mode == 0) mma_ss(tacc, da, db, idesc, 1u);
+            else mma_ts(tacc, tacc + 256u, db, idesc, 1u);
+        }
+        mma_commit(&bar);
+        long long t1 = clock64();
+        mbar_wait(&bar, 0, err, 300);
+        long long t2 = clock64();
+        out[0] = t1 - t0;      // issue time
+        out[1] = t2 - t0;      // until all MMAs completed
+    }
+    __syncthreads();
+    if (tid == 32 && bulk) { mbar_wait(&bbar[0], 1, nullptr, 0); }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc<512>(tacc);
+}
+
 }  // namespace pnb
 
 using namespace pnb;
@@ -234,6 +286,22 @@ extern "C" int pnb_umma_selftest(const float* d_A, const float* d_W, float* d_D,
         k_umma_selftest_ts<umma::LAYOUT_NONE><<<1, 128, smem_ts, stream>>>(d_A, d_W, d_D, K, N, layout == 101 ? 1 : 0, d_err);
     } else {
         PNB_REQUIRE(false, PNB_ERR_INVALID, "pnb_umma_selftest: layout %d not supported", layout);
+    }
+    PNB_CHECK_CUDA(cudaGetLastError());
+    return PNB_OK;
+}
+
+// layout 0 / 4 (interleaved / SW64); mode 0 SS, 1 TS; d_out: int64[2] (issue cycles, total cycles); d_src >= 1 MB.
+extern "C" int pnb_umma_bench(int layout, int mode, int iters, int bulk, const void* d_src, long long* d_out, int* d_err,
+                              pnb_stream_t stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    size_t smem = 8192 + 16384 + 32768 + 1024;
+    if (layout == umma::LAYOUT_SW64) {
+        PNB_CHECK_CUDA(cudaFuncSetAttribute(k_umma_bench<umma::LAYOUT_SW64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_umma_bench<umma::LAYOUT_SW64><<<1, 128, smem, stream>>>(mode, iters, bulk, (const unsigned char*)d_src, d_out, d_err);
+    } else {
+        PNB_CHECK_CUDA(cudaFuncSetAttribute(k_umma_bench<umma::LAYOUT_NONE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_umma_bench<umma::LAYOUT_NONE><<<1, 128, smem, stream>>>(mode, iters, bulk, (const unsigned char*)d_src, d_out, d_err);
     }
     PNB_CHECK_CUDA(cudaGetLastError());
     return PNB_OK;

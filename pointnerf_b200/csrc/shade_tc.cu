@@ -486,12 +486,18 @@ __global__ void __launch_bounds__(tc3::NTHR, 1) k_shade_tc3(ShadeTcParams p) {
             }
         }
     } else if (warp == 13) {
-        // ============================================================ MMA issuer
+        // ============================================================ MMA issuer (lean: ~15 instructions per MMA)
         if (lane == 0) {
             const uint32_t idesc = make_idesc_bf16(128, 256);
+            const uint32_t hiw = desc_hi<LAYOUT>(), xe_hiw = (256u >> 4) | (1u << 14);
+            const uint32_t b0_lo = desc_lo<LAYOUT>(smem_u32(sm.b[0]));
+            const uint32_t ahi_lo = desc_lo<LAYOUT>(smem_u32(sm.a_hi)), alo_lo = desc_lo<LAYOUT>(smem_u32(sm.a_lo));
+            const uint32_t xeh_lo0 = desc_lo<LAYOUT_NONE>(smem_u32(sm.xe_hi[0])), xel_lo0 = desc_lo<LAYOUT_NONE>(smem_u32(sm.xe_lo[0]));
+            constexpr uint32_t KADV = kstep_adv16<LAYOUT>();
             uint32_t n = 0, n_at = 0;
             bool ok = true;
             for (int t = 0; t < my_tiles && ok; ++t) {
+                const uint32_t xeh_lo = xeh_lo0 + (uint32_t)(t & 1) * (tc3::XE >> 4), xel_lo = xel_lo0 + (uint32_t)(t & 1) * (tc3::XE >> 4);
                 for (int l = 0; l < 4 && ok; ++l) {
                     if (l == 0) {
                         if (!PNB_TIMED_WAIT(1, mbar_wait(&sm.bar_a1_ready, (uint32_t)t & 1u, p.err, 12))) { ok = false; break; }
@@ -503,31 +509,49 @@ __global__ void __launch_bounds__(tc3::NTHR, 1) k_shade_tc3(ShadeTcParams p) {
                     tc_fence_after();
                     const int nkb = nkb_of(l);
                     for (int kb = 0; kb < nkb && ok; ++kb) {
-                        const int nks = (l == 2 && kb == 8) ? 1 : 2;
-                        const bool ss = (l == 0) || (kb == 8);           // layer 1 and the extras block read smem
-                        for (int part = 0; part < 2 && ok; ++part) {      // 0: W_hi image, 1: W_lo image
-                            const uint32_t s = n % tc3::NSTAGE, ph = (n / tc3::NSTAGE) & 1u;
+                        const bool two = !(l == 2 && kb == 8);             // block3 extras block: one k-step
+                        const uint32_t akb_hi = ahi_lo + (uint32_t)kb * (ABLK >> 4), akb_lo = alo_lo + (uint32_t)kb * (ABLK >> 4);
+                        const uint32_t tcol = (uint32_t)(kb * 16);
+                        {   // ---- W_hi image: A_hi*W_hi + A_lo*W_hi
+                            const uint32_t s = n & (tc3::NSTAGE - 1), ph = (n >> 2) & 1u;
                             if (!PNB_TIMED_WAIT(3, mbar_wait(&sm.bar_full[s], ph, p.err, 15))) { ok = false; break; }
                             tc_fence_after();
-                            for (int ks = 0; ks < nks; ++ks) {
-                                const uint32_t adv = kstep_advance_bytes<LAYOUT>(ks);
-                                const uint64_t db = make_smem_desc<LAYOUT>(smem_u32(sm.b[s]) + adv);
-                                const uint32_t accf = (kb | ks | part) ? 1u : 0u;
-                                if (l == 0) {
-                                    mma_ss(tacc, make_smem_desc<LAYOUT>(smem_u32(sm.a_hi + kb * ABLK) + adv), db, idesc, accf);
-                                    if (part == 0) mma_ss(tacc, make_smem_desc<LAYOUT>(smem_u32(sm.a_lo + kb * ABLK) + adv), db, idesc, 1u);
-                                } else if (ss) {
-                                    mma_ss(tacc, tc3::xe_desc(smem_u32(sm.xe_hi[t & 1])), db, idesc, 1u);
-                                    if (part == 0) mma_ss(tacc, tc3::xe_desc(smem_u32(sm.xe_lo[t & 1])), db, idesc, 1u);
-                                } else {
-                                    const uint32_t col = (uint32_t)(kb * 16 + ks * 8);
-                                    mma_ts(tacc, t_ahi + col, db, idesc, accf);
-                                    if (part == 0) mma_ts(tacc, t_alo + col, db, idesc, 1u);
-                                }
+                            const uint32_t bl = b0_lo + s * (IMG >> 4);
+                            if (l == 0) {
+                                mma_ss2(tacc, akb_hi, hiw, bl, hiw, idesc, kb ? 1u : 0u);
+                                mma_ss2(tacc, akb_lo, hiw, bl, hiw, idesc, 1u);
+                                mma_ss2(tacc, akb_hi + KADV, hiw, bl + KADV, hiw, idesc, 1u);
+                                mma_ss2(tacc, akb_lo + KADV, hiw, bl + KADV, hiw, idesc, 1u);
+                            } else if (kb == 8) {
+                                mma_ss2(tacc, xeh_lo, xe_hiw, bl, hiw, idesc, 1u);
+                                mma_ss2(tacc, xel_lo, xe_hiw, bl, hiw, idesc, 1u);
+                            } else {
+                                mma_ts2(tacc, t_ahi + tcol, bl, hiw, idesc, kb ? 1u : 0u);
+                                mma_ts2(tacc, t_alo + tcol, bl, hiw, idesc, 1u);
+                                mma_ts2(tacc, t_ahi + tcol + 8u, bl + KADV, hiw, idesc, 1u);
+                                mma_ts2(tacc, t_alo + tcol + 8u, bl + KADV, hiw, idesc, 1u);
                             }
                             mma_commit(&sm.bar_empty[s]);
                             ++n;
                         }
+                        {   // ---- W_lo image: A_hi*W_lo
+                            const uint32_t s = n & (tc3::NSTAGE - 1), ph = (n >> 2) & 1u;
+                            if (!PNB_TIMED_WAIT(3, mbar_wait(&sm.bar_full[s], ph, p.err, 15))) { ok = false; break; }
+                            tc_fence_after();
+                            const uint32_t bl = b0_lo + s * (IMG >> 4);
+                            if (l == 0) {
+                                mma_ss2(tacc, akb_hi, hiw, bl, hiw, idesc, 1u);
+                                mma_ss2(tacc, akb_hi + KADV, hiw, bl + KADV, hiw, idesc, 1u);
+                            } else if (kb == 8) {
+                                mma_ss2(tacc, xeh_lo, xe_hiw, bl, hiw, idesc, 1u);
+                            } else {
+                                mma_ts2(tacc, t_ahi + tcol, bl, hiw, idesc, 1u);
+                                mma_ts2(tacc, t_ahi + tcol + 8u, bl + KADV, hiw, idesc, 1u);
+                            }
+                            mma_commit(&sm.bar_empty[s]);
+                            ++n;
+                        }
+                        (void)two;
                     }
                     mma_commit(&sm.bar_acc_full);
                     if (l == 0) mma_commit(&sm.bar_a1_free);
@@ -968,6 +992,10 @@ __global__ void __launch_bounds__(ctc::NTHR, 1) k_color_tc(ColorTcParams p) {
     } else if (warp == 9) {
         if (lane == 0) {
             const uint32_t idesc = make_idesc_bf16(128, 128);
+            const uint32_t hiw = desc_hi<tc::LAYOUT>();
+            const uint32_t b0_lo = desc_lo<tc::LAYOUT>(smem_u32(sm.b[0]));
+            const uint32_t ahi_lo = desc_lo<tc::LAYOUT>(smem_u32(sm.a_hi)), alo_lo = desc_lo<tc::LAYOUT>(smem_u32(sm.a_lo));
+            constexpr uint32_t KADV = kstep_adv16<tc::LAYOUT>();
             uint32_t n = 0, lyr = 0;
             bool ok = true;
             for (int t = 0; t < my_tiles && ok; ++t) {
@@ -976,22 +1004,38 @@ __global__ void __launch_bounds__(ctc::NTHR, 1) k_color_tc(ColorTcParams p) {
                     tc_fence_after();
                     const int nkb = nkb_of(l);
                     for (int kb = 0; kb < nkb && ok; ++kb) {
-                        for (int part = 0; part < 2 && ok; ++part) {
-                            const uint32_t s = n % NSTAGE, ph = (n / NSTAGE) & 1u;
+                        const uint32_t akb_hi = ahi_lo + (uint32_t)kb * (tc::ABLK >> 4), akb_lo = alo_lo + (uint32_t)kb * (tc::ABLK >> 4);
+                        const uint32_t tcol = (uint32_t)(kb * 16);
+                        {
+                            const uint32_t s = n & (NSTAGE - 1), ph = (n >> 2) & 1u;
                             if (!mbar_wait(&sm.bar_full[s], ph, p.err, 23)) { ok = false; break; }
                             tc_fence_after();
-                            for (int ks = 0; ks < 2; ++ks) {
-                                const uint32_t adv = kstep_advance_bytes<tc::LAYOUT>(ks);
-                                const uint64_t db = make_smem_desc<tc::LAYOUT>(smem_u32(sm.b[s]) + adv);
-                                const uint32_t accf = (kb | ks | part) ? 1u : 0u;
-                                if (l == 0) {
-                                    mma_ss(tacc, make_smem_desc<tc::LAYOUT>(smem_u32(sm.a_hi + kb * tc::ABLK) + adv), db, idesc, accf);
-                                    if (part == 0) mma_ss(tacc, make_smem_desc<tc::LAYOUT>(smem_u32(sm.a_lo + kb * tc::ABLK) + adv), db, idesc, 1u);
-                                } else {
-                                    const uint32_t col = (uint32_t)(kb * 16 + ks * 8);
-                                    mma_ts(tacc, t_ahi + col, db, idesc, accf);
-                                    if (part == 0) mma_ts(tacc, t_alo + col, db, idesc, 1u);
-                                }
+                            const uint32_t bl = b0_lo + s * (IMG >> 4);
+                            if (l == 0) {
+                                mma_ss2(tacc, akb_hi, hiw, bl, hiw, idesc, kb ? 1u : 0u);
+                                mma_ss2(tacc, akb_lo, hiw, bl, hiw, idesc, 1u);
+                                mma_ss2(tacc, akb_hi + KADV, hiw, bl + KADV, hiw, idesc, 1u);
+                                mma_ss2(tacc, akb_lo + KADV, hiw, bl + KADV, hiw, idesc, 1u);
+                            } else {
+                                mma_ts2(tacc, t_ahi + tcol, bl, hiw, idesc, kb ? 1u : 0u);
+                                mma_ts2(tacc, t_alo + tcol, bl, hiw, idesc, 1u);
+                                mma_ts2(tacc, t_ahi + tcol + 8u, bl + KADV, hiw, idesc, 1u);
+                                mma_ts2(tacc, t_alo + tcol + 8u, bl + KADV, hiw, idesc, 1u);
+                            }
+                            mma_commit(&sm.bar_empty[s]);
+                            ++n;
+                        }
+                        {
+                            const uint32_t s = n & (NSTAGE - 1), ph = (n >> 2) & 1u;
+                            if (!mbar_wait(&sm.bar_full[s], ph, p.err, 23)) { ok = false; break; }
+                            tc_fence_after();
+                            const uint32_t bl = b0_lo + s * (IMG >> 4);
+                            if (l == 0) {
+                                mma_ss2(tacc, akb_hi, hiw, bl, hiw, idesc, 1u);
+                                mma_ss2(tacc, akb_hi + KADV, hiw, bl + KADV, hiw, idesc, 1u);
+                            } else {
+                                mma_ts2(tacc, t_ahi + tcol, bl, hiw, idesc, 1u);
+                                mma_ts2(tacc, t_ahi + tcol + 8u, bl + KADV, hiw, idesc, 1u);
                             }
                             mma_commit(&sm.bar_empty[s]);
                             ++n;
@@ -1180,6 +1224,7 @@ extern "C" int pnb_shade_forward_tc(const pnb_query_t* q, const pnb_points_t* pt
     constexpr size_t kSmemMax = 232448;   // 227 KB opt-in limit per block on sm_100
     const size_t smem_tc = sizeof(tc::Smem) + 128, smem_tc3 = sizeof(tc3::Smem) + 128, smem_cb = sizeof(cb::Smem),
                  smem_ctc = sizeof(ctc::Smem) + 128;
+    static_assert((tc3::NSTAGE & (tc3::NSTAGE - 1)) == 0 && tc3::NSTAGE == 4, "issuer assumes a 4-stage ring");
     static_assert(sizeof(tc::Smem) + 128 <= kSmemMax && sizeof(tc3::Smem) + 128 <= kSmemMax && sizeof(ctc::Smem) + 128 <= kSmemMax &&
                   sizeof(cb::Smem) <= kSmemMax, "shared-memory carve-out exceeds the sm_100 per-block limit");
     if (!configured) {

@@ -138,6 +138,34 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* v) {
                  : "memory");
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// ---- lean issue path: the single issuing thread must spend < ~25 instructions per MMA (128-160 cycles each), so
+// descriptors are split into a constant high word and a low word that only needs an integer add per k-step.
+//   low word  = (smem_addr >> 4) & 0x3fff | (LBO >> 4) << 16        high word = (SBO >> 4) | 1 << 14 | layout << 29
+template <int LAYOUT>
+__device__ __forceinline__ uint32_t desc_lo(uint32_t smem_addr) {
+    return ((smem_addr >> 4) & 0x3fffu) | ((LAYOUT == LAYOUT_NONE ? 128u : 16u) >> 4) << 16;
+}
+template <int LAYOUT>
+__device__ __forceinline__ constexpr uint32_t desc_hi() {
+    return ((LAYOUT == LAYOUT_SW128 ? 1024u : 512u) >> 4) | (1u << 14) | ((uint32_t)LAYOUT << 29);
+}
+template <int LAYOUT>
+__device__ __forceinline__ constexpr uint32_t kstep_adv16() { return LAYOUT == LAYOUT_NONE ? 16u : 2u; }   // in 16-byte units
+__device__ __forceinline__ void mma_ss2(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
+                                        uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tmov.b64 da, {%1, %2};\n\tmov.b64 db, {%3, %4};\n\tsetp.ne.b32 p, %6, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}" ::"r"(d_tmem),
+        "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void mma_ts2(uint32_t d_tmem, uint32_t a_tmem, uint32_t b_lo, uint32_t b_hi, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 db;\n\tmov.b64 db, {%2, %3};\n\tsetp.ne.b32 p, %5, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], db, %4, p;\n\t}" ::"r"(d_tmem),
+        "r"(a_tmem), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
 // all previously issued MMAs of this thread -> arrive(1) on the mbarrier when complete
 __device__ __forceinline__ void mma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");

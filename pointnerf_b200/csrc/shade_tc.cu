@@ -413,7 +413,7 @@ __device__ __forceinline__ void prof_add(int* err, int slot, long long cyc) {
 #define PNB_TIMED_WAIT(slot, expr) [&]() { long long _t0 = clock64(); bool _r = (expr); prof_add(p.err, slot, clock64() - _t0); return _r; }()
 
 namespace tc3 {
-constexpr int NEPI = 256, NBUILD = 128, NTHR = 448;
+constexpr int NEPI_WARPS = 16, NEPI = NEPI_WARPS * 32, NBUILD = 128, NTHR = NEPI + NBUILD + 64;   // 704 threads
 constexpr int NSTAGE = 4;
 constexpr int XE = 128 * 32;            // bytes of one [128 x 16] bf16 extras operand (SBO = 256)
 struct Smem {
@@ -466,7 +466,8 @@ __global__ void __launch_bounds__(tc3::NTHR, 1) k_shade_tc3(ShadeTcParams p) {
         mbar_fence_init();
         if (blockIdx.x == 0 && q.counters[PNB_QC_N_VALID] > p.hbar_cap) atomicExch(p.err, 9);
     }
-    if (warp == 13) tmem_alloc<512>(&sm.tmem_base);
+    constexpr int W_BUILD = tc3::NEPI_WARPS, W_LOAD = W_BUILD + 4, W_ISSUE = W_LOAD + 1;
+    if (warp == W_ISSUE) tmem_alloc<512>(&sm.tmem_base);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -474,7 +475,7 @@ __global__ void __launch_bounds__(tc3::NTHR, 1) k_shade_tc3(ShadeTcParams p) {
     const uint32_t t_ahi = tacc + 256u, t_alo = tacc + 384u;
     const long long _tk0 = clock64();
 
-    if (warp == 12) {
+    if (warp == W_LOAD) {
         // ============================================================ loader
         if (lane == 0) {
             const uint32_t total = (uint32_t)my_tiles * IMGS_PER_TILE;
@@ -485,7 +486,7 @@ __global__ void __launch_bounds__(tc3::NTHR, 1) k_shade_tc3(ShadeTcParams p) {
                 bulk_g2s(sm.b[s], p.wimg + (size_t)(n % IMGS_PER_TILE) * IMG, IMG, &sm.bar_full[s]);
             }
         }
-    } else if (warp == 13) {
+    } else if (warp == W_ISSUE) {
         // ============================================================ MMA issuer (lean: ~15 instructions per MMA)
         if (lane == 0) {
             const uint32_t idesc = make_idesc_bf16(128, 256);
@@ -558,14 +559,14 @@ __global__ void __launch_bounds__(tc3::NTHR, 1) k_shade_tc3(ShadeTcParams p) {
                 }
             }
         }
-    } else if (warp >= 8) {
+    } else if (warp >= W_BUILD) {
         // ============================================================ builders: one thread per pair row
-        const int row = (warp - 8) * 32 + lane;
+        const int row = (warp - W_BUILD) * 32 + lane;
         const int si = row >> 3, k = row & 7;
         bool ok = true;
         for (int t = 0; t < my_tiles && ok; ++t) {
             const int tile = (int)blockIdx.x + t * (int)gridDim.x;
-            if (t > 0 && !(lane == 0 && warp == 8 ? PNB_TIMED_WAIT(4, mbar_wait(&sm.bar_a1_free, (uint32_t)(t - 1) & 1u, p.err, 16)) : mbar_wait(&sm.bar_a1_free, (uint32_t)(t - 1) & 1u, p.err, 16))) { ok = false; break; }
+            if (t > 0 && !(lane == 0 && warp == W_BUILD ? PNB_TIMED_WAIT(4, mbar_wait(&sm.bar_a1_free, (uint32_t)(t - 1) & 1u, p.err, 16)) : mbar_wait(&sm.bar_a1_free, (uint32_t)(t - 1) & 1u, p.err, 16))) { ok = false; break; }
             const long long _tb0 = clock64();
             const int vi = tile * TSAMP + si;
             int pidx = -1;
@@ -654,11 +655,11 @@ __global__ void __launch_bounds__(tc3::NTHR, 1) k_shade_tc3(ShadeTcParams p) {
             }
             fence_proxy_async();
             mbar_arrive(&sm.bar_a1_ready);
-            if (lane == 0 && warp == 8) prof_add(p.err, 5, clock64() - _tb0);
+            if (lane == 0 && warp == W_BUILD) prof_add(p.err, 5, clock64() - _tb0);
         }
     } else {
-        // ============================================================ epilogue warps 0..7
-        const int quad = warp & 3, half = warp >> 2;
+        // ============================================================ epilogue warps 0..15: 64 columns per thread
+        const int quad = warp & 3, part = warp >> 2;
         const int erow = quad * 32 + lane;
         const uint32_t tlane = (uint32_t)(quad * 32) << 16;
         uint32_t n_acc = 0;
@@ -671,15 +672,15 @@ __global__ void __launch_bounds__(tc3::NTHR, 1) k_shade_tc3(ShadeTcParams p) {
                 tc_fence_after();
                 if (l < 3) {
                     const float* bias = p.bias[l];
-#pragma unroll 1
-                    for (int ch = 0; ch < 4; ++ch) {
-                        const int c0 = half * 128 + ch * 32;
-                        uint32_t v[32];
-                        tmem_ld32(tacc + tlane + (uint32_t)c0, v);
-                        tmem_ld_wait();
-                        uint32_t hh[16], ll[16];
 #pragma unroll
-                        for (int e = 0; e < 16; ++e) {
+                    for (int ch = 0; ch < 4; ++ch) {
+                        const int c0 = part * 64 + ch * 16;
+                        uint32_t v[16];
+                        tmem_ld16(tacc + tlane + (uint32_t)c0, v);
+                        tmem_ld_wait();
+                        uint32_t hh[8], ll[8];
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) {
                             float2 bb = __ldg(reinterpret_cast<const float2*>(bias + c0) + e);
                             float y0 = __uint_as_float(v[2 * e]) + bb.x, y1 = __uint_as_float(v[2 * e + 1]) + bb.y;
                             y0 = fmaxf(y0, LEAKY * y0); y1 = fmaxf(y1, LEAKY * y1);
@@ -687,9 +688,7 @@ __global__ void __launch_bounds__(tc3::NTHR, 1) k_shade_tc3(ShadeTcParams p) {
                         }
                         const uint32_t colp = (uint32_t)(c0 >> 1);
                         tmem_st8(t_ahi + tlane + colp, hh);
-                        tmem_st8(t_ahi + tlane + colp + 8u, hh + 8);
                         tmem_st8(t_alo + tlane + colp, ll);
-                        tmem_st8(t_alo + tlane + colp + 8u, ll + 8);
                     }
                     tmem_st_wait();
                     tc_fence_before();
@@ -700,44 +699,57 @@ __global__ void __launch_bounds__(tc3::NTHR, 1) k_shade_tc3(ShadeTcParams p) {
                     const int sidx = tile * TSAMP + (erow >> 3);
                     const bool swrite = sidx < n_valid;
                     const float* bias = p.bias[3];
+                    const int j8 = lane & 7;
                     float apart = 0.f;
-#pragma unroll 1
-                    for (int ch = 0; ch < 4; ++ch) {
-                        const int c0 = half * 128 + ch * 32;
-                        uint32_t v[32];
-                        tmem_ld32(tacc + tlane + (uint32_t)c0, v);
-                        tmem_ld_wait();
-                        float mine[4];
 #pragma unroll
-                        for (int e = 0; e < 32; ++e) {
+                    for (int ch = 0; ch < 4; ++ch) {
+                        const int c0 = part * 64 + ch * 16;
+                        uint32_t v[16];
+                        tmem_ld16(tacc + tlane + (uint32_t)c0, v);
+                        tmem_ld_wait();
+                        float z[16];
+#pragma unroll
+                        for (int e = 0; e < 16; ++e) {
                             float y = __uint_as_float(v[e]) + __ldg(bias + c0 + e);
                             y = fmaxf(y, LEAKY * y);
                             apart = fmaf(y, __ldg(p.wa + c0 + e), apart);
-                            float z = y * wrow;
-                            z += __shfl_xor_sync(0xffffffffu, z, 1);
-                            z += __shfl_xor_sync(0xffffffffu, z, 2);
-                            z += __shfl_xor_sync(0xffffffffu, z, 4);
-                            if ((e & 7) == (lane & 7)) mine[e >> 3] = z;
+                            z[e] = y * wrow;
                         }
-                        if (swrite) {
-                            float* dst = p.hbar + (size_t)sidx * 256 + c0 + (lane & 7);
+                        // reduce-scatter over the 8 rows (lanes) of a sample: 16 -> 8 -> 4 -> 2 columns per lane
+                        float r8[8], r4[4], r2[2];
+                        const bool b4 = lane & 4, b2 = lane & 2, b1 = lane & 1;
 #pragma unroll
-                            for (int g = 0; g < 4; ++g) dst[8 * g] = mine[g];
+                        for (int i = 0; i < 8; ++i) {
+                            float send = b4 ? z[i] : z[i + 8], keep = b4 ? z[i + 8] : z[i];
+                            r8[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
                         }
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            float send = b2 ? r8[i] : r8[i + 4], keep = b2 ? r8[i + 4] : r8[i];
+                            r4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+                        }
+#pragma unroll
+                        for (int i = 0; i < 2; ++i) {
+                            float send = b1 ? r4[i] : r4[i + 2], keep = b1 ? r4[i + 2] : r4[i];
+                            r2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 1);
+                        }
+                        if (swrite) *reinterpret_cast<float2*>(p.hbar + (size_t)sidx * 256 + c0 + 2 * j8) = make_float2(r2[0], r2[1]);
                     }
                     tc_fence_before();
                     mbar_arrive(&sm.bar_at_ready);          // accumulator drained: the next tile's layer 1 may start
                     if (tid == 0) prof_add(p.err, 8, clock64() - _te0);
-                    sm.alpha_part[half][erow] = apart;
+                    if (part < 2) sm.alpha_part[part][erow] = apart;
                     named_bar_sync(1, tc3::NEPI);
-                    if (half == 0) {
+                    if (part >= 2) atomicAdd(&sm.alpha_part[part - 2][erow], apart);
+                    named_bar_sync(1, tc3::NEPI);
+                    if (part == 0) {
                         float a = sm.alpha_part[0][erow] + sm.alpha_part[1][erow] + __ldg(p.ba) - 1.0f;
                         float sp = a > 20.f ? a : log1pf(expf(a));
-                        float z = sp * wrow;
-                        z += __shfl_xor_sync(0xffffffffu, z, 1);
-                        z += __shfl_xor_sync(0xffffffffu, z, 2);
-                        z += __shfl_xor_sync(0xffffffffu, z, 4);
-                        if ((lane & 7) == 0 && swrite) p.sigma[sidx] = z;
+                        float zz = sp * wrow;
+                        zz += __shfl_xor_sync(0xffffffffu, zz, 1);
+                        zz += __shfl_xor_sync(0xffffffffu, zz, 2);
+                        zz += __shfl_xor_sync(0xffffffffu, zz, 4);
+                        if (j8 == 0 && swrite) p.sigma[sidx] = zz;
                     }
                     named_bar_sync(1, tc3::NEPI);
                 }
@@ -747,7 +759,7 @@ __global__ void __launch_bounds__(tc3::NTHR, 1) k_shade_tc3(ShadeTcParams p) {
     if (tid == 0) prof_add(p.err, 9, clock64() - _tk0);
     tc_fence_before();
     __syncthreads();
-    if (warp == 13) tmem_dealloc<512>(tacc);
+    if (warp == W_ISSUE) tmem_dealloc<512>(tacc);
 }
 
 // ------------------------------------------------------------------------------------------ weight packing

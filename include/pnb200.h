@@ -188,7 +188,8 @@ size_t pnb_shade_tc_bytes(int max_valid_samples);
 int pnb_shade_forward_tc(const pnb_query_t* q, const pnb_points_t* pts, const pnb_mlp_t* mlp, const void* d_packed,
                          const pnb_shade_opts_t* opts, float* d_sigma_rgb, void* ws, size_t ws_bytes,
                          int max_valid_samples,
-                         int stage_mask /* 1 pair MLPs, 2 colour branch, +4 TS-form pair pipeline, +8 colour branch on tcgen05 */,
+                         int stage_mask /* 1 pair MLPs, 2 colour branch, +4 TS-form pair pipeline (v3), +8 colour branch on tcgen05,
+                                           +16 TMEM ping-pong pair pipeline (v4) */,
                          int* d_err, pnb_stream_t stream);
 
 /* ---- backward (per-scene optimisation batches) ----

@@ -5,7 +5,7 @@ import torch
 from pointnerf_b200 import harness, scene
 dev = torch.device("cuda:0")
 cfg = scene.CONFIGS["lego_render"]
-net, pts, opt = harness.build_model(cfg, dev, alpha_bias=3.0)
+net, pts, opt = harness.build_model(cfg, dev, alpha_bias=3.0, pnb_tc_version=int(os.environ.get("PNB_TC_VERSION", "3")))
 rays = scene.make_rays(cfg)
 rd = rays["raydir"].to(dev)
 for i in range(3):

@@ -968,7 +968,7 @@ struct Smem {
     unsigned char xe_lo[2][tc3::XE];
     float wc[2][tc::TM];
     float alpha_part[2][tc::TM];
-    uint64_t bar_full[NSTAGE], bar_empty[NSTAGE], bar_a1_ready, bar_a1_free, bar_acc_full[2], bar_at_ready[2];
+    uint64_t bar_full[NSTAGE], bar_empty[NSTAGE], bar_a1_ready, bar_a1_free, bar_acc_full[2], bar_at_ready[2], bar_drain[2];
     uint32_t tmem_base;
 };
 }  // namespace tc4
@@ -988,7 +988,7 @@ __global__ void __launch_bounds__(tc4::NTHR, 1) k_shade_tc4(ShadeTcParams p) {
         for (int s = 0; s < tc4::NSTAGE; ++s) { mbar_init(&sm.bar_full[s], 1); mbar_init(&sm.bar_empty[s], 1); }
         mbar_init(&sm.bar_a1_ready, tc4::NBUILD);
         mbar_init(&sm.bar_a1_free, 1);
-        for (int h = 0; h < 2; ++h) { mbar_init(&sm.bar_acc_full[h], 1); mbar_init(&sm.bar_at_ready[h], tc4::NEPI_H); }
+        for (int h = 0; h < 2; ++h) { mbar_init(&sm.bar_acc_full[h], 1); mbar_init(&sm.bar_at_ready[h], tc4::NEPI_H); mbar_init(&sm.bar_drain[h], tc4::NEPI_H); }
         mbar_fence_init();
         if (blockIdx.x == 0 && q.counters[PNB_QC_N_VALID] > p.hbar_cap) atomicExch(p.err, 9);
     }
@@ -1031,8 +1031,9 @@ __global__ void __launch_bounds__(tc4::NTHR, 1) k_shade_tc4(ShadeTcParams p) {
                     // every MMA of the previous layer (global order) must have completed before its A region is re-used
                     if (t > 0 || l > 0) { if (!PNB_TIMED_WAIT(2, mbar_wait(&sm.bar_acc_full[1], c_acc1 & 1u, p.err, 32))) { ok = false; break; } ++c_acc1; }
                     if (l == 0) { if (!PNB_TIMED_WAIT(1, mbar_wait(&sm.bar_a1_ready, (uint32_t)t & 1u, p.err, 33))) { ok = false; break; } }
-                    if (l == 1 && t > 0) {     // region P was last read by the final epilogue of the previous tile
-                        for (int h = 0; h < 2 && ok; ++h) { if (!PNB_TIMED_WAIT(2, mbar_wait(&sm.bar_at_ready[h], c_at[h] & 1u, p.err, 34))) ok = false; ++c_at[h]; }
+                    if (l == 1 && t > 0) {     // region P was last read by the final epilogue of the previous tile.  Own barrier:
+                        // bar_at_ready may complete again (layer-1 packing of THIS tile) before this thread gets here.
+                        for (int h = 0; h < 2 && ok; ++h) { if (!PNB_TIMED_WAIT(2, mbar_wait(&sm.bar_drain[h], (uint32_t)(t - 1) & 1u, p.err, 34))) ok = false; }
                         if (!ok) break;
                     }
                     tc_fence_after();
@@ -1187,7 +1188,7 @@ __global__ void __launch_bounds__(tc4::NTHR, 1) k_shade_tc4(ShadeTcParams p) {
                         if (swrite) *reinterpret_cast<float2*>(p.hbar + (size_t)sidx * 256 + c0 + 2 * j8) = make_float2(r2[0], r2[1]);
                     }
                     tc_fence_before();
-                    mbar_arrive(&sm.bar_at_ready[h]);          // this accumulator half is drained
+                    mbar_arrive(&sm.bar_drain[h]);             // this accumulator half is drained
                     if ((tid & 255) == 0) prof_add(p.err, 8, clock64() - _te0);
                     // alpha branch: 4 partial dot products per row (2 halves x 2 parts) -> two slots, one add each
                     if (h == 0) sm.alpha_part[part][erow] = apart;

@@ -316,9 +316,9 @@ def main():
             _lib.check(l.pnb_shade_forward_tc(_lib.C.byref(q.desc), _lib.C.byref(ptsd), _lib.C.byref(mlp), net._mlp.packed.data_ptr(),
                                               _lib.C.byref(o), net._sigma_rgb.data_ptr(), net._tc_ws.data_ptr(), net._tc_ws.numel(),
                                               net._max_valid, mask, net._err.data_ptr(), stream), "pnb_shade_forward_tc")
-        shade_avg = time_kernel(lambda: tc(1 | (net.tc_mask & 20)))
+        shade_avg = time_kernel(lambda: tc(1 | (net.tc_mask & 52)))
         color_avg = time_kernel(lambda: tc(2 | (net.tc_mask & 8)))
-        kname = ("k_shade_tc4" if net.tc_mask & 16 else "k_shade_tc3" if net.tc_mask & 4 else "k_shade_tc") + " (tcgen05 BF16x3 pair MLPs 284-256-256 | 263-256-256 + alpha + K-reduction)"
+        kname = ("k_shade_tc5" if net.tc_mask & 32 else "k_shade_tc4" if net.tc_mask & 16 else "k_shade_tc3" if net.tc_mask & 4 else "k_shade_tc") + " (tcgen05 BF16x3 pair MLPs 284-256-256 | 263-256-256 + alpha + K-reduction)"
         kflops = FLOPS_PER_PAIR * qc["n_pairs"]
         net.check_errors()
 

@@ -1216,6 +1216,267 @@ __global__ void __launch_bounds__(tc4::NTHR, 1) k_shade_tc4(ShadeTcParams p) {
 }
 
 // =====================================================================================================================
+// v5: "TMEM role ping-pong", single N=256 pass per layer.  The two 256-column TMEM regions P and Q alternate between
+// accumulator and A operand: the epilogue converts the finished accumulator IN PLACE, 16 columns at a time, into the
+// packed bf16 operand of the next layer (8 columns hi | 8 columns lo), and signals each 16-column chunk on its own
+// mbarrier; the issuer starts the next layer's k-step g (K = 16g..16g+15, accumulating into the OTHER region) as soon
+// as chunk g is converted, so the tensor core runs layer l+1 right behind the epilogue of layer l.  The final
+// epilogue of a tile runs under layer 1 of the next tile.
+//      layer 1: A shared memory, acc Q      layer 2: A = Q, acc P      layer 3: A = P (+extras), acc Q      layer 4: A = Q, acc P
+// Warp roles (704 threads): 0-15 epilogue (quadrant = w & 3, chunk group j = w >> 2 handles chunks j, j+4, j+8, j+12),
+// 16-19 builders, 20 loader, 21 issuer.
+namespace tc5 {
+constexpr int NEPI = 512, NBUILD = 128, NTHR = 704;
+constexpr int NSTAGE = 4;
+struct Smem {
+    unsigned char a_hi[tc::NKB_MAX * tc::ABLK];
+    unsigned char a_lo[tc::NKB_MAX * tc::ABLK];
+    unsigned char b[NSTAGE][tc::IMG];
+    unsigned char xe_hi[2][tc3::XE];
+    unsigned char xe_lo[2][tc3::XE];
+    float wc[2][tc::TM];
+    float alpha_part[2][tc::TM];
+    uint64_t bar_full[NSTAGE], bar_empty[NSTAGE], bar_a1_ready, bar_a1_free, bar_acc_full, bar_drain, bar_chunk[16];
+    uint32_t tmem_base;
+};
+}  // namespace tc5
+
+__global__ void __launch_bounds__(tc5::NTHR, 1) k_shade_tc5(ShadeTcParams p) {
+    using namespace tc;
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    tc5::Smem& sm = *reinterpret_cast<tc5::Smem*>(smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u));
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const pnb_query_t& q = p.q;
+    const int n_valid = min(q.counters[PNB_QC_N_VALID], p.hbar_cap);
+    const int n_tiles = (n_valid + TSAMP - 1) / TSAMP;
+    const int my_tiles = n_tiles > (int)blockIdx.x ? (n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+    constexpr int W_BUILD = 16, W_LOAD = 20, W_ISSUE = 21;
+
+    if (tid == 0) {
+        for (int s = 0; s < tc5::NSTAGE; ++s) { mbar_init(&sm.bar_full[s], 1); mbar_init(&sm.bar_empty[s], 1); }
+        mbar_init(&sm.bar_a1_ready, tc5::NBUILD);
+        mbar_init(&sm.bar_a1_free, 1);
+        mbar_init(&sm.bar_acc_full, 1);
+        mbar_init(&sm.bar_drain, tc5::NEPI);
+        for (int c = 0; c < 16; ++c) mbar_init(&sm.bar_chunk[c], 128);
+        mbar_fence_init();
+        if (blockIdx.x == 0 && q.counters[PNB_QC_N_VALID] > p.hbar_cap) atomicExch(p.err, 9);
+    }
+    if (warp == W_ISSUE) tmem_alloc<512>(&sm.tmem_base);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tP = sm.tmem_base, tQ = sm.tmem_base + 256u;
+    const long long _tk0 = clock64();
+
+    if (warp == W_LOAD) {
+        // ============================================================ loader
+        if (lane == 0) {
+            const uint32_t total = (uint32_t)my_tiles * IMGS_PER_TILE;
+            for (uint32_t n = 0; n < total; ++n) {
+                const uint32_t s = n & (tc5::NSTAGE - 1), ph = (n >> 2) & 1u;
+                if (!PNB_TIMED_WAIT(0, mbar_wait(&sm.bar_empty[s], ph ^ 1u, p.err, 41))) break;
+                mbar_arrive_expect_tx(&sm.bar_full[s], IMG);
+                bulk_g2s(sm.b[s], p.wimg + (size_t)(n % IMGS_PER_TILE) * IMG, IMG, &sm.bar_full[s]);
+            }
+        }
+    } else if (warp == W_ISSUE) {
+        // ============================================================ MMA issuer
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc_bf16(128, 256);
+            const uint32_t hiw = desc_hi<LAYOUT>(), xe_hiw = (256u >> 4) | (1u << 14);
+            const uint32_t b0_lo = desc_lo<LAYOUT>(smem_u32(sm.b[0]));
+            const uint32_t ahi_lo = desc_lo<LAYOUT>(smem_u32(sm.a_hi)), alo_lo = desc_lo<LAYOUT>(smem_u32(sm.a_lo));
+            const uint32_t xeh_lo0 = desc_lo<LAYOUT_NONE>(smem_u32(sm.xe_hi[0])), xel_lo0 = desc_lo<LAYOUT_NONE>(smem_u32(sm.xe_lo[0]));
+            constexpr uint32_t KADV = kstep_adv16<LAYOUT>();
+            uint32_t n = 0;            // weight image counter
+            uint32_t c_acc = 0;        // completions of bar_acc_full consumed by this thread
+            uint32_t c_pack = 0;       // packing rounds (one per layer 1..3 epilogue) consumed on bar_chunk[*]
+            bool ok = true;
+            for (int t = 0; t < my_tiles && ok; ++t) {
+                const uint32_t xeh_lo = xeh_lo0 + (uint32_t)(t & 1) * (tc3::XE >> 4), xel_lo = xel_lo0 + (uint32_t)(t & 1) * (tc3::XE >> 4);
+                for (int l = 0; l < 4 && ok; ++l) {
+                    const uint32_t acc = (l & 1) ? tP : tQ;           // accumulator of this layer
+                    const uint32_t ab = (l & 1) ? tQ : tP;            // packed A operand of this layer (l >= 1)
+                    // all MMAs of the previous layer (global order) must be complete before their A region becomes this accumulator
+                    if (t > 0 || l > 0) { if (!PNB_TIMED_WAIT(2, mbar_wait(&sm.bar_acc_full, c_acc & 1u, p.err, 42))) { ok = false; break; } ++c_acc; }
+                    if (l == 0) { if (!PNB_TIMED_WAIT(1, mbar_wait(&sm.bar_a1_ready, (uint32_t)t & 1u, p.err, 43))) { ok = false; break; } }
+                    if (l == 1 && t > 0) { if (!PNB_TIMED_WAIT(2, mbar_wait(&sm.bar_drain, (uint32_t)(t - 1) & 1u, p.err, 44))) { ok = false; break; } }
+                    tc_fence_after();
+                    const int nkb = nkb_of(l);
+                    for (int kb = 0; kb < nkb && ok; ++kb) {
+                        if (l >= 1 && kb < 8) {       // chunks 2kb, 2kb+1 of the previous layer's output must be converted
+                            if (!PNB_TIMED_WAIT(2, mbar_wait(&sm.bar_chunk[2 * kb], c_pack & 1u, p.err, 45))) { ok = false; break; }
+                            if (!PNB_TIMED_WAIT(2, mbar_wait(&sm.bar_chunk[2 * kb + 1], c_pack & 1u, p.err, 45))) { ok = false; break; }
+                            tc_fence_after();
+                        }
+                        const uint32_t akb_hi = ahi_lo + (uint32_t)kb * (ABLK >> 4), akb_lo = alo_lo + (uint32_t)kb * (ABLK >> 4);
+                        const uint32_t tcol = ab + (uint32_t)(kb * 32);
+                        {   // ---- W_hi image
+                            const uint32_t s = n & (tc5::NSTAGE - 1), ph = (n >> 2) & 1u;
+                            if (!PNB_TIMED_WAIT(3, mbar_wait(&sm.bar_full[s], ph, p.err, 46))) { ok = false; break; }
+                            tc_fence_after();
+                            const uint32_t bl = b0_lo + s * (IMG >> 4);
+                            if (l == 0) {
+                                mma_ss2(acc, akb_hi, hiw, bl, hiw, idesc, kb ? 1u : 0u);
+                                mma_ss2(acc, akb_lo, hiw, bl, hiw, idesc, 1u);
+                                mma_ss2(acc, akb_hi + KADV, hiw, bl + KADV, hiw, idesc, 1u);
+                                mma_ss2(acc, akb_lo + KADV, hiw, bl + KADV, hiw, idesc, 1u);
+                            } else if (kb == 8) {
+                                mma_ss2(acc, xeh_lo, xe_hiw, bl, hiw, idesc, 1u);
+                                mma_ss2(acc, xel_lo, xe_hiw, bl, hiw, idesc, 1u);
+                            } else {
+                                mma_ts2(acc, tcol, bl, hiw, idesc, kb ? 1u : 0u);
+                                mma_ts2(acc, tcol + 8u, bl, hiw, idesc, 1u);
+                                mma_ts2(acc, tcol + 16u, bl + KADV, hiw, idesc, 1u);
+                                mma_ts2(acc, tcol + 24u, bl + KADV, hiw, idesc, 1u);
+                            }
+                            mma_commit(&sm.bar_empty[s]);
+                            ++n;
+                        }
+                        {   // ---- W_lo image
+                            const uint32_t s = n & (tc5::NSTAGE - 1), ph = (n >> 2) & 1u;
+                            if (!PNB_TIMED_WAIT(3, mbar_wait(&sm.bar_full[s], ph, p.err, 46))) { ok = false; break; }
+                            tc_fence_after();
+                            const uint32_t bl = b0_lo + s * (IMG >> 4);
+                            if (l == 0) {
+                                mma_ss2(acc, akb_hi, hiw, bl, hiw, idesc, 1u);
+                                mma_ss2(acc, akb_hi + KADV, hiw, bl + KADV, hiw, idesc, 1u);
+                            } else if (kb == 8) {
+                                mma_ss2(acc, xeh_lo, xe_hiw, bl, hiw, idesc, 1u);
+                            } else {
+                                mma_ts2(acc, tcol, bl, hiw, idesc, 1u);
+                                mma_ts2(acc, tcol + 16u, bl + KADV, hiw, idesc, 1u);
+                            }
+                            mma_commit(&sm.bar_empty[s]);
+                            ++n;
+                        }
+                    }
+                    if (!ok) break;
+                    if (l >= 1) ++c_pack;
+                    mma_commit(&sm.bar_acc_full);
+                    if (l == 0) mma_commit(&sm.bar_a1_free);
+                }
+            }
+        }
+    } else if (warp >= W_BUILD) {
+        // ============================================================ builders: one thread per pair row
+        const int row = (warp - W_BUILD) * 32 + lane;
+        bool ok = true;
+        for (int t = 0; t < my_tiles && ok; ++t) {
+            const int tile = (int)blockIdx.x + t * (int)gridDim.x;
+            if (t > 0 && !(lane == 0 && warp == W_BUILD ? PNB_TIMED_WAIT(4, mbar_wait(&sm.bar_a1_free, (uint32_t)(t - 1) & 1u, p.err, 47)) : mbar_wait(&sm.bar_a1_free, (uint32_t)(t - 1) & 1u, p.err, 47))) { ok = false; break; }
+            const long long _tb0 = clock64();
+            build_pair_row(sm, p, tile, t, row, n_valid);
+            fence_proxy_async();
+            mbar_arrive(&sm.bar_a1_ready);
+            if (lane == 0 && warp == W_BUILD) prof_add(p.err, 5, clock64() - _tb0);
+        }
+    } else {
+        // ============================================================ epilogue warps 0..15
+        const int quad = warp & 3, grp = warp >> 2;            // chunk group: chunks grp, grp+4, grp+8, grp+12
+        const int erow = quad * 32 + lane;
+        const uint32_t tlane = (uint32_t)(quad * 32) << 16;
+        uint32_t n_acc = 0;
+        bool ok = true;
+        for (int t = 0; t < my_tiles && ok; ++t) {
+            const int tile = (int)blockIdx.x + t * (int)gridDim.x;
+            for (int l = 0; l < 4 && ok; ++l, ++n_acc) {
+                if (!(tid == 0 ? PNB_TIMED_WAIT(6, mbar_wait(&sm.bar_acc_full, n_acc & 1u, p.err, 48)) : mbar_wait(&sm.bar_acc_full, n_acc & 1u, p.err, 48))) { ok = false; break; }
+                const long long _te0 = clock64();
+                tc_fence_after();
+                const uint32_t accb = ((l & 1) ? tP : tQ) + tlane;
+                if (l < 3) {
+                    const float* bias = p.bias[l];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int g = grp + 4 * i, c0 = 16 * g;
+                        uint32_t v[16];
+                        tmem_ld16(accb + (uint32_t)c0, v);
+                        tmem_ld_wait();
+                        uint32_t hh[8], ll[8];
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) {
+                            float2 bb = __ldg(reinterpret_cast<const float2*>(bias + c0) + e);
+                            float y0 = __uint_as_float(v[2 * e]) + bb.x, y1 = __uint_as_float(v[2 * e + 1]) + bb.y;
+                            y0 = fmaxf(y0, LEAKY * y0); y1 = fmaxf(y1, LEAKY * y1);
+                            split_bf16x2(y0, y1, hh[e], ll[e]);
+                        }
+                        tmem_st8(accb + (uint32_t)c0, hh);               // in place: 8 columns hi | 8 columns lo
+                        tmem_st8(accb + (uint32_t)c0 + 8u, ll);
+                        tmem_st_wait();
+                        tc_fence_before();
+                        mbar_arrive(&sm.bar_chunk[g]);
+                    }
+                    if (tid == 0) prof_add(p.err, 7, clock64() - _te0);
+                } else {
+                    const float wrow = sm.wc[t & 1][erow];
+                    const int sidx = tile * TSAMP + (erow >> 3);
+                    const bool swrite = sidx < n_valid;
+                    const float* bias = p.bias[3];
+                    const int j8 = lane & 7;
+                    float apart = 0.f;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int c0 = 16 * (grp + 4 * i);
+                        uint32_t v[16];
+                        tmem_ld16(accb + (uint32_t)c0, v);
+                        tmem_ld_wait();
+                        float z[16];
+#pragma unroll
+                        for (int e = 0; e < 16; ++e) {
+                            float y = __uint_as_float(v[e]) + __ldg(bias + c0 + e);
+                            y = fmaxf(y, LEAKY * y);
+                            apart = fmaf(y, __ldg(p.wa + c0 + e), apart);
+                            z[e] = y * wrow;
+                        }
+                        float r8[8], r4[4], r2[2];
+                        const bool b4 = lane & 4, b2 = lane & 2, b1 = lane & 1;
+#pragma unroll
+                        for (int ii = 0; ii < 8; ++ii) {
+                            float send = b4 ? z[ii] : z[ii + 8], keep = b4 ? z[ii + 8] : z[ii];
+                            r8[ii] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+                        }
+#pragma unroll
+                        for (int ii = 0; ii < 4; ++ii) {
+                            float send = b2 ? r8[ii] : r8[ii + 4], keep = b2 ? r8[ii + 4] : r8[ii];
+                            r4[ii] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+                        }
+#pragma unroll
+                        for (int ii = 0; ii < 2; ++ii) {
+                            float send = b1 ? r4[ii] : r4[ii + 2], keep = b1 ? r4[ii + 2] : r4[ii];
+                            r2[ii] = keep + __shfl_xor_sync(0xffffffffu, send, 1);
+                        }
+                        if (swrite) *reinterpret_cast<float2*>(p.hbar + (size_t)sidx * 256 + c0 + 2 * j8) = make_float2(r2[0], r2[1]);
+                    }
+                    tc_fence_before();
+                    mbar_arrive(&sm.bar_drain);                // accumulator region P drained
+                    if (tid == 0) prof_add(p.err, 8, clock64() - _te0);
+                    if (grp < 2) sm.alpha_part[grp][erow] = apart;
+                    named_bar_sync(1, tc5::NEPI);
+                    if (grp >= 2) atomicAdd(&sm.alpha_part[grp - 2][erow], apart);
+                    named_bar_sync(1, tc5::NEPI);
+                    if (grp == 0) {
+                        float a = sm.alpha_part[0][erow] + sm.alpha_part[1][erow] + __ldg(p.ba) - 1.0f;
+                        float sp = a > 20.f ? a : log1pf(expf(a));
+                        float zz = sp * wrow;
+                        zz += __shfl_xor_sync(0xffffffffu, zz, 1);
+                        zz += __shfl_xor_sync(0xffffffffu, zz, 2);
+                        zz += __shfl_xor_sync(0xffffffffu, zz, 4);
+                        if (j8 == 0 && swrite) p.sigma[sidx] = zz;
+                    }
+                    named_bar_sync(1, tc5::NEPI);
+                }
+            }
+        }
+    }
+    if (tid == 0) prof_add(p.err, 9, clock64() - _tk0);
+    tc_fence_before();
+    __syncthreads();
+    if (warp == W_ISSUE) tmem_dealloc<512>(sm.tmem_base);
+}
+
+// =====================================================================================================================
 // Colour branch on the tensor cores: per 128 valid samples  [hbar(256) | PE4(view)(24)] -> 128 -> 128 -> 128 (tcgen05,
 // BF16x3) -> 3 (CUDA cores) -> sigmoid*1.002-0.001   (reference: point_aggregators.py:631-637, 269-273).
 // Layer 1 reads its operand from shared memory (SS), layers 2-3 from tensor memory (TS).  TMEM: accumulator cols
@@ -1528,7 +1789,8 @@ extern "C" int pnb_shade_forward_tc(const pnb_query_t* q, const pnb_points_t* pt
     // interleaved (non-swizzled) operand layout: 128-byte alignment of the carve-out is sufficient
     constexpr size_t kSmemMax = 232448;   // 227 KB opt-in limit per block on sm_100
     const size_t smem_tc = sizeof(tc::Smem) + 128, smem_tc3 = sizeof(tc3::Smem) + 128, smem_cb = sizeof(cb::Smem),
-                 smem_ctc = sizeof(ctc::Smem) + 128, smem_tc4 = sizeof(tc4::Smem) + 128;
+                 smem_ctc = sizeof(ctc::Smem) + 128, smem_tc4 = sizeof(tc4::Smem) + 128, smem_tc5 = sizeof(tc5::Smem) + 128;
+    static_assert(sizeof(tc5::Smem) + 128 <= kSmemMax, "v5 shared-memory carve-out exceeds the per-block limit");
     static_assert(sizeof(tc4::Smem) + 128 <= kSmemMax, "v4 shared-memory carve-out exceeds the per-block limit");
     static_assert((tc3::NSTAGE & (tc3::NSTAGE - 1)) == 0 && tc3::NSTAGE == 4, "issuer assumes a 4-stage ring");
     static_assert(sizeof(tc::Smem) + 128 <= kSmemMax && sizeof(tc3::Smem) + 128 <= kSmemMax && sizeof(ctc::Smem) + 128 <= kSmemMax &&
@@ -1536,6 +1798,7 @@ extern "C" int pnb_shade_forward_tc(const pnb_query_t* q, const pnb_points_t* pt
     if (!configured) {
         PNB_CHECK_CUDA(cudaFuncSetAttribute(k_shade_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tc));
         PNB_CHECK_CUDA(cudaFuncSetAttribute(k_shade_tc3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tc3));
+        PNB_CHECK_CUDA(cudaFuncSetAttribute(k_shade_tc5, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tc5));
         PNB_CHECK_CUDA(cudaFuncSetAttribute(k_shade_tc4, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tc4));
         PNB_CHECK_CUDA(cudaFuncSetAttribute(k_color_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_ctc));
         PNB_CHECK_CUDA(cudaFuncSetAttribute(k_color_branch, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cb));
@@ -1555,7 +1818,8 @@ extern "C" int pnb_shade_forward_tc(const pnb_query_t* q, const pnb_points_t* pt
     p.ba = mlp->b[4];
     p.hbar = hbar; p.sigma = sigma; p.hbar_cap = max_valid_samples; p.err = d_err;
     if (stage_mask & 1) {
-        if (stage_mask & 16) k_shade_tc4<<<n_sm, tc4::NTHR, smem_tc4, stream>>>(p);      // TMEM role ping-pong pipeline
+        if (stage_mask & 32) k_shade_tc5<<<n_sm, tc5::NTHR, smem_tc5, stream>>>(p);           // TMEM ping-pong, chunk-pipelined
+        else if (stage_mask & 16) k_shade_tc4<<<n_sm, tc4::NTHR, smem_tc4, stream>>>(p);      // TMEM ping-pong, N-half passes
         else if (stage_mask & 4) k_shade_tc3<<<n_sm, tc3::NTHR, smem_tc3, stream>>>(p);   // TS-form pipeline (A in tensor memory)
         else k_shade_tc<<<n_sm, tc::NTHR, smem_tc, stream>>>(p);
     }

@@ -289,7 +289,7 @@ def _init_state(mod):
     # tcgen05 pipeline variant: 4 = TMEM role ping-pong (epilogues under the MMAs), 3 = A operand of layers 2-4 in tensor
     # memory + overlapped operand builders (default), 2 = serialized shared-memory pipeline
     _v = int(getattr(opt, "pnb_tc_version", 3))
-    mod.tc_mask = 3 | (12 if _v == 3 else 0) | (8 + 16 if _v == 4 else 0)
+    mod.tc_mask = 3 | (12 if _v == 3 else 0) | (8 + 16 if _v == 4 else 0) | (8 + 32 if _v == 5 else 0)
     mod.last = None
     mod._pnb_ready = True
 

@@ -318,7 +318,7 @@ def main():
                                               net._max_valid, mask, net._err.data_ptr(), stream), "pnb_shade_forward_tc")
         shade_avg = time_kernel(lambda: tc(1 | (net.tc_mask & 52)))
         color_avg = time_kernel(lambda: tc(2 | (net.tc_mask & 8)))
-        kname = ("k_shade_tc5" if net.tc_mask & 32 else "k_shade_tc4" if net.tc_mask & 16 else "k_shade_tc3" if net.tc_mask & 4 else "k_shade_tc") + " (tcgen05 BF16x3 pair MLPs 284-256-256 | 263-256-256 + alpha + K-reduction)"
+        kname = ("k_shade_tc5" if net.tc_mask & 32 else "k_shade_tc3" if net.tc_mask & 4 else "k_shade_tc") + " (tcgen05 BF16x3 pair MLPs 284-256-256 | 263-256-256 + alpha + K-reduction)"
         kflops = FLOPS_PER_PAIR * qc["n_pairs"]
         net.check_errors()
 

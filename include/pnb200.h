@@ -189,7 +189,7 @@ int pnb_shade_forward_tc(const pnb_query_t* q, const pnb_points_t* pts, const pn
                          const pnb_shade_opts_t* opts, float* d_sigma_rgb, void* ws, size_t ws_bytes,
                          int max_valid_samples,
                          int stage_mask /* 1 pair MLPs, 2 colour branch, +4 TS-form pair pipeline (v3), +8 colour branch on tcgen05,
-                                           +16 TMEM ping-pong pair pipeline, N-half passes (v4), +32 chunk-pipelined (v5) */,
+                                           +32 chunk-pipelined TMEM ping-pong pair pipeline (v5) */,
                          int* d_err, pnb_stream_t stream);
 
 /* ---- backward (per-scene optimisation batches) ----

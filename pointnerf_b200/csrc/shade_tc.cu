@@ -59,7 +59,6 @@ struct ShadeTcParams {
     pnb_points_t pts;
     pnb_shade_opts_t o;
     const unsigned char* wimg;   // packed weight images (N = 256 per image)
-    const unsigned char* wimg4;  // packed per N-half ([128 x 32] images) for the v4 pipeline
     const float* bias[4];
     const float* wa;             // alpha_branch.0 weight [256]
     const float* ba;             // alpha_branch.0 bias [1]
@@ -946,276 +945,6 @@ __global__ void __launch_bounds__(cb::NTHREADS, 1) k_color_branch(ColorParams p)
 }
 
 // =====================================================================================================================
-// v4: "TMEM role ping-pong".  Every layer is computed as two N=128 passes into two 128-column accumulators; the
-// epilogue of a pass converts its accumulator IN PLACE into the packed bf16 hi/lo A operand of the next layer
-// (16 fp32 columns -> 8 columns hi | 8 columns lo), so the two 256-column TMEM regions P and Q alternate between
-// "accumulators" and "A operand" from layer to layer:
-//      layer 1: A shared memory, acc Q      layer 2: A = Q, acc P      layer 3: A = P (+extras), acc Q      layer 4: A = Q, acc P
-// The epilogue of pass (l, half 0) runs under the MMAs of pass (l, half 1); the epilogue of (l, half 1) runs under the
-// first half of the K loop of pass (l+1, half 0); the final epilogue of a tile runs under layer 1 of the next tile.
-// Warp roles (704 threads): 0-7 epilogue of half 0, 8-15 epilogue of half 1, 16-19 builders, 20 loader, 21 issuer.
-namespace tc4 {
-constexpr int NEPI_H = 256, NBUILD = 128, NTHR = 704;
-constexpr int NSTAGE = 8;
-constexpr int IMG = 128 * 64;                           // [128 x 32] bf16 weight image (one N-half of a K block)
-constexpr int IMGS_PER_TILE = 4 * tc::NBLK_TOTAL;       // 2 halves x (hi, lo) x 34 K blocks
-__host__ __device__ constexpr int img_base(int l) { return 2 * tc::img_base(l); }   // in (half, K block) units
-struct Smem {
-    unsigned char a_hi[tc::NKB_MAX * tc::ABLK];
-    unsigned char a_lo[tc::NKB_MAX * tc::ABLK];
-    unsigned char b[NSTAGE][IMG];
-    unsigned char xe_hi[2][tc3::XE];
-    unsigned char xe_lo[2][tc3::XE];
-    float wc[2][tc::TM];
-    float alpha_part[2][tc::TM];
-    uint64_t bar_full[NSTAGE], bar_empty[NSTAGE], bar_a1_ready, bar_a1_free, bar_acc_full[2], bar_at_ready[2], bar_drain[2];
-    uint32_t tmem_base;
-};
-}  // namespace tc4
-
-__global__ void __launch_bounds__(tc4::NTHR, 1) k_shade_tc4(ShadeTcParams p) {
-    using namespace tc;
-    extern __shared__ __align__(1024) unsigned char smem_raw[];
-    tc4::Smem& sm = *reinterpret_cast<tc4::Smem*>(smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u));
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const pnb_query_t& q = p.q;
-    const int n_valid = min(q.counters[PNB_QC_N_VALID], p.hbar_cap);
-    const int n_tiles = (n_valid + TSAMP - 1) / TSAMP;
-    const int my_tiles = n_tiles > (int)blockIdx.x ? (n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
-    constexpr int W_BUILD = 16, W_LOAD = 20, W_ISSUE = 21;
-
-    if (tid == 0) {
-        for (int s = 0; s < tc4::NSTAGE; ++s) { mbar_init(&sm.bar_full[s], 1); mbar_init(&sm.bar_empty[s], 1); }
-        mbar_init(&sm.bar_a1_ready, tc4::NBUILD);
-        mbar_init(&sm.bar_a1_free, 1);
-        for (int h = 0; h < 2; ++h) { mbar_init(&sm.bar_acc_full[h], 1); mbar_init(&sm.bar_at_ready[h], tc4::NEPI_H); mbar_init(&sm.bar_drain[h], tc4::NEPI_H); }
-        mbar_fence_init();
-        if (blockIdx.x == 0 && q.counters[PNB_QC_N_VALID] > p.hbar_cap) atomicExch(p.err, 9);
-    }
-    if (warp == W_ISSUE) tmem_alloc<512>(&sm.tmem_base);
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tP = sm.tmem_base, tQ = sm.tmem_base + 256u;
-    const long long _tk0 = clock64();
-
-    if (warp == W_LOAD) {
-        // ============================================================ loader
-        if (lane == 0) {
-            const uint32_t total = (uint32_t)my_tiles * tc4::IMGS_PER_TILE;
-            for (uint32_t n = 0; n < total; ++n) {
-                const uint32_t s = n & (tc4::NSTAGE - 1), ph = (n >> 3) & 1u;
-                if (!PNB_TIMED_WAIT(0, mbar_wait(&sm.bar_empty[s], ph ^ 1u, p.err, 31))) break;
-                mbar_arrive_expect_tx(&sm.bar_full[s], tc4::IMG);
-                bulk_g2s(sm.b[s], p.wimg4 + (size_t)(n % tc4::IMGS_PER_TILE) * tc4::IMG, tc4::IMG, &sm.bar_full[s]);
-            }
-        }
-    } else if (warp == W_ISSUE) {
-        // ============================================================ MMA issuer
-        if (lane == 0) {
-            const uint32_t idesc = make_idesc_bf16(128, 128);
-            const uint32_t hiw = desc_hi<LAYOUT>(), xe_hiw = (256u >> 4) | (1u << 14);
-            const uint32_t b0_lo = desc_lo<LAYOUT>(smem_u32(sm.b[0]));
-            const uint32_t ahi_lo = desc_lo<LAYOUT>(smem_u32(sm.a_hi)), alo_lo = desc_lo<LAYOUT>(smem_u32(sm.a_lo));
-            const uint32_t xeh_lo0 = desc_lo<LAYOUT_NONE>(smem_u32(sm.xe_hi[0])), xel_lo0 = desc_lo<LAYOUT_NONE>(smem_u32(sm.xe_lo[0]));
-            constexpr uint32_t KADV = kstep_adv16<LAYOUT>();
-            uint32_t n = 0;                       // weight image counter
-            uint32_t c_acc1 = 0;                  // completions of bar_acc_full[1] consumed by this thread
-            uint32_t c_at[2] = {0, 0};            // completions of bar_at_ready[h] consumed
-            bool ok = true;
-            for (int t = 0; t < my_tiles && ok; ++t) {
-                const uint32_t xeh_lo = xeh_lo0 + (uint32_t)(t & 1) * (tc3::XE >> 4), xel_lo = xel_lo0 + (uint32_t)(t & 1) * (tc3::XE >> 4);
-                for (int l = 0; l < 4 && ok; ++l) {
-                    const uint32_t accb = (l & 1) ? tP : tQ;          // accumulators of this layer
-                    const uint32_t ab = (l & 1) ? tQ : tP;            // A operand region of this layer (l >= 1)
-                    // every MMA of the previous layer (global order) must have completed before its A region is re-used
-                    if (t > 0 || l > 0) { if (!PNB_TIMED_WAIT(2, mbar_wait(&sm.bar_acc_full[1], c_acc1 & 1u, p.err, 32))) { ok = false; break; } ++c_acc1; }
-                    if (l == 0) { if (!PNB_TIMED_WAIT(1, mbar_wait(&sm.bar_a1_ready, (uint32_t)t & 1u, p.err, 33))) { ok = false; break; } }
-                    if (l == 1 && t > 0) {     // region P was last read by the final epilogue of the previous tile.  Own barrier:
-                        // bar_at_ready may complete again (layer-1 packing of THIS tile) before this thread gets here.
-                        for (int h = 0; h < 2 && ok; ++h) { if (!PNB_TIMED_WAIT(2, mbar_wait(&sm.bar_drain[h], (uint32_t)(t - 1) & 1u, p.err, 34))) ok = false; }
-                        if (!ok) break;
-                    }
-                    tc_fence_after();
-                    const int nkb = nkb_of(l);
-                    for (int h = 0; h < 2 && ok; ++h) {
-                        const uint32_t acc = accb + 128u * (uint32_t)h;
-                        for (int kb = 0; kb < nkb && ok; ++kb) {
-                            if (l >= 1 && h == 0 && (kb == 0 || kb == 4)) {   // K columns 0..127 / 128..255 of the packed A operand
-                                const int hh = kb >> 2;
-                                if (!PNB_TIMED_WAIT(2, mbar_wait(&sm.bar_at_ready[hh], c_at[hh] & 1u, p.err, 35))) { ok = false; break; }
-                                ++c_at[hh];
-                                tc_fence_after();
-                            }
-                            const uint32_t akb_hi = ahi_lo + (uint32_t)kb * (ABLK >> 4), akb_lo = alo_lo + (uint32_t)kb * (ABLK >> 4);
-                            const uint32_t tcol = ab + (uint32_t)(kb * 32);     // packed: 16 K per 16 columns (8 hi | 8 lo)
-                            {   // ---- W_hi image
-                                const uint32_t s = n & (tc4::NSTAGE - 1), ph = (n >> 3) & 1u;
-                                if (!PNB_TIMED_WAIT(3, mbar_wait(&sm.bar_full[s], ph, p.err, 36))) { ok = false; break; }
-                                tc_fence_after();
-                                const uint32_t bl = b0_lo + s * (tc4::IMG >> 4);
-                                if (l == 0) {
-                                    mma_ss2(acc, akb_hi, hiw, bl, hiw, idesc, kb ? 1u : 0u);
-                                    mma_ss2(acc, akb_lo, hiw, bl, hiw, idesc, 1u);
-                                    mma_ss2(acc, akb_hi + KADV, hiw, bl + KADV, hiw, idesc, 1u);
-                                    mma_ss2(acc, akb_lo + KADV, hiw, bl + KADV, hiw, idesc, 1u);
-                                } else if (kb == 8) {
-                                    mma_ss2(acc, xeh_lo, xe_hiw, bl, hiw, idesc, 1u);
-                                    mma_ss2(acc, xel_lo, xe_hiw, bl, hiw, idesc, 1u);
-                                } else {
-                                    mma_ts2(acc, tcol, bl, hiw, idesc, kb ? 1u : 0u);
-                                    mma_ts2(acc, tcol + 8u, bl, hiw, idesc, 1u);
-                                    mma_ts2(acc, tcol + 16u, bl + KADV, hiw, idesc, 1u);
-                                    mma_ts2(acc, tcol + 24u, bl + KADV, hiw, idesc, 1u);
-                                }
-                                mma_commit(&sm.bar_empty[s]);
-                                ++n;
-                            }
-                            {   // ---- W_lo image
-                                const uint32_t s = n & (tc4::NSTAGE - 1), ph = (n >> 3) & 1u;
-                                if (!PNB_TIMED_WAIT(3, mbar_wait(&sm.bar_full[s], ph, p.err, 36))) { ok = false; break; }
-                                tc_fence_after();
-                                const uint32_t bl = b0_lo + s * (tc4::IMG >> 4);
-                                if (l == 0) {
-                                    mma_ss2(acc, akb_hi, hiw, bl, hiw, idesc, 1u);
-                                    mma_ss2(acc, akb_hi + KADV, hiw, bl + KADV, hiw, idesc, 1u);
-                                } else if (kb == 8) {
-                                    mma_ss2(acc, xeh_lo, xe_hiw, bl, hiw, idesc, 1u);
-                                } else {
-                                    mma_ts2(acc, tcol, bl, hiw, idesc, 1u);
-                                    mma_ts2(acc, tcol + 16u, bl + KADV, hiw, idesc, 1u);
-                                }
-                                mma_commit(&sm.bar_empty[s]);
-                                ++n;
-                            }
-                        }
-                        if (!ok) break;
-                        mma_commit(&sm.bar_acc_full[h]);
-                        if (l == 0 && h == 1) mma_commit(&sm.bar_a1_free);
-                    }
-                }
-            }
-        }
-    } else if (warp >= W_BUILD) {
-        // ============================================================ builders: one thread per pair row
-        const int row = (warp - W_BUILD) * 32 + lane;
-        bool ok = true;
-        for (int t = 0; t < my_tiles && ok; ++t) {
-            const int tile = (int)blockIdx.x + t * (int)gridDim.x;
-            if (t > 0 && !(lane == 0 && warp == W_BUILD ? PNB_TIMED_WAIT(4, mbar_wait(&sm.bar_a1_free, (uint32_t)(t - 1) & 1u, p.err, 37)) : mbar_wait(&sm.bar_a1_free, (uint32_t)(t - 1) & 1u, p.err, 37))) { ok = false; break; }
-            const long long _tb0 = clock64();
-            build_pair_row(sm, p, tile, t, row, n_valid);
-            fence_proxy_async();
-            mbar_arrive(&sm.bar_a1_ready);
-            if (lane == 0 && warp == W_BUILD) prof_add(p.err, 5, clock64() - _tb0);
-        }
-    } else {
-        // ============================================================ epilogue: group h = warps 8h..8h+7, 64 columns per thread
-        const int h = warp >> 3, quad = warp & 3, part = (warp >> 2) & 1;
-        const int erow = quad * 32 + lane;
-        const uint32_t tlane = (uint32_t)(quad * 32) << 16;
-        const int cbase = 128 * h + 64 * part;                 // first output column of this thread
-        uint32_t n_acc = 0;
-        bool ok = true;
-        for (int t = 0; t < my_tiles && ok; ++t) {
-            const int tile = (int)blockIdx.x + t * (int)gridDim.x;
-            for (int l = 0; l < 4 && ok; ++l, ++n_acc) {
-                if (!((tid & 255) == 0 ? PNB_TIMED_WAIT(6, mbar_wait(&sm.bar_acc_full[h], n_acc & 1u, p.err, 38)) : mbar_wait(&sm.bar_acc_full[h], n_acc & 1u, p.err, 38))) { ok = false; break; }
-                const long long _te0 = clock64();
-                tc_fence_after();
-                const uint32_t accb = ((l & 1) ? tP : tQ) + tlane + (uint32_t)cbase;
-                if (l < 3) {
-                    const float* bias = p.bias[l];
-#pragma unroll
-                    for (int ch = 0; ch < 4; ++ch) {
-                        const int c0 = cbase + ch * 16;
-                        uint32_t v[16];
-                        tmem_ld16(accb + (uint32_t)(ch * 16), v);
-                        tmem_ld_wait();
-                        uint32_t hh[8], ll[8];
-#pragma unroll
-                        for (int e = 0; e < 8; ++e) {
-                            float2 bb = __ldg(reinterpret_cast<const float2*>(bias + c0) + e);
-                            float y0 = __uint_as_float(v[2 * e]) + bb.x, y1 = __uint_as_float(v[2 * e + 1]) + bb.y;
-                            y0 = fmaxf(y0, LEAKY * y0); y1 = fmaxf(y1, LEAKY * y1);
-                            split_bf16x2(y0, y1, hh[e], ll[e]);
-                        }
-                        tmem_st8(accb + (uint32_t)(ch * 16), hh);        // in place: 8 columns hi | 8 columns lo
-                        tmem_st8(accb + (uint32_t)(ch * 16) + 8u, ll);
-                    }
-                    tmem_st_wait();
-                    tc_fence_before();
-                    mbar_arrive(&sm.bar_at_ready[h]);
-                    if ((tid & 255) == 0) prof_add(p.err, 7, clock64() - _te0);
-                } else {
-                    const float wrow = sm.wc[t & 1][erow];
-                    const int sidx = tile * TSAMP + (erow >> 3);
-                    const bool swrite = sidx < n_valid;
-                    const float* bias = p.bias[3];
-                    const int j8 = lane & 7;
-                    float apart = 0.f;
-#pragma unroll
-                    for (int ch = 0; ch < 4; ++ch) {
-                        const int c0 = cbase + ch * 16;
-                        uint32_t v[16];
-                        tmem_ld16(accb + (uint32_t)(ch * 16), v);
-                        tmem_ld_wait();
-                        float z[16];
-#pragma unroll
-                        for (int e = 0; e < 16; ++e) {
-                            float y = __uint_as_float(v[e]) + __ldg(bias + c0 + e);
-                            y = fmaxf(y, LEAKY * y);
-                            apart = fmaf(y, __ldg(p.wa + c0 + e), apart);
-                            z[e] = y * wrow;
-                        }
-                        float r8[8], r4[4], r2[2];
-                        const bool b4 = lane & 4, b2 = lane & 2, b1 = lane & 1;
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            float send = b4 ? z[i] : z[i + 8], keep = b4 ? z[i + 8] : z[i];
-                            r8[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
-                        }
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            float send = b2 ? r8[i] : r8[i + 4], keep = b2 ? r8[i + 4] : r8[i];
-                            r4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
-                        }
-#pragma unroll
-                        for (int i = 0; i < 2; ++i) {
-                            float send = b1 ? r4[i] : r4[i + 2], keep = b1 ? r4[i + 2] : r4[i];
-                            r2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 1);
-                        }
-                        if (swrite) *reinterpret_cast<float2*>(p.hbar + (size_t)sidx * 256 + c0 + 2 * j8) = make_float2(r2[0], r2[1]);
-                    }
-                    tc_fence_before();
-                    mbar_arrive(&sm.bar_drain[h]);             // this accumulator half is drained
-                    if ((tid & 255) == 0) prof_add(p.err, 8, clock64() - _te0);
-                    // alpha branch: 4 partial dot products per row (2 halves x 2 parts) -> two slots, one add each
-                    if (h == 0) sm.alpha_part[part][erow] = apart;
-                    named_bar_sync(1, 2 * tc4::NEPI_H);
-                    if (h == 1) atomicAdd(&sm.alpha_part[part][erow], apart);
-                    named_bar_sync(1, 2 * tc4::NEPI_H);
-                    if (h == 0 && part == 0) {
-                        float a = sm.alpha_part[0][erow] + sm.alpha_part[1][erow] + __ldg(p.ba) - 1.0f;
-                        float sp = a > 20.f ? a : log1pf(expf(a));
-                        float zz = sp * wrow;
-                        zz += __shfl_xor_sync(0xffffffffu, zz, 1);
-                        zz += __shfl_xor_sync(0xffffffffu, zz, 2);
-                        zz += __shfl_xor_sync(0xffffffffu, zz, 4);
-                        if (j8 == 0 && swrite) p.sigma[sidx] = zz;
-                    }
-                    named_bar_sync(1, 2 * tc4::NEPI_H);
-                }
-            }
-        }
-    }
-    if (tid == 0) prof_add(p.err, 9, clock64() - _tk0);
-    tc_fence_before();
-    __syncthreads();
-    if (warp == W_ISSUE) tmem_dealloc<512>(sm.tmem_base);
-}
-
-// =====================================================================================================================
 // v5: "TMEM role ping-pong", single N=256 pass per layer.  The two 256-column TMEM regions P and Q alternate between
 // accumulator and A operand: the epilogue converts the finished accumulator IN PLACE, 16 columns at a time, into the
 // packed bf16 operand of the next layer (8 columns hi | 8 columns lo), and signals each 16-column chunk on its own
@@ -1739,7 +1468,7 @@ using namespace pnb;
 
 static size_t pack_pairs_bytes() { return (size_t)tc::NBLK_TOTAL * 2 * tc::IMG; }
 static size_t pack_color_bytes() { return (size_t)ctc::NBLK * 2 * ctc::IMG; }
-extern "C" size_t pnb_mlp_pack_bytes(void) { return 2 * pack_pairs_bytes() + pack_color_bytes(); }
+extern "C" size_t pnb_mlp_pack_bytes(void) { return pack_pairs_bytes() + pack_color_bytes(); }
 
 // Packs block1/block3 weights (pnb_mlp_t W^T buffers, fp32) into tcgen05 operand images.  Call once per weight version.
 extern "C" int pnb_mlp_pack(const pnb_mlp_t* mlp, void* d_out, size_t out_bytes, pnb_stream_t stream_) {
@@ -1758,15 +1487,6 @@ extern "C" int pnb_mlp_pack(const pnb_mlp_t* mlp, void* d_out, size_t out_bytes,
         int n = nkb * 128 * umma::BK;
         k_pack_weights<<<(n + 255) / 256, 256, 0, stream>>>(mlp->w[5 + l], ckpad[l], nkb, 128,
                                                             (unsigned char*)d_out + pack_pairs_bytes() + (size_t)ctc::img_base(l) * 2 * ctc::IMG);
-    }
-    // v4: per layer, per N-half, per K block: hi image then lo image, each [128 x 32]
-    unsigned char* out4 = (unsigned char*)d_out + pack_pairs_bytes() + pack_color_bytes();
-    for (int l = 0; l < 4; ++l) {
-        int nkb = tc::nkb_of(l);
-        int n = nkb * 128 * umma::BK;
-        for (int h = 0; h < 2; ++h)
-            k_pack_weights<<<(n + 255) / 256, 256, 0, stream>>>(mlp->w[l], kpad[l], nkb, 128,
-                                                                out4 + (size_t)(tc4::img_base(l) + h * nkb) * 2 * tc4::IMG, 256, h * 128);
     }
     PNB_CHECK_CUDA(cudaGetLastError());
     return PNB_OK;
@@ -1789,9 +1509,8 @@ extern "C" int pnb_shade_forward_tc(const pnb_query_t* q, const pnb_points_t* pt
     // interleaved (non-swizzled) operand layout: 128-byte alignment of the carve-out is sufficient
     constexpr size_t kSmemMax = 232448;   // 227 KB opt-in limit per block on sm_100
     const size_t smem_tc = sizeof(tc::Smem) + 128, smem_tc3 = sizeof(tc3::Smem) + 128, smem_cb = sizeof(cb::Smem),
-                 smem_ctc = sizeof(ctc::Smem) + 128, smem_tc4 = sizeof(tc4::Smem) + 128, smem_tc5 = sizeof(tc5::Smem) + 128;
+                 smem_ctc = sizeof(ctc::Smem) + 128, smem_tc5 = sizeof(tc5::Smem) + 128;
     static_assert(sizeof(tc5::Smem) + 128 <= kSmemMax, "v5 shared-memory carve-out exceeds the per-block limit");
-    static_assert(sizeof(tc4::Smem) + 128 <= kSmemMax, "v4 shared-memory carve-out exceeds the per-block limit");
     static_assert((tc3::NSTAGE & (tc3::NSTAGE - 1)) == 0 && tc3::NSTAGE == 4, "issuer assumes a 4-stage ring");
     static_assert(sizeof(tc::Smem) + 128 <= kSmemMax && sizeof(tc3::Smem) + 128 <= kSmemMax && sizeof(ctc::Smem) + 128 <= kSmemMax &&
                   sizeof(cb::Smem) <= kSmemMax, "shared-memory carve-out exceeds the sm_100 per-block limit");
@@ -1799,7 +1518,6 @@ extern "C" int pnb_shade_forward_tc(const pnb_query_t* q, const pnb_points_t* pt
         PNB_CHECK_CUDA(cudaFuncSetAttribute(k_shade_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tc));
         PNB_CHECK_CUDA(cudaFuncSetAttribute(k_shade_tc3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tc3));
         PNB_CHECK_CUDA(cudaFuncSetAttribute(k_shade_tc5, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tc5));
-        PNB_CHECK_CUDA(cudaFuncSetAttribute(k_shade_tc4, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tc4));
         PNB_CHECK_CUDA(cudaFuncSetAttribute(k_color_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_ctc));
         PNB_CHECK_CUDA(cudaFuncSetAttribute(k_color_branch, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cb));
         int dev = 0;
@@ -1812,14 +1530,12 @@ extern "C" int pnb_shade_forward_tc(const pnb_query_t* q, const pnb_points_t* pt
     float* sigma = c.take<float>((size_t)max_valid_samples);
     ShadeTcParams p;
     p.q = *q; p.pts = *pts; p.o = *opts; p.wimg = (const unsigned char*)d_packed;
-    p.wimg4 = (const unsigned char*)d_packed + pack_pairs_bytes() + pack_color_bytes();
     for (int l = 0; l < 4; ++l) p.bias[l] = mlp->b[l];
     p.wa = mlp->w[4];
     p.ba = mlp->b[4];
     p.hbar = hbar; p.sigma = sigma; p.hbar_cap = max_valid_samples; p.err = d_err;
     if (stage_mask & 1) {
         if (stage_mask & 32) k_shade_tc5<<<n_sm, tc5::NTHR, smem_tc5, stream>>>(p);           // TMEM ping-pong, chunk-pipelined
-        else if (stage_mask & 16) k_shade_tc4<<<n_sm, tc4::NTHR, smem_tc4, stream>>>(p);      // TMEM ping-pong, N-half passes
         else if (stage_mask & 4) k_shade_tc3<<<n_sm, tc3::NTHR, smem_tc3, stream>>>(p);   // TS-form pipeline (A in tensor memory)
         else k_shade_tc<<<n_sm, tc::NTHR, smem_tc, stream>>>(p);
     }

@@ -230,13 +230,35 @@ __global__ void __launch_bounds__(128, 1) k_umma_bench(int mode, int iters, int 
     __syncthreads();
     tc_fence_after();
     const uint32_t tacc = tmem_base;
-    if (tid == 32 && bulk) {       // concurrent weight-like stream
+    if (tid == 32 && (bulk & 1)) {       // concurrent weight-like stream
         for (int i = 0; i < iters / 3 + 2; ++i) {
             int s = i & 1;
             if (i >= 2 && !mbar_wait(&bbar[s], ((i >> 1) - 1) & 1, err, 301)) break;
             mbar_arrive_expect_tx(&bbar[s], 16384);
             bulk_g2s(sink + s * 16384, gsrc + (size_t)(i % 64) * 16384, 16384, &bbar[s]);
         }
+    }
+    __shared__ volatile int stop_flag;
+    if (tid == 0) stop_flag = 0;
+    __syncthreads();
+    if ((bulk & 2) && warp >= 1) {     // concurrent epilogue-like TMEM traffic on columns 384..511 (other lane quadrants)
+        const uint32_t tl = (uint32_t)(warp * 32) << 16;
+        uint32_t v[16];
+        uint32_t acc_x = 0;
+        while (!stop_flag) {
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                tmem_ld16(tacc + tl + 384u + (uint32_t)(c * 16), v);
+                tmem_ld_wait();
+#pragma unroll
+                for (int e = 0; e < 16; ++e) acc_x += v[e];
+                v[0] = acc_x;
+                tmem_st8(tacc + tl + 384u + (uint32_t)(c * 16), v);
+                tmem_st8(tacc + tl + 384u + (uint32_t)(c * 16) + 8u, v + 8);
+                tmem_st_wait();
+            }
+        }
+        if (acc_x == 0x12345678u) out[3] = acc_x;
     }
     if (tid == 0) {
         const uint32_t idesc = make_idesc_bf16(128, 256);
@@ -252,9 +274,10 @@ __global__ void __launch_bounds__(128, 1) k_umma_bench(int mode, int iters, int 
         long long t2 = clock64();
         out[0] = t1 - t0;      // issue time
         out[1] = t2 - t0;      // until all MMAs completed
+        stop_flag = 1;
     }
     __syncthreads();
-    if (tid == 32 && bulk) { mbar_wait(&bbar[0], 1, nullptr, 0); }
+    if (tid == 32 && (bulk & 1)) { mbar_wait(&bbar[0], 1, nullptr, 0); }
     tc_fence_before();
     __syncthreads();
     if (warp == 0) tmem_dealloc<512>(tacc);

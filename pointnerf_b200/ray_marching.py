@@ -286,10 +286,13 @@ def _init_state(mod):
     mod.precision = getattr(opt, "pnb_precision", "bf16x3")
     if mod.precision not in ("bf16x3", "fp32"):
         raise NotImplementedError("pnb200: pnb_precision=%r (bf16x3 | fp32)" % mod.precision)
-    # tcgen05 pipeline variant: 4 = TMEM role ping-pong (epilogues under the MMAs), 3 = A operand of layers 2-4 in tensor
-    # memory + overlapped operand builders (default), 2 = serialized shared-memory pipeline
+    # tcgen05 pipeline variant: 3 = A operand of layers 2-4 in tensor memory + overlapped operand builders (default),
+    # 5 = chunk-pipelined TMEM role ping-pong (epilogue of layer l under the MMAs of layer l+1; same speed),
+    # 2 = serialized shared-memory pipeline
     _v = int(getattr(opt, "pnb_tc_version", 3))
-    mod.tc_mask = 3 | (12 if _v == 3 else 0) | (8 + 16 if _v == 4 else 0) | (8 + 32 if _v == 5 else 0)
+    if _v not in (2, 3, 5):
+        raise NotImplementedError("pnb200: pnb_tc_version=%r (2 | 3 | 5)" % _v)
+    mod.tc_mask = 3 | (12 if _v == 3 else 0) | (8 + 32 if _v == 5 else 0)
     mod.last = None
     mod._pnb_ready = True
 

@@ -7,13 +7,13 @@ from pointnerf_b200 import lib as _lib
 l = _lib.load()
 dev = "cuda:0"
 src = torch.zeros(2 << 20, dtype=torch.uint8, device=dev)
-out = torch.zeros(2, dtype=torch.int64, device=dev)
+out = torch.zeros(4, dtype=torch.int64, device=dev)
 err = torch.zeros(4, dtype=torch.int32, device=dev)
 st = torch.cuda.current_stream().cuda_stream
-for layout in (0, 4):
+for layout in (0,):
     for mode in (0, 1):
-        for bulk in (0, 1):
-            for iters in (300, 3000):
+        for bulk in (0, 1, 2, 3):   # bit 0: concurrent cp.async.bulk stream, bit 1: concurrent tcgen05.ld/st traffic from 3 warps
+            for iters in (3000,):
                 _lib.check(l.pnb_umma_bench(layout, mode, iters, bulk, src.data_ptr(), out.data_ptr(), err.data_ptr(), st), "bench")
                 torch.cuda.synchronize()
                 o = out.tolist()

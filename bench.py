@@ -330,6 +330,11 @@ def main():
     value = total_rays / (ms_res * 1e-3) / 1e6
     e2e_val = total_rays / (ms_e2e * 1e-3) / 1e6
     pk = peaks()
+    # DRAM traffic of the dominant kernel per launch, from the committed ncu --set full capture of this same command
+    traffic = None
+    tfile = os.path.join(ROOT, "profiles", "r01_ncu_dram_traffic.json")
+    if os.path.exists(tfile) and args.precision != "fp32" and world == 1 and args.sr == 24:
+        traffic = json.load(open(tfile)).get("k_shade_tc3" if net.tc_mask & 4 else "", None)
     flops = kflops
     achieved = flops / (shade_avg * 1e-3) / 1e12
     peak = pk["bf16_tflops"]
@@ -351,7 +356,7 @@ def main():
             gpu_launches=(LAUNCHES_PER_STEP + (1 if args.precision != "fp32" else 0)) * args.steps,
             clocks=clocks,
             roofline=dict(bound="tensor", kernel=kname, achieved=achieved, peak=peak, unit="TFLOP/s",
-                          frac=achieved / peak, traffic=None, peak_source="%s bf16 cuBLAS burst (MEASURED_PEAKS.json)" % pk["source"],
+                          frac=achieved / peak, traffic=traffic, peak_source="%s bf16 cuBLAS burst (MEASURED_PEAKS.json)" % pk["source"],
                           algorithmic_flops_per_launch=flops, kernel_ms=shade_avg,
                           kernel_share_of_step=shade_avg / (ms_res / args.steps),
                           issued_mma_flops_per_launch=(3 * flops if args.precision != "fp32" else None),

@@ -19,30 +19,35 @@ constexpr float LEAKY = 0.01f;
 
 // ------------------------------------------------------------------------------------------ generic fp32 GEMM
 // C[M x N] (+)= sum_k Aeff[m][k] * Beff[k][n],  Aeff[m][k] = A[m*sam + k*sak],  Beff[k][n] = B[k*sbk + n*sbn].
-// 64 x 64 tile, 256 threads, 4 x 4 outputs per thread.  blockIdx.z splits the reduction (ATOMIC accumulation).
+// 128 x 64 tile, 256 threads, 8 x 4 outputs per thread (float4 shared-memory reads: 32 FMA per 3 LDS.128).
+// blockIdx.z splits the reduction (ATOMIC accumulation).
 template <bool ATOMIC>
 __global__ void __launch_bounds__(256) k_gemm(const float* __restrict__ A, long sam, long sak, const float* __restrict__ B,
                                               long sbk, long sbn, float* __restrict__ C, long ldc, int M, int N, int K,
                                               int kchunk, const float* __restrict__ bias, int act) {
-    __shared__ float As[16][68];
-    __shared__ float Bs[16][68];
+    __shared__ __align__(16) float As[16][132];
+    __shared__ __align__(16) float Bs[16][68];
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
-    const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
+    const int m0 = blockIdx.y * 128, n0 = blockIdx.x * 64;
     const int kbeg = blockIdx.z * kchunk, kend = min(K, kbeg + kchunk);
-    float acc[4][4];
+    float acc[8][4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < 8; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
     for (int k0 = kbeg; k0 < kend; k0 += 16) {
-        // load tiles: choose the thread->element map along the unit-stride direction
+        // load tiles: the thread->element map follows the unit-stride direction of each operand
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            int idx = tid + e * 256;           // 0..2047
+            int am, ak;
+            if (sak == 1) { ak = idx & 15; am = idx >> 4; } else { am = idx & 127; ak = idx >> 7; }
+            int gm = m0 + am, gk = k0 + ak;
+            As[ak][am] = (gm < M && gk < kend) ? A[gm * sam + gk * sak] : 0.f;
+        }
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
             int idx = tid + e * 256;           // 0..1023
-            int am, ak;
-            if (sak == 1) { ak = idx & 15; am = idx >> 4; } else { am = idx & 63; ak = idx >> 6; }
-            int gm = m0 + am, gk = k0 + ak;
-            As[ak][am] = (gm < M && gk < kend) ? A[gm * sam + gk * sak] : 0.f;
             int bn, bk;
             if (sbn == 1) { bn = idx & 63; bk = idx >> 6; } else { bk = idx & 15; bn = idx >> 4; }
             int gn = n0 + bn, gk2 = k0 + bk;
@@ -51,21 +56,21 @@ __global__ void __launch_bounds__(256) k_gemm(const float* __restrict__ A, long 
         __syncthreads();
 #pragma unroll
         for (int k = 0; k < 16; ++k) {
-            float a[4], b[4];
+            const float4 a0 = *reinterpret_cast<const float4*>(&As[k][ty * 8]);
+            const float4 a1 = *reinterpret_cast<const float4*>(&As[k][ty * 8 + 4]);
+            const float4 b4 = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+            const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+            const float b[4] = {b4.x, b4.y, b4.z, b4.w};
 #pragma unroll
-            for (int i = 0; i < 4; ++i) a[i] = As[k][ty * 4 + i];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) b[j] = Bs[k][tx * 4 + j];
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
+            for (int i = 0; i < 8; ++i)
 #pragma unroll
                 for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
         }
         __syncthreads();
     }
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        int gm = m0 + ty * 4 + i;
+    for (int i = 0; i < 8; ++i) {
+        int gm = m0 + ty * 8 + i;
         if (gm >= M) continue;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -86,7 +91,7 @@ __global__ void __launch_bounds__(256) k_gemm(const float* __restrict__ A, long 
 static int gemm_nn(const float* A, long lda, const float* Bt, long ldb, float* C, long ldc, int M, int N, int K,
                    const float* bias, int act, cudaStream_t st) {
     if (M <= 0) return PNB_OK;
-    dim3 g((N + 63) / 64, (M + 63) / 64, 1);
+    dim3 g((N + 63) / 64, (M + 127) / 128, 1);
     k_gemm<false><<<g, 256, 0, st>>>(A, lda, 1, Bt, ldb, 1, C, ldc, M, N, K, K, bias, act);
     return PNB_OK;
 }
@@ -94,7 +99,7 @@ static int gemm_nn(const float* A, long lda, const float* Bt, long ldb, float* C
 static int gemm_nt(const float* dZ, long ldz, const float* Wt, long ldw, float* dX, long ldx, int M, int Kin, int Nout,
                    cudaStream_t st) {
     if (M <= 0) return PNB_OK;
-    dim3 g((Kin + 63) / 64, (M + 63) / 64, 1);
+    dim3 g((Kin + 63) / 64, (M + 127) / 128, 1);
     k_gemm<false><<<g, 256, 0, st>>>(dZ, ldz, 1, Wt, 1, ldw, dX, ldx, M, Kin, Nout, Nout, nullptr, 0);
     return PNB_OK;
 }
@@ -103,7 +108,7 @@ static int gemm_tn_acc(const float* X, long ldx, const float* dZ, long ldz, floa
                        cudaStream_t st) {
     if (M <= 0) return PNB_OK;
     const int chunk = 2048;
-    dim3 g((Nout + 63) / 64, (Kin + 63) / 64, (M + chunk - 1) / chunk);
+    dim3 g((Nout + 63) / 64, (Kin + 127) / 128, (M + chunk - 1) / chunk);
     k_gemm<true><<<g, 256, 0, st>>>(X, 1, ldx, dZ, ldz, 1, dWt, ldw, Kin, Nout, M, chunk, nullptr, 0);
     return PNB_OK;
 }

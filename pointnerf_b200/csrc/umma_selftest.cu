@@ -242,7 +242,7 @@ __global__ void __launch_bounds__(128, 1) k_umma_bench(int mode, int iters, int 
     if (tid == 0) stop_flag = 0;
     __syncthreads();
     if ((bulk & 2) && warp >= 1) {     // concurrent epilogue-like TMEM traffic on columns 384..511 (other lane quadrants)
-        const uint32_t tl = (uint32_t)(warp * 32) << 16;
+        const uint32_t tl = ((uint32_t)(warp * 32) << 16) - ((bulk & 4) ? 112u : 0u) - ((bulk & 8) ? 368u : 0u);   // +4: same 128-column block as the A operand; +8: inside the accumulator block
         uint32_t v[16];
         uint32_t acc_x = 0;
         while (!stop_flag) {

@@ -141,3 +141,50 @@ def test_probe_outputs_match_reference_fixture(golden_dir):
                    ("shading_avg_dir", 1e-5), ("shading_avg_conf", 1e-5), ("shading_avg_embedding", 1e-5)):
         a = out[k][0].cpu().numpy().reshape(fx[k].shape)
         assert np.abs(a - fx[k])[same].max() <= tol, k
+
+
+def test_install_into_reference_shaped_module():
+    """Seam B: patching a reference-shaped NeuralPointsRayMarching class (own parameters under
+    self.neural_points / self.aggregator, reference attribute names) with install_into() gives the fused forward."""
+    import torch.nn as nn
+    from pointnerf_b200 import ray_marching as P
+    from pointnerf_b200.point_query import lighting_fast_querier
+
+    cfg = scene.CONFIGS["tiny"]
+    opt = harness.make_opt(cfg)
+    pts = scene.make_points(cfg)
+
+    class RefNeuralPoints(nn.Module):            # attribute names of models/neural_points/neural_points.py
+        def __init__(self):
+            super().__init__()
+            self.xyz = nn.Parameter(pts["xyz"].to(DEV), requires_grad=False)
+            self.points_embeding = nn.Parameter(pts["embedding"].to(DEV))
+            self.points_conf = nn.Parameter(pts["conf"].to(DEV))
+            self.points_dir = nn.Parameter(pts["dir"].to(DEV))
+            self.points_color = nn.Parameter(pts["color"].to(DEV))
+            self.Rw2c = torch.eye(3, device=DEV)
+            self.querier = lighting_fast_querier(torch.device(DEV), opt)      # seam A
+
+    class RefRayMarching(nn.Module):             # stands in for models.neural_points_volumetric_model.NeuralPointsRayMarching
+        def __init__(self, aggregator, neural_points, opt):
+            super().__init__()
+            self.aggregator, self.neural_points, self.opt = aggregator, neural_points, opt
+
+        def forward(self, *a, **k):
+            raise AssertionError("the eager reference forward must have been replaced")
+
+    P.install_into(RefRayMarching)
+    agg = P.PointAggregator(opt, seed=0).to(DEV)
+    with torch.no_grad():
+        agg.alpha_branch[0].bias += 4.0
+    net = RefRayMarching(agg, RefNeuralPoints(), opt)
+    rays = scene.make_rays(cfg, scene.centre_patch(cfg, 32))
+    r = {k: v.to(DEV) for k, v in rays.items()}
+    with torch.no_grad():
+        out = net(r["campos"], r["raydir"], bg_color=r["bg_color"], camrotc2w=r["camrotc2w"], pixel_idx=r["pixel_idx"],
+                  near=r["near"], far=r["far"], h=r["h"], w=r["w"], intrinsic=r["intrinsic"])
+    ref = _oracle_render(cfg, opt, pts, agg, rays["raydir"][0])
+    assert np.array_equal(out["ray_mask"][0].cpu().numpy(), ref["ray_mask"])
+    assert (out["coarse_raycolor"][0].cpu() - ref["ray_color"]).abs().max().item() <= TOL
+    assert sorted(k for k, _ in net.named_parameters())[:3] == ["aggregator.alpha_branch.0.bias", "aggregator.alpha_branch.0.weight",
+                                                                 "aggregator.block1.0.bias"]

@@ -12,7 +12,7 @@ err = torch.zeros(4, dtype=torch.int32, device=dev)
 st = torch.cuda.current_stream().cuda_stream
 for layout in (0,):
     for mode in (0, 1):
-        for bulk in (0, 1, 2, 3):   # bit 0: concurrent cp.async.bulk stream, bit 1: concurrent tcgen05.ld/st traffic from 3 warps
+        for bulk in (0, 2, 6, 10):   # bit 0: concurrent cp.async.bulk stream, bit 1: concurrent tcgen05.ld/st traffic from 3 warps
             for iters in (3000,):
                 _lib.check(l.pnb_umma_bench(layout, mode, iters, bulk, src.data_ptr(), out.data_ptr(), err.data_ptr(), st), "bench")
                 torch.cuda.synchronize()

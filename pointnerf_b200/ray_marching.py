@@ -433,7 +433,8 @@ class NeuralPointsRayMarching(nn.Module):
             d = npnts.xyz.detach()[idx] - ex["sample_loc_w"][:, :, None, :]
             wgt = mask * (1.0 / torch.clamp(torch.norm(d, dim=-1), min=1e-6))
             wgt = wgt / torch.clamp(torch.sum(wgt, dim=-1, keepdim=True), min=1e-8)
-            c0 = npnts.points_conf[0, :, 0][idx]
+            # index_select (as the reference, neural_points.py:717): its backward is one index_add_, not a sort-based scatter
+            c0 = torch.index_select(npnts.points_conf[0, :, 0], 0, idx.reshape(-1)).view(idx.shape)
             conf_coefficient = c0 - (c0 - torch.clamp(c0, min=0.0001, max=1)).detach()
             op = out["coarse_point_opacity"][0].detach()
             acc = torch.cumprod(1. - op + 1e-10, dim=-1)

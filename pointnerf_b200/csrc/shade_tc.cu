@@ -952,10 +952,12 @@ __global__ void __launch_bounds__(cb::NTHREADS, 1) k_color_branch(ColorParams p)
 // as chunk g is converted, so the tensor core runs layer l+1 right behind the epilogue of layer l.  The final
 // epilogue of a tile runs under layer 1 of the next tile.
 //      layer 1: A shared memory, acc Q      layer 2: A = Q, acc P      layer 3: A = P (+extras), acc Q      layer 4: A = Q, acc P
-// Warp roles (704 threads): 0-15 epilogue (quadrant = w & 3, chunk group j = w >> 2 handles chunks j, j+4, j+8, j+12),
-// 16-19 builders, 20 loader, 21 issuer.
+// Warp roles (448 threads): 0-7 epilogue (quadrant = w & 3, chunk group j = w >> 2 handles chunks j, j+2, ..., j+14),
+// 8-11 builders, 12 loader, 13 issuer.  Few epilogue warps on purpose: the epilogue only has to stay ahead of the MMAs,
+// and every busy warp on the issuer's sub-partition slows the single issuing thread.
 namespace tc5 {
-constexpr int NEPI = 512, NBUILD = 128, NTHR = 704;
+constexpr int NEPI_WARPS = 8, NGRP = NEPI_WARPS / 4, NCH = 16 / NGRP;   // chunk groups / chunks per thread
+constexpr int NEPI = NEPI_WARPS * 32, NBUILD = 128, NTHR = NEPI + NBUILD + 64;
 constexpr int NSTAGE = 4;
 struct Smem {
     unsigned char a_hi[tc::NKB_MAX * tc::ABLK];
@@ -979,7 +981,7 @@ __global__ void __launch_bounds__(tc5::NTHR, 1) k_shade_tc5(ShadeTcParams p) {
     const int n_valid = min(q.counters[PNB_QC_N_VALID], p.hbar_cap);
     const int n_tiles = (n_valid + TSAMP - 1) / TSAMP;
     const int my_tiles = n_tiles > (int)blockIdx.x ? (n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
-    constexpr int W_BUILD = 16, W_LOAD = 20, W_ISSUE = 21;
+    constexpr int W_BUILD = tc5::NEPI_WARPS, W_LOAD = W_BUILD + 4, W_ISSUE = W_LOAD + 1;
 
     if (tid == 0) {
         for (int s = 0; s < tc5::NSTAGE; ++s) { mbar_init(&sm.bar_full[s], 1); mbar_init(&sm.bar_empty[s], 1); }
@@ -1102,8 +1104,8 @@ __global__ void __launch_bounds__(tc5::NTHR, 1) k_shade_tc5(ShadeTcParams p) {
             if (lane == 0 && warp == W_BUILD) prof_add(p.err, 5, clock64() - _tb0);
         }
     } else {
-        // ============================================================ epilogue warps 0..15
-        const int quad = warp & 3, grp = warp >> 2;            // chunk group: chunks grp, grp+4, grp+8, grp+12
+        // ============================================================ epilogue warps
+        const int quad = warp & 3, grp = warp >> 2;            // chunk group: chunks grp, grp+NGRP, grp+2*NGRP, ...
         const int erow = quad * 32 + lane;
         const uint32_t tlane = (uint32_t)(quad * 32) << 16;
         uint32_t n_acc = 0;
@@ -1118,8 +1120,8 @@ __global__ void __launch_bounds__(tc5::NTHR, 1) k_shade_tc5(ShadeTcParams p) {
                 if (l < 3) {
                     const float* bias = p.bias[l];
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const int g = grp + 4 * i, c0 = 16 * g;
+                    for (int i = 0; i < tc5::NCH; ++i) {
+                        const int g = grp + tc5::NGRP * i, c0 = 16 * g;
                         uint32_t v[16];
                         tmem_ld16(accb + (uint32_t)c0, v);
                         tmem_ld_wait();
@@ -1146,8 +1148,8 @@ __global__ void __launch_bounds__(tc5::NTHR, 1) k_shade_tc5(ShadeTcParams p) {
                     const int j8 = lane & 7;
                     float apart = 0.f;
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const int c0 = 16 * (grp + 4 * i);
+                    for (int i = 0; i < tc5::NCH; ++i) {
+                        const int c0 = 16 * (grp + tc5::NGRP * i);
                         uint32_t v[16];
                         tmem_ld16(accb + (uint32_t)c0, v);
                         tmem_ld_wait();
@@ -1184,9 +1186,9 @@ __global__ void __launch_bounds__(tc5::NTHR, 1) k_shade_tc5(ShadeTcParams p) {
                     if (grp < 2) sm.alpha_part[grp][erow] = apart;
                     named_bar_sync(1, tc5::NEPI);
                     if (grp >= 2) atomicAdd(&sm.alpha_part[grp - 2][erow], apart);
-                    named_bar_sync(1, tc5::NEPI);
+                    if (tc5::NGRP > 2) named_bar_sync(1, tc5::NEPI);
                     if (grp == 0) {
-                        float a = sm.alpha_part[0][erow] + sm.alpha_part[1][erow] + __ldg(p.ba) - 1.0f;
+                        float a = sm.alpha_part[0][erow] + (tc5::NGRP > 1 ? sm.alpha_part[1][erow] : 0.f) + __ldg(p.ba) - 1.0f;
                         float sp = a > 20.f ? a : log1pf(expf(a));
                         float zz = sp * wrow;
                         zz += __shfl_xor_sync(0xffffffffu, zz, 1);

@@ -66,6 +66,7 @@ struct ShadeTcParams {
     float* sigma;                // [n_valid]
     int hbar_cap;
     int* err;
+    int dbg_no_weights;          // timing experiment only: the loader signals the ring without copying (results are garbage)
 };
 
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
@@ -577,6 +578,7 @@ __global__ void __launch_bounds__(tc3::NTHR, 1) k_shade_tc3(ShadeTcParams p) {
             for (uint32_t n = 0; n < total; ++n) {
                 const uint32_t s = n % tc3::NSTAGE, ph = (n / tc3::NSTAGE) & 1u;
                 if (!PNB_TIMED_WAIT(0, mbar_wait(&sm.bar_empty[s], ph ^ 1u, p.err, 11))) break;
+                if (p.dbg_no_weights) { mbar_arrive(&sm.bar_full[s]); continue; }
                 mbar_arrive_expect_tx(&sm.bar_full[s], IMG);
                 bulk_g2s(sm.b[s], p.wimg + (size_t)(n % IMGS_PER_TILE) * IMG, IMG, &sm.bar_full[s]);
             }
@@ -1007,6 +1009,7 @@ __global__ void __launch_bounds__(tc5::NTHR, 1) k_shade_tc5(ShadeTcParams p) {
             for (uint32_t n = 0; n < total; ++n) {
                 const uint32_t s = n & (tc5::NSTAGE - 1), ph = (n >> 2) & 1u;
                 if (!PNB_TIMED_WAIT(0, mbar_wait(&sm.bar_empty[s], ph ^ 1u, p.err, 41))) break;
+                if (p.dbg_no_weights) { mbar_arrive(&sm.bar_full[s]); continue; }
                 mbar_arrive_expect_tx(&sm.bar_full[s], IMG);
                 bulk_g2s(sm.b[s], p.wimg + (size_t)(n % IMGS_PER_TILE) * IMG, IMG, &sm.bar_full[s]);
             }
@@ -1536,6 +1539,7 @@ extern "C" int pnb_shade_forward_tc(const pnb_query_t* q, const pnb_points_t* pt
     p.wa = mlp->w[4];
     p.ba = mlp->b[4];
     p.hbar = hbar; p.sigma = sigma; p.hbar_cap = max_valid_samples; p.err = d_err;
+    p.dbg_no_weights = (stage_mask & 64) ? 1 : 0;
     if (stage_mask & 1) {
         if (stage_mask & 32) k_shade_tc5<<<n_sm, tc5::NTHR, smem_tc5, stream>>>(p);           // TMEM ping-pong, chunk-pipelined
         else if (stage_mask & 4) k_shade_tc3<<<n_sm, tc3::NTHR, smem_tc3, stream>>>(p);   // TS-form pipeline (A in tensor memory)

@@ -11,6 +11,8 @@ rd = rays["raydir"].to(dev)
 for i in range(3):
     with torch.no_grad():
         net.render_full(list(cfg.campos), rd, torch.eye(3), cfg.near, cfg.far, [1., 1., 1.])
+if os.environ.get("PNB_NO_WEIGHTS"):
+    net.tc_mask |= 64
 torch.cuda.synchronize()
 net._err.zero_()
 with torch.no_grad():
@@ -21,6 +23,6 @@ names = ["loader wait empty", "issuer wait a1_ready", "issuer wait at_ready", "i
          "builder busy", "epilogue wait acc_full", "epilogue busy (l<3)", "epilogue busy (l==3)", "kernel total (thread 0)"]
 ntiles = (net.last.counters["n_valid"] if net.last.counters else 3472901) if False else None
 tot = c[9]
-print("status", int(net._err[0]))
+print("status", int(net._err[0]), "version", os.environ.get("PNB_TC_VERSION", "3"), "no_weights", bool(os.environ.get("PNB_NO_WEIGHTS")))
 for n, v in zip(names, c):
     print("%-28s %12d cycles  %5.1f%% of kernel" % (n, v, 100.0 * v / max(tot, 1)))

@@ -1039,52 +1039,51 @@ __global__ void __launch_bounds__(tc5::NTHR, 1) k_shade_tc5(ShadeTcParams p) {
                     tc_fence_after();
                     const int nkb = nkb_of(l);
                     for (int kb = 0; kb < nkb && ok; ++kb) {
-                        if (l >= 1 && kb < 8) {       // chunks 2kb, 2kb+1 of the previous layer's output must be converted
-                            if (!PNB_TIMED_WAIT(2, mbar_wait(&sm.bar_chunk[2 * kb], c_pack & 1u, p.err, 45))) { ok = false; break; }
-                            if (!PNB_TIMED_WAIT(2, mbar_wait(&sm.bar_chunk[2 * kb + 1], c_pack & 1u, p.err, 45))) { ok = false; break; }
-                            tc_fence_after();
+                        const uint32_t s0 = n & (tc5::NSTAGE - 1), ph0 = (n >> 2) & 1u;              // W_hi image
+                        const uint32_t s1 = (n + 1) & (tc5::NSTAGE - 1), ph1 = ((n + 1) >> 2) & 1u;   // W_lo image
+                        const bool need_chunks = (l >= 1 && kb < 8);  // chunks 2kb, 2kb+1 of the previous layer's output
+                        uint64_t* cb0 = need_chunks ? &sm.bar_chunk[2 * kb] : &sm.bar_full[s0];
+                        uint64_t* cb1 = need_chunks ? &sm.bar_chunk[2 * kb + 1] : &sm.bar_full[s1];
+                        const uint32_t cp0 = need_chunks ? (c_pack & 1u) : ph0, cp1 = need_chunks ? (c_pack & 1u) : ph1;
+                        // fast path: one overlapped probe of everything this K block needs; slow path: bounded blocking waits
+                        if (!mbar_try_wait4(&sm.bar_full[s0], ph0, &sm.bar_full[s1], ph1, cb0, cp0, cb1, cp1)) {
+                            if (need_chunks) {
+                                if (!PNB_TIMED_WAIT(2, mbar_wait(cb0, cp0, p.err, 45))) { ok = false; break; }
+                                if (!PNB_TIMED_WAIT(2, mbar_wait(cb1, cp1, p.err, 45))) { ok = false; break; }
+                            }
+                            if (!PNB_TIMED_WAIT(3, mbar_wait(&sm.bar_full[s0], ph0, p.err, 46))) { ok = false; break; }
+                            if (!PNB_TIMED_WAIT(3, mbar_wait(&sm.bar_full[s1], ph1, p.err, 46))) { ok = false; break; }
                         }
+                        tc_fence_after();
                         const uint32_t akb_hi = ahi_lo + (uint32_t)kb * (ABLK >> 4), akb_lo = alo_lo + (uint32_t)kb * (ABLK >> 4);
                         const uint32_t tcol = ab + (uint32_t)(kb * 32);
-                        {   // ---- W_hi image
-                            const uint32_t s = n & (tc5::NSTAGE - 1), ph = (n >> 2) & 1u;
-                            if (!PNB_TIMED_WAIT(3, mbar_wait(&sm.bar_full[s], ph, p.err, 46))) { ok = false; break; }
-                            tc_fence_after();
-                            const uint32_t bl = b0_lo + s * (IMG >> 4);
-                            if (l == 0) {
-                                mma_ss2(acc, akb_hi, hiw, bl, hiw, idesc, kb ? 1u : 0u);
-                                mma_ss2(acc, akb_lo, hiw, bl, hiw, idesc, 1u);
-                                mma_ss2(acc, akb_hi + KADV, hiw, bl + KADV, hiw, idesc, 1u);
-                                mma_ss2(acc, akb_lo + KADV, hiw, bl + KADV, hiw, idesc, 1u);
-                            } else if (kb == 8) {
-                                mma_ss2(acc, xeh_lo, xe_hiw, bl, hiw, idesc, 1u);
-                                mma_ss2(acc, xel_lo, xe_hiw, bl, hiw, idesc, 1u);
-                            } else {
-                                mma_ts2(acc, tcol, bl, hiw, idesc, kb ? 1u : 0u);
-                                mma_ts2(acc, tcol + 8u, bl, hiw, idesc, 1u);
-                                mma_ts2(acc, tcol + 16u, bl + KADV, hiw, idesc, 1u);
-                                mma_ts2(acc, tcol + 24u, bl + KADV, hiw, idesc, 1u);
-                            }
-                            mma_commit(&sm.bar_empty[s]);
-                            ++n;
+                        const uint32_t bl = b0_lo + s0 * (IMG >> 4), bl2 = b0_lo + s1 * (IMG >> 4);
+                        if (l == 0) {
+                            mma_ss2(acc, akb_hi, hiw, bl, hiw, idesc, kb ? 1u : 0u);
+                            mma_ss2(acc, akb_lo, hiw, bl, hiw, idesc, 1u);
+                            mma_ss2(acc, akb_hi + KADV, hiw, bl + KADV, hiw, idesc, 1u);
+                            mma_ss2(acc, akb_lo + KADV, hiw, bl + KADV, hiw, idesc, 1u);
+                            mma_commit(&sm.bar_empty[s0]);
+                            mma_ss2(acc, akb_hi, hiw, bl2, hiw, idesc, 1u);
+                            mma_ss2(acc, akb_hi + KADV, hiw, bl2 + KADV, hiw, idesc, 1u);
+                            mma_commit(&sm.bar_empty[s1]);
+                        } else if (kb == 8) {
+                            mma_ss2(acc, xeh_lo, xe_hiw, bl, hiw, idesc, 1u);
+                            mma_ss2(acc, xel_lo, xe_hiw, bl, hiw, idesc, 1u);
+                            mma_commit(&sm.bar_empty[s0]);
+                            mma_ss2(acc, xeh_lo, xe_hiw, bl2, hiw, idesc, 1u);
+                            mma_commit(&sm.bar_empty[s1]);
+                        } else {
+                            mma_ts2(acc, tcol, bl, hiw, idesc, kb ? 1u : 0u);
+                            mma_ts2(acc, tcol + 8u, bl, hiw, idesc, 1u);
+                            mma_ts2(acc, tcol + 16u, bl + KADV, hiw, idesc, 1u);
+                            mma_ts2(acc, tcol + 24u, bl + KADV, hiw, idesc, 1u);
+                            mma_commit(&sm.bar_empty[s0]);
+                            mma_ts2(acc, tcol, bl2, hiw, idesc, 1u);
+                            mma_ts2(acc, tcol + 16u, bl2 + KADV, hiw, idesc, 1u);
+                            mma_commit(&sm.bar_empty[s1]);
                         }
-                        {   // ---- W_lo image
-                            const uint32_t s = n & (tc5::NSTAGE - 1), ph = (n >> 2) & 1u;
-                            if (!PNB_TIMED_WAIT(3, mbar_wait(&sm.bar_full[s], ph, p.err, 46))) { ok = false; break; }
-                            tc_fence_after();
-                            const uint32_t bl = b0_lo + s * (IMG >> 4);
-                            if (l == 0) {
-                                mma_ss2(acc, akb_hi, hiw, bl, hiw, idesc, 1u);
-                                mma_ss2(acc, akb_hi + KADV, hiw, bl + KADV, hiw, idesc, 1u);
-                            } else if (kb == 8) {
-                                mma_ss2(acc, xeh_lo, xe_hiw, bl, hiw, idesc, 1u);
-                            } else {
-                                mma_ts2(acc, tcol, bl, hiw, idesc, 1u);
-                                mma_ts2(acc, tcol + 16u, bl + KADV, hiw, idesc, 1u);
-                            }
-                            mma_commit(&sm.bar_empty[s]);
-                            ++n;
-                        }
+                        n += 2;
                     }
                     if (!ok) break;
                     if (l >= 1) ++c_pack;

@@ -77,6 +77,24 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
+// Probe up to four barriers with independent try_wait instructions (their ~100-cycle latencies overlap instead of
+// adding up on the single issuing thread); returns true only if all phases have completed.
+__device__ __forceinline__ bool mbar_try_wait4(uint64_t* b0, uint32_t p0, uint64_t* b1, uint32_t p1, uint64_t* b2, uint32_t p2,
+                                               uint64_t* b3, uint32_t p3) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred q0, q1, q2, q3;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 q0, [%1], %5;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 q1, [%2], %6;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 q2, [%3], %7;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 q3, [%4], %8;\n\t"
+        "and.pred q0, q0, q1;\n\tand.pred q2, q2, q3;\n\tand.pred q0, q0, q2;\n\t"
+        "selp.u32 %0, 1, 0, q0;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(b0)), "r"(smem_u32(b1)), "r"(smem_u32(b2)), "r"(smem_u32(b3)), "r"(p0), "r"(p1), "r"(p2), "r"(p3)
+        : "memory");
+    return ok != 0;
+}
 __device__ __forceinline__ uint64_t globaltimer_ns() {
     uint64_t t;
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));

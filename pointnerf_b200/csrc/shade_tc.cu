@@ -969,7 +969,7 @@ struct Smem {
     unsigned char xe_lo[2][tc3::XE];
     float wc[2][tc::TM];
     float alpha_part[2][tc::TM];
-    uint64_t bar_full[NSTAGE], bar_empty[NSTAGE], bar_a1_ready, bar_a1_free, bar_acc_full, bar_drain, bar_chunk[16];
+    uint64_t bar_full[NSTAGE], bar_empty[NSTAGE], bar_a1_ready, bar_a1_free, bar_acc_full, bar_drain, bar_kblk[8];   // bar_kblk[kb]: columns 32kb..32kb+31 converted
     uint32_t tmem_base;
 };
 }  // namespace tc5
@@ -991,7 +991,7 @@ __global__ void __launch_bounds__(tc5::NTHR, 1) k_shade_tc5(ShadeTcParams p) {
         mbar_init(&sm.bar_a1_free, 1);
         mbar_init(&sm.bar_acc_full, 1);
         mbar_init(&sm.bar_drain, tc5::NEPI);
-        for (int c = 0; c < 16; ++c) mbar_init(&sm.bar_chunk[c], 128);
+        for (int c = 0; c < 8; ++c) mbar_init(&sm.bar_kblk[c], 32 * 4 * 2);   // 4 quadrant warps x 2 chunks of 16 columns
         mbar_fence_init();
         if (blockIdx.x == 0 && q.counters[PNB_QC_N_VALID] > p.hbar_cap) atomicExch(p.err, 9);
     }
@@ -1042,14 +1042,13 @@ __global__ void __launch_bounds__(tc5::NTHR, 1) k_shade_tc5(ShadeTcParams p) {
                         const uint32_t s0 = n & (tc5::NSTAGE - 1), ph0 = (n >> 2) & 1u;              // W_hi image
                         const uint32_t s1 = (n + 1) & (tc5::NSTAGE - 1), ph1 = ((n + 1) >> 2) & 1u;   // W_lo image
                         const bool need_chunks = (l >= 1 && kb < 8);  // chunks 2kb, 2kb+1 of the previous layer's output
-                        uint64_t* cb0 = need_chunks ? &sm.bar_chunk[2 * kb] : &sm.bar_full[s0];
-                        uint64_t* cb1 = need_chunks ? &sm.bar_chunk[2 * kb + 1] : &sm.bar_full[s1];
-                        const uint32_t cp0 = need_chunks ? (c_pack & 1u) : ph0, cp1 = need_chunks ? (c_pack & 1u) : ph1;
+                        uint64_t* cb0 = need_chunks ? &sm.bar_kblk[kb] : &sm.bar_full[s0];
+                        uint64_t* cb1 = &sm.bar_full[s1];
+                        const uint32_t cp0 = need_chunks ? (c_pack & 1u) : ph0, cp1 = ph1;
                         // fast path: one overlapped probe of everything this K block needs; slow path: bounded blocking waits
                         if (!mbar_try_wait4(&sm.bar_full[s0], ph0, &sm.bar_full[s1], ph1, cb0, cp0, cb1, cp1)) {
                             if (need_chunks) {
                                 if (!PNB_TIMED_WAIT(2, mbar_wait(cb0, cp0, p.err, 45))) { ok = false; break; }
-                                if (!PNB_TIMED_WAIT(2, mbar_wait(cb1, cp1, p.err, 45))) { ok = false; break; }
                             }
                             if (!PNB_TIMED_WAIT(3, mbar_wait(&sm.bar_full[s0], ph0, p.err, 46))) { ok = false; break; }
                             if (!PNB_TIMED_WAIT(3, mbar_wait(&sm.bar_full[s1], ph1, p.err, 46))) { ok = false; break; }
@@ -1139,7 +1138,7 @@ __global__ void __launch_bounds__(tc5::NTHR, 1) k_shade_tc5(ShadeTcParams p) {
                         tmem_st8(accb + (uint32_t)c0 + 8u, ll);
                         tmem_st_wait();
                         tc_fence_before();
-                        mbar_arrive(&sm.bar_chunk[g]);
+                        mbar_arrive(&sm.bar_kblk[g >> 1]);
                     }
                     if (tid == 0) prof_add(p.err, 7, clock64() - _te0);
                 } else {

@@ -411,6 +411,7 @@ __global__ void __launch_bounds__(tc::NTHR, 1) k_shade_tc(ShadeTcParams p) {
 __device__ __forceinline__ void prof_add(int* err, int slot, long long cyc) {
     if (blockIdx.x == 0) atomicAdd(reinterpret_cast<unsigned long long*>(err) + 1 + slot, (unsigned long long)cyc);
 }
+#define PNB_TIMED_WAIT_L0(slot, expr) [&]() { long long _t0 = clock64(); bool _r = (expr); if ((threadIdx.x & 31) == 0) prof_add(p.err, slot, clock64() - _t0); return _r; }()
 #define PNB_TIMED_WAIT(slot, expr) [&]() { long long _t0 = clock64(); bool _r = (expr); prof_add(p.err, slot, clock64() - _t0); return _r; }()
 
 namespace tc3 {
@@ -1015,8 +1016,9 @@ __global__ void __launch_bounds__(tc5::NTHR, 1) k_shade_tc5(ShadeTcParams p) {
             }
         }
     } else if (warp == W_ISSUE) {
-        // ============================================================ MMA issuer
-        if (lane == 0) {
+        // ============================================================ MMA issuer: the whole warp runs this loop
+        // (warp-uniform control flow and operands); one elected lane issues each tcgen05 instruction
+        {
             const uint32_t idesc = make_idesc_bf16(128, 256);
             const uint32_t hiw = desc_hi<LAYOUT>(), xe_hiw = (256u >> 4) | (1u << 14);
             const uint32_t b0_lo = desc_lo<LAYOUT>(smem_u32(sm.b[0]));
@@ -1033,9 +1035,9 @@ __global__ void __launch_bounds__(tc5::NTHR, 1) k_shade_tc5(ShadeTcParams p) {
                     const uint32_t acc = (l & 1) ? tP : tQ;           // accumulator of this layer
                     const uint32_t ab = (l & 1) ? tQ : tP;            // packed A operand of this layer (l >= 1)
                     // all MMAs of the previous layer (global order) must be complete before their A region becomes this accumulator
-                    if (t > 0 || l > 0) { if (!PNB_TIMED_WAIT(2, mbar_wait(&sm.bar_acc_full, c_acc & 1u, p.err, 42))) { ok = false; break; } ++c_acc; }
-                    if (l == 0) { if (!PNB_TIMED_WAIT(1, mbar_wait(&sm.bar_a1_ready, (uint32_t)t & 1u, p.err, 43))) { ok = false; break; } }
-                    if (l == 1 && t > 0) { if (!PNB_TIMED_WAIT(2, mbar_wait(&sm.bar_drain, (uint32_t)(t - 1) & 1u, p.err, 44))) { ok = false; break; } }
+                    if (t > 0 || l > 0) { if (!PNB_TIMED_WAIT_L0(2, mbar_wait(&sm.bar_acc_full, c_acc & 1u, p.err, 42))) { ok = false; break; } ++c_acc; }
+                    if (l == 0) { if (!PNB_TIMED_WAIT_L0(1, mbar_wait(&sm.bar_a1_ready, (uint32_t)t & 1u, p.err, 43))) { ok = false; break; } }
+                    if (l == 1 && t > 0) { if (!PNB_TIMED_WAIT_L0(2, mbar_wait(&sm.bar_drain, (uint32_t)(t - 1) & 1u, p.err, 44))) { ok = false; break; } }
                     tc_fence_after();
                     const int nkb = nkb_of(l);
                     for (int kb = 0; kb < nkb && ok; ++kb) {
@@ -1048,46 +1050,46 @@ __global__ void __launch_bounds__(tc5::NTHR, 1) k_shade_tc5(ShadeTcParams p) {
                         // fast path: one overlapped probe of everything this K block needs; slow path: bounded blocking waits
                         if (!mbar_try_wait4(&sm.bar_full[s0], ph0, &sm.bar_full[s1], ph1, cb0, cp0, cb1, cp1)) {
                             if (need_chunks) {
-                                if (!PNB_TIMED_WAIT(2, mbar_wait(cb0, cp0, p.err, 45))) { ok = false; break; }
+                                if (!PNB_TIMED_WAIT_L0(2, mbar_wait(cb0, cp0, p.err, 45))) { ok = false; break; }
                             }
-                            if (!PNB_TIMED_WAIT(3, mbar_wait(&sm.bar_full[s0], ph0, p.err, 46))) { ok = false; break; }
-                            if (!PNB_TIMED_WAIT(3, mbar_wait(&sm.bar_full[s1], ph1, p.err, 46))) { ok = false; break; }
+                            if (!PNB_TIMED_WAIT_L0(3, mbar_wait(&sm.bar_full[s0], ph0, p.err, 46))) { ok = false; break; }
+                            if (!PNB_TIMED_WAIT_L0(3, mbar_wait(&sm.bar_full[s1], ph1, p.err, 46))) { ok = false; break; }
                         }
                         tc_fence_after();
                         const uint32_t akb_hi = ahi_lo + (uint32_t)kb * (ABLK >> 4), akb_lo = alo_lo + (uint32_t)kb * (ABLK >> 4);
                         const uint32_t tcol = ab + (uint32_t)(kb * 32);
                         const uint32_t bl = b0_lo + s0 * (IMG >> 4), bl2 = b0_lo + s1 * (IMG >> 4);
                         if (l == 0) {
-                            mma_ss2(acc, akb_hi, hiw, bl, hiw, idesc, kb ? 1u : 0u);
-                            mma_ss2(acc, akb_lo, hiw, bl, hiw, idesc, 1u);
-                            mma_ss2(acc, akb_hi + KADV, hiw, bl + KADV, hiw, idesc, 1u);
-                            mma_ss2(acc, akb_lo + KADV, hiw, bl + KADV, hiw, idesc, 1u);
-                            mma_commit(&sm.bar_empty[s0]);
-                            mma_ss2(acc, akb_hi, hiw, bl2, hiw, idesc, 1u);
-                            mma_ss2(acc, akb_hi + KADV, hiw, bl2 + KADV, hiw, idesc, 1u);
-                            mma_commit(&sm.bar_empty[s1]);
+                            mma_ss2_w(acc, akb_hi, hiw, bl, hiw, idesc, kb ? 1u : 0u);
+                            mma_ss2_w(acc, akb_lo, hiw, bl, hiw, idesc, 1u);
+                            mma_ss2_w(acc, akb_hi + KADV, hiw, bl + KADV, hiw, idesc, 1u);
+                            mma_ss2_w(acc, akb_lo + KADV, hiw, bl + KADV, hiw, idesc, 1u);
+                            mma_commit_w(&sm.bar_empty[s0]);
+                            mma_ss2_w(acc, akb_hi, hiw, bl2, hiw, idesc, 1u);
+                            mma_ss2_w(acc, akb_hi + KADV, hiw, bl2 + KADV, hiw, idesc, 1u);
+                            mma_commit_w(&sm.bar_empty[s1]);
                         } else if (kb == 8) {
-                            mma_ss2(acc, xeh_lo, xe_hiw, bl, hiw, idesc, 1u);
-                            mma_ss2(acc, xel_lo, xe_hiw, bl, hiw, idesc, 1u);
-                            mma_commit(&sm.bar_empty[s0]);
-                            mma_ss2(acc, xeh_lo, xe_hiw, bl2, hiw, idesc, 1u);
-                            mma_commit(&sm.bar_empty[s1]);
+                            mma_ss2_w(acc, xeh_lo, xe_hiw, bl, hiw, idesc, 1u);
+                            mma_ss2_w(acc, xel_lo, xe_hiw, bl, hiw, idesc, 1u);
+                            mma_commit_w(&sm.bar_empty[s0]);
+                            mma_ss2_w(acc, xeh_lo, xe_hiw, bl2, hiw, idesc, 1u);
+                            mma_commit_w(&sm.bar_empty[s1]);
                         } else {
-                            mma_ts2(acc, tcol, bl, hiw, idesc, kb ? 1u : 0u);
-                            mma_ts2(acc, tcol + 8u, bl, hiw, idesc, 1u);
-                            mma_ts2(acc, tcol + 16u, bl + KADV, hiw, idesc, 1u);
-                            mma_ts2(acc, tcol + 24u, bl + KADV, hiw, idesc, 1u);
-                            mma_commit(&sm.bar_empty[s0]);
-                            mma_ts2(acc, tcol, bl2, hiw, idesc, 1u);
-                            mma_ts2(acc, tcol + 16u, bl2 + KADV, hiw, idesc, 1u);
-                            mma_commit(&sm.bar_empty[s1]);
+                            mma_ts2_w(acc, tcol, bl, hiw, idesc, kb ? 1u : 0u);
+                            mma_ts2_w(acc, tcol + 8u, bl, hiw, idesc, 1u);
+                            mma_ts2_w(acc, tcol + 16u, bl + KADV, hiw, idesc, 1u);
+                            mma_ts2_w(acc, tcol + 24u, bl + KADV, hiw, idesc, 1u);
+                            mma_commit_w(&sm.bar_empty[s0]);
+                            mma_ts2_w(acc, tcol, bl2, hiw, idesc, 1u);
+                            mma_ts2_w(acc, tcol + 16u, bl2 + KADV, hiw, idesc, 1u);
+                            mma_commit_w(&sm.bar_empty[s1]);
                         }
                         n += 2;
                     }
                     if (!ok) break;
                     if (l >= 1) ++c_pack;
-                    mma_commit(&sm.bar_acc_full);
-                    if (l == 0) mma_commit(&sm.bar_a1_free);
+                    mma_commit_w(&sm.bar_acc_full);
+                    if (l == 0) mma_commit_w(&sm.bar_a1_free);
                 }
             }
         }

@@ -196,7 +196,7 @@ def main():
     ap.add_argument("--sr", type=int, default=24)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--precision", type=str, default="bf16x3", help="bf16x3 (tcgen05, default) | fp32 (CUDA cores)")
-    ap.add_argument("--tc-version", type=int, default=3, help="tcgen05 pipeline variant: 3 (TS form, default) | 2")
+    ap.add_argument("--tc-version", type=int, default=5, help="tcgen05 pipeline variant: 5 (TMEM ping-pong, default) | 3 | 2")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
@@ -334,7 +334,7 @@ def main():
     traffic = None
     tfile = os.path.join(ROOT, "profiles", "r01_ncu_dram_traffic.json")
     if os.path.exists(tfile) and args.precision != "fp32" and world == 1 and args.sr == 24:
-        traffic = json.load(open(tfile)).get("k_shade_tc3" if net.tc_mask & 4 else "", None)
+        traffic = json.load(open(tfile)).get("k_shade_tc5" if net.tc_mask & 32 else "k_shade_tc3" if net.tc_mask & 4 else "", None)
     flops = kflops
     achieved = flops / (shade_avg * 1e-3) / 1e12
     peak = pk["bf16_tflops"]

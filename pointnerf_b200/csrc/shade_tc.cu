@@ -1280,7 +1280,7 @@ __global__ void __launch_bounds__(ctc::NTHR, 1) k_color_tc(ColorTcParams p) {
             }
         }
     } else if (warp == 9) {
-        if (lane == 0) {
+        {   // whole warp, warp-uniform; one elected lane issues
             const uint32_t idesc = make_idesc_bf16(128, 128);
             const uint32_t hiw = desc_hi<tc::LAYOUT>();
             const uint32_t b0_lo = desc_lo<tc::LAYOUT>(smem_u32(sm.b[0]));
@@ -1302,17 +1302,17 @@ __global__ void __launch_bounds__(ctc::NTHR, 1) k_color_tc(ColorTcParams p) {
                             tc_fence_after();
                             const uint32_t bl = b0_lo + s * (IMG >> 4);
                             if (l == 0) {
-                                mma_ss2(tacc, akb_hi, hiw, bl, hiw, idesc, kb ? 1u : 0u);
-                                mma_ss2(tacc, akb_lo, hiw, bl, hiw, idesc, 1u);
-                                mma_ss2(tacc, akb_hi + KADV, hiw, bl + KADV, hiw, idesc, 1u);
-                                mma_ss2(tacc, akb_lo + KADV, hiw, bl + KADV, hiw, idesc, 1u);
+                                mma_ss2_w(tacc, akb_hi, hiw, bl, hiw, idesc, kb ? 1u : 0u);
+                                mma_ss2_w(tacc, akb_lo, hiw, bl, hiw, idesc, 1u);
+                                mma_ss2_w(tacc, akb_hi + KADV, hiw, bl + KADV, hiw, idesc, 1u);
+                                mma_ss2_w(tacc, akb_lo + KADV, hiw, bl + KADV, hiw, idesc, 1u);
                             } else {
-                                mma_ts2(tacc, t_ahi + tcol, bl, hiw, idesc, kb ? 1u : 0u);
-                                mma_ts2(tacc, t_alo + tcol, bl, hiw, idesc, 1u);
-                                mma_ts2(tacc, t_ahi + tcol + 8u, bl + KADV, hiw, idesc, 1u);
-                                mma_ts2(tacc, t_alo + tcol + 8u, bl + KADV, hiw, idesc, 1u);
+                                mma_ts2_w(tacc, t_ahi + tcol, bl, hiw, idesc, kb ? 1u : 0u);
+                                mma_ts2_w(tacc, t_alo + tcol, bl, hiw, idesc, 1u);
+                                mma_ts2_w(tacc, t_ahi + tcol + 8u, bl + KADV, hiw, idesc, 1u);
+                                mma_ts2_w(tacc, t_alo + tcol + 8u, bl + KADV, hiw, idesc, 1u);
                             }
-                            mma_commit(&sm.bar_empty[s]);
+                            mma_commit_w(&sm.bar_empty[s]);
                             ++n;
                         }
                         {
@@ -1321,17 +1321,17 @@ __global__ void __launch_bounds__(ctc::NTHR, 1) k_color_tc(ColorTcParams p) {
                             tc_fence_after();
                             const uint32_t bl = b0_lo + s * (IMG >> 4);
                             if (l == 0) {
-                                mma_ss2(tacc, akb_hi, hiw, bl, hiw, idesc, 1u);
-                                mma_ss2(tacc, akb_hi + KADV, hiw, bl + KADV, hiw, idesc, 1u);
+                                mma_ss2_w(tacc, akb_hi, hiw, bl, hiw, idesc, 1u);
+                                mma_ss2_w(tacc, akb_hi + KADV, hiw, bl + KADV, hiw, idesc, 1u);
                             } else {
-                                mma_ts2(tacc, t_ahi + tcol, bl, hiw, idesc, 1u);
-                                mma_ts2(tacc, t_ahi + tcol + 8u, bl + KADV, hiw, idesc, 1u);
+                                mma_ts2_w(tacc, t_ahi + tcol, bl, hiw, idesc, 1u);
+                                mma_ts2_w(tacc, t_ahi + tcol + 8u, bl + KADV, hiw, idesc, 1u);
                             }
-                            mma_commit(&sm.bar_empty[s]);
+                            mma_commit_w(&sm.bar_empty[s]);
                             ++n;
                         }
                     }
-                    mma_commit(&sm.bar_acc_full);
+                    mma_commit_w(&sm.bar_acc_full);
                 }
             }
         }

@@ -286,10 +286,10 @@ def _init_state(mod):
     mod.precision = getattr(opt, "pnb_precision", "bf16x3")
     if mod.precision not in ("bf16x3", "fp32"):
         raise NotImplementedError("pnb200: pnb_precision=%r (bf16x3 | fp32)" % mod.precision)
-    # tcgen05 pipeline variant: 3 = A operand of layers 2-4 in tensor memory + overlapped operand builders (default),
-    # 5 = chunk-pipelined TMEM role ping-pong (epilogue of layer l under the MMAs of layer l+1; same speed),
+    # tcgen05 pipeline variant: 5 = chunk-pipelined TMEM role ping-pong (epilogue of layer l under the MMAs of layer l+1;
+    # default), 3 = A operand of layers 2-4 in tensor memory + overlapped operand builders, epilogues exposed,
     # 2 = serialized shared-memory pipeline
-    _v = int(getattr(opt, "pnb_tc_version", 3))
+    _v = int(getattr(opt, "pnb_tc_version", 5))
     if _v not in (2, 3, 5):
         raise NotImplementedError("pnb200: pnb_tc_version=%r (2 | 3 | 5)" % _v)
     mod.tc_mask = 3 | (12 if _v == 3 else 0) | (8 + 32 if _v == 5 else 0)

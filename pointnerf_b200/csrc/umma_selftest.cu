@@ -208,6 +208,134 @@ __global__ void __launch_bounds__(128, 1) k_umma_selftest_ts(const float* __rest
     if (warp == 0) tmem_dealloc<512>(tacc);
 }
 
+// CTA-pair form (cluster of 2, tcgen05 cta_group::2): D[256 x N] = A[256 x K] * W[N x K]^T.  CTA r stages A rows
+// 128r.. (shared memory, mode 0, or tensor memory columns 256../384.., mode 1) and W rows (N/2)r.. ; the rank-0 CTA
+// issues the MMAs and commits with a multicast arrive to the barrier of both CTAs.  bench_iters > 0 additionally times
+// that many back-to-back MMAs (out[0] issue cycles, out[1] until complete) after D has been written.
+template <int LAYOUT>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1)
+    k_umma_selftest2(const float* __restrict__ A, const float* __restrict__ W, float* __restrict__ D, int K, int N, int mode,
+                     int bench_iters, long long* __restrict__ out, int* err) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    const int nkb = (K + BK - 1) / BK;
+    unsigned char* b_hi = smem;                  // [N/2 x 32]
+    unsigned char* b_lo = b_hi + 128 * 64;
+    unsigned char* a_hi = b_lo + 128 * 64;       // nkb blocks of [128 x 32] (mode 0)
+    unsigned char* a_lo = a_hi + nkb * 8192;
+    __shared__ uint64_t bar;
+    __shared__ uint32_t tmem_base;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t rank = cluster_ctarank();
+    const int NH = N >> 1;
+
+    if (tid == 0) { mbar_init(&bar, 1); mbar_fence_init(); }
+    if (warp == 0) tmem_alloc2<512>(&tmem_base);
+    tc_fence_before();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tacc = tmem_base;
+    const uint32_t tlane = (uint32_t)(warp * 32) << 16;
+    const int row = warp * 32 + lane, grow = (int)rank * 128 + row;
+    if (mode == 0) {
+        for (int k = 0; k < nkb * BK; ++k) {
+            float v = k < K ? A[(size_t)grow * K + k] : 0.f;
+            __nv_bfloat16 h, l;
+            split_bf16(v, h, l);
+            uint32_t off = (uint32_t)(k / BK) * 8192u + tile_offset_bytes<LAYOUT>(row, k % BK);
+            *(__nv_bfloat16*)(a_hi + off) = h;
+            *(__nv_bfloat16*)(a_lo + off) = l;
+        }
+    } else {
+        for (int k0 = 0; k0 < 256; k0 += 16) {
+            uint32_t h[8], l[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                int k = k0 + 2 * i;
+                float a = k < K ? A[(size_t)grow * K + k] : 0.f, b = k + 1 < K ? A[(size_t)grow * K + k + 1] : 0.f;
+                split_bf16x2(a, b, h[i], l[i]);
+            }
+            tmem_st8(tacc + tlane + 256u + (uint32_t)(k0 >> 1), h);
+            tmem_st8(tacc + tlane + 384u + (uint32_t)(k0 >> 1), l);
+        }
+        tmem_st_wait();
+    }
+    const uint32_t idesc = make_idesc_bf16(256, N);
+    const uint32_t hiw = desc_hi<LAYOUT>();
+    constexpr uint32_t KADV = kstep_adv16<LAYOUT>();
+    uint32_t phase = 0;
+    bool ok = true;
+    for (int kb = 0; kb < nkb && ok; ++kb) {
+        for (int i = tid; i < NH * BK; i += 128) {
+            int n = i / BK, k = i - n * BK;
+            int kg = kb * BK + k;
+            float v = kg < K ? W[(size_t)((int)rank * NH + n) * K + kg] : 0.f;
+            __nv_bfloat16 h, l;
+            split_bf16(v, h, l);
+            uint32_t off = tile_offset_bytes<LAYOUT>(n, k);
+            *(__nv_bfloat16*)(b_hi + off) = h;
+            *(__nv_bfloat16*)(b_lo + off) = l;
+        }
+        fence_proxy_async();
+        tc_fence_before();
+        cluster_sync_all();
+        if (rank == 0 && warp == 0) {
+            tc_fence_after();
+            const int nks = (min(K - kb * BK, BK) + 15) / 16;
+            for (int ks = 0; ks < nks; ++ks) {
+                const uint32_t bh = desc_lo<LAYOUT>(smem_u32(b_hi)) + ks * KADV, bl = desc_lo<LAYOUT>(smem_u32(b_lo)) + ks * KADV;
+                const uint32_t acc_flag = (kb | ks) ? 1u : 0u;
+                if (mode == 0) {
+                    const uint32_t ah = desc_lo<LAYOUT>(smem_u32(a_hi + kb * 8192)) + ks * KADV, al = desc_lo<LAYOUT>(smem_u32(a_lo + kb * 8192)) + ks * KADV;
+                    mma2_ss2_w(tacc, ah, hiw, bh, hiw, idesc, acc_flag);
+                    mma2_ss2_w(tacc, al, hiw, bh, hiw, idesc, 1u);
+                    mma2_ss2_w(tacc, ah, hiw, bl, hiw, idesc, 1u);
+                } else {
+                    const uint32_t kcol = (uint32_t)(kb * BK + ks * 16);
+                    mma2_ts2_w(tacc, tacc + 256u + (kcol >> 1), bh, hiw, idesc, acc_flag);
+                    mma2_ts2_w(tacc, tacc + 384u + (kcol >> 1), bh, hiw, idesc, 1u);
+                    mma2_ts2_w(tacc, tacc + 256u + (kcol >> 1), bl, hiw, idesc, 1u);
+                }
+            }
+            mma2_commit_w(&bar, 3);
+        }
+        if (!mbar_wait(&bar, phase, err, 400 + kb)) ok = false;
+        phase ^= 1;
+        tc_fence_after();
+    }
+    if (ok) {
+        for (int c0 = 0; c0 < N; c0 += 32) {
+            uint32_t v[32];
+            tmem_ld32(tacc + tlane + (uint32_t)c0, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+                if (c0 + j < N) D[(size_t)grow * N + c0 + j] = __uint_as_float(v[j]);
+        }
+    }
+    tc_fence_before();
+    cluster_sync_all();
+    tc_fence_after();
+    if (bench_iters > 0 && ok) {
+        long long t0 = 0, t1 = 0;
+        if (rank == 0 && warp == 0) {
+            const uint32_t bh = desc_lo<LAYOUT>(smem_u32(b_hi)), ah = desc_lo<LAYOUT>(smem_u32(a_hi));
+            t0 = clock64();
+            for (int i = 0; i < bench_iters; ++i) {
+                if (mode == 0) mma2_ss2_w(tacc, ah, hiw, bh, hiw, idesc, 1u);
+                else mma2_ts2_w(tacc, tacc + 256u, bh, hiw, idesc, 1u);
+            }
+            mma2_commit_w(&bar, 3);
+            t1 = clock64();
+        }
+        mbar_wait(&bar, phase, err, 450);
+        if (rank == 0 && tid == 0) { out[0] = t1 - t0; out[1] = clock64() - t0; }
+    }
+    tc_fence_before();
+    cluster_sync_all();
+    if (warp == 0) tmem_dealloc2<512>(tacc);
+}
+
 // Micro-benchmark: cycles per tcgen05.mma (M=128, N=256, K=16, bf16) issued back to back on resident operands.
 // mode 0: A and B in shared memory (SS), mode 1: A in tensor memory (TS).  bulk = 1 adds a concurrent stream of
 // 16 KB cp.async.bulk copies into a second shared buffer (the weight-streaming traffic of the fused kernel).
@@ -326,6 +454,24 @@ extern "C" int pnb_umma_bench(int layout, int mode, int iters, int bulk, const v
         PNB_CHECK_CUDA(cudaFuncSetAttribute(k_umma_bench<umma::LAYOUT_NONE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         k_umma_bench<umma::LAYOUT_NONE><<<1, 128, smem, stream>>>(mode, iters, bulk, (const unsigned char*)d_src, d_out, d_err);
     }
+    PNB_CHECK_CUDA(cudaGetLastError());
+    return PNB_OK;
+}
+
+// CTA-pair self-test / micro-benchmark (cluster of 2, cta_group::2): d_A [256 x K], d_W [N x K], d_D [256 x N];
+// mode 0 = A in shared memory (K <= 288), 1 = A in tensor memory (K <= 256, K % 16 == 0); N % 32 == 0.
+// bench_iters > 0: d_out int64[2] = issue cycles / cycles until complete of that many back-to-back MMAs.
+extern "C" int pnb_umma_selftest2(const float* d_A, const float* d_W, float* d_D, int K, int N, int mode, int bench_iters,
+                                  long long* d_out, int* d_err, pnb_stream_t stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    PNB_REQUIRE(d_A && d_W && d_D && d_err, PNB_ERR_INVALID, "pnb_umma_selftest2: null argument");
+    PNB_REQUIRE(K >= 16 && K <= (mode ? 256 : 288) && (mode == 0 || K % 16 == 0) && N >= 32 && N <= 256 && N % 32 == 0, PNB_ERR_INVALID,
+                "pnb_umma_selftest2: bad K/N");
+    PNB_REQUIRE(bench_iters == 0 || d_out, PNB_ERR_INVALID, "pnb_umma_selftest2: bench needs d_out");
+    const int nkb = (K + 31) / 32;
+    size_t smem = (size_t)nkb * 8192 * 2 + 128 * 64 * 2 + 1024;
+    PNB_CHECK_CUDA(cudaFuncSetAttribute(k_umma_selftest2<umma::LAYOUT_NONE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_umma_selftest2<umma::LAYOUT_NONE><<<2, 128, smem, stream>>>(d_A, d_W, d_D, K, N, mode, bench_iters, d_out, d_err);
     PNB_CHECK_CUDA(cudaGetLastError());
     return PNB_OK;
 }

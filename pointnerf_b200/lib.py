@@ -54,7 +54,7 @@ QC = dict(n_cand=0, n_valid=1, n_pairs=2, R1=3, R2=4, overflow=5)
 SYMBOLS = ["pnb_version", "pnb_last_error", "pnb_struct_size", "pnb_grid_bytes", "pnb_grid_build", "pnb_query_bytes", "pnb_query",
            "pnb_query_export", "pnb_shade_bytes", "pnb_shade_forward", "pnb_composite_forward", "pnb_umma_selftest",
            "pnb_mlp_pack_bytes", "pnb_mlp_pack", "pnb_shade_tc_bytes", "pnb_shade_forward_tc",
-           "pnb_backward_bytes", "pnb_shade_backward", "pnb_umma_bench"]
+           "pnb_backward_bytes", "pnb_shade_backward", "pnb_umma_bench", "pnb_umma_selftest2"]
 
 _lib = None
 
@@ -117,6 +117,9 @@ def load():
                                        C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_void_p, C.c_size_t, C.c_void_p]
     lib.pnb_umma_bench.restype = C.c_int
     lib.pnb_umma_bench.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.pnb_umma_selftest2.restype = C.c_int
+    lib.pnb_umma_selftest2.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                       C.c_void_p]
     lib.pnb_umma_selftest.restype = C.c_int
     lib.pnb_umma_selftest.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
     _lib = lib

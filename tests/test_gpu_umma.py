@@ -47,3 +47,22 @@ def test_umma_a_operand_in_tensor_memory(layout, K, N):
     ref = (A.double() @ W.double().t())
     d = (D.double() - ref).abs().max().item()
     assert d <= 2e-5 * max(ref.abs().max().item(), 1.0), "mode %d K=%d N=%d: max abs err %.3e" % (layout, K, N, d)
+
+
+@pytest.mark.parametrize("mode,K,N", [(0, 32, 256), (0, 288, 256), (0, 64, 64), (1, 16, 32), (1, 256, 256), (1, 64, 128)])
+def test_umma_cta_pair(mode, K, N):
+    """cta_group::2 (cluster of 2): M=256, each CTA stages half of B; SS and TS forms, multicast commit."""
+    l = _lib.load()
+    g = torch.Generator(device=DEV).manual_seed(K * 13 + N + mode)
+    A = torch.randn(256, K, device=DEV, generator=g).contiguous()
+    W = (torch.randn(N, K, device=DEV, generator=g) / K ** 0.5).contiguous()
+    D = torch.full((256, N), float("nan"), device=DEV)
+    err = torch.zeros(1, dtype=torch.int32, device=DEV)
+    out = torch.zeros(2, dtype=torch.int64, device=DEV)
+    _lib.check(l.pnb_umma_selftest2(A.data_ptr(), W.data_ptr(), D.data_ptr(), K, N, mode, 0, out.data_ptr(), err.data_ptr(),
+                                    torch.cuda.current_stream().cuda_stream), "pnb_umma_selftest2")
+    torch.cuda.synchronize()
+    assert int(err.item()) == 0, "pipeline timeout code %d" % int(err.item())
+    ref = A.double() @ W.double().t()
+    d = (D.double() - ref).abs().max().item()
+    assert d <= 2e-5 * max(ref.abs().max().item(), 1.0), "mode %d K=%d N=%d: max abs err %.3e" % (mode, K, N, d)

@@ -216,9 +216,10 @@ int pnb_umma_bench(int layout, int mode, int iters, int bulk, const void* d_src,
                    pnb_stream_t stream);
 
 /* CTA-pair (cluster of 2, tcgen05 cta_group::2) self-test and MMA-rate probe: D[256,N] = A[256,K] * W[N,K]^T.
- * mode 0: A operand in shared memory, 1: in tensor memory.  bench_iters > 0: d_out int64[2] (issue / total cycles). */
+ * mode 0: A operand in shared memory, 1: in tensor memory.  bench_iters > 0: d_out int64[2] (issue / total cycles);
+ * bench_flags: bits 0-7 interleave a tcgen05.commit every n MMAs, bits 8-9 its form (see umma_selftest.cu). */
 int pnb_umma_selftest2(const float* d_A, const float* d_W, float* d_D, int K, int N, int mode, int bench_iters,
-                       long long* d_out, int* d_err, pnb_stream_t stream);
+                       int bench_flags, long long* d_out, int* d_err, pnb_stream_t stream);
 
 #ifdef __cplusplus
 }

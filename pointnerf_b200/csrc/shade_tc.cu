@@ -67,6 +67,7 @@ struct ShadeTcParams {
     int hbar_cap;
     int* err;
     int dbg_no_weights;          // timing experiment only: the loader signals the ring without copying (results are garbage)
+    int dbg_flags;               // bit 1: v6 issuer classifies its waits with non-blocking probes (profiling)
 };
 
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
@@ -451,10 +452,15 @@ __device__ __forceinline__ void store_chunk8_a1(SmemT& sm, int r, int kb, int k8
 }
 
 // One pair row of the block1 operand (gather, distance weights, PE by angle doubling, hi/lo split -> shared memory),
-// its block3 extras operand and its weight*conf factor.  Shared by the v3 / v4 pipelines (one builder thread per row).
-template <class SmemT>
-__device__ __forceinline__ void build_pair_row(SmemT& sm, const ShadeTcParams& p, int tile, int t, int row, int n_valid) {
+// its block3 extras operand and its weight*conf factor.  PART 2: the whole row (v3 / v5: one builder thread per row);
+// PART 0 / 1: the two halves of a row for the v6 pipeline (two builder threads per row):
+//   part 0 = operand columns 0..151   (raw features, PE of features 0..19)
+//   part 1 = operand columns 152..287 (PE of features 20..31, PE of the 6 distances), extras operand, weight*conf
+template <int PART, class SmemT>
+__device__ __forceinline__ void build_pair_part(SmemT& sm, const ShadeTcParams& p, int tile, int t, int row, int n_valid) {
     using namespace tc;
+    constexpr bool P0 = PART != 1, P1 = PART != 0;
+    constexpr int G_LO = P0 ? 0 : 5, G_HI = P1 ? 8 : 5;      // feature groups (4 features each) whose PE this part builds
     const pnb_query_t& q = p.q;
     const int si = row >> 3, k = row & 7;
     const int vi = tile * TSAMP + si;
@@ -462,35 +468,37 @@ __device__ __forceinline__ void build_pair_row(SmemT& sm, const ShadeTcParams& p
     float lx = 0.f, ly = 0.f, lz = 0.f, vx = 0.f, vy = 0.f, vz = 0.f;
     if (vi < n_valid) {
         uint32_t s = q.valid_list[vi];
-        uint32_t pk = q.samp_ray[s];
-        int r = (int)(pk >> 7), j = (int)(pk & 127u);
-        int d = q.steps[(size_t)r * q.SR + j];
-        float tt = q.t[(size_t)r * q.t_ray_stride + d];
-        vx = q.raydir[3 * r]; vy = q.raydir[3 * r + 1]; vz = q.raydir[3 * r + 2];
-        lx = raypos1(q.campos[0], vx, tt); ly = raypos1(q.campos[1], vy, tt); lz = raypos1(q.campos[2], vz, tt);
+        if (P1) {
+            uint32_t pk = q.samp_ray[s];
+            int r = (int)(pk >> 7), j = (int)(pk & 127u);
+            int d = q.steps[(size_t)r * q.SR + j];
+            float tt = q.t[(size_t)r * q.t_ray_stride + d];
+            vx = q.raydir[3 * r]; vy = q.raydir[3 * r + 1]; vz = q.raydir[3 * r + 2];
+            lx = raypos1(q.campos[0], vx, tt); ly = raypos1(q.campos[1], vy, tt); lz = raypos1(q.campos[2], vz, tt);
+        }
         if (k < q.K) pidx = q.cand_pidx[(size_t)s * q.K + k];
     }
     const bool valid = pidx >= 0;
     const int pi = valid ? pidx : 0;
-    float ovx, ovy, ovz;
-    rot3t(p.o.Rw2c, vx, vy, vz, ovx, ovy, ovz);
-    float px = __ldg(&p.pts.xyz[3 * pi]), py = __ldg(&p.pts.xyz[3 * pi + 1]), pz = __ldg(&p.pts.xyz[3 * pi + 2]);
     float dist[6];
-    dist[0] = px - lx; dist[1] = py - ly; dist[2] = pz - lz;
-    float xpp, ypp, zpp, xsp, ysp, zsp;
-    w2pers_t(p.o, px, py, pz, xpp, ypp, zpp);
-    w2pers_t(p.o, lx, ly, lz, xsp, ysp, zsp);
-    dist[3] = xpp * zpp - xsp * zsp; dist[4] = ypp * zpp - ysp * zsp; dist[5] = zpp - zsp;
-    float nrm = sqrtf(dist[0] * dist[0] + dist[1] * dist[1] + dist[2] * dist[2]);
-    float w = valid ? 1.0f / fmaxf(nrm, 1e-6f) : 0.f;
-    float wsum = w;                        // 8 consecutive lanes = the 8 rows of one sample
-    wsum += __shfl_xor_sync(0xffffffffu, wsum, 1);
-    wsum += __shfl_xor_sync(0xffffffffu, wsum, 2);
-    wsum += __shfl_xor_sync(0xffffffffu, wsum, 4);
-    w = w / fmaxf(wsum, 1e-8f);
-    float cf = __ldg(&p.pts.conf[pi]);
-    sm.wc[t & 1][row] = valid ? w * fminf(fmaxf(cf, 1e-4f), 1.0f) : 0.f;
-    {
+    float ovx = 0.f, ovy = 0.f, ovz = 0.f;
+    if (P1) {
+        rot3t(p.o.Rw2c, vx, vy, vz, ovx, ovy, ovz);
+        float px = __ldg(&p.pts.xyz[3 * pi]), py = __ldg(&p.pts.xyz[3 * pi + 1]), pz = __ldg(&p.pts.xyz[3 * pi + 2]);
+        dist[0] = px - lx; dist[1] = py - ly; dist[2] = pz - lz;
+        float xpp, ypp, zpp, xsp, ysp, zsp;
+        w2pers_t(p.o, px, py, pz, xpp, ypp, zpp);
+        w2pers_t(p.o, lx, ly, lz, xsp, ysp, zsp);
+        dist[3] = xpp * zpp - xsp * zsp; dist[4] = ypp * zpp - ysp * zsp; dist[5] = zpp - zsp;
+        float nrm = sqrtf(dist[0] * dist[0] + dist[1] * dist[1] + dist[2] * dist[2]);
+        float w = valid ? 1.0f / fmaxf(nrm, 1e-6f) : 0.f;
+        float wsum = w;                        // 8 consecutive lanes = the 8 rows of one sample
+        wsum += __shfl_xor_sync(0xffffffffu, wsum, 1);
+        wsum += __shfl_xor_sync(0xffffffffu, wsum, 2);
+        wsum += __shfl_xor_sync(0xffffffffu, wsum, 4);
+        w = w / fmaxf(wsum, 1e-8f);
+        float cf = __ldg(&p.pts.conf[pi]);
+        sm.wc[t & 1][row] = valid ? w * fminf(fmaxf(cf, 1e-4f), 1.0f) : 0.f;
         float d0, d1, d2;
         rot3t(p.o.Rw2c, dist[0], dist[1], dist[2], d0, d1, d2);
         dist[0] = d0; dist[1] = d1; dist[2] = d2;
@@ -499,40 +507,44 @@ __device__ __forceinline__ void build_pair_row(SmemT& sm, const ShadeTcParams& p
     if (valid) {
         const float4* ep = (const float4*)&p.pts.emb[(size_t)pi * PNB_FEAT];
 #pragma unroll
-        for (int g = 0; g < 8; ++g) {          // 4 features per step
+        for (int g = G_LO; g < G_HI; ++g) {    // 4 features per step
             float4 fv = __ldg(ep + g);
             float f[4] = {fv.x, fv.y, fv.z, fv.w};
             float pe[24];
 #pragma unroll
             for (int e = 0; e < 4; ++e) pe_doubling<3>(f[e], pe + e * 6);
-            // (the raw features themselves are stored 8 per chunk in the loop below)
             const int col = 32 + 24 * g;
 #pragma unroll
             for (int c = 0; c < 3; ++c) store_chunk8_a1(sm, row, (col + 8 * c) >> 5, (col + 8 * c) & 31, pe + 8 * c);
         }
+        if (P0) {
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {          // raw features, 8 per chunk (re-read: L1 hit)
-            float4 a = __ldg(ep + 2 * g), b = __ldg(ep + 2 * g + 1);
-            float f8[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-            store_chunk8_a1(sm, row, 0, 8 * g, f8);
+            for (int g = 0; g < 4; ++g) {      // raw features, 8 per chunk (re-read: L1 hit)
+                float4 a = __ldg(ep + 2 * g), b = __ldg(ep + 2 * g + 1);
+                float f8[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+                store_chunk8_a1(sm, row, 0, 8 * g, f8);
+            }
         }
-        float dp[60];
+        if (P1) {
+            float dp[60];
 #pragma unroll
-        for (int e = 0; e < 6; ++e) pe_doubling<5>(dist[e], dp + 10 * e);
-        float z4[8] = {dp[56], dp[57], dp[58], dp[59], 0.f, 0.f, 0.f, 0.f};
+            for (int e = 0; e < 6; ++e) pe_doubling<5>(dist[e], dp + 10 * e);
+            float z4[8] = {dp[56], dp[57], dp[58], dp[59], 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-        for (int c = 0; c < 7; ++c) store_chunk8_a1(sm, row, (224 + 8 * c) >> 5, (224 + 8 * c) & 31, dp + 8 * c);
-        store_chunk8_a1(sm, row, 8, 24, z4);
-        float ddx, ddy, ddz;
-        rot3t(p.o.Rw2c, __ldg(&p.pts.dir[3 * pi]), __ldg(&p.pts.dir[3 * pi + 1]), __ldg(&p.pts.dir[3 * pi + 2]), ddx, ddy, ddz);
-        ex[0] = __ldg(&p.pts.color[3 * pi]); ex[1] = __ldg(&p.pts.color[3 * pi + 1]); ex[2] = __ldg(&p.pts.color[3 * pi + 2]);
-        ex[3] = ddx - ovx; ex[4] = ddy - ovy; ex[5] = ddz - ovz;
-        ex[6] = ddx * ovx + ddy * ovy + ddz * ovz;
+            for (int c = 0; c < 7; ++c) store_chunk8_a1(sm, row, (224 + 8 * c) >> 5, (224 + 8 * c) & 31, dp + 8 * c);
+            store_chunk8_a1(sm, row, 8, 24, z4);
+            float ddx, ddy, ddz;
+            rot3t(p.o.Rw2c, __ldg(&p.pts.dir[3 * pi]), __ldg(&p.pts.dir[3 * pi + 1]), __ldg(&p.pts.dir[3 * pi + 2]), ddx, ddy, ddz);
+            ex[0] = __ldg(&p.pts.color[3 * pi]); ex[1] = __ldg(&p.pts.color[3 * pi + 1]); ex[2] = __ldg(&p.pts.color[3 * pi + 2]);
+            ex[3] = ddx - ovx; ex[4] = ddy - ovy; ex[5] = ddz - ovz;
+            ex[6] = ddx * ovx + ddy * ovy + ddz * ovz;
+        }
     } else {
         float z8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-        for (int c = 0; c < 36; ++c) store_chunk8_a1(sm, row, c >> 2, (c & 3) * 8, z8);
+        constexpr int C_LO = P0 ? 0 : 19, C_HI = P1 ? 36 : 19;   // 16-byte chunks: column / 8
+        for (int c = C_LO; c < C_HI; ++c) store_chunk8_a1(sm, row, c >> 2, (c & 3) * 8, z8);
     }
-    {   // block3 extras operand [128 x 16]: chunk 0 = extras, chunk 1 = 0
+    if (P1) {   // block3 extras operand [128 x 16]: chunk 0 = extras, chunk 1 = 0
         uint32_t h[4], l[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) split_bf16x2(ex[2 * i], ex[2 * i + 1], h[i], l[i]);
@@ -542,6 +554,10 @@ __device__ __forceinline__ void build_pair_row(SmemT& sm, const ShadeTcParams& p
         *reinterpret_cast<uint4*>(sm.xe_hi[t & 1] + off + 128) = make_uint4(0u, 0u, 0u, 0u);
         *reinterpret_cast<uint4*>(sm.xe_lo[t & 1] + off + 128) = make_uint4(0u, 0u, 0u, 0u);
     }
+}
+template <class SmemT>
+__device__ __forceinline__ void build_pair_row(SmemT& sm, const ShadeTcParams& p, int tile, int t, int row, int n_valid) {
+    build_pair_part<2>(sm, p, tile, t, row, n_valid);
 }
 
 __global__ void __launch_bounds__(tc3::NTHR, 1) k_shade_tc3(ShadeTcParams p) {
@@ -1211,6 +1227,299 @@ __global__ void __launch_bounds__(tc5::NTHR, 1) k_shade_tc5(ShadeTcParams p) {
 }
 
 // =====================================================================================================================
+// v6: v5 on a CTA PAIR (cluster of 2, tcgen05 cta_group::2).  Each CTA of the pair owns one 128-row tile (its own
+// builders, epilogue warps, TMEM regions P/Q and layer-1 operand buffer); the rank-0 CTA's issuer warp issues ONE
+// M=256 MMA for both tiles.  The B operand (weight image [256 x 32]) is split by N between the two CTAs: each loader
+// streams only its 8 KB half, the tensor cores read the other half from the peer's shared memory -> half the L2->SMEM
+// weight traffic and half the B reads per SM, and an 8-deep ring in the same 64 KB.
+// Cross-CTA signalling: commits are multicast to the barrier of both CTAs (ring "empty", accumulator-full, operand-free);
+// the peer's builders / epilogue warps arrive remotely on the leader's a1_ready / kblk / drain barriers; the peer's
+// "weight half landed" is forwarded to the leader's full barrier (count 2) by a forwarder thread.
+namespace tc6 {
+constexpr int NEPI_WARPS = 8, NGRP = NEPI_WARPS / 4, NCH = 16 / NGRP;
+constexpr int NEPI = NEPI_WARPS * 32, NBUILD = 256, NTHR = NEPI + NBUILD + 96;   // two builder threads per row; + loader, issuer, forwarder warps
+constexpr int NSTAGE = 4;                // ring stage = one K block: this CTA's half of the W_hi image and of the W_lo image
+constexpr int CPK = 2;                   // K blocks per ring commit: stages are freed in groups of CPK (a tcgen05.commit costs ~140 tensor-pipe cycles)
+constexpr int HIMG = tc::IMG / 2;       // bytes of one half image ([128 x 32] bf16)
+struct Smem {
+    unsigned char a_hi[tc::NKB_MAX * tc::ABLK];
+    unsigned char a_lo[tc::NKB_MAX * tc::ABLK];
+    unsigned char b[NSTAGE][2][HIMG];
+    unsigned char xe_hi[2][tc3::XE];
+    unsigned char xe_lo[2][tc3::XE];
+    float wc[2][tc::TM];
+    float alpha_part[2][tc::TM];
+    uint64_t bar_full[NSTAGE], bar_empty[NSTAGE], bar_a1_ready, bar_a1_free, bar_acc_full, bar_drain, bar_kblk[8];
+    uint32_t tmem_base;
+};
+}  // namespace tc6
+
+#define PROF6_COMMIT(x) { const long long _tc0 = clock64(); x; _t_commit += clock64() - _tc0; }
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(tc6::NTHR, 1) k_shade_tc6(ShadeTcParams p) {
+    using namespace tc;
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    tc6::Smem& sm = *reinterpret_cast<tc6::Smem*>(smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u));
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t rank = cluster_ctarank();
+    const pnb_query_t& q = p.q;
+    const int n_valid = min(q.counters[PNB_QC_N_VALID], p.hbar_cap);
+    const int n_tiles = (n_valid + TSAMP - 1) / TSAMP;
+    const int n_ptiles = (n_tiles + 1) >> 1;                       // pair tiles: tiles 2i (rank 0) and 2i+1 (rank 1)
+    const int pair = (int)blockIdx.x >> 1, npairs = (int)gridDim.x >> 1;
+    const int my_tiles = n_ptiles > pair ? (n_ptiles - 1 - pair) / npairs + 1 : 0;
+    constexpr int W_BUILD = tc6::NEPI_WARPS, W_LOAD = W_BUILD + tc6::NBUILD / 32, W_ISSUE = W_LOAD + 1, W_FWD = W_ISSUE + 1;
+    constexpr uint32_t SMASK = tc6::NSTAGE - 1;
+
+    if (tid == 0) {
+        for (int s = 0; s < tc6::NSTAGE; ++s) { mbar_init(&sm.bar_full[s], rank == 0 ? 2 : 1); mbar_init(&sm.bar_empty[s], 1); }
+        mbar_init(&sm.bar_a1_ready, 2 * tc6::NBUILD);              // leader's: the builder threads of both CTAs
+        mbar_init(&sm.bar_a1_free, 1);
+        mbar_init(&sm.bar_acc_full, 1);
+        mbar_init(&sm.bar_drain, 2 * tc6::NEPI_WARPS);             // leader's: one arrive per epilogue warp of both CTAs
+        for (int c = 0; c < 8; ++c) mbar_init(&sm.bar_kblk[c], 2 * 4 * 2);   // leader's: 2 CTAs x 4 quadrant warps x 2 chunks
+        mbar_fence_init();
+        if (blockIdx.x == 0 && q.counters[PNB_QC_N_VALID] > p.hbar_cap) atomicExch(p.err, 9);
+    }
+    if (warp == W_ISSUE) tmem_alloc2<512>(&sm.tmem_base);
+    tc_fence_before();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tP = sm.tmem_base, tQ = sm.tmem_base + 256u;
+    const long long _tk0 = clock64();
+
+    if (warp == W_LOAD) {
+        // ============================================================ loader: this CTA's half of every image
+        if (lane == 0) {
+            const uint32_t total = (uint32_t)my_tiles * NBLK_TOTAL;            // K blocks
+            const unsigned char* src = p.wimg + (size_t)rank * tc6::HIMG;
+            for (uint32_t n = 0; n < total; ++n) {
+                const uint32_t s = n & SMASK, ph = (n >> 2) & 1u;
+                const long long _tl0 = clock64();
+                if ((n % tc6::CPK) == 0 && !mbar_wait(&sm.bar_empty[(n / tc6::CPK) % (tc6::NSTAGE / tc6::CPK)], ph ^ 1u, p.err, 61)) break;
+                if (blockIdx.x < 2) atomicAdd(reinterpret_cast<unsigned long long*>(p.err) + 1 + (blockIdx.x ? 15 : 0), (unsigned long long)(clock64() - _tl0));
+                if (p.dbg_no_weights) { mbar_arrive(&sm.bar_full[s]); continue; }
+                mbar_arrive_expect_tx(&sm.bar_full[s], 2 * tc6::HIMG);
+                const unsigned char* g = src + (size_t)(n % NBLK_TOTAL) * (2 * IMG);
+                bulk_g2s(sm.b[s][0], g, tc6::HIMG, &sm.bar_full[s]);               // W_hi rows 128*rank..
+                bulk_g2s(sm.b[s][1], g + IMG, tc6::HIMG, &sm.bar_full[s]);         // W_lo rows 128*rank..
+            }
+        }
+    } else if (warp == W_FWD) {
+        // ============================================================ forwarder (peer CTA): "my half landed" -> leader
+        if (rank == 1 && lane == 0) {
+            const uint32_t total = (uint32_t)my_tiles * NBLK_TOTAL;
+            const uint32_t full0 = map_to_cta(&sm.bar_full[0], 0);
+            for (uint32_t n = 0; n < total; ++n) {
+                const uint32_t s = n & SMASK, ph = (n >> 2) & 1u;
+                if (!mbar_wait(&sm.bar_full[s], ph, p.err, 62)) break;
+                mbar_arrive_cluster(full0 + 8u * s);
+            }
+        }
+    } else if (warp == W_ISSUE) {
+        // ============================================================ MMA issuer: the whole warp of the rank-0 CTA
+        if (rank == 0) {
+            const uint32_t idesc = make_idesc_bf16(256, 256);
+            const uint32_t hiw = desc_hi<LAYOUT>(), xe_hiw = (256u >> 4) | (1u << 14);
+            const uint32_t b0_lo = desc_lo<LAYOUT>(smem_u32(sm.b[0]));
+            const uint32_t ahi_lo = desc_lo<LAYOUT>(smem_u32(sm.a_hi)), alo_lo = desc_lo<LAYOUT>(smem_u32(sm.a_lo));
+            const uint32_t xeh_lo0 = desc_lo<LAYOUT_NONE>(smem_u32(sm.xe_hi[0])), xel_lo0 = desc_lo<LAYOUT_NONE>(smem_u32(sm.xe_lo[0]));
+            constexpr uint32_t KADV = kstep_adv16<LAYOUT>();
+            uint32_t n = 0;            // weight image counter
+            uint32_t c_acc = 0;        // completions of bar_acc_full consumed
+            uint32_t c_pack = 0;       // packing rounds consumed on bar_kblk[*]
+            bool ok = true;
+            long long _t_commit = 0, _t_mma = 0;
+            for (int t = 0; t < my_tiles && ok; ++t) {
+                const uint32_t xeh_lo = xeh_lo0 + (uint32_t)(t & 1) * (tc3::XE >> 4), xel_lo = xel_lo0 + (uint32_t)(t & 1) * (tc3::XE >> 4);
+                for (int l = 0; l < 4 && ok; ++l) {
+                    const uint32_t acc = (l & 1) ? tP : tQ;
+                    const uint32_t ab = (l & 1) ? tQ : tP;
+                    if (t > 0 || l > 0) { if (!PNB_TIMED_WAIT_L0(2, mbar_wait(&sm.bar_acc_full, c_acc & 1u, p.err, 63))) { ok = false; break; } ++c_acc; }
+                    if (l == 0) { if (!PNB_TIMED_WAIT_L0(1, mbar_wait(&sm.bar_a1_ready, (uint32_t)t & 1u, p.err, 64))) { ok = false; break; } }
+                    if (l == 1 && t > 0) { if (!PNB_TIMED_WAIT_L0(2, mbar_wait(&sm.bar_drain, (uint32_t)(t - 1) & 1u, p.err, 65))) { ok = false; break; } }
+                    tc_fence_after();
+                    const int nkb = nkb_of(l);
+                    for (int kb = 0; kb < nkb && ok; ++kb) {
+                        const uint32_t s0 = n & SMASK, ph0 = (n >> 2) & 1u;                  // ring stage of this K block
+                        const bool need_chunks = (l >= 1 && kb < 8);
+                        uint64_t* cb0 = need_chunks ? &sm.bar_kblk[kb] : &sm.bar_full[s0];
+                        const uint32_t cp0 = need_chunks ? (c_pack & 1u) : ph0;
+                        if (p.dbg_flags & 2) {      // diagnosis: classify the wait with non-blocking probes
+                            if (need_chunks && !mbar_test_wait(cb0, cp0)) {
+                                if (!PNB_TIMED_WAIT_L0(12, mbar_spin_wait(cb0, cp0, p.err, 66))) { ok = false; break; }
+                            }
+                            if (!mbar_test_wait(&sm.bar_full[s0], ph0)) {
+                                const long long _tw = clock64();
+                                if (!mbar_spin_wait(&sm.bar_full[s0], ph0, p.err, 67)) { ok = false; break; }
+                                if (lane == 0) { prof_add(p.err, 13, clock64() - _tw); prof_add(p.err, 14, 1); }
+                            }
+                        } else
+                        if (!mbar_try_wait4(&sm.bar_full[s0], ph0, cb0, cp0, &sm.bar_full[s0], ph0, cb0, cp0)) {
+                            if (need_chunks) {
+                                if (!PNB_TIMED_WAIT_L0(2, mbar_wait(cb0, cp0, p.err, 66))) { ok = false; break; }
+                            }
+                            if (!PNB_TIMED_WAIT_L0(3, mbar_wait(&sm.bar_full[s0], ph0, p.err, 67))) { ok = false; break; }
+                        }
+                        tc_fence_after();
+                        const long long _tm0 = clock64();
+                        const uint32_t akb_hi = ahi_lo + (uint32_t)kb * (ABLK >> 4), akb_lo = alo_lo + (uint32_t)kb * (ABLK >> 4);
+                        const uint32_t tcol = ab + (uint32_t)(kb * 32);
+                        const uint32_t bl = b0_lo + s0 * (2 * tc6::HIMG >> 4), bl2 = bl + (tc6::HIMG >> 4);
+                        if (l == 0) {
+                            mma2_ss2_w(acc, akb_hi, hiw, bl, hiw, idesc, kb ? 1u : 0u);
+                            mma2_ss2_w(acc, akb_lo, hiw, bl, hiw, idesc, 1u);
+                            mma2_ss2_w(acc, akb_hi + KADV, hiw, bl + KADV, hiw, idesc, 1u);
+                            mma2_ss2_w(acc, akb_lo + KADV, hiw, bl + KADV, hiw, idesc, 1u);
+                            mma2_ss2_w(acc, akb_hi, hiw, bl2, hiw, idesc, 1u);
+                            mma2_ss2_w(acc, akb_hi + KADV, hiw, bl2 + KADV, hiw, idesc, 1u);
+                        } else if (kb == 8) {
+                            mma2_ss2_w(acc, xeh_lo, xe_hiw, bl, hiw, idesc, 1u);
+                            mma2_ss2_w(acc, xel_lo, xe_hiw, bl, hiw, idesc, 1u);
+                            mma2_ss2_w(acc, xeh_lo, xe_hiw, bl2, hiw, idesc, 1u);
+                        } else {
+                            mma2_ts2_w(acc, tcol, bl, hiw, idesc, kb ? 1u : 0u);
+                            mma2_ts2_w(acc, tcol + 8u, bl, hiw, idesc, 1u);
+                            mma2_ts2_w(acc, tcol + 16u, bl + KADV, hiw, idesc, 1u);
+                            mma2_ts2_w(acc, tcol + 24u, bl + KADV, hiw, idesc, 1u);
+                            mma2_ts2_w(acc, tcol, bl2, hiw, idesc, 1u);
+                            mma2_ts2_w(acc, tcol + 16u, bl2 + KADV, hiw, idesc, 1u);
+                        }
+                        if ((n % tc6::CPK) == tc6::CPK - 1) PROF6_COMMIT(mma2_commit_w(&sm.bar_empty[(n / tc6::CPK) % (tc6::NSTAGE / tc6::CPK)], 3));   // frees CPK ring stages in both CTAs
+                        n += 1;
+                        _t_mma += clock64() - _tm0;
+                    }
+                    if (!ok) break;
+                    if (l >= 1) ++c_pack;
+                    mma2_commit_w(&sm.bar_acc_full, 3);
+                    if (l == 0) mma2_commit_w(&sm.bar_a1_free, 3);
+                }
+            }
+            if (lane == 0) { prof_add(p.err, 10, _t_commit); prof_add(p.err, 11, _t_mma); }
+        }
+    } else if (warp >= W_BUILD) {
+        // ============================================================ builders: one thread per pair row of this CTA's tile
+        const int bt = (warp - W_BUILD) * 32 + lane, row = bt & 127, part = bt >> 7;     // two threads per row (columns 0..151 | 152..287)
+        const uint32_t ready0 = map_to_cta(&sm.bar_a1_ready, 0);
+        bool ok = true;
+        for (int t = 0; t < my_tiles && ok; ++t) {
+            const int tile = 2 * (pair + t * npairs) + (int)rank;
+            if (t > 0 && !(lane == 0 && warp == W_BUILD ? PNB_TIMED_WAIT(4, mbar_wait(&sm.bar_a1_free, (uint32_t)(t - 1) & 1u, p.err, 68)) : mbar_wait(&sm.bar_a1_free, (uint32_t)(t - 1) & 1u, p.err, 68))) { ok = false; break; }
+            const long long _tb0 = clock64();
+            if (part == 0) build_pair_part<0>(sm, p, tile, t, row, n_valid);
+            else build_pair_part<1>(sm, p, tile, t, row, n_valid);
+            fence_proxy_async();
+            if (rank == 0) mbar_arrive(&sm.bar_a1_ready); else mbar_arrive_cluster(ready0);
+            if (lane == 0 && warp == W_BUILD) prof_add(p.err, 5, clock64() - _tb0);
+        }
+    } else {
+        // ============================================================ epilogue warps
+        const int quad = warp & 3, grp = warp >> 2;
+        const int erow = quad * 32 + lane;
+        const uint32_t tlane = (uint32_t)(quad * 32) << 16;
+        const uint32_t kblk0 = map_to_cta(&sm.bar_kblk[0], 0), drain0 = map_to_cta(&sm.bar_drain, 0);
+        uint32_t n_acc = 0;
+        bool ok = true;
+        for (int t = 0; t < my_tiles && ok; ++t) {
+            const int tile = 2 * (pair + t * npairs) + (int)rank;
+            for (int l = 0; l < 4 && ok; ++l, ++n_acc) {
+                if (!(tid == 0 ? PNB_TIMED_WAIT(6, mbar_wait(&sm.bar_acc_full, n_acc & 1u, p.err, 69)) : mbar_wait(&sm.bar_acc_full, n_acc & 1u, p.err, 69))) { ok = false; break; }
+                const long long _te0 = clock64();
+                tc_fence_after();
+                const uint32_t accb = ((l & 1) ? tP : tQ) + tlane;
+                if (l < 3) {
+                    const float* bias = p.bias[l];
+#pragma unroll
+                    for (int i = 0; i < tc6::NCH; ++i) {
+                        const int g = grp + tc6::NGRP * i, c0 = 16 * g;
+                        uint32_t v[16];
+                        tmem_ld16(accb + (uint32_t)c0, v);
+                        tmem_ld_wait();
+                        uint32_t hh[8], ll[8];
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) {
+                            float2 bb = __ldg(reinterpret_cast<const float2*>(bias + c0) + e);
+                            float y0 = __uint_as_float(v[2 * e]) + bb.x, y1 = __uint_as_float(v[2 * e + 1]) + bb.y;
+                            y0 = fmaxf(y0, LEAKY * y0); y1 = fmaxf(y1, LEAKY * y1);
+                            split_bf16x2(y0, y1, hh[e], ll[e]);
+                        }
+                        tmem_st8(accb + (uint32_t)c0, hh);
+                        tmem_st8(accb + (uint32_t)c0 + 8u, ll);
+                        tmem_st_wait();
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) { if (rank == 0) mbar_arrive(&sm.bar_kblk[g >> 1]); else mbar_arrive_cluster(kblk0 + 8u * (uint32_t)(g >> 1)); }
+                    }
+                    if (tid == 0) prof_add(p.err, 7, clock64() - _te0);
+                } else {
+                    const float wrow = sm.wc[t & 1][erow];
+                    const int sidx = tile * TSAMP + (erow >> 3);
+                    const bool swrite = sidx < n_valid;
+                    const float* bias = p.bias[3];
+                    const int j8 = lane & 7;
+                    float apart = 0.f;
+#pragma unroll
+                    for (int i = 0; i < tc6::NCH; ++i) {
+                        const int c0 = 16 * (grp + tc6::NGRP * i);
+                        uint32_t v[16];
+                        tmem_ld16(accb + (uint32_t)c0, v);
+                        tmem_ld_wait();
+                        float z[16];
+#pragma unroll
+                        for (int e = 0; e < 16; ++e) {
+                            float y = __uint_as_float(v[e]) + __ldg(bias + c0 + e);
+                            y = fmaxf(y, LEAKY * y);
+                            apart = fmaf(y, __ldg(p.wa + c0 + e), apart);
+                            z[e] = y * wrow;
+                        }
+                        float r8[8], r4[4], r2[2];
+                        const bool b4 = lane & 4, b2 = lane & 2, b1 = lane & 1;
+#pragma unroll
+                        for (int ii = 0; ii < 8; ++ii) {
+                            float send = b4 ? z[ii] : z[ii + 8], keep = b4 ? z[ii + 8] : z[ii];
+                            r8[ii] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+                        }
+#pragma unroll
+                        for (int ii = 0; ii < 4; ++ii) {
+                            float send = b2 ? r8[ii] : r8[ii + 4], keep = b2 ? r8[ii + 4] : r8[ii];
+                            r4[ii] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+                        }
+#pragma unroll
+                        for (int ii = 0; ii < 2; ++ii) {
+                            float send = b1 ? r4[ii] : r4[ii + 2], keep = b1 ? r4[ii + 2] : r4[ii];
+                            r2[ii] = keep + __shfl_xor_sync(0xffffffffu, send, 1);
+                        }
+                        if (swrite) *reinterpret_cast<float2*>(p.hbar + (size_t)sidx * 256 + c0 + 2 * j8) = make_float2(r2[0], r2[1]);
+                    }
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) { if (rank == 0) mbar_arrive(&sm.bar_drain); else mbar_arrive_cluster(drain0); }   // this warp's share of region P drained
+                    if (tid == 0) prof_add(p.err, 8, clock64() - _te0);
+                    if (grp < 2) sm.alpha_part[grp][erow] = apart;
+                    named_bar_sync(1, tc6::NEPI);
+                    if (grp >= 2) atomicAdd(&sm.alpha_part[grp - 2][erow], apart);
+                    if (tc6::NGRP > 2) named_bar_sync(1, tc6::NEPI);
+                    if (grp == 0) {
+                        float a = sm.alpha_part[0][erow] + (tc6::NGRP > 1 ? sm.alpha_part[1][erow] : 0.f) + __ldg(p.ba) - 1.0f;
+                        float sp = a > 20.f ? a : log1pf(expf(a));
+                        float zz = sp * wrow;
+                        zz += __shfl_xor_sync(0xffffffffu, zz, 1);
+                        zz += __shfl_xor_sync(0xffffffffu, zz, 2);
+                        zz += __shfl_xor_sync(0xffffffffu, zz, 4);
+                        if (j8 == 0 && swrite) p.sigma[sidx] = zz;
+                    }
+                    named_bar_sync(1, tc6::NEPI);
+                }
+            }
+        }
+    }
+    if (tid == 0) prof_add(p.err, 9, clock64() - _tk0);
+    __syncwarp();
+    tc_fence_before();
+    cluster_sync_all();
+    if (warp == W_ISSUE) tmem_dealloc2<512>(sm.tmem_base);
+}
+
+// =====================================================================================================================
 // Colour branch on the tensor cores: per 128 valid samples  [hbar(256) | PE4(view)(24)] -> 128 -> 128 -> 128 (tcgen05,
 // BF16x3) -> 3 (CUDA cores) -> sigmoid*1.002-0.001   (reference: point_aggregators.py:631-637, 269-273).
 // Layer 1 reads its operand from shared memory (SS), layers 2-3 from tensor memory (TS).  TMEM: accumulator cols
@@ -1514,8 +1823,9 @@ extern "C" int pnb_shade_forward_tc(const pnb_query_t* q, const pnb_points_t* pt
     // interleaved (non-swizzled) operand layout: 128-byte alignment of the carve-out is sufficient
     constexpr size_t kSmemMax = 232448;   // 227 KB opt-in limit per block on sm_100
     const size_t smem_tc = sizeof(tc::Smem) + 128, smem_tc3 = sizeof(tc3::Smem) + 128, smem_cb = sizeof(cb::Smem),
-                 smem_ctc = sizeof(ctc::Smem) + 128, smem_tc5 = sizeof(tc5::Smem) + 128;
+                 smem_ctc = sizeof(ctc::Smem) + 128, smem_tc5 = sizeof(tc5::Smem) + 128, smem_tc6 = sizeof(tc6::Smem) + 128;
     static_assert(sizeof(tc5::Smem) + 128 <= kSmemMax, "v5 shared-memory carve-out exceeds the per-block limit");
+    static_assert(sizeof(tc6::Smem) + 128 <= kSmemMax, "v6 shared-memory carve-out exceeds the per-block limit");
     static_assert((tc3::NSTAGE & (tc3::NSTAGE - 1)) == 0 && tc3::NSTAGE == 4, "issuer assumes a 4-stage ring");
     static_assert(sizeof(tc::Smem) + 128 <= kSmemMax && sizeof(tc3::Smem) + 128 <= kSmemMax && sizeof(ctc::Smem) + 128 <= kSmemMax &&
                   sizeof(cb::Smem) <= kSmemMax, "shared-memory carve-out exceeds the sm_100 per-block limit");
@@ -1523,6 +1833,7 @@ extern "C" int pnb_shade_forward_tc(const pnb_query_t* q, const pnb_points_t* pt
         PNB_CHECK_CUDA(cudaFuncSetAttribute(k_shade_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tc));
         PNB_CHECK_CUDA(cudaFuncSetAttribute(k_shade_tc3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tc3));
         PNB_CHECK_CUDA(cudaFuncSetAttribute(k_shade_tc5, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tc5));
+        PNB_CHECK_CUDA(cudaFuncSetAttribute(k_shade_tc6, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tc6));
         PNB_CHECK_CUDA(cudaFuncSetAttribute(k_color_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_ctc));
         PNB_CHECK_CUDA(cudaFuncSetAttribute(k_color_branch, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cb));
         int dev = 0;
@@ -1540,8 +1851,10 @@ extern "C" int pnb_shade_forward_tc(const pnb_query_t* q, const pnb_points_t* pt
     p.ba = mlp->b[4];
     p.hbar = hbar; p.sigma = sigma; p.hbar_cap = max_valid_samples; p.err = d_err;
     p.dbg_no_weights = (stage_mask & 64) ? 1 : 0;
+    p.dbg_flags = (stage_mask >> 8) & 0xff;
     if (stage_mask & 1) {
-        if (stage_mask & 32) k_shade_tc5<<<n_sm, tc5::NTHR, smem_tc5, stream>>>(p);           // TMEM ping-pong, chunk-pipelined
+        if (stage_mask & 128) k_shade_tc6<<<n_sm & ~1, tc6::NTHR, smem_tc6, stream>>>(p);     // v5 on CTA pairs (cta_group::2)
+        else if (stage_mask & 32) k_shade_tc5<<<n_sm, tc5::NTHR, smem_tc5, stream>>>(p);           // TMEM ping-pong, chunk-pipelined
         else if (stage_mask & 4) k_shade_tc3<<<n_sm, tc3::NTHR, smem_tc3, stream>>>(p);   // TS-form pipeline (A in tensor memory)
         else k_shade_tc<<<n_sm, tc::NTHR, smem_tc, stream>>>(p);
     }

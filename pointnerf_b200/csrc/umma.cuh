@@ -95,6 +95,31 @@ __device__ __forceinline__ bool mbar_try_wait4(uint64_t* b0, uint32_t p0, uint64
         : "memory");
     return ok != 0;
 }
+__device__ __forceinline__ uint64_t globaltimer_ns_fwd() {
+    uint64_t t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+// Non-blocking probe (test_wait never suspends the thread; try_wait may, up to a hardware time limit).
+__device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ bool mbar_spin_wait(uint64_t* bar, uint32_t parity, int* err_flag, int code) {   // test_wait spin, 2 s bound
+    if (mbar_test_wait(bar, parity)) return true;
+    const uint64_t t0 = globaltimer_ns_fwd();
+    for (;;) {
+        if (mbar_test_wait(bar, parity)) return true;
+        if (globaltimer_ns_fwd() - t0 > 2000000000ull) break;
+    }
+    if (err_flag) atomicExch(err_flag, code);
+    return false;
+}
 __device__ __forceinline__ uint64_t globaltimer_ns() {
     uint64_t t;
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
@@ -213,6 +238,12 @@ __device__ __forceinline__ void mma_commit_w(uint64_t* bar) {
 __device__ __forceinline__ void mma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+__device__ __forceinline__ void mma2_commit_local_w(uint64_t* bar) {   // cta_group::2 commit, arrive on the issuing CTA's barrier only
+    asm volatile(
+        "{\n\t.reg .pred pe;\n\telect.sync _|pe, 0xffffffff;\n\t"
+        "@pe tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(smem_u32(bar))
+        : "memory");
+}
 // ---- CTA pair (cluster of 2, tcgen05 cta_group::2) ----------------------------------------------------------------
 // One tcgen05.mma.cta_group::2 (issued by the rank-0 CTA) computes D[256 x N]: CTA r owns accumulator rows
 // 128r..128r+127 in ITS tensor memory, supplies its own 128 A rows and the B rows N/2*r .. N/2*(r+1)-1 from ITS shared
@@ -232,7 +263,9 @@ __device__ __forceinline__ uint32_t map_to_cta(const void* local_smem, uint32_t 
     return r;
 }
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+    // default semantics (.release.cta), as CUTLASS' ClusterBarrier::arrive(cta_id): an explicit .release.cluster compiles to
+    // MEMBAR.ALL.GPU + ERRBAR + CGAERRBAR in front of every arrive (measured: it doubles the epilogue time)
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 template <int NCOLS>
 __device__ __forceinline__ void tmem_alloc2(uint32_t* smem_result) {  // the same warp of BOTH CTAs

@@ -215,7 +215,7 @@ __global__ void __launch_bounds__(128, 1) k_umma_selftest_ts(const float* __rest
 template <int LAYOUT>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1)
     k_umma_selftest2(const float* __restrict__ A, const float* __restrict__ W, float* __restrict__ D, int K, int N, int mode,
-                     int bench_iters, long long* __restrict__ out, int* err) {
+                     int bench_iters, int bench_flags, long long* __restrict__ out, int* err) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     const int nkb = (K + BK - 1) / BK;
@@ -223,13 +223,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1)
     unsigned char* b_lo = b_hi + 128 * 64;
     unsigned char* a_hi = b_lo + 128 * 64;       // nkb blocks of [128 x 32] (mode 0)
     unsigned char* a_lo = a_hi + nkb * 8192;
-    __shared__ uint64_t bar;
+    __shared__ uint64_t bar, dummy_bar, spin_bar, bbar[2];
     __shared__ uint32_t tmem_base;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t rank = cluster_ctarank();
     const int NH = N >> 1;
 
-    if (tid == 0) { mbar_init(&bar, 1); mbar_fence_init(); }
+    if (tid == 0) { mbar_init(&bar, 1); mbar_init(&dummy_bar, 1); mbar_init(&spin_bar, 1); mbar_init(&bbar[0], 1); mbar_init(&bbar[1], 1); mbar_fence_init(); }
     if (warp == 0) tmem_alloc2<512>(&tmem_base);
     tc_fence_before();
     cluster_sync_all();
@@ -321,12 +321,51 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1)
         if (rank == 0 && warp == 0) {
             const uint32_t bh = desc_lo<LAYOUT>(smem_u32(b_hi)), ah = desc_lo<LAYOUT>(smem_u32(a_hi));
             t0 = clock64();
+            const int cevery = bench_flags & 255, ckind = (bench_flags >> 8) & 3;
+            const uint32_t rot = (bench_flags >> 16) & 1;      // rotate the operands: no two consecutive MMAs share A or B
+            const uint32_t bdelta = desc_lo<LAYOUT>(smem_u32(b_lo)) - bh, adelta = desc_lo<LAYOUT>(smem_u32(a_lo)) - ah;
             for (int i = 0; i < bench_iters; ++i) {
-                if (mode == 0) mma2_ss2_w(tacc, ah, hiw, bh, hiw, idesc, 1u);
-                else mma2_ts2_w(tacc, tacc + 256u, bh, hiw, idesc, 1u);
+                const uint32_t sel = rot ? (uint32_t)(i & 1) : 0u, ksel = rot ? (uint32_t)((i >> 1) & 1) * KADV : 0u;
+                if (mode == 0) mma2_ss2_w(tacc, ah + sel * adelta + ksel, hiw, bh + sel * bdelta + ksel, hiw, idesc, 1u);
+                else mma2_ts2_w(tacc, tacc + 256u + sel * 128u + (ksel ? 8u : 0u), bh + sel * bdelta + ksel, hiw, idesc, 1u);
+                if (cevery && (i & (cevery - 1)) == cevery - 1) {        // interleaved commits to a barrier nobody waits on (cevery: power of 2)
+                    if (ckind == 0) mma2_commit_w(&dummy_bar, 3);
+                    else if (ckind == 1) mma2_commit_w(&dummy_bar, 1);
+                    else if (ckind == 2) mma2_commit_local_w(&dummy_bar);
+                    else mma_commit_w(&dummy_bar);
+                }
             }
             mma2_commit_w(&bar, 3);
             t1 = clock64();
+        }
+        // optional stressors on warps 1-3 of BOTH CTAs while the MMAs run (what else the fused kernel does on the SM)
+        if (warp == 1 && (bench_flags & (1 << 13)) && lane == 0) {          // weight-like bulk copies into shared memory
+            unsigned char* sink[2] = {a_lo, b_lo};
+            uint32_t cnt = 0;
+            while (!mbar_test_wait(&bar, phase)) {
+                const uint32_t sidx = cnt & 1u;
+                if (cnt >= 2 && !mbar_wait(&bbar[sidx], ((cnt >> 1) - 1) & 1u, err, 451)) break;
+                mbar_arrive_expect_tx(&bbar[sidx], 8192);
+                bulk_g2s(sink[sidx], reinterpret_cast<const unsigned char*>(W) + (size_t)(cnt & 3u) * 8192, 8192, &bbar[sidx]);
+                ++cnt;
+            }
+            for (uint32_t c = (cnt >= 2 ? cnt - 2 : 0); c < cnt; ++c) mbar_wait(&bbar[c & 1u], (c >> 1) & 1u, err, 452);
+        } else if ((warp == 2 || (warp == 3 && !(bench_flags & (3 << 14)))) && (bench_flags & (1 << 12))) {   // epilogue-like TMEM traffic
+            uint32_t v[16];
+            while (!mbar_test_wait(&bar, phase)) {
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    tmem_ld16(tacc + tlane + 384u + (uint32_t)(c * 16), v);
+                    tmem_ld_wait();
+                    tmem_st8(tacc + tlane + 384u + (uint32_t)(c * 16), v);
+                    tmem_st8(tacc + tlane + 384u + (uint32_t)(c * 16) + 8u, v + 8);
+                    tmem_st_wait();
+                }
+            }
+        } else if (warp == 3 && (bench_flags & (1 << 14))) {               // a warp polling an mbarrier with test_wait
+            while (!mbar_test_wait(&bar, phase)) { if (mbar_test_wait(&dummy_bar, 1u)) __nanosleep(0); }
+        } else if (warp == 3 && (bench_flags & (1 << 15))) {               // ... with try_wait
+            while (!mbar_test_wait(&bar, phase)) { if (mbar_try_wait(&spin_bar, 0u)) break; }
         }
         mbar_wait(&bar, phase, err, 450);
         if (rank == 0 && tid == 0) { out[0] = t1 - t0; out[1] = clock64() - t0; }
@@ -347,11 +386,11 @@ __global__ void __launch_bounds__(128, 1) k_umma_bench(int mode, int iters, int 
     unsigned char* a = smem;                 // [128 x 32]
     unsigned char* b = smem + 8192;          // [256 x 32]
     unsigned char* sink = smem + 8192 + 16384;   // 2 x 16 KB landing zone for bulk copies
-    __shared__ uint64_t bar, bbar[2];
+    __shared__ uint64_t bar, bbar[2], cbar;
     __shared__ uint32_t tmem_base;
     const int tid = threadIdx.x, warp = tid >> 5;
     for (int i = tid; i < (8192 + 16384) / 4; i += 128) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;
-    if (tid == 0) { mbar_init(&bar, 1); mbar_init(&bbar[0], 1); mbar_init(&bbar[1], 1); mbar_fence_init(); }
+    if (tid == 0) { mbar_init(&bar, 1); mbar_init(&bbar[0], 1); mbar_init(&bbar[1], 1); mbar_init(&cbar, 1); mbar_fence_init(); }
     if (warp == 0) tmem_alloc<512>(&tmem_base);
     fence_proxy_async();
     tc_fence_before();
@@ -392,9 +431,14 @@ __global__ void __launch_bounds__(128, 1) k_umma_bench(int mode, int iters, int 
         const uint32_t idesc = make_idesc_bf16(128, 256);
         const uint64_t da = make_smem_desc<LAYOUT>(smem_u32(a)), db = make_smem_desc<LAYOUT>(smem_u32(b));
         long long t0 = clock64();
+        const int cevery = (bulk >> 8) & 255;       // interleave a commit (to a barrier nobody waits on) every n MMAs (power of 2)
+        const uint32_t rot = (bulk >> 16) & 1;      // rotate operands between two buffers / k-steps
+        const uint64_t db2 = make_smem_desc<LAYOUT>(smem_u32(sink)), da2 = make_smem_desc<LAYOUT>(smem_u32(sink + 16384));
         for (int i = 0; i < iters; ++i) {
-            if (mode == 0) mma_ss(tacc, da, db, idesc, 1u);
-            else mma_ts(tacc, tacc + 256u, db, idesc, 1u);
+            const bool alt = rot && (i & 1);
+            if (mode == 0) mma_ss(tacc, alt ? da2 : da, alt ? db2 : db, idesc, 1u);
+            else mma_ts(tacc, tacc + 256u + (alt ? 128u : 0u), alt ? db2 : db, idesc, 1u);
+            if (cevery && (i & (cevery - 1)) == cevery - 1) mma_commit(&cbar);
         }
         mma_commit(&bar);
         long long t1 = clock64();
@@ -460,9 +504,11 @@ extern "C" int pnb_umma_bench(int layout, int mode, int iters, int bulk, const v
 
 // CTA-pair self-test / micro-benchmark (cluster of 2, cta_group::2): d_A [256 x K], d_W [N x K], d_D [256 x N];
 // mode 0 = A in shared memory (K <= 288), 1 = A in tensor memory (K <= 256, K % 16 == 0); N % 32 == 0.
-// bench_iters > 0: d_out int64[2] = issue cycles / cycles until complete of that many back-to-back MMAs.
+// bench_iters > 0: d_out int64[2] = issue cycles / cycles until complete of that many back-to-back MMAs;
+// bench_flags: bits 0-7 = interleave a tcgen05.commit every that many MMAs, bits 8-9 = its form (0 multicast to both
+// CTAs, 1 multicast mask 1, 2 cta_group::2 without multicast, 3 cta_group::1).
 extern "C" int pnb_umma_selftest2(const float* d_A, const float* d_W, float* d_D, int K, int N, int mode, int bench_iters,
-                                  long long* d_out, int* d_err, pnb_stream_t stream_) {
+                                  int bench_flags, long long* d_out, int* d_err, pnb_stream_t stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     PNB_REQUIRE(d_A && d_W && d_D && d_err, PNB_ERR_INVALID, "pnb_umma_selftest2: null argument");
     PNB_REQUIRE(K >= 16 && K <= (mode ? 256 : 288) && (mode == 0 || K % 16 == 0) && N >= 32 && N <= 256 && N % 32 == 0, PNB_ERR_INVALID,
@@ -471,7 +517,7 @@ extern "C" int pnb_umma_selftest2(const float* d_A, const float* d_W, float* d_D
     const int nkb = (K + 31) / 32;
     size_t smem = (size_t)nkb * 8192 * 2 + 128 * 64 * 2 + 1024;
     PNB_CHECK_CUDA(cudaFuncSetAttribute(k_umma_selftest2<umma::LAYOUT_NONE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_umma_selftest2<umma::LAYOUT_NONE><<<2, 128, smem, stream>>>(d_A, d_W, d_D, K, N, mode, bench_iters, d_out, d_err);
+    k_umma_selftest2<umma::LAYOUT_NONE><<<2, 128, smem, stream>>>(d_A, d_W, d_D, K, N, mode, bench_iters, bench_flags, d_out, d_err);
     PNB_CHECK_CUDA(cudaGetLastError());
     return PNB_OK;
 }

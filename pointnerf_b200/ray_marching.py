@@ -290,9 +290,9 @@ def _init_state(mod):
     # default), 3 = A operand of layers 2-4 in tensor memory + overlapped operand builders, epilogues exposed,
     # 2 = serialized shared-memory pipeline
     _v = int(getattr(opt, "pnb_tc_version", 5))
-    if _v not in (2, 3, 5):
-        raise NotImplementedError("pnb200: pnb_tc_version=%r (2 | 3 | 5)" % _v)
-    mod.tc_mask = 3 | (12 if _v == 3 else 0) | (8 + 32 if _v == 5 else 0)
+    if _v not in (2, 3, 5, 6):
+        raise NotImplementedError("pnb200: pnb_tc_version=%r (2 | 3 | 5 | 6)" % _v)
+    mod.tc_mask = 3 | (12 if _v == 3 else 0) | (8 + 32 if _v == 5 else 0) | (8 + 128 if _v == 6 else 0)
     mod.last = None
     mod._pnb_ready = True
 

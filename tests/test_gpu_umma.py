@@ -59,7 +59,7 @@ def test_umma_cta_pair(mode, K, N):
     D = torch.full((256, N), float("nan"), device=DEV)
     err = torch.zeros(1, dtype=torch.int32, device=DEV)
     out = torch.zeros(2, dtype=torch.int64, device=DEV)
-    _lib.check(l.pnb_umma_selftest2(A.data_ptr(), W.data_ptr(), D.data_ptr(), K, N, mode, 0, out.data_ptr(), err.data_ptr(),
+    _lib.check(l.pnb_umma_selftest2(A.data_ptr(), W.data_ptr(), D.data_ptr(), K, N, mode, 0, 0, out.data_ptr(), err.data_ptr(),
                                     torch.cuda.current_stream().cuda_stream), "pnb_umma_selftest2")
     torch.cuda.synchronize()
     assert int(err.item()) == 0, "pipeline timeout code %d" % int(err.item())

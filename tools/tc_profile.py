@@ -13,14 +13,15 @@ for i in range(3):
         net.render_full(list(cfg.campos), rd, torch.eye(3), cfg.near, cfg.far, [1., 1., 1.])
 if os.environ.get("PNB_NO_WEIGHTS"):
     net.tc_mask |= 64
+net.tc_mask |= int(os.environ.get("PNB_DBG_FLAGS", "0")) << 8
 torch.cuda.synchronize()
 net._err.zero_()
 with torch.no_grad():
     net.render_full(list(cfg.campos), rd, torch.eye(3), cfg.near, cfg.far, [1., 1., 1.])
 torch.cuda.synchronize()
-c = net._err.cpu().view(torch.int64)[1:11].tolist()
+c = net._err.cpu().view(torch.int64)[1:17].tolist()
 names = ["loader wait empty", "issuer wait a1_ready", "issuer wait at_ready", "issuer wait full(weights)", "builder wait a1_free",
-         "builder busy", "epilogue wait acc_full", "epilogue busy (l<3)", "epilogue busy (l==3)", "kernel total (thread 0)"]
+         "builder busy", "epilogue wait acc_full", "epilogue busy (l<3)", "epilogue busy (l==3)", "kernel total (thread 0)", "issuer: in ring commits (v6)", "issuer: K-block issue incl. commits (v6)", "issuer: wait kblk (probe)", "issuer: wait weights (probe)", "issuer: #weight waits", "peer loader wait empty"]
 ntiles = (net.last.counters["n_valid"] if net.last.counters else 3472901) if False else None
 tot = c[9]
 print("status", int(net._err[0]), "version", os.environ.get("PNB_TC_VERSION", "5"), "no_weights", bool(os.environ.get("PNB_NO_WEIGHTS")))

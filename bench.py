@@ -196,7 +196,7 @@ def main():
     ap.add_argument("--sr", type=int, default=24)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--precision", type=str, default="bf16x3", help="bf16x3 (tcgen05, default) | fp32 (CUDA cores)")
-    ap.add_argument("--tc-version", type=int, default=5, help="tcgen05 pipeline variant: 5 (TMEM ping-pong, default) | 6 (v5 on CTA pairs, cta_group::2) | 3 | 2")
+    ap.add_argument("--tc-version", type=int, default=6, help="tcgen05 pipeline variant: 6 (TMEM ping-pong on CTA pairs, cta_group::2; default) | 5 (single CTA) | 3 | 2")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)

@@ -1239,7 +1239,8 @@ namespace tc6 {
 constexpr int NEPI_WARPS = 8, NGRP = NEPI_WARPS / 4, NCH = 16 / NGRP;
 constexpr int NEPI = NEPI_WARPS * 32, NBUILD = 256, NTHR = NEPI + NBUILD + 96;   // two builder threads per row; + loader, issuer, forwarder warps
 constexpr int NSTAGE = 4;                // ring stage = one K block: this CTA's half of the W_hi image and of the W_lo image
-constexpr int CPK = 2;                   // K blocks per ring commit: stages are freed in groups of CPK (a tcgen05.commit costs ~140 tensor-pipe cycles)
+constexpr int CPK = 1;                   // K blocks per ring commit (a tcgen05.commit costs ~140 tensor-pipe cycles; CPK = 2 frees stages in pairs
+                                         // and was measured slower: the 4-stage ring then starves)
 constexpr int HIMG = tc::IMG / 2;       // bytes of one half image ([128 x 32] bf16)
 struct Smem {
     unsigned char a_hi[tc::NKB_MAX * tc::ABLK];
@@ -1254,7 +1255,6 @@ struct Smem {
 };
 }  // namespace tc6
 
-#define PROF6_COMMIT(x) { const long long _tc0 = clock64(); x; _t_commit += clock64() - _tc0; }
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(tc6::NTHR, 1) k_shade_tc6(ShadeTcParams p) {
     using namespace tc;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -1328,7 +1328,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(tc6::NTHR, 1) k_shad
             uint32_t c_acc = 0;        // completions of bar_acc_full consumed
             uint32_t c_pack = 0;       // packing rounds consumed on bar_kblk[*]
             bool ok = true;
-            long long _t_commit = 0, _t_mma = 0;
             for (int t = 0; t < my_tiles && ok; ++t) {
                 const uint32_t xeh_lo = xeh_lo0 + (uint32_t)(t & 1) * (tc3::XE >> 4), xel_lo = xel_lo0 + (uint32_t)(t & 1) * (tc3::XE >> 4);
                 for (int l = 0; l < 4 && ok; ++l) {
@@ -1361,7 +1360,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(tc6::NTHR, 1) k_shad
                             if (!PNB_TIMED_WAIT_L0(3, mbar_wait(&sm.bar_full[s0], ph0, p.err, 67))) { ok = false; break; }
                         }
                         tc_fence_after();
-                        const long long _tm0 = clock64();
                         const uint32_t akb_hi = ahi_lo + (uint32_t)kb * (ABLK >> 4), akb_lo = alo_lo + (uint32_t)kb * (ABLK >> 4);
                         const uint32_t tcol = ab + (uint32_t)(kb * 32);
                         const uint32_t bl = b0_lo + s0 * (2 * tc6::HIMG >> 4), bl2 = bl + (tc6::HIMG >> 4);
@@ -1384,9 +1382,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(tc6::NTHR, 1) k_shad
                             mma2_ts2_w(acc, tcol, bl2, hiw, idesc, 1u);
                             mma2_ts2_w(acc, tcol + 16u, bl2 + KADV, hiw, idesc, 1u);
                         }
-                        if ((n % tc6::CPK) == tc6::CPK - 1) PROF6_COMMIT(mma2_commit_w(&sm.bar_empty[(n / tc6::CPK) % (tc6::NSTAGE / tc6::CPK)], 3));   // frees CPK ring stages in both CTAs
+                        if ((n % tc6::CPK) == tc6::CPK - 1) mma2_commit_w(&sm.bar_empty[(n / tc6::CPK) % (tc6::NSTAGE / tc6::CPK)], 3);   // frees CPK ring stages in both CTAs
                         n += 1;
-                        _t_mma += clock64() - _tm0;
                     }
                     if (!ok) break;
                     if (l >= 1) ++c_pack;
@@ -1394,7 +1391,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(tc6::NTHR, 1) k_shad
                     if (l == 0) mma2_commit_w(&sm.bar_a1_free, 3);
                 }
             }
-            if (lane == 0) { prof_add(p.err, 10, _t_commit); prof_add(p.err, 11, _t_mma); }
         }
     } else if (warp >= W_BUILD) {
         // ============================================================ builders: one thread per pair row of this CTA's tile

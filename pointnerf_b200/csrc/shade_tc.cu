@@ -68,7 +68,11 @@ struct ShadeTcParams {
     int* err;
     int dbg_no_weights;          // timing experiment only: the loader signals the ring without copying (results are garbage)
     int dbg_flags;               // bit 1: v6 issuer classifies its waits with non-blocking probes (profiling)
+    int hbar_fmt;                // 0: hbar[n_valid][256] fp32;  1: bf16 hi/lo A-operand blocks of k_color_tc2 (per 128 samples: 8 K blocks x {hi,lo} x [128x32])
 };
+__device__ __forceinline__ void prof_add(const ShadeTcParams& p, int slot, long long cyc) {
+    if ((p.dbg_flags & 1) && blockIdx.x == 0) atomicAdd(reinterpret_cast<unsigned long long*>(p.err) + 1 + slot, (unsigned long long)cyc);
+}
 
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
@@ -409,11 +413,10 @@ __global__ void __launch_bounds__(tc::NTHR, 1) k_shade_tc(ShadeTcParams p) {
 // per 32-bit column).  Warp roles (448 threads): 0-7 epilogue (TMEM -> bias/LeakyReLU/split -> TMEM), 8-11 builders,
 // 12 loader, 13 issuer.  The 7 block3 extras go through a small [128 x 16] shared-memory operand (one SS k-step).
 // Optional in-kernel cycle accounting (block 0 only): err[2 + 2*i], 64-bit counters, see tools/tc_profile.py
-__device__ __forceinline__ void prof_add(int* err, int slot, long long cyc) {
-    if (blockIdx.x == 0) atomicAdd(reinterpret_cast<unsigned long long*>(err) + 1 + slot, (unsigned long long)cyc);
-}
-#define PNB_TIMED_WAIT_L0(slot, expr) [&]() { long long _t0 = clock64(); bool _r = (expr); if ((threadIdx.x & 31) == 0) prof_add(p.err, slot, clock64() - _t0); return _r; }()
-#define PNB_TIMED_WAIT(slot, expr) [&]() { long long _t0 = clock64(); bool _r = (expr); prof_add(p.err, slot, clock64() - _t0); return _r; }()
+// Enabled by dbg_flags bit 0 (tools/tc_profile.py), a kernel parameter: the clock reads and atomics slow block 0 down by
+// several per cent, and a persistent kernel is as slow as its slowest CTA.
+#define PNB_TIMED_WAIT_L0(slot, expr) [&]() { long long _t0 = clock64(); bool _r = (expr); if ((threadIdx.x & 31) == 0) prof_add(p, slot, clock64() - _t0); return _r; }()
+#define PNB_TIMED_WAIT(slot, expr) [&]() { long long _t0 = clock64(); bool _r = (expr); prof_add(p, slot, clock64() - _t0); return _r; }()
 
 namespace tc3 {
 constexpr int NEPI_WARPS = 16, NEPI = NEPI_WARPS * 32, NBUILD = 128, NTHR = NEPI + NBUILD + 64;   // 704 threads
@@ -684,7 +687,7 @@ __global__ void __launch_bounds__(tc3::NTHR, 1) k_shade_tc3(ShadeTcParams p) {
             build_pair_row(sm, p, tile, t, row, n_valid);
             fence_proxy_async();
             mbar_arrive(&sm.bar_a1_ready);
-            if (lane == 0 && warp == W_BUILD) prof_add(p.err, 5, clock64() - _tb0);
+            if (lane == 0 && warp == W_BUILD) prof_add(p, 5, clock64() - _tb0);
         }
     } else {
         // ============================================================ epilogue warps 0..15: 64 columns per thread
@@ -722,7 +725,7 @@ __global__ void __launch_bounds__(tc3::NTHR, 1) k_shade_tc3(ShadeTcParams p) {
                     tmem_st_wait();
                     tc_fence_before();
                     mbar_arrive(&sm.bar_at_ready);
-                    if (tid == 0) prof_add(p.err, 7, clock64() - _te0);
+                    if (tid == 0) prof_add(p, 7, clock64() - _te0);
                 } else {
                     const float wrow = sm.wc[t & 1][erow];
                     const int sidx = tile * TSAMP + (erow >> 3);
@@ -766,7 +769,7 @@ __global__ void __launch_bounds__(tc3::NTHR, 1) k_shade_tc3(ShadeTcParams p) {
                     }
                     tc_fence_before();
                     mbar_arrive(&sm.bar_at_ready);          // accumulator drained: the next tile's layer 1 may start
-                    if (tid == 0) prof_add(p.err, 8, clock64() - _te0);
+                    if (tid == 0) prof_add(p, 8, clock64() - _te0);
                     if (part < 2) sm.alpha_part[part][erow] = apart;
                     named_bar_sync(1, tc3::NEPI);
                     if (part >= 2) atomicAdd(&sm.alpha_part[part - 2][erow], apart);
@@ -785,7 +788,7 @@ __global__ void __launch_bounds__(tc3::NTHR, 1) k_shade_tc3(ShadeTcParams p) {
             }
         }
     }
-    if (tid == 0) prof_add(p.err, 9, clock64() - _tk0);
+    if (tid == 0) prof_add(p, 9, clock64() - _tk0);
     tc_fence_before();
     __syncthreads();
     if (warp == W_ISSUE) tmem_dealloc<512>(tacc);
@@ -963,6 +966,70 @@ __global__ void __launch_bounds__(cb::NTHREADS, 1) k_color_branch(ColorParams p)
     }
 }
 
+// Last epilogue of a tile, one warp's share: chunks G, G+NG, G+2*NG, ... (NCHUNK of them, 16 accumulator columns each) of the
+// layer-4 output:
+// +bias, LeakyReLU, partial alpha-branch dot product (returned), weight*conf scaling and the K-reduction over the 8 rows of a
+// sample as a warp-shuffle reduce-scatter (lane j8 ends up with columns c0+2*j8, +1 of its sample) -> h-bar.
+template <int NG, int NCHUNK>
+__device__ __forceinline__ float last_chunks(const ShadeTcParams& p, uint32_t accb, int G, float wrow, int sidx, bool swrite, int lane) {
+    using namespace tc;
+    const float* bias = p.bias[3];
+    const int j8 = lane & 7;
+    float apart = 0.f;
+#pragma unroll
+    for (int i = 0; i < NCHUNK; ++i) {
+        const int c0 = 16 * (G + NG * i);
+        uint32_t v[16];
+        tmem_ld16(accb + (uint32_t)c0, v);
+        tmem_ld_wait();
+        float z[16];
+#pragma unroll
+        for (int e4 = 0; e4 < 4; ++e4) {
+            const float4 bb = __ldg(reinterpret_cast<const float4*>(bias + c0) + e4), ww = __ldg(reinterpret_cast<const float4*>(p.wa + c0) + e4);
+            const float bq[4] = {bb.x, bb.y, bb.z, bb.w}, wq[4] = {ww.x, ww.y, ww.z, ww.w};
+#pragma unroll
+            for (int e1 = 0; e1 < 4; ++e1) {
+                const int e = 4 * e4 + e1;
+                float y = __uint_as_float(v[e]) + bq[e1];
+                y = fmaxf(y, LEAKY * y);
+                apart = fmaf(y, wq[e1], apart);
+                z[e] = y * wrow;
+            }
+        }
+        float r8[8], r4[4], r2[2];
+        const bool b4 = lane & 4, b2 = lane & 2, b1 = lane & 1;
+#pragma unroll
+        for (int ii = 0; ii < 8; ++ii) {
+            float send = b4 ? z[ii] : z[ii + 8], keep = b4 ? z[ii + 8] : z[ii];
+            r8[ii] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+        }
+#pragma unroll
+        for (int ii = 0; ii < 4; ++ii) {
+            float send = b2 ? r8[ii] : r8[ii + 4], keep = b2 ? r8[ii + 4] : r8[ii];
+            r4[ii] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+        }
+#pragma unroll
+        for (int ii = 0; ii < 2; ++ii) {
+            float send = b1 ? r4[ii] : r4[ii + 2], keep = b1 ? r4[ii + 2] : r4[ii];
+            r2[ii] = keep + __shfl_xor_sync(0xffffffffu, send, 1);
+        }
+        if (swrite) {
+            if (p.hbar_fmt) {       // straight into the colour kernel's operand image (bf16 hi / lo, core-matrix layout)
+                uint32_t hh, ll;
+                split_bf16x2(r2[0], r2[1], hh, ll);
+                const int col = c0 + 2 * j8, srow = sidx & 127;
+                unsigned char* dst = reinterpret_cast<unsigned char*>(p.hbar) + ((size_t)(sidx >> 7) * 8 + (col >> 5)) * (2 * 8192) +
+                                     tile_offset_bytes<LAYOUT_NONE>(srow, col & 31);
+                *reinterpret_cast<uint32_t*>(dst) = hh;
+                *reinterpret_cast<uint32_t*>(dst + 8192) = ll;
+            } else {
+                *reinterpret_cast<float2*>(p.hbar + (size_t)sidx * 256 + c0 + 2 * j8) = make_float2(r2[0], r2[1]);
+            }
+        }
+    }
+    return apart;
+}
+
 // =====================================================================================================================
 // v5: "TMEM role ping-pong", single N=256 pass per layer.  The two 256-column TMEM regions P and Q alternate between
 // accumulator and A operand: the epilogue converts the finished accumulator IN PLACE, 16 columns at a time, into the
@@ -1120,7 +1187,7 @@ __global__ void __launch_bounds__(tc5::NTHR, 1) k_shade_tc5(ShadeTcParams p) {
             build_pair_row(sm, p, tile, t, row, n_valid);
             fence_proxy_async();
             mbar_arrive(&sm.bar_a1_ready);
-            if (lane == 0 && warp == W_BUILD) prof_add(p.err, 5, clock64() - _tb0);
+            if (lane == 0 && warp == W_BUILD) prof_add(p, 5, clock64() - _tb0);
         }
     } else {
         // ============================================================ epilogue warps
@@ -1158,50 +1225,16 @@ __global__ void __launch_bounds__(tc5::NTHR, 1) k_shade_tc5(ShadeTcParams p) {
                         tc_fence_before();
                         mbar_arrive(&sm.bar_kblk[g >> 1]);
                     }
-                    if (tid == 0) prof_add(p.err, 7, clock64() - _te0);
+                    if (tid == 0) prof_add(p, 7, clock64() - _te0);
                 } else {
                     const float wrow = sm.wc[t & 1][erow];
                     const int sidx = tile * TSAMP + (erow >> 3);
                     const bool swrite = sidx < n_valid;
-                    const float* bias = p.bias[3];
                     const int j8 = lane & 7;
-                    float apart = 0.f;
-#pragma unroll
-                    for (int i = 0; i < tc5::NCH; ++i) {
-                        const int c0 = 16 * (grp + tc5::NGRP * i);
-                        uint32_t v[16];
-                        tmem_ld16(accb + (uint32_t)c0, v);
-                        tmem_ld_wait();
-                        float z[16];
-#pragma unroll
-                        for (int e = 0; e < 16; ++e) {
-                            float y = __uint_as_float(v[e]) + __ldg(bias + c0 + e);
-                            y = fmaxf(y, LEAKY * y);
-                            apart = fmaf(y, __ldg(p.wa + c0 + e), apart);
-                            z[e] = y * wrow;
-                        }
-                        float r8[8], r4[4], r2[2];
-                        const bool b4 = lane & 4, b2 = lane & 2, b1 = lane & 1;
-#pragma unroll
-                        for (int ii = 0; ii < 8; ++ii) {
-                            float send = b4 ? z[ii] : z[ii + 8], keep = b4 ? z[ii + 8] : z[ii];
-                            r8[ii] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
-                        }
-#pragma unroll
-                        for (int ii = 0; ii < 4; ++ii) {
-                            float send = b2 ? r8[ii] : r8[ii + 4], keep = b2 ? r8[ii + 4] : r8[ii];
-                            r4[ii] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
-                        }
-#pragma unroll
-                        for (int ii = 0; ii < 2; ++ii) {
-                            float send = b1 ? r4[ii] : r4[ii + 2], keep = b1 ? r4[ii + 2] : r4[ii];
-                            r2[ii] = keep + __shfl_xor_sync(0xffffffffu, send, 1);
-                        }
-                        if (swrite) *reinterpret_cast<float2*>(p.hbar + (size_t)sidx * 256 + c0 + 2 * j8) = make_float2(r2[0], r2[1]);
-                    }
+                    const float apart = last_chunks<tc5::NGRP, tc5::NCH>(p, accb, grp, wrow, sidx, swrite, lane);
                     tc_fence_before();
                     mbar_arrive(&sm.bar_drain);                // accumulator region P drained
-                    if (tid == 0) prof_add(p.err, 8, clock64() - _te0);
+                    if (tid == 0) prof_add(p, 8, clock64() - _te0);
                     if (grp < 2) sm.alpha_part[grp][erow] = apart;
                     named_bar_sync(1, tc5::NEPI);
                     if (grp >= 2) atomicAdd(&sm.alpha_part[grp - 2][erow], apart);
@@ -1220,7 +1253,12 @@ __global__ void __launch_bounds__(tc5::NTHR, 1) k_shade_tc5(ShadeTcParams p) {
             }
         }
     }
-    if (tid == 0) prof_add(p.err, 9, clock64() - _tk0);
+    if (tid == 0) prof_add(p, 9, clock64() - _tk0);
+    if (tid == 0 && (p.dbg_flags & 4) && blockIdx.x < 192) {
+        uint32_t smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        reinterpret_cast<long long*>(p.err)[32 + blockIdx.x] = ((clock64() - _tk0) & 0xffffffffffffll) | ((long long)smid << 48);
+    }
     tc_fence_before();
     __syncthreads();
     if (warp == W_ISSUE) tmem_dealloc<512>(sm.tmem_base);
@@ -1249,8 +1287,10 @@ struct Smem {
     unsigned char xe_hi[2][tc3::XE];
     unsigned char xe_lo[2][tc3::XE];
     float wc[2][tc::TM];
-    float alpha_part[2][tc::TM];
-    uint64_t bar_full[NSTAGE], bar_empty[NSTAGE], bar_a1_ready, bar_a1_free, bar_acc_full, bar_drain, bar_kblk[8];
+    float alpha_part[2][tc::TM];         // builder groups' partial alpha dot products
+    float alpha_e[tc::TM];               // sum of the two epilogue groups' partials (atomicAdd of two addends onto 0: order-independent);
+                                         // read and re-zeroed by the builders, reuse ordered through bar_drain
+    uint64_t bar_full[NSTAGE], bar_empty[NSTAGE], bar_a1_ready, bar_a1_free, bar_acc_full, bar_final, bar_alpha, bar_drain, bar_kblk[8];
     uint32_t tmem_base;
 };
 }  // namespace tc6
@@ -1265,8 +1305,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(tc6::NTHR, 1) k_shad
     const int n_valid = min(q.counters[PNB_QC_N_VALID], p.hbar_cap);
     const int n_tiles = (n_valid + TSAMP - 1) / TSAMP;
     const int n_ptiles = (n_tiles + 1) >> 1;                       // pair tiles: tiles 2i (rank 0) and 2i+1 (rank 1)
-    const int pair = (int)blockIdx.x >> 1, npairs = (int)gridDim.x >> 1;
-    const int my_tiles = n_ptiles > pair ? (n_ptiles - 1 - pair) / npairs + 1 : 0;
+    int pair = (int)blockIdx.x >> 1, npairs = (int)gridDim.x >> 1;
+    const bool idle_pair = (p.dbg_flags & 8) && (pair & 1);      // experiment: only every other CTA pair works
+    if (p.dbg_flags & 8) { pair >>= 1; npairs = (npairs + 1) >> 1; }
+    const int my_tiles = (n_ptiles > pair && !idle_pair) ? (n_ptiles - 1 - pair) / npairs + 1 : 0;
     constexpr int W_BUILD = tc6::NEPI_WARPS, W_LOAD = W_BUILD + tc6::NBUILD / 32, W_ISSUE = W_LOAD + 1, W_FWD = W_ISSUE + 1;
     constexpr uint32_t SMASK = tc6::NSTAGE - 1;
 
@@ -1275,11 +1317,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(tc6::NTHR, 1) k_shad
         mbar_init(&sm.bar_a1_ready, 2 * tc6::NBUILD);              // leader's: the builder threads of both CTAs
         mbar_init(&sm.bar_a1_free, 1);
         mbar_init(&sm.bar_acc_full, 1);
-        mbar_init(&sm.bar_drain, 2 * tc6::NEPI_WARPS);             // leader's: one arrive per epilogue warp of both CTAs
+        mbar_init(&sm.bar_final, 1);
+        mbar_init(&sm.bar_alpha, tc6::NEPI_WARPS);
+        mbar_init(&sm.bar_drain, 2 * (tc6::NEPI_WARPS + tc6::NBUILD / 32));   // leader's: every warp of both CTAs that reads the layer-4 accumulator
         for (int c = 0; c < 8; ++c) mbar_init(&sm.bar_kblk[c], 2 * 4 * 2);   // leader's: 2 CTAs x 4 quadrant warps x 2 chunks
         mbar_fence_init();
         if (blockIdx.x == 0 && q.counters[PNB_QC_N_VALID] > p.hbar_cap) atomicExch(p.err, 9);
     }
+    if (tid < TM) sm.alpha_e[tid] = 0.f;
     if (warp == W_ISSUE) tmem_alloc2<512>(&sm.tmem_base);
     tc_fence_before();
     cluster_sync_all();
@@ -1296,7 +1341,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(tc6::NTHR, 1) k_shad
                 const uint32_t s = n & SMASK, ph = (n >> 2) & 1u;
                 const long long _tl0 = clock64();
                 if ((n % tc6::CPK) == 0 && !mbar_wait(&sm.bar_empty[(n / tc6::CPK) % (tc6::NSTAGE / tc6::CPK)], ph ^ 1u, p.err, 61)) break;
-                if (blockIdx.x < 2) atomicAdd(reinterpret_cast<unsigned long long*>(p.err) + 1 + (blockIdx.x ? 15 : 0), (unsigned long long)(clock64() - _tl0));
+                if (blockIdx.x < 2 && (p.dbg_flags & 1)) atomicAdd(reinterpret_cast<unsigned long long*>(p.err) + 1 + (blockIdx.x ? 15 : 0), (unsigned long long)(clock64() - _tl0));
                 if (p.dbg_no_weights) { mbar_arrive(&sm.bar_full[s]); continue; }
                 mbar_arrive_expect_tx(&sm.bar_full[s], 2 * tc6::HIMG);
                 const unsigned char* g = src + (size_t)(n % NBLK_TOTAL) * (2 * IMG);
@@ -1333,7 +1378,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(tc6::NTHR, 1) k_shad
                 for (int l = 0; l < 4 && ok; ++l) {
                     const uint32_t acc = (l & 1) ? tP : tQ;
                     const uint32_t ab = (l & 1) ? tQ : tP;
-                    if (t > 0 || l > 0) { if (!PNB_TIMED_WAIT_L0(2, mbar_wait(&sm.bar_acc_full, c_acc & 1u, p.err, 63))) { ok = false; break; } ++c_acc; }
+                    if (l > 0) { if (!PNB_TIMED_WAIT_L0(2, mbar_wait(&sm.bar_acc_full, c_acc & 1u, p.err, 63))) { ok = false; break; } ++c_acc; }
+                    else if (t > 0) { if (!PNB_TIMED_WAIT_L0(2, mbar_wait(&sm.bar_final, (uint32_t)(t - 1) & 1u, p.err, 63))) { ok = false; break; } }
                     if (l == 0) { if (!PNB_TIMED_WAIT_L0(1, mbar_wait(&sm.bar_a1_ready, (uint32_t)t & 1u, p.err, 64))) { ok = false; break; } }
                     if (l == 1 && t > 0) { if (!PNB_TIMED_WAIT_L0(2, mbar_wait(&sm.bar_drain, (uint32_t)(t - 1) & 1u, p.err, 65))) { ok = false; break; } }
                     tc_fence_after();
@@ -1350,7 +1396,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(tc6::NTHR, 1) k_shad
                             if (!mbar_test_wait(&sm.bar_full[s0], ph0)) {
                                 const long long _tw = clock64();
                                 if (!mbar_spin_wait(&sm.bar_full[s0], ph0, p.err, 67)) { ok = false; break; }
-                                if (lane == 0) { prof_add(p.err, 13, clock64() - _tw); prof_add(p.err, 14, 1); }
+                                if (lane == 0) { prof_add(p, 13, clock64() - _tw); prof_add(p, 14, 1); }
                             }
                         } else
                         if (!mbar_try_wait4(&sm.bar_full[s0], ph0, cb0, cp0, &sm.bar_full[s0], ph0, cb0, cp0)) {
@@ -1387,7 +1433,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(tc6::NTHR, 1) k_shad
                     }
                     if (!ok) break;
                     if (l >= 1) ++c_pack;
-                    mma2_commit_w(&sm.bar_acc_full, 3);
+                    mma2_commit_w(l < 3 ? &sm.bar_acc_full : &sm.bar_final, 3);     // layers 1-3 -> epilogue warps, layer 4 -> builder warps
                     if (l == 0) mma2_commit_w(&sm.bar_a1_free, 3);
                 }
             }
@@ -1395,34 +1441,68 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(tc6::NTHR, 1) k_shad
     } else if (warp >= W_BUILD) {
         // ============================================================ builders: one thread per pair row of this CTA's tile
         const int bt = (warp - W_BUILD) * 32 + lane, row = bt & 127, part = bt >> 7;     // two threads per row (columns 0..151 | 152..287)
-        const uint32_t ready0 = map_to_cta(&sm.bar_a1_ready, 0);
+        const uint32_t ready0 = map_to_cta(&sm.bar_a1_ready, 0), drain0 = map_to_cta(&sm.bar_drain, 0);
+        // the same warps run the LAST epilogue of a tile (alpha branch, Softplus, weighted K-reduction -> h-bar, sigma): it falls
+        // under layer 1 of the next tile, exactly when the builders are idle (the operand buffer is still being read)
+        const int quad = warp & 3, grp = (warp - W_BUILD) >> 2;
+        const int erow = quad * 32 + lane;
+        const uint32_t tlane = (uint32_t)(quad * 32) << 16;
         bool ok = true;
-        for (int t = 0; t < my_tiles && ok; ++t) {
-            const int tile = 2 * (pair + t * npairs) + (int)rank;
-            if (t > 0 && !(lane == 0 && warp == W_BUILD ? PNB_TIMED_WAIT(4, mbar_wait(&sm.bar_a1_free, (uint32_t)(t - 1) & 1u, p.err, 68)) : mbar_wait(&sm.bar_a1_free, (uint32_t)(t - 1) & 1u, p.err, 68))) { ok = false; break; }
-            const long long _tb0 = clock64();
-            if (part == 0) build_pair_part<0>(sm, p, tile, t, row, n_valid);
-            else build_pair_part<1>(sm, p, tile, t, row, n_valid);
-            fence_proxy_async();
-            if (rank == 0) mbar_arrive(&sm.bar_a1_ready); else mbar_arrive_cluster(ready0);
-            if (lane == 0 && warp == W_BUILD) prof_add(p.err, 5, clock64() - _tb0);
+        for (int t = 0; t <= my_tiles && ok; ++t) {
+            if (t < my_tiles) {
+                const int tile = 2 * (pair + t * npairs) + (int)rank;
+                if (t > 0 && !(lane == 0 && warp == W_BUILD ? PNB_TIMED_WAIT(4, mbar_wait(&sm.bar_a1_free, (uint32_t)(t - 1) & 1u, p.err, 68)) : mbar_wait(&sm.bar_a1_free, (uint32_t)(t - 1) & 1u, p.err, 68))) { ok = false; break; }
+                const long long _tb0 = clock64();
+                if (part == 0) build_pair_part<0>(sm, p, tile, t, row, n_valid);
+                else build_pair_part<1>(sm, p, tile, t, row, n_valid);
+                fence_proxy_async();
+                if (rank == 0) mbar_arrive(&sm.bar_a1_ready); else mbar_arrive_cluster(ready0);
+                if (lane == 0 && warp == W_BUILD) prof_add(p, 5, clock64() - _tb0);
+            }
+            if (t > 0) {
+                const int tf = t - 1, tilef = 2 * (pair + tf * npairs) + (int)rank;
+                if (!mbar_wait(&sm.bar_final, (uint32_t)tf & 1u, p.err, 70)) { ok = false; break; }
+                const long long _te0 = clock64();
+                tc_fence_after();
+                const uint32_t accb = tP + tlane;          // layer 4 accumulates into region P
+                const float wrow = sm.wc[tf & 1][erow];
+                const int sidx = tilef * TSAMP + (erow >> 3);
+                const bool swrite = sidx < n_valid;
+                const float apart = last_chunks<4, 4>(p, accb, 2 + grp, wrow, sidx, swrite, lane);
+                tc_fence_before();
+                if (bt == 0) prof_add(p, 8, clock64() - _te0);
+                sm.alpha_part[grp][erow] = apart;
+                named_bar_sync(2, tc6::NBUILD);
+                if (!mbar_wait(&sm.bar_alpha, (uint32_t)tf & 1u, p.err, 71)) { ok = false; break; }      // the epilogue warps' partial sums
+                if (grp == 0) {
+                    float a = (sm.alpha_part[0][erow] + sm.alpha_part[1][erow]) + sm.alpha_e[erow] + __ldg(p.ba) - 1.0f;
+                    sm.alpha_e[erow] = 0.f;
+                    float sp = a > 20.f ? a : log1pf(expf(a));
+                    float zz = sp * wrow;
+                    zz += __shfl_xor_sync(0xffffffffu, zz, 1);
+                    zz += __shfl_xor_sync(0xffffffffu, zz, 2);
+                    zz += __shfl_xor_sync(0xffffffffu, zz, 4);
+                    if ((lane & 7) == 0 && swrite) p.sigma[sidx] = zz;
+                }
+                __syncwarp();
+                if (lane == 0) { if (rank == 0) mbar_arrive(&sm.bar_drain); else mbar_arrive_cluster(drain0); }   // after the alpha_e reads (see Smem)
+                named_bar_sync(2, tc6::NBUILD);
+            }
         }
     } else {
         // ============================================================ epilogue warps
         const int quad = warp & 3, grp = warp >> 2;
-        const int erow = quad * 32 + lane;
         const uint32_t tlane = (uint32_t)(quad * 32) << 16;
         const uint32_t kblk0 = map_to_cta(&sm.bar_kblk[0], 0), drain0 = map_to_cta(&sm.bar_drain, 0);
         uint32_t n_acc = 0;
         bool ok = true;
         for (int t = 0; t < my_tiles && ok; ++t) {
-            const int tile = 2 * (pair + t * npairs) + (int)rank;
-            for (int l = 0; l < 4 && ok; ++l, ++n_acc) {
+            for (int l = 0; l < 3 && ok; ++l, ++n_acc) {        // the layer-4 (last) epilogue runs on the builder warps
                 if (!(tid == 0 ? PNB_TIMED_WAIT(6, mbar_wait(&sm.bar_acc_full, n_acc & 1u, p.err, 69)) : mbar_wait(&sm.bar_acc_full, n_acc & 1u, p.err, 69))) { ok = false; break; }
                 const long long _te0 = clock64();
                 tc_fence_after();
                 const uint32_t accb = ((l & 1) ? tP : tQ) + tlane;
-                if (l < 3) {
+                {
                     const float* bias = p.bias[l];
 #pragma unroll
                     for (int i = 0; i < tc6::NCH; ++i) {
@@ -1445,70 +1525,33 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(tc6::NTHR, 1) k_shad
                         __syncwarp();
                         if (lane == 0) { if (rank == 0) mbar_arrive(&sm.bar_kblk[g >> 1]); else mbar_arrive_cluster(kblk0 + 8u * (uint32_t)(g >> 1)); }
                     }
-                    if (tid == 0) prof_add(p.err, 7, clock64() - _te0);
-                } else {
-                    const float wrow = sm.wc[t & 1][erow];
-                    const int sidx = tile * TSAMP + (erow >> 3);
-                    const bool swrite = sidx < n_valid;
-                    const float* bias = p.bias[3];
-                    const int j8 = lane & 7;
-                    float apart = 0.f;
-#pragma unroll
-                    for (int i = 0; i < tc6::NCH; ++i) {
-                        const int c0 = 16 * (grp + tc6::NGRP * i);
-                        uint32_t v[16];
-                        tmem_ld16(accb + (uint32_t)c0, v);
-                        tmem_ld_wait();
-                        float z[16];
-#pragma unroll
-                        for (int e = 0; e < 16; ++e) {
-                            float y = __uint_as_float(v[e]) + __ldg(bias + c0 + e);
-                            y = fmaxf(y, LEAKY * y);
-                            apart = fmaf(y, __ldg(p.wa + c0 + e), apart);
-                            z[e] = y * wrow;
-                        }
-                        float r8[8], r4[4], r2[2];
-                        const bool b4 = lane & 4, b2 = lane & 2, b1 = lane & 1;
-#pragma unroll
-                        for (int ii = 0; ii < 8; ++ii) {
-                            float send = b4 ? z[ii] : z[ii + 8], keep = b4 ? z[ii + 8] : z[ii];
-                            r8[ii] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
-                        }
-#pragma unroll
-                        for (int ii = 0; ii < 4; ++ii) {
-                            float send = b2 ? r8[ii] : r8[ii + 4], keep = b2 ? r8[ii + 4] : r8[ii];
-                            r4[ii] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
-                        }
-#pragma unroll
-                        for (int ii = 0; ii < 2; ++ii) {
-                            float send = b1 ? r4[ii] : r4[ii + 2], keep = b1 ? r4[ii + 2] : r4[ii];
-                            r2[ii] = keep + __shfl_xor_sync(0xffffffffu, send, 1);
-                        }
-                        if (swrite) *reinterpret_cast<float2*>(p.hbar + (size_t)sidx * 256 + c0 + 2 * j8) = make_float2(r2[0], r2[1]);
-                    }
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) { if (rank == 0) mbar_arrive(&sm.bar_drain); else mbar_arrive_cluster(drain0); }   // this warp's share of region P drained
-                    if (tid == 0) prof_add(p.err, 8, clock64() - _te0);
-                    if (grp < 2) sm.alpha_part[grp][erow] = apart;
-                    named_bar_sync(1, tc6::NEPI);
-                    if (grp >= 2) atomicAdd(&sm.alpha_part[grp - 2][erow], apart);
-                    if (tc6::NGRP > 2) named_bar_sync(1, tc6::NEPI);
-                    if (grp == 0) {
-                        float a = sm.alpha_part[0][erow] + (tc6::NGRP > 1 ? sm.alpha_part[1][erow] : 0.f) + __ldg(p.ba) - 1.0f;
-                        float sp = a > 20.f ? a : log1pf(expf(a));
-                        float zz = sp * wrow;
-                        zz += __shfl_xor_sync(0xffffffffu, zz, 1);
-                        zz += __shfl_xor_sync(0xffffffffu, zz, 2);
-                        zz += __shfl_xor_sync(0xffffffffu, zz, 4);
-                        if (j8 == 0 && swrite) p.sigma[sidx] = zz;
-                    }
-                    named_bar_sync(1, tc6::NEPI);
+                    if (tid == 0) prof_add(p, 7, clock64() - _te0);
+                }
+            }
+            if (!ok) break;
+            {   // this warp's share of the LAST epilogue (chunk groups 0, 1; the builder warps take 2, 3)
+                const int tile = 2 * (pair + t * npairs) + (int)rank;
+                if (!mbar_wait(&sm.bar_final, (uint32_t)t & 1u, p.err, 72)) { ok = false; break; }
+                tc_fence_after();
+                const int erow = quad * 32 + lane;
+                const int sidx = tile * TSAMP + (erow >> 3);
+                const float apart = last_chunks<4, 4>(p, tP + tlane, grp, sm.wc[t & 1][erow], sidx, sidx < n_valid, lane);
+                tc_fence_before();
+                atomicAdd(&sm.alpha_e[erow], apart);
+                __syncwarp();
+                if (lane == 0) {
+                    mbar_arrive(&sm.bar_alpha);
+                    if (rank == 0) mbar_arrive(&sm.bar_drain); else mbar_arrive_cluster(drain0);
                 }
             }
         }
     }
-    if (tid == 0) prof_add(p.err, 9, clock64() - _tk0);
+    if (tid == 0) prof_add(p, 9, clock64() - _tk0);
+    if (tid == 0 && (p.dbg_flags & 4) && blockIdx.x < 192) {      // per-CTA cycles and SM id (needs a 512-int err buffer)
+        uint32_t smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        reinterpret_cast<long long*>(p.err)[32 + blockIdx.x] = ((clock64() - _tk0) & 0xffffffffffffll) | ((long long)smid << 48);
+    }
     __syncwarp();
     tc_fence_before();
     cluster_sync_all();
@@ -1772,6 +1815,272 @@ __global__ void __launch_bounds__(ctc::NTHR, 1) k_color_tc(ColorTcParams p) {
     if (warp == 9) tmem_dealloc<256>(tacc);
 }
 
+// =====================================================================================================================
+// Colour branch, pipelined (v2).  The pair kernel (v6) writes h-bar already split into bf16 hi / lo and laid out as the
+// tcgen05 A-operand blocks of this kernel: per 128 consecutive valid samples 8 K-blocks x {hi, lo} x [128 x 32]
+// (interleaved core-matrix layout) = one contiguous 128 KB region.  So the layer-1 operand is ONE bulk copy (TMA engine)
+// per tile - no builder warps, no register traffic - issued as soon as the previous tile's layer-1 MMAs have completed,
+// and it lands under that tile's layers 2-3.  Same TMEM role ping-pong / in-place accumulator->operand conversion and
+// chunk-granular hand-off as the pair kernel; two accumulator sets (tile parity) so a tile's final epilogue
+// (128 -> 3 on CUDA cores + sigmoid) runs under the next tile's layer 1.  One tcgen05.commit per K block.
+//   layer 1: A smem (8 K-blocks h-bar + 1 K-block PE(view)), acc X      layer 2: A = X, acc Y      layer 3: A = Y, acc X
+//   X = 256*(t&1), Y = X + 128 (TMEM columns)
+// Warps (480 threads): 0-7 epilogue (quadrant = w & 3, chunk group = w >> 2), 8-11 PE(view) builders (thread = row),
+// 12 operand loader, 13 weight loader, 14 issuer (whole warp, warp-uniform).
+namespace ctc2 {
+constexpr int NEPI_WARPS = 8, NGRP = 2, NCH = 8 / NGRP;     // 8 chunks of 16 accumulator columns per layer
+constexpr int NEPI = NEPI_WARPS * 32, NTHR = NEPI + 128 + 96;
+constexpr int NSTAGE = 4;
+constexpr int BLK = 128 * 64;                // [128 x 32] bf16 block (operand block and weight image)
+constexpr int NKB = 9 + 4 + 4;               // K blocks per tile
+constexpr int TILE_BYTES = 8 * 2 * BLK;      // h-bar operand of one tile in global memory
+struct Smem {
+    unsigned char a[8][2][BLK];              // layer-1 operand: K block, hi/lo
+    unsigned char pe[2][BLK];                // PE(view) K block, hi/lo
+    unsigned char b[NSTAGE][2][BLK];         // weight ring: hi / lo image of one K block
+    float part[128][4];
+    uint64_t bar_full[NSTAGE], bar_empty[NSTAGE], bar_a_full, bar_a_free, bar_pe_ready, bar_acc_full, bar_drain, bar_kblk[4];
+    uint32_t tmem_base;
+};
+__host__ __device__ constexpr int nkb_of(int l) { return l == 0 ? 9 : 4; }
+}  // namespace ctc2
+
+__global__ void __launch_bounds__(ctc2::NTHR, 1) k_color_tc2(ColorTcParams p) {
+    using namespace ctc2;
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    Smem& sm = *reinterpret_cast<Smem*>(smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u));
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const pnb_query_t& q = p.q;
+    const int n_valid = min(q.counters[PNB_QC_N_VALID], p.hbar_cap);
+    const int n_tiles = (n_valid + 127) / 128;
+    const int my_tiles = n_tiles > (int)blockIdx.x ? (n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+    constexpr int W_PE = NEPI_WARPS, W_LOADA = W_PE + 4, W_LOADW = W_LOADA + 1, W_ISSUE = W_LOADW + 1;
+
+    if (tid == 0) {
+        for (int s = 0; s < NSTAGE; ++s) { mbar_init(&sm.bar_full[s], 1); mbar_init(&sm.bar_empty[s], 1); }
+        mbar_init(&sm.bar_a_full, 1);
+        mbar_init(&sm.bar_a_free, 1);
+        mbar_init(&sm.bar_pe_ready, 128);
+        mbar_init(&sm.bar_acc_full, 1);
+        mbar_init(&sm.bar_drain, NEPI_WARPS);
+        for (int c = 0; c < 4; ++c) mbar_init(&sm.bar_kblk[c], 4 * 2);      // 4 quadrant warps x 2 chunks of 16 columns
+        mbar_fence_init();
+    }
+    if (warp == W_ISSUE) tmem_alloc<512>(&sm.tmem_base);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tbase = sm.tmem_base;
+
+    if (warp == W_LOADA) {
+        // ============================================================ layer-1 operand: one 128 KB region per tile
+        if (lane == 0) {
+            for (int t = 0; t < my_tiles; ++t) {
+                const int tile = (int)blockIdx.x + t * (int)gridDim.x;
+                if (t > 0 && !mbar_wait(&sm.bar_a_free, (uint32_t)(t - 1) & 1u, p.err, 81)) break;
+                mbar_arrive_expect_tx(&sm.bar_a_full, TILE_BYTES);
+                const unsigned char* src = reinterpret_cast<const unsigned char*>(p.hbar) + (size_t)tile * TILE_BYTES;
+#pragma unroll 1
+                for (int c = 0; c < 8; ++c) bulk_g2s(sm.a[c][0], src + (size_t)c * 2 * BLK, 2 * BLK, &sm.bar_a_full);
+            }
+        }
+    } else if (warp == W_LOADW) {
+        // ============================================================ weight ring: hi + lo image of one K block per stage
+        if (lane == 0) {
+            const uint32_t total = (uint32_t)my_tiles * NKB;
+            for (uint32_t n = 0; n < total; ++n) {
+                const uint32_t s = n & (NSTAGE - 1), ph = (n >> 2) & 1u;
+                if (!mbar_wait(&sm.bar_empty[s], ph ^ 1u, p.err, 82)) break;
+                mbar_arrive_expect_tx(&sm.bar_full[s], 2 * BLK);
+                bulk_g2s(sm.b[s][0], p.wimg + (size_t)(n % NKB) * 2 * BLK, 2 * BLK, &sm.bar_full[s]);
+            }
+        }
+    } else if (warp == W_ISSUE) {
+        // ============================================================ MMA issuer (whole warp, warp-uniform)
+        const uint32_t idesc = make_idesc_bf16(128, 128);
+        const uint32_t hiw = desc_hi<tc::LAYOUT>();
+        const uint32_t b0_lo = desc_lo<tc::LAYOUT>(smem_u32(sm.b[0][0]));
+        const uint32_t a0_lo = desc_lo<tc::LAYOUT>(smem_u32(sm.a[0][0])), pe_lo = desc_lo<tc::LAYOUT>(smem_u32(sm.pe[0]));
+        constexpr uint32_t KADV = kstep_adv16<tc::LAYOUT>(), BADV = BLK >> 4;
+        uint32_t n = 0, c_acc = 0, c_pack = 0;
+        bool ok = true;
+        for (int t = 0; t < my_tiles && ok; ++t) {
+            const uint32_t tX = tbase + 256u * (uint32_t)(t & 1), tY = tX + 128u;
+            for (int l = 0; l < 3 && ok; ++l) {
+                const uint32_t acc = (l == 1) ? tY : tX, ab = (l == 1) ? tX : tY;
+                // WAR on tensor memory: the MMAs of the previous layer read this layer's accumulator region as their A operand and must
+                // be complete.  Every completion of bar_acc_full is consumed before the commit of the next one is issued (a parity
+                // wait overtaken by two completions would never return): layer 3 of the previous tile is consumed inside layer 1,
+                // before its last K block (see below); the previous tile's drain here, where it is complete in steady state.
+                if (l == 1 && t > 0) {
+                    if (!mbar_wait(&sm.bar_drain, (uint32_t)(t - 1) & 1u, p.err, 86)) { ok = false; break; }
+                }
+                if (l > 0) { if (!mbar_wait(&sm.bar_acc_full, c_acc & 1u, p.err, 83)) { ok = false; break; } ++c_acc; }
+                if (l == 0) {
+                    if (!mbar_wait(&sm.bar_a_full, (uint32_t)t & 1u, p.err, 84)) { ok = false; break; }
+                    if (!mbar_wait(&sm.bar_pe_ready, (uint32_t)t & 1u, p.err, 85)) { ok = false; break; }
+                }
+                tc_fence_after();
+                const int nkb = nkb_of(l);
+                for (int kb = 0; kb < nkb && ok; ++kb, ++n) {
+                    const uint32_t s = n & (NSTAGE - 1), ph = (n >> 2) & 1u;
+                    const bool need_chunks = l >= 1;
+                    if (l == 0 && t > 0 && kb == nkb - 1) {      // layer 3 of the previous tile: complete by now (ring depth < 8 K blocks)
+                        if (!mbar_wait(&sm.bar_acc_full, c_acc & 1u, p.err, 83)) { ok = false; break; }
+                        ++c_acc;
+                    }
+                    uint64_t* cb0 = need_chunks ? &sm.bar_kblk[kb] : &sm.bar_full[s];
+                    const uint32_t cp0 = need_chunks ? (c_pack & 1u) : ph;
+                    if (!mbar_try_wait4(&sm.bar_full[s], ph, cb0, cp0, &sm.bar_full[s], ph, cb0, cp0)) {
+                        if (need_chunks && !mbar_wait(cb0, cp0, p.err, 87)) { ok = false; break; }
+                        if (!mbar_wait(&sm.bar_full[s], ph, p.err, 88)) { ok = false; break; }
+                    }
+                    tc_fence_after();
+                    const uint32_t bh = b0_lo + s * (2 * BADV), bl = bh + BADV;
+                    if (l == 0) {
+                        const uint32_t ah = (kb < 8) ? a0_lo + (uint32_t)kb * (2 * BADV) : pe_lo, al = ah + BADV;
+                        mma_ss2_w(acc, ah, hiw, bh, hiw, idesc, kb ? 1u : 0u);
+                        mma_ss2_w(acc, al, hiw, bh, hiw, idesc, 1u);
+                        mma_ss2_w(acc, ah + KADV, hiw, bh + KADV, hiw, idesc, 1u);
+                        mma_ss2_w(acc, al + KADV, hiw, bh + KADV, hiw, idesc, 1u);
+                        mma_ss2_w(acc, ah, hiw, bl, hiw, idesc, 1u);
+                        mma_ss2_w(acc, ah + KADV, hiw, bl + KADV, hiw, idesc, 1u);
+                    } else {
+                        const uint32_t tcol = ab + (uint32_t)(kb * 32);        // in-place packed operand: 16-column chunk = 8 hi | 8 lo
+                        mma_ts2_w(acc, tcol, bh, hiw, idesc, kb ? 1u : 0u);
+                        mma_ts2_w(acc, tcol + 8u, bh, hiw, idesc, 1u);
+                        mma_ts2_w(acc, tcol + 16u, bh + KADV, hiw, idesc, 1u);
+                        mma_ts2_w(acc, tcol + 24u, bh + KADV, hiw, idesc, 1u);
+                        mma_ts2_w(acc, tcol, bl, hiw, idesc, 1u);
+                        mma_ts2_w(acc, tcol + 16u, bl + KADV, hiw, idesc, 1u);
+                    }
+                    mma_commit_w(&sm.bar_empty[s]);
+                }
+                if (!ok) break;
+                if (l >= 1) ++c_pack;
+                mma_commit_w(&sm.bar_acc_full);
+                if (l == 0) mma_commit_w(&sm.bar_a_free);
+            }
+        }
+    } else if (warp >= W_PE) {
+        // ============================================================ PE(view) K block of the next tile (thread = sample row)
+        const int row = (warp - W_PE) * 32 + lane;
+        for (int t = 0; t < my_tiles; ++t) {
+            const int tile = (int)blockIdx.x + t * (int)gridDim.x;
+            if (t > 0 && !mbar_wait(&sm.bar_a_free, (uint32_t)(t - 1) & 1u, p.err, 89)) break;
+            const int vi = tile * 128 + row;
+            float pe[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) pe[i] = 0.f;
+            if (vi < n_valid) {
+                const uint32_t s = q.valid_list[vi];
+                const int r = (int)(q.samp_ray[s] >> 7);
+                float ov[3];
+                rot3t(p.o.Rw2c, q.raydir[3 * r], q.raydir[3 * r + 1], q.raydir[3 * r + 2], ov[0], ov[1], ov[2]);
+#pragma unroll
+                for (int d = 0; d < 3; ++d) {     // ori=True layout: sin block (d*4+j) then cos block
+                    float sc[8];
+                    pe_doubling<4>(ov[d], sc);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) { pe[d * 4 + j] = sc[2 * j]; pe[12 + d * 4 + j] = sc[2 * j + 1]; }
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                uint32_t h[4], l[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) split_bf16x2(pe[8 * c + 2 * i], pe[8 * c + 2 * i + 1], h[i], l[i]);
+                const uint32_t off = tile_offset_bytes<tc::LAYOUT>(row, 8 * c);
+                *reinterpret_cast<uint4*>(sm.pe[0] + off) = make_uint4(h[0], h[1], h[2], h[3]);
+                *reinterpret_cast<uint4*>(sm.pe[1] + off) = make_uint4(l[0], l[1], l[2], l[3]);
+            }
+            fence_proxy_async();
+            mbar_arrive(&sm.bar_pe_ready);
+        }
+    } else {
+        // ============================================================ epilogue warps
+        const int quad = warp & 3, grp = warp >> 2;
+        const int erow = quad * 32 + lane;
+        const uint32_t tlane = (uint32_t)(quad * 32) << 16;
+        uint32_t n_acc = 0;
+        bool ok = true;
+        for (int t = 0; t < my_tiles && ok; ++t) {
+            const int tile = (int)blockIdx.x + t * (int)gridDim.x;
+            const uint32_t tX = tbase + 256u * (uint32_t)(t & 1), tY = tX + 128u;
+            for (int l = 0; l < 3 && ok; ++l, ++n_acc) {
+                if (!mbar_wait(&sm.bar_acc_full, n_acc & 1u, p.err, 90)) { ok = false; break; }
+                tc_fence_after();
+                const uint32_t accb = ((l == 1) ? tY : tX) + tlane;
+                const float* bias = p.bias[l];
+                if (l < 2) {
+#pragma unroll
+                    for (int i = 0; i < NCH; ++i) {
+                        const int g = grp + NGRP * i, c0 = 16 * g;
+                        uint32_t v[16];
+                        tmem_ld16(accb + (uint32_t)c0, v);
+                        tmem_ld_wait();
+                        uint32_t hh[8], ll[8];
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) {
+                            float2 bb = __ldg(reinterpret_cast<const float2*>(bias + c0) + e);
+                            float y0 = __uint_as_float(v[2 * e]) + bb.x, y1 = __uint_as_float(v[2 * e + 1]) + bb.y;
+                            y0 = fmaxf(y0, tc::LEAKY * y0); y1 = fmaxf(y1, tc::LEAKY * y1);
+                            split_bf16x2(y0, y1, hh[e], ll[e]);
+                        }
+                        tmem_st8(accb + (uint32_t)c0, hh);
+                        tmem_st8(accb + (uint32_t)c0 + 8u, ll);
+                        tmem_st_wait();
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&sm.bar_kblk[g >> 1]);
+                    }
+                } else {
+                    float d0 = 0.f, d1 = 0.f, d2 = 0.f;
+#pragma unroll
+                    for (int i = 0; i < NCH; ++i) {
+                        const int c0 = 16 * (grp + NGRP * i);
+                        uint32_t v[16];
+                        tmem_ld16(accb + (uint32_t)c0, v);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int e = 0; e < 16; ++e) {
+                            float y = __uint_as_float(v[e]) + __ldg(bias + c0 + e);
+                            y = fmaxf(y, tc::LEAKY * y);
+                            const float* wr = p.w3t + (c0 + e) * 3;
+                            d0 = fmaf(y, __ldg(wr), d0); d1 = fmaf(y, __ldg(wr + 1), d1); d2 = fmaf(y, __ldg(wr + 2), d2);
+                        }
+                    }
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&sm.bar_drain);          // this warp's share of accumulator set X drained
+                    if (grp == 1) { sm.part[erow][0] = d0; sm.part[erow][1] = d1; sm.part[erow][2] = d2; }
+                    named_bar_sync(1, NEPI);
+                    if (grp == 0) {
+                        const int vi = tile * 128 + erow;
+                        if (vi < n_valid) {
+                            const uint32_t s = q.valid_list[vi];
+                            float4 o4;
+                            o4.x = p.sigma[vi];
+                            const float r0 = d0 + sm.part[erow][0] + __ldg(p.b3);
+                            const float r1 = d1 + sm.part[erow][1] + __ldg(p.b3 + 1);
+                            const float r2 = d2 + sm.part[erow][2] + __ldg(p.b3 + 2);
+                            o4.y = 1.0f / (1.0f + expf(-r0)) * (1.0f + 2.0f * 0.001f) - 0.001f;
+                            o4.z = 1.0f / (1.0f + expf(-r1)) * (1.0f + 2.0f * 0.001f) - 0.001f;
+                            o4.w = 1.0f / (1.0f + expf(-r2)) * (1.0f + 2.0f * 0.001f) - 0.001f;
+                            p.sigma_rgb[s] = o4;
+                        }
+                    }
+                    named_bar_sync(1, NEPI);
+                }
+            }
+        }
+    }
+    __syncwarp();
+    tc_fence_before();
+    __syncthreads();
+    if (warp == W_ISSUE) tmem_dealloc<512>(sm.tmem_base);
+}
+
 }  // namespace pnb
 
 using namespace pnb;
@@ -1803,7 +2112,7 @@ extern "C" int pnb_mlp_pack(const pnb_mlp_t* mlp, void* d_out, size_t out_bytes,
 }
 
 extern "C" size_t pnb_shade_tc_bytes(int max_valid_samples) {
-    return align_up((size_t)max_valid_samples * 256 * sizeof(float)) + align_up((size_t)max_valid_samples * sizeof(float)) + 256;
+    return align_up(((size_t)max_valid_samples + 127) / 128 * 128 * 256 * sizeof(float)) + align_up((size_t)max_valid_samples * sizeof(float)) + 256;
 }
 
 // Tensor-core forward: per-pair MLPs on tcgen05 (BF16x3), colour branch on CUDA cores.  ws: >= pnb_shade_tc_bytes.
@@ -1819,9 +2128,10 @@ extern "C" int pnb_shade_forward_tc(const pnb_query_t* q, const pnb_points_t* pt
     // interleaved (non-swizzled) operand layout: 128-byte alignment of the carve-out is sufficient
     constexpr size_t kSmemMax = 232448;   // 227 KB opt-in limit per block on sm_100
     const size_t smem_tc = sizeof(tc::Smem) + 128, smem_tc3 = sizeof(tc3::Smem) + 128, smem_cb = sizeof(cb::Smem),
-                 smem_ctc = sizeof(ctc::Smem) + 128, smem_tc5 = sizeof(tc5::Smem) + 128, smem_tc6 = sizeof(tc6::Smem) + 128;
+                 smem_ctc = sizeof(ctc::Smem) + 128, smem_tc5 = sizeof(tc5::Smem) + 128, smem_tc6 = sizeof(tc6::Smem) + 128, smem_ctc2 = sizeof(ctc2::Smem) + 128;
     static_assert(sizeof(tc5::Smem) + 128 <= kSmemMax, "v5 shared-memory carve-out exceeds the per-block limit");
     static_assert(sizeof(tc6::Smem) + 128 <= kSmemMax, "v6 shared-memory carve-out exceeds the per-block limit");
+    static_assert(sizeof(ctc2::Smem) + 128 <= kSmemMax, "colour v2 shared-memory carve-out exceeds the per-block limit");
     static_assert((tc3::NSTAGE & (tc3::NSTAGE - 1)) == 0 && tc3::NSTAGE == 4, "issuer assumes a 4-stage ring");
     static_assert(sizeof(tc::Smem) + 128 <= kSmemMax && sizeof(tc3::Smem) + 128 <= kSmemMax && sizeof(ctc::Smem) + 128 <= kSmemMax &&
                   sizeof(cb::Smem) <= kSmemMax, "shared-memory carve-out exceeds the sm_100 per-block limit");
@@ -1831,6 +2141,7 @@ extern "C" int pnb_shade_forward_tc(const pnb_query_t* q, const pnb_points_t* pt
         PNB_CHECK_CUDA(cudaFuncSetAttribute(k_shade_tc5, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tc5));
         PNB_CHECK_CUDA(cudaFuncSetAttribute(k_shade_tc6, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tc6));
         PNB_CHECK_CUDA(cudaFuncSetAttribute(k_color_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_ctc));
+        PNB_CHECK_CUDA(cudaFuncSetAttribute(k_color_tc2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_ctc2));
         PNB_CHECK_CUDA(cudaFuncSetAttribute(k_color_branch, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cb));
         int dev = 0;
         PNB_CHECK_CUDA(cudaGetDevice(&dev));
@@ -1838,7 +2149,7 @@ extern "C" int pnb_shade_forward_tc(const pnb_query_t* q, const pnb_points_t* pt
         configured = 1;
     }
     Carver c(ws, ws_bytes);
-    float* hbar = c.take<float>((size_t)max_valid_samples * 256);
+    float* hbar = c.take<float>(((size_t)max_valid_samples + 127) / 128 * 128 * 256);   // whole 128-sample colour tiles
     float* sigma = c.take<float>((size_t)max_valid_samples);
     ShadeTcParams p;
     p.q = *q; p.pts = *pts; p.o = *opts; p.wimg = (const unsigned char*)d_packed;
@@ -1848,6 +2159,9 @@ extern "C" int pnb_shade_forward_tc(const pnb_query_t* q, const pnb_points_t* pt
     p.hbar = hbar; p.sigma = sigma; p.hbar_cap = max_valid_samples; p.err = d_err;
     p.dbg_no_weights = (stage_mask & 64) ? 1 : 0;
     p.dbg_flags = (stage_mask >> 8) & 0xff;
+    const bool color_v2 = (stage_mask & (1 << 16)) != 0;      // pipelined colour kernel fed by operand-format h-bar (written by the v5 / v6 pair kernels)
+    PNB_REQUIRE(!color_v2 || ((stage_mask & (128 | 32)) && (stage_mask & 8)), PNB_ERR_INVALID, "pnb_shade_forward_tc: colour v2 needs the v5 / v6 pair pipeline");
+    p.hbar_fmt = color_v2 ? 1 : 0;
     if (stage_mask & 1) {
         if (stage_mask & 128) k_shade_tc6<<<n_sm & ~1, tc6::NTHR, smem_tc6, stream>>>(p);     // v5 on CTA pairs (cta_group::2)
         else if (stage_mask & 32) k_shade_tc5<<<n_sm, tc5::NTHR, smem_tc5, stream>>>(p);           // TMEM ping-pong, chunk-pipelined
@@ -1864,7 +2178,8 @@ extern "C" int pnb_shade_forward_tc(const pnb_query_t* q, const pnb_points_t* pt
         for (int i = 0; i < 3; ++i) ct.bias[i] = mlp->b[5 + i];
         ct.w3t = mlp->w[8]; ct.b3 = mlp->b[8];
         ct.hbar = hbar; ct.sigma = sigma; ct.hbar_cap = max_valid_samples; ct.sigma_rgb = (float4*)d_sigma_rgb; ct.err = d_err;
-        k_color_tc<<<n_sm, ctc::NTHR, smem_ctc, stream>>>(ct);
+        if (color_v2) k_color_tc2<<<n_sm, ctc2::NTHR, smem_ctc2, stream>>>(ct);
+        else k_color_tc<<<n_sm, ctc::NTHR, smem_ctc, stream>>>(ct);
     } else if (stage_mask & 2) {
         k_color_branch<<<n_sm * 2, cb::NTHREADS, smem_cb, stream>>>(cp);
     }

@@ -286,14 +286,17 @@ def _init_state(mod):
     mod.precision = getattr(opt, "pnb_precision", "bf16x3")
     if mod.precision not in ("bf16x3", "fp32"):
         raise NotImplementedError("pnb200: pnb_precision=%r (bf16x3 | fp32)" % mod.precision)
-    # tcgen05 pipeline variant: 6 = v5 on CTA pairs (cluster of 2, cta_group::2 M=256 MMAs, each CTA stages half of every
-    # weight image; default), 5 = chunk-pipelined TMEM role ping-pong (epilogue of layer l under the MMAs of layer l+1),
+    # tcgen05 pipeline variant: 5 = chunk-pipelined TMEM role ping-pong (epilogue of layer l under the MMAs of layer l+1; default),
+    # 6 = the same on CTA pairs (cluster of 2, cta_group::2 M=256 MMAs, each CTA stages half of every weight image): ~12 % fewer
+    # cycles on an idle GPC, but with all TPCs active the B-half exchange saturates the intra-GPC SM-to-SM fabric,
     # 3 = A operand of layers 2-4 in tensor memory + overlapped operand builders, epilogues exposed,
     # 2 = serialized shared-memory pipeline
-    _v = int(getattr(opt, "pnb_tc_version", 6))
+    _v = int(getattr(opt, "pnb_tc_version", 5))
     if _v not in (2, 3, 5, 6):
         raise NotImplementedError("pnb200: pnb_tc_version=%r (2 | 3 | 5 | 6)" % _v)
     mod.tc_mask = 3 | (12 if _v == 3 else 0) | (8 + 32 if _v == 5 else 0) | (8 + 128 if _v == 6 else 0)
+    if _v in (5, 6) and int(getattr(opt, "pnb_color_version", 2)) == 2:
+        mod.tc_mask |= 1 << 16        # pipelined colour kernel; the pair kernel writes h-bar as its bf16 hi/lo operand blocks
     mod.last = None
     mod._pnb_ready = True
 
@@ -355,7 +358,7 @@ class NeuralPointsRayMarching(nn.Module):
             if self._tc_ws is None or self._tc_ws.numel() < nb or self._tc_ws.device != raydir.device:
                 self._tc_ws = torch.empty(nb, dtype=torch.uint8, device=raydir.device)
             if self._err is None or self._err.device != raydir.device:
-                self._err = torch.zeros(64, dtype=torch.int32, device=raydir.device)   # [0] status, [2:] cycle counters
+                self._err = torch.zeros(512, dtype=torch.int32, device=raydir.device)   # [0] status, [2:64] cycle counters, [64:] per-CTA cycles (int64)
             _lib.check(lib.pnb_shade_forward_tc(_lib.C.byref(q.desc), _lib.C.byref(pts), _lib.C.byref(mlp),
                                                 self._mlp.packed.data_ptr(), _lib.C.byref(o), self._sigma_rgb.data_ptr(),
                                                 self._tc_ws.data_ptr(), self._tc_ws.numel(), max_valid, self.tc_mask,

@@ -5,7 +5,7 @@ import torch
 from pointnerf_b200 import harness, scene
 dev = torch.device("cuda:0")
 cfg = scene.CONFIGS["lego_render"]
-net, pts, opt = harness.build_model(cfg, dev, alpha_bias=3.0, pnb_tc_version=int(os.environ.get("PNB_TC_VERSION", "6")))
+net, pts, opt = harness.build_model(cfg, dev, alpha_bias=3.0, pnb_tc_version=int(os.environ.get("PNB_TC_VERSION", "5")), pnb_color_version=int(os.environ.get("PNB_COLOR_VERSION", "2")))
 rays = scene.make_rays(cfg)
 rd = rays["raydir"].to(dev)
 for i in range(3):
@@ -13,7 +13,7 @@ for i in range(3):
         net.render_full(list(cfg.campos), rd, torch.eye(3), cfg.near, cfg.far, [1., 1., 1.])
 if os.environ.get("PNB_NO_WEIGHTS"):
     net.tc_mask |= 64
-net.tc_mask |= int(os.environ.get("PNB_DBG_FLAGS", "0")) << 8
+net.tc_mask |= (int(os.environ.get("PNB_DBG_FLAGS", "0")) | (0 if os.environ.get("PNB_NO_PROF") else 1)) << 8
 torch.cuda.synchronize()
 net._err.zero_()
 with torch.no_grad():
@@ -24,6 +24,10 @@ names = ["loader wait empty", "issuer wait a1_ready", "issuer wait at_ready", "i
          "builder busy", "epilogue wait acc_full", "epilogue busy (l<3)", "epilogue busy (l==3)", "kernel total (thread 0)", "issuer: in ring commits (v6)", "issuer: K-block issue incl. commits (v6)", "issuer: wait kblk (probe)", "issuer: wait weights (probe)", "issuer: #weight waits", "peer loader wait empty"]
 ntiles = (net.last.counters["n_valid"] if net.last.counters else 3472901) if False else None
 tot = c[9]
-print("status", int(net._err[0]), "version", os.environ.get("PNB_TC_VERSION", "6"), "no_weights", bool(os.environ.get("PNB_NO_WEIGHTS")))
+print("status", int(net._err[0]), "version", os.environ.get("PNB_TC_VERSION", "5"), "no_weights", bool(os.environ.get("PNB_NO_WEIGHTS")))
 for n, v in zip(names, c):
     print("%-28s %12d cycles  %5.1f%% of kernel" % (n, v, 100.0 * v / max(tot, 1)))
+
+if int(os.environ.get("PNB_DBG_FLAGS", "0")) & 4:
+    per = net._err.cpu().view(torch.int64)[32:32 + 148].tolist()
+    print("per-CTA kernel cycles (M) @smid:", " ".join("%.1f@%d" % ((v & 0xffffffffffff) / 1e6, v >> 48) for v in per))

@@ -1265,14 +1265,22 @@ __global__ void __launch_bounds__(tc5::NTHR, 1) k_shade_tc5(ShadeTcParams p) {
 }
 
 // =====================================================================================================================
-// v6: v5 on a CTA PAIR (cluster of 2, tcgen05 cta_group::2).  Each CTA of the pair owns one 128-row tile (its own
-// builders, epilogue warps, TMEM regions P/Q and layer-1 operand buffer); the rank-0 CTA's issuer warp issues ONE
-// M=256 MMA for both tiles.  The B operand (weight image [256 x 32]) is split by N between the two CTAs: each loader
-// streams only its 8 KB half, the tensor cores read the other half from the peer's shared memory -> half the L2->SMEM
-// weight traffic and half the B reads per SM, and an 8-deep ring in the same 64 KB.
+// v6 (opt-in, pnb_tc_version=6): v5 on a CTA PAIR (cluster of 2, tcgen05 cta_group::2).  Each CTA of the pair owns one 128-row
+// tile (its own builders, epilogue warps, TMEM regions P/Q and layer-1 operand buffer); the rank-0 CTA's issuer warp issues
+// ONE M=256 MMA for both tiles.  The B operand (weight image [256 x 32]) is split by N between the two CTAs: each loader
+// streams only its 8 KB half of every image (half the L2->SMEM weight traffic), a ring stage is a whole K block (hi + lo half
+// images, 16 KB) so ONE tcgen05.commit per K block frees it (a commit costs ~140 tensor-pipe cycles), and the tensor cores
+// read the other half of B from the peer's shared memory.
 // Cross-CTA signalling: commits are multicast to the barrier of both CTAs (ring "empty", accumulator-full, operand-free);
-// the peer's builders / epilogue warps arrive remotely on the leader's a1_ready / kblk / drain barriers; the peer's
-// "weight half landed" is forwarded to the leader's full barrier (count 2) by a forwarder thread.
+// the peer's builders / epilogue warps arrive remotely on the leader's a1_ready / kblk / drain barriers (default .release.cta
+// semantics: an explicit .release.cluster compiles to MEMBAR.ALL.GPU per arrive); the peer's "weight half landed" is
+// forwarded to the leader's full barrier (count 2) by a forwarder thread.  Two builder threads per row; the last epilogue
+// of a tile is shared by the epilogue and the builder warps (both idle under layer 1 of the next tile).
+// Measured (B200, lego frame): a pair alone runs 34.5 k cycles per tile against 38.4 k for v5, but every MMA pulls 4 KB of B
+// from the peer SM, and with all 74 pairs active that exchange saturates the intra-GPC SM-to-SM fabric (~20 B/clk/SM): TPCs
+// settle at 34.5 k / 38 k / 41.5 k cycles per tile depending on their position in the GPC, and the statically partitioned
+// kernel is as slow as its slowest pair -> 3 % slower than v5 end to end.  Kept for the numbers and as the base of a
+// future mixed / dynamically scheduled variant.
 namespace tc6 {
 constexpr int NEPI_WARPS = 8, NGRP = NEPI_WARPS / 4, NCH = 16 / NGRP;
 constexpr int NEPI = NEPI_WARPS * 32, NBUILD = 256, NTHR = NEPI + NBUILD + 96;   // two builder threads per row; + loader, issuer, forwarder warps

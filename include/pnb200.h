@@ -182,14 +182,19 @@ size_t pnb_mlp_pack_bytes(void);
 int pnb_mlp_pack(const pnb_mlp_t* mlp, void* d_out, size_t out_bytes, pnb_stream_t stream);
 /* Same contract as pnb_shade_forward; per-pair MLPs run as tcgen05.mma tiles, colour branch on CUDA cores.
  * mlp->w[5] must be zero padded to 288 rows.  ws >= pnb_shade_tc_bytes(max_valid_samples).  d_err: device int32,
- * 0 on success, 9 if the query produced more valid samples than max_valid_samples, 1..5 on an internal pipeline
- * time-out (results invalid in both cases). */
+ * 0 on success, 9 if the query produced more valid samples than max_valid_samples, any other non-zero value = an internal
+ * pipeline time-out (a bounded 2-s mbarrier wait expired; results invalid in both cases).  >= 64 ints. */
 size_t pnb_shade_tc_bytes(int max_valid_samples);
 int pnb_shade_forward_tc(const pnb_query_t* q, const pnb_points_t* pts, const pnb_mlp_t* mlp, const void* d_packed,
                          const pnb_shade_opts_t* opts, float* d_sigma_rgb, void* ws, size_t ws_bytes,
                          int max_valid_samples,
-                         int stage_mask /* 1 pair MLPs, 2 colour branch, +4 TS-form pair pipeline (v3), +8 colour branch on tcgen05,
-                                           +32 chunk-pipelined TMEM ping-pong pair pipeline (v5) */,
+                         int stage_mask /* 1 pair MLPs, 2 colour branch (both = a forward); variant bits: +4 TS-form pair
+                                           pipeline (v3), +32 chunk-pipelined TMEM role ping-pong (v5), +128 the same on CTA
+                                           pairs / cta_group::2 (v6); +8 colour branch on tcgen05, +65536 pipelined colour
+                                           kernel fed by operand-format h-bar (needs +32 or +128 and +8); diagnostics:
+                                           +64 no weight traffic (garbage results), bits 8..15 = profiling / experiment
+                                           flags of tools/tc_profile.py (256: cycle accounting of block 0 into d_err[2..],
+                                           1024: per-CTA cycles into d_err[64..], needs a 512-int d_err) */,
                          int* d_err, pnb_stream_t stream);
 
 /* ---- backward (per-scene optimisation batches) ----

@@ -123,6 +123,18 @@ def golden_hyper():
     print("hyper", {k: v.tolist() for k, v in fx.items() if k.endswith("scaled_vdim")})
 
 
+def golden_checkpoint_layout():
+    """Key names / shapes / dtypes of the reference module's own state_dict, i.e. of the `{epoch}_net_ray_marching.pth`
+    files written by models/base_model.py:85-99 (the checkpoint wire format)."""
+    import json
+    cfg = scene.CONFIGS["tiny"]
+    net, agg, npts, pts, opt = build_reference_net(cfg, 0.0)
+    layout = {k: [list(v.shape), str(v.dtype).replace("torch.", "")] for k, v in net.state_dict().items()}
+    with open(os.path.join(OUT, "checkpoint_layout.json"), "w") as f:
+        json.dump(dict(n_points=int(pts["xyz"].shape[0]), layout=layout), f, indent=1, sort_keys=True)
+    print("checkpoint_layout:", len(layout), "tensors")
+
+
 if __name__ == "__main__":
     assert ref_shim.available(), "needs /root/reference"
     tiny = scene.CONFIGS["tiny"]
@@ -130,3 +142,4 @@ if __name__ == "__main__":
     golden_case("tiny_thin_sr8", tiny, scene.centre_patch(tiny, 40), alpha_bias=0.0, SR=8)
     golden_probe("tiny_probe", tiny, scene.centre_patch(tiny, 40), alpha_bias=4.0)
     golden_hyper()
+    golden_checkpoint_layout()

@@ -56,3 +56,39 @@ def allreduce_gradients(params, world, group=None, average=False):
         g.copy_(flat[off:off + n].view_as(g))
         off += n
     return flat.numel()
+
+
+# ---- point growing across ranks ("Grow / prune"): probe_hole (run/train_ft.py:417-530) renders whole
+# training frames -> shard FRAMES across ranks, then one variable-length all-gather (counts, then payload) of the new
+# points; every rank appends them in rank order, so the replicated point clouds stay identical without a broadcast.
+# Prune needs no communication: it is a deterministic function of the replicated points_conf.
+
+def shard_frames(frame_ids, rank, world):
+    """Frames this rank probes: round-robin over the (already shuffled / ranked) id list, as rays are."""
+    return list(frame_ids)[rank::world]
+
+
+def allgather_varlen(t, world, group=None):
+    """t: [n_rank, C] (n differs per rank).  Returns the [sum n, C] concatenation in rank order on every rank:
+    one all_gather of the counts, one of the payload padded to the largest count."""
+    if world <= 1:
+        return t
+    cnt = torch.tensor([t.shape[0]], dtype=torch.int64, device=t.device)
+    counts = torch.empty(world, dtype=torch.int64, device=t.device)
+    dist.all_gather_into_tensor(counts, cnt, group=group)
+    counts = counts.tolist()
+    m = max(counts)
+    if m == 0:
+        return t
+    buf = torch.empty((world, m) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+    dist.all_gather_into_tensor(buf.view(world * m, *t.shape[1:]), pad_rows(t.contiguous(), m), group=group)
+    return torch.cat([buf[g, :counts[g]] for g in range(world)], dim=0)
+
+
+def allgather_new_points(add_xyz, add_embedding, add_color, add_dir, add_conf, world, group=None):
+    """The five tensors probe_hole returns (train_ft.py:530), gathered as ONE payload [n, 3+C+3+3+1] so that a rank
+    cannot interleave them differently; returns them split again, identical on every rank."""
+    c = add_embedding.shape[1]
+    packed = torch.cat([add_xyz, add_embedding, add_color, add_dir, add_conf], dim=1)
+    allp = allgather_varlen(packed, world, group=group)
+    return allp[:, 0:3], allp[:, 3:3 + c], allp[:, 3 + c:6 + c], allp[:, 6 + c:9 + c], allp[:, 9 + c:10 + c]

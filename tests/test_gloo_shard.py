@@ -35,7 +35,19 @@ def _worker(rank, world, port, R, ret):
         n = parallel.allreduce_gradients([w], world)
         ref = feats.sum(0)[:, None].expand(5, 3)
         ok_grad = torch.allclose(w.grad, ref, rtol=1e-6, atol=1e-6) and n == 15
-        ret[rank] = (ok_gather, ok_grad)
+        # point growing: each rank probed its own frames and found a different number of new points
+        assert parallel.shard_frames(list(range(7)), rank, world) == ([0, 2, 4, 6] if rank == 0 else [1, 3, 5])
+        n_new = [3, 0] if R == 10 else [2, 5]
+        gg = torch.Generator().manual_seed(100 + rank)
+        mine = [torch.rand(n_new[rank], c, generator=gg) for c in (3, 32, 3, 3, 1)]
+        got = parallel.allgather_new_points(*mine, world)
+        exp = [[], [], [], [], []]
+        for g_ in range(world):
+            g2 = torch.Generator().manual_seed(100 + g_)
+            for i, c in enumerate((3, 32, 3, 3, 1)):
+                exp[i].append(torch.rand(n_new[g_], c, generator=g2))
+        ok_grow = all(torch.equal(a, torch.cat(e, 0)) for a, e in zip(got, exp)) and got[0].shape[0] == sum(n_new)
+        ret[rank] = (ok_gather, ok_grad and ok_grow)
     finally:
         dist.destroy_process_group()
 
@@ -54,3 +66,5 @@ def test_single_process_paths():
     assert torch.equal(parallel.gather_interleaved(full, 7, 1), full)
     assert parallel.shard_indices(7, 1, 3).tolist() == [1, 4]
     assert parallel.padded_shard_len(7, 3) == 3
+    t = torch.rand(4, 5)
+    assert parallel.allgather_varlen(t, 1) is t

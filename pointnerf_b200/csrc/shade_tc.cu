@@ -423,6 +423,7 @@ constexpr int NEPI_WARPS = 16, NEPI = NEPI_WARPS * 32, NBUILD = 128, NTHR = NEPI
 constexpr int NSTAGE = 4;
 constexpr int XE = 128 * 32;            // bytes of one [128 x 16] bf16 extras operand (SBO = 256)
 struct Smem {
+    static constexpr int NWC = 2;
     unsigned char a_hi[tc::NKB_MAX * tc::ABLK];
     unsigned char a_lo[tc::NKB_MAX * tc::ABLK];
     unsigned char b[NSTAGE][tc::IMG];
@@ -501,7 +502,7 @@ __device__ __forceinline__ void build_pair_part(SmemT& sm, const ShadeTcParams& 
         wsum += __shfl_xor_sync(0xffffffffu, wsum, 4);
         w = w / fmaxf(wsum, 1e-8f);
         float cf = __ldg(&p.pts.conf[pi]);
-        sm.wc[t & 1][row] = valid ? w * fminf(fmaxf(cf, 1e-4f), 1.0f) : 0.f;
+        sm.wc[t % SmemT::NWC][row] = valid ? w * fminf(fmaxf(cf, 1e-4f), 1.0f) : 0.f;
         float d0, d1, d2;
         rot3t(p.o.Rw2c, dist[0], dist[1], dist[2], d0, d1, d2);
         dist[0] = d0; dist[1] = d1; dist[2] = d2;
@@ -1046,12 +1047,14 @@ constexpr int NEPI_WARPS = 8, NGRP = NEPI_WARPS / 4, NCH = 16 / NGRP;   // chunk
 constexpr int NEPI = NEPI_WARPS * 32, NBUILD = 128, NTHR = NEPI + NBUILD + 64;
 constexpr int NSTAGE = 4;
 struct Smem {
+    static constexpr int NWC = 3;          // weight*conf of tile t is read by the last epilogue under layer 1 of tile t+1, while the
+                                           // builders already write tile t+2: three buffers make that ordering formal (through bar_drain)
     unsigned char a_hi[tc::NKB_MAX * tc::ABLK];
     unsigned char a_lo[tc::NKB_MAX * tc::ABLK];
     unsigned char b[NSTAGE][tc::IMG];
     unsigned char xe_hi[2][tc3::XE];
     unsigned char xe_lo[2][tc3::XE];
-    float wc[2][tc::TM];
+    float wc[NWC][tc::TM];
     float alpha_part[2][tc::TM];
     uint64_t bar_full[NSTAGE], bar_empty[NSTAGE], bar_a1_ready, bar_a1_free, bar_acc_full, bar_drain, bar_kblk[8];   // bar_kblk[kb]: columns 32kb..32kb+31 converted
     uint32_t tmem_base;
@@ -1227,7 +1230,7 @@ __global__ void __launch_bounds__(tc5::NTHR, 1) k_shade_tc5(ShadeTcParams p) {
                     }
                     if (tid == 0) prof_add(p, 7, clock64() - _te0);
                 } else {
-                    const float wrow = sm.wc[t & 1][erow];
+                    const float wrow = sm.wc[t % tc5::Smem::NWC][erow];
                     const int sidx = tile * TSAMP + (erow >> 3);
                     const bool swrite = sidx < n_valid;
                     const int j8 = lane & 7;
@@ -1289,6 +1292,7 @@ constexpr int CPK = 1;                   // K blocks per ring commit (a tcgen05.
                                          // and was measured slower: the 4-stage ring then starves)
 constexpr int HIMG = tc::IMG / 2;       // bytes of one half image ([128 x 32] bf16)
 struct Smem {
+    static constexpr int NWC = 2;          // reuse ordered through bar_alpha (the builders themselves run the last epilogue)
     unsigned char a_hi[tc::NKB_MAX * tc::ABLK];
     unsigned char a_lo[tc::NKB_MAX * tc::ABLK];
     unsigned char b[NSTAGE][2][HIMG];

@@ -14,10 +14,11 @@ DEV = "cuda:0"
 
 def test_whole_image_equals_reference_chunk_loop():
     """render_vid.py:45-71 renders `random_sample_size**2`-ray chunks and assembles them on the host; one whole-image call
-    must give the same pixels bit for bit (48x48 = 2304 rays, the shipped chunk; 200x120 centre crop of the lego view)."""
+    must give the same pixels bit for bit (48x48 = 2304 rays, the shipped chunk; a 640x96 strip through the lego view's centre:
+    hits and misses)."""
     cfg = scene.CONFIGS["lego_render"]
     net, pts, opt = harness.build_model(cfg, DEV, alpha_bias=3.0)
-    W, H = 200, 120
+    W, H = 640, 96
     x0, y0 = cfg.W // 2 - W // 2, cfg.H // 2 - H // 2
     px, py = np.meshgrid(np.arange(x0, x0 + W), np.arange(y0, y0 + H))
     rays = scene.make_rays(cfg, np.stack((px, py), -1).reshape(-1, 2).astype(np.float32))
@@ -27,7 +28,8 @@ def test_whole_image_equals_reference_chunk_loop():
     assert whole["coarse_raycolor"].shape == (H, W, 3) and whole["ray_mask"].shape == (H, W)
     assert np.array_equal(whole["coarse_raycolor"].cpu().numpy(), chunked["coarse_raycolor"])
     hit = whole["ray_mask"] > 0
-    assert 0.2 < hit.float().mean().item() < 1.0
+    frac = hit.float().mean().item()
+    assert 0.2 < frac < 0.98, frac
     assert torch.all(whole["coarse_raycolor"][~hit] == 1.0) and torch.all(whole["coarse_point_opacity"][~hit] == 0)
     net.check_errors()
 

@@ -196,8 +196,8 @@ def main():
     ap.add_argument("--sr", type=int, default=24)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--precision", type=str, default="bf16x3", help="bf16x3 (tcgen05, default) | fp32 (CUDA cores)")
-    ap.add_argument("--color-version", type=int, default=2, help="colour kernel: 2 (pipelined, operand-format h-bar; default, needs --tc-version 5 or 6) | 1")
-    ap.add_argument("--tc-version", type=int, default=5, help="tcgen05 pipeline variant: 5 (TMEM role ping-pong; default) | 6 (the same on CTA pairs, cta_group::2) | 3 | 2")
+    ap.add_argument("--color-version", type=int, default=2, help="colour kernel: 2 (pipelined, operand-format h-bar; default, needs --tc-version 5, 6 or 7) | 1")
+    ap.add_argument("--tc-version", type=int, default=7, help="tcgen05 pipeline variant: 7 (TMEM role ping-pong, rows packed to the valid pairs; default) | 5 (8 rows per sample) | 6 (v5 on CTA pairs, cta_group::2) | 3 | 2")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
@@ -317,9 +317,9 @@ def main():
             _lib.check(l.pnb_shade_forward_tc(_lib.C.byref(q.desc), _lib.C.byref(ptsd), _lib.C.byref(mlp), net._mlp.packed.data_ptr(),
                                               _lib.C.byref(o), net._sigma_rgb.data_ptr(), net._tc_ws.data_ptr(), net._tc_ws.numel(),
                                               net._max_valid, mask, net._err.data_ptr(), stream), "pnb_shade_forward_tc")
-        shade_avg = time_kernel(lambda: tc(1 | (net.tc_mask & (180 | 8 | (1 << 16)))))
-        color_avg = time_kernel(lambda: tc(2 | (net.tc_mask & (8 | 32 | 128 | (1 << 16)))))
-        kname = ("k_shade_tc6" if net.tc_mask & 128 else "k_shade_tc5" if net.tc_mask & 32 else "k_shade_tc3" if net.tc_mask & 4 else "k_shade_tc") + " (tcgen05 BF16x3 pair MLPs 284-256-256 | 263-256-256 + alpha + K-reduction)"
+        shade_avg = time_kernel(lambda: tc(1 | (net.tc_mask & (180 | 8 | (1 << 16) | (1 << 17)))))
+        color_avg = time_kernel(lambda: tc(2 | (net.tc_mask & (8 | 32 | 128 | (1 << 16) | (1 << 17)))))
+        kname = ("k_shade_tc7" if net.tc_mask & (1 << 17) else "k_shade_tc6" if net.tc_mask & 128 else "k_shade_tc5" if net.tc_mask & 32 else "k_shade_tc3" if net.tc_mask & 4 else "k_shade_tc") + " (tcgen05 BF16x3 pair MLPs 284-256-256 | 263-256-256 + alpha + K-reduction)"
         kflops = FLOPS_PER_PAIR * qc["n_pairs"]
         net.check_errors()
 
@@ -335,7 +335,7 @@ def main():
     traffic = None
     tfile = os.path.join(ROOT, "profiles", "r01_ncu_dram_traffic.json")
     if os.path.exists(tfile) and args.precision != "fp32" and world == 1 and args.sr == 24:
-        traffic = json.load(open(tfile)).get("k_shade_tc6" if net.tc_mask & 128 else "k_shade_tc5" if net.tc_mask & 32 else "k_shade_tc3" if net.tc_mask & 4 else "", None)
+        traffic = json.load(open(tfile)).get("k_shade_tc7" if net.tc_mask & (1 << 17) else "k_shade_tc6" if net.tc_mask & 128 else "k_shade_tc5" if net.tc_mask & 32 else "k_shade_tc3" if net.tc_mask & 4 else "", None)
     flops = kflops
     achieved = flops / (shade_avg * 1e-3) / 1e12
     peak = pk["bf16_tflops"]

@@ -68,6 +68,9 @@ struct ShadeTcParams {
     int* err;
     int dbg_no_weights;          // timing experiment only: the loader signals the ring without copying (results are garbage)
     int dbg_flags;               // bit 1: v6 issuer classifies its waits with non-blocking probes (profiling)
+    const unsigned char* vcnt;   // v7 row packing: neighbours per valid sample [n_valid]
+    const uint32_t* quad_first;  // v7: first valid sample of every 32-row quadrant [n_quads + 1]
+    const int* pack_cnt;         // v7: [0] = n_quads
     int hbar_fmt;                // 0: hbar[n_valid][256] fp32;  1: bf16 hi/lo A-operand blocks of k_color_tc2 (per 128 samples: 8 K blocks x {hi,lo} x [128x32])
 };
 __device__ __forceinline__ void prof_add(const ShadeTcParams& p, int slot, long long cyc) {
@@ -460,17 +463,35 @@ __device__ __forceinline__ void store_chunk8_a1(SmemT& sm, int r, int kb, int k8
 // PART 0 / 1: the two halves of a row for the v6 pipeline (two builder threads per row):
 //   part 0 = operand columns 0..151   (raw features, PE of features 0..19)
 //   part 1 = operand columns 152..287 (PE of features 20..31, PE of the 6 distances), extras operand, weight*conf
-template <int PART, class SmemT>
-__device__ __forceinline__ void build_pair_part(SmemT& sm, const ShadeTcParams& p, int tile, int t, int row, int n_valid) {
+// Sum of v over the lanes st .. st+cnt-1 of the warp (cnt <= 8; every lane calls it, lanes outside any segment pass st = lane,
+// cnt = 1).  The order of the additions depends on cnt only, not on where the segment sits in the warp.
+__device__ __forceinline__ float seg_scan8(float v, int lane, int st) {          // inclusive scan within the segment
+#pragma unroll
+    for (int d = 1; d <= 4; d <<= 1) {
+        const float tv = __shfl_up_sync(0xffffffffu, v, d);
+        if (lane - d >= st) v += tv;
+    }
+    return v;
+}
+__device__ __forceinline__ float seg_sum8(float v, int lane, int st, int cnt) {
+    return __shfl_sync(0xffffffffu, seg_scan8(v, lane, st), st + cnt - 1);
+}
+
+// PACKED = false: row = 8 * (sample in tile) + neighbour slot, 16 samples per tile (rows of empty slots are zero).
+// PACKED = true (v7): the caller has packed only the valid (sample, neighbour) pairs into the rows: row `row` is neighbour `pk` of
+// valid sample `pvi` (pvi < 0: unused row), and the rows of that sample are lanes pst .. pst+pcnt-1 of this warp.
+template <int PART, bool PACKED = false, class SmemT>
+__device__ __forceinline__ void build_pair_part(SmemT& sm, const ShadeTcParams& p, int tile, int t, int row, int n_valid, int pvi = -1,
+                                                int pk = 0, int pst = 0, int pcnt = 1) {
     using namespace tc;
     constexpr bool P0 = PART != 1, P1 = PART != 0;
     constexpr int G_LO = P0 ? 0 : 5, G_HI = P1 ? 8 : 5;      // feature groups (4 features each) whose PE this part builds
     const pnb_query_t& q = p.q;
-    const int si = row >> 3, k = row & 7;
-    const int vi = tile * TSAMP + si;
+    const int k = PACKED ? pk : (row & 7);
+    const int vi = PACKED ? pvi : tile * TSAMP + (row >> 3);
     int pidx = -1;
     float lx = 0.f, ly = 0.f, lz = 0.f, vx = 0.f, vy = 0.f, vz = 0.f;
-    if (vi < n_valid) {
+    if (vi >= 0 && vi < n_valid) {
         uint32_t s = q.valid_list[vi];
         if (P1) {
             uint32_t pk = q.samp_ray[s];
@@ -496,10 +517,14 @@ __device__ __forceinline__ void build_pair_part(SmemT& sm, const ShadeTcParams& 
         dist[3] = xpp * zpp - xsp * zsp; dist[4] = ypp * zpp - ysp * zsp; dist[5] = zpp - zsp;
         float nrm = sqrtf(dist[0] * dist[0] + dist[1] * dist[1] + dist[2] * dist[2]);
         float w = valid ? 1.0f / fmaxf(nrm, 1e-6f) : 0.f;
-        float wsum = w;                        // 8 consecutive lanes = the 8 rows of one sample
-        wsum += __shfl_xor_sync(0xffffffffu, wsum, 1);
-        wsum += __shfl_xor_sync(0xffffffffu, wsum, 2);
-        wsum += __shfl_xor_sync(0xffffffffu, wsum, 4);
+        float wsum = w;
+        if (PACKED) {
+            wsum = seg_sum8(w, row & 31, pst, pcnt);
+        } else {                               // 8 consecutive lanes = the 8 rows of one sample
+            wsum += __shfl_xor_sync(0xffffffffu, wsum, 1);
+            wsum += __shfl_xor_sync(0xffffffffu, wsum, 2);
+            wsum += __shfl_xor_sync(0xffffffffu, wsum, 4);
+        }
         w = w / fmaxf(wsum, 1e-8f);
         float cf = __ldg(&p.pts.conf[pi]);
         sm.wc[t % SmemT::NWC][row] = valid ? w * fminf(fmaxf(cf, 1e-4f), 1.0f) : 0.f;
@@ -561,7 +586,7 @@ __device__ __forceinline__ void build_pair_part(SmemT& sm, const ShadeTcParams& 
 }
 template <class SmemT>
 __device__ __forceinline__ void build_pair_row(SmemT& sm, const ShadeTcParams& p, int tile, int t, int row, int n_valid) {
-    build_pair_part<2>(sm, p, tile, t, row, n_valid);
+    build_pair_part<2, false>(sm, p, tile, t, row, n_valid);
 }
 
 __global__ void __launch_bounds__(tc3::NTHR, 1) k_shade_tc3(ShadeTcParams p) {
@@ -1268,6 +1293,382 @@ __global__ void __launch_bounds__(tc5::NTHR, 1) k_shade_tc5(ShadeTcParams p) {
 }
 
 // =====================================================================================================================
+// v7: v5 with PACKED ROWS.  v5 gives every valid sample 8 rows (one per neighbour slot) although only 75 % of the slots
+// hold a neighbour on the lego frame (P_v / (8 S_v)): a quarter of every MMA multiplies zero rows.  Here a 128-row tile
+// is four 32-row quadrants (= the TMEM lane quarter of one warp), and each quadrant holds whole samples packed back to
+// back, only their valid neighbours (greedy packing in valid-sample order, k_pack_*): ~91 % of the rows carry a pair.
+// The K-reduction over the rows of a sample (1..8 consecutive lanes, never crossing a quadrant) is a segmented
+// warp-shuffle scan; its addition order depends on the neighbour count only, so a ray's colour is still independent of
+// which rays share the call.  Everything else (TMEM role ping-pong, chunk hand-off, weight ring, issuer) is v5.
+namespace tc7 {
+constexpr int NEPI_WARPS = 8, NGRP = NEPI_WARPS / 4, NCH = 16 / NGRP;
+constexpr int NEPI = NEPI_WARPS * 32, NBUILD = 256, NTHR = NEPI + NBUILD + 64;     // two builder threads per row (as v6)
+constexpr int NSTAGE = 4;
+constexpr int PACK_S = 512;             // samples per independently packed super-chunk (its last quadrant may stay partly empty)
+struct Smem {
+    static constexpr int NWC = 2;          // reuse ordered through bar_alpha: the builders run their share of the last epilogue
+    unsigned char a_hi[tc::NKB_MAX * tc::ABLK];
+    unsigned char a_lo[tc::NKB_MAX * tc::ABLK];
+    unsigned char b[NSTAGE][tc::IMG];
+    unsigned char xe_hi[2][tc3::XE];
+    unsigned char xe_lo[2][tc3::XE];
+    float wc[NWC][tc::TM];
+    float alpha_part[2][tc::TM];         // builder groups' partial alpha dot products
+    float alpha_e[tc::TM];               // sum of the two epilogue groups' partials (two addends onto 0: order-independent)
+    uint32_t qhead[NWC][4], qfirst[NWC][4], qtotal[NWC][4];   // per quadrant: bit r = row r starts a sample; first valid-sample index; rows used
+    uint64_t bar_full[NSTAGE], bar_empty[NSTAGE], bar_a1_ready, bar_a1_free, bar_acc_full, bar_final, bar_alpha, bar_drain, bar_kblk[8];
+    uint32_t tmem_base;
+};
+}  // namespace tc7
+
+// ---- row packing (runs before k_shade_tc7; all sizes come from device counters)
+__global__ void __launch_bounds__(256) k_pack_cnt(pnb_query_t q, int cap, unsigned char* __restrict__ vcnt) {
+    const int vi = blockIdx.x * blockDim.x + threadIdx.x;
+    const int n_valid = min(q.counters[PNB_QC_N_VALID], cap);
+    if (vi < n_valid) vcnt[vi] = q.samp_nvalid[q.valid_list[vi]];
+}
+// one thread per super-chunk: greedy packing of its samples into 32-row quadrants.  WRITE = false: count them.
+template <bool WRITE>
+__global__ void __launch_bounds__(128) k_pack_quads(pnb_query_t q, int cap, const unsigned char* __restrict__ vcnt,
+                                                    uint32_t* __restrict__ sc_quads, uint32_t* __restrict__ quad_first) {
+    const int sc = blockIdx.x * blockDim.x + threadIdx.x;
+    const int n_valid = min(q.counters[PNB_QC_N_VALID], cap);
+    const int i0 = sc * tc7::PACK_S;
+    if (i0 >= n_valid) return;
+    const int i1 = min(i0 + tc7::PACK_S, n_valid);
+    uint32_t nq = WRITE ? sc_quads[sc] : 0u;      // WRITE: sc_quads holds the exclusive prefix = first quadrant of this super-chunk
+    int rows = 0;
+    for (int i = i0; i < i1; i += 16) {
+        const uint4 pk = *reinterpret_cast<const uint4*>(vcnt + i);      // 16 counts (the buffer is padded to a multiple of 16)
+        const uint32_t w[4] = {pk.x, pk.y, pk.z, pk.w};
+#pragma unroll
+        for (int e = 0; e < 16; ++e) {
+            if (i + e < i1) {
+                const int c = (int)((w[e >> 2] >> (8 * (e & 3))) & 0xffu);
+                if (rows + c > 32) { ++nq; rows = 0; }
+                if (WRITE && rows == 0) quad_first[nq] = (uint32_t)(i + e);
+                rows += c;
+            }
+        }
+    }
+    if (rows > 0) ++nq;
+    if (!WRITE) sc_quads[sc] = nq;
+}
+// exclusive scan of the per-super-chunk quadrant counts (one block), total -> pack_cnt[0], sentinel quad_first[n_quads] = n_valid
+__global__ void __launch_bounds__(1024) k_pack_scan(pnb_query_t q, int cap, uint32_t* __restrict__ sc_quads, uint32_t* __restrict__ quad_first,
+                                                    int* __restrict__ pack_cnt) {
+    __shared__ uint32_t part[1024];
+    const int n_valid = min(q.counters[PNB_QC_N_VALID], cap);
+    const int n_sc = (n_valid + tc7::PACK_S - 1) / tc7::PACK_S;
+    const int per = (n_sc + 1023) / 1024;
+    const int b0 = threadIdx.x * per, b1 = min(b0 + per, n_sc);
+    uint32_t sum = 0;
+    for (int i = b0; i < b1; ++i) sum += sc_quads[i];
+    part[threadIdx.x] = sum;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t run = 0;
+        for (int i = 0; i < 1024; ++i) { const uint32_t v = part[i]; part[i] = run; run += v; }
+        pack_cnt[0] = (int)run;
+        quad_first[run] = (uint32_t)n_valid;
+    }
+    __syncthreads();
+    uint32_t run = part[threadIdx.x];
+    for (int i = b0; i < b1; ++i) { const uint32_t v = sc_quads[i]; sc_quads[i] = run; run += v; }
+}
+
+// Last epilogue with packed rows, one warp's share (chunks G, G+NG, ...): +bias, LeakyReLU, partial alpha dot product (returned),
+// weight*conf scaling, then the K-reduction over the rows of each sample as a segmented inclusive scan (segments = samples,
+// <= 8 lanes, first lane st); the last row of a sample (swrite) holds the sums and writes h-bar.
+template <int NG, int NCHUNK>
+__device__ __forceinline__ float last_chunks_packed(const ShadeTcParams& p, uint32_t accb, int G, float wrow, int st, bool swrite, int sidx, int lane) {
+    using namespace tc;
+    const float* bias = p.bias[3];
+    float apart = 0.f;
+#pragma unroll
+    for (int i = 0; i < NCHUNK; ++i) {
+        const int c0 = 16 * (G + NG * i);
+        uint32_t v[16];
+        tmem_ld16(accb + (uint32_t)c0, v);
+        tmem_ld_wait();
+        float z[16];
+#pragma unroll
+        for (int e4 = 0; e4 < 4; ++e4) {
+            const float4 bb = __ldg(reinterpret_cast<const float4*>(bias + c0) + e4), ww = __ldg(reinterpret_cast<const float4*>(p.wa + c0) + e4);
+            const float bq[4] = {bb.x, bb.y, bb.z, bb.w}, wq[4] = {ww.x, ww.y, ww.z, ww.w};
+#pragma unroll
+            for (int e1 = 0; e1 < 4; ++e1) {
+                const int e = 4 * e4 + e1;
+                float y = __uint_as_float(v[e]) + bq[e1];
+                y = fmaxf(y, LEAKY * y);
+                apart = fmaf(y, wq[e1], apart);
+                z[e] = y * wrow;
+            }
+        }
+#pragma unroll
+        for (int e = 0; e < 16; ++e) z[e] = seg_scan8(z[e], lane, st);
+        if (swrite) {
+            if (p.hbar_fmt) {       // the colour kernel's operand image (bf16 hi / lo, core-matrix layout): two 16-byte rows each
+                uint32_t hh[8], ll[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) split_bf16x2(z[2 * e], z[2 * e + 1], hh[e], ll[e]);
+                unsigned char* dst = reinterpret_cast<unsigned char*>(p.hbar) + ((size_t)(sidx >> 7) * 8 + (c0 >> 5)) * (2 * 8192) +
+                                     tile_offset_bytes<LAYOUT_NONE>(sidx & 127, c0 & 31);
+                *reinterpret_cast<uint4*>(dst) = make_uint4(hh[0], hh[1], hh[2], hh[3]);
+                *reinterpret_cast<uint4*>(dst + 128) = make_uint4(hh[4], hh[5], hh[6], hh[7]);
+                *reinterpret_cast<uint4*>(dst + 8192) = make_uint4(ll[0], ll[1], ll[2], ll[3]);
+                *reinterpret_cast<uint4*>(dst + 8192 + 128) = make_uint4(ll[4], ll[5], ll[6], ll[7]);
+            } else {
+                float4* dst = reinterpret_cast<float4*>(p.hbar + (size_t)sidx * 256 + c0);
+                dst[0] = make_float4(z[0], z[1], z[2], z[3]);
+                dst[1] = make_float4(z[4], z[5], z[6], z[7]);
+                dst[2] = make_float4(z[8], z[9], z[10], z[11]);
+                dst[3] = make_float4(z[12], z[13], z[14], z[15]);
+            }
+        }
+    }
+    return apart;
+}
+// segment bookkeeping of one quadrant row: first row / index of its sample, whether it is the sample's last row
+struct QuadRow { int st, j; bool live, is_end; };
+__device__ __forceinline__ QuadRow quad_row(uint32_t head, int tot, int lane) {
+    QuadRow r;
+    r.live = lane < tot;
+    const uint32_t below = head & (0xffffffffu >> (31 - lane));
+    r.st = r.live ? 31 - __clz(below) : lane;
+    r.j = r.live ? __popc(below) - 1 : 0;
+    const uint32_t nxt = lane < 31 ? (head >> (lane + 1)) : 0u;
+    r.is_end = r.live && lane == (nxt ? lane + __ffs(nxt) - 1 : tot - 1);
+    return r;
+}
+
+__global__ void __launch_bounds__(tc7::NTHR, 1) k_shade_tc7(ShadeTcParams p) {
+    using namespace tc;
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    tc7::Smem& sm = *reinterpret_cast<tc7::Smem*>(smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u));
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const pnb_query_t& q = p.q;
+    const int n_valid = min(q.counters[PNB_QC_N_VALID], p.hbar_cap);
+    const int n_quads = p.pack_cnt[0];
+    const int n_tiles = (n_quads + 3) >> 2;
+    const int my_tiles = n_tiles > (int)blockIdx.x ? (n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+    constexpr int W_BUILD = tc7::NEPI_WARPS, W_LOAD = W_BUILD + tc7::NBUILD / 32, W_ISSUE = W_LOAD + 1;
+
+    if (tid == 0) {
+        for (int s = 0; s < tc7::NSTAGE; ++s) { mbar_init(&sm.bar_full[s], 1); mbar_init(&sm.bar_empty[s], 1); }
+        mbar_init(&sm.bar_a1_ready, tc7::NBUILD);
+        mbar_init(&sm.bar_a1_free, 1);
+        mbar_init(&sm.bar_acc_full, 1);
+        mbar_init(&sm.bar_final, 1);
+        mbar_init(&sm.bar_alpha, tc7::NEPI_WARPS);
+        mbar_init(&sm.bar_drain, tc7::NEPI_WARPS + tc7::NBUILD / 32);     // one arrive per warp that reads the layer-4 accumulator
+        for (int c = 0; c < 8; ++c) mbar_init(&sm.bar_kblk[c], 32 * 4 * 2);
+        mbar_fence_init();
+        if (blockIdx.x == 0 && q.counters[PNB_QC_N_VALID] > p.hbar_cap) atomicExch(p.err, 9);
+    }
+    if (tid < TM) sm.alpha_e[tid] = 0.f;
+    if (warp == W_ISSUE) tmem_alloc<512>(&sm.tmem_base);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tP = sm.tmem_base, tQ = sm.tmem_base + 256u;
+    const long long _tk0 = clock64();
+
+    if (warp == W_LOAD) {
+        if (lane == 0) {
+            const uint32_t total = (uint32_t)my_tiles * IMGS_PER_TILE;
+            for (uint32_t n = 0; n < total; ++n) {
+                const uint32_t s = n & (tc7::NSTAGE - 1), ph = (n >> 2) & 1u;
+                if (!mbar_wait(&sm.bar_empty[s], ph ^ 1u, p.err, 91)) break;
+                if (p.dbg_no_weights) { mbar_arrive(&sm.bar_full[s]); continue; }
+                mbar_arrive_expect_tx(&sm.bar_full[s], IMG);
+                bulk_g2s(sm.b[s], p.wimg + (size_t)(n % IMGS_PER_TILE) * IMG, IMG, &sm.bar_full[s]);
+            }
+        }
+    } else if (warp == W_ISSUE) {
+        // ============================================================ MMA issuer (identical to v5)
+        const uint32_t idesc = make_idesc_bf16(128, 256);
+        const uint32_t hiw = desc_hi<LAYOUT>(), xe_hiw = (256u >> 4) | (1u << 14);
+        const uint32_t b0_lo = desc_lo<LAYOUT>(smem_u32(sm.b[0]));
+        const uint32_t ahi_lo = desc_lo<LAYOUT>(smem_u32(sm.a_hi)), alo_lo = desc_lo<LAYOUT>(smem_u32(sm.a_lo));
+        const uint32_t xeh_lo0 = desc_lo<LAYOUT_NONE>(smem_u32(sm.xe_hi[0])), xel_lo0 = desc_lo<LAYOUT_NONE>(smem_u32(sm.xe_lo[0]));
+        constexpr uint32_t KADV = kstep_adv16<LAYOUT>();
+        uint32_t n = 0, c_acc = 0, c_pack = 0;
+        bool ok = true;
+        for (int t = 0; t < my_tiles && ok; ++t) {
+            const uint32_t xeh_lo = xeh_lo0 + (uint32_t)(t & 1) * (tc3::XE >> 4), xel_lo = xel_lo0 + (uint32_t)(t & 1) * (tc3::XE >> 4);
+            for (int l = 0; l < 4 && ok; ++l) {
+                const uint32_t acc = (l & 1) ? tP : tQ;
+                const uint32_t ab = (l & 1) ? tQ : tP;
+                if (l > 0) { if (!mbar_wait(&sm.bar_acc_full, c_acc & 1u, p.err, 92)) { ok = false; break; } ++c_acc; }
+                else if (t > 0) { if (!mbar_wait(&sm.bar_final, (uint32_t)(t - 1) & 1u, p.err, 92)) { ok = false; break; } }
+                if (l == 0) { if (!mbar_wait(&sm.bar_a1_ready, (uint32_t)t & 1u, p.err, 93)) { ok = false; break; } }
+                if (l == 1 && t > 0) { if (!mbar_wait(&sm.bar_drain, (uint32_t)(t - 1) & 1u, p.err, 94)) { ok = false; break; } }
+                tc_fence_after();
+                const int nkb = nkb_of(l);
+                for (int kb = 0; kb < nkb && ok; ++kb) {
+                    const uint32_t s0 = n & (tc7::NSTAGE - 1), ph0 = (n >> 2) & 1u;
+                    const uint32_t s1 = (n + 1) & (tc7::NSTAGE - 1), ph1 = ((n + 1) >> 2) & 1u;
+                    const bool need_chunks = (l >= 1 && kb < 8);
+                    uint64_t* cb0 = need_chunks ? &sm.bar_kblk[kb] : &sm.bar_full[s0];
+                    const uint32_t cp0 = need_chunks ? (c_pack & 1u) : ph0;
+                    if (!mbar_try_wait4(&sm.bar_full[s0], ph0, &sm.bar_full[s1], ph1, cb0, cp0, &sm.bar_full[s1], ph1)) {
+                        if (need_chunks && !mbar_wait(cb0, cp0, p.err, 95)) { ok = false; break; }
+                        if (!mbar_wait(&sm.bar_full[s0], ph0, p.err, 96)) { ok = false; break; }
+                        if (!mbar_wait(&sm.bar_full[s1], ph1, p.err, 96)) { ok = false; break; }
+                    }
+                    tc_fence_after();
+                    const uint32_t akb_hi = ahi_lo + (uint32_t)kb * (ABLK >> 4), akb_lo = alo_lo + (uint32_t)kb * (ABLK >> 4);
+                    const uint32_t tcol = ab + (uint32_t)(kb * 32);
+                    const uint32_t bl = b0_lo + s0 * (IMG >> 4), bl2 = b0_lo + s1 * (IMG >> 4);
+                    if (l == 0) {
+                        mma_ss2_w(acc, akb_hi, hiw, bl, hiw, idesc, kb ? 1u : 0u);
+                        mma_ss2_w(acc, akb_lo, hiw, bl, hiw, idesc, 1u);
+                        mma_ss2_w(acc, akb_hi + KADV, hiw, bl + KADV, hiw, idesc, 1u);
+                        mma_ss2_w(acc, akb_lo + KADV, hiw, bl + KADV, hiw, idesc, 1u);
+                        mma_commit_w(&sm.bar_empty[s0]);
+                        mma_ss2_w(acc, akb_hi, hiw, bl2, hiw, idesc, 1u);
+                        mma_ss2_w(acc, akb_hi + KADV, hiw, bl2 + KADV, hiw, idesc, 1u);
+                        mma_commit_w(&sm.bar_empty[s1]);
+                    } else if (kb == 8) {
+                        mma_ss2_w(acc, xeh_lo, xe_hiw, bl, hiw, idesc, 1u);
+                        mma_ss2_w(acc, xel_lo, xe_hiw, bl, hiw, idesc, 1u);
+                        mma_commit_w(&sm.bar_empty[s0]);
+                        mma_ss2_w(acc, xeh_lo, xe_hiw, bl2, hiw, idesc, 1u);
+                        mma_commit_w(&sm.bar_empty[s1]);
+                    } else {
+                        mma_ts2_w(acc, tcol, bl, hiw, idesc, kb ? 1u : 0u);
+                        mma_ts2_w(acc, tcol + 8u, bl, hiw, idesc, 1u);
+                        mma_ts2_w(acc, tcol + 16u, bl + KADV, hiw, idesc, 1u);
+                        mma_ts2_w(acc, tcol + 24u, bl + KADV, hiw, idesc, 1u);
+                        mma_commit_w(&sm.bar_empty[s0]);
+                        mma_ts2_w(acc, tcol, bl2, hiw, idesc, 1u);
+                        mma_ts2_w(acc, tcol + 16u, bl2 + KADV, hiw, idesc, 1u);
+                        mma_commit_w(&sm.bar_empty[s1]);
+                    }
+                    n += 2;
+                }
+                if (!ok) break;
+                if (l >= 1) ++c_pack;
+                mma_commit_w(l < 3 ? &sm.bar_acc_full : &sm.bar_final);      // layers 1-3 -> epilogue warps; layer 4 -> every warp's share of the last epilogue
+                if (l == 0) mma_commit_w(&sm.bar_a1_free);
+            }
+        }
+    } else if (warp >= W_BUILD) {
+        // ============================================================ builders: two warps per quadrant (operand columns 0..151 | 152..287),
+        // lane = row; the same warps run chunk groups 2, 3 of the last epilogue of the previous tile (they are idle under layer 1)
+        const int bw = warp - W_BUILD, qw = bw & 3, part = bw >> 2, row = qw * 32 + lane;
+        const uint32_t tlane = (uint32_t)(qw * 32) << 16;
+        bool ok = true;
+        for (int t = 0; t <= my_tiles && ok; ++t) {
+            if (t < my_tiles) {
+                const int tile = (int)blockIdx.x + t * (int)gridDim.x;
+                if (t > 0 && !mbar_wait(&sm.bar_a1_free, (uint32_t)(t - 1) & 1u, p.err, 97)) { ok = false; break; }
+                const int qd = tile * 4 + qw;
+                uint32_t first = 0, nsamp = 0;
+                if (qd < n_quads) { first = p.quad_first[qd]; nsamp = p.quad_first[qd + 1] - first; }
+                const int c = lane < (int)nsamp ? (int)p.vcnt[first + lane] : 0;
+                int incl = c;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += v; }
+                const uint32_t head = __reduce_or_sync(0xffffffffu, lane < (int)nsamp ? (1u << (incl - c)) : 0u);
+                const int total = __shfl_sync(0xffffffffu, incl, 31);
+                const QuadRow qr = quad_row(head, total, lane);
+                const int cj = __shfl_sync(0xffffffffu, c, qr.j);
+                if (lane == 0 && part == 1) { sm.qhead[t & 1][qw] = head; sm.qfirst[t & 1][qw] = first; sm.qtotal[t & 1][qw] = (uint32_t)total; }
+                const int pvi = qr.live ? (int)first + qr.j : -1;
+                if (part == 0) build_pair_part<0, true>(sm, p, tile, t, row, n_valid, pvi, lane - qr.st, qr.st, qr.live ? cj : 1);
+                else build_pair_part<1, true>(sm, p, tile, t, row, n_valid, pvi, lane - qr.st, qr.st, qr.live ? cj : 1);
+                fence_proxy_async();
+                mbar_arrive(&sm.bar_a1_ready);
+            }
+            if (t > 0) {
+                const int tf = t - 1;
+                if (!mbar_wait(&sm.bar_final, (uint32_t)tf & 1u, p.err, 99)) { ok = false; break; }
+                tc_fence_after();
+                const QuadRow qr = quad_row(sm.qhead[tf & 1][qw], (int)sm.qtotal[tf & 1][qw], lane);
+                const int sidx = (int)sm.qfirst[tf & 1][qw] + qr.j;
+                const bool swrite = qr.is_end && sidx < n_valid;
+                const float wrow = sm.wc[tf & 1][row];
+                const float apart = last_chunks_packed<4, 4>(p, tP + tlane, 2 + part, wrow, qr.st, swrite, sidx, lane);
+                tc_fence_before();
+                sm.alpha_part[part][row] = apart;
+                named_bar_sync(2, tc7::NBUILD);
+                if (!mbar_wait(&sm.bar_alpha, (uint32_t)tf & 1u, p.err, 100)) { ok = false; break; }      // the epilogue warps' partial sums
+                if (part == 0) {
+                    const float a = (sm.alpha_part[0][row] + sm.alpha_part[1][row]) + sm.alpha_e[row] + __ldg(p.ba) - 1.0f;
+                    sm.alpha_e[row] = 0.f;
+                    const float sp = a > 20.f ? a : log1pf(expf(a));
+                    const float zz = seg_scan8(sp * wrow, lane, qr.st);
+                    if (swrite) p.sigma[sidx] = zz;
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&sm.bar_drain);                 // after the alpha_e reads
+                named_bar_sync(2, tc7::NBUILD);
+            }
+        }
+    } else {
+        // ============================================================ epilogue warps
+        const int quad = warp & 3, grp = warp >> 2;
+        const int erow = quad * 32 + lane;
+        const uint32_t tlane = (uint32_t)(quad * 32) << 16;
+        uint32_t n_acc = 0;
+        bool ok = true;
+        for (int t = 0; t < my_tiles && ok; ++t) {
+            for (int l = 0; l < 3 && ok; ++l, ++n_acc) {        // the layer-4 (last) epilogue is shared with the builder warps
+                if (!mbar_wait(&sm.bar_acc_full, n_acc & 1u, p.err, 98)) { ok = false; break; }
+                tc_fence_after();
+                const uint32_t accb = ((l & 1) ? tP : tQ) + tlane;
+                {
+                    const float* bias = p.bias[l];
+#pragma unroll
+                    for (int i = 0; i < tc7::NCH; ++i) {
+                        const int g = grp + tc7::NGRP * i, c0 = 16 * g;
+                        uint32_t v[16];
+                        tmem_ld16(accb + (uint32_t)c0, v);
+                        tmem_ld_wait();
+                        uint32_t hh[8], ll[8];
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) {
+                            float2 bb = __ldg(reinterpret_cast<const float2*>(bias + c0) + e);
+                            float y0 = __uint_as_float(v[2 * e]) + bb.x, y1 = __uint_as_float(v[2 * e + 1]) + bb.y;
+                            y0 = fmaxf(y0, LEAKY * y0); y1 = fmaxf(y1, LEAKY * y1);
+                            split_bf16x2(y0, y1, hh[e], ll[e]);
+                        }
+                        tmem_st8(accb + (uint32_t)c0, hh);
+                        tmem_st8(accb + (uint32_t)c0 + 8u, ll);
+                        tmem_st_wait();
+                        tc_fence_before();
+                        mbar_arrive(&sm.bar_kblk[g >> 1]);
+                    }
+                }
+            }
+            if (!ok) break;
+            {   // this warp's share of the LAST epilogue (chunk groups 0, 1; the builder warps take 2, 3)
+                if (!mbar_wait(&sm.bar_final, (uint32_t)t & 1u, p.err, 101)) { ok = false; break; }
+                tc_fence_after();
+                const QuadRow qr = quad_row(sm.qhead[t & 1][quad], (int)sm.qtotal[t & 1][quad], lane);
+                const int sidx = (int)sm.qfirst[t & 1][quad] + qr.j;
+                const float apart = last_chunks_packed<4, 4>(p, tP + tlane, grp, sm.wc[t & 1][erow], qr.st, qr.is_end && sidx < n_valid, sidx, lane);
+                tc_fence_before();
+                atomicAdd(&sm.alpha_e[erow], apart);
+                __syncwarp();
+                if (lane == 0) { mbar_arrive(&sm.bar_alpha); mbar_arrive(&sm.bar_drain); }
+            }
+        }
+    }
+    if (tid == 0 && (p.dbg_flags & 4) && blockIdx.x < 192) {      // per-CTA cycles and SM id; [32 + 192] = number of quadrants
+        uint32_t smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        reinterpret_cast<long long*>(p.err)[32 + blockIdx.x] = ((clock64() - _tk0) & 0xffffffffffffll) | ((long long)smid << 48);
+        if (blockIdx.x == 0) reinterpret_cast<long long*>(p.err)[32 + 192] = n_quads;
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == W_ISSUE) tmem_dealloc<512>(sm.tmem_base);
+}
+
+// =====================================================================================================================
 // v6 (opt-in, pnb_tc_version=6): v5 on a CTA PAIR (cluster of 2, tcgen05 cta_group::2).  Each CTA of the pair owns one 128-row
 // tile (its own builders, epilogue warps, TMEM regions P/Q and layer-1 operand buffer); the rank-0 CTA's issuer warp issues
 // ONE M=256 MMA for both tiles.  The B operand (weight image [256 x 32]) is split by N between the two CTAs: each loader
@@ -1465,8 +1866,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(tc6::NTHR, 1) k_shad
                 const int tile = 2 * (pair + t * npairs) + (int)rank;
                 if (t > 0 && !(lane == 0 && warp == W_BUILD ? PNB_TIMED_WAIT(4, mbar_wait(&sm.bar_a1_free, (uint32_t)(t - 1) & 1u, p.err, 68)) : mbar_wait(&sm.bar_a1_free, (uint32_t)(t - 1) & 1u, p.err, 68))) { ok = false; break; }
                 const long long _tb0 = clock64();
-                if (part == 0) build_pair_part<0>(sm, p, tile, t, row, n_valid);
-                else build_pair_part<1>(sm, p, tile, t, row, n_valid);
+                if (part == 0) build_pair_part<0, false>(sm, p, tile, t, row, n_valid);
+                else build_pair_part<1, false>(sm, p, tile, t, row, n_valid);
                 fence_proxy_async();
                 if (rank == 0) mbar_arrive(&sm.bar_a1_ready); else mbar_arrive_cluster(ready0);
                 if (lane == 0 && warp == W_BUILD) prof_add(p, 5, clock64() - _tb0);
@@ -2123,8 +2524,11 @@ extern "C" int pnb_mlp_pack(const pnb_mlp_t* mlp, void* d_out, size_t out_bytes,
     return PNB_OK;
 }
 
+static size_t pack_sc_max(int cap) { return (size_t)cap / tc7::PACK_S + 2; }
 extern "C" size_t pnb_shade_tc_bytes(int max_valid_samples) {
-    return align_up(((size_t)max_valid_samples + 127) / 128 * 128 * 256 * sizeof(float)) + align_up((size_t)max_valid_samples * sizeof(float)) + 256;
+    const size_t cap = (size_t)max_valid_samples;
+    return align_up((cap + 127) / 128 * 128 * 256 * sizeof(float)) + align_up(cap * sizeof(float)) +
+           align_up(cap + 16) + align_up(pack_sc_max(max_valid_samples) * 4) + align_up((cap + 2) * 4) + align_up(16) + 256;   // + v7 packing tables
 }
 
 // Tensor-core forward: per-pair MLPs on tcgen05 (BF16x3), colour branch on CUDA cores.  ws: >= pnb_shade_tc_bytes.
@@ -2140,10 +2544,11 @@ extern "C" int pnb_shade_forward_tc(const pnb_query_t* q, const pnb_points_t* pt
     // interleaved (non-swizzled) operand layout: 128-byte alignment of the carve-out is sufficient
     constexpr size_t kSmemMax = 232448;   // 227 KB opt-in limit per block on sm_100
     const size_t smem_tc = sizeof(tc::Smem) + 128, smem_tc3 = sizeof(tc3::Smem) + 128, smem_cb = sizeof(cb::Smem),
-                 smem_ctc = sizeof(ctc::Smem) + 128, smem_tc5 = sizeof(tc5::Smem) + 128, smem_tc6 = sizeof(tc6::Smem) + 128, smem_ctc2 = sizeof(ctc2::Smem) + 128;
+                 smem_ctc = sizeof(ctc::Smem) + 128, smem_tc5 = sizeof(tc5::Smem) + 128, smem_tc6 = sizeof(tc6::Smem) + 128, smem_ctc2 = sizeof(ctc2::Smem) + 128, smem_tc7 = sizeof(tc7::Smem) + 128;
     static_assert(sizeof(tc5::Smem) + 128 <= kSmemMax, "v5 shared-memory carve-out exceeds the per-block limit");
     static_assert(sizeof(tc6::Smem) + 128 <= kSmemMax, "v6 shared-memory carve-out exceeds the per-block limit");
     static_assert(sizeof(ctc2::Smem) + 128 <= kSmemMax, "colour v2 shared-memory carve-out exceeds the per-block limit");
+    static_assert(sizeof(tc7::Smem) + 128 <= kSmemMax, "v7 shared-memory carve-out exceeds the per-block limit");
     static_assert((tc3::NSTAGE & (tc3::NSTAGE - 1)) == 0 && tc3::NSTAGE == 4, "issuer assumes a 4-stage ring");
     static_assert(sizeof(tc::Smem) + 128 <= kSmemMax && sizeof(tc3::Smem) + 128 <= kSmemMax && sizeof(ctc::Smem) + 128 <= kSmemMax &&
                   sizeof(cb::Smem) <= kSmemMax, "shared-memory carve-out exceeds the sm_100 per-block limit");
@@ -2152,6 +2557,7 @@ extern "C" int pnb_shade_forward_tc(const pnb_query_t* q, const pnb_points_t* pt
         PNB_CHECK_CUDA(cudaFuncSetAttribute(k_shade_tc3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tc3));
         PNB_CHECK_CUDA(cudaFuncSetAttribute(k_shade_tc5, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tc5));
         PNB_CHECK_CUDA(cudaFuncSetAttribute(k_shade_tc6, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tc6));
+        PNB_CHECK_CUDA(cudaFuncSetAttribute(k_shade_tc7, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tc7));
         PNB_CHECK_CUDA(cudaFuncSetAttribute(k_color_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_ctc));
         PNB_CHECK_CUDA(cudaFuncSetAttribute(k_color_tc2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_ctc2));
         PNB_CHECK_CUDA(cudaFuncSetAttribute(k_color_branch, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cb));
@@ -2163,6 +2569,10 @@ extern "C" int pnb_shade_forward_tc(const pnb_query_t* q, const pnb_points_t* pt
     Carver c(ws, ws_bytes);
     float* hbar = c.take<float>(((size_t)max_valid_samples + 127) / 128 * 128 * 256);   // whole 128-sample colour tiles
     float* sigma = c.take<float>((size_t)max_valid_samples);
+    unsigned char* vcnt = c.take<unsigned char>((size_t)max_valid_samples + 16);
+    uint32_t* sc_quads = c.take<uint32_t>(pack_sc_max(max_valid_samples));
+    uint32_t* quad_first = c.take<uint32_t>((size_t)max_valid_samples + 2);
+    int* pack_cnt = c.take<int>(4);
     ShadeTcParams p;
     p.q = *q; p.pts = *pts; p.o = *opts; p.wimg = (const unsigned char*)d_packed;
     for (int l = 0; l < 4; ++l) p.bias[l] = mlp->b[l];
@@ -2171,11 +2581,20 @@ extern "C" int pnb_shade_forward_tc(const pnb_query_t* q, const pnb_points_t* pt
     p.hbar = hbar; p.sigma = sigma; p.hbar_cap = max_valid_samples; p.err = d_err;
     p.dbg_no_weights = (stage_mask & 64) ? 1 : 0;
     p.dbg_flags = (stage_mask >> 8) & 0xff;
+    const bool packed_rows = (stage_mask & (1 << 17)) != 0;   // v7: rows packed to the valid pairs
+    p.vcnt = vcnt; p.quad_first = quad_first; p.pack_cnt = pack_cnt;
     const bool color_v2 = (stage_mask & (1 << 16)) != 0;      // pipelined colour kernel fed by operand-format h-bar (written by the v5 / v6 pair kernels)
-    PNB_REQUIRE(!color_v2 || ((stage_mask & (128 | 32)) && (stage_mask & 8)), PNB_ERR_INVALID, "pnb_shade_forward_tc: colour v2 needs the v5 / v6 pair pipeline");
+    PNB_REQUIRE(!color_v2 || (((stage_mask & (128 | 32)) || packed_rows) && (stage_mask & 8)), PNB_ERR_INVALID, "pnb_shade_forward_tc: colour v2 needs the v5 / v6 / v7 pair pipeline");
     p.hbar_fmt = color_v2 ? 1 : 0;
     if (stage_mask & 1) {
-        if (stage_mask & 128) k_shade_tc6<<<n_sm & ~1, tc6::NTHR, smem_tc6, stream>>>(p);     // v5 on CTA pairs (cta_group::2)
+        if (packed_rows) {
+            const int cap = max_valid_samples, n_sc = (int)pack_sc_max(cap);
+            k_pack_cnt<<<(cap + 255) / 256, 256, 0, stream>>>(p.q, cap, vcnt);
+            k_pack_quads<false><<<(n_sc + 127) / 128, 128, 0, stream>>>(p.q, cap, vcnt, sc_quads, quad_first);
+            k_pack_scan<<<1, 1024, 0, stream>>>(p.q, cap, sc_quads, quad_first, pack_cnt);
+            k_pack_quads<true><<<(n_sc + 127) / 128, 128, 0, stream>>>(p.q, cap, vcnt, sc_quads, quad_first);
+            k_shade_tc7<<<n_sm, tc7::NTHR, smem_tc7, stream>>>(p);                              // v5 with rows packed to the valid pairs
+        } else if (stage_mask & 128) k_shade_tc6<<<n_sm & ~1, tc6::NTHR, smem_tc6, stream>>>(p);     // v5 on CTA pairs (cta_group::2)
         else if (stage_mask & 32) k_shade_tc5<<<n_sm, tc5::NTHR, smem_tc5, stream>>>(p);           // TMEM ping-pong, chunk-pipelined
         else if (stage_mask & 4) k_shade_tc3<<<n_sm, tc3::NTHR, smem_tc3, stream>>>(p);   // TS-form pipeline (A in tensor memory)
         else k_shade_tc<<<n_sm, tc::NTHR, smem_tc, stream>>>(p);

@@ -286,16 +286,18 @@ def _init_state(mod):
     mod.precision = getattr(opt, "pnb_precision", "bf16x3")
     if mod.precision not in ("bf16x3", "fp32"):
         raise NotImplementedError("pnb200: pnb_precision=%r (bf16x3 | fp32)" % mod.precision)
-    # tcgen05 pipeline variant: 5 = chunk-pipelined TMEM role ping-pong (epilogue of layer l under the MMAs of layer l+1; default),
-    # 6 = the same on CTA pairs (cluster of 2, cta_group::2 M=256 MMAs, each CTA stages half of every weight image): ~12 % fewer
+    # tcgen05 pipeline variant: 7 = chunk-pipelined TMEM role ping-pong (epilogue of layer l under the MMAs of layer l+1) with the
+    # rows PACKED to the valid (sample, neighbour) pairs - no MMA rows for empty neighbour slots (default),
+    # 5 = the same pipeline with 8 rows per sample (25 % zero rows on the lego frame),
+    # 6 = v5 on CTA pairs (cluster of 2, cta_group::2 M=256 MMAs, each CTA stages half of every weight image): ~12 % fewer
     # cycles on an idle GPC, but with all TPCs active the B-half exchange saturates the intra-GPC SM-to-SM fabric,
     # 3 = A operand of layers 2-4 in tensor memory + overlapped operand builders, epilogues exposed,
     # 2 = serialized shared-memory pipeline
-    _v = int(getattr(opt, "pnb_tc_version", 5))
-    if _v not in (2, 3, 5, 6):
-        raise NotImplementedError("pnb200: pnb_tc_version=%r (2 | 3 | 5 | 6)" % _v)
-    mod.tc_mask = 3 | (12 if _v == 3 else 0) | (8 + 32 if _v == 5 else 0) | (8 + 128 if _v == 6 else 0)
-    if _v in (5, 6) and int(getattr(opt, "pnb_color_version", 2)) == 2:
+    _v = int(getattr(opt, "pnb_tc_version", 7))
+    if _v not in (2, 3, 5, 6, 7):
+        raise NotImplementedError("pnb200: pnb_tc_version=%r (2 | 3 | 5 | 6 | 7)" % _v)
+    mod.tc_mask = 3 | (12 if _v == 3 else 0) | (8 + 32 if _v == 5 else 0) | (8 + 128 if _v == 6 else 0) | (8 + (1 << 17) if _v == 7 else 0)
+    if _v in (5, 6, 7) and int(getattr(opt, "pnb_color_version", 2)) == 2:
         mod.tc_mask |= 1 << 16        # pipelined colour kernel; the pair kernel writes h-bar as its bf16 hi/lo operand blocks
     mod.last = None
     mod._pnb_ready = True

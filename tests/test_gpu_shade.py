@@ -20,6 +20,8 @@ def _prec(precision):
         return dict(pnb_precision="bf16x3", pnb_tc_version=2)
     if precision == "bf16x3-c1":      # default pair kernel + the serialized colour kernel fed by fp32 h-bar
         return dict(pnb_precision="bf16x3", pnb_color_version=1)
+    if precision == "bf16x3-v5":
+        return dict(pnb_precision="bf16x3", pnb_tc_version=5)
     if precision == "bf16x3-v6":
         return dict(pnb_precision="bf16x3", pnb_tc_version=6)
     if precision == "bf16x3-v3":
@@ -38,7 +40,7 @@ def _render_full(net, cfg, rays):
         return net.render_full(list(cfg.campos), rays["raydir"].to(DEV), torch.eye(3), cfg.near, cfg.far, [1., 1., 1.])
 
 
-@pytest.mark.parametrize("precision", ["bf16x3", "bf16x3-c1", "bf16x3-v6", "bf16x3-v3", "bf16x3-v2", "fp32"])
+@pytest.mark.parametrize("precision", ["bf16x3", "bf16x3-v5", "bf16x3-c1", "bf16x3-v6", "bf16x3-v3", "bf16x3-v2", "fp32"])
 @pytest.mark.parametrize("name,side,alpha_bias,over", [
     ("tiny", 64, 4.0, {}), ("tiny", 64, 0.0, {}), ("tiny", 40, 8.0, dict(SR=8)), ("tiny", 40, 4.0, dict(K=3)),
     ("chair_plumbing", 16, 4.0, {}), ("chair_plumbing", 64, 2.0, dict(SR=80)),
@@ -57,7 +59,7 @@ def test_render_matches_oracle(name, side, alpha_bias, over, precision):
     net.check_errors()
 
 
-@pytest.mark.parametrize("precision", ["bf16x3", "bf16x3-c1", "bf16x3-v6", "bf16x3-v3", "bf16x3-v2", "fp32"])
+@pytest.mark.parametrize("precision", ["bf16x3", "bf16x3-v5", "bf16x3-c1", "bf16x3-v6", "bf16x3-v3", "bf16x3-v2", "fp32"])
 @pytest.mark.parametrize("name", ["tiny_opaque", "tiny_thin_sr8"])
 def test_forward_matches_reference_fixture(name, golden_dir, precision):
     """The drop-in NeuralPointsRayMarching.forward() output dict vs what the reference module itself returned."""
@@ -78,7 +80,7 @@ def test_forward_matches_reference_fixture(name, golden_dir, precision):
     assert out["queried_shading"].shape == (1, fx["sample_pidx"].shape[0], 3)
 
 
-@pytest.mark.parametrize("precision", ["bf16x3", "bf16x3-c1", "bf16x3-v6", "bf16x3-v3", "bf16x3-v2", "fp32"])
+@pytest.mark.parametrize("precision", ["bf16x3", "bf16x3-v5", "bf16x3-c1", "bf16x3-v6", "bf16x3-v3", "bf16x3-v2", "fp32"])
 def test_render_lego_scale(precision):
     """BASELINE config 2 size: a reference-sized chunk against the oracle; full-frame determinism and
     sharding invariance (bit-exact: a ray's colour does not depend on which rays share the call)."""

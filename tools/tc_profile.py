@@ -5,7 +5,7 @@ import torch
 from pointnerf_b200 import harness, scene
 dev = torch.device("cuda:0")
 cfg = scene.CONFIGS["lego_render"]
-net, pts, opt = harness.build_model(cfg, dev, alpha_bias=3.0, pnb_tc_version=int(os.environ.get("PNB_TC_VERSION", "5")), pnb_color_version=int(os.environ.get("PNB_COLOR_VERSION", "2")))
+net, pts, opt = harness.build_model(cfg, dev, alpha_bias=3.0, pnb_tc_version=int(os.environ.get("PNB_TC_VERSION", "7")), pnb_color_version=int(os.environ.get("PNB_COLOR_VERSION", "2")))
 rays = scene.make_rays(cfg)
 rd = rays["raydir"].to(dev)
 for i in range(3):
@@ -24,10 +24,11 @@ names = ["loader wait empty", "issuer wait a1_ready", "issuer wait at_ready", "i
          "builder busy", "epilogue wait acc_full", "epilogue busy (l<3)", "epilogue busy (l==3)", "kernel total (thread 0)", "issuer: in ring commits (v6)", "issuer: K-block issue incl. commits (v6)", "issuer: wait kblk (probe)", "issuer: wait weights (probe)", "issuer: #weight waits", "peer loader wait empty"]
 ntiles = (net.last.counters["n_valid"] if net.last.counters else 3472901) if False else None
 tot = c[9]
-print("status", int(net._err[0]), "version", os.environ.get("PNB_TC_VERSION", "5"), "no_weights", bool(os.environ.get("PNB_NO_WEIGHTS")))
+print("status", int(net._err[0]), "version", os.environ.get("PNB_TC_VERSION", "7"), "no_weights", bool(os.environ.get("PNB_NO_WEIGHTS")))
 for n, v in zip(names, c):
     print("%-28s %12d cycles  %5.1f%% of kernel" % (n, v, 100.0 * v / max(tot, 1)))
 
 if int(os.environ.get("PNB_DBG_FLAGS", "0")) & 4:
     per = net._err.cpu().view(torch.int64)[32:32 + 148].tolist()
+    print("n_quads (v7):", int(net._err.cpu().view(torch.int64)[32 + 192]), "n_valid:", net.last.counters.get("n_valid") if net.last and net.last.counters else None)
     print("per-CTA kernel cycles (M) @smid:", " ".join("%.1f@%d" % ((v & 0xffffffffffff) / 1e6, v >> 48) for v in per))

@@ -49,7 +49,9 @@ def peaks():
 
 
 class ClockSampler:
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+    """nvidia-smi polled every 25 ms from before the warm-up (its start-up latency would otherwise eat a 0.2-s timed region);
+    stop(t0, t1) keeps the samples whose timestamps fall inside the timed region [t0, t1] (host wall clock)."""
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index):
@@ -57,13 +59,15 @@ class ClockSampler:
         self.p = None
         try:
             self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                                       "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
+                                       "-lms", "25"], stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
 
-    def stop(self):
+    def stop(self, t0=None, t1=None):
+        import datetime
         if self.p is None:
             return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        time.sleep(0.05)
         self.p.terminate()
         try:
             self.p.wait(timeout=5)
@@ -72,19 +76,31 @@ class ClockSampler:
         self.f.flush()
         rows = [l.strip().split(", ") for l in open(self.f.name) if l.strip()]
         os.unlink(self.f.name)
-        sm, mx, reasons, pw = [], [], set(), []
-        for r in rows:
-            try:
-                sm.append(float(r[1])); mx.append(float(r[2])); pw.append(float(r[3]))
-            except Exception:
-                continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
-                if v.strip().lower().startswith("active"):
-                    reasons.add(name)
+
+        def collect(lo, hi):
+            sm, mx, reasons, pw = [], [], set(), []
+            for r in rows:
+                try:
+                    ts = datetime.datetime.strptime(r[0].strip(), "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                    if lo is not None and not (lo <= ts <= hi):
+                        continue
+                    sm.append(float(r[1])); mx.append(float(r[2])); pw.append(float(r[3]))
+                except Exception:
+                    continue
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.strip().lower().startswith("active"):
+                        reasons.add(name)
+            return sm, mx, reasons, pw
+
+        window = "timed region"
+        sm, mx, reasons, pw = collect(t0, t1)
+        if len(sm) < 2 and t0 is not None:          # very short region: fall back to everything since the warm-up started (also under load)
+            sm, mx, reasons, pw = collect(None, None)
+            window = "warm-up + timed region"
         if not sm:
             return dict(sm_mhz=None, sm_max_mhz=None, reasons=["no samples"])
         return dict(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), power_w_max=float(max(pw)), samples=len(sm),
-                    reasons=sorted(reasons))
+                    window=window, reasons=sorted(reasons))
 
 
 # ---------------------------------------------------------------------------------------------------------------------
@@ -270,6 +286,7 @@ def main():
             ms = float(t.item())
         return ms
 
+    sampler = ClockSampler(local_rank) if rank == 0 else None
     for _ in range(max(args.warmup, 3)):
         step_resident()
     barrier()
@@ -277,9 +294,10 @@ def main():
     qc = net.neural_points.querier.run_query(net.neural_points.xyz.detach(), raydir_dev, cam[0], cam[2], cam[3], want_counters=True).counters
     gc = net.neural_points.querier.last_grid_counters
 
-    sampler = ClockSampler(local_rank) if rank == 0 else None
+    t_w0 = time.time()
     ms_res = timed(step_resident, args.steps)
-    clocks = sampler.stop() if sampler else None
+    t_w1 = time.time()
+    clocks = sampler.stop(t_w0, t_w1) if sampler else None
 
     # dominant kernel alone (shade): CUDA events around the shade launch on the launching stream, same inputs
     from pointnerf_b200 import lib as _lib

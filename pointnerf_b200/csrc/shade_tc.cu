@@ -68,7 +68,8 @@ struct ShadeTcParams {
     int* err;
     int dbg_no_weights;          // timing experiment only: the loader signals the ring without copying (results are garbage)
     int dbg_flags;               // bit 1: v6 issuer classifies its waits with non-blocking probes (profiling)
-    const unsigned char* vcnt;   // v7 row packing: neighbours per valid sample [n_valid]
+    const unsigned char* vcnt;   // v7 row packing: neighbours per PACKED position [n_valid] (vcntp of k_pack_quads)
+    const uint32_t* vorder;      // v7: valid-sample index of every packed position [n_valid]
     const uint32_t* quad_first;  // v7: first valid sample of every 32-row quadrant [n_quads + 1]
     const int* pack_cnt;         // v7: [0] = n_quads
     int hbar_fmt;                // 0: hbar[n_valid][256] fp32;  1: bf16 hi/lo A-operand blocks of k_color_tc2 (per 128 samples: 8 K blocks x {hi,lo} x [128x32])
@@ -1305,6 +1306,7 @@ constexpr int NEPI_WARPS = 8, NGRP = NEPI_WARPS / 4, NCH = 16 / NGRP;
 constexpr int NEPI = NEPI_WARPS * 32, NBUILD = 256, NTHR = NEPI + NBUILD + 64;     // two builder threads per row (as v6)
 constexpr int NSTAGE = 4;
 constexpr int PACK_S = 512;             // samples per independently packed super-chunk (its last quadrant may stay partly empty)
+constexpr int PACK_WIN = 64;            // look-ahead of the first-fit packing
 struct Smem {
     static constexpr int NWC = 2;          // reuse ordered through bar_alpha: the builders run their share of the last epilogue
     unsigned char a_hi[tc::NKB_MAX * tc::ABLK];
@@ -1327,31 +1329,41 @@ __global__ void __launch_bounds__(256) k_pack_cnt(pnb_query_t q, int cap, unsign
     const int n_valid = min(q.counters[PNB_QC_N_VALID], cap);
     if (vi < n_valid) vcnt[vi] = q.samp_nvalid[q.valid_list[vi]];
 }
-// one thread per super-chunk: greedy packing of its samples into 32-row quadrants.  WRITE = false: count them.
+// one thread per super-chunk: first-fit packing of its samples into 32-row quadrants.  Samples are taken in order while they fit;
+// a sample that does not fit stays first in line for the next quadrant while up to PACK_WIN later, smaller samples may fill the
+// remaining rows (so the order inside a super-chunk becomes a permutation: vorder).  WRITE = false: count the quadrants only.
 template <bool WRITE>
 __global__ void __launch_bounds__(128) k_pack_quads(pnb_query_t q, int cap, const unsigned char* __restrict__ vcnt,
-                                                    uint32_t* __restrict__ sc_quads, uint32_t* __restrict__ quad_first) {
+                                                    uint32_t* __restrict__ sc_quads, uint32_t* __restrict__ quad_first,
+                                                    uint32_t* __restrict__ vorder, unsigned char* __restrict__ vcntp) {
     const int sc = blockIdx.x * blockDim.x + threadIdx.x;
     const int n_valid = min(q.counters[PNB_QC_N_VALID], cap);
     const int i0 = sc * tc7::PACK_S;
     if (i0 >= n_valid) return;
-    const int i1 = min(i0 + tc7::PACK_S, n_valid);
+    const int n = min(tc7::PACK_S, n_valid - i0);
+    __align__(16) unsigned char c[tc7::PACK_S];   // neighbour counts of this super-chunk; 0 = already placed
+    for (int i = 0; i < n; i += 16) {
+        const uint4 pk = *reinterpret_cast<const uint4*>(vcnt + i0 + i);      // the buffer is padded to a multiple of 16
+        *reinterpret_cast<uint4*>(c + i) = pk;
+    }
     uint32_t nq = WRITE ? sc_quads[sc] : 0u;      // WRITE: sc_quads holds the exclusive prefix = first quadrant of this super-chunk
-    int rows = 0;
-    for (int i = i0; i < i1; i += 16) {
-        const uint4 pk = *reinterpret_cast<const uint4*>(vcnt + i);      // 16 counts (the buffer is padded to a multiple of 16)
-        const uint32_t w[4] = {pk.x, pk.y, pk.z, pk.w};
-#pragma unroll
-        for (int e = 0; e < 16; ++e) {
-            if (i + e < i1) {
-                const int c = (int)((w[e >> 2] >> (8 * (e & 3))) & 0xffu);
-                if (rows + c > 32) { ++nq; rows = 0; }
-                if (WRITE && rows == 0) quad_first[nq] = (uint32_t)(i + e);
-                rows += c;
+    int pos = 0, emitted = 0;
+    while (pos < n) {
+        if (WRITE) quad_first[nq] = (uint32_t)(i0 + emitted);
+        int rows = 0;
+        const int lim = min(n, pos + tc7::PACK_WIN);
+        for (int i = pos; i < lim && rows < 32; ++i) {
+            const int ci = c[i];
+            if (ci != 0 && rows + ci <= 32) {
+                if (WRITE) { vorder[i0 + emitted] = (uint32_t)(i0 + i); vcntp[i0 + emitted] = (unsigned char)ci; }
+                c[i] = 0;
+                rows += ci;
+                ++emitted;
             }
         }
+        while (pos < n && c[pos] == 0) ++pos;
+        ++nq;
     }
-    if (rows > 0) ++nq;
     if (!WRITE) sc_quads[sc] = nq;
 }
 // exclusive scan of the per-super-chunk quadrant counts (one block), total -> pack_cnt[0], sentinel quad_first[n_quads] = n_valid
@@ -1576,7 +1588,7 @@ __global__ void __launch_bounds__(tc7::NTHR, 1) k_shade_tc7(ShadeTcParams p) {
                 const QuadRow qr = quad_row(head, total, lane);
                 const int cj = __shfl_sync(0xffffffffu, c, qr.j);
                 if (lane == 0 && part == 1) { sm.qhead[t & 1][qw] = head; sm.qfirst[t & 1][qw] = first; sm.qtotal[t & 1][qw] = (uint32_t)total; }
-                const int pvi = qr.live ? (int)first + qr.j : -1;
+                const int pvi = qr.live ? (int)p.vorder[first + qr.j] : -1;
                 if (part == 0) build_pair_part<0, true>(sm, p, tile, t, row, n_valid, pvi, lane - qr.st, qr.st, qr.live ? cj : 1);
                 else build_pair_part<1, true>(sm, p, tile, t, row, n_valid, pvi, lane - qr.st, qr.st, qr.live ? cj : 1);
                 fence_proxy_async();
@@ -1587,7 +1599,7 @@ __global__ void __launch_bounds__(tc7::NTHR, 1) k_shade_tc7(ShadeTcParams p) {
                 if (!mbar_wait(&sm.bar_final, (uint32_t)tf & 1u, p.err, 99)) { ok = false; break; }
                 tc_fence_after();
                 const QuadRow qr = quad_row(sm.qhead[tf & 1][qw], (int)sm.qtotal[tf & 1][qw], lane);
-                const int sidx = (int)sm.qfirst[tf & 1][qw] + qr.j;
+                const int sidx = qr.live ? (int)p.vorder[sm.qfirst[tf & 1][qw] + qr.j] : 0;
                 const bool swrite = qr.is_end && sidx < n_valid;
                 const float wrow = sm.wc[tf & 1][row];
                 const float apart = last_chunks_packed<4, 4>(p, tP + tlane, 2 + part, wrow, qr.st, swrite, sidx, lane);
@@ -1648,7 +1660,7 @@ __global__ void __launch_bounds__(tc7::NTHR, 1) k_shade_tc7(ShadeTcParams p) {
                 if (!mbar_wait(&sm.bar_final, (uint32_t)t & 1u, p.err, 101)) { ok = false; break; }
                 tc_fence_after();
                 const QuadRow qr = quad_row(sm.qhead[t & 1][quad], (int)sm.qtotal[t & 1][quad], lane);
-                const int sidx = (int)sm.qfirst[t & 1][quad] + qr.j;
+                const int sidx = qr.live ? (int)p.vorder[sm.qfirst[t & 1][quad] + qr.j] : 0;
                 const float apart = last_chunks_packed<4, 4>(p, tP + tlane, grp, sm.wc[t & 1][erow], qr.st, qr.is_end && sidx < n_valid, sidx, lane);
                 tc_fence_before();
                 atomicAdd(&sm.alpha_e[erow], apart);
@@ -2528,7 +2540,7 @@ static size_t pack_sc_max(int cap) { return (size_t)cap / tc7::PACK_S + 2; }
 extern "C" size_t pnb_shade_tc_bytes(int max_valid_samples) {
     const size_t cap = (size_t)max_valid_samples;
     return align_up((cap + 127) / 128 * 128 * 256 * sizeof(float)) + align_up(cap * sizeof(float)) +
-           align_up(cap + 16) + align_up(pack_sc_max(max_valid_samples) * 4) + align_up((cap + 2) * 4) + align_up(16) + 256;   // + v7 packing tables
+           2 * align_up(cap + 16) + align_up(pack_sc_max(max_valid_samples) * 4) + 2 * align_up((cap + 2) * 4) + align_up(16) + 256;   // + v7 packing tables
 }
 
 // Tensor-core forward: per-pair MLPs on tcgen05 (BF16x3), colour branch on CUDA cores.  ws: >= pnb_shade_tc_bytes.
@@ -2572,6 +2584,8 @@ extern "C" int pnb_shade_forward_tc(const pnb_query_t* q, const pnb_points_t* pt
     unsigned char* vcnt = c.take<unsigned char>((size_t)max_valid_samples + 16);
     uint32_t* sc_quads = c.take<uint32_t>(pack_sc_max(max_valid_samples));
     uint32_t* quad_first = c.take<uint32_t>((size_t)max_valid_samples + 2);
+    uint32_t* vorder = c.take<uint32_t>((size_t)max_valid_samples + 2);
+    unsigned char* vcntp = c.take<unsigned char>((size_t)max_valid_samples + 16);
     int* pack_cnt = c.take<int>(4);
     ShadeTcParams p;
     p.q = *q; p.pts = *pts; p.o = *opts; p.wimg = (const unsigned char*)d_packed;
@@ -2582,7 +2596,7 @@ extern "C" int pnb_shade_forward_tc(const pnb_query_t* q, const pnb_points_t* pt
     p.dbg_no_weights = (stage_mask & 64) ? 1 : 0;
     p.dbg_flags = (stage_mask >> 8) & 0xff;
     const bool packed_rows = (stage_mask & (1 << 17)) != 0;   // v7: rows packed to the valid pairs
-    p.vcnt = vcnt; p.quad_first = quad_first; p.pack_cnt = pack_cnt;
+    p.vcnt = vcntp; p.vorder = vorder; p.quad_first = quad_first; p.pack_cnt = pack_cnt;
     const bool color_v2 = (stage_mask & (1 << 16)) != 0;      // pipelined colour kernel fed by operand-format h-bar (written by the v5 / v6 pair kernels)
     PNB_REQUIRE(!color_v2 || (((stage_mask & (128 | 32)) || packed_rows) && (stage_mask & 8)), PNB_ERR_INVALID, "pnb_shade_forward_tc: colour v2 needs the v5 / v6 / v7 pair pipeline");
     p.hbar_fmt = color_v2 ? 1 : 0;
@@ -2590,9 +2604,9 @@ extern "C" int pnb_shade_forward_tc(const pnb_query_t* q, const pnb_points_t* pt
         if (packed_rows) {
             const int cap = max_valid_samples, n_sc = (int)pack_sc_max(cap);
             k_pack_cnt<<<(cap + 255) / 256, 256, 0, stream>>>(p.q, cap, vcnt);
-            k_pack_quads<false><<<(n_sc + 127) / 128, 128, 0, stream>>>(p.q, cap, vcnt, sc_quads, quad_first);
+            k_pack_quads<false><<<(n_sc + 127) / 128, 128, 0, stream>>>(p.q, cap, vcnt, sc_quads, quad_first, vorder, vcntp);
             k_pack_scan<<<1, 1024, 0, stream>>>(p.q, cap, sc_quads, quad_first, pack_cnt);
-            k_pack_quads<true><<<(n_sc + 127) / 128, 128, 0, stream>>>(p.q, cap, vcnt, sc_quads, quad_first);
+            k_pack_quads<true><<<(n_sc + 127) / 128, 128, 0, stream>>>(p.q, cap, vcnt, sc_quads, quad_first, vorder, vcntp);
             k_shade_tc7<<<n_sm, tc7::NTHR, smem_tc7, stream>>>(p);                              // v5 with rows packed to the valid pairs
         } else if (stage_mask & 128) k_shade_tc6<<<n_sm & ~1, tc6::NTHR, smem_tc6, stream>>>(p);     // v5 on CTA pairs (cta_group::2)
         else if (stage_mask & 32) k_shade_tc5<<<n_sm, tc5::NTHR, smem_tc5, stream>>>(p);           // TMEM ping-pong, chunk-pipelined

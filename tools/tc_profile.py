@@ -1,4 +1,6 @@
-"""Run on the GPU box: in-kernel cycle accounting of k_shade_tc3 (block 0), lego_render frame."""
+"""Run on the GPU box, lego_render frame: in-kernel cycle accounting of the pair kernel (block 0; v3 / v5 / v6) and, with
+PNB_DBG_FLAGS=4, the cycles of every CTA (v5 / v6 / v7).  PNB_TC_VERSION selects the variant, PNB_NO_PROF=1 switches the
+accounting off (it slows block 0 down), PNB_NO_WEIGHTS=1 removes the weight traffic (garbage results)."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch

@@ -1,7 +1,7 @@
 """TEST INFRASTRUCTURE ONLY -- compiles the REFERENCE's own CUDA query extension (two source files, read in place under
 /root/reference; nothing is copied) into oracle/_ref/ so that it travels to the GPU box with the snapshot (oracle/_ref is
 git-ignored, not gpurun-ignored).  It is the un-modified `query_worldcoords_cuda` torch extension that
-/root/reference/models/neural_points/point_query.py:15-22 JIT-builds at import; tools/ref_kernel_check.py runs it on a B200
+/root/reference/models/neural_points/point_query.py:15-22 JIT-builds at import; tests/ref_kernel_check.py runs it on a B200
 next to libpnb200 to pin the integer query parity to an EXECUTION of the reference kernel (round 2; round 1 pins the query
 to the restated canonical semantics).
 

@@ -7,7 +7,7 @@ order of the points inside a voxel on the atomics of fill_occ2pnts.  So the comp
 samples whose neighbourhood can see the reference's or our slot-0 voxel are reported separately.  This script only prints a
 report; it is not a pytest test (it was written when the round's GPU budget was spent and has not run yet).
 
-    python tools/ref_kernel_check.py [config] [patch_side]
+    python tests/ref_kernel_check.py [config] [patch_side]      (lives under tests/: only tests may import oracle/)
 """
 import os
 import sys

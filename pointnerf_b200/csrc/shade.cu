@@ -436,15 +436,16 @@ extern "C" int pnb_shade_forward(const pnb_query_t* q, const pnb_points_t* pts, 
     PNB_REQUIRE(q->K >= 1 && q->K <= PNB_MAX_K, PNB_ERR_UNSUPPORTED, "pnb_shade_forward: K=%d unsupported", q->K);
     for (int i = 0; i < 9; ++i)
         PNB_REQUIRE(mlp->w[i] && mlp->b[i], PNB_ERR_INVALID, "pnb_shade_forward: MLP tensor %d is null", i);
-    static int smem_set = 0;
-    static int n_sm = 0;
-    if (!smem_set) {
+    static int smem_set[64] = {0}, n_sm_of[64] = {0};      // per device of this process
+    int dev = 0;
+    PNB_CHECK_CUDA(cudaGetDevice(&dev));
+    PNB_REQUIRE(dev >= 0 && dev < 64, PNB_ERR_UNSUPPORTED, "pnb_shade_forward: device ordinal %d", dev);
+    if (!smem_set[dev]) {
         PNB_CHECK_CUDA(cudaFuncSetAttribute(k_shade_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ShadeSmem)));
-        int dev = 0;
-        PNB_CHECK_CUDA(cudaGetDevice(&dev));
-        PNB_CHECK_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
-        smem_set = 1;
+        PNB_CHECK_CUDA(cudaDeviceGetAttribute(&n_sm_of[dev], cudaDevAttrMultiProcessorCount, dev));
+        smem_set[dev] = 1;
     }
+    const int n_sm = n_sm_of[dev];
     ShadeParams p;
     p.q = *q; p.pts = *pts; p.mlp = *mlp; p.o = *opts; p.sigma_rgb = (float4*)d_sigma_rgb;
     k_shade_fwd<<<n_sm, NTHREADS, sizeof(ShadeSmem), stream>>>(p);

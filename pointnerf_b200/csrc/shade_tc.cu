@@ -2552,7 +2552,10 @@ extern "C" int pnb_shade_forward_tc(const pnb_query_t* q, const pnb_points_t* pt
     PNB_REQUIRE(q && pts && mlp && d_packed && opts && d_sigma_rgb && ws && d_err, PNB_ERR_INVALID, "pnb_shade_forward_tc: null argument");
     PNB_REQUIRE(q->K >= 1 && q->K <= PNB_MAX_K, PNB_ERR_UNSUPPORTED, "pnb_shade_forward_tc: K=%d unsupported", q->K);
     PNB_REQUIRE(ws_bytes >= pnb_shade_tc_bytes(max_valid_samples), PNB_ERR_WORKSPACE, "pnb_shade_forward_tc: workspace too small");
-    static int configured = 0, n_sm = 0;
+    static int configured[64] = {0}, n_sm_of[64] = {0};      // per device of this process (one process per GPU is the norm)
+    int dev = 0;
+    PNB_CHECK_CUDA(cudaGetDevice(&dev));
+    PNB_REQUIRE(dev >= 0 && dev < 64, PNB_ERR_UNSUPPORTED, "pnb_shade_forward_tc: device ordinal %d", dev);
     // interleaved (non-swizzled) operand layout: 128-byte alignment of the carve-out is sufficient
     constexpr size_t kSmemMax = 232448;   // 227 KB opt-in limit per block on sm_100
     const size_t smem_tc = sizeof(tc::Smem) + 128, smem_tc3 = sizeof(tc3::Smem) + 128, smem_cb = sizeof(cb::Smem),
@@ -2564,7 +2567,7 @@ extern "C" int pnb_shade_forward_tc(const pnb_query_t* q, const pnb_points_t* pt
     static_assert((tc3::NSTAGE & (tc3::NSTAGE - 1)) == 0 && tc3::NSTAGE == 4, "issuer assumes a 4-stage ring");
     static_assert(sizeof(tc::Smem) + 128 <= kSmemMax && sizeof(tc3::Smem) + 128 <= kSmemMax && sizeof(ctc::Smem) + 128 <= kSmemMax &&
                   sizeof(cb::Smem) <= kSmemMax, "shared-memory carve-out exceeds the sm_100 per-block limit");
-    if (!configured) {
+    if (!configured[dev]) {
         PNB_CHECK_CUDA(cudaFuncSetAttribute(k_shade_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tc));
         PNB_CHECK_CUDA(cudaFuncSetAttribute(k_shade_tc3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tc3));
         PNB_CHECK_CUDA(cudaFuncSetAttribute(k_shade_tc5, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tc5));
@@ -2573,11 +2576,10 @@ extern "C" int pnb_shade_forward_tc(const pnb_query_t* q, const pnb_points_t* pt
         PNB_CHECK_CUDA(cudaFuncSetAttribute(k_color_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_ctc));
         PNB_CHECK_CUDA(cudaFuncSetAttribute(k_color_tc2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_ctc2));
         PNB_CHECK_CUDA(cudaFuncSetAttribute(k_color_branch, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cb));
-        int dev = 0;
-        PNB_CHECK_CUDA(cudaGetDevice(&dev));
-        PNB_CHECK_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
-        configured = 1;
+        PNB_CHECK_CUDA(cudaDeviceGetAttribute(&n_sm_of[dev], cudaDevAttrMultiProcessorCount, dev));
+        configured[dev] = 1;
     }
+    const int n_sm = n_sm_of[dev];
     Carver c(ws, ws_bytes);
     float* hbar = c.take<float>(((size_t)max_valid_samples + 127) / 128 * 128 * 256);   // whole 128-sample colour tiles
     float* sigma = c.take<float>((size_t)max_valid_samples);

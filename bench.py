@@ -383,11 +383,28 @@ def main():
                           colour_branch_kernel_ms=color_avg),
             cpu_baseline=cpu,
         )
+        if _RETRY_NOTE:
+            line["retried_after"] = _RETRY_NOTE        # the first attempt tripped the in-kernel watchdog (see __main__)
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
     return 0
 
 
+_RETRY_NOTE = None
+
 if __name__ == "__main__":
-    sys.exit(main())
+    try:
+        rc = main()
+    except Exception as e:  # noqa: BLE001
+        from pointnerf_b200.lib import PnbError
+        single = int(os.environ.get("WORLD_SIZE", "1")) == 1       # with several ranks a one-sided retry would hang the collectives
+        if isinstance(e, PnbError) and "time-out" in str(e) and single:
+            # every in-kernel mbarrier wait is bounded (2 s): a protocol stall surfaces as this error instead of a hung GPU.
+            # Never seen on the final pipeline; if it ever happens the run is re-measured once and the JSON line says so.
+            print("bench.py: %s -- re-measuring once" % e, file=sys.stderr)
+            _RETRY_NOTE = str(e)
+            rc = main()
+        else:
+            raise
+    sys.exit(rc)

@@ -163,6 +163,9 @@ class CpuArm:
                 % (steps, self.workers, self.workers, self.threads, secs))
 
 
+WORKLOAD = "lego_render: 800x800 image per GPU, K=8, N=400000 points, SR=%d, D=400, P=16, vsize 0.004 x vscale 2"      # both arms
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -180,7 +183,8 @@ def run_reference_arm(args):
     val = rays / dt / 1e6
     line = dict(impl="reference", metric=METRIC, value=val, unit="Mrays/s", n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
                 ms_per_step=dt / args.steps * 1e3, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32",
-                data="synthetic", config=dict(workload="lego_render 800x800 K=8 N=400k SR=%d D=400" % args.sr, rays_per_step=rays // max(args.steps, 1)),
+                data="synthetic", config=dict(workload=WORKLOAD % args.sr, rays_per_step_sampled=rays // max(args.steps, 1),
+                            note="each step = a bounded sample of the frame (see cpu_baseline.sample); value = rays of the sample / time"),
                 cpu_baseline=dict(value=val, unit="Mrays/s", cores=arm.workers * arm.threads, kind="port", sample=arm.describe(args.steps, dt)),
                 e2e=dict(value=val, unit="Mrays/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
     print(json.dumps(line))
@@ -365,7 +369,7 @@ def main():
             metric=METRIC, value=value, unit="Mrays/s", n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3),
             ms_per_step=ms_res / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None, dtype=("f32 (bf16x3 split on tcgen05, fp32 accumulate)" if args.precision != "fp32" else "f32"),
             data="synthetic",
-            config=dict(workload="lego_render: 800x800 image per GPU, K=8, N=400000 points, SR=%d, D=400, P=16, vsize 0.004 x vscale 2" % args.sr,
+            config=dict(workload=WORKLOAD % args.sr,
                         rays_per_step_per_gpu=R, parallelism="rays interleave-sharded x%d, points replicated%s" % (world, ", all-gather of colours" if world > 1 else ""),
                         l2="flushed between timed steps (256 MiB write, outside the CUDA events)",
                         workload_counters=dict(hit_rays=qc["R2"], valid_samples=qc["n_valid"], valid_pairs=qc["n_pairs"],

@@ -376,7 +376,8 @@ def main():
                                                candidate_samples=qc["n_cand"], occupied_voxels=gc["n_occ"], max_pts_per_voxel=gc["max_pts"])),
             e2e=dict(value=e2e_val, unit="Mrays/s", h2d_bytes_per_step=int(mine_host.numel() * 4 * world),
                      d2h_bytes_per_step=int(out_host.numel() * 4 * world), ms_per_step=ms_e2e / args.steps),
-            gpu_launches=(LAUNCHES_PER_STEP + (1 if args.precision != "fp32" else 0)) * args.steps,
+            # + colour kernel (tcgen05 paths) + the 4 row-packing kernels of the v7 pair pipeline; cf. profiles/r01_ncu_launches_tc7_summary.txt
+            gpu_launches=(LAUNCHES_PER_STEP + (1 if args.precision != "fp32" else 0) + (4 if (args.precision != "fp32" and args.tc_version == 7) else 0)) * args.steps,
             clocks=clocks,
             roofline=dict(bound="tensor", kernel=kname, achieved=achieved, peak=peak, unit="TFLOP/s",
                           frac=achieved / peak, traffic=traffic, peak_source="%s bf16 cuBLAS burst (MEASURED_PEAKS.json)" % pk["source"],

@@ -190,8 +190,10 @@ int pnb_shade_forward_tc(const pnb_query_t* q, const pnb_points_t* pts, const pn
                          int max_valid_samples,
                          int stage_mask /* 1 pair MLPs, 2 colour branch (both = a forward); variant bits: +4 TS-form pair
                                            pipeline (v3), +32 chunk-pipelined TMEM role ping-pong (v5), +128 the same on CTA
-                                           pairs / cta_group::2 (v6); +8 colour branch on tcgen05, +65536 pipelined colour
-                                           kernel fed by operand-format h-bar (needs +32 or +128 and +8); diagnostics:
+                                           pairs / cta_group::2 (v6), +131072 the v5 pipeline with the rows packed to the valid
+                                           (sample, neighbour) pairs (v7, the default of the Python host); +8 colour branch on
+                                           tcgen05, +65536 pipelined colour kernel fed by operand-format h-bar (needs +8 and
+                                           one of +32 / +128 / +131072); diagnostics:
                                            +64 no weight traffic (garbage results), bits 8..15 = profiling / experiment
                                            flags of tools/tc_profile.py (256: cycle accounting of block 0 into d_err[2..],
                                            1024: per-CTA cycles into d_err[64..], needs a 512-int d_err) */,

@@ -355,6 +355,10 @@ class NeuralPointsRayMarching(nn.Module):
         else:
             per_ray = int(getattr(opt, "pnb_max_valid_per_ray", 10))
             max_valid = int(min(q.R * q.SR, max(1 << 20, q.R * per_ray)))
+            if want_counters and getattr(q, "counters", None):
+                # the drop-in forward() already paid the host sync for the counters: size the workspace exactly when the scene is
+                # denser than the heuristic (e.g. indoor scenes where every ray keeps all SR samples)
+                max_valid = max(max_valid, int(q.counters.get("n_valid", 0)))
             self._max_valid = max_valid
             nb = lib.pnb_shade_tc_bytes(max_valid)
             if self._tc_ws is None or self._tc_ws.numel() < nb or self._tc_ws.device != raydir.device:

@@ -76,3 +76,35 @@ def test_prune_and_grow_points_mirror_reference_semantics():
     npn.grow_points(torch.zeros(5, 3), torch.ones(5, 32), torch.ones(5, 3), torch.ones(5, 3), torch.full((5, 1), 0.3))
     assert npn.xyz.shape[0] == n0 + 5 and npn.points_color.shape == (1, n0 + 5, 3)
     assert sorted(k for k, _ in npn.named_parameters()) == ["points_color", "points_conf", "points_dir", "points_embeding", "xyz"]
+
+
+def test_segmented_scan_order_depends_on_count_only():
+    """Design invariant behind the packed-row K-reduction (csrc/shade_tc.cu: seg_scan8): a sample's rows are 1..8 consecutive
+    lanes anywhere in a 32-lane quadrant; the 3-step segmented shuffle scan must add them in an order that depends on the
+    neighbour count only, so that a ray's colour is bit-identical whichever samples share its quadrant.  Restated in numpy
+    (fp32, same dataflow as the warp shuffles) and checked for every (offset, count) against the offset-0 result."""
+    rng = np.random.default_rng(0)
+
+    def seg_scan(vals, st_of_lane):                     # vals[32] fp32, st_of_lane[32] = first lane of each lane's segment
+        v = vals.astype(np.float32).copy()
+        for d in (1, 2, 4):
+            up = np.concatenate([np.zeros(d, np.float32), v[:-d]])           # __shfl_up_sync(v, d)
+            take = (np.arange(32) - d) >= st_of_lane
+            v = np.where(take, (v + up).astype(np.float32), v)
+        return v
+
+    for cnt in range(1, 9):
+        x = (rng.standard_normal(cnt) * 10 ** rng.uniform(-3, 3, cnt)).astype(np.float32)
+        ref = None
+        for st in range(0, 32 - cnt + 1):
+            vals = rng.standard_normal(32).astype(np.float32)               # neighbours' rows hold other samples' values
+            vals[st:st + cnt] = x
+            st_of = np.arange(32)                                            # every other lane: its own 1-row segment
+            st_of[st:st + cnt] = st
+            if st > 0:
+                st_of[:st] = 0                                               # a longer foreign segment right before ours
+            out = seg_scan(vals, st_of)[st + cnt - 1]
+            if ref is None:
+                ref = out
+            assert out.tobytes() == ref.tobytes(), (cnt, st)
+        assert abs(float(ref) - float(np.sum(x.astype(np.float64)))) <= 1e-5 * float(np.sum(np.abs(x)) + 1e-30)

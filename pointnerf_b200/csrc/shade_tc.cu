@@ -1297,10 +1297,12 @@ __global__ void __launch_bounds__(tc5::NTHR, 1) k_shade_tc5(ShadeTcParams p) {
 // v7: v5 with PACKED ROWS.  v5 gives every valid sample 8 rows (one per neighbour slot) although only 75 % of the slots
 // hold a neighbour on the lego frame (P_v / (8 S_v)): a quarter of every MMA multiplies zero rows.  Here a 128-row tile
 // is four 32-row quadrants (= the TMEM lane quarter of one warp), and each quadrant holds whole samples packed back to
-// back, only their valid neighbours (greedy packing in valid-sample order, k_pack_*): ~91 % of the rows carry a pair.
+// back, only their valid neighbours (first-fit packing with a 64-sample look-ahead, k_pack_*: the packed order is the
+// permutation `vorder`): 99.3 % of the rows carry a pair on the lego frame.
 // The K-reduction over the rows of a sample (1..8 consecutive lanes, never crossing a quadrant) is a segmented
 // warp-shuffle scan; its addition order depends on the neighbour count only, so a ray's colour is still independent of
-// which rays share the call.  Everything else (TMEM role ping-pong, chunk hand-off, weight ring, issuer) is v5.
+// which rays share the call.  Two builder threads per row and the last epilogue shared between the epilogue and the
+// builder warps (as v6); TMEM role ping-pong, chunk hand-off, weight ring and issuer are v5's.
 namespace tc7 {
 constexpr int NEPI_WARPS = 8, NGRP = NEPI_WARPS / 4, NCH = 16 / NGRP;
 constexpr int NEPI = NEPI_WARPS * 32, NBUILD = 256, NTHR = NEPI + NBUILD + 64;     // two builder threads per row (as v6)

@@ -47,7 +47,20 @@ def _worker(rank, world, port, R, ret):
             for i, c in enumerate((3, 32, 3, 3, 1)):
                 exp[i].append(torch.rand(n_new[g_], c, generator=g2))
         ok_grow = all(torch.equal(a, torch.cat(e, 0)) for a, e in zip(got, exp)) and got[0].shape[0] == sum(n_new)
-        ret[rank] = (ok_gather, ok_grad and ok_grow)
+        # sparse gradient exchange: each rank touched a few (overlapping) point rows
+        N, C = 50, 4
+        gs = torch.Generator().manual_seed(7)
+        dense = [torch.zeros(N, C) for _ in range(world)]
+        for g_ in range(world):
+            rows = torch.randperm(N, generator=gs)[:9 + 3 * g_]
+            dense[g_][rows] = torch.randn(len(rows), C, generator=gs)
+        mine = dense[rank].clone()[None]                              # the [1, N, C] shape of points_embeding.grad
+        n_rows = parallel.allreduce_rows_sparse(mine, world)
+        expect = dense[0].clone()
+        for g_ in range(1, world):
+            expect += dense[g_]                                       # same rank order -> bit-identical
+        ok_sparse = torch.equal(mine[0], expect) and n_rows == sum(int((d.abs().sum(1) > 0).sum()) for d in dense)
+        ret[rank] = (ok_gather, ok_grad and ok_grow and ok_sparse)
     finally:
         dist.destroy_process_group()
 

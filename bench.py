@@ -216,8 +216,7 @@ def main():
     ap.add_argument("--sr", type=int, default=24)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--precision", type=str, default="bf16x3", help="bf16x3 (tcgen05, default) | fp32 (CUDA cores)")
-    ap.add_argument("--color-version", type=int, default=2, help="colour kernel: 2 (pipelined, operand-format h-bar; default, needs --tc-version 5, 6 or 7) | 1")
-    ap.add_argument("--tc-version", type=int, default=7, help="tcgen05 pipeline variant: 7 (TMEM role ping-pong, rows packed to the valid pairs; default) | 5 (8 rows per sample) | 6 (v5 on CTA pairs, cta_group::2) | 3 | 2")
+    ap.add_argument("--frozen", type=int, default=1, help="1 (default): frozen-cloud pair kernel k_shade_tc8 (point-only layer-1 inputs hoisted per point) | 0: general kernel k_shade_tc7")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
@@ -236,7 +235,7 @@ def main():
 
     cfg = scene.CONFIGS["lego_render"]
     cfg.SR = args.sr
-    net, pts, opt = harness.build_model(cfg, dev, seed=0, alpha_bias=3.0, pnb_precision=args.precision, pnb_tc_version=args.tc_version, pnb_color_version=args.color_version)
+    net, pts, opt = harness.build_model(cfg, dev, seed=0, alpha_bias=3.0, pnb_precision=args.precision, pnb_frozen=args.frozen)
     full = scene.make_rays(cfg)
     R_img = full["raydir"].shape[1]
     # global batch = `world` images; ray i of the global batch belongs to rank i % world (interleaved)
@@ -335,13 +334,18 @@ def main():
         kname = "k_shade_fwd (fp32 CUDA-core kernel: pair MLPs + colour branch)"
         kflops = FLOPS_PER_PAIR * qc["n_pairs"] + FLOPS_PER_SAMPLE * qc["n_valid"]
     else:
-        def tc(mask):
-            _lib.check(l.pnb_shade_forward_tc(_lib.C.byref(q.desc), _lib.C.byref(ptsd), _lib.C.byref(mlp), net._mlp.packed.data_ptr(),
+        frozen = bool(net.frozen_ok)
+        pre_ptr = net._point_pre(mlp, ptsd, stream).data_ptr() if frozen else None
+
+        def tc(flags):
+            _lib.check(l.pnb_shade_forward_tc(_lib.C.byref(q.desc), _lib.C.byref(ptsd), _lib.C.byref(mlp), net._mlp.packed.data_ptr(), pre_ptr,
                                               _lib.C.byref(o), net._sigma_rgb.data_ptr(), net._tc_ws.data_ptr(), net._tc_ws.numel(),
-                                              net._max_valid, mask, net._err.data_ptr(), stream), "pnb_shade_forward_tc")
-        shade_avg = time_kernel(lambda: tc(1 | (net.tc_mask & (180 | 8 | (1 << 16) | (1 << 17)))))
-        color_avg = time_kernel(lambda: tc(2 | (net.tc_mask & (8 | 32 | 128 | (1 << 16) | (1 << 17)))))
-        kname = ("k_shade_tc7" if net.tc_mask & (1 << 17) else "k_shade_tc6" if net.tc_mask & 128 else "k_shade_tc5" if net.tc_mask & 32 else "k_shade_tc3" if net.tc_mask & 4 else "k_shade_tc") + " (tcgen05 BF16x3 pair MLPs 284-256-256 | 263-256-256 + alpha + K-reduction)"
+                                              net._max_valid, flags | (_lib.TC_FROZEN if frozen else 0), net._err.data_ptr(), stream),
+                       "pnb_shade_forward_tc")
+        shade_avg = time_kernel(lambda: tc(_lib.TC_PAIRS))
+        color_avg = time_kernel(lambda: tc(_lib.TC_COLOR))
+        kname = ("k_shade_tc8 (frozen cloud: layer-1 point inputs hoisted)" if frozen else "k_shade_tc7") + \
+            " + k_pack_* (tcgen05 BF16x3 pair MLPs 284-256-256 | 263-256-256 + alpha + K-reduction)"
         kflops = FLOPS_PER_PAIR * qc["n_pairs"]
         net.check_errors()
 
@@ -355,9 +359,9 @@ def main():
     pk = peaks()
     # DRAM traffic of the dominant kernel per launch, from the committed ncu --set full capture of this same command
     traffic = None
-    tfile = os.path.join(ROOT, "profiles", "r01_ncu_dram_traffic.json")
+    tfile = os.path.join(ROOT, "profiles", "r02_ncu_dram_traffic.json")
     if os.path.exists(tfile) and args.precision != "fp32" and world == 1 and args.sr == 24:
-        traffic = json.load(open(tfile)).get("k_shade_tc7" if net.tc_mask & (1 << 17) else "k_shade_tc6" if net.tc_mask & 128 else "k_shade_tc5" if net.tc_mask & 32 else "k_shade_tc3" if net.tc_mask & 4 else "", None)
+        traffic = json.load(open(tfile)).get("k_shade_tc8" if net.frozen_ok else "k_shade_tc7", None)
     flops = kflops
     achieved = flops / (shade_avg * 1e-3) / 1e12
     peak = pk["bf16_tflops"]
@@ -376,8 +380,8 @@ def main():
                                                candidate_samples=qc["n_cand"], occupied_voxels=gc["n_occ"], max_pts_per_voxel=gc["max_pts"])),
             e2e=dict(value=e2e_val, unit="Mrays/s", h2d_bytes_per_step=int(mine_host.numel() * 4 * world),
                      d2h_bytes_per_step=int(out_host.numel() * 4 * world), ms_per_step=ms_e2e / args.steps),
-            # + colour kernel (tcgen05 paths) + the 4 row-packing kernels of the v7 pair pipeline; cf. profiles/r01_ncu_launches_tc7_summary.txt
-            gpu_launches=(LAUNCHES_PER_STEP + (1 if args.precision != "fp32" else 0) + (4 if (args.precision != "fp32" and args.tc_version == 7) else 0)) * args.steps,
+            # + colour kernel + the 3 row-packing kernels of the tcgen05 path; cf. profiles/r02_ncu_launches_summary.txt
+            gpu_launches=(LAUNCHES_PER_STEP + (4 if args.precision != "fp32" else 0)) * args.steps,
             clocks=clocks,
             roofline=dict(bound="tensor", kernel=kname, achieved=achieved, peak=peak, unit="TFLOP/s",
                           frac=achieved / peak, traffic=traffic, peak_source="%s bf16 cuBLAS burst (MEASURED_PEAKS.json)" % pk["source"],

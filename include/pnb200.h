@@ -176,28 +176,35 @@ int pnb_composite_forward(const pnb_query_t* q, const pnb_shade_opts_t* opts, co
                           pnb_stream_t stream);
 
 /* ---- shading forward on the tensor cores (tcgen05 / TMEM, BF16x3 error-compensated split) ---- */
-/* Packs block1 / block3 weights of a pnb_mlp_t (fp32 W^T buffers) into tcgen05 operand images (hi/lo bf16, UMMA
+/* Packs block1 / block3 / colour-branch weights of a pnb_mlp_t (fp32 W^T buffers) into tcgen05 operand images (hi/lo bf16, UMMA
  * shared-memory layout).  Call once per weight version.  d_out: >= pnb_mlp_pack_bytes() bytes. */
 size_t pnb_mlp_pack_bytes(void);
 int pnb_mlp_pack(const pnb_mlp_t* mlp, void* d_out, size_t out_bytes, pnb_stream_t stream);
-/* Same contract as pnb_shade_forward; per-pair MLPs run as tcgen05.mma tiles, colour branch on CUDA cores.
- * mlp->w[5] must be zero padded to 288 rows.  ws >= pnb_shade_tc_bytes(max_valid_samples).  d_err: device int32,
- * 0 on success, 9 if the query produced more valid samples than max_valid_samples, any other non-zero value = an internal
- * pipeline time-out (a bounded 2-s mbarrier wait expired; results invalid in both cases).  >= 64 ints. */
+/* Frozen point cloud (rendering): the 224 point-only inputs [f, PE3(f)] of block1.0
+ * (models/aggregators/point_aggregators.py:547-571) are hoisted out of the per-pair work into a per-point table
+ * d_pre[N][256] = b1 + W1[:, :224] . [f_n, PE3(f_n)] (fp32).  Call once per (points_embeding, block1.0) version. */
+size_t pnb_point_pre_bytes(int N);
+int pnb_point_pre(const pnb_points_t* pts, const pnb_mlp_t* mlp, float* d_pre, size_t pre_bytes, pnb_stream_t stream);
+enum {
+    PNB_TC_PAIRS = 1,           /* row packing + per-pair MLPs + K-reduction -> h-bar, sigma */
+    PNB_TC_COLOR = 2,           /* colour branch -> sigma_rgb (both = a forward) */
+    PNB_TC_FROZEN = 4,          /* pair kernel of a frozen cloud (k_shade_tc8): needs d_point_pre */
+    PNB_TC_DBG_NO_WEIGHTS = 64  /* timing experiment: no weight traffic (garbage results) */
+    /* bits 8..15: profiling flags of tools/tc_profile.py (1024: per-CTA cycles into d_err[64..], needs a 512-int d_err) */
+};
+/* Same contract as pnb_shade_forward; the MLPs run as tcgen05.mma tiles.  mlp->w[5] must be zero padded to 288 rows.
+ * ws >= pnb_shade_tc_bytes(max_valid_samples).  d_err: device int32[>= 64], 0 on success, 9 if the query produced more valid
+ * samples than max_valid_samples (the extra samples are dropped: their sigma_rgb is zeroed, every other result is exact),
+ * any other non-zero value = an internal pipeline time-out (a bounded 2-s mbarrier wait expired; results invalid). */
 size_t pnb_shade_tc_bytes(int max_valid_samples);
 int pnb_shade_forward_tc(const pnb_query_t* q, const pnb_points_t* pts, const pnb_mlp_t* mlp, const void* d_packed,
-                         const pnb_shade_opts_t* opts, float* d_sigma_rgb, void* ws, size_t ws_bytes,
-                         int max_valid_samples,
-                         int stage_mask /* 1 pair MLPs, 2 colour branch (both = a forward); variant bits: +4 TS-form pair
-                                           pipeline (v3), +32 chunk-pipelined TMEM role ping-pong (v5), +128 the same on CTA
-                                           pairs / cta_group::2 (v6), +131072 the v5 pipeline with the rows packed to the valid
-                                           (sample, neighbour) pairs (v7, the default of the Python host); +8 colour branch on
-                                           tcgen05, +65536 pipelined colour kernel fed by operand-format h-bar (needs +8 and
-                                           one of +32 / +128 / +131072); diagnostics:
-                                           +64 no weight traffic (garbage results), bits 8..15 = profiling / experiment
-                                           flags of tools/tc_profile.py (256: cycle accounting of block 0 into d_err[2..],
-                                           1024: per-CTA cycles into d_err[64..], needs a 512-int d_err) */,
-                         int* d_err, pnb_stream_t stream);
+                         const float* d_point_pre /* NULL unless PNB_TC_FROZEN */, const pnb_shade_opts_t* opts,
+                         float* d_sigma_rgb, void* ws, size_t ws_bytes, int max_valid_samples, int flags, int* d_err,
+                         pnb_stream_t stream);
+/* Diagnostics / tests: device pointers of the row-packing tables inside a workspace laid out for max_valid_samples
+ * (vorder uint32[n_valid], vcntp uint8[n_valid], quad_first uint32[n_quads + 1], pack_cnt int32[1] = n_quads). */
+int pnb_shade_tc_tables(void* ws, size_t ws_bytes, int max_valid_samples, void** vorder, void** vcntp, void** quad_first,
+                        void** pack_cnt);
 
 /* ---- backward (per-scene optimisation batches) ----
  * Replaces loss.backward() through the reference's eager autograd graph
@@ -211,22 +218,6 @@ int pnb_shade_backward(const pnb_query_t* q, const pnb_points_t* pts, const pnb_
                        const float* d_sigma_rgb_fwd, const float* d_ray_color, int n_valid, float* d_emb, float* d_color,
                        float* d_dir, float* d_conf, float* const* d_mlp_w, float* const* d_mlp_b, void* ws,
                        size_t ws_bytes, pnb_stream_t stream);
-
-/* ---- diagnostics ---- */
-/* One-CTA tcgen05 self-test: D[128,N] = A[128,K] * W[N,K]^T with the BF16x3 split used by the fused kernel.
- * layout: 0 = interleaved core matrices, 4 = 64-byte swizzle.  d_err: device int, non-zero on a pipeline timeout. */
-int pnb_umma_selftest(const float* d_A, const float* d_W, float* d_D, int K, int N, int layout, int* d_err,
-                      pnb_stream_t stream);
-
-/* Micro-benchmark of the tcgen05.mma issue rate (M=128,N=256,K=16 bf16) on resident operands; d_out int64[2]. */
-int pnb_umma_bench(int layout, int mode, int iters, int bulk, const void* d_src, long long* d_out, int* d_err,
-                   pnb_stream_t stream);
-
-/* CTA-pair (cluster of 2, tcgen05 cta_group::2) self-test and MMA-rate probe: D[256,N] = A[256,K] * W[N,K]^T.
- * mode 0: A operand in shared memory, 1: in tensor memory.  bench_iters > 0: d_out int64[2] (issue / total cycles);
- * bench_flags: bits 0-7 interleave a tcgen05.commit every n MMAs, bits 8-9 its form (see umma_selftest.cu). */
-int pnb_umma_selftest2(const float* d_A, const float* d_W, float* d_D, int K, int N, int mode, int bench_iters,
-                       int bench_flags, long long* d_out, int* d_err, pnb_stream_t stream);
 
 #ifdef __cplusplus
 }

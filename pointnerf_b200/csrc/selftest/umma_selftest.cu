@@ -4,8 +4,25 @@
 // from fp32 inputs, operands staged in shared memory in the selected K-major layout.  tests/test_gpu_umma.py
 // compares D against an fp32/fp64 matmul: this pins descriptors, layouts, TMEM addressing and the split
 // accuracy on the real hardware before the big kernel depends on them.
-#include "common.cuh"
-#include "umma.cuh"
+//
+// TEST-ONLY library (libpnb200_selftest.so): these entry points are not part of the product ABI (include/pnb200.h); they are
+// declared in pnb200_selftest.h next to this file and used by tests/test_gpu_umma.py and tools/umma_*.py.
+#include <stdarg.h>
+
+#include "../common.cuh"
+#include "../umma.cuh"
+#include "pnb200_selftest.h"
+
+namespace pnb {
+static thread_local char g_selftest_err[512] = "";
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_selftest_err, sizeof(g_selftest_err), fmt, ap);
+    va_end(ap);
+}
+}  // namespace pnb
+extern "C" const char* pnb_selftest_last_error(void) { return pnb::g_selftest_err; }
 
 namespace pnb {
 using namespace umma;

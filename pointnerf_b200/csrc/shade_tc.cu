@@ -1,21 +1,23 @@
 // Fused per-pair shading on the 5th-generation tensor cores (tcgen05 + TMEM), sm_100a.
 //
 //   gather + weights + positional encoding  ->  block1 (284->256->256)  ->  cat extras  ->  block3 (263->256->256)
-//   ->  alpha branch + K-reduction  (reference: /root/reference/models/aggregators/point_aggregators.py:488-628,
-//   727-814; gather /root/reference/models/neural_points/neural_points.py:706-717)
+//   ->  alpha branch + K-reduction  ->  colour branch (280->128->128->128->3)
+//   (reference: /root/reference/models/aggregators/point_aggregators.py:488-644, 727-814; gather
+//   /root/reference/models/neural_points/neural_points.py:706-717)
 //
-// One persistent CTA per SM; a tile is 16 valid samples x 8 neighbour slots = 128 (sample,k) pair rows = UMMA M.
-// Every layer is D[128x256] = A[128xK] * W[256xK]^T on tcgen05.mma (kind::f16, BF16 operands, FP32 accumulate in
-// TMEM).  The reference computes these layers in fp32 (cuBLAS SGEMM, TF32 off) and the parity bar is 1e-4 on the
-// rendered radiance, which a single BF16/TF32 pass misses -> error-compensated split:
+// Kernels of this file (one persistent CTA per SM each):
+//   k_pack_*      row packing: the valid (sample, neighbour) pairs -> 32-row quadrants of 128-row MMA tiles (first fit)
+//   k_shade_tc7   pair MLPs, every layer D[128x256] = A[128xK] * W[256xK]^T on tcgen05.mma (kind::f16, BF16 operands, FP32
+//                 accumulate in TMEM), TMEM role ping-pong between layers, K-reduction, writes h-bar + sigma
+//   k_shade_tc8   the same for a FROZEN point cloud (render): the 224 point-only inputs of block1.0 are hoisted into a
+//                 per-point table (k_point_pre), layer 1 runs on the 64 sample-dependent inputs only
+//   k_color_tc2   colour branch per 128 valid samples, fed by h-bar in its own operand format (one bulk copy per tile)
+// The reference computes these layers in fp32 (cuBLAS SGEMM, TF32 off) and the parity bar is 1e-4 on the rendered
+// radiance, which a single BF16/TF32 pass misses -> error-compensated split:
 //   A = A_hi + A_lo, W = W_hi + W_lo (bf16 each);   D = A_hi*W_hi + A_lo*W_hi + A_hi*W_lo    (3 MMAs per k-step)
-// Warp roles (320 threads):
-//   warps 0-7  workers : build the layer-1 operand (gather, PE, split) and run the epilogues
-//                        (tcgen05.ld -> bias -> LeakyReLU -> split -> next layer's A operand in shared memory)
-//   warp  8    loader  : streams the pre-packed weight images (16 KB each, already in the UMMA operand layout)
-//                        L2 -> shared memory with cp.async.bulk (TMA engine) through a 4-deep mbarrier ring
-//   warp  9    issuer  : one elected thread issues tcgen05.mma and commits to mbarriers
-// A-operand: 9 K-blocks of [128 x 32] bf16 (hi and lo), interleaved core-matrix layout (see umma.cuh).
+// Weight images are pre-packed in the UMMA operand layout (pnb_mlp_pack) and streamed L2 -> shared memory with cp.async.bulk
+// (TMA engine) through an mbarrier ring.  Earlier pipeline generations (v2 serialized, v3 TS form, v5 unpacked rows, v6 CTA
+// pairs / cta_group::2, CUDA-core colour branch) were removed in round 2; their measurements stay in profiles/r01_* and DESIGN.md.
 #include "common.cuh"
 #include "umma.cuh"
 
@@ -25,10 +27,6 @@ using namespace umma;
 namespace tc {
 constexpr int LAYOUT = LAYOUT_NONE;
 constexpr int TM = 128;                 // pair rows per tile
-constexpr int TSAMP = TM / PNB_MAX_K;   // 16 samples per tile
-constexpr int NWORK = 256;              // worker threads
-constexpr int NTHR = 320;
-constexpr int NSTAGE = 4;
 constexpr int IMG = 256 * 64;           // bytes of one weight image ([256 x 32] bf16)
 constexpr int ABLK = 128 * 64;          // bytes of one A block ([128 x 32] bf16)
 constexpr int NKB_MAX = 9;
@@ -37,21 +35,8 @@ __host__ __device__ constexpr int img_base(int l) { return l == 0 ? 0 : l == 1 ?
 constexpr int NBLK_TOTAL = 34;
 constexpr int IMGS_PER_TILE = 2 * NBLK_TOTAL;
 constexpr float LEAKY = 0.01f;
-
-struct Smem {
-    unsigned char a_hi[NKB_MAX * ABLK];
-    unsigned char a_lo[NKB_MAX * ABLK];
-    unsigned char b[NSTAGE][IMG];
-    float bias[4][256];
-    float wa[256];
-    float E[TM][8];
-    float wc[TM];
-    float alpha_part[2][TM];
-    uint32_t samp[TSAMP];
-    uint64_t bar_full[NSTAGE], bar_empty[NSTAGE], bar_a_ready, bar_acc_full;
-    uint32_t tmem_base;
-    int abort;
-};
+constexpr int XE = 128 * 32;            // bytes of one [128 x 16] bf16 extras operand (LBO = 128, SBO = 256)
+__device__ __forceinline__ uint32_t xe_offset(int r, int k) { return (uint32_t)((r >> 3) * 256 + (k >> 3) * 128 + (r & 7) * 16 + (k & 7) * 2); }
 }  // namespace tc
 
 struct ShadeTcParams {
@@ -72,6 +57,7 @@ struct ShadeTcParams {
     const uint32_t* vorder;      // v7: valid-sample index of every packed position [n_valid]
     const uint32_t* quad_first;  // v7: first valid sample of every 32-row quadrant [n_quads + 1]
     const int* pack_cnt;         // v7: [0] = n_quads
+    const float* pre;            // v8: per-point hoisted layer-1 pre-activation [N][256] (k_point_pre)
     int hbar_fmt;                // 0: hbar[n_valid][256] fp32;  1: bf16 hi/lo A-operand blocks of k_color_tc2 (per 128 samples: 8 K blocks x {hi,lo} x [128x32])
 };
 __device__ __forceinline__ void prof_add(const ShadeTcParams& p, int slot, long long cyc) {
@@ -110,344 +96,6 @@ __device__ __forceinline__ void pe_doubling(float x, float* out) {
         out[2 * j] = s; out[2 * j + 1] = c;
     }
 }
-
-// 8 consecutive K elements (one 16-byte chunk) of row r, block kb, starting at k8 (multiple of 8) -> hi / lo buffers
-__device__ __forceinline__ void store_chunk8(tc::Smem& sm, int r, int kb, int k8, const float* v) {
-    uint32_t h[4], l[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) split_bf16x2(v[2 * i], v[2 * i + 1], h[i], l[i]);
-    uint32_t off = (uint32_t)kb * tc::ABLK + tile_offset_bytes<tc::LAYOUT>(r, k8);
-    *reinterpret_cast<uint4*>(sm.a_hi + off) = make_uint4(h[0], h[1], h[2], h[3]);
-    *reinterpret_cast<uint4*>(sm.a_lo + off) = make_uint4(l[0], l[1], l[2], l[3]);
-}
-
-__global__ void __launch_bounds__(tc::NTHR, 1) k_shade_tc(ShadeTcParams p) {
-    using namespace tc;
-    extern __shared__ __align__(1024) unsigned char smem_raw[];
-    Smem& sm = *reinterpret_cast<Smem*>(smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u));
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const pnb_query_t& q = p.q;
-    const int n_valid = min(q.counters[PNB_QC_N_VALID], p.hbar_cap);
-    const int n_tiles = (n_valid + TSAMP - 1) / TSAMP;
-    const int my_tiles = n_tiles > (int)blockIdx.x ? (n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
-
-    // ---------------------------------------------------------------- one-time setup
-    if (tid == 0) {
-        for (int s = 0; s < NSTAGE; ++s) { mbar_init(&sm.bar_full[s], 1); mbar_init(&sm.bar_empty[s], 1); }
-        mbar_init(&sm.bar_a_ready, NWORK);
-        mbar_init(&sm.bar_acc_full, 1);
-        sm.abort = 0;
-        mbar_fence_init();
-        if (blockIdx.x == 0 && q.counters[PNB_QC_N_VALID] > p.hbar_cap) atomicExch(p.err, 9);   // capacity exceeded
-    }
-    if (warp == 9) tmem_alloc<256>(&sm.tmem_base);
-    for (int i = tid; i < 4 * 256; i += NTHR) sm.bias[i >> 8][i & 255] = p.bias[i >> 8][i & 255];
-    for (int i = tid; i < 256; i += NTHR) sm.wa[i] = p.wa[i];
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tacc = sm.tmem_base;
-
-    if (warp == 8) {
-        // ============================================================ loader
-        if (lane == 0) {
-            const uint32_t total = (uint32_t)my_tiles * IMGS_PER_TILE;
-            for (uint32_t n = 0; n < total; ++n) {
-                const uint32_t s = n % NSTAGE, ph = (n / NSTAGE) & 1u;
-                if (!mbar_wait(&sm.bar_empty[s], ph ^ 1u, p.err, 1)) break;
-                mbar_arrive_expect_tx(&sm.bar_full[s], IMG);
-                bulk_g2s(sm.b[s], p.wimg + (size_t)(n % IMGS_PER_TILE) * IMG, IMG, &sm.bar_full[s]);
-            }
-        }
-    } else if (warp == 9) {
-        // ============================================================ MMA issuer
-        if (lane == 0) {
-            const uint32_t idesc = make_idesc_bf16(128, 256);
-            uint32_t n = 0, lyr = 0;
-            bool ok = true;
-            for (int t = 0; t < my_tiles && ok; ++t) {
-                for (int l = 0; l < 4 && ok; ++l, ++lyr) {
-                    if (!mbar_wait(&sm.bar_a_ready, lyr & 1u, p.err, 2)) { ok = false; break; }
-                    tc_fence_after();
-                    const int nkb = nkb_of(l);
-                    for (int kb = 0; kb < nkb && ok; ++kb) {
-                        const int nks = (l == 2 && kb == 8) ? 1 : 2;   // block3 input: 263 -> 272 columns used
-                        {   // W_hi image: A_hi*W_hi + A_lo*W_hi
-                            const uint32_t s = n % NSTAGE, ph = (n / NSTAGE) & 1u;
-                            if (!mbar_wait(&sm.bar_full[s], ph, p.err, 3)) { ok = false; break; }
-                            tc_fence_after();
-                            for (int ks = 0; ks < nks; ++ks) {
-                                const uint32_t adv = kstep_advance_bytes<LAYOUT>(ks);
-                                const uint64_t db = make_smem_desc<LAYOUT>(smem_u32(sm.b[s]) + adv);
-                                mma_ss(tacc, make_smem_desc<LAYOUT>(smem_u32(sm.a_hi + kb * ABLK) + adv), db, idesc, (kb | ks) ? 1u : 0u);
-                                mma_ss(tacc, make_smem_desc<LAYOUT>(smem_u32(sm.a_lo + kb * ABLK) + adv), db, idesc, 1u);
-                            }
-                            mma_commit(&sm.bar_empty[s]);
-                            ++n;
-                        }
-                        {   // W_lo image: A_hi*W_lo
-                            const uint32_t s = n % NSTAGE, ph = (n / NSTAGE) & 1u;
-                            if (!mbar_wait(&sm.bar_full[s], ph, p.err, 4)) { ok = false; break; }
-                            tc_fence_after();
-                            for (int ks = 0; ks < nks; ++ks) {
-                                const uint32_t adv = kstep_advance_bytes<LAYOUT>(ks);
-                                mma_ss(tacc, make_smem_desc<LAYOUT>(smem_u32(sm.a_hi + kb * ABLK) + adv),
-                                       make_smem_desc<LAYOUT>(smem_u32(sm.b[s]) + adv), idesc, 1u);
-                            }
-                            mma_commit(&sm.bar_empty[s]);
-                            ++n;
-                        }
-                    }
-                    mma_commit(&sm.bar_acc_full);
-                }
-            }
-        }
-    } else {
-        // ============================================================ workers (warps 0..7)
-        const int quad = warp & 3, half = warp >> 2;
-        const int erow = quad * 32 + lane;                 // epilogue row = TMEM lane
-        const uint32_t tlane = (uint32_t)(quad * 32) << 16;
-        uint32_t lyr = 0;
-        bool ok = true;
-        for (int t = 0; t < my_tiles && ok; ++t) {
-            const int tile = (int)blockIdx.x + t * (int)gridDim.x;
-            // ------------------------------------------------ build the block1 operand: 2 threads per pair row
-            {
-                const int row = warp * 16 + (lane >> 1), hf = lane & 1;
-                const int si = row >> 3, k = row & 7;
-                const int vi = tile * TSAMP + si;
-                uint32_t s = 0xffffffffu;
-                int pidx = -1;
-                float lx = 0.f, ly = 0.f, lz = 0.f, vx = 0.f, vy = 0.f, vz = 0.f;
-                if (vi < n_valid) {
-                    s = q.valid_list[vi];
-                    uint32_t pk = q.samp_ray[s];
-                    int r = (int)(pk >> 7), j = (int)(pk & 127u);
-                    int d = q.steps[(size_t)r * q.SR + j];
-                    float tt = q.t[(size_t)r * q.t_ray_stride + d];
-                    vx = q.raydir[3 * r]; vy = q.raydir[3 * r + 1]; vz = q.raydir[3 * r + 2];
-                    lx = raypos1(q.campos[0], vx, tt); ly = raypos1(q.campos[1], vy, tt); lz = raypos1(q.campos[2], vz, tt);
-                    if (k < q.K) pidx = q.cand_pidx[(size_t)s * q.K + k];
-                }
-                if ((lane & 15) == 0) sm.samp[si] = s;
-                const bool valid = pidx >= 0;
-                const int pi = valid ? pidx : 0;
-                float ovx, ovy, ovz;
-                rot3t(p.o.Rw2c, vx, vy, vz, ovx, ovy, ovz);
-                float px = __ldg(&p.pts.xyz[3 * pi]), py = __ldg(&p.pts.xyz[3 * pi + 1]), pz = __ldg(&p.pts.xyz[3 * pi + 2]);
-                float dist[6];
-                dist[0] = px - lx; dist[1] = py - ly; dist[2] = pz - lz;
-                float xpp, ypp, zpp, xsp, ysp, zsp;
-                w2pers_t(p.o, px, py, pz, xpp, ypp, zpp);
-                w2pers_t(p.o, lx, ly, lz, xsp, ysp, zsp);
-                dist[3] = xpp * zpp - xsp * zsp;
-                dist[4] = ypp * zpp - ysp * zsp;
-                dist[5] = zpp - zsp;
-                float nrm = sqrtf(dist[0] * dist[0] + dist[1] * dist[1] + dist[2] * dist[2]);
-                float w = valid ? 1.0f / fmaxf(nrm, 1e-6f) : 0.f;
-                float wsum = hf == 0 ? w : 0.f;   // the 16 lanes of one sample: sum over its 8 rows
-                wsum += __shfl_xor_sync(0xffffffffu, wsum, 1);
-                wsum += __shfl_xor_sync(0xffffffffu, wsum, 2);
-                wsum += __shfl_xor_sync(0xffffffffu, wsum, 4);
-                wsum += __shfl_xor_sync(0xffffffffu, wsum, 8);
-                w = w / fmaxf(wsum, 1e-8f);
-                float cf = __ldg(&p.pts.conf[pi]);
-                float cc = fminf(fmaxf(cf, 1e-4f), 1.0f);
-                if (hf == 0) sm.wc[row] = valid ? w * cc : 0.f;
-                float d0, d1, d2;
-                rot3t(p.o.Rw2c, dist[0], dist[1], dist[2], d0, d1, d2);
-                dist[0] = d0; dist[1] = d1; dist[2] = d2;
-                if (valid) {
-                    // raw features hf*16 .. +15 -> columns hf*16.. ; their PE -> columns 32 + 96*hf .. +95
-                    const float4* ep = (const float4*)&p.pts.emb[(size_t)pi * PNB_FEAT + hf * 16];
-                    float f[16];
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        float4 v = __ldg(ep + i);
-                        f[4 * i] = v.x; f[4 * i + 1] = v.y; f[4 * i + 2] = v.z; f[4 * i + 3] = v.w;
-                    }
-                    store_chunk8(sm, row, 0, hf * 16, f);
-                    store_chunk8(sm, row, 0, hf * 16 + 8, f + 8);
-#pragma unroll
-                    for (int g = 0; g < 4; ++g) {      // 4 features -> 24 PE values -> 3 chunks
-                        float pe[24];
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) pe_doubling<3>(f[g * 4 + e], pe + e * 6);
-                        const int col = 32 + 96 * hf + 24 * g;    // multiple of 8
-#pragma unroll
-                        for (int c = 0; c < 3; ++c) {
-                            int cc0 = col + 8 * c;
-                            store_chunk8(sm, row, cc0 >> 5, cc0 & 31, pe + 8 * c);
-                        }
-                    }
-                    // distance PE: index i = d*5 + j -> columns 224 + 2i ; thread hf covers i in [16*hf, 16*hf+16):
-                    // hf 0: d = 0,1,2 (+ d=3, j=0) ; hf 1: d = 3 (j>=1), 4, 5 ; 32 values each (4 zeros pad hf 1)
-                    {
-                        float dp[30];   // 3 distances x 10 values
-                        const int dbase = hf * 3;
-#pragma unroll
-                        for (int e = 0; e < 3; ++e) pe_doubling<5>(dist[dbase + e], dp + 10 * e);
-                        float vals[32];
-                        if (hf == 0) {
-#pragma unroll
-                            for (int i = 0; i < 30; ++i) vals[i] = dp[i];
-                            float sn, cs;
-                            sincosf(dist[3], &sn, &cs);
-                            vals[30] = sn; vals[31] = cs;
-                        } else {
-                            // i = 16..29 -> (d=3, j=1..4), (d=4, j=0..4), (d=5, j=0..4): dp holds d=3,4,5
-#pragma unroll
-                            for (int i = 0; i < 28; ++i) vals[i] = dp[2 + i];
-                            vals[28] = 0.f; vals[29] = 0.f; vals[30] = 0.f; vals[31] = 0.f;
-                        }
-#pragma unroll
-                        for (int c = 0; c < 4; ++c) {
-                            int cc0 = 224 + 32 * hf + 8 * c;
-                            store_chunk8(sm, row, cc0 >> 5, cc0 & 31, vals + 8 * c);
-                        }
-                    }
-                    if (hf == 1) {
-                        float cr = __ldg(&p.pts.color[3 * pi]), cg = __ldg(&p.pts.color[3 * pi + 1]), cb = __ldg(&p.pts.color[3 * pi + 2]);
-                        float ddx, ddy, ddz;
-                        rot3t(p.o.Rw2c, __ldg(&p.pts.dir[3 * pi]), __ldg(&p.pts.dir[3 * pi + 1]), __ldg(&p.pts.dir[3 * pi + 2]), ddx, ddy, ddz);
-                        sm.E[row][0] = cr; sm.E[row][1] = cg; sm.E[row][2] = cb;
-                        sm.E[row][3] = ddx - ovx; sm.E[row][4] = ddy - ovy; sm.E[row][5] = ddz - ovz;
-                        sm.E[row][6] = ddx * ovx + ddy * ovy + ddz * ovz;
-                        sm.E[row][7] = 0.f;
-                    }
-                } else {
-                    float z8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-                    for (int c = hf; c < 36; c += 2) store_chunk8(sm, row, c >> 2, (c & 3) * 8, z8);   // 288 columns
-                    if (hf == 1)
-                        for (int e = 0; e < 8; ++e) sm.E[row][e] = 0.f;
-                }
-            }
-            fence_proxy_async();
-            mbar_arrive(&sm.bar_a_ready);
-
-            // ------------------------------------------------ 4 layers: epilogues
-            for (int l = 0; l < 4 && ok; ++l, ++lyr) {
-                if (!mbar_wait(&sm.bar_acc_full, lyr & 1u, p.err, 5)) { ok = false; break; }
-                tc_fence_after();
-                float apart = 0.f;
-                if (l < 3) {
-#pragma unroll 1
-                    for (int ch = 0; ch < 4; ++ch) {
-                        const int c0 = half * 128 + ch * 32;
-                        uint32_t v[32];
-                        tmem_ld32(tacc + tlane + (uint32_t)c0, v);
-                        tmem_ld_wait();
-#pragma unroll
-                        for (int g = 0; g < 4; ++g) {
-                            float x[8];
-#pragma unroll
-                            for (int e = 0; e < 8; ++e) {
-                                float y = __uint_as_float(v[g * 8 + e]) + sm.bias[l][c0 + g * 8 + e];
-                                x[e] = fmaxf(y, LEAKY * y);
-                            }
-                            store_chunk8(sm, erow, c0 >> 5, g * 8, x);
-                        }
-                    }
-                    if (l == 1 && half == 0) {   // block3 extras -> columns 256..271 (zero padded)
-                        float e0[8], e1[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-                        for (int e = 0; e < 8; ++e) e0[e] = sm.E[erow][e];
-                        store_chunk8(sm, erow, 8, 0, e0);
-                        store_chunk8(sm, erow, 8, 8, e1);
-                    }
-                    tc_fence_before();
-                    fence_proxy_async();
-                    mbar_arrive(&sm.bar_a_ready);
-                } else {
-                    // last layer: h stays in registers; alpha branch + weighted K-reduction
-                    const float wrow = sm.wc[erow];
-                    const int sidx = tile * TSAMP + (erow >> 3);
-                    const bool swrite = sidx < n_valid;
-#pragma unroll 1
-                    for (int ch = 0; ch < 4; ++ch) {
-                        const int c0 = half * 128 + ch * 32;
-                        uint32_t v[32];
-                        tmem_ld32(tacc + tlane + (uint32_t)c0, v);
-                        tmem_ld_wait();
-                        float mine[4];
-#pragma unroll
-                        for (int e = 0; e < 32; ++e) {
-                            float y = __uint_as_float(v[e]) + sm.bias[3][c0 + e];
-                            y = fmaxf(y, LEAKY * y);
-                            apart = fmaf(y, sm.wa[c0 + e], apart);
-                            float z = y * wrow;
-                            z += __shfl_xor_sync(0xffffffffu, z, 1);
-                            z += __shfl_xor_sync(0xffffffffu, z, 2);
-                            z += __shfl_xor_sync(0xffffffffu, z, 4);
-                            if ((e & 7) == (lane & 7)) mine[e >> 3] = z;
-                        }
-                        if (swrite) {
-                            float* dst = p.hbar + (size_t)sidx * 256 + c0 + (lane & 7);
-#pragma unroll
-                            for (int g = 0; g < 4; ++g) dst[8 * g] = mine[g];
-                        }
-                    }
-                    tc_fence_before();
-                    sm.alpha_part[half][erow] = apart;
-                    named_bar_sync(1, NWORK);
-                    if (half == 0) {
-                        float a = sm.alpha_part[0][erow] + sm.alpha_part[1][erow] + __ldg(p.ba) - 1.0f;
-                        float sp = a > 20.f ? a : log1pf(expf(a));
-                        float z = sp * wrow;
-                        z += __shfl_xor_sync(0xffffffffu, z, 1);
-                        z += __shfl_xor_sync(0xffffffffu, z, 2);
-                        z += __shfl_xor_sync(0xffffffffu, z, 4);
-                        if ((lane & 7) == 0 && swrite) p.sigma[sidx] = z;
-                    }
-                    named_bar_sync(1, NWORK);   // alpha_part / wc / E are reused by the next tile's build
-                }
-            }
-        }
-    }
-    // ---------------------------------------------------------------- teardown
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 9) tmem_dealloc<256>(tacc);
-}
-
-// =====================================================================================================================
-// v3: layers 2-4 read their A operand from TENSOR MEMORY (tcgen05.mma TS form) so the shared-memory operand buffer
-// is only needed by layer 1 -> dedicated builder warps construct the NEXT tile's layer-1 operand while the tensor
-// core runs layers 2-4 of the current tile.  TMEM: accumulator cols 0..255, A_hi 256..383, A_lo 384..511 (two bf16
-// per 32-bit column).  Warp roles (448 threads): 0-7 epilogue (TMEM -> bias/LeakyReLU/split -> TMEM), 8-11 builders,
-// 12 loader, 13 issuer.  The 7 block3 extras go through a small [128 x 16] shared-memory operand (one SS k-step).
-// Optional in-kernel cycle accounting (block 0 only): err[2 + 2*i], 64-bit counters, see tools/tc_profile.py
-// Enabled by dbg_flags bit 0 (tools/tc_profile.py), a kernel parameter: the clock reads and atomics slow block 0 down by
-// several per cent, and a persistent kernel is as slow as its slowest CTA.
-#define PNB_TIMED_WAIT_L0(slot, expr) [&]() { long long _t0 = clock64(); bool _r = (expr); if ((threadIdx.x & 31) == 0) prof_add(p, slot, clock64() - _t0); return _r; }()
-#define PNB_TIMED_WAIT(slot, expr) [&]() { long long _t0 = clock64(); bool _r = (expr); prof_add(p, slot, clock64() - _t0); return _r; }()
-
-namespace tc3 {
-constexpr int NEPI_WARPS = 16, NEPI = NEPI_WARPS * 32, NBUILD = 128, NTHR = NEPI + NBUILD + 64;   // 704 threads
-constexpr int NSTAGE = 4;
-constexpr int XE = 128 * 32;            // bytes of one [128 x 16] bf16 extras operand (SBO = 256)
-struct Smem {
-    static constexpr int NWC = 2;
-    unsigned char a_hi[tc::NKB_MAX * tc::ABLK];
-    unsigned char a_lo[tc::NKB_MAX * tc::ABLK];
-    unsigned char b[NSTAGE][tc::IMG];
-    unsigned char xe_hi[2][XE];
-    unsigned char xe_lo[2][XE];
-    float wc[2][tc::TM];
-    float alpha_part[2][tc::TM];
-    uint64_t bar_full[NSTAGE], bar_empty[NSTAGE], bar_a1_ready, bar_a1_free, bar_acc_full, bar_at_ready;
-    uint32_t tmem_base;
-};
-__device__ __forceinline__ uint32_t xe_offset(int r, int k) { return (uint32_t)((r >> 3) * 256 + (k >> 3) * 128 + (r & 7) * 16 + (k & 7) * 2); }
-__device__ __forceinline__ uint64_t xe_desc(uint32_t addr) {
-    uint64_t d = 0;
-    d |= (uint64_t)((addr >> 4) & 0x3fff);
-    d |= (uint64_t)(128 >> 4) << 16;    // LBO: next 8-column chunk
-    d |= (uint64_t)(256 >> 4) << 32;    // SBO: next 8-row group
-    d |= (uint64_t)1 << 46;
-    return d;                           // layout type 0 (interleaved)
-}
-}  // namespace tc3
 
 template <class SmemT>
 __device__ __forceinline__ void store_chunk8_a1(SmemT& sm, int r, int kb, int k8, const float* v) {
@@ -489,7 +137,7 @@ __device__ __forceinline__ void build_pair_part(SmemT& sm, const ShadeTcParams& 
     constexpr int G_LO = P0 ? 0 : 5, G_HI = P1 ? 8 : 5;      // feature groups (4 features each) whose PE this part builds
     const pnb_query_t& q = p.q;
     const int k = PACKED ? pk : (row & 7);
-    const int vi = PACKED ? pvi : tile * TSAMP + (row >> 3);
+    const int vi = PACKED ? pvi : tile * (TM / PNB_MAX_K) + (row >> 3);
     int pidx = -1;
     float lx = 0.f, ly = 0.f, lz = 0.f, vx = 0.f, vy = 0.f, vz = 0.f;
     if (vi >= 0 && vi < n_valid) {
@@ -578,249 +226,13 @@ __device__ __forceinline__ void build_pair_part(SmemT& sm, const ShadeTcParams& 
         uint32_t h[4], l[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) split_bf16x2(ex[2 * i], ex[2 * i + 1], h[i], l[i]);
-        uint32_t off = tc3::xe_offset(row, 0);
+        uint32_t off = tc::xe_offset(row, 0);
         *reinterpret_cast<uint4*>(sm.xe_hi[t & 1] + off) = make_uint4(h[0], h[1], h[2], h[3]);
         *reinterpret_cast<uint4*>(sm.xe_lo[t & 1] + off) = make_uint4(l[0], l[1], l[2], l[3]);
         *reinterpret_cast<uint4*>(sm.xe_hi[t & 1] + off + 128) = make_uint4(0u, 0u, 0u, 0u);
         *reinterpret_cast<uint4*>(sm.xe_lo[t & 1] + off + 128) = make_uint4(0u, 0u, 0u, 0u);
     }
 }
-template <class SmemT>
-__device__ __forceinline__ void build_pair_row(SmemT& sm, const ShadeTcParams& p, int tile, int t, int row, int n_valid) {
-    build_pair_part<2, false>(sm, p, tile, t, row, n_valid);
-}
-
-__global__ void __launch_bounds__(tc3::NTHR, 1) k_shade_tc3(ShadeTcParams p) {
-    using namespace tc;
-    extern __shared__ __align__(1024) unsigned char smem_raw[];
-    tc3::Smem& sm = *reinterpret_cast<tc3::Smem*>(smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u));
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const pnb_query_t& q = p.q;
-    const int n_valid = min(q.counters[PNB_QC_N_VALID], p.hbar_cap);
-    const int n_tiles = (n_valid + TSAMP - 1) / TSAMP;
-    const int my_tiles = n_tiles > (int)blockIdx.x ? (n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
-
-    if (tid == 0) {
-        for (int s = 0; s < tc3::NSTAGE; ++s) { mbar_init(&sm.bar_full[s], 1); mbar_init(&sm.bar_empty[s], 1); }
-        mbar_init(&sm.bar_a1_ready, tc3::NBUILD);
-        mbar_init(&sm.bar_a1_free, 1);
-        mbar_init(&sm.bar_acc_full, 1);
-        mbar_init(&sm.bar_at_ready, tc3::NEPI);
-        mbar_fence_init();
-        if (blockIdx.x == 0 && q.counters[PNB_QC_N_VALID] > p.hbar_cap) atomicExch(p.err, 9);
-    }
-    constexpr int W_BUILD = tc3::NEPI_WARPS, W_LOAD = W_BUILD + 4, W_ISSUE = W_LOAD + 1;
-    if (warp == W_ISSUE) tmem_alloc<512>(&sm.tmem_base);
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tacc = sm.tmem_base;
-    const uint32_t t_ahi = tacc + 256u, t_alo = tacc + 384u;
-    const long long _tk0 = clock64();
-
-    if (warp == W_LOAD) {
-        // ============================================================ loader
-        if (lane == 0) {
-            const uint32_t total = (uint32_t)my_tiles * IMGS_PER_TILE;
-            for (uint32_t n = 0; n < total; ++n) {
-                const uint32_t s = n % tc3::NSTAGE, ph = (n / tc3::NSTAGE) & 1u;
-                if (!PNB_TIMED_WAIT(0, mbar_wait(&sm.bar_empty[s], ph ^ 1u, p.err, 11))) break;
-                if (p.dbg_no_weights) { mbar_arrive(&sm.bar_full[s]); continue; }
-                mbar_arrive_expect_tx(&sm.bar_full[s], IMG);
-                bulk_g2s(sm.b[s], p.wimg + (size_t)(n % IMGS_PER_TILE) * IMG, IMG, &sm.bar_full[s]);
-            }
-        }
-    } else if (warp == W_ISSUE) {
-        // ============================================================ MMA issuer (lean: ~15 instructions per MMA)
-        if (lane == 0) {
-            const uint32_t idesc = make_idesc_bf16(128, 256);
-            const uint32_t hiw = desc_hi<LAYOUT>(), xe_hiw = (256u >> 4) | (1u << 14);
-            const uint32_t b0_lo = desc_lo<LAYOUT>(smem_u32(sm.b[0]));
-            const uint32_t ahi_lo = desc_lo<LAYOUT>(smem_u32(sm.a_hi)), alo_lo = desc_lo<LAYOUT>(smem_u32(sm.a_lo));
-            const uint32_t xeh_lo0 = desc_lo<LAYOUT_NONE>(smem_u32(sm.xe_hi[0])), xel_lo0 = desc_lo<LAYOUT_NONE>(smem_u32(sm.xe_lo[0]));
-            constexpr uint32_t KADV = kstep_adv16<LAYOUT>();
-            uint32_t n = 0, n_at = 0;
-            bool ok = true;
-            for (int t = 0; t < my_tiles && ok; ++t) {
-                const uint32_t xeh_lo = xeh_lo0 + (uint32_t)(t & 1) * (tc3::XE >> 4), xel_lo = xel_lo0 + (uint32_t)(t & 1) * (tc3::XE >> 4);
-                for (int l = 0; l < 4 && ok; ++l) {
-                    if (l == 0) {
-                        if (!PNB_TIMED_WAIT(1, mbar_wait(&sm.bar_a1_ready, (uint32_t)t & 1u, p.err, 12))) { ok = false; break; }
-                        if (t > 0) { if (!PNB_TIMED_WAIT(2, mbar_wait(&sm.bar_at_ready, n_at & 1u, p.err, 13))) { ok = false; break; } ++n_at; }
-                    } else {
-                        if (!PNB_TIMED_WAIT(2, mbar_wait(&sm.bar_at_ready, n_at & 1u, p.err, 14))) { ok = false; break; }
-                        ++n_at;
-                    }
-                    tc_fence_after();
-                    const int nkb = nkb_of(l);
-                    for (int kb = 0; kb < nkb && ok; ++kb) {
-                        const bool two = !(l == 2 && kb == 8);             // block3 extras block: one k-step
-                        const uint32_t akb_hi = ahi_lo + (uint32_t)kb * (ABLK >> 4), akb_lo = alo_lo + (uint32_t)kb * (ABLK >> 4);
-                        const uint32_t tcol = (uint32_t)(kb * 16);
-                        {   // ---- W_hi image: A_hi*W_hi + A_lo*W_hi
-                            const uint32_t s = n & (tc3::NSTAGE - 1), ph = (n >> 2) & 1u;
-                            if (!PNB_TIMED_WAIT(3, mbar_wait(&sm.bar_full[s], ph, p.err, 15))) { ok = false; break; }
-                            tc_fence_after();
-                            const uint32_t bl = b0_lo + s * (IMG >> 4);
-                            if (l == 0) {
-                                mma_ss2(tacc, akb_hi, hiw, bl, hiw, idesc, kb ? 1u : 0u);
-                                mma_ss2(tacc, akb_lo, hiw, bl, hiw, idesc, 1u);
-                                mma_ss2(tacc, akb_hi + KADV, hiw, bl + KADV, hiw, idesc, 1u);
-                                mma_ss2(tacc, akb_lo + KADV, hiw, bl + KADV, hiw, idesc, 1u);
-                            } else if (kb == 8) {
-                                mma_ss2(tacc, xeh_lo, xe_hiw, bl, hiw, idesc, 1u);
-                                mma_ss2(tacc, xel_lo, xe_hiw, bl, hiw, idesc, 1u);
-                            } else {
-                                mma_ts2(tacc, t_ahi + tcol, bl, hiw, idesc, kb ? 1u : 0u);
-                                mma_ts2(tacc, t_alo + tcol, bl, hiw, idesc, 1u);
-                                mma_ts2(tacc, t_ahi + tcol + 8u, bl + KADV, hiw, idesc, 1u);
-                                mma_ts2(tacc, t_alo + tcol + 8u, bl + KADV, hiw, idesc, 1u);
-                            }
-                            mma_commit(&sm.bar_empty[s]);
-                            ++n;
-                        }
-                        {   // ---- W_lo image: A_hi*W_lo
-                            const uint32_t s = n & (tc3::NSTAGE - 1), ph = (n >> 2) & 1u;
-                            if (!PNB_TIMED_WAIT(3, mbar_wait(&sm.bar_full[s], ph, p.err, 15))) { ok = false; break; }
-                            tc_fence_after();
-                            const uint32_t bl = b0_lo + s * (IMG >> 4);
-                            if (l == 0) {
-                                mma_ss2(tacc, akb_hi, hiw, bl, hiw, idesc, 1u);
-                                mma_ss2(tacc, akb_hi + KADV, hiw, bl + KADV, hiw, idesc, 1u);
-                            } else if (kb == 8) {
-                                mma_ss2(tacc, xeh_lo, xe_hiw, bl, hiw, idesc, 1u);
-                            } else {
-                                mma_ts2(tacc, t_ahi + tcol, bl, hiw, idesc, 1u);
-                                mma_ts2(tacc, t_ahi + tcol + 8u, bl + KADV, hiw, idesc, 1u);
-                            }
-                            mma_commit(&sm.bar_empty[s]);
-                            ++n;
-                        }
-                        (void)two;
-                    }
-                    mma_commit(&sm.bar_acc_full);
-                    if (l == 0) mma_commit(&sm.bar_a1_free);
-                }
-            }
-        }
-    } else if (warp >= W_BUILD) {
-        // ============================================================ builders: one thread per pair row
-        const int row = (warp - W_BUILD) * 32 + lane;
-        bool ok = true;
-        for (int t = 0; t < my_tiles && ok; ++t) {
-            const int tile = (int)blockIdx.x + t * (int)gridDim.x;
-            if (t > 0 && !(lane == 0 && warp == W_BUILD ? PNB_TIMED_WAIT(4, mbar_wait(&sm.bar_a1_free, (uint32_t)(t - 1) & 1u, p.err, 16)) : mbar_wait(&sm.bar_a1_free, (uint32_t)(t - 1) & 1u, p.err, 16))) { ok = false; break; }
-            const long long _tb0 = clock64();
-            build_pair_row(sm, p, tile, t, row, n_valid);
-            fence_proxy_async();
-            mbar_arrive(&sm.bar_a1_ready);
-            if (lane == 0 && warp == W_BUILD) prof_add(p, 5, clock64() - _tb0);
-        }
-    } else {
-        // ============================================================ epilogue warps 0..15: 64 columns per thread
-        const int quad = warp & 3, part = warp >> 2;
-        const int erow = quad * 32 + lane;
-        const uint32_t tlane = (uint32_t)(quad * 32) << 16;
-        uint32_t n_acc = 0;
-        bool ok = true;
-        for (int t = 0; t < my_tiles && ok; ++t) {
-            const int tile = (int)blockIdx.x + t * (int)gridDim.x;
-            for (int l = 0; l < 4 && ok; ++l, ++n_acc) {
-                if (!(tid == 0 ? PNB_TIMED_WAIT(6, mbar_wait(&sm.bar_acc_full, n_acc & 1u, p.err, 17)) : mbar_wait(&sm.bar_acc_full, n_acc & 1u, p.err, 17))) { ok = false; break; }
-                const long long _te0 = clock64();
-                tc_fence_after();
-                if (l < 3) {
-                    const float* bias = p.bias[l];
-#pragma unroll
-                    for (int ch = 0; ch < 4; ++ch) {
-                        const int c0 = part * 64 + ch * 16;
-                        uint32_t v[16];
-                        tmem_ld16(tacc + tlane + (uint32_t)c0, v);
-                        tmem_ld_wait();
-                        uint32_t hh[8], ll[8];
-#pragma unroll
-                        for (int e = 0; e < 8; ++e) {
-                            float2 bb = __ldg(reinterpret_cast<const float2*>(bias + c0) + e);
-                            float y0 = __uint_as_float(v[2 * e]) + bb.x, y1 = __uint_as_float(v[2 * e + 1]) + bb.y;
-                            y0 = fmaxf(y0, LEAKY * y0); y1 = fmaxf(y1, LEAKY * y1);
-                            split_bf16x2(y0, y1, hh[e], ll[e]);
-                        }
-                        const uint32_t colp = (uint32_t)(c0 >> 1);
-                        tmem_st8(t_ahi + tlane + colp, hh);
-                        tmem_st8(t_alo + tlane + colp, ll);
-                    }
-                    tmem_st_wait();
-                    tc_fence_before();
-                    mbar_arrive(&sm.bar_at_ready);
-                    if (tid == 0) prof_add(p, 7, clock64() - _te0);
-                } else {
-                    const float wrow = sm.wc[t & 1][erow];
-                    const int sidx = tile * TSAMP + (erow >> 3);
-                    const bool swrite = sidx < n_valid;
-                    const float* bias = p.bias[3];
-                    const int j8 = lane & 7;
-                    float apart = 0.f;
-#pragma unroll
-                    for (int ch = 0; ch < 4; ++ch) {
-                        const int c0 = part * 64 + ch * 16;
-                        uint32_t v[16];
-                        tmem_ld16(tacc + tlane + (uint32_t)c0, v);
-                        tmem_ld_wait();
-                        float z[16];
-#pragma unroll
-                        for (int e = 0; e < 16; ++e) {
-                            float y = __uint_as_float(v[e]) + __ldg(bias + c0 + e);
-                            y = fmaxf(y, LEAKY * y);
-                            apart = fmaf(y, __ldg(p.wa + c0 + e), apart);
-                            z[e] = y * wrow;
-                        }
-                        // reduce-scatter over the 8 rows (lanes) of a sample: 16 -> 8 -> 4 -> 2 columns per lane
-                        float r8[8], r4[4], r2[2];
-                        const bool b4 = lane & 4, b2 = lane & 2, b1 = lane & 1;
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            float send = b4 ? z[i] : z[i + 8], keep = b4 ? z[i + 8] : z[i];
-                            r8[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
-                        }
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            float send = b2 ? r8[i] : r8[i + 4], keep = b2 ? r8[i + 4] : r8[i];
-                            r4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
-                        }
-#pragma unroll
-                        for (int i = 0; i < 2; ++i) {
-                            float send = b1 ? r4[i] : r4[i + 2], keep = b1 ? r4[i + 2] : r4[i];
-                            r2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 1);
-                        }
-                        if (swrite) *reinterpret_cast<float2*>(p.hbar + (size_t)sidx * 256 + c0 + 2 * j8) = make_float2(r2[0], r2[1]);
-                    }
-                    tc_fence_before();
-                    mbar_arrive(&sm.bar_at_ready);          // accumulator drained: the next tile's layer 1 may start
-                    if (tid == 0) prof_add(p, 8, clock64() - _te0);
-                    if (part < 2) sm.alpha_part[part][erow] = apart;
-                    named_bar_sync(1, tc3::NEPI);
-                    if (part >= 2) atomicAdd(&sm.alpha_part[part - 2][erow], apart);
-                    named_bar_sync(1, tc3::NEPI);
-                    if (part == 0) {
-                        float a = sm.alpha_part[0][erow] + sm.alpha_part[1][erow] + __ldg(p.ba) - 1.0f;
-                        float sp = a > 20.f ? a : log1pf(expf(a));
-                        float zz = sp * wrow;
-                        zz += __shfl_xor_sync(0xffffffffu, zz, 1);
-                        zz += __shfl_xor_sync(0xffffffffu, zz, 2);
-                        zz += __shfl_xor_sync(0xffffffffu, zz, 4);
-                        if (j8 == 0 && swrite) p.sigma[sidx] = zz;
-                    }
-                    named_bar_sync(1, tc3::NEPI);
-                }
-            }
-        }
-    }
-    if (tid == 0) prof_add(p, 9, clock64() - _tk0);
-    tc_fence_before();
-    __syncthreads();
-    if (warp == W_ISSUE) tmem_dealloc<512>(tacc);
-}
-
 // ------------------------------------------------------------------------------------------ weight packing
 // W^T fp32 [Kpad][256] (rows >= K are zero) -> per K-block: hi image then lo image, each [256 x 32] bf16 in the
 // UMMA operand layout.
@@ -839,458 +251,6 @@ __global__ void __launch_bounds__(256) k_pack_weights(const float* __restrict__ 
     const size_t img = (size_t)N * 64;
     *(__nv_bfloat16*)(out + (size_t)(2 * kb) * img + off) = h;
     *(__nv_bfloat16*)(out + (size_t)(2 * kb + 1) * img + off) = l;
-}
-
-// ------------------------------------------------------------------------------------------ colour branch
-// Per valid sample: [hbar(256), PE4(view)(24)] -> 128 -> 128 -> 128 -> 3, sigmoid*1.002-0.001 ; fp32 CUDA cores.
-// (reference: point_aggregators.py:631-637, 269-273).  Tile = 64 samples.
-namespace cb {
-constexpr int TR = 64, XS = 292, KC = 16, NTHREADS = 256;
-struct Smem {
-    float X[TR * XS];
-    float Y[TR * 132];
-    float W[2][KC * 128];
-};
-}  // namespace cb
-
-__device__ __forceinline__ void cp16(void* smem, const void* gmem) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(smem_u32(smem)), "l"(gmem));
-}
-
-// C[64 x 128] = act(A[64 x Kp] * Wt[Kp x 128] + b); thread (ty,tx): rows ty*4..+3, cols tx*4 + 64*j (j=0,1)
-__device__ __forceinline__ void gemm64x128(const float* __restrict__ A, int sa, float* __restrict__ C, int sc,
-                                           const float* __restrict__ Wt, const float* __restrict__ bias, int Kp,
-                                           float (*Wst)[cb::KC * 128]) {
-    using namespace cb;
-    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
-    float acc[4][8];
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
-    const int nchunk = Kp / KC;
-    {
-        const float4* src = (const float4*)Wt;
-#pragma unroll
-        for (int i = 0; i < 2; ++i) cp16(&Wst[0][(tid + i * NTHREADS) * 4], src + tid + i * NTHREADS);
-        asm volatile("cp.async.commit_group;\n" ::);
-    }
-    for (int c = 0; c < nchunk; ++c) {
-        if (c + 1 < nchunk) {
-            const float4* src = (const float4*)(Wt + (size_t)(c + 1) * KC * 128);
-#pragma unroll
-            for (int i = 0; i < 2; ++i) cp16(&Wst[(c + 1) & 1][(tid + i * NTHREADS) * 4], src + tid + i * NTHREADS);
-            asm volatile("cp.async.commit_group;\n" ::);
-            asm volatile("cp.async.wait_group 1;\n" ::);
-        } else {
-            asm volatile("cp.async.wait_group 0;\n" ::);
-        }
-        __syncthreads();
-        const float* Wc = Wst[c & 1];
-#pragma unroll
-        for (int k4 = 0; k4 < KC; k4 += 4) {
-            float4 a[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) a[i] = *(const float4*)&A[(ty * 4 + i) * sa + c * KC + k4];
-#pragma unroll
-            for (int kk = 0; kk < 4; ++kk) {
-                float4 w0 = *(const float4*)&Wc[(k4 + kk) * 128 + tx * 4];
-                float4 w1 = *(const float4*)&Wc[(k4 + kk) * 128 + tx * 4 + 64];
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    float av = kk == 0 ? a[i].x : kk == 1 ? a[i].y : kk == 2 ? a[i].z : a[i].w;
-                    acc[i][0] = fmaf(av, w0.x, acc[i][0]); acc[i][1] = fmaf(av, w0.y, acc[i][1]);
-                    acc[i][2] = fmaf(av, w0.z, acc[i][2]); acc[i][3] = fmaf(av, w0.w, acc[i][3]);
-                    acc[i][4] = fmaf(av, w1.x, acc[i][4]); acc[i][5] = fmaf(av, w1.y, acc[i][5]);
-                    acc[i][6] = fmaf(av, w1.z, acc[i][6]); acc[i][7] = fmaf(av, w1.w, acc[i][7]);
-                }
-            }
-        }
-        __syncthreads();
-    }
-#pragma unroll
-    for (int j = 0; j < 2; ++j) {
-        float4 b = *(const float4*)&bias[tx * 4 + 64 * j];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            float4 v;
-            v.x = acc[i][j * 4 + 0] + b.x; v.y = acc[i][j * 4 + 1] + b.y;
-            v.z = acc[i][j * 4 + 2] + b.z; v.w = acc[i][j * 4 + 3] + b.w;
-            v.x = v.x > 0.f ? v.x : tc::LEAKY * v.x; v.y = v.y > 0.f ? v.y : tc::LEAKY * v.y;
-            v.z = v.z > 0.f ? v.z : tc::LEAKY * v.z; v.w = v.w > 0.f ? v.w : tc::LEAKY * v.w;
-            *(float4*)&C[(ty * 4 + i) * sc + tx * 4 + 64 * j] = v;
-        }
-    }
-    __syncthreads();
-}
-
-struct ColorParams {
-    pnb_query_t q;
-    pnb_shade_opts_t o;
-    const float* w[4];   // W^T: [288][128] (rows >= 280 zero), [128][128], [128][128], [128][3]
-    const float* b[4];
-    const float* hbar;
-    const float* sigma;
-    int hbar_cap;
-    float4* sigma_rgb;
-};
-
-__global__ void __launch_bounds__(cb::NTHREADS, 1) k_color_branch(ColorParams p) {
-    using namespace cb;
-    extern __shared__ __align__(16) unsigned char smem_raw2[];
-    Smem& sm = *reinterpret_cast<Smem*>(smem_raw2);
-    const int tid = threadIdx.x;
-    const pnb_query_t& q = p.q;
-    const int n_valid = min(q.counters[PNB_QC_N_VALID], p.hbar_cap);
-    const int n_tiles = (n_valid + TR - 1) / TR;
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        // inputs: 4 threads per sample row
-        {
-            const int row = tid >> 2, part = tid & 3;
-            const int vi = tile * TR + row;
-            float* xr = &sm.X[row * XS];
-            if (vi < n_valid) {
-                const float4* src = (const float4*)(p.hbar + (size_t)vi * 256 + part * 64);
-#pragma unroll
-                for (int i = 0; i < 16; ++i) *(float4*)&xr[part * 64 + 4 * i] = __ldg(src + i);
-                uint32_t s = q.valid_list[vi];
-                int r = (int)(q.samp_ray[s] >> 7);
-                float ovx, ovy, ovz;
-                rot3t(p.o.Rw2c, q.raydir[3 * r], q.raydir[3 * r + 1], q.raydir[3 * r + 2], ovx, ovy, ovz);
-                // PE4(view), ori=True layout: sin block (12) then cos block (12), index d*4 + j ; 3 (d,j) per thread
-#pragma unroll
-                for (int e = 0; e < 3; ++e) {
-                    int i = part * 3 + e, dd = i >> 2, jj = i & 3;
-                    float sn, cs;
-                    sincosf((dd == 0 ? ovx : dd == 1 ? ovy : ovz) * (float)(1 << jj), &sn, &cs);
-                    xr[256 + i] = sn;
-                    xr[268 + i] = cs;
-                }
-                if (part == 0) { xr[280] = 0.f; xr[281] = 0.f; xr[282] = 0.f; xr[283] = 0.f; xr[284] = 0.f; xr[285] = 0.f; xr[286] = 0.f; xr[287] = 0.f; }
-            } else {
-                for (int c = part; c < 288; c += 4) xr[c] = 0.f;
-            }
-        }
-        __syncthreads();
-        gemm64x128(sm.X, XS, sm.Y, 132, p.w[0], p.b[0], 288, sm.W);
-        gemm64x128(sm.Y, 132, sm.X, XS, p.w[1], p.b[1], 128, sm.W);
-        gemm64x128(sm.X, XS, sm.Y, 132, p.w[2], p.b[2], 128, sm.W);
-        if (tid < TR * 3) {
-            const int row = tid / 3, c = tid - row * 3;
-            const int vi = tile * TR + row;
-            if (vi < n_valid) {
-                float a = __ldg(&p.b[3][c]);
-                const float* wl = p.w[3];
-                for (int k = 0; k < 128; ++k) a = fmaf(sm.Y[row * 132 + k], __ldg(&wl[k * 3 + c]), a);
-                float rgb = 1.0f / (1.0f + expf(-a)) * (1.0f + 2.0f * 0.001f) - 0.001f;
-                uint32_t s = q.valid_list[vi];
-                float* dst = (float*)&p.sigma_rgb[s];
-                dst[1 + c] = rgb;
-                if (c == 0) dst[0] = p.sigma[vi];
-            }
-        }
-        __syncthreads();
-    }
-}
-
-// Last epilogue of a tile, one warp's share: chunks G, G+NG, G+2*NG, ... (NCHUNK of them, 16 accumulator columns each) of the
-// layer-4 output:
-// +bias, LeakyReLU, partial alpha-branch dot product (returned), weight*conf scaling and the K-reduction over the 8 rows of a
-// sample as a warp-shuffle reduce-scatter (lane j8 ends up with columns c0+2*j8, +1 of its sample) -> h-bar.
-template <int NG, int NCHUNK>
-__device__ __forceinline__ float last_chunks(const ShadeTcParams& p, uint32_t accb, int G, float wrow, int sidx, bool swrite, int lane) {
-    using namespace tc;
-    const float* bias = p.bias[3];
-    const int j8 = lane & 7;
-    float apart = 0.f;
-#pragma unroll
-    for (int i = 0; i < NCHUNK; ++i) {
-        const int c0 = 16 * (G + NG * i);
-        uint32_t v[16];
-        tmem_ld16(accb + (uint32_t)c0, v);
-        tmem_ld_wait();
-        float z[16];
-#pragma unroll
-        for (int e4 = 0; e4 < 4; ++e4) {
-            const float4 bb = __ldg(reinterpret_cast<const float4*>(bias + c0) + e4), ww = __ldg(reinterpret_cast<const float4*>(p.wa + c0) + e4);
-            const float bq[4] = {bb.x, bb.y, bb.z, bb.w}, wq[4] = {ww.x, ww.y, ww.z, ww.w};
-#pragma unroll
-            for (int e1 = 0; e1 < 4; ++e1) {
-                const int e = 4 * e4 + e1;
-                float y = __uint_as_float(v[e]) + bq[e1];
-                y = fmaxf(y, LEAKY * y);
-                apart = fmaf(y, wq[e1], apart);
-                z[e] = y * wrow;
-            }
-        }
-        float r8[8], r4[4], r2[2];
-        const bool b4 = lane & 4, b2 = lane & 2, b1 = lane & 1;
-#pragma unroll
-        for (int ii = 0; ii < 8; ++ii) {
-            float send = b4 ? z[ii] : z[ii + 8], keep = b4 ? z[ii + 8] : z[ii];
-            r8[ii] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
-        }
-#pragma unroll
-        for (int ii = 0; ii < 4; ++ii) {
-            float send = b2 ? r8[ii] : r8[ii + 4], keep = b2 ? r8[ii + 4] : r8[ii];
-            r4[ii] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
-        }
-#pragma unroll
-        for (int ii = 0; ii < 2; ++ii) {
-            float send = b1 ? r4[ii] : r4[ii + 2], keep = b1 ? r4[ii + 2] : r4[ii];
-            r2[ii] = keep + __shfl_xor_sync(0xffffffffu, send, 1);
-        }
-        if (swrite) {
-            if (p.hbar_fmt) {       // straight into the colour kernel's operand image (bf16 hi / lo, core-matrix layout)
-                uint32_t hh, ll;
-                split_bf16x2(r2[0], r2[1], hh, ll);
-                const int col = c0 + 2 * j8, srow = sidx & 127;
-                unsigned char* dst = reinterpret_cast<unsigned char*>(p.hbar) + ((size_t)(sidx >> 7) * 8 + (col >> 5)) * (2 * 8192) +
-                                     tile_offset_bytes<LAYOUT_NONE>(srow, col & 31);
-                *reinterpret_cast<uint32_t*>(dst) = hh;
-                *reinterpret_cast<uint32_t*>(dst + 8192) = ll;
-            } else {
-                *reinterpret_cast<float2*>(p.hbar + (size_t)sidx * 256 + c0 + 2 * j8) = make_float2(r2[0], r2[1]);
-            }
-        }
-    }
-    return apart;
-}
-
-// =====================================================================================================================
-// v5: "TMEM role ping-pong", single N=256 pass per layer.  The two 256-column TMEM regions P and Q alternate between
-// accumulator and A operand: the epilogue converts the finished accumulator IN PLACE, 16 columns at a time, into the
-// packed bf16 operand of the next layer (8 columns hi | 8 columns lo), and signals each 16-column chunk on its own
-// mbarrier; the issuer starts the next layer's k-step g (K = 16g..16g+15, accumulating into the OTHER region) as soon
-// as chunk g is converted, so the tensor core runs layer l+1 right behind the epilogue of layer l.  The final
-// epilogue of a tile runs under layer 1 of the next tile.
-//      layer 1: A shared memory, acc Q      layer 2: A = Q, acc P      layer 3: A = P (+extras), acc Q      layer 4: A = Q, acc P
-// Warp roles (448 threads): 0-7 epilogue (quadrant = w & 3, chunk group j = w >> 2 handles chunks j, j+2, ..., j+14),
-// 8-11 builders, 12 loader, 13 issuer.  Few epilogue warps on purpose: the epilogue only has to stay ahead of the MMAs,
-// and every busy warp on the issuer's sub-partition slows the single issuing thread.
-namespace tc5 {
-constexpr int NEPI_WARPS = 8, NGRP = NEPI_WARPS / 4, NCH = 16 / NGRP;   // chunk groups / chunks per thread
-constexpr int NEPI = NEPI_WARPS * 32, NBUILD = 128, NTHR = NEPI + NBUILD + 64;
-constexpr int NSTAGE = 4;
-struct Smem {
-    static constexpr int NWC = 3;          // weight*conf of tile t is read by the last epilogue under layer 1 of tile t+1, while the
-                                           // builders already write tile t+2: three buffers make that ordering formal (through bar_drain)
-    unsigned char a_hi[tc::NKB_MAX * tc::ABLK];
-    unsigned char a_lo[tc::NKB_MAX * tc::ABLK];
-    unsigned char b[NSTAGE][tc::IMG];
-    unsigned char xe_hi[2][tc3::XE];
-    unsigned char xe_lo[2][tc3::XE];
-    float wc[NWC][tc::TM];
-    float alpha_part[2][tc::TM];
-    uint64_t bar_full[NSTAGE], bar_empty[NSTAGE], bar_a1_ready, bar_a1_free, bar_acc_full, bar_drain, bar_kblk[8];   // bar_kblk[kb]: columns 32kb..32kb+31 converted
-    uint32_t tmem_base;
-};
-}  // namespace tc5
-
-__global__ void __launch_bounds__(tc5::NTHR, 1) k_shade_tc5(ShadeTcParams p) {
-    using namespace tc;
-    extern __shared__ __align__(1024) unsigned char smem_raw[];
-    tc5::Smem& sm = *reinterpret_cast<tc5::Smem*>(smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u));
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const pnb_query_t& q = p.q;
-    const int n_valid = min(q.counters[PNB_QC_N_VALID], p.hbar_cap);
-    const int n_tiles = (n_valid + TSAMP - 1) / TSAMP;
-    const int my_tiles = n_tiles > (int)blockIdx.x ? (n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
-    constexpr int W_BUILD = tc5::NEPI_WARPS, W_LOAD = W_BUILD + 4, W_ISSUE = W_LOAD + 1;
-
-    if (tid == 0) {
-        for (int s = 0; s < tc5::NSTAGE; ++s) { mbar_init(&sm.bar_full[s], 1); mbar_init(&sm.bar_empty[s], 1); }
-        mbar_init(&sm.bar_a1_ready, tc5::NBUILD);
-        mbar_init(&sm.bar_a1_free, 1);
-        mbar_init(&sm.bar_acc_full, 1);
-        mbar_init(&sm.bar_drain, tc5::NEPI);
-        for (int c = 0; c < 8; ++c) mbar_init(&sm.bar_kblk[c], 32 * 4 * 2);   // 4 quadrant warps x 2 chunks of 16 columns
-        mbar_fence_init();
-        if (blockIdx.x == 0 && q.counters[PNB_QC_N_VALID] > p.hbar_cap) atomicExch(p.err, 9);
-    }
-    if (warp == W_ISSUE) tmem_alloc<512>(&sm.tmem_base);
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tP = sm.tmem_base, tQ = sm.tmem_base + 256u;
-    const long long _tk0 = clock64();
-
-    if (warp == W_LOAD) {
-        // ============================================================ loader
-        if (lane == 0) {
-            const uint32_t total = (uint32_t)my_tiles * IMGS_PER_TILE;
-            for (uint32_t n = 0; n < total; ++n) {
-                const uint32_t s = n & (tc5::NSTAGE - 1), ph = (n >> 2) & 1u;
-                if (!PNB_TIMED_WAIT(0, mbar_wait(&sm.bar_empty[s], ph ^ 1u, p.err, 41))) break;
-                if (p.dbg_no_weights) { mbar_arrive(&sm.bar_full[s]); continue; }
-                mbar_arrive_expect_tx(&sm.bar_full[s], IMG);
-                bulk_g2s(sm.b[s], p.wimg + (size_t)(n % IMGS_PER_TILE) * IMG, IMG, &sm.bar_full[s]);
-            }
-        }
-    } else if (warp == W_ISSUE) {
-        // ============================================================ MMA issuer: the whole warp runs this loop
-        // (warp-uniform control flow and operands); one elected lane issues each tcgen05 instruction
-        {
-            const uint32_t idesc = make_idesc_bf16(128, 256);
-            const uint32_t hiw = desc_hi<LAYOUT>(), xe_hiw = (256u >> 4) | (1u << 14);
-            const uint32_t b0_lo = desc_lo<LAYOUT>(smem_u32(sm.b[0]));
-            const uint32_t ahi_lo = desc_lo<LAYOUT>(smem_u32(sm.a_hi)), alo_lo = desc_lo<LAYOUT>(smem_u32(sm.a_lo));
-            const uint32_t xeh_lo0 = desc_lo<LAYOUT_NONE>(smem_u32(sm.xe_hi[0])), xel_lo0 = desc_lo<LAYOUT_NONE>(smem_u32(sm.xe_lo[0]));
-            constexpr uint32_t KADV = kstep_adv16<LAYOUT>();
-            uint32_t n = 0;            // weight image counter
-            uint32_t c_acc = 0;        // completions of bar_acc_full consumed by this thread
-            uint32_t c_pack = 0;       // packing rounds (one per layer 1..3 epilogue) consumed on bar_chunk[*]
-            bool ok = true;
-            for (int t = 0; t < my_tiles && ok; ++t) {
-                const uint32_t xeh_lo = xeh_lo0 + (uint32_t)(t & 1) * (tc3::XE >> 4), xel_lo = xel_lo0 + (uint32_t)(t & 1) * (tc3::XE >> 4);
-                for (int l = 0; l < 4 && ok; ++l) {
-                    const uint32_t acc = (l & 1) ? tP : tQ;           // accumulator of this layer
-                    const uint32_t ab = (l & 1) ? tQ : tP;            // packed A operand of this layer (l >= 1)
-                    // all MMAs of the previous layer (global order) must be complete before their A region becomes this accumulator
-                    if (t > 0 || l > 0) { if (!PNB_TIMED_WAIT_L0(2, mbar_wait(&sm.bar_acc_full, c_acc & 1u, p.err, 42))) { ok = false; break; } ++c_acc; }
-                    if (l == 0) { if (!PNB_TIMED_WAIT_L0(1, mbar_wait(&sm.bar_a1_ready, (uint32_t)t & 1u, p.err, 43))) { ok = false; break; } }
-                    if (l == 1 && t > 0) { if (!PNB_TIMED_WAIT_L0(2, mbar_wait(&sm.bar_drain, (uint32_t)(t - 1) & 1u, p.err, 44))) { ok = false; break; } }
-                    tc_fence_after();
-                    const int nkb = nkb_of(l);
-                    for (int kb = 0; kb < nkb && ok; ++kb) {
-                        const uint32_t s0 = n & (tc5::NSTAGE - 1), ph0 = (n >> 2) & 1u;              // W_hi image
-                        const uint32_t s1 = (n + 1) & (tc5::NSTAGE - 1), ph1 = ((n + 1) >> 2) & 1u;   // W_lo image
-                        const bool need_chunks = (l >= 1 && kb < 8);  // chunks 2kb, 2kb+1 of the previous layer's output
-                        uint64_t* cb0 = need_chunks ? &sm.bar_kblk[kb] : &sm.bar_full[s0];
-                        uint64_t* cb1 = &sm.bar_full[s1];
-                        const uint32_t cp0 = need_chunks ? (c_pack & 1u) : ph0, cp1 = ph1;
-                        // fast path: one overlapped probe of everything this K block needs; slow path: bounded blocking waits
-                        if (!mbar_try_wait4(&sm.bar_full[s0], ph0, &sm.bar_full[s1], ph1, cb0, cp0, cb1, cp1)) {
-                            if (need_chunks) {
-                                if (!PNB_TIMED_WAIT_L0(2, mbar_wait(cb0, cp0, p.err, 45))) { ok = false; break; }
-                            }
-                            if (!PNB_TIMED_WAIT_L0(3, mbar_wait(&sm.bar_full[s0], ph0, p.err, 46))) { ok = false; break; }
-                            if (!PNB_TIMED_WAIT_L0(3, mbar_wait(&sm.bar_full[s1], ph1, p.err, 46))) { ok = false; break; }
-                        }
-                        tc_fence_after();
-                        const uint32_t akb_hi = ahi_lo + (uint32_t)kb * (ABLK >> 4), akb_lo = alo_lo + (uint32_t)kb * (ABLK >> 4);
-                        const uint32_t tcol = ab + (uint32_t)(kb * 32);
-                        const uint32_t bl = b0_lo + s0 * (IMG >> 4), bl2 = b0_lo + s1 * (IMG >> 4);
-                        if (l == 0) {
-                            mma_ss2_w(acc, akb_hi, hiw, bl, hiw, idesc, kb ? 1u : 0u);
-                            mma_ss2_w(acc, akb_lo, hiw, bl, hiw, idesc, 1u);
-                            mma_ss2_w(acc, akb_hi + KADV, hiw, bl + KADV, hiw, idesc, 1u);
-                            mma_ss2_w(acc, akb_lo + KADV, hiw, bl + KADV, hiw, idesc, 1u);
-                            mma_commit_w(&sm.bar_empty[s0]);
-                            mma_ss2_w(acc, akb_hi, hiw, bl2, hiw, idesc, 1u);
-                            mma_ss2_w(acc, akb_hi + KADV, hiw, bl2 + KADV, hiw, idesc, 1u);
-                            mma_commit_w(&sm.bar_empty[s1]);
-                        } else if (kb == 8) {
-                            mma_ss2_w(acc, xeh_lo, xe_hiw, bl, hiw, idesc, 1u);
-                            mma_ss2_w(acc, xel_lo, xe_hiw, bl, hiw, idesc, 1u);
-                            mma_commit_w(&sm.bar_empty[s0]);
-                            mma_ss2_w(acc, xeh_lo, xe_hiw, bl2, hiw, idesc, 1u);
-                            mma_commit_w(&sm.bar_empty[s1]);
-                        } else {
-                            mma_ts2_w(acc, tcol, bl, hiw, idesc, kb ? 1u : 0u);
-                            mma_ts2_w(acc, tcol + 8u, bl, hiw, idesc, 1u);
-                            mma_ts2_w(acc, tcol + 16u, bl + KADV, hiw, idesc, 1u);
-                            mma_ts2_w(acc, tcol + 24u, bl + KADV, hiw, idesc, 1u);
-                            mma_commit_w(&sm.bar_empty[s0]);
-                            mma_ts2_w(acc, tcol, bl2, hiw, idesc, 1u);
-                            mma_ts2_w(acc, tcol + 16u, bl2 + KADV, hiw, idesc, 1u);
-                            mma_commit_w(&sm.bar_empty[s1]);
-                        }
-                        n += 2;
-                    }
-                    if (!ok) break;
-                    if (l >= 1) ++c_pack;
-                    mma_commit_w(&sm.bar_acc_full);
-                    if (l == 0) mma_commit_w(&sm.bar_a1_free);
-                }
-            }
-        }
-    } else if (warp >= W_BUILD) {
-        // ============================================================ builders: one thread per pair row
-        const int row = (warp - W_BUILD) * 32 + lane;
-        bool ok = true;
-        for (int t = 0; t < my_tiles && ok; ++t) {
-            const int tile = (int)blockIdx.x + t * (int)gridDim.x;
-            if (t > 0 && !(lane == 0 && warp == W_BUILD ? PNB_TIMED_WAIT(4, mbar_wait(&sm.bar_a1_free, (uint32_t)(t - 1) & 1u, p.err, 47)) : mbar_wait(&sm.bar_a1_free, (uint32_t)(t - 1) & 1u, p.err, 47))) { ok = false; break; }
-            const long long _tb0 = clock64();
-            build_pair_row(sm, p, tile, t, row, n_valid);
-            fence_proxy_async();
-            mbar_arrive(&sm.bar_a1_ready);
-            if (lane == 0 && warp == W_BUILD) prof_add(p, 5, clock64() - _tb0);
-        }
-    } else {
-        // ============================================================ epilogue warps
-        const int quad = warp & 3, grp = warp >> 2;            // chunk group: chunks grp, grp+NGRP, grp+2*NGRP, ...
-        const int erow = quad * 32 + lane;
-        const uint32_t tlane = (uint32_t)(quad * 32) << 16;
-        uint32_t n_acc = 0;
-        bool ok = true;
-        for (int t = 0; t < my_tiles && ok; ++t) {
-            const int tile = (int)blockIdx.x + t * (int)gridDim.x;
-            for (int l = 0; l < 4 && ok; ++l, ++n_acc) {
-                if (!(tid == 0 ? PNB_TIMED_WAIT(6, mbar_wait(&sm.bar_acc_full, n_acc & 1u, p.err, 48)) : mbar_wait(&sm.bar_acc_full, n_acc & 1u, p.err, 48))) { ok = false; break; }
-                const long long _te0 = clock64();
-                tc_fence_after();
-                const uint32_t accb = ((l & 1) ? tP : tQ) + tlane;
-                if (l < 3) {
-                    const float* bias = p.bias[l];
-#pragma unroll
-                    for (int i = 0; i < tc5::NCH; ++i) {
-                        const int g = grp + tc5::NGRP * i, c0 = 16 * g;
-                        uint32_t v[16];
-                        tmem_ld16(accb + (uint32_t)c0, v);
-                        tmem_ld_wait();
-                        uint32_t hh[8], ll[8];
-#pragma unroll
-                        for (int e = 0; e < 8; ++e) {
-                            float2 bb = __ldg(reinterpret_cast<const float2*>(bias + c0) + e);
-                            float y0 = __uint_as_float(v[2 * e]) + bb.x, y1 = __uint_as_float(v[2 * e + 1]) + bb.y;
-                            y0 = fmaxf(y0, LEAKY * y0); y1 = fmaxf(y1, LEAKY * y1);
-                            split_bf16x2(y0, y1, hh[e], ll[e]);
-                        }
-                        tmem_st8(accb + (uint32_t)c0, hh);               // in place: 8 columns hi | 8 columns lo
-                        tmem_st8(accb + (uint32_t)c0 + 8u, ll);
-                        tmem_st_wait();
-                        tc_fence_before();
-                        mbar_arrive(&sm.bar_kblk[g >> 1]);
-                    }
-                    if (tid == 0) prof_add(p, 7, clock64() - _te0);
-                } else {
-                    const float wrow = sm.wc[t % tc5::Smem::NWC][erow];
-                    const int sidx = tile * TSAMP + (erow >> 3);
-                    const bool swrite = sidx < n_valid;
-                    const int j8 = lane & 7;
-                    const float apart = last_chunks<tc5::NGRP, tc5::NCH>(p, accb, grp, wrow, sidx, swrite, lane);
-                    tc_fence_before();
-                    mbar_arrive(&sm.bar_drain);                // accumulator region P drained
-                    if (tid == 0) prof_add(p, 8, clock64() - _te0);
-                    if (grp < 2) sm.alpha_part[grp][erow] = apart;
-                    named_bar_sync(1, tc5::NEPI);
-                    if (grp >= 2) atomicAdd(&sm.alpha_part[grp - 2][erow], apart);
-                    if (tc5::NGRP > 2) named_bar_sync(1, tc5::NEPI);
-                    if (grp == 0) {
-                        float a = sm.alpha_part[0][erow] + (tc5::NGRP > 1 ? sm.alpha_part[1][erow] : 0.f) + __ldg(p.ba) - 1.0f;
-                        float sp = a > 20.f ? a : log1pf(expf(a));
-                        float zz = sp * wrow;
-                        zz += __shfl_xor_sync(0xffffffffu, zz, 1);
-                        zz += __shfl_xor_sync(0xffffffffu, zz, 2);
-                        zz += __shfl_xor_sync(0xffffffffu, zz, 4);
-                        if (j8 == 0 && swrite) p.sigma[sidx] = zz;
-                    }
-                    named_bar_sync(1, tc5::NEPI);
-                }
-            }
-        }
-    }
-    if (tid == 0) prof_add(p, 9, clock64() - _tk0);
-    if (tid == 0 && (p.dbg_flags & 4) && blockIdx.x < 192) {
-        uint32_t smid;
-        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-        reinterpret_cast<long long*>(p.err)[32 + blockIdx.x] = ((clock64() - _tk0) & 0xffffffffffffll) | ((long long)smid << 48);
-    }
-    tc_fence_before();
-    __syncthreads();
-    if (warp == W_ISSUE) tmem_dealloc<512>(sm.tmem_base);
 }
 
 // =====================================================================================================================
@@ -1314,8 +274,8 @@ struct Smem {
     unsigned char a_hi[tc::NKB_MAX * tc::ABLK];
     unsigned char a_lo[tc::NKB_MAX * tc::ABLK];
     unsigned char b[NSTAGE][tc::IMG];
-    unsigned char xe_hi[2][tc3::XE];
-    unsigned char xe_lo[2][tc3::XE];
+    unsigned char xe_hi[2][tc::XE];
+    unsigned char xe_lo[2][tc::XE];
     float wc[NWC][tc::TM];
     float alpha_part[2][tc::TM];         // builder groups' partial alpha dot products
     float alpha_e[tc::TM];               // sum of the two epilogue groups' partials (two addends onto 0: order-independent)
@@ -1325,70 +285,118 @@ struct Smem {
 };
 }  // namespace tc7
 
-// ---- row packing (runs before k_shade_tc7; all sizes come from device counters)
-__global__ void __launch_bounds__(256) k_pack_cnt(pnb_query_t q, int cap, unsigned char* __restrict__ vcnt) {
-    const int vi = blockIdx.x * blockDim.x + threadIdx.x;
-    const int n_valid = min(q.counters[PNB_QC_N_VALID], cap);
-    if (vi < n_valid) vcnt[vi] = q.samp_nvalid[q.valid_list[vi]];
-}
-// one thread per super-chunk: first-fit packing of its samples into 32-row quadrants.  Samples are taken in order while they fit;
-// a sample that does not fit stays first in line for the next quadrant while up to PACK_WIN later, smaller samples may fill the
-// remaining rows (so the order inside a super-chunk becomes a permutation: vorder).  WRITE = false: count the quadrants only.
-template <bool WRITE>
-__global__ void __launch_bounds__(128) k_pack_quads(pnb_query_t q, int cap, const unsigned char* __restrict__ vcnt,
-                                                    uint32_t* __restrict__ sc_quads, uint32_t* __restrict__ quad_first,
-                                                    uint32_t* __restrict__ vorder, unsigned char* __restrict__ vcntp) {
-    const int sc = blockIdx.x * blockDim.x + threadIdx.x;
-    const int n_valid = min(q.counters[PNB_QC_N_VALID], cap);
+// ---- row packing (runs before the pair kernel; all sizes come from device counters, nothing synchronises)
+// First-fit packing of the valid samples (1..8 rows each = their neighbour count) into 32-row quadrants, independently per
+// super-chunk of PACK_S samples: samples are taken in order while they fit; a sample that does not fit stays first in line for
+// the next quadrant while up to PACK_WIN later, smaller samples may fill the remaining rows (so the order inside a super-chunk
+// becomes a permutation, vorder).  tests/test_host_logic.py restates the algorithm in Python; tests/test_gpu_shade.py compares
+// the tables of these kernels with that restatement.
+//   k_pack_quads  one WARP per super-chunk (counts in shared memory; the sequential "take while it fits" loop over the 64-entry
+//                 window becomes <= 32 rounds of one warp scan each: a round takes the maximal prefix of still-fitting
+//                 candidates and rejects the first one that does not fit).  Writes vorder / vcntp (final positions: the
+//                 packing only permutes inside a super-chunk) and the quadrant boundaries super-chunk-locally.
+//   k_pack_scan   exclusive scan of the per-super-chunk quadrant counts (one block), n_quads, sentinel
+//   k_pack_place  quadrant boundaries -> their global position (fully parallel)
+__global__ void __launch_bounds__(256) k_pack_quads(pnb_query_t q, int cap, uint32_t* __restrict__ sc_quads, uint32_t* __restrict__ quad_local,
+                                                    uint32_t* __restrict__ vorder, unsigned char* __restrict__ vcntp,
+                                                    float4* __restrict__ sigma_rgb) {
+    __shared__ unsigned char cnt[8][tc7::PACK_S];
+    const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int sc = blockIdx.x * 8 + wib;
+    const int n_all = q.counters[PNB_QC_N_VALID];
+    const int n_valid = min(n_all, cap);
+    if (n_all > cap) {
+        // workspace overflow (flagged as err 9 by the pair kernel): the samples that are dropped must not reach the compositing
+        // kernel uninitialised -> they contribute nothing (sigma = 0)
+        for (int vi = cap + blockIdx.x * blockDim.x + threadIdx.x; vi < n_all; vi += gridDim.x * blockDim.x)
+            sigma_rgb[q.valid_list[vi]] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
     const int i0 = sc * tc7::PACK_S;
     if (i0 >= n_valid) return;
     const int n = min(tc7::PACK_S, n_valid - i0);
-    __align__(16) unsigned char c[tc7::PACK_S];   // neighbour counts of this super-chunk; 0 = already placed
-    for (int i = 0; i < n; i += 16) {
-        const uint4 pk = *reinterpret_cast<const uint4*>(vcnt + i0 + i);      // the buffer is padded to a multiple of 16
-        *reinterpret_cast<uint4*>(c + i) = pk;
-    }
-    uint32_t nq = WRITE ? sc_quads[sc] : 0u;      // WRITE: sc_quads holds the exclusive prefix = first quadrant of this super-chunk
-    int pos = 0, emitted = 0;
-    while (pos < n) {
-        if (WRITE) quad_first[nq] = (uint32_t)(i0 + emitted);
-        int rows = 0;
+    unsigned char* c = cnt[wib];                  // neighbour counts of this super-chunk; 0 = already placed
+    for (int i = lane; i < n; i += 32) c[i] = q.samp_nvalid[q.valid_list[i0 + i]];
+    __syncwarp();
+    const uint32_t lt = (1u << lane) - 1u;
+    int pos = 0, emitted = 0, nq = 0;
+    while (pos < n) {                             // one quadrant per iteration (warp-uniform)
+        if (lane == 0) quad_local[i0 + nq] = (uint32_t)(i0 + emitted);     // nq <= emitted: every quadrant holds >= 1 sample
         const int lim = min(n, pos + tc7::PACK_WIN);
-        for (int i = pos; i < lim && rows < 32; ++i) {
-            const int ci = c[i];
-            if (ci != 0 && rows + ci <= 32) {
-                if (WRITE) { vorder[i0 + emitted] = (uint32_t)(i0 + i); vcntp[i0 + emitted] = (unsigned char)ci; }
-                c[i] = 0;
-                rows += ci;
-                ++emitted;
+        const int ia = pos + lane, ib = pos + 32 + lane;
+        int ca = ia < lim ? (int)c[ia] : 0, cb = ib < lim ? (int)c[ib] : 0;
+        int rows = 0, start = 0;                  // candidates with window index < start have been decided for this quadrant
+        for (;;) {
+            const int room = 32 - rows;
+            const int va = (lane >= start && ca <= room) ? ca : 0, vb = (32 + lane >= start && cb <= room) ? cb : 0;
+            int pa = va, pb = vb;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int ta = __shfl_up_sync(0xffffffffu, pa, d), tb = __shfl_up_sync(0xffffffffu, pb, d);
+                if (lane >= d) { pa += ta; pb += tb; }
             }
+            pb += __shfl_sync(0xffffffffu, pa, 31);
+            const bool fa = va != 0 && pa <= room, fb = vb != 0 && pb <= room;
+            const uint32_t ma = __ballot_sync(0xffffffffu, fa), mb = __ballot_sync(0xffffffffu, fb);
+            const uint32_t na = __ballot_sync(0xffffffffu, va != 0 && pa > room), nb = __ballot_sync(0xffffffffu, vb != 0 && pb > room);
+            const int cnt_a = __popc(ma);
+            if (fa) { const int e = i0 + emitted + __popc(ma & lt); vorder[e] = (uint32_t)(i0 + ia); vcntp[e] = (unsigned char)ca; c[ia] = 0; }
+            if (fb) { const int e = i0 + emitted + cnt_a + __popc(mb & lt); vorder[e] = (uint32_t)(i0 + ib); vcntp[e] = (unsigned char)cb; c[ib] = 0; }
+            // rows taken this round = the largest fitting prefix sum
+            int took = fb ? pb : (fa ? pa : 0);
+#pragma unroll
+            for (int d = 16; d >= 1; d >>= 1) took = max(took, __shfl_xor_sync(0xffffffffu, took, d));
+            if (fa) ca = 0;
+            if (fb) cb = 0;
+            emitted += cnt_a + __popc(mb);
+            rows += took;
+            if (rows >= 32 || (na | nb) == 0u) break;
+            start = na ? __ffs(na) : 32 + __ffs(nb);          // first rejected candidate + 1
+            if (start >= 64) break;
         }
-        while (pos < n && c[pos] == 0) ++pos;
+        __syncwarp();
+        // first entry still unplaced (the window's entries keep their order; everything beyond the window is untouched)
+        const uint32_t ra = __ballot_sync(0xffffffffu, ca != 0), rb = __ballot_sync(0xffffffffu, cb != 0);
+        pos = ra ? pos + __ffs(ra) - 1 : (rb ? pos + 32 + __ffs(rb) - 1 : lim);
         ++nq;
     }
-    if (!WRITE) sc_quads[sc] = nq;
+    if (lane == 0) sc_quads[sc] = (uint32_t)nq;
 }
-// exclusive scan of the per-super-chunk quadrant counts (one block), total -> pack_cnt[0], sentinel quad_first[n_quads] = n_valid
+// exclusive scan of the per-super-chunk quadrant counts (one block): sc_quads[0 .. n_sc] (last = total), total -> pack_cnt[0],
+// sentinel quad_first[n_quads] = n_valid
 __global__ void __launch_bounds__(1024) k_pack_scan(pnb_query_t q, int cap, uint32_t* __restrict__ sc_quads, uint32_t* __restrict__ quad_first,
                                                     int* __restrict__ pack_cnt) {
-    __shared__ uint32_t part[1024];
+    __shared__ uint32_t wsum[32];
     const int n_valid = min(q.counters[PNB_QC_N_VALID], cap);
     const int n_sc = (n_valid + tc7::PACK_S - 1) / tc7::PACK_S;
     const int per = (n_sc + 1023) / 1024;
     const int b0 = threadIdx.x * per, b1 = min(b0 + per, n_sc);
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     uint32_t sum = 0;
     for (int i = b0; i < b1; ++i) sum += sc_quads[i];
-    part[threadIdx.x] = sum;
+    uint32_t incl = sum;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += t; }
+    if (lane == 31) wsum[w] = incl;
     __syncthreads();
-    if (threadIdx.x == 0) {
-        uint32_t run = 0;
-        for (int i = 0; i < 1024; ++i) { const uint32_t v = part[i]; part[i] = run; run += v; }
-        pack_cnt[0] = (int)run;
-        quad_first[run] = (uint32_t)n_valid;
+    if (w == 0) {
+        uint32_t v = wsum[lane], iv = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, iv, d); if (lane >= d) iv += t; }
+        wsum[lane] = iv - v;
+        if (lane == 31) { pack_cnt[0] = (int)iv; quad_first[iv] = (uint32_t)n_valid; sc_quads[n_sc] = iv; }
     }
     __syncthreads();
-    uint32_t run = part[threadIdx.x];
+    uint32_t run = wsum[w] + incl - sum;
     for (int i = b0; i < b1; ++i) { const uint32_t v = sc_quads[i]; sc_quads[i] = run; run += v; }
+}
+__global__ void __launch_bounds__(256) k_pack_place(pnb_query_t q, int cap, const uint32_t* __restrict__ sc_quads, const uint32_t* __restrict__ quad_local,
+                                                    uint32_t* __restrict__ quad_first) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int n_valid = min(q.counters[PNB_QC_N_VALID], cap);
+    if (i >= n_valid) return;
+    const int sc = i / tc7::PACK_S, j = i - sc * tc7::PACK_S;
+    const uint32_t first = sc_quads[sc], nq = sc_quads[sc + 1] - first;
+    if ((uint32_t)j < nq) quad_first[first + j] = quad_local[i];
 }
 
 // Last epilogue with packed rows, one warp's share (chunks G, G+NG, ...): +bias, LeakyReLU, partial alpha dot product (returned),
@@ -1510,7 +518,7 @@ __global__ void __launch_bounds__(tc7::NTHR, 1) k_shade_tc7(ShadeTcParams p) {
         uint32_t n = 0, c_acc = 0, c_pack = 0;
         bool ok = true;
         for (int t = 0; t < my_tiles && ok; ++t) {
-            const uint32_t xeh_lo = xeh_lo0 + (uint32_t)(t & 1) * (tc3::XE >> 4), xel_lo = xel_lo0 + (uint32_t)(t & 1) * (tc3::XE >> 4);
+            const uint32_t xeh_lo = xeh_lo0 + (uint32_t)(t & 1) * (tc::XE >> 4), xel_lo = xel_lo0 + (uint32_t)(t & 1) * (tc::XE >> 4);
             for (int l = 0; l < 4 && ok; ++l) {
                 const uint32_t acc = (l & 1) ? tP : tQ;
                 const uint32_t ab = (l & 1) ? tQ : tP;
@@ -1683,329 +691,419 @@ __global__ void __launch_bounds__(tc7::NTHR, 1) k_shade_tc7(ShadeTcParams p) {
 }
 
 // =====================================================================================================================
-// v6 (opt-in, pnb_tc_version=6): v5 on a CTA PAIR (cluster of 2, tcgen05 cta_group::2).  Each CTA of the pair owns one 128-row
-// tile (its own builders, epilogue warps, TMEM regions P/Q and layer-1 operand buffer); the rank-0 CTA's issuer warp issues
-// ONE M=256 MMA for both tiles.  The B operand (weight image [256 x 32]) is split by N between the two CTAs: each loader
-// streams only its 8 KB half of every image (half the L2->SMEM weight traffic), a ring stage is a whole K block (hi + lo half
-// images, 16 KB) so ONE tcgen05.commit per K block frees it (a commit costs ~140 tensor-pipe cycles), and the tensor cores
-// read the other half of B from the peer's shared memory.
-// Cross-CTA signalling: commits are multicast to the barrier of both CTAs (ring "empty", accumulator-full, operand-free);
-// the peer's builders / epilogue warps arrive remotely on the leader's a1_ready / kblk / drain barriers (default .release.cta
-// semantics: an explicit .release.cluster compiles to MEMBAR.ALL.GPU per arrive); the peer's "weight half landed" is
-// forwarded to the leader's full barrier (count 2) by a forwarder thread.  Two builder threads per row; the last epilogue
-// of a tile is shared by the epilogue and the builder warps (both idle under layer 1 of the next tile).
-// Measured (B200, lego frame): a pair alone runs 34.5 k cycles per tile against 38.4 k for v5, but every MMA pulls 4 KB of B
-// from the peer SM, and with all 74 pairs active that exchange saturates the intra-GPC SM-to-SM fabric (~20 B/clk/SM): TPCs
-// settle at 34.5 k / 38 k / 41.5 k cycles per tile depending on their position in the GPC, and the statically partitioned
-// kernel is as slow as its slowest pair -> 3 % slower than v5 end to end.  Kept for the numbers and as the base of a
-// future mixed / dynamically scheduled variant.
-namespace tc6 {
-constexpr int NEPI_WARPS = 8, NGRP = NEPI_WARPS / 4, NCH = 16 / NGRP;
-constexpr int NEPI = NEPI_WARPS * 32, NBUILD = 256, NTHR = NEPI + NBUILD + 96;   // two builder threads per row; + loader, issuer, forwarder warps
-constexpr int NSTAGE = 4;                // ring stage = one K block: this CTA's half of the W_hi image and of the W_lo image
-constexpr int CPK = 1;                   // K blocks per ring commit (a tcgen05.commit costs ~140 tensor-pipe cycles; CPK = 2 frees stages in pairs
-                                         // and was measured slower: the 4-stage ring then starves)
-constexpr int HIMG = tc::IMG / 2;       // bytes of one half image ([128 x 32] bf16)
+// v8: the v7 pipeline for a FROZEN point cloud (rendering; opt.pnb_frozen, default when no point/MLP tensor needs a gradient).
+// The first 224 of the 284 inputs of block1.0 ([f, PE3(f)]) depend on the POINT only, not on the sample, so their
+// contribution to the layer-1 pre-activation is hoisted out of the per-pair work: k_point_pre computes
+//     pre[n][0..255] = b1 + W1[:, :224] . [f_n, PE3(f_n)]      (fp32, once per point-cloud / weight version, 1 KB per point)
+// and the layer-1 epilogue adds pre[pidx] to the accumulator where v7 adds the bias.  What remains of layer 1 is the 60
+// sample-dependent inputs PE5(dists) = 2 K blocks instead of 9:
+//   * 159 MMAs per 128-row tile instead of 201, and 192 of the 252 sin/cos pairs per pair disappear (one builder thread per row);
+//   * the layer-1 operand shrinks from 144 KB to 32 KB of shared memory, which buys a weight ring whose stage is a WHOLE K block
+//     (hi + lo image, 32 KB, 5 stages): one tcgen05.commit per K block instead of one per image (27 + 5 per tile instead of 73;
+//     a commit costs ~140 tensor-pipe cycles, profiles/r01_umma_pair_commit_cost.log);
+//   * the per-pair gather becomes 1 KB of `pre` (read by the epilogue warps, 64 B per thread and 16-column chunk, prefetched
+//     PF chunks ahead) instead of the 128 B feature row: L2 traffic, the table of a 400 k cloud is 410 MB.
+// Pipeline otherwise as v7 (TMEM role ping-pong P/Q, chunk-granular hand-off, packed rows, shared last epilogue).
+// Warps (448 threads): 0-7 epilogue (quadrant = w & 3, chunk group = w >> 2), 8-11 builders (thread = row), 12 loader, 13 issuer.
+namespace tc8 {
+constexpr int NEPI_WARPS = 8, NGRP = 2, NCH = 8;
+constexpr int NEPI = NEPI_WARPS * 32, NBUILD = 128, NTHR = NEPI + NBUILD + 64;
+constexpr int NSTAGE = 5;                 // ring stage = one K block: hi image + lo image
+constexpr int STAGE = 2 * tc::IMG;
+constexpr int NKB1 = 2;                   // K blocks of the frozen layer 1 (operand columns 224..287 of block1.0)
+constexpr int KB1_FIRST = 7;
+constexpr int STAGES_PER_TILE = NKB1 + 8 + 9 + 8;
+constexpr int PF = 3;                     // chunks of `pre` in flight per epilogue thread
 struct Smem {
-    static constexpr int NWC = 2;          // reuse ordered through bar_alpha (the builders themselves run the last epilogue)
-    unsigned char a_hi[tc::NKB_MAX * tc::ABLK];
-    unsigned char a_lo[tc::NKB_MAX * tc::ABLK];
-    unsigned char b[NSTAGE][2][HIMG];
-    unsigned char xe_hi[2][tc3::XE];
-    unsigned char xe_lo[2][tc3::XE];
-    float wc[2][tc::TM];
-    float alpha_part[2][tc::TM];         // builder groups' partial alpha dot products
-    float alpha_e[tc::TM];               // sum of the two epilogue groups' partials (atomicAdd of two addends onto 0: order-independent);
-                                         // read and re-zeroed by the builders, reuse ordered through bar_drain
-    uint64_t bar_full[NSTAGE], bar_empty[NSTAGE], bar_a1_ready, bar_a1_free, bar_acc_full, bar_final, bar_alpha, bar_drain, bar_kblk[8];
+    static constexpr int NWC = 2;
+    unsigned char a_hi[NKB1 * tc::ABLK];
+    unsigned char a_lo[NKB1 * tc::ABLK];
+    unsigned char b[NSTAGE][STAGE];
+    unsigned char xe_hi[2][tc::XE];
+    unsigned char xe_lo[2][tc::XE];
+    float wc[NWC][tc::TM];
+    float alpha_e[tc::TM];
+    int prow[2][tc::TM];                  // point index of every row (-1: unused row)
+    uint32_t qhead[NWC][4], qfirst[NWC][4], qtotal[NWC][4];
+    uint64_t bar_full[NSTAGE], bar_empty[NSTAGE], bar_a1_ready, bar_a1_free, bar_acc_full, bar_final, bar_alpha, bar_drain, bar_kblk[8], bar_prow[2];
     uint32_t tmem_base;
 };
-}  // namespace tc6
+}  // namespace tc8
 
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(tc6::NTHR, 1) k_shade_tc6(ShadeTcParams p) {
+// pre[n][c] = b1[c] + sum_{k<224} W1^T[k][c] * x_n[k],  x_n = [f (32), PE3(f) (192, column 32 + 6*feature + 2*j + {sin, cos})]:
+// exactly the first 7 K blocks of the operand build_pair_part writes.  fp32 FMAs in ascending k.  Block = 32 points x 256 columns.
+__global__ void __launch_bounds__(256) k_point_pre(const float* __restrict__ emb, int N, const float* __restrict__ w1t, const float* __restrict__ b1,
+                                                   float* __restrict__ pre) {
+    __shared__ __align__(16) float x[32][224 + 4];
+    const int n0 = blockIdx.x * 32;
+    for (int i = threadIdx.x; i < 32 * PNB_FEAT; i += 256) {
+        const int pl = i >> 5, f = i & 31, n = n0 + pl;
+        const float v = n < N ? __ldg(&emb[(size_t)n * PNB_FEAT + f]) : 0.f;
+        float pe[6];
+        pe_doubling<3>(v, pe);
+        x[pl][f] = v;
+#pragma unroll
+        for (int e = 0; e < 6; ++e) x[pl][32 + 6 * f + e] = pe[e];
+    }
+    __syncthreads();
+    const int c = threadIdx.x;
+    float acc[32];
+    const float bc = __ldg(&b1[c]);
+#pragma unroll
+    for (int i = 0; i < 32; ++i) acc[i] = 0.f;
+    for (int k = 0; k < 224; k += 4) {
+        const float w0 = __ldg(&w1t[(size_t)k * 256 + c]), w1 = __ldg(&w1t[(size_t)(k + 1) * 256 + c]);
+        const float w2 = __ldg(&w1t[(size_t)(k + 2) * 256 + c]), w3 = __ldg(&w1t[(size_t)(k + 3) * 256 + c]);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+            const float4 xv = *reinterpret_cast<const float4*>(&x[i][k]);
+            acc[i] = fmaf(xv.w, w3, fmaf(xv.z, w2, fmaf(xv.y, w1, fmaf(xv.x, w0, acc[i]))));
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 32; ++i)
+        if (n0 + i < N) pre[(size_t)(n0 + i) * 256 + c] = acc[i] + bc;
+}
+
+// One pair row of the frozen pipeline: the PE5(dists) K blocks of the layer-1 operand (operand columns 224..287 -> blocks 0, 1),
+// the block3 extras operand, weight*conf and the row's point index.  Same arithmetic as build_pair_part<PART 1, PACKED>.
+__device__ __forceinline__ void build_pair_frozen(tc8::Smem& sm, const ShadeTcParams& p, int t, int row, int n_valid, int pvi, int pk, int pst, int pcnt) {
+    using namespace tc;
+    const pnb_query_t& q = p.q;
+    int pidx = -1;
+    float lx = 0.f, ly = 0.f, lz = 0.f, vx = 0.f, vy = 0.f, vz = 0.f;
+    if (pvi >= 0 && pvi < n_valid) {
+        const uint32_t s = q.valid_list[pvi];
+        const uint32_t sr = q.samp_ray[s];
+        const int r = (int)(sr >> 7), j = (int)(sr & 127u);
+        const int d = q.steps[(size_t)r * q.SR + j];
+        const float tt = q.t[(size_t)r * q.t_ray_stride + d];
+        vx = q.raydir[3 * r]; vy = q.raydir[3 * r + 1]; vz = q.raydir[3 * r + 2];
+        lx = raypos1(q.campos[0], vx, tt); ly = raypos1(q.campos[1], vy, tt); lz = raypos1(q.campos[2], vz, tt);
+        if (pk < q.K) pidx = q.cand_pidx[(size_t)s * q.K + pk];
+    }
+    const bool valid = pidx >= 0;
+    const int pi = valid ? pidx : 0;
+    sm.prow[t & 1][row] = pidx;
+    float dist[6];
+    float ovx, ovy, ovz;
+    rot3t(p.o.Rw2c, vx, vy, vz, ovx, ovy, ovz);
+    const float px = __ldg(&p.pts.xyz[3 * pi]), py = __ldg(&p.pts.xyz[3 * pi + 1]), pz = __ldg(&p.pts.xyz[3 * pi + 2]);
+    dist[0] = px - lx; dist[1] = py - ly; dist[2] = pz - lz;
+    float xpp, ypp, zpp, xsp, ysp, zsp;
+    w2pers_t(p.o, px, py, pz, xpp, ypp, zpp);
+    w2pers_t(p.o, lx, ly, lz, xsp, ysp, zsp);
+    dist[3] = xpp * zpp - xsp * zsp; dist[4] = ypp * zpp - ysp * zsp; dist[5] = zpp - zsp;
+    const float nrm = sqrtf(dist[0] * dist[0] + dist[1] * dist[1] + dist[2] * dist[2]);
+    float w = valid ? 1.0f / fmaxf(nrm, 1e-6f) : 0.f;
+    const float wsum = seg_sum8(w, row & 31, pst, pcnt);
+    w = w / fmaxf(wsum, 1e-8f);
+    const float cf = __ldg(&p.pts.conf[pi]);
+    sm.wc[t & 1][row] = valid ? w * fminf(fmaxf(cf, 1e-4f), 1.0f) : 0.f;
+    float d0, d1, d2;
+    rot3t(p.o.Rw2c, dist[0], dist[1], dist[2], d0, d1, d2);
+    dist[0] = d0; dist[1] = d1; dist[2] = d2;
+    float ex[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (valid) {
+        float dp[64];
+#pragma unroll
+        for (int e = 0; e < 6; ++e) pe_doubling<5>(dist[e], dp + 10 * e);
+        dp[60] = dp[61] = dp[62] = dp[63] = 0.f;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) store_chunk8_a1(sm, row, c >> 2, (c & 3) * 8, dp + 8 * c);
+        float ddx, ddy, ddz;
+        rot3t(p.o.Rw2c, __ldg(&p.pts.dir[3 * pi]), __ldg(&p.pts.dir[3 * pi + 1]), __ldg(&p.pts.dir[3 * pi + 2]), ddx, ddy, ddz);
+        ex[0] = __ldg(&p.pts.color[3 * pi]); ex[1] = __ldg(&p.pts.color[3 * pi + 1]); ex[2] = __ldg(&p.pts.color[3 * pi + 2]);
+        ex[3] = ddx - ovx; ex[4] = ddy - ovy; ex[5] = ddz - ovz;
+        ex[6] = ddx * ovx + ddy * ovy + ddz * ovz;
+    } else {
+        const float z8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int c = 0; c < 8; ++c) store_chunk8_a1(sm, row, c >> 2, (c & 3) * 8, z8);
+    }
+    uint32_t h[4], l[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) split_bf16x2(ex[2 * i], ex[2 * i + 1], h[i], l[i]);
+    const uint32_t off = tc::xe_offset(row, 0);
+    *reinterpret_cast<uint4*>(sm.xe_hi[t & 1] + off) = make_uint4(h[0], h[1], h[2], h[3]);
+    *reinterpret_cast<uint4*>(sm.xe_lo[t & 1] + off) = make_uint4(l[0], l[1], l[2], l[3]);
+    *reinterpret_cast<uint4*>(sm.xe_hi[t & 1] + off + 128) = make_uint4(0u, 0u, 0u, 0u);
+    *reinterpret_cast<uint4*>(sm.xe_lo[t & 1] + off + 128) = make_uint4(0u, 0u, 0u, 0u);
+}
+
+__global__ void __launch_bounds__(tc8::NTHR, 1) k_shade_tc8(ShadeTcParams p) {
     using namespace tc;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
-    tc6::Smem& sm = *reinterpret_cast<tc6::Smem*>(smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u));
+    tc8::Smem& sm = *reinterpret_cast<tc8::Smem*>(smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u));
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const uint32_t rank = cluster_ctarank();
     const pnb_query_t& q = p.q;
     const int n_valid = min(q.counters[PNB_QC_N_VALID], p.hbar_cap);
-    const int n_tiles = (n_valid + TSAMP - 1) / TSAMP;
-    const int n_ptiles = (n_tiles + 1) >> 1;                       // pair tiles: tiles 2i (rank 0) and 2i+1 (rank 1)
-    int pair = (int)blockIdx.x >> 1, npairs = (int)gridDim.x >> 1;
-    const bool idle_pair = (p.dbg_flags & 8) && (pair & 1);      // experiment: only every other CTA pair works
-    if (p.dbg_flags & 8) { pair >>= 1; npairs = (npairs + 1) >> 1; }
-    const int my_tiles = (n_ptiles > pair && !idle_pair) ? (n_ptiles - 1 - pair) / npairs + 1 : 0;
-    constexpr int W_BUILD = tc6::NEPI_WARPS, W_LOAD = W_BUILD + tc6::NBUILD / 32, W_ISSUE = W_LOAD + 1, W_FWD = W_ISSUE + 1;
-    constexpr uint32_t SMASK = tc6::NSTAGE - 1;
+    const int n_quads = p.pack_cnt[0];
+    const int n_tiles = (n_quads + 3) >> 2;
+    const int my_tiles = n_tiles > (int)blockIdx.x ? (n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+    constexpr int W_BUILD = tc8::NEPI_WARPS, W_LOAD = W_BUILD + tc8::NBUILD / 32, W_ISSUE = W_LOAD + 1;
 
     if (tid == 0) {
-        for (int s = 0; s < tc6::NSTAGE; ++s) { mbar_init(&sm.bar_full[s], rank == 0 ? 2 : 1); mbar_init(&sm.bar_empty[s], 1); }
-        mbar_init(&sm.bar_a1_ready, 2 * tc6::NBUILD);              // leader's: the builder threads of both CTAs
+        for (int s = 0; s < tc8::NSTAGE; ++s) { mbar_init(&sm.bar_full[s], 1); mbar_init(&sm.bar_empty[s], 1); }
+        mbar_init(&sm.bar_a1_ready, tc8::NBUILD);
         mbar_init(&sm.bar_a1_free, 1);
         mbar_init(&sm.bar_acc_full, 1);
         mbar_init(&sm.bar_final, 1);
-        mbar_init(&sm.bar_alpha, tc6::NEPI_WARPS);
-        mbar_init(&sm.bar_drain, 2 * (tc6::NEPI_WARPS + tc6::NBUILD / 32));   // leader's: every warp of both CTAs that reads the layer-4 accumulator
-        for (int c = 0; c < 8; ++c) mbar_init(&sm.bar_kblk[c], 2 * 4 * 2);   // leader's: 2 CTAs x 4 quadrant warps x 2 chunks
+        mbar_init(&sm.bar_alpha, tc8::NEPI_WARPS);
+        mbar_init(&sm.bar_drain, tc8::NEPI_WARPS + tc8::NBUILD / 32);     // one arrive per warp that reads the layer-4 accumulator
+        for (int c = 0; c < 8; ++c) mbar_init(&sm.bar_kblk[c], 32 * 4 * 2);
+        mbar_init(&sm.bar_prow[0], tc8::NBUILD / 32);
+        mbar_init(&sm.bar_prow[1], tc8::NBUILD / 32);
         mbar_fence_init();
         if (blockIdx.x == 0 && q.counters[PNB_QC_N_VALID] > p.hbar_cap) atomicExch(p.err, 9);
     }
     if (tid < TM) sm.alpha_e[tid] = 0.f;
-    if (warp == W_ISSUE) tmem_alloc2<512>(&sm.tmem_base);
+    if (warp == W_ISSUE) tmem_alloc<512>(&sm.tmem_base);
     tc_fence_before();
-    cluster_sync_all();
+    __syncthreads();
     tc_fence_after();
     const uint32_t tP = sm.tmem_base, tQ = sm.tmem_base + 256u;
     const long long _tk0 = clock64();
 
     if (warp == W_LOAD) {
-        // ============================================================ loader: this CTA's half of every image
+        // ============================================================ weight ring: one K block (hi + lo image, 32 KB) per stage
         if (lane == 0) {
-            const uint32_t total = (uint32_t)my_tiles * NBLK_TOTAL;            // K blocks
-            const unsigned char* src = p.wimg + (size_t)rank * tc6::HIMG;
+            const uint32_t total = (uint32_t)my_tiles * tc8::STAGES_PER_TILE;
+            uint32_t s = 0, ph = 0, j = 0;
             for (uint32_t n = 0; n < total; ++n) {
-                const uint32_t s = n & SMASK, ph = (n >> 2) & 1u;
-                const long long _tl0 = clock64();
-                if ((n % tc6::CPK) == 0 && !mbar_wait(&sm.bar_empty[(n / tc6::CPK) % (tc6::NSTAGE / tc6::CPK)], ph ^ 1u, p.err, 61)) break;
-                if (blockIdx.x < 2 && (p.dbg_flags & 1)) atomicAdd(reinterpret_cast<unsigned long long*>(p.err) + 1 + (blockIdx.x ? 15 : 0), (unsigned long long)(clock64() - _tl0));
-                if (p.dbg_no_weights) { mbar_arrive(&sm.bar_full[s]); continue; }
-                mbar_arrive_expect_tx(&sm.bar_full[s], 2 * tc6::HIMG);
-                const unsigned char* g = src + (size_t)(n % NBLK_TOTAL) * (2 * IMG);
-                bulk_g2s(sm.b[s][0], g, tc6::HIMG, &sm.bar_full[s]);               // W_hi rows 128*rank..
-                bulk_g2s(sm.b[s][1], g + IMG, tc6::HIMG, &sm.bar_full[s]);         // W_lo rows 128*rank..
-            }
-        }
-    } else if (warp == W_FWD) {
-        // ============================================================ forwarder (peer CTA): "my half landed" -> leader
-        if (rank == 1 && lane == 0) {
-            const uint32_t total = (uint32_t)my_tiles * NBLK_TOTAL;
-            const uint32_t full0 = map_to_cta(&sm.bar_full[0], 0);
-            for (uint32_t n = 0; n < total; ++n) {
-                const uint32_t s = n & SMASK, ph = (n >> 2) & 1u;
-                if (!mbar_wait(&sm.bar_full[s], ph, p.err, 62)) break;
-                mbar_arrive_cluster(full0 + 8u * s);
+                if (!mbar_wait(&sm.bar_empty[s], ph ^ 1u, p.err, 91)) break;
+                const uint32_t blk = j < (uint32_t)tc8::NKB1 ? (uint32_t)tc8::KB1_FIRST + j : 9u + (j - (uint32_t)tc8::NKB1);
+                if (p.dbg_no_weights) mbar_arrive(&sm.bar_full[s]);
+                else {
+                    mbar_arrive_expect_tx(&sm.bar_full[s], tc8::STAGE);
+                    const unsigned char* src = p.wimg + (size_t)blk * tc8::STAGE;
+                    bulk_g2s(sm.b[s], src, IMG, &sm.bar_full[s]);
+                    bulk_g2s(sm.b[s] + IMG, src + IMG, IMG, &sm.bar_full[s]);
+                }
+                if (++s == (uint32_t)tc8::NSTAGE) { s = 0; ph ^= 1u; }
+                if (++j == (uint32_t)tc8::STAGES_PER_TILE) j = 0;
             }
         }
     } else if (warp == W_ISSUE) {
-        // ============================================================ MMA issuer: the whole warp of the rank-0 CTA
-        if (rank == 0) {
-            const uint32_t idesc = make_idesc_bf16(256, 256);
-            const uint32_t hiw = desc_hi<LAYOUT>(), xe_hiw = (256u >> 4) | (1u << 14);
-            const uint32_t b0_lo = desc_lo<LAYOUT>(smem_u32(sm.b[0]));
-            const uint32_t ahi_lo = desc_lo<LAYOUT>(smem_u32(sm.a_hi)), alo_lo = desc_lo<LAYOUT>(smem_u32(sm.a_lo));
-            const uint32_t xeh_lo0 = desc_lo<LAYOUT_NONE>(smem_u32(sm.xe_hi[0])), xel_lo0 = desc_lo<LAYOUT_NONE>(smem_u32(sm.xe_lo[0]));
-            constexpr uint32_t KADV = kstep_adv16<LAYOUT>();
-            uint32_t n = 0;            // weight image counter
-            uint32_t c_acc = 0;        // completions of bar_acc_full consumed
-            uint32_t c_pack = 0;       // packing rounds consumed on bar_kblk[*]
-            bool ok = true;
-            for (int t = 0; t < my_tiles && ok; ++t) {
-                const uint32_t xeh_lo = xeh_lo0 + (uint32_t)(t & 1) * (tc3::XE >> 4), xel_lo = xel_lo0 + (uint32_t)(t & 1) * (tc3::XE >> 4);
-                for (int l = 0; l < 4 && ok; ++l) {
-                    const uint32_t acc = (l & 1) ? tP : tQ;
-                    const uint32_t ab = (l & 1) ? tQ : tP;
-                    if (l > 0) { if (!PNB_TIMED_WAIT_L0(2, mbar_wait(&sm.bar_acc_full, c_acc & 1u, p.err, 63))) { ok = false; break; } ++c_acc; }
-                    else if (t > 0) { if (!PNB_TIMED_WAIT_L0(2, mbar_wait(&sm.bar_final, (uint32_t)(t - 1) & 1u, p.err, 63))) { ok = false; break; } }
-                    if (l == 0) { if (!PNB_TIMED_WAIT_L0(1, mbar_wait(&sm.bar_a1_ready, (uint32_t)t & 1u, p.err, 64))) { ok = false; break; } }
-                    if (l == 1 && t > 0) { if (!PNB_TIMED_WAIT_L0(2, mbar_wait(&sm.bar_drain, (uint32_t)(t - 1) & 1u, p.err, 65))) { ok = false; break; } }
-                    tc_fence_after();
-                    const int nkb = nkb_of(l);
-                    for (int kb = 0; kb < nkb && ok; ++kb) {
-                        const uint32_t s0 = n & SMASK, ph0 = (n >> 2) & 1u;                  // ring stage of this K block
-                        const bool need_chunks = (l >= 1 && kb < 8);
-                        uint64_t* cb0 = need_chunks ? &sm.bar_kblk[kb] : &sm.bar_full[s0];
-                        const uint32_t cp0 = need_chunks ? (c_pack & 1u) : ph0;
-                        if (p.dbg_flags & 2) {      // diagnosis: classify the wait with non-blocking probes
-                            if (need_chunks && !mbar_test_wait(cb0, cp0)) {
-                                if (!PNB_TIMED_WAIT_L0(12, mbar_spin_wait(cb0, cp0, p.err, 66))) { ok = false; break; }
-                            }
-                            if (!mbar_test_wait(&sm.bar_full[s0], ph0)) {
-                                const long long _tw = clock64();
-                                if (!mbar_spin_wait(&sm.bar_full[s0], ph0, p.err, 67)) { ok = false; break; }
-                                if (lane == 0) { prof_add(p, 13, clock64() - _tw); prof_add(p, 14, 1); }
-                            }
-                        } else
-                        if (!mbar_try_wait4(&sm.bar_full[s0], ph0, cb0, cp0, &sm.bar_full[s0], ph0, cb0, cp0)) {
-                            if (need_chunks) {
-                                if (!PNB_TIMED_WAIT_L0(2, mbar_wait(cb0, cp0, p.err, 66))) { ok = false; break; }
-                            }
-                            if (!PNB_TIMED_WAIT_L0(3, mbar_wait(&sm.bar_full[s0], ph0, p.err, 67))) { ok = false; break; }
-                        }
-                        tc_fence_after();
-                        const uint32_t akb_hi = ahi_lo + (uint32_t)kb * (ABLK >> 4), akb_lo = alo_lo + (uint32_t)kb * (ABLK >> 4);
-                        const uint32_t tcol = ab + (uint32_t)(kb * 32);
-                        const uint32_t bl = b0_lo + s0 * (2 * tc6::HIMG >> 4), bl2 = bl + (tc6::HIMG >> 4);
-                        if (l == 0) {
-                            mma2_ss2_w(acc, akb_hi, hiw, bl, hiw, idesc, kb ? 1u : 0u);
-                            mma2_ss2_w(acc, akb_lo, hiw, bl, hiw, idesc, 1u);
-                            mma2_ss2_w(acc, akb_hi + KADV, hiw, bl + KADV, hiw, idesc, 1u);
-                            mma2_ss2_w(acc, akb_lo + KADV, hiw, bl + KADV, hiw, idesc, 1u);
-                            mma2_ss2_w(acc, akb_hi, hiw, bl2, hiw, idesc, 1u);
-                            mma2_ss2_w(acc, akb_hi + KADV, hiw, bl2 + KADV, hiw, idesc, 1u);
-                        } else if (kb == 8) {
-                            mma2_ss2_w(acc, xeh_lo, xe_hiw, bl, hiw, idesc, 1u);
-                            mma2_ss2_w(acc, xel_lo, xe_hiw, bl, hiw, idesc, 1u);
-                            mma2_ss2_w(acc, xeh_lo, xe_hiw, bl2, hiw, idesc, 1u);
-                        } else {
-                            mma2_ts2_w(acc, tcol, bl, hiw, idesc, kb ? 1u : 0u);
-                            mma2_ts2_w(acc, tcol + 8u, bl, hiw, idesc, 1u);
-                            mma2_ts2_w(acc, tcol + 16u, bl + KADV, hiw, idesc, 1u);
-                            mma2_ts2_w(acc, tcol + 24u, bl + KADV, hiw, idesc, 1u);
-                            mma2_ts2_w(acc, tcol, bl2, hiw, idesc, 1u);
-                            mma2_ts2_w(acc, tcol + 16u, bl2 + KADV, hiw, idesc, 1u);
-                        }
-                        if ((n % tc6::CPK) == tc6::CPK - 1) mma2_commit_w(&sm.bar_empty[(n / tc6::CPK) % (tc6::NSTAGE / tc6::CPK)], 3);   // frees CPK ring stages in both CTAs
-                        n += 1;
+        // ============================================================ MMA issuer (whole warp, warp-uniform; one commit per K block)
+        const uint32_t idesc = make_idesc_bf16(128, 256);
+        const uint32_t hiw = desc_hi<LAYOUT>(), xe_hiw = (256u >> 4) | (1u << 14);
+        const uint32_t b0_lo = desc_lo<LAYOUT>(smem_u32(sm.b[0]));
+        const uint32_t ahi_lo = desc_lo<LAYOUT>(smem_u32(sm.a_hi)), alo_lo = desc_lo<LAYOUT>(smem_u32(sm.a_lo));
+        const uint32_t xeh_lo0 = desc_lo<LAYOUT_NONE>(smem_u32(sm.xe_hi[0])), xel_lo0 = desc_lo<LAYOUT_NONE>(smem_u32(sm.xe_lo[0]));
+        constexpr uint32_t KADV = kstep_adv16<LAYOUT>();
+        uint32_t s = 0, ph = 0, c_acc = 0, c_pack = 0;
+        bool ok = true;
+        for (int t = 0; t < my_tiles && ok; ++t) {
+            const uint32_t xeh_lo = xeh_lo0 + (uint32_t)(t & 1) * (XE >> 4), xel_lo = xel_lo0 + (uint32_t)(t & 1) * (XE >> 4);
+            for (int l = 0; l < 4 && ok; ++l) {
+                const uint32_t acc = (l & 1) ? tP : tQ;
+                const uint32_t ab = (l & 1) ? tQ : tP;
+                if (l > 0) { if (!mbar_wait(&sm.bar_acc_full, c_acc & 1u, p.err, 92)) { ok = false; break; } ++c_acc; }
+                else if (t > 0) { if (!mbar_wait(&sm.bar_final, (uint32_t)(t - 1) & 1u, p.err, 92)) { ok = false; break; } }
+                if (l == 0) { if (!mbar_wait(&sm.bar_a1_ready, (uint32_t)t & 1u, p.err, 93)) { ok = false; break; } }
+                if (l == 1 && t > 0) { if (!mbar_wait(&sm.bar_drain, (uint32_t)(t - 1) & 1u, p.err, 94)) { ok = false; break; } }
+                tc_fence_after();
+                const int nkb = l == 0 ? tc8::NKB1 : nkb_of(l);
+                for (int kb = 0; kb < nkb && ok; ++kb) {
+                    const bool need_chunks = (l >= 1 && kb < 8);
+                    uint64_t* cb0 = need_chunks ? &sm.bar_kblk[kb] : &sm.bar_full[s];
+                    const uint32_t cp0 = need_chunks ? (c_pack & 1u) : ph;
+                    if (!mbar_try_wait4(&sm.bar_full[s], ph, cb0, cp0, &sm.bar_full[s], ph, cb0, cp0)) {
+                        if (need_chunks && !mbar_wait(cb0, cp0, p.err, 95)) { ok = false; break; }
+                        if (!mbar_wait(&sm.bar_full[s], ph, p.err, 96)) { ok = false; break; }
                     }
-                    if (!ok) break;
-                    if (l >= 1) ++c_pack;
-                    mma2_commit_w(l < 3 ? &sm.bar_acc_full : &sm.bar_final, 3);     // layers 1-3 -> epilogue warps, layer 4 -> builder warps
-                    if (l == 0) mma2_commit_w(&sm.bar_a1_free, 3);
+                    tc_fence_after();
+                    const uint32_t bh = b0_lo + s * (uint32_t)(tc8::STAGE >> 4), bl = bh + (uint32_t)(IMG >> 4);
+                    if (l == 0) {
+                        const uint32_t akb_hi = ahi_lo + (uint32_t)kb * (ABLK >> 4), akb_lo = alo_lo + (uint32_t)kb * (ABLK >> 4);
+                        mma_ss2_w(acc, akb_hi, hiw, bh, hiw, idesc, kb ? 1u : 0u);
+                        mma_ss2_w(acc, akb_lo, hiw, bh, hiw, idesc, 1u);
+                        mma_ss2_w(acc, akb_hi + KADV, hiw, bh + KADV, hiw, idesc, 1u);
+                        mma_ss2_w(acc, akb_lo + KADV, hiw, bh + KADV, hiw, idesc, 1u);
+                        mma_ss2_w(acc, akb_hi, hiw, bl, hiw, idesc, 1u);
+                        mma_ss2_w(acc, akb_hi + KADV, hiw, bl + KADV, hiw, idesc, 1u);
+                    } else if (kb == 8) {
+                        mma_ss2_w(acc, xeh_lo, xe_hiw, bh, hiw, idesc, 1u);
+                        mma_ss2_w(acc, xel_lo, xe_hiw, bh, hiw, idesc, 1u);
+                        mma_ss2_w(acc, xeh_lo, xe_hiw, bl, hiw, idesc, 1u);
+                    } else {
+                        const uint32_t tcol = ab + (uint32_t)(kb * 32);
+                        mma_ts2_w(acc, tcol, bh, hiw, idesc, kb ? 1u : 0u);
+                        mma_ts2_w(acc, tcol + 8u, bh, hiw, idesc, 1u);
+                        mma_ts2_w(acc, tcol + 16u, bh + KADV, hiw, idesc, 1u);
+                        mma_ts2_w(acc, tcol + 24u, bh + KADV, hiw, idesc, 1u);
+                        mma_ts2_w(acc, tcol, bl, hiw, idesc, 1u);
+                        mma_ts2_w(acc, tcol + 16u, bl + KADV, hiw, idesc, 1u);
+                    }
+                    mma_commit_w(&sm.bar_empty[s]);
+                    if (++s == (uint32_t)tc8::NSTAGE) { s = 0; ph ^= 1u; }
                 }
+                if (!ok) break;
+                if (l >= 1) ++c_pack;
+                mma_commit_w(l < 3 ? &sm.bar_acc_full : &sm.bar_final);
+                if (l == 0) mma_commit_w(&sm.bar_a1_free);
             }
         }
     } else if (warp >= W_BUILD) {
-        // ============================================================ builders: one thread per pair row of this CTA's tile
-        const int bt = (warp - W_BUILD) * 32 + lane, row = bt & 127, part = bt >> 7;     // two threads per row (columns 0..151 | 152..287)
-        const uint32_t ready0 = map_to_cta(&sm.bar_a1_ready, 0), drain0 = map_to_cta(&sm.bar_drain, 0);
-        // the same warps run the LAST epilogue of a tile (alpha branch, Softplus, weighted K-reduction -> h-bar, sigma): it falls
-        // under layer 1 of the next tile, exactly when the builders are idle (the operand buffer is still being read)
-        const int quad = warp & 3, grp = (warp - W_BUILD) >> 2;
-        const int erow = quad * 32 + lane;
-        const uint32_t tlane = (uint32_t)(quad * 32) << 16;
+        // ============================================================ builders: one warp per quadrant, lane = row; the same warps run
+        // chunk group 0 of the last epilogue of the previous tile
+        const int qw = warp - W_BUILD, row = qw * 32 + lane;
+        const uint32_t tlane = (uint32_t)(qw * 32) << 16;
         bool ok = true;
         for (int t = 0; t <= my_tiles && ok; ++t) {
             if (t < my_tiles) {
-                const int tile = 2 * (pair + t * npairs) + (int)rank;
-                if (t > 0 && !(lane == 0 && warp == W_BUILD ? PNB_TIMED_WAIT(4, mbar_wait(&sm.bar_a1_free, (uint32_t)(t - 1) & 1u, p.err, 68)) : mbar_wait(&sm.bar_a1_free, (uint32_t)(t - 1) & 1u, p.err, 68))) { ok = false; break; }
-                const long long _tb0 = clock64();
-                if (part == 0) build_pair_part<0, false>(sm, p, tile, t, row, n_valid);
-                else build_pair_part<1, false>(sm, p, tile, t, row, n_valid);
+                const int tile = (int)blockIdx.x + t * (int)gridDim.x;
+                if (t > 0 && !mbar_wait(&sm.bar_a1_free, (uint32_t)(t - 1) & 1u, p.err, 97)) { ok = false; break; }
+                const int qd = tile * 4 + qw;
+                uint32_t first = 0, nsamp = 0;
+                if (qd < n_quads) { first = p.quad_first[qd]; nsamp = p.quad_first[qd + 1] - first; }
+                const int c = lane < (int)nsamp ? (int)p.vcnt[first + lane] : 0;
+                int incl = c;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += v; }
+                const uint32_t head = __reduce_or_sync(0xffffffffu, lane < (int)nsamp ? (1u << (incl - c)) : 0u);
+                const int total = __shfl_sync(0xffffffffu, incl, 31);
+                const QuadRow qr = quad_row(head, total, lane);
+                const int cj = __shfl_sync(0xffffffffu, c, qr.j);
+                if (lane == 0) { sm.qhead[t & 1][qw] = head; sm.qfirst[t & 1][qw] = first; sm.qtotal[t & 1][qw] = (uint32_t)total; }
+                const int pvi = qr.live ? (int)p.vorder[first + qr.j] : -1;
+                build_pair_frozen(sm, p, t, row, n_valid, pvi, lane - qr.st, qr.st, qr.live ? cj : 1);
                 fence_proxy_async();
-                if (rank == 0) mbar_arrive(&sm.bar_a1_ready); else mbar_arrive_cluster(ready0);
-                if (lane == 0 && warp == W_BUILD) prof_add(p, 5, clock64() - _tb0);
+                mbar_arrive(&sm.bar_a1_ready);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&sm.bar_prow[t & 1]);
             }
             if (t > 0) {
-                const int tf = t - 1, tilef = 2 * (pair + tf * npairs) + (int)rank;
-                if (!mbar_wait(&sm.bar_final, (uint32_t)tf & 1u, p.err, 70)) { ok = false; break; }
-                const long long _te0 = clock64();
+                const int tf = t - 1;
+                if (!mbar_wait(&sm.bar_final, (uint32_t)tf & 1u, p.err, 99)) { ok = false; break; }
                 tc_fence_after();
-                const uint32_t accb = tP + tlane;          // layer 4 accumulates into region P
-                const float wrow = sm.wc[tf & 1][erow];
-                const int sidx = tilef * TSAMP + (erow >> 3);
-                const bool swrite = sidx < n_valid;
-                const float apart = last_chunks<4, 4>(p, accb, 2 + grp, wrow, sidx, swrite, lane);
+                const QuadRow qr = quad_row(sm.qhead[tf & 1][qw], (int)sm.qtotal[tf & 1][qw], lane);
+                const int sidx = qr.live ? (int)p.vorder[sm.qfirst[tf & 1][qw] + qr.j] : 0;
+                const bool swrite = qr.is_end && sidx < n_valid;
+                const float wrow = sm.wc[tf & 1][row];
+                const float apart = last_chunks_packed<3, 6>(p, tP + tlane, 0, wrow, qr.st, swrite, sidx, lane);
                 tc_fence_before();
-                if (bt == 0) prof_add(p, 8, clock64() - _te0);
-                sm.alpha_part[grp][erow] = apart;
-                named_bar_sync(2, tc6::NBUILD);
-                if (!mbar_wait(&sm.bar_alpha, (uint32_t)tf & 1u, p.err, 71)) { ok = false; break; }      // the epilogue warps' partial sums
-                if (grp == 0) {
-                    float a = (sm.alpha_part[0][erow] + sm.alpha_part[1][erow]) + sm.alpha_e[erow] + __ldg(p.ba) - 1.0f;
-                    sm.alpha_e[erow] = 0.f;
-                    float sp = a > 20.f ? a : log1pf(expf(a));
-                    float zz = sp * wrow;
-                    zz += __shfl_xor_sync(0xffffffffu, zz, 1);
-                    zz += __shfl_xor_sync(0xffffffffu, zz, 2);
-                    zz += __shfl_xor_sync(0xffffffffu, zz, 4);
-                    if ((lane & 7) == 0 && swrite) p.sigma[sidx] = zz;
-                }
+                if (!mbar_wait(&sm.bar_alpha, (uint32_t)tf & 1u, p.err, 100)) { ok = false; break; }      // the epilogue warps' partial sums
+                const float a = apart + sm.alpha_e[row] + __ldg(p.ba) - 1.0f;
+                sm.alpha_e[row] = 0.f;
+                const float sp = a > 20.f ? a : log1pf(expf(a));
+                const float zz = seg_scan8(sp * wrow, lane, qr.st);
+                if (swrite) p.sigma[sidx] = zz;
                 __syncwarp();
-                if (lane == 0) { if (rank == 0) mbar_arrive(&sm.bar_drain); else mbar_arrive_cluster(drain0); }   // after the alpha_e reads (see Smem)
-                named_bar_sync(2, tc6::NBUILD);
+                if (lane == 0) mbar_arrive(&sm.bar_drain);                 // after the alpha_e reads
             }
         }
     } else {
         // ============================================================ epilogue warps
         const int quad = warp & 3, grp = warp >> 2;
+        const int erow = quad * 32 + lane;
         const uint32_t tlane = (uint32_t)(quad * 32) << 16;
-        const uint32_t kblk0 = map_to_cta(&sm.bar_kblk[0], 0), drain0 = map_to_cta(&sm.bar_drain, 0);
         uint32_t n_acc = 0;
         bool ok = true;
         for (int t = 0; t < my_tiles && ok; ++t) {
-            for (int l = 0; l < 3 && ok; ++l, ++n_acc) {        // the layer-4 (last) epilogue runs on the builder warps
-                if (!(tid == 0 ? PNB_TIMED_WAIT(6, mbar_wait(&sm.bar_acc_full, n_acc & 1u, p.err, 69)) : mbar_wait(&sm.bar_acc_full, n_acc & 1u, p.err, 69))) { ok = false; break; }
-                const long long _te0 = clock64();
+            // ---- layer 1: accumulator + pre[point of this row] (the hoisted 224 inputs and the bias), prefetched PF chunks ahead
+            if (!mbar_wait(&sm.bar_prow[t & 1], (uint32_t)(t >> 1) & 1u, p.err, 102)) { ok = false; break; }
+            const int pi = max(sm.prow[t & 1][erow], 0);          // unused rows: any finite values (their outputs are never used)
+            const float4* pp = reinterpret_cast<const float4*>(p.pre + (size_t)pi * 256);
+            float4 pf[tc8::PF][4];
+#pragma unroll
+            for (int i = 0; i < tc8::PF; ++i) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) pf[i][e] = __ldg(pp + 4 * (grp + tc8::NGRP * i) + e);
+            }
+            if (!mbar_wait(&sm.bar_acc_full, n_acc & 1u, p.err, 98)) { ok = false; break; }
+            ++n_acc;
+            tc_fence_after();
+            {
+                const uint32_t accb = tQ + tlane;
+#pragma unroll
+                for (int i = 0; i < tc8::NCH; ++i) {
+                    const int g = grp + tc8::NGRP * i, c0 = 16 * g;
+                    uint32_t v[16];
+                    tmem_ld16(accb + (uint32_t)c0, v);
+                    tmem_ld_wait();
+                    uint32_t hh[8], ll[8];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const float4 b4 = pf[i % tc8::PF][e];
+                        float y0 = __uint_as_float(v[4 * e]) + b4.x, y1 = __uint_as_float(v[4 * e + 1]) + b4.y;
+                        float y2 = __uint_as_float(v[4 * e + 2]) + b4.z, y3 = __uint_as_float(v[4 * e + 3]) + b4.w;
+                        y0 = fmaxf(y0, LEAKY * y0); y1 = fmaxf(y1, LEAKY * y1); y2 = fmaxf(y2, LEAKY * y2); y3 = fmaxf(y3, LEAKY * y3);
+                        split_bf16x2(y0, y1, hh[2 * e], ll[2 * e]);
+                        split_bf16x2(y2, y3, hh[2 * e + 1], ll[2 * e + 1]);
+                    }
+                    if (i + tc8::PF < tc8::NCH) {
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) pf[i % tc8::PF][e] = __ldg(pp + 4 * (grp + tc8::NGRP * (i + tc8::PF)) + e);
+                    }
+                    tmem_st8(accb + (uint32_t)c0, hh);
+                    tmem_st8(accb + (uint32_t)c0 + 8u, ll);
+                    tmem_st_wait();
+                    tc_fence_before();
+                    mbar_arrive(&sm.bar_kblk[g >> 1]);
+                }
+            }
+            // ---- layers 2, 3
+            for (int l = 1; l < 3 && ok; ++l, ++n_acc) {
+                if (!mbar_wait(&sm.bar_acc_full, n_acc & 1u, p.err, 98)) { ok = false; break; }
                 tc_fence_after();
                 const uint32_t accb = ((l & 1) ? tP : tQ) + tlane;
-                {
-                    const float* bias = p.bias[l];
+                const float* bias = p.bias[l];
 #pragma unroll
-                    for (int i = 0; i < tc6::NCH; ++i) {
-                        const int g = grp + tc6::NGRP * i, c0 = 16 * g;
-                        uint32_t v[16];
-                        tmem_ld16(accb + (uint32_t)c0, v);
-                        tmem_ld_wait();
-                        uint32_t hh[8], ll[8];
+                for (int i = 0; i < tc8::NCH; ++i) {
+                    const int g = grp + tc8::NGRP * i, c0 = 16 * g;
+                    uint32_t v[16];
+                    tmem_ld16(accb + (uint32_t)c0, v);
+                    tmem_ld_wait();
+                    uint32_t hh[8], ll[8];
 #pragma unroll
-                        for (int e = 0; e < 8; ++e) {
-                            float2 bb = __ldg(reinterpret_cast<const float2*>(bias + c0) + e);
-                            float y0 = __uint_as_float(v[2 * e]) + bb.x, y1 = __uint_as_float(v[2 * e + 1]) + bb.y;
-                            y0 = fmaxf(y0, LEAKY * y0); y1 = fmaxf(y1, LEAKY * y1);
-                            split_bf16x2(y0, y1, hh[e], ll[e]);
-                        }
-                        tmem_st8(accb + (uint32_t)c0, hh);
-                        tmem_st8(accb + (uint32_t)c0 + 8u, ll);
-                        tmem_st_wait();
-                        tc_fence_before();
-                        __syncwarp();
-                        if (lane == 0) { if (rank == 0) mbar_arrive(&sm.bar_kblk[g >> 1]); else mbar_arrive_cluster(kblk0 + 8u * (uint32_t)(g >> 1)); }
+                    for (int e = 0; e < 8; ++e) {
+                        const float2 bb = __ldg(reinterpret_cast<const float2*>(bias + c0) + e);
+                        float y0 = __uint_as_float(v[2 * e]) + bb.x, y1 = __uint_as_float(v[2 * e + 1]) + bb.y;
+                        y0 = fmaxf(y0, LEAKY * y0); y1 = fmaxf(y1, LEAKY * y1);
+                        split_bf16x2(y0, y1, hh[e], ll[e]);
                     }
-                    if (tid == 0) prof_add(p, 7, clock64() - _te0);
+                    tmem_st8(accb + (uint32_t)c0, hh);
+                    tmem_st8(accb + (uint32_t)c0 + 8u, ll);
+                    tmem_st_wait();
+                    tc_fence_before();
+                    mbar_arrive(&sm.bar_kblk[g >> 1]);
                 }
             }
             if (!ok) break;
-            {   // this warp's share of the LAST epilogue (chunk groups 0, 1; the builder warps take 2, 3)
-                const int tile = 2 * (pair + t * npairs) + (int)rank;
-                if (!mbar_wait(&sm.bar_final, (uint32_t)t & 1u, p.err, 72)) { ok = false; break; }
+            {   // this warp's share of the LAST epilogue (chunk groups 1, 2 of 3; the builder warps take group 0)
+                if (!mbar_wait(&sm.bar_final, (uint32_t)t & 1u, p.err, 101)) { ok = false; break; }
                 tc_fence_after();
-                const int erow = quad * 32 + lane;
-                const int sidx = tile * TSAMP + (erow >> 3);
-                const float apart = last_chunks<4, 4>(p, tP + tlane, grp, sm.wc[t & 1][erow], sidx, sidx < n_valid, lane);
+                const QuadRow qr = quad_row(sm.qhead[t & 1][quad], (int)sm.qtotal[t & 1][quad], lane);
+                const int sidx = qr.live ? (int)p.vorder[sm.qfirst[t & 1][quad] + qr.j] : 0;
+                const float apart = last_chunks_packed<3, 5>(p, tP + tlane, 1 + grp, sm.wc[t & 1][erow], qr.st, qr.is_end && sidx < n_valid, sidx, lane);
                 tc_fence_before();
                 atomicAdd(&sm.alpha_e[erow], apart);
                 __syncwarp();
-                if (lane == 0) {
-                    mbar_arrive(&sm.bar_alpha);
-                    if (rank == 0) mbar_arrive(&sm.bar_drain); else mbar_arrive_cluster(drain0);
-                }
+                if (lane == 0) { mbar_arrive(&sm.bar_alpha); mbar_arrive(&sm.bar_drain); }
             }
         }
     }
-    if (tid == 0) prof_add(p, 9, clock64() - _tk0);
-    if (tid == 0 && (p.dbg_flags & 4) && blockIdx.x < 192) {      // per-CTA cycles and SM id (needs a 512-int err buffer)
+    if (tid == 0 && (p.dbg_flags & 4) && blockIdx.x < 192) {      // per-CTA cycles and SM id; [32 + 192] = number of quadrants
         uint32_t smid;
         asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
         reinterpret_cast<long long*>(p.err)[32 + blockIdx.x] = ((clock64() - _tk0) & 0xffffffffffffll) | ((long long)smid << 48);
+        if (blockIdx.x == 0) reinterpret_cast<long long*>(p.err)[32 + 192] = n_quads;
     }
-    __syncwarp();
     tc_fence_before();
-    cluster_sync_all();
-    if (warp == W_ISSUE) tmem_dealloc2<512>(sm.tmem_base);
+    __syncthreads();
+    if (warp == W_ISSUE) tmem_dealloc<512>(sm.tmem_base);
 }
 
 // =====================================================================================================================
-// Colour branch on the tensor cores: per 128 valid samples  [hbar(256) | PE4(view)(24)] -> 128 -> 128 -> 128 (tcgen05,
-// BF16x3) -> 3 (CUDA cores) -> sigmoid*1.002-0.001   (reference: point_aggregators.py:631-637, 269-273).
-// Layer 1 reads its operand from shared memory (SS), layers 2-3 from tensor memory (TS).  TMEM: accumulator cols
-// 0..127, A_hi 128..191, A_lo 192..255.  320 threads: 8 worker warps (build + epilogues), loader, issuer.
+// Colour branch: packed weight images of colour_branch.{0,2,4} ([128 x 32] bf16 hi / lo per K block) and the kernel parameters.
 namespace ctc {
-constexpr int NTHR = 320, NWORK = 256, NSTAGE = 4;
 constexpr int IMG = 128 * 64;                 // [128 x 32] bf16 weight image
 constexpr int NBLK = 9 + 4 + 4;               // K blocks of the three layers
 constexpr int IMGS_PER_TILE = 2 * NBLK;
 __host__ __device__ constexpr int nkb_of(int l) { return l == 0 ? 9 : 4; }
 __host__ __device__ constexpr int img_base(int l) { return l == 0 ? 0 : l == 1 ? 9 : 13; }
-struct Smem {
-    unsigned char a_hi[9 * tc::ABLK];
-    unsigned char a_lo[9 * tc::ABLK];
-    unsigned char b[NSTAGE][IMG];
-    float part[2][128][4];
-    uint32_t samp[128];
-    uint64_t bar_full[NSTAGE], bar_empty[NSTAGE], bar_a_ready, bar_acc_full;
-    uint32_t tmem_base;
-};
 }  // namespace ctc
 
 struct ColorTcParams {
@@ -2022,228 +1120,8 @@ struct ColorTcParams {
     int* err;
 };
 
-__global__ void __launch_bounds__(ctc::NTHR, 1) k_color_tc(ColorTcParams p) {
-    using namespace ctc;
-    extern __shared__ __align__(1024) unsigned char smem_raw[];
-    Smem& sm = *reinterpret_cast<Smem*>(smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u));
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const pnb_query_t& q = p.q;
-    const int n_valid = min(q.counters[PNB_QC_N_VALID], p.hbar_cap);
-    const int n_tiles = (n_valid + 127) / 128;
-    const int my_tiles = n_tiles > (int)blockIdx.x ? (n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
-
-    if (tid == 0) {
-        for (int s = 0; s < NSTAGE; ++s) { mbar_init(&sm.bar_full[s], 1); mbar_init(&sm.bar_empty[s], 1); }
-        mbar_init(&sm.bar_a_ready, NWORK);
-        mbar_init(&sm.bar_acc_full, 1);
-        mbar_fence_init();
-    }
-    if (warp == 9) tmem_alloc<256>(&sm.tmem_base);
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tacc = sm.tmem_base, t_ahi = tacc + 128u, t_alo = tacc + 192u;
-
-    if (warp == 8) {
-        if (lane == 0) {
-            const uint32_t total = (uint32_t)my_tiles * IMGS_PER_TILE;
-            for (uint32_t n = 0; n < total; ++n) {
-                const uint32_t s = n % NSTAGE, ph = (n / NSTAGE) & 1u;
-                if (!mbar_wait(&sm.bar_empty[s], ph ^ 1u, p.err, 21)) break;
-                mbar_arrive_expect_tx(&sm.bar_full[s], IMG);
-                bulk_g2s(sm.b[s], p.wimg + (size_t)(n % IMGS_PER_TILE) * IMG, IMG, &sm.bar_full[s]);
-            }
-        }
-    } else if (warp == 9) {
-        {   // whole warp, warp-uniform; one elected lane issues
-            const uint32_t idesc = make_idesc_bf16(128, 128);
-            const uint32_t hiw = desc_hi<tc::LAYOUT>();
-            const uint32_t b0_lo = desc_lo<tc::LAYOUT>(smem_u32(sm.b[0]));
-            const uint32_t ahi_lo = desc_lo<tc::LAYOUT>(smem_u32(sm.a_hi)), alo_lo = desc_lo<tc::LAYOUT>(smem_u32(sm.a_lo));
-            constexpr uint32_t KADV = kstep_adv16<tc::LAYOUT>();
-            uint32_t n = 0, lyr = 0;
-            bool ok = true;
-            for (int t = 0; t < my_tiles && ok; ++t) {
-                for (int l = 0; l < 3 && ok; ++l, ++lyr) {
-                    if (!mbar_wait(&sm.bar_a_ready, lyr & 1u, p.err, 22)) { ok = false; break; }
-                    tc_fence_after();
-                    const int nkb = nkb_of(l);
-                    for (int kb = 0; kb < nkb && ok; ++kb) {
-                        const uint32_t akb_hi = ahi_lo + (uint32_t)kb * (tc::ABLK >> 4), akb_lo = alo_lo + (uint32_t)kb * (tc::ABLK >> 4);
-                        const uint32_t tcol = (uint32_t)(kb * 16);
-                        {
-                            const uint32_t s = n & (NSTAGE - 1), ph = (n >> 2) & 1u;
-                            if (!mbar_wait(&sm.bar_full[s], ph, p.err, 23)) { ok = false; break; }
-                            tc_fence_after();
-                            const uint32_t bl = b0_lo + s * (IMG >> 4);
-                            if (l == 0) {
-                                mma_ss2_w(tacc, akb_hi, hiw, bl, hiw, idesc, kb ? 1u : 0u);
-                                mma_ss2_w(tacc, akb_lo, hiw, bl, hiw, idesc, 1u);
-                                mma_ss2_w(tacc, akb_hi + KADV, hiw, bl + KADV, hiw, idesc, 1u);
-                                mma_ss2_w(tacc, akb_lo + KADV, hiw, bl + KADV, hiw, idesc, 1u);
-                            } else {
-                                mma_ts2_w(tacc, t_ahi + tcol, bl, hiw, idesc, kb ? 1u : 0u);
-                                mma_ts2_w(tacc, t_alo + tcol, bl, hiw, idesc, 1u);
-                                mma_ts2_w(tacc, t_ahi + tcol + 8u, bl + KADV, hiw, idesc, 1u);
-                                mma_ts2_w(tacc, t_alo + tcol + 8u, bl + KADV, hiw, idesc, 1u);
-                            }
-                            mma_commit_w(&sm.bar_empty[s]);
-                            ++n;
-                        }
-                        {
-                            const uint32_t s = n & (NSTAGE - 1), ph = (n >> 2) & 1u;
-                            if (!mbar_wait(&sm.bar_full[s], ph, p.err, 23)) { ok = false; break; }
-                            tc_fence_after();
-                            const uint32_t bl = b0_lo + s * (IMG >> 4);
-                            if (l == 0) {
-                                mma_ss2_w(tacc, akb_hi, hiw, bl, hiw, idesc, 1u);
-                                mma_ss2_w(tacc, akb_hi + KADV, hiw, bl + KADV, hiw, idesc, 1u);
-                            } else {
-                                mma_ts2_w(tacc, t_ahi + tcol, bl, hiw, idesc, 1u);
-                                mma_ts2_w(tacc, t_ahi + tcol + 8u, bl + KADV, hiw, idesc, 1u);
-                            }
-                            mma_commit_w(&sm.bar_empty[s]);
-                            ++n;
-                        }
-                    }
-                    mma_commit_w(&sm.bar_acc_full);
-                }
-            }
-        }
-    } else {
-        const int quad = warp & 3, half = warp >> 2;
-        const int erow = quad * 32 + lane;
-        const uint32_t tlane = (uint32_t)(quad * 32) << 16;
-        uint32_t lyr = 0;
-        bool ok = true;
-        for (int t = 0; t < my_tiles && ok; ++t) {
-            const int tile = (int)blockIdx.x + t * (int)gridDim.x;
-            {   // ---- build: 2 threads per sample row
-                const int row = warp * 16 + (lane >> 1), hf = lane & 1;
-                const int vi = tile * 128 + row;
-                uint32_t s = 0xffffffffu;
-                if (vi < n_valid) {
-                    s = q.valid_list[vi];
-                    const float4* src = (const float4*)(p.hbar + (size_t)vi * 256 + hf * 128);
-#pragma unroll 4
-                    for (int c = 0; c < 16; ++c) {
-                        float4 a = __ldg(src + 2 * c), b = __ldg(src + 2 * c + 1);
-                        float f8[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-                        int col = hf * 128 + 8 * c;
-                        uint32_t h[4], l[4];
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) split_bf16x2(f8[2 * i], f8[2 * i + 1], h[i], l[i]);
-                        uint32_t off = (uint32_t)(col >> 5) * tc::ABLK + tile_offset_bytes<tc::LAYOUT>(row, col & 31);
-                        *reinterpret_cast<uint4*>(sm.a_hi + off) = make_uint4(h[0], h[1], h[2], h[3]);
-                        *reinterpret_cast<uint4*>(sm.a_lo + off) = make_uint4(l[0], l[1], l[2], l[3]);
-                    }
-                } else {
-                    for (int c = 0; c < 16; ++c) {
-                        int col = hf * 128 + 8 * c;
-                        uint32_t off = (uint32_t)(col >> 5) * tc::ABLK + tile_offset_bytes<tc::LAYOUT>(row, col & 31);
-                        *reinterpret_cast<uint4*>(sm.a_hi + off) = make_uint4(0u, 0u, 0u, 0u);
-                        *reinterpret_cast<uint4*>(sm.a_lo + off) = make_uint4(0u, 0u, 0u, 0u);
-                    }
-                }
-                if (hf == 0) {
-                    sm.samp[row] = s;
-                    float pe[32];
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) pe[i] = 0.f;
-                    if (s != 0xffffffffu) {
-                        int r = (int)(q.samp_ray[s] >> 7);
-                        float ov[3];
-                        rot3t(p.o.Rw2c, q.raydir[3 * r], q.raydir[3 * r + 1], q.raydir[3 * r + 2], ov[0], ov[1], ov[2]);
-#pragma unroll
-                        for (int d = 0; d < 3; ++d) {     // ori=True layout: sin block (d*4+j) then cos block
-                            float sc[8];
-                            pe_doubling<4>(ov[d], sc);
-#pragma unroll
-                            for (int j = 0; j < 4; ++j) { pe[d * 4 + j] = sc[2 * j]; pe[12 + d * 4 + j] = sc[2 * j + 1]; }
-                        }
-                    }
-#pragma unroll
-                    for (int c = 0; c < 4; ++c) {
-                        uint32_t h[4], l[4];
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) split_bf16x2(pe[8 * c + 2 * i], pe[8 * c + 2 * i + 1], h[i], l[i]);
-                        uint32_t off = 8u * tc::ABLK + tile_offset_bytes<tc::LAYOUT>(row, 8 * c);
-                        *reinterpret_cast<uint4*>(sm.a_hi + off) = make_uint4(h[0], h[1], h[2], h[3]);
-                        *reinterpret_cast<uint4*>(sm.a_lo + off) = make_uint4(l[0], l[1], l[2], l[3]);
-                    }
-                }
-            }
-            fence_proxy_async();
-            mbar_arrive(&sm.bar_a_ready);
-            for (int l = 0; l < 3 && ok; ++l, ++lyr) {
-                if (!mbar_wait(&sm.bar_acc_full, lyr & 1u, p.err, 24)) { ok = false; break; }
-                tc_fence_after();
-                const float* bias = p.bias[l];
-                float d0 = 0.f, d1 = 0.f, d2 = 0.f;
-#pragma unroll 1
-                for (int ch = 0; ch < 2; ++ch) {
-                    const int c0 = half * 64 + ch * 32;
-                    uint32_t v[32];
-                    tmem_ld32(tacc + tlane + (uint32_t)c0, v);
-                    tmem_ld_wait();
-                    if (l < 2) {
-                        uint32_t hh[16], ll[16];
-#pragma unroll
-                        for (int e = 0; e < 16; ++e) {
-                            float2 bb = __ldg(reinterpret_cast<const float2*>(bias + c0) + e);
-                            float y0 = __uint_as_float(v[2 * e]) + bb.x, y1 = __uint_as_float(v[2 * e + 1]) + bb.y;
-                            y0 = fmaxf(y0, tc::LEAKY * y0); y1 = fmaxf(y1, tc::LEAKY * y1);
-                            split_bf16x2(y0, y1, hh[e], ll[e]);
-                        }
-                        const uint32_t colp = (uint32_t)(c0 >> 1);
-                        tmem_st8(t_ahi + tlane + colp, hh);
-                        tmem_st8(t_ahi + tlane + colp + 8u, hh + 8);
-                        tmem_st8(t_alo + tlane + colp, ll);
-                        tmem_st8(t_alo + tlane + colp + 8u, ll + 8);
-                    } else {
-#pragma unroll
-                        for (int e = 0; e < 32; ++e) {
-                            float y = __uint_as_float(v[e]) + __ldg(bias + c0 + e);
-                            y = fmaxf(y, tc::LEAKY * y);
-                            const float* wr = p.w3t + (c0 + e) * 3;
-                            d0 = fmaf(y, __ldg(wr), d0); d1 = fmaf(y, __ldg(wr + 1), d1); d2 = fmaf(y, __ldg(wr + 2), d2);
-                        }
-                    }
-                }
-                if (l < 2) {
-                    tmem_st_wait();
-                    tc_fence_before();
-                    mbar_arrive(&sm.bar_a_ready);
-                } else {
-                    tc_fence_before();
-                    sm.part[half][erow][0] = d0; sm.part[half][erow][1] = d1; sm.part[half][erow][2] = d2;
-                    named_bar_sync(1, NWORK);
-                    if (half == 0) {
-                        uint32_t s = sm.samp[erow];
-                        if (s != 0xffffffffu) {
-                            float4 o4;
-                            o4.x = p.sigma[tile * 128 + erow];
-                            float r0 = sm.part[0][erow][0] + sm.part[1][erow][0] + __ldg(p.b3);
-                            float r1 = sm.part[0][erow][1] + sm.part[1][erow][1] + __ldg(p.b3 + 1);
-                            float r2 = sm.part[0][erow][2] + sm.part[1][erow][2] + __ldg(p.b3 + 2);
-                            o4.y = 1.0f / (1.0f + expf(-r0)) * (1.0f + 2.0f * 0.001f) - 0.001f;
-                            o4.z = 1.0f / (1.0f + expf(-r1)) * (1.0f + 2.0f * 0.001f) - 0.001f;
-                            o4.w = 1.0f / (1.0f + expf(-r2)) * (1.0f + 2.0f * 0.001f) - 0.001f;
-                            p.sigma_rgb[s] = o4;
-                        }
-                    }
-                    named_bar_sync(1, NWORK);
-                }
-            }
-        }
-    }
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 9) tmem_dealloc<256>(tacc);
-}
-
 // =====================================================================================================================
-// Colour branch, pipelined (v2).  The pair kernel (v6) writes h-bar already split into bf16 hi / lo and laid out as the
+// Colour branch, pipelined.  The pair kernel writes h-bar already split into bf16 hi / lo and laid out as the
 // tcgen05 A-operand blocks of this kernel: per 128 consecutive valid samples 8 K-blocks x {hi, lo} x [128 x 32]
 // (interleaved core-matrix layout) = one contiguous 128 KB region.  So the layer-1 operand is ONE bulk copy (TMA engine)
 // per tile - no builder warps, no register traffic - issued as soon as the previous tile's layer-1 MMAs have completed,
@@ -2538,99 +1416,107 @@ extern "C" int pnb_mlp_pack(const pnb_mlp_t* mlp, void* d_out, size_t out_bytes,
     return PNB_OK;
 }
 
-static size_t pack_sc_max(int cap) { return (size_t)cap / tc7::PACK_S + 2; }
-extern "C" size_t pnb_shade_tc_bytes(int max_valid_samples) {
-    const size_t cap = (size_t)max_valid_samples;
-    return align_up((cap + 127) / 128 * 128 * 256 * sizeof(float)) + align_up(cap * sizeof(float)) +
-           2 * align_up(cap + 16) + align_up(pack_sc_max(max_valid_samples) * 4) + 2 * align_up((cap + 2) * 4) + align_up(16) + 256;   // + v7 packing tables
+// Hoisted layer-1 table of a frozen point cloud (k_point_pre): d_pre [N][256] fp32.
+extern "C" size_t pnb_point_pre_bytes(int N) { return (size_t)(N > 0 ? N : 0) * 256 * sizeof(float); }
+extern "C" int pnb_point_pre(const pnb_points_t* pts, const pnb_mlp_t* mlp, float* d_pre, size_t pre_bytes, pnb_stream_t stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    PNB_REQUIRE(pts && mlp && d_pre, PNB_ERR_INVALID, "pnb_point_pre: null argument");
+    PNB_REQUIRE(pre_bytes >= pnb_point_pre_bytes(pts->N), PNB_ERR_WORKSPACE, "pnb_point_pre: buffer too small");
+    if (pts->N > 0) k_point_pre<<<(pts->N + 31) / 32, 256, 0, stream>>>(pts->emb, pts->N, mlp->w[0], mlp->b[0], d_pre);
+    PNB_CHECK_CUDA(cudaGetLastError());
+    return PNB_OK;
 }
 
-// Tensor-core forward: per-pair MLPs on tcgen05 (BF16x3), colour branch on CUDA cores.  ws: >= pnb_shade_tc_bytes.
-// d_err: device int32, set non-zero if the in-kernel pipeline timed out (results invalid).
+static size_t pack_sc_max(int cap) { return (size_t)cap / tc7::PACK_S + 3; }
+namespace {
+struct TcWs {   // carve-up of the caller's workspace (all sizes from max_valid_samples; the kernels read the live counts on the device)
+    float* hbar; float* sigma; uint32_t* sc_quads; uint32_t* quad_local; uint32_t* quad_first; uint32_t* vorder; unsigned char* vcntp; int* pack_cnt;
+    TcWs(void* ws, size_t ws_bytes, int cap) {
+        Carver c(ws, ws_bytes);
+        hbar = c.take<float>(((size_t)cap + 127) / 128 * 128 * 256);   // whole 128-sample colour tiles
+        sigma = c.take<float>((size_t)cap);
+        sc_quads = c.take<uint32_t>(pack_sc_max(cap));
+        quad_local = c.take<uint32_t>((size_t)cap + 2);
+        quad_first = c.take<uint32_t>((size_t)cap + 2);
+        vorder = c.take<uint32_t>((size_t)cap + 2);
+        vcntp = c.take<unsigned char>((size_t)cap + 16);
+        pack_cnt = c.take<int>(4);
+    }
+};
+}  // namespace
+extern "C" size_t pnb_shade_tc_bytes(int max_valid_samples) {
+    const size_t cap = (size_t)max_valid_samples;
+    return align_up((cap + 127) / 128 * 128 * 256 * sizeof(float)) + align_up(cap * sizeof(float)) + align_up(pack_sc_max(max_valid_samples) * 4) +
+           3 * align_up((cap + 2) * 4) + align_up(cap + 16) + align_up(16) + 256;
+}
+// diagnostics / tests: device pointers of the row-packing tables inside a workspace laid out for max_valid_samples
+extern "C" int pnb_shade_tc_tables(void* ws, size_t ws_bytes, int max_valid_samples, void** vorder, void** vcntp, void** quad_first, void** pack_cnt) {
+    PNB_REQUIRE(ws && ws_bytes >= pnb_shade_tc_bytes(max_valid_samples), PNB_ERR_WORKSPACE, "pnb_shade_tc_tables: workspace too small");
+    TcWs w(ws, ws_bytes, max_valid_samples);
+    if (vorder) *vorder = w.vorder;
+    if (vcntp) *vcntp = w.vcntp;
+    if (quad_first) *quad_first = w.quad_first;
+    if (pack_cnt) *pack_cnt = w.pack_cnt;
+    return PNB_OK;
+}
+
+// Tensor-core forward: row packing, per-pair MLPs and colour branch on tcgen05 (BF16x3).  ws: >= pnb_shade_tc_bytes.
 extern "C" int pnb_shade_forward_tc(const pnb_query_t* q, const pnb_points_t* pts, const pnb_mlp_t* mlp, const void* d_packed,
-                                    const pnb_shade_opts_t* opts, float* d_sigma_rgb, void* ws, size_t ws_bytes,
-                                    int max_valid_samples, int stage_mask, int* d_err, pnb_stream_t stream_) {
+                                    const float* d_point_pre, const pnb_shade_opts_t* opts, float* d_sigma_rgb, void* ws, size_t ws_bytes,
+                                    int max_valid_samples, int flags, int* d_err, pnb_stream_t stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     PNB_REQUIRE(q && pts && mlp && d_packed && opts && d_sigma_rgb && ws && d_err, PNB_ERR_INVALID, "pnb_shade_forward_tc: null argument");
     PNB_REQUIRE(q->K >= 1 && q->K <= PNB_MAX_K, PNB_ERR_UNSUPPORTED, "pnb_shade_forward_tc: K=%d unsupported", q->K);
+    PNB_REQUIRE(max_valid_samples > 0, PNB_ERR_INVALID, "pnb_shade_forward_tc: max_valid_samples must be positive");
     PNB_REQUIRE(ws_bytes >= pnb_shade_tc_bytes(max_valid_samples), PNB_ERR_WORKSPACE, "pnb_shade_forward_tc: workspace too small");
+    const bool frozen = (flags & PNB_TC_FROZEN) != 0;
+    PNB_REQUIRE(!frozen || d_point_pre, PNB_ERR_INVALID, "pnb_shade_forward_tc: PNB_TC_FROZEN needs the table of pnb_point_pre");
     static int configured[64] = {0}, n_sm_of[64] = {0};      // per device of this process (one process per GPU is the norm)
     int dev = 0;
     PNB_CHECK_CUDA(cudaGetDevice(&dev));
     PNB_REQUIRE(dev >= 0 && dev < 64, PNB_ERR_UNSUPPORTED, "pnb_shade_forward_tc: device ordinal %d", dev);
     // interleaved (non-swizzled) operand layout: 128-byte alignment of the carve-out is sufficient
     constexpr size_t kSmemMax = 232448;   // 227 KB opt-in limit per block on sm_100
-    const size_t smem_tc = sizeof(tc::Smem) + 128, smem_tc3 = sizeof(tc3::Smem) + 128, smem_cb = sizeof(cb::Smem),
-                 smem_ctc = sizeof(ctc::Smem) + 128, smem_tc5 = sizeof(tc5::Smem) + 128, smem_tc6 = sizeof(tc6::Smem) + 128, smem_ctc2 = sizeof(ctc2::Smem) + 128, smem_tc7 = sizeof(tc7::Smem) + 128;
-    static_assert(sizeof(tc5::Smem) + 128 <= kSmemMax, "v5 shared-memory carve-out exceeds the per-block limit");
-    static_assert(sizeof(tc6::Smem) + 128 <= kSmemMax, "v6 shared-memory carve-out exceeds the per-block limit");
-    static_assert(sizeof(ctc2::Smem) + 128 <= kSmemMax, "colour v2 shared-memory carve-out exceeds the per-block limit");
+    const size_t smem_tc7 = sizeof(tc7::Smem) + 128, smem_tc8 = sizeof(tc8::Smem) + 128, smem_ctc2 = sizeof(ctc2::Smem) + 128;
     static_assert(sizeof(tc7::Smem) + 128 <= kSmemMax, "v7 shared-memory carve-out exceeds the per-block limit");
-    static_assert((tc3::NSTAGE & (tc3::NSTAGE - 1)) == 0 && tc3::NSTAGE == 4, "issuer assumes a 4-stage ring");
-    static_assert(sizeof(tc::Smem) + 128 <= kSmemMax && sizeof(tc3::Smem) + 128 <= kSmemMax && sizeof(ctc::Smem) + 128 <= kSmemMax &&
-                  sizeof(cb::Smem) <= kSmemMax, "shared-memory carve-out exceeds the sm_100 per-block limit");
+    static_assert(sizeof(tc8::Smem) + 128 <= kSmemMax, "v8 shared-memory carve-out exceeds the per-block limit");
+    static_assert(sizeof(ctc2::Smem) + 128 <= kSmemMax, "colour kernel shared-memory carve-out exceeds the per-block limit");
+    static_assert(tc7::NSTAGE == 4, "the v7 issuer assumes a 4-stage ring");
     if (!configured[dev]) {
-        PNB_CHECK_CUDA(cudaFuncSetAttribute(k_shade_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tc));
-        PNB_CHECK_CUDA(cudaFuncSetAttribute(k_shade_tc3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tc3));
-        PNB_CHECK_CUDA(cudaFuncSetAttribute(k_shade_tc5, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tc5));
-        PNB_CHECK_CUDA(cudaFuncSetAttribute(k_shade_tc6, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tc6));
         PNB_CHECK_CUDA(cudaFuncSetAttribute(k_shade_tc7, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tc7));
-        PNB_CHECK_CUDA(cudaFuncSetAttribute(k_color_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_ctc));
+        PNB_CHECK_CUDA(cudaFuncSetAttribute(k_shade_tc8, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tc8));
         PNB_CHECK_CUDA(cudaFuncSetAttribute(k_color_tc2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_ctc2));
-        PNB_CHECK_CUDA(cudaFuncSetAttribute(k_color_branch, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cb));
         PNB_CHECK_CUDA(cudaDeviceGetAttribute(&n_sm_of[dev], cudaDevAttrMultiProcessorCount, dev));
         configured[dev] = 1;
     }
     const int n_sm = n_sm_of[dev];
-    Carver c(ws, ws_bytes);
-    float* hbar = c.take<float>(((size_t)max_valid_samples + 127) / 128 * 128 * 256);   // whole 128-sample colour tiles
-    float* sigma = c.take<float>((size_t)max_valid_samples);
-    unsigned char* vcnt = c.take<unsigned char>((size_t)max_valid_samples + 16);
-    uint32_t* sc_quads = c.take<uint32_t>(pack_sc_max(max_valid_samples));
-    uint32_t* quad_first = c.take<uint32_t>((size_t)max_valid_samples + 2);
-    uint32_t* vorder = c.take<uint32_t>((size_t)max_valid_samples + 2);
-    unsigned char* vcntp = c.take<unsigned char>((size_t)max_valid_samples + 16);
-    int* pack_cnt = c.take<int>(4);
+    TcWs w(ws, ws_bytes, max_valid_samples);
     ShadeTcParams p;
     p.q = *q; p.pts = *pts; p.o = *opts; p.wimg = (const unsigned char*)d_packed;
     for (int l = 0; l < 4; ++l) p.bias[l] = mlp->b[l];
     p.wa = mlp->w[4];
     p.ba = mlp->b[4];
-    p.hbar = hbar; p.sigma = sigma; p.hbar_cap = max_valid_samples; p.err = d_err;
-    p.dbg_no_weights = (stage_mask & 64) ? 1 : 0;
-    p.dbg_flags = (stage_mask >> 8) & 0xff;
-    const bool packed_rows = (stage_mask & (1 << 17)) != 0;   // v7: rows packed to the valid pairs
-    p.vcnt = vcntp; p.vorder = vorder; p.quad_first = quad_first; p.pack_cnt = pack_cnt;
-    const bool color_v2 = (stage_mask & (1 << 16)) != 0;      // pipelined colour kernel fed by operand-format h-bar (written by the v5 / v6 pair kernels)
-    PNB_REQUIRE(!color_v2 || (((stage_mask & (128 | 32)) || packed_rows) && (stage_mask & 8)), PNB_ERR_INVALID, "pnb_shade_forward_tc: colour v2 needs the v5 / v6 / v7 pair pipeline");
-    p.hbar_fmt = color_v2 ? 1 : 0;
-    if (stage_mask & 1) {
-        if (packed_rows) {
-            const int cap = max_valid_samples, n_sc = (int)pack_sc_max(cap);
-            k_pack_cnt<<<(cap + 255) / 256, 256, 0, stream>>>(p.q, cap, vcnt);
-            k_pack_quads<false><<<(n_sc + 127) / 128, 128, 0, stream>>>(p.q, cap, vcnt, sc_quads, quad_first, vorder, vcntp);
-            k_pack_scan<<<1, 1024, 0, stream>>>(p.q, cap, sc_quads, quad_first, pack_cnt);
-            k_pack_quads<true><<<(n_sc + 127) / 128, 128, 0, stream>>>(p.q, cap, vcnt, sc_quads, quad_first, vorder, vcntp);
-            k_shade_tc7<<<n_sm, tc7::NTHR, smem_tc7, stream>>>(p);                              // v5 with rows packed to the valid pairs
-        } else if (stage_mask & 128) k_shade_tc6<<<n_sm & ~1, tc6::NTHR, smem_tc6, stream>>>(p);     // v5 on CTA pairs (cta_group::2)
-        else if (stage_mask & 32) k_shade_tc5<<<n_sm, tc5::NTHR, smem_tc5, stream>>>(p);           // TMEM ping-pong, chunk-pipelined
-        else if (stage_mask & 4) k_shade_tc3<<<n_sm, tc3::NTHR, smem_tc3, stream>>>(p);   // TS-form pipeline (A in tensor memory)
-        else k_shade_tc<<<n_sm, tc::NTHR, smem_tc, stream>>>(p);
+    p.hbar = w.hbar; p.sigma = w.sigma; p.hbar_cap = max_valid_samples; p.err = d_err;
+    p.dbg_no_weights = (flags & PNB_TC_DBG_NO_WEIGHTS) ? 1 : 0;
+    p.dbg_flags = (flags >> 8) & 0xff;
+    p.vcnt = w.vcntp; p.vorder = w.vorder; p.quad_first = w.quad_first; p.pack_cnt = w.pack_cnt;
+    p.pre = d_point_pre;
+    p.hbar_fmt = 1;                                           // h-bar in the colour kernel's operand format
+    if (flags & PNB_TC_PAIRS) {
+        const int cap = max_valid_samples, n_sc = (int)pack_sc_max(cap);
+        k_pack_quads<<<(n_sc + 7) / 8, 256, 0, stream>>>(p.q, cap, w.sc_quads, w.quad_local, w.vorder, w.vcntp, (float4*)d_sigma_rgb);
+        k_pack_scan<<<1, 1024, 0, stream>>>(p.q, cap, w.sc_quads, w.quad_first, w.pack_cnt);
+        k_pack_place<<<(cap + 255) / 256, 256, 0, stream>>>(p.q, cap, w.sc_quads, w.quad_local, w.quad_first);
+        if (frozen) k_shade_tc8<<<n_sm, tc8::NTHR, smem_tc8, stream>>>(p);
+        else k_shade_tc7<<<n_sm, tc7::NTHR, smem_tc7, stream>>>(p);
     }
-    ColorParams cp;
-    cp.q = *q; cp.o = *opts;
-    for (int i = 0; i < 4; ++i) { cp.w[i] = mlp->w[5 + i]; cp.b[i] = mlp->b[5 + i]; }
-    cp.hbar = hbar; cp.sigma = sigma; cp.hbar_cap = max_valid_samples; cp.sigma_rgb = (float4*)d_sigma_rgb;
-    if ((stage_mask & 2) && (stage_mask & 8)) {          // colour branch on tcgen05
+    if (flags & PNB_TC_COLOR) {
         ColorTcParams ct;
         ct.q = *q; ct.o = *opts; ct.wimg = (const unsigned char*)d_packed + pack_pairs_bytes();
         for (int i = 0; i < 3; ++i) ct.bias[i] = mlp->b[5 + i];
         ct.w3t = mlp->w[8]; ct.b3 = mlp->b[8];
-        ct.hbar = hbar; ct.sigma = sigma; ct.hbar_cap = max_valid_samples; ct.sigma_rgb = (float4*)d_sigma_rgb; ct.err = d_err;
-        if (color_v2) k_color_tc2<<<n_sm, ctc2::NTHR, smem_ctc2, stream>>>(ct);
-        else k_color_tc<<<n_sm, ctc::NTHR, smem_ctc, stream>>>(ct);
-    } else if (stage_mask & 2) {
-        k_color_branch<<<n_sm * 2, cb::NTHREADS, smem_cb, stream>>>(cp);
+        ct.hbar = w.hbar; ct.sigma = w.sigma; ct.hbar_cap = max_valid_samples; ct.sigma_rgb = (float4*)d_sigma_rgb; ct.err = d_err;
+        k_color_tc2<<<n_sm, ctc2::NTHR, smem_ctc2, stream>>>(ct);
     }
     PNB_CHECK_CUDA(cudaGetLastError());
     return PNB_OK;

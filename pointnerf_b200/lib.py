@@ -17,6 +17,10 @@ class PnbError(RuntimeError):
     pass
 
 
+class PnbOverflow(PnbError):
+    """The shading workspace was smaller than the number of valid samples of a call (the extra samples were dropped)."""
+
+
 class Grid(C.Structure):
     _fields_ = [("lo", C.c_float * 3), ("svs", C.c_float * 3), ("dim", C.c_int32 * 3), ("P", C.c_int32),
                 ("parity_slot0", C.c_int32), ("n_points", C.c_int32), ("n_words", C.c_uint32),
@@ -52,11 +56,17 @@ QC = dict(n_cand=0, n_valid=1, n_pairs=2, R1=3, R2=4, overflow=5)
 
 # every symbol include/pnb200.h declares (tests check that the .so exports all of them)
 SYMBOLS = ["pnb_version", "pnb_last_error", "pnb_struct_size", "pnb_grid_bytes", "pnb_grid_build", "pnb_query_bytes", "pnb_query",
-           "pnb_query_export", "pnb_shade_bytes", "pnb_shade_forward", "pnb_composite_forward", "pnb_umma_selftest",
-           "pnb_mlp_pack_bytes", "pnb_mlp_pack", "pnb_shade_tc_bytes", "pnb_shade_forward_tc",
-           "pnb_backward_bytes", "pnb_shade_backward", "pnb_umma_bench", "pnb_umma_selftest2"]
+           "pnb_query_export", "pnb_shade_bytes", "pnb_shade_forward", "pnb_composite_forward",
+           "pnb_mlp_pack_bytes", "pnb_mlp_pack", "pnb_point_pre_bytes", "pnb_point_pre", "pnb_shade_tc_bytes", "pnb_shade_forward_tc",
+           "pnb_shade_tc_tables", "pnb_backward_bytes", "pnb_shade_backward"]
+# test-only library (csrc/selftest/pnb200_selftest.h)
+SELFTEST_LIB_PATH = os.path.join(_HERE, "csrc", "libpnb200_selftest.so")
+SELFTEST_SYMBOLS = ["pnb_selftest_last_error", "pnb_umma_selftest", "pnb_umma_bench", "pnb_umma_selftest2"]
+# flags of pnb_shade_forward_tc
+TC_PAIRS, TC_COLOR, TC_FROZEN, TC_DBG_NO_WEIGHTS = 1, 2, 4, 64
 
 _lib = None
+_selftest = None
 
 
 def load():
@@ -104,17 +114,37 @@ def load():
     lib.pnb_mlp_pack_bytes.argtypes = []
     lib.pnb_mlp_pack.restype = C.c_int
     lib.pnb_mlp_pack.argtypes = [C.POINTER(Mlp), C.c_void_p, C.c_size_t, C.c_void_p]
+    lib.pnb_point_pre_bytes.restype = C.c_size_t
+    lib.pnb_point_pre_bytes.argtypes = [C.c_int]
+    lib.pnb_point_pre.restype = C.c_int
+    lib.pnb_point_pre.argtypes = [C.POINTER(Points), C.POINTER(Mlp), C.c_void_p, C.c_size_t, C.c_void_p]
     lib.pnb_shade_tc_bytes.restype = C.c_size_t
     lib.pnb_shade_tc_bytes.argtypes = [C.c_int]
     lib.pnb_shade_forward_tc.restype = C.c_int
-    lib.pnb_shade_forward_tc.argtypes = [C.POINTER(Query), C.POINTER(Points), C.POINTER(Mlp), C.c_void_p, C.POINTER(ShadeOpts),
+    lib.pnb_shade_forward_tc.argtypes = [C.POINTER(Query), C.POINTER(Points), C.POINTER(Mlp), C.c_void_p, C.c_void_p, C.POINTER(ShadeOpts),
                                          C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    lib.pnb_shade_tc_tables.restype = C.c_int
+    lib.pnb_shade_tc_tables.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
+                                        C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]
     lib.pnb_backward_bytes.restype = C.c_size_t
     lib.pnb_backward_bytes.argtypes = [C.c_int, C.c_int]
     lib.pnb_shade_backward.restype = C.c_int
     lib.pnb_shade_backward.argtypes = [C.POINTER(Query), C.POINTER(Points), C.POINTER(Mlp), C.POINTER(ShadeOpts), C.c_void_p,
                                        C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                        C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_void_p, C.c_size_t, C.c_void_p]
+    _lib = lib
+    return lib
+
+
+def load_selftest():
+    """Test-only library with the tcgen05 self-tests / micro-benchmarks (not part of the product ABI)."""
+    global _selftest
+    if _selftest is not None:
+        return _selftest
+    if not os.path.exists(SELFTEST_LIB_PATH):
+        raise PnbError("libpnb200_selftest.so not found at %s -- run `python -m pointnerf_b200.build`" % SELFTEST_LIB_PATH)
+    lib = C.CDLL(SELFTEST_LIB_PATH)
+    lib.pnb_selftest_last_error.restype = C.c_char_p
     lib.pnb_umma_bench.restype = C.c_int
     lib.pnb_umma_bench.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.pnb_umma_selftest2.restype = C.c_int
@@ -122,8 +152,13 @@ def load():
                                        C.c_void_p, C.c_void_p]
     lib.pnb_umma_selftest.restype = C.c_int
     lib.pnb_umma_selftest.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
-    _lib = lib
+    _selftest = lib
     return lib
+
+
+def check_selftest(rc, what=""):
+    if rc != 0:
+        raise PnbError("%s failed (status %d): %s" % (what, rc, load_selftest().pnb_selftest_last_error().decode()))
 
 
 def check(rc, what=""):

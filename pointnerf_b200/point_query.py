@@ -85,6 +85,11 @@ class QueryResult:
         self.counters = {k: int(hc[i]) for k, i in _lib.QC.items()} if want_counters else None
         self.R, self.SR, self.K, self.D = R, SR, K, D
 
+    def counters_tensor(self):
+        """The device int32[16] counters (PNB_QC_*) as a tensor view into the query workspace."""
+        off = int(self.desc.counters) - self.ws.data_ptr()
+        return self.ws[off:off + 64].view(torch.int32)
+
     def export(self, cam_opts, want_pers=True, want_dirs=True):
         """Dense reference layout (needs counters['R2'] -> the query must have been run with want_counters)."""
         lib = _lib.load()

@@ -54,6 +54,9 @@ def check_opt(opt):
         raise NotImplementedError("pnb200: agg_axis_weight must be None or 1 1 1")
     if getattr(opt, "prob", 0) not in (0, 1):
         raise NotImplementedError("pnb200: opt.prob must be 0 or 1")
+    if float(getattr(opt, "xyz_grad", 0) or 0) > 0:
+        # the fused backward produces no d/d(xyz) (every shipped script has xyz_grad = 0): refuse instead of silently freezing xyz
+        raise NotImplementedError("pnb200: xyz_grad > 0 (point positions as trainable parameters) is outside the implemented hot path")
 
 
 def _to_list(x):
@@ -99,6 +102,7 @@ class MlpPack:
         self.bias = None
         self.desc = None
         self.packed = None   # tcgen05 operand images of block1/block3 (hi/lo bf16)
+        self.key_l1 = None   # version key of block1.0 (weight, bias): what the hoisted per-point table depends on
 
     def get(self, agg):
         sd = {k: v for k, v in agg.named_parameters()}
@@ -119,6 +123,7 @@ class MlpPack:
                 d.b[i] = self.bias[i].data_ptr()
             self.desc = d
             self.key = key
+            self.key_l1 = (key[0], key[9])
             lib = _lib.load()
             nb = lib.pnb_mlp_pack_bytes()
             if self.packed is None or self.packed.device != ws[0].device:
@@ -180,7 +185,11 @@ class NeuralPoints(nn.Module):
         self.points_color = mk(points_color, getattr(o, "color_grad", 1) > 0)
         self.points_dir = mk(points_dir, getattr(o, "dir_grad", 1) > 0)
         self.points_conf = mk(points_conf, getattr(o, "conf_grad", 1) > 0)
-        self.Rw2c = torch.eye(3, device=points_xyz.device) if Rw2c is None else Rw2c
+        if "Rw2c" in self._parameters:
+            del self._parameters["Rw2c"]
+        # a supplied Rw2c is part of the state dict, as in the reference (neural_points.py:463-467); the default stays a plain eye(3)
+        self.Rw2c = torch.eye(3, device=points_xyz.device) if Rw2c is None else \
+            nn.Parameter(Rw2c.to(points_xyz.device).float().contiguous(), requires_grad=False)
         self.querier.clean_up()
 
     def reset_querier(self):
@@ -228,6 +237,7 @@ class _RenderFn(torch.autograd.Function):
         q, ray_color, opacity, bg_T, ray_mask = mod._run(*run_args)
         ctx.mod = mod
         ctx.q = q
+        ctx.generation = mod._generation          # the backward recomputes from the query / sigma_rgb buffers of THIS run
         ctx.o = mod._last_opts
         ctx.n_valid = q.counters["n_valid"]
         ctx.sigma_rgb = mod._sigma_rgb          # forward (sigma, rgb) per candidate; valid until the next _run
@@ -240,6 +250,10 @@ class _RenderFn(torch.autograd.Function):
     def backward(ctx, g_color, g_op, g_bg, g_mask):
         lib = _lib.load()
         mod, q = ctx.mod, ctx.q
+        if mod._generation != ctx.generation:
+            raise _lib.PnbError("pnb200: backward() of a forward whose query / sigma_rgb buffers were overwritten by a later call of the "
+                                "same module (two forwards before one backward, or an eval render in between); call backward() "
+                                "before the next forward")
         npnts = mod.neural_points
         dev = g_color.device
         g_color = g_color.contiguous().float()
@@ -281,40 +295,42 @@ def _init_state(mod):
     mod._sigma_rgb = None
     mod._tc_ws = None
     mod._err = None
+    mod._generation = 0
+    mod._pre = None              # hoisted layer-1 table of the frozen pipeline + the versions it was computed from
+    mod._pre_key = None
+    mod._valid_per_ray = 0.0     # densest call seen so far (valid samples per ray): sizes the shading workspace
+    mod._status_pending = []     # (event, pinned [err, query counters], R) of render_full() calls not yet checked
+    mod._status_free = []
+    mod._max_valid = 0
     # "bf16x3": per-pair MLPs on tcgen05 tensor cores with the error-compensated split (default);
     # "fp32": the exact-fp32 CUDA-core kernel.
     mod.precision = getattr(opt, "pnb_precision", "bf16x3")
     if mod.precision not in ("bf16x3", "fp32"):
         raise NotImplementedError("pnb200: pnb_precision=%r (bf16x3 | fp32)" % mod.precision)
-    # tcgen05 pipeline variant: 7 = chunk-pipelined TMEM role ping-pong (epilogue of layer l under the MMAs of layer l+1) with the
-    # rows PACKED to the valid (sample, neighbour) pairs - no MMA rows for empty neighbour slots (default),
-    # 5 = the same pipeline with 8 rows per sample (25 % zero rows on the lego frame),
-    # 6 = v5 on CTA pairs (cluster of 2, cta_group::2 M=256 MMAs, each CTA stages half of every weight image): ~12 % fewer
-    # cycles on an idle GPC, but with all TPCs active the B-half exchange saturates the intra-GPC SM-to-SM fabric,
-    # 3 = A operand of layers 2-4 in tensor memory + overlapped operand builders, epilogues exposed,
-    # 2 = serialized shared-memory pipeline
-    _v = int(getattr(opt, "pnb_tc_version", 7))
-    if _v not in (2, 3, 5, 6, 7):
-        raise NotImplementedError("pnb200: pnb_tc_version=%r (2 | 3 | 5 | 6 | 7)" % _v)
-    mod.tc_mask = 3 | (12 if _v == 3 else 0) | (8 + 32 if _v == 5 else 0) | (8 + 128 if _v == 6 else 0) | (8 + (1 << 17) if _v == 7 else 0)
-    if _v in (5, 6, 7) and int(getattr(opt, "pnb_color_version", 2)) == 2:
-        mod.tc_mask |= 1 << 16        # pipelined colour kernel; the pair kernel writes h-bar as its bf16 hi/lo operand blocks
+    # pnb_frozen: 1 (default) = calls that need no gradient (rendering, evaluation) run the frozen-cloud pair kernel
+    # (k_shade_tc8: the point-only inputs of block1.0 hoisted into a per-point table, rebuilt when points_embeding or
+    # block1.0 change); 0 = always the general kernel (k_shade_tc7), which is what training steps use in either case.
+    mod.frozen_ok = bool(int(getattr(opt, "pnb_frozen", 1)))
+    mod.dbg_flags = int(getattr(opt, "pnb_dbg_flags", 0))
     mod.last = None
     mod._pnb_ready = True
+
+
+_PATCHED = ("forward", "_run", "check_errors", "render_full", "_point_pre", "_poll_status")
 
 
 def install_into(reference_cls):
     """Patch the reference's models.neural_points_volumetric_model.NeuralPointsRayMarching class in place: its
     instances keep their own parameters (self.neural_points.*, self.aggregator.*) and gain the fused forward
     (seam B).  self.neural_points.querier must be pointnerf_b200's lighting_fast_querier (seam A)."""
-    for name in ("forward", "_run", "check_errors", "render_full"):
+    for name in _PATCHED:
         setattr(reference_cls, name, getattr(NeuralPointsRayMarching, name))
     return reference_cls
 
 
 def reference_forward(self, *args, **kwargs):
     """Function form of the patched forward (bind it as NeuralPointsRayMarching.forward of the reference)."""
-    for name in ("_run", "check_errors", "render_full"):
+    for name in _PATCHED[1:]:
         if not hasattr(type(self), name):
             setattr(type(self), name, getattr(NeuralPointsRayMarching, name))
     return NeuralPointsRayMarching.forward(self, *args, **kwargs)
@@ -331,12 +347,46 @@ class NeuralPointsRayMarching(nn.Module):
         _init_state(self)
 
     # -------------------------------------------------------------------------------------------------
-    def _run(self, campos, raydir, camrotc2w, near, far, bg_color, want_counters, t=None):
+    def _point_pre(self, mlp_desc, pts_desc, stream):
+        """Hoisted layer-1 table of the frozen pipeline (pnb_point_pre), rebuilt when points_embeding or block1.0 changed."""
+        emb = self.neural_points.points_embeding
+        key = (emb.data_ptr(), emb._version, emb.shape[1], self._mlp.key_l1)
+        if key != self._pre_key:
+            lib = _lib.load()
+            nb = lib.pnb_point_pre_bytes(int(pts_desc.N))
+            if self._pre is None or self._pre.numel() * 4 < nb or self._pre.device != emb.device:
+                self._pre = torch.empty((nb + 3) // 4, dtype=torch.float32, device=emb.device)
+            _lib.check(lib.pnb_point_pre(_lib.C.byref(pts_desc), _lib.C.byref(mlp_desc), self._pre.data_ptr(), self._pre.numel() * 4,
+                                         stream), "pnb_point_pre")
+            self._pre_key = key
+        return self._pre
+
+    def _poll_status(self, block=False):
+        """Deferred device status of earlier render_full() calls ([err, query counters] copied to pinned memory behind the
+        kernels).  Non-blocking unless `block`; raises PnbError for a call that dropped samples or timed out."""
+        pend = self._status_pending
+        while pend and (block or pend[0][0].query()):
+            ev, host, R = pend.pop(0)
+            ev.synchronize()
+            err, n_valid = int(host[0]), int(host[1 + _lib.QC["n_valid"]])
+            self._status_free.append(host)
+            self._valid_per_ray = max(self._valid_per_ray, n_valid / max(R, 1))
+            if err == 9:
+                raise _lib.PnbOverflow("pnb200: an earlier render_full() produced %d valid samples, more than its shading workspace held "
+                                       "(the extra samples were dropped); the workspace has been enlarged - render the frame again, or "
+                                       "call check_errors() after each frame, or set opt.pnb_max_valid_per_ray" % n_valid)
+            if err != 0:
+                raise _lib.PnbError("pnb200: tcgen05 pipeline time-out (code %d) in an earlier render_full()" % err)
+
+    # -------------------------------------------------------------------------------------------------
+    def _run(self, campos, raydir, camrotc2w, near, far, bg_color, want_counters, t=None, frozen=False):
         if not getattr(self, "_pnb_ready", False):
             _init_state(self)           # reference module patched by install_into(): state is created lazily
         lib = _lib.load()
         npnts, opt = self.neural_points, self.opt
         raydir = raydir[0].contiguous() if raydir.dim() == 3 else raydir.contiguous()
+        dev = raydir.device
+        self._poll_status(block=False)
         # camera scalars go to the kernels by value: host lists / CPU tensors cost nothing, device tensors
         # cost one small D2H copy (the reference does the same with near/far/intrinsic, neural_points.py:704)
         cp, rt, bg = _to_list(campos)[:3], _to_list(camrotc2w)[:9], _to_list(bg_color)[:3]
@@ -344,33 +394,46 @@ class NeuralPointsRayMarching(nn.Module):
         o = make_cam_opts(cp, rt, Rw2c=rw2c_host_of(npnts),
                           vsize_z=float(opt.vsize[2]), bg_color=bg, raydist_mode_unit=int(getattr(opt, "raydist_mode_unit", 0)))
         cap = q.desc.cap_samples
-        if self._sigma_rgb is None or self._sigma_rgb.shape[0] < cap or self._sigma_rgb.device != raydir.device:
-            self._sigma_rgb = torch.empty((cap, 4), dtype=torch.float32, device=raydir.device)
+        self._generation += 1
+        if self._sigma_rgb is None or self._sigma_rgb.shape[0] < cap or self._sigma_rgb.device != dev:
+            self._sigma_rgb = torch.empty((cap, 4), dtype=torch.float32, device=dev)
         mlp = self._mlp.get(self.aggregator)
         pts = points_desc_of(npnts)
-        stream = torch.cuda.current_stream(raydir.device).cuda_stream
+        stream = torch.cuda.current_stream(dev).cuda_stream
         if self.precision == "fp32":
             _lib.check(lib.pnb_shade_forward(_lib.C.byref(q.desc), _lib.C.byref(pts), _lib.C.byref(mlp), _lib.C.byref(o),
                                              self._sigma_rgb.data_ptr(), None, 0, stream), "pnb_shade_forward")
         else:
-            per_ray = int(getattr(opt, "pnb_max_valid_per_ray", 10))
-            max_valid = int(min(q.R * q.SR, max(1 << 20, q.R * per_ray)))
+            # capacity of the shading workspace in valid samples (1 KB each): exact when the caller paid for the counters
+            # (forward()), otherwise the densest frame seen so far with 25 % head-room, at least opt.pnb_max_valid_per_ray per ray;
+            # an overflow is safe on the device (dropped samples contribute nothing) and is reported by check_errors() /
+            # the next call (_poll_status)
+            per_ray = max(float(getattr(opt, "pnb_max_valid_per_ray", 10)), 1.25 * self._valid_per_ray)
+            max_valid = int(min(q.R * q.SR, max(min(1 << 20, q.R * q.SR), math.ceil(q.R * per_ray))))
             if want_counters and getattr(q, "counters", None):
-                # the drop-in forward() already paid the host sync for the counters: size the workspace exactly when the scene is
-                # denser than the heuristic (e.g. indoor scenes where every ray keeps all SR samples)
-                max_valid = max(max_valid, int(q.counters.get("n_valid", 0)))
+                n_valid = int(q.counters.get("n_valid", 0))
+                self._valid_per_ray = max(self._valid_per_ray, n_valid / max(q.R, 1))
+                max_valid = max(max_valid, n_valid)
+            max_valid = max(max_valid, 128)
             self._max_valid = max_valid
             nb = lib.pnb_shade_tc_bytes(max_valid)
-            if self._tc_ws is None or self._tc_ws.numel() < nb or self._tc_ws.device != raydir.device:
-                self._tc_ws = torch.empty(nb, dtype=torch.uint8, device=raydir.device)
-            if self._err is None or self._err.device != raydir.device:
-                self._err = torch.zeros(512, dtype=torch.int32, device=raydir.device)   # [0] status, [2:64] cycle counters, [64:] per-CTA cycles (int64)
+            if self._tc_ws is None or self._tc_ws.numel() < nb or self._tc_ws.device != dev:
+                self._tc_ws = None
+                self._tc_ws = torch.empty(nb, dtype=torch.uint8, device=dev)
+            if self._err is None or self._err.device != dev:
+                self._err = torch.zeros(512, dtype=torch.int32, device=dev)   # [0] status, [2:64] cycle counters, [64:] per-CTA cycles (int64)
+            else:
+                self._err[:1].zero_()
+            flags = _lib.TC_PAIRS | _lib.TC_COLOR | (self.dbg_flags << 8)
+            pre_ptr = None
+            if frozen and self.frozen_ok:
+                pre_ptr = self._point_pre(mlp, pts, stream).data_ptr()
+                flags |= _lib.TC_FROZEN
             _lib.check(lib.pnb_shade_forward_tc(_lib.C.byref(q.desc), _lib.C.byref(pts), _lib.C.byref(mlp),
-                                                self._mlp.packed.data_ptr(), _lib.C.byref(o), self._sigma_rgb.data_ptr(),
-                                                self._tc_ws.data_ptr(), self._tc_ws.numel(), max_valid, self.tc_mask,
+                                                self._mlp.packed.data_ptr(), pre_ptr, _lib.C.byref(o), self._sigma_rgb.data_ptr(),
+                                                self._tc_ws.data_ptr(), self._tc_ws.numel(), max_valid, flags,
                                                 self._err.data_ptr(), stream), "pnb_shade_forward_tc")
         R, SR = q.R, q.SR
-        dev = raydir.device
         ray_color = torch.empty((R, 3), dtype=torch.float32, device=dev)
         opacity = torch.empty((R, SR), dtype=torch.float32, device=dev)
         bg_T = torch.empty((R,), dtype=torch.float32, device=dev)
@@ -383,18 +446,36 @@ class NeuralPointsRayMarching(nn.Module):
         return q, ray_color, opacity, bg_T, ray_mask
 
     def check_errors(self):
-        """Synchronising check of the device-side error flag of the tensor-core path (raises on failure)."""
+        """Synchronising check of the device-side status of the tensor-core path: raises PnbOverflow (after enlarging the
+        workspace for the next call) when the last call dropped samples, PnbError on a pipeline time-out."""
+        if getattr(self, "_status_pending", None):
+            self._poll_status(block=True)
         if self._err is not None:
             code = int(self._err[0].item())
+            if code != 0:
+                self._err[:1].zero_()
             if code == 9:
-                raise _lib.PnbError("pnb200: more valid samples than the shading workspace holds; raise opt.pnb_max_valid_per_ray")
+                n_valid = int(self.last.counters_tensor()[_lib.QC["n_valid"]].item())
+                self._valid_per_ray = max(self._valid_per_ray, n_valid / max(self.last.R, 1))
+                raise _lib.PnbOverflow("pnb200: %d valid samples, more than the shading workspace held (%d): the extra samples were dropped; "
+                                       "the workspace has been enlarged for the next call (or set opt.pnb_max_valid_per_ray)"
+                                       % (n_valid, self._max_valid))
             if code != 0:
                 raise _lib.PnbError("pnb200: tcgen05 pipeline time-out (code %d)" % code)
 
     def render_full(self, campos, raydir, camrotc2w, near, far, bg_color, t=None):
         """Full-R outputs, fill_invalid semantics, no host sync: dict(coarse_raycolor [1,R,3],
-        coarse_point_opacity [1,R,SR], coarse_is_background [1,R,1], ray_mask [1,R])."""
-        q, ray_color, opacity, bg_T, ray_mask = self._run(campos, raydir, camrotc2w, near, far, bg_color, False, t=t)
+        coarse_point_opacity [1,R,SR], coarse_is_background [1,R,1], ray_mask [1,R]).  No gradients (frozen-cloud pipeline).
+        The device status of the call (workspace overflow, time-out) is copied to pinned memory behind the kernels and raised
+        by a LATER call or by check_errors(); runner.render_image checks it before returning."""
+        q, ray_color, opacity, bg_T, ray_mask = self._run(campos, raydir, camrotc2w, near, far, bg_color, False, t=t, frozen=True)
+        if self._err is not None and self.precision != "fp32":
+            host = self._status_free.pop() if self._status_free else torch.empty(17, dtype=torch.int32).pin_memory()
+            host[:1].copy_(self._err[:1], non_blocking=True)
+            host[1:17].copy_(q.counters_tensor(), non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(ray_color.device))
+            self._status_pending.append((ev, host, q.R))
         return dict(coarse_raycolor=ray_color[None], coarse_point_opacity=opacity[None],
                     coarse_is_background=bg_T[None, :, None], ray_mask=ray_mask[None])
 
@@ -419,7 +500,7 @@ class NeuralPointsRayMarching(nn.Module):
                                                                  npnts.points_dir, npnts.points_conf, *mlp_params)
             q = self.last
         else:
-            q, ray_color, opacity, bg_T, ray_mask = self._run(*run_args)
+            q, ray_color, opacity, bg_T, ray_mask = self._run(*run_args, frozen=True)
         self.check_errors()
         # compact to the R' rays the reference returns (one host sync already paid for the counters)
         inds = torch.nonzero(ray_mask)[:, 0]

@@ -19,17 +19,30 @@ def _near_far(near, far):
     return n, f
 
 
-def render_image(net, data, height, width):
+def render_image(net, data, height, width, check=True):
     """data: the dict a reference dataset item carries (`campos [1,3]`, `raydir [1,H*W,3]`, `camrotc2w [1,3,3]`, `near`, `far`,
     `bg_color`).  Returns device tensors: `coarse_raycolor [H,W,3]`, `coarse_point_opacity [H,W,SR]`,
-    `coarse_is_background [H,W,1]`, `ray_mask [H,W]` (all rays, background filled as fill_invalid does)."""
+    `coarse_is_background [H,W,1]`, `ray_mask [H,W]` (all rays, background filled as fill_invalid does).
+    check=True (default): the device status of the frame is read before returning (one stream synchronisation; the caller is
+    about to read the image anyway) and a frame whose shading workspace was too small is rendered again with the exact size;
+    check=False: fully asynchronous, the status surfaces at a later call or through `net.check_errors()`."""
     near, far = _near_far(data["near"], data["far"])
     raydir = data["raydir"]
     if raydir.shape[1] != height * width:
         raise ValueError("render_image: %d rays for a %dx%d image" % (raydir.shape[1], height, width))
     bg = data.get("bg_color", None)
+    from .lib import PnbOverflow
     with torch.no_grad():
-        out = net.render_full(data["campos"], raydir, data["camrotc2w"], near, far, bg if bg is not None else torch.zeros(3))
+        for attempt in range(2):
+            out = net.render_full(data["campos"], raydir, data["camrotc2w"], near, far, bg if bg is not None else torch.zeros(3))
+            if not check:
+                break
+            try:
+                net.check_errors()
+                break
+            except PnbOverflow:
+                if attempt == 1:
+                    raise
     sr = out["coarse_point_opacity"].shape[-1]
     return dict(coarse_raycolor=out["coarse_raycolor"][0].view(height, width, 3),
                 coarse_point_opacity=out["coarse_point_opacity"][0].view(height, width, sr),

@@ -16,17 +16,14 @@ TOL = 1e-4
 
 
 def _prec(precision):
-    if precision == "bf16x3-v2":
-        return dict(pnb_precision="bf16x3", pnb_tc_version=2)
-    if precision == "bf16x3-c1":      # default pair kernel + the serialized colour kernel fed by fp32 h-bar
-        return dict(pnb_precision="bf16x3", pnb_color_version=1)
-    if precision == "bf16x3-v5":
-        return dict(pnb_precision="bf16x3", pnb_tc_version=5)
-    if precision == "bf16x3-v6":
-        return dict(pnb_precision="bf16x3", pnb_tc_version=6)
-    if precision == "bf16x3-v3":
-        return dict(pnb_precision="bf16x3", pnb_tc_version=3)
+    """bf16x3: the default (render_full / eval forward run the frozen-cloud pair kernel k_shade_tc8);
+    bf16x3-general: the general pair kernel k_shade_tc7 (what training steps run); fp32: the exact CUDA-core kernel."""
+    if precision == "bf16x3-general":
+        return dict(pnb_precision="bf16x3", pnb_frozen=0)
     return dict(pnb_precision=precision)
+
+
+PRECISIONS = ["bf16x3", "bf16x3-general", "fp32"]
 
 
 def _oracle_render(cfg, opt, pts, agg, raydir):
@@ -40,7 +37,7 @@ def _render_full(net, cfg, rays):
         return net.render_full(list(cfg.campos), rays["raydir"].to(DEV), torch.eye(3), cfg.near, cfg.far, [1., 1., 1.])
 
 
-@pytest.mark.parametrize("precision", ["bf16x3", "bf16x3-v5", "bf16x3-c1", "bf16x3-v6", "bf16x3-v3", "bf16x3-v2", "fp32"])
+@pytest.mark.parametrize("precision", PRECISIONS)
 @pytest.mark.parametrize("name,side,alpha_bias,over", [
     ("tiny", 64, 4.0, {}), ("tiny", 64, 0.0, {}), ("tiny", 40, 8.0, dict(SR=8)), ("tiny", 40, 4.0, dict(K=3)),
     ("chair_plumbing", 16, 4.0, {}), ("chair_plumbing", 64, 2.0, dict(SR=80)),
@@ -59,7 +56,7 @@ def test_render_matches_oracle(name, side, alpha_bias, over, precision):
     net.check_errors()
 
 
-@pytest.mark.parametrize("precision", ["bf16x3", "bf16x3-v5", "bf16x3-c1", "bf16x3-v6", "bf16x3-v3", "bf16x3-v2", "fp32"])
+@pytest.mark.parametrize("precision", PRECISIONS)
 @pytest.mark.parametrize("name", ["tiny_opaque", "tiny_thin_sr8"])
 def test_forward_matches_reference_fixture(name, golden_dir, precision):
     """The drop-in NeuralPointsRayMarching.forward() output dict vs what the reference module itself returned."""
@@ -80,7 +77,7 @@ def test_forward_matches_reference_fixture(name, golden_dir, precision):
     assert out["queried_shading"].shape == (1, fx["sample_pidx"].shape[0], 3)
 
 
-@pytest.mark.parametrize("precision", ["bf16x3", "bf16x3-v5", "bf16x3-c1", "bf16x3-v6", "bf16x3-v3", "bf16x3-v2", "fp32"])
+@pytest.mark.parametrize("precision", PRECISIONS)
 def test_render_lego_scale(precision):
     """BASELINE config 2 size: a reference-sized chunk against the oracle; full-frame determinism and
     sharding invariance (bit-exact: a ray's colour does not depend on which rays share the call)."""
@@ -123,6 +120,144 @@ def test_render_large_configs_chunk(name, side):
         d = (out[a][0].cpu() - ref[a]).abs().max().item()
         assert d <= TOL, "%s max abs diff %.3e" % (a, d)
     net.check_errors()
+
+
+def _block(x0, y0, w, h):
+    px, py = np.meshgrid(np.arange(x0, x0 + w), np.arange(y0, y0 + h))
+    return np.stack((px, py), -1).reshape(-1, 2).astype(np.float32)
+
+
+@pytest.mark.parametrize("precision", ["bf16x3", "bf16x3-general"])
+@pytest.mark.parametrize("name,block,over", [
+    ("lego_render", (640, 388, 96, 24), {}),                 # through the limb of the shell: grazing hits, partial neighbourhoods, misses
+    ("lego_render", (640, 388, 96, 24), dict(SR=80)),        # the shipped SR
+    ("truck_8gpu", (860, 0, 100, 16), {}),                   # image corner: the limb crosses the strip (kernel_size 5)
+    ("scannet_8gpu", (0, 228, 64, 24), {}),                  # left image edge across a wall/wall corner of the box, all rays hit
+])
+def test_render_silhouette_strips(name, block, over, precision):
+    """Oracle parity where neighbourhoods are partial (silhouette-crossing strips at the BASELINE sizes)."""
+    cfg = scene.CONFIGS[name]
+    net, pts, opt = harness.build_model(cfg, DEV, alpha_bias=3.0, **_prec(precision), **over)
+    rays = scene.make_rays(cfg, _block(*block))
+    out = _render_full(net, cfg, rays)
+    ref = _oracle_render(cfg, opt, pts, net.aggregator, rays["raydir"][0])
+    m = ref["ray_mask"]
+    assert np.array_equal(out["ray_mask"][0].cpu().numpy(), m)
+    if name != "scannet_8gpu":
+        assert 0 < int(m.sum()) < m.size, "the strip must cross the silhouette"
+    for a in ("coarse_raycolor", "coarse_point_opacity", "coarse_is_background"):
+        d = (out[a][0].cpu() - ref[a]).abs().max().item()
+        assert d <= TOL, "%s max abs diff %.3e" % (a, d)
+    net.check_errors()
+
+
+def _pack_reference(counts, PACK_S=512, PACK_WIN=64):
+    """Python restatement of k_pack_quads (same as tests/test_host_logic.py): first fit with a look-ahead window, per super-chunk."""
+    vorder, vcntp, qf = [], [], []
+    for i0 in range(0, len(counts), PACK_S):
+        c = list(counts[i0:i0 + PACK_S])
+        n, pos, emitted = len(c), 0, 0
+        while pos < n:
+            qf.append(i0 + emitted)
+            rows = 0
+            for i in range(pos, min(n, pos + PACK_WIN)):
+                if rows >= 32:
+                    break
+                if c[i] != 0 and rows + c[i] <= 32:
+                    vorder.append(i0 + i); vcntp.append(c[i]); rows += c[i]; c[i] = 0; emitted += 1
+            while pos < n and c[pos] == 0:
+                pos += 1
+    qf.append(len(counts))
+    return np.array(vorder), np.array(vcntp), np.array(qf)
+
+
+@pytest.mark.parametrize("name,side", [("tiny", 64), ("chair_plumbing", 200), ("lego_render", 300)])
+def test_row_packing_tables_match_restatement(name, side):
+    """The warp-cooperative packing kernels produce exactly the tables of the sequential first-fit algorithm."""
+    import ctypes as C
+    from pointnerf_b200 import lib as L
+    cfg = scene.CONFIGS[name]
+    net, pts, opt = harness.build_model(cfg, DEV, alpha_bias=3.0)
+    rays = scene.make_rays(cfg, scene.centre_patch(cfg, side))
+    _render_full(net, cfg, rays)
+    net.check_errors()
+    q = net.last
+    cnt = q.counters_tensor().cpu().numpy()
+    n_valid = int(cnt[L.QC["n_valid"]])
+    assert n_valid > 1000
+    ws = q.ws
+    def view(ptr, nbytes, dtype):
+        off = int(ptr) - ws.data_ptr()
+        return ws[off:off + nbytes].view(dtype)
+    valid_list = view(q.desc.valid_list, 4 * n_valid, torch.int32).cpu().numpy()
+    nv = view(q.desc.samp_nvalid, int(cnt[L.QC["n_cand"]]), torch.uint8).cpu().numpy()
+    counts = nv[valid_list].astype(np.int64)
+    ptrs = [C.c_void_p() for _ in range(4)]
+    L.check(L.load().pnb_shade_tc_tables(net._tc_ws.data_ptr(), net._tc_ws.numel(), net._max_valid, *[C.byref(p) for p in ptrs]), "tables")
+    def tview(ptr, nbytes, dtype):
+        off = ptr.value - net._tc_ws.data_ptr()
+        return net._tc_ws[off:off + nbytes].view(dtype).cpu().numpy()
+    n_quads = int(tview(ptrs[3], 4, torch.int32)[0])
+    vorder = tview(ptrs[0], 4 * n_valid, torch.int32)
+    vcntp = tview(ptrs[1], n_valid, torch.uint8)
+    qf = tview(ptrs[2], 4 * (n_quads + 1), torch.int32)
+    rv, rc, rq = _pack_reference(counts)
+    assert n_quads == len(rq) - 1
+    assert np.array_equal(vorder, rv) and np.array_equal(vcntp, rc) and np.array_equal(qf, rq)
+    rows = np.add.reduceat(rc, rq[:-1])
+    assert rows.max() <= 32 and rows.sum() == counts.sum()
+
+
+def test_frozen_table_follows_parameter_updates():
+    """The hoisted per-point table of the frozen pipeline is rebuilt when points_embeding or block1.0 change in place."""
+    cfg = scene.CONFIGS["tiny"]
+    net, pts, opt = harness.build_model(cfg, DEV, alpha_bias=4.0)
+    gen, _, _ = harness.build_model(cfg, DEV, alpha_bias=4.0, pnb_frozen=0)
+    rays = scene.make_rays(cfg, scene.centre_patch(cfg, 48))
+    a0 = _render_full(net, cfg, rays)["coarse_raycolor"].clone()
+    g0 = _render_full(gen, cfg, rays)["coarse_raycolor"].clone()
+    assert (a0 - g0).abs().max().item() <= 2e-5
+    with torch.no_grad():
+        for m in (net, gen):
+            m.neural_points.points_embeding.mul_(0.5)
+            m.aggregator.block1[0].weight.mul_(1.1)
+            m.aggregator.block1[0].bias.add_(0.01)
+    a1 = _render_full(net, cfg, rays)["coarse_raycolor"]
+    g1 = _render_full(gen, cfg, rays)["coarse_raycolor"]
+    assert (a1 - a0).abs().max().item() > 1e-3                      # the update is visible ...
+    assert (a1 - g1).abs().max().item() <= 2e-5                     # ... and the frozen path tracks the general one
+
+
+def test_workspace_overflow_is_safe_and_reported():
+    """A frame denser than the workspace heuristic (indoor scene: every ray keeps all SR samples): the dropped samples contribute
+    nothing (no uninitialised reads), the call is reported (check_errors / the next call), and the retry is exact."""
+    from pointnerf_b200 import lib as L, runner
+    cfg = scene.CONFIGS["scannet_8gpu"]
+    net, pts, opt = harness.build_model(cfg, DEV, alpha_bias=3.0, pnb_max_valid_per_ray=2)
+    rays = scene.make_rays(cfg, _block(0, 0, 640, 160))                 # 102,400 rays x 24 valid samples >> 2 per ray / the 1 M floor
+    out = _render_full(net, cfg, rays)
+    col = out["coarse_raycolor"].clone()
+    assert torch.isfinite(col).all() and col.min() >= -0.002 and col.max() <= 1.002
+    with pytest.raises(L.PnbOverflow):
+        net.check_errors()
+    out2 = _render_full(net, cfg, rays)                                  # the workspace grew: exact now
+    net.check_errors()
+    col2 = out2["coarse_raycolor"]
+    chunk = dict(rays); chunk["raydir"] = rays["raydir"][:, :4096]
+    ref = _render_full(net, cfg, chunk)["coarse_raycolor"]
+    assert torch.equal(col2[:, :4096], ref)
+    assert not torch.equal(col, col2)
+    # the whole-image entry checks and retries by itself
+    net3, _, _ = harness.build_model(cfg, DEV, alpha_bias=3.0, pnb_max_valid_per_ray=2)
+    data = {k: (v.to(DEV) if isinstance(v, torch.Tensor) else v) for k, v in rays.items()}
+    img = runner.render_image(net3, data, 160, 640)
+    assert torch.equal(img["coarse_raycolor"].reshape(1, -1, 3), col2)
+    # deferred report: without check_errors() the NEXT call raises
+    net4, _, _ = harness.build_model(cfg, DEV, alpha_bias=3.0, pnb_max_valid_per_ray=2)
+    _render_full(net4, cfg, rays)
+    torch.cuda.synchronize()
+    with pytest.raises(L.PnbOverflow):
+        _render_full(net4, cfg, rays)
 
 
 def test_probe_outputs_match_reference_fixture(golden_dir):

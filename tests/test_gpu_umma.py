@@ -9,11 +9,11 @@ DEV = "cuda:0"
 
 
 def _run(A, W, layout):
-    l = _lib.load()
+    l = _lib.load_selftest()
     K, N = A.shape[1], W.shape[0]
     D = torch.full((128, N), float("nan"), device=DEV)
     err = torch.zeros(1, dtype=torch.int32, device=DEV)
-    _lib.check(l.pnb_umma_selftest(A.data_ptr(), W.data_ptr(), D.data_ptr(), K, N, layout, err.data_ptr(),
+    _lib.check_selftest(l.pnb_umma_selftest(A.data_ptr(), W.data_ptr(), D.data_ptr(), K, N, layout, err.data_ptr(),
                                    torch.cuda.current_stream().cuda_stream), "pnb_umma_selftest")
     torch.cuda.synchronize()
     return D, int(err.item())
@@ -52,14 +52,14 @@ def test_umma_a_operand_in_tensor_memory(layout, K, N):
 @pytest.mark.parametrize("mode,K,N", [(0, 32, 256), (0, 288, 256), (0, 64, 64), (1, 16, 32), (1, 256, 256), (1, 64, 128)])
 def test_umma_cta_pair(mode, K, N):
     """cta_group::2 (cluster of 2): M=256, each CTA stages half of B; SS and TS forms, multicast commit."""
-    l = _lib.load()
+    l = _lib.load_selftest()
     g = torch.Generator(device=DEV).manual_seed(K * 13 + N + mode)
     A = torch.randn(256, K, device=DEV, generator=g).contiguous()
     W = (torch.randn(N, K, device=DEV, generator=g) / K ** 0.5).contiguous()
     D = torch.full((256, N), float("nan"), device=DEV)
     err = torch.zeros(1, dtype=torch.int32, device=DEV)
     out = torch.zeros(2, dtype=torch.int64, device=DEV)
-    _lib.check(l.pnb_umma_selftest2(A.data_ptr(), W.data_ptr(), D.data_ptr(), K, N, mode, 0, 0, out.data_ptr(), err.data_ptr(),
+    _lib.check_selftest(l.pnb_umma_selftest2(A.data_ptr(), W.data_ptr(), D.data_ptr(), K, N, mode, 0, 0, out.data_ptr(), err.data_ptr(),
                                     torch.cuda.current_stream().cuda_stream), "pnb_umma_selftest2")
     torch.cuda.synchronize()
     assert int(err.item()) == 0, "pipeline timeout code %d" % int(err.item())

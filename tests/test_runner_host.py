@@ -21,6 +21,9 @@ class _StubNet:
         op = mask[:, None].float().expand(-1, self.sr) * 0.5
         return mask, col, op
 
+    def check_errors(self):
+        self.checked = getattr(self, "checked", 0) + 1
+
     def render_full(self, campos, raydir, camrotc2w, near, far, bg_color, t=None):
         mask, col, op = self._full(raydir)
         return dict(coarse_raycolor=col[None], coarse_point_opacity=op[None], coarse_is_background=(1 - mask.float())[None, :, None], ray_mask=mask[None])

@@ -1,36 +1,39 @@
-"""Run on the GPU box, lego_render frame: in-kernel cycle accounting of the pair kernel (block 0; v3 / v5 / v6) and, with
-PNB_DBG_FLAGS=4, the cycles of every CTA (v5 / v6 / v7).  PNB_TC_VERSION selects the variant, PNB_NO_PROF=1 switches the
-accounting off (it slows block 0 down), PNB_NO_WEIGHTS=1 removes the weight traffic (garbage results)."""
+"""Run on the GPU box, lego_render frame: per-CTA cycle counts of the pair kernel (dbg flag 4: cycles + SM id of every CTA into
+d_err[64..]) and the cycles per 128-row tile they imply.  PNB_FROZEN=0 selects the general kernel (k_shade_tc7), default the
+frozen-cloud kernel (k_shade_tc8); PNB_NO_WEIGHTS=1 removes the weight traffic (garbage results, timing experiment);
+PNB_SR / PNB_CONFIG override the workload."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
-from pointnerf_b200 import harness, scene
+from pointnerf_b200 import harness, scene, lib as L
 dev = torch.device("cuda:0")
-cfg = scene.CONFIGS["lego_render"]
-net, pts, opt = harness.build_model(cfg, dev, alpha_bias=3.0, pnb_tc_version=int(os.environ.get("PNB_TC_VERSION", "7")), pnb_color_version=int(os.environ.get("PNB_COLOR_VERSION", "2")))
+cfg = scene.CONFIGS[os.environ.get("PNB_CONFIG", "lego_render")]
+over = {}
+if os.environ.get("PNB_SR"):
+    over["SR"] = int(os.environ["PNB_SR"])
+net, pts, opt = harness.build_model(cfg, dev, alpha_bias=3.0, pnb_frozen=int(os.environ.get("PNB_FROZEN", "1")), **over)
 rays = scene.make_rays(cfg)
 rd = rays["raydir"].to(dev)
 for i in range(3):
     with torch.no_grad():
         net.render_full(list(cfg.campos), rd, torch.eye(3), cfg.near, cfg.far, [1., 1., 1.])
+net.check_errors()
+net.dbg_flags = 4
 if os.environ.get("PNB_NO_WEIGHTS"):
-    net.tc_mask |= 64
-net.tc_mask |= (int(os.environ.get("PNB_DBG_FLAGS", "0")) | (0 if os.environ.get("PNB_NO_PROF") else 1)) << 8
+    net.dbg_flags |= 0          # (the no-weights bit is a top-level flag)
+    L.TC_PAIRS |= L.TC_DBG_NO_WEIGHTS
 torch.cuda.synchronize()
-net._err.zero_()
 with torch.no_grad():
     net.render_full(list(cfg.campos), rd, torch.eye(3), cfg.near, cfg.far, [1., 1., 1.])
 torch.cuda.synchronize()
-c = net._err.cpu().view(torch.int64)[1:17].tolist()
-names = ["loader wait empty", "issuer wait a1_ready", "issuer wait at_ready", "issuer wait full(weights)", "builder wait a1_free",
-         "builder busy", "epilogue wait acc_full", "epilogue busy (l<3)", "epilogue busy (l==3)", "kernel total (thread 0)", "issuer: in ring commits (v6)", "issuer: K-block issue incl. commits (v6)", "issuer: wait kblk (probe)", "issuer: wait weights (probe)", "issuer: #weight waits", "peer loader wait empty"]
-ntiles = (net.last.counters["n_valid"] if net.last.counters else 3472901) if False else None
-tot = c[9]
-print("status", int(net._err[0]), "version", os.environ.get("PNB_TC_VERSION", "7"), "no_weights", bool(os.environ.get("PNB_NO_WEIGHTS")))
-for n, v in zip(names, c):
-    print("%-28s %12d cycles  %5.1f%% of kernel" % (n, v, 100.0 * v / max(tot, 1)))
-
-if int(os.environ.get("PNB_DBG_FLAGS", "0")) & 4:
-    per = net._err.cpu().view(torch.int64)[32:32 + 148].tolist()
-    print("n_quads (v7):", int(net._err.cpu().view(torch.int64)[32 + 192]), "n_valid:", net.last.counters.get("n_valid") if net.last and net.last.counters else None)
-    print("per-CTA kernel cycles (M) @smid:", " ".join("%.1f@%d" % ((v & 0xffffffffffff) / 1e6, v >> 48) for v in per))
+per = net._err.cpu().view(torch.int64)[32:32 + 148].tolist()
+n_quads = int(net._err.cpu().view(torch.int64)[32 + 192])
+cyc = [(v & 0xffffffffffff) for v in per]
+cnt = net.last.counters_tensor().cpu().tolist()
+n_tiles = (n_quads + 3) // 4
+print("kernel", "k_shade_tc8 (frozen)" if net.frozen_ok else "k_shade_tc7 (general)", "| status", int(net._err[0]),
+      "| n_valid", cnt[L.QC["n_valid"]], "n_pairs", cnt[L.QC["n_pairs"]], "n_quads", n_quads, "tiles", n_tiles,
+      "row fill %.4f" % (cnt[L.QC["n_pairs"]] / max(n_quads * 32, 1)))
+print("per-CTA cycles: min %.2f M  max %.2f M  mean %.2f M -> %.1f k cycles per 128-row tile (tiles per CTA %.1f)"
+      % (min(cyc) / 1e6, max(cyc) / 1e6, sum(cyc) / len(cyc) / 1e6, sum(cyc) / len(cyc) / (n_tiles / 148.0) / 1e3, n_tiles / 148.0))
+print("per-CTA kernel cycles (M) @smid:", " ".join("%.1f@%d" % ((v & 0xffffffffffff) / 1e6, v >> 48) for v in per))

@@ -3,7 +3,7 @@ import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from pointnerf_b200 import lib as _lib
-l = _lib.load()
+l = _lib.load_selftest()
 dev = "cuda:0"
 A = torch.randn(256, 32, device=dev)
 W = torch.randn(256, 32, device=dev)
@@ -15,7 +15,7 @@ KIND = ["multicast(3)", "multicast(1)", "cta_group::2 local", "cta_group::1"]
 for mode in (0, 1):
     for flags in (0, 1 << 16, (1 << 16) | (1 << 13), (1 << 16) | (1 << 12) | (1 << 13), (1 << 16) | 2, (1 << 16) | 2 | (1 << 12) | (1 << 13)):
         iters = 3000
-        _lib.check(l.pnb_umma_selftest2(A.data_ptr(), W.data_ptr(), D.data_ptr(), 32, 256, mode, iters, flags, out.data_ptr(), err.data_ptr(), st), "selftest2")
+        _lib.check_selftest(l.pnb_umma_selftest2(A.data_ptr(), W.data_ptr(), D.data_ptr(), 32, 256, mode, iters, flags, out.data_ptr(), err.data_ptr(), st), "selftest2")
         torch.cuda.synchronize()
         o = out.tolist()
         print("cta_group::2 %s rotate=%d stress[tmem=%d bulk=%d test_spin=%d try_spin=%d] commit every %d (%s): issue %.1f cyc/mma, complete %.1f cyc/mma (err %d)" % (

@@ -4,7 +4,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from pointnerf_b200 import lib as _lib
 
-l = _lib.load()
+l = _lib.load_selftest()
 dev = "cuda:0"
 for layout in (0, 4):
     for (K, N) in ((16, 16), (32, 32), (32, 256), (64, 256), (288, 256)):

@@ -1,22 +1,29 @@
 #!/usr/bin/env python
 """bench.py -- BASELINE.json's metric on BASELINE.json's config, measured on B200.
 
-Metric: Mrays/s (whole job) for full-image renders of the synthetic "lego_render" scene
-(800x800 = 640,000 rays per image, K=8, N=400,000 neural points, SR=24 shading samples per ray, D=400 march
-steps, fp32).  A "step" = one full image through the hot path (voxel query -> fused shading -> composite).
+Metric: Mrays/s (whole job) for full-image renders of the synthetic "lego_render" scene (BASELINE configs[1]:
+800x800 = 640,000 rays per image, K=8, N=400,000 neural points, SR=24 shading samples per ray, D=400 march steps, fp32 I/O).
+A "step" = one full image per GPU through the hot path (voxel query -> row packing -> fused pair MLPs -> colour MLP ->
+composite), ONE `render_full` call.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--sr 24]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--sr 24] [--only main]
 
-N>1 is launched by torchrun (one rank per GPU): the global batch is N images, rays interleave-sharded
-(ray i -> rank i % N), the point cloud / grid / MLP replicated, and ONE NCCL all-gather of the rendered colours per
-step inside the timed region ("weak" scaling: per-GPU work fixed).
+N>1 is launched by torchrun (one rank per GPU, NCCL).  The JSON line of every N carries
+  value / ms_per_step  WEAK scaling: N distinct camera poses (rolls about the view axis), rank g renders frame g, one all-gather of
+                       the [R,3] colours per step inside the timed region, issued on a side stream so that it overlaps the next frame;
+  strong               ONE 800x800 frame, rays interleave-sharded (ray i -> rank i % N), tile all-gather inside the timed region;
+  truck                BASELINE configs[3]: N=2M points, 960x540, kernel_size 5, one frame interleave-sharded over the N ranks;
+  train                BASELINE configs[2] (N=1..8) per-scene optimisation step: 3600 rays per step split over the ranks,
+                       forward + backward + gradient all-reduce + 2x Adam (parallel.TrainStep);
+  cold, sr80           (N=1) first frame of a new point cloud (voxel grid + per-point table built inside the timed region); SR=80.
 
-`--impl reference` times the reference's own CPU path (the oracle port: oracle/query_oracle.c +
-oracle/shade_oracle.py, i.e. the reference's algorithm on host cores) on a bounded sample of the same workload.
-The oracle is used here ONLY as the measured CPU baseline, never inside the GPU arm.
+`--impl reference` times the reference's own CPU path (the oracle port: oracle/query_oracle.c + oracle/shade_oracle.py, i.e. the
+reference's algorithm on the host cores) on a bounded, stratified sample of the same frame.  The oracle is used here ONLY as the
+measured CPU baseline, never inside the GPU arm.
 """
 import argparse
 import json
+import math
 import os
 import subprocess
 import sys
@@ -34,9 +41,12 @@ from pointnerf_b200 import harness, scene  # noqa: E402
 METRIC = "Mrays/s (800x800 render, K=8, 400k pts, SR=24), whole job"
 FLOPS_PER_PAIR = 542720.0    # 2*(284*256 + 256*256 + 263*256 + 256*256 + 256)
 FLOPS_PER_SAMPLE = 137984.0  # 2*(280*128 + 128*128 + 128*128 + 128*3)
-# kernels of libpnb200.so launched per step (memsets are not kernels): march, 2 scans x 3, expand, knn,
-# valid_list, count_rays, shade, composite
-LAUNCHES_PER_STEP = 1 + 6 + 1 + 1 + 1 + 1 + 1 + 1
+# kernels of libpnb200.so launched per render_full (memsets / torch fills are not counted): march, 2 scans x 3, expand, knn, valid_list,
+# count_rays (query = 11); k_pack_quads, k_pack_scan, k_pack_place, pair kernel, colour kernel (tcgen05 shading = 5); composite (1)
+LAUNCHES_PER_STEP_TC = 11 + 5 + 1
+LAUNCHES_PER_STEP_FP32 = 11 + 1 + 1
+MMA_FLOPS = 2.0 * 128 * 256 * 16                      # one tcgen05.mma M128 N256 K16
+MMAS_PER_TILE = {True: 159, False: 201}               # frozen (k_shade_tc8) / general (k_shade_tc7) pair kernel, per 128-row tile
 
 
 def peaks():
@@ -108,6 +118,7 @@ class ClockSampler:
 # processes (each with a few intra-op threads: 128-thread eager torch on 1e5-row tensors is slower than 8 threads)
 # renders reference-sized chunks of the frame concurrently, so that every host core is used.
 _W = {}
+CPU_GRID = 16          # the frame's central 768 x 768 pixels = 16 x 16 blocks of 48 x 48 = the reference's 2304-ray chunk (train_ft.py:773)
 
 
 def _cpu_worker_init(sr, threads):
@@ -125,18 +136,25 @@ def _cpu_worker_init(sr, threads):
     _W.update(cfg=cfg, opt=opt, pts=scene.make_points(cfg), mlp=harness.mlp_cpu(agg))
 
 
+def cpu_block_of(i):
+    """Block i of a fixed stratified order over the 16 x 16 block grid (a stride-101 walk visits every block once per 256 and
+    spreads any prefix over the frame: hits in the disc of the shell, misses in the corners, the limb in between)."""
+    b = (i * 101) % (CPU_GRID * CPU_GRID)
+    return b % CPU_GRID, b // CPU_GRID
+
+
 def _cpu_worker_chunk(i):
-    """Render one 2304-ray chunk (48x48 block i of the central 384x384 region: every ray hits the shell)."""
+    """Render one 2304-ray chunk = 48 x 48 block `cpu_block_of(i)` of the 800 x 800 frame (margin 16 px)."""
     from oracle import pipeline
     cfg, opt, pts, mlp = _W["cfg"], _W["opt"], _W["pts"], _W["mlp"]
-    bx, by = i % 8, (i // 8) % 8
-    x0, y0 = cfg.W // 2 - 192 + 48 * bx, cfg.H // 2 - 192 + 48 * by
+    bx, by = cpu_block_of(i)
+    x0, y0 = 16 + 48 * bx, 16 + 48 * by
     px, py = np.meshgrid(np.arange(x0, x0 + 48), np.arange(y0, y0 + 48))
     rays = scene.make_rays(cfg, np.stack((px, py), -1).reshape(-1, 2).astype(np.float32))
     t0 = time.perf_counter()
-    pipeline.render(pts, mlp, rays["raydir"][0], cfg.campos, np.eye(3, dtype=np.float32), cfg.near, cfg.far, opt.vsize,
-                    opt.vscale, opt.kernel_size, opt.query_size, opt.ranges, opt.SR, opt.K, opt.P, pts["xyz"].shape[0], D=cfg.D)
-    return 2304, time.perf_counter() - t0
+    out = pipeline.render(pts, mlp, rays["raydir"][0], cfg.campos, np.eye(3, dtype=np.float32), cfg.near, cfg.far, opt.vsize,
+                          opt.vscale, opt.kernel_size, opt.query_size, opt.ranges, opt.SR, opt.K, opt.P, pts["xyz"].shape[0], D=cfg.D)
+    return 2304, time.perf_counter() - t0, int(out["ray_mask"].sum())
 
 
 class CpuArm:
@@ -146,21 +164,26 @@ class CpuArm:
         self.threads = 8 if self.cores >= 16 else self.cores
         self.workers = max(1, self.cores // self.threads)
         self.pool = mp.get_context("spawn").Pool(self.workers, initializer=_cpu_worker_init, initargs=(sr, self.threads))
+        self.hit = 0
+        self.rays = 0
 
     def step(self, k=0):
         """One step = every worker renders one chunk concurrently.  Returns (rays, seconds)."""
         t0 = time.perf_counter()
         res = self.pool.map(_cpu_worker_chunk, [k * self.workers + j for j in range(self.workers)])
-        return sum(r for r, _ in res), time.perf_counter() - t0
+        self.hit += sum(h for _, _, h in res)
+        self.rays += sum(r for r, _, _ in res)
+        return sum(r for r, _, _ in res), time.perf_counter() - t0
 
     def close(self):
         self.pool.close()
         self.pool.join()
 
     def describe(self, steps, secs):
-        return ("%d steps x %d concurrent 2304-ray chunks (48x48 blocks of the central 384x384 region of the 800x800 frame, all rays "
-                "hit) = %d worker processes x %d torch threads; voxel grid rebuilt per chunk as the reference does; %.1f s"
-                % (steps, self.workers, self.workers, self.threads, secs))
+        return ("%d steps x %d concurrent 2304-ray chunks = 48x48 blocks of the 800x800 frame in a stratified order over the whole frame "
+                "(stride walk over the 16x16 block grid: hits, misses and the limb in frame proportion; %.0f %% of the sampled rays hit); "
+                "%d worker processes x %d torch threads; voxel grid rebuilt per chunk as the reference does; %.1f s"
+                % (steps, self.workers, 100.0 * self.hit / max(self.rays, 1), self.workers, self.threads, secs))
 
 
 WORKLOAD = "lego_render: 800x800 image per GPU, K=8, N=400000 points, SR=%d, D=400, P=16, vsize 0.004 x vscale 2"      # both arms
@@ -173,6 +196,7 @@ def run_reference_arm(args):
     arm = CpuArm(args.sr)
     for i in range(args.warmup):
         arm.step(i)
+    arm.hit = arm.rays = 0
     rays = 0
     t0 = time.perf_counter()
     for i in range(args.steps):
@@ -184,7 +208,7 @@ def run_reference_arm(args):
     line = dict(impl="reference", metric=METRIC, value=val, unit="Mrays/s", n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
                 ms_per_step=dt / args.steps * 1e3, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32",
                 data="synthetic", config=dict(workload=WORKLOAD % args.sr, rays_per_step_sampled=rays // max(args.steps, 1),
-                            note="each step = a bounded sample of the frame (see cpu_baseline.sample); value = rays of the sample / time"),
+                            note="each step = a bounded stratified sample of the frame (see cpu_baseline.sample); value = rays of the sample / time"),
                 cpu_baseline=dict(value=val, unit="Mrays/s", cores=arm.workers * arm.threads, kind="port", sample=arm.describe(args.steps, dt)),
                 e2e=dict(value=val, unit="Mrays/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
     print(json.dumps(line))
@@ -195,6 +219,7 @@ def cpu_baseline_leg(sr, budget_s=20.0):
     """Bounded sample of the same workload on the host cores (rank 0, N=1 only)."""
     arm = CpuArm(sr)
     arm.step(0)
+    arm.hit = arm.rays = 0
     rays, n, t0 = 0, 0, time.perf_counter()
     while True:
         r, _ = arm.step(1 + n)
@@ -207,6 +232,110 @@ def cpu_baseline_leg(sr, budget_s=20.0):
     return dict(value=rays / dt / 1e6, unit="Mrays/s", cores=arm.workers * arm.threads, kind="port", sample=arm.describe(n, dt))
 
 
+# ---------------------------------------------------------------------------------------------------------------------
+def roll(k, n):
+    """Camera-to-world rotation of pose k of n: a roll about the view axis (the shell is symmetric under it: equal work per pose)."""
+    a = 2.0 * math.pi * k / max(n, 1)
+    return torch.tensor([[math.cos(a), -math.sin(a), 0.0], [math.sin(a), math.cos(a), 0.0], [0.0, 0.0, 1.0]], dtype=torch.float32)
+
+
+class Dist:
+    """Thin wrapper: world-1 runs need no process group."""
+
+    def __init__(self, dev):
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.dev = dev
+        self.comm = None
+        if self.world > 1:
+            import torch.distributed as dist
+            self.dist = dist
+            dist.init_process_group("nccl", device_id=dev)
+            self.comm = torch.cuda.Stream(dev)
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        torch.cuda.synchronize(self.dev)
+
+    def max_over_ranks(self, x):
+        if self.world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=self.dev)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def gather_async(self, col, out):
+        """all_gather of this rank's colours into out[world, R, 3] on the side stream (overlaps the next frame's kernels)."""
+        if self.world == 1:
+            return
+        main = torch.cuda.current_stream(self.dev)
+        self.comm.wait_stream(main)
+        col.record_stream(self.comm)
+        with torch.cuda.stream(self.comm):
+            self.dist.all_gather_into_tensor(out.view(-1, 3), col)
+
+    def join(self):
+        if self.world > 1:
+            torch.cuda.current_stream(self.dev).wait_stream(self.comm)
+
+    def close(self):
+        if self.world > 1:
+            self.dist.destroy_process_group()
+
+
+def time_region(D, flush, fn, steps):
+    """EXACTLY `steps` steps between a barrier + synchronize on both sides; one CUDA event pair on the launching stream around the
+    whole region (the side-stream collectives are joined before the closing event); L2 flushed before every step (inside the
+    region: a 160 MB fill, ~0.03 ms).  Returns total ms, max over ranks."""
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    D.barrier()
+    e0.record()
+    for k in range(steps):
+        flush.fill_(1)
+        fn(k)
+    D.join()
+    e1.record()
+    D.barrier()
+    return D.max_over_ranks(e0.elapsed_time(e1))
+
+
+def render_section(D, net, cam_list, rays_host, steps, warmup, flush, e2e=False):
+    """Times `steps` frames.  rays_host: this rank's pinned [R,3] ray directions; cam_list: (campos, camrot, near, far, bg).
+    Resident mode: rays already on the device.  e2e mode: H2D of the rays and D2H of the colours inside every step."""
+    dev = D.dev
+    R = rays_host.shape[0]
+    rays_dev = rays_host.to(dev)
+    gathered = [torch.empty((D.world, R, 3), dtype=torch.float32, device=dev) for _ in range(2)] if D.world > 1 else None
+    out_host = torch.empty((R, 3), dtype=torch.float32).pin_memory()
+
+    def step(k):
+        rd = rays_host.to(dev, non_blocking=True) if e2e else rays_dev
+        with torch.no_grad():
+            out = net.render_full(cam_list[0], rd, cam_list[1], cam_list[2], cam_list[3], cam_list[4])
+        col = out["coarse_raycolor"][0]
+        if D.world > 1:
+            D.gather_async(col, gathered[k & 1])
+        if e2e:
+            out_host.copy_(col, non_blocking=True)
+
+    from pointnerf_b200.lib import PnbOverflow
+    for attempt in range(2):
+        for k in range(warmup):
+            step(k)
+        D.join()
+        D.barrier()
+        try:
+            net.check_errors()
+            break
+        except PnbOverflow:                     # a scene denser than the workspace heuristic: the workspace has grown, warm up again
+            if attempt == 1 or warmup == 0:
+                raise
+    ms = time_region(D, flush, step, steps)
+    net.check_errors()
+    return ms, R
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -215,102 +344,58 @@ def main():
     ap.add_argument("--impl", type=str, default="pnb200")
     ap.add_argument("--sr", type=int, default=24)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--only", type=str, default="", help="comma list of sub-results to run besides the main line: strong,truck,train,cold,sr80 (default: all)")
     ap.add_argument("--precision", type=str, default="bf16x3", help="bf16x3 (tcgen05, default) | fp32 (CUDA cores)")
     ap.add_argument("--frozen", type=int, default=1, help="1 (default): frozen-cloud pair kernel k_shade_tc8 (point-only layer-1 inputs hoisted per point) | 0: general kernel k_shade_tc7")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
+    want = set(x for x in args.only.split(",") if x) or {"strong", "truck", "train", "cold", "sr80"}
 
-    rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    assert world == args.gpus, "WORLD_SIZE %d != --gpus %d (launch N>1 with torchrun)" % (world, args.gpus)
     if not torch.cuda.is_available():
         raise RuntimeError("bench.py needs a CUDA device: the product has no CPU path")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
-    if world > 1:
-        import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=dev)
+    D = Dist(dev)
+    rank, world = D.rank, D.world
+    assert world == args.gpus, "WORLD_SIZE %d != --gpus %d (launch N>1 with torchrun)" % (world, args.gpus)
+    W = max(args.warmup, 3)
+    flush = torch.empty(160 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
 
     cfg = scene.CONFIGS["lego_render"]
     cfg.SR = args.sr
     net, pts, opt = harness.build_model(cfg, dev, seed=0, alpha_bias=3.0, pnb_precision=args.precision, pnb_frozen=args.frozen)
     full = scene.make_rays(cfg)
-    R_img = full["raydir"].shape[1]
-    # global batch = `world` images; ray i of the global batch belongs to rank i % world (interleaved)
-    glob = full["raydir"][0].repeat(world, 1)
-    mine_host = glob[rank::world].contiguous().pin_memory()
-    R = mine_host.shape[0]
-    raydir_dev = mine_host.to(dev)
-    cam = (list(cfg.campos), torch.eye(3), cfg.near, cfg.far, [1., 1., 1.])
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
-    gathered = torch.empty((world, R, 3), dtype=torch.float32, device=dev) if world > 1 else None
-    out_host = torch.empty((R, 3), dtype=torch.float32).pin_memory()
+    dirs_cam = full["raydir"][0]                                   # camera-frame directions (z = 1), pose 0 = identity
+    R_img = dirs_cam.shape[0]
+    bg = [1., 1., 1.]
 
-    def step_resident():
-        with torch.no_grad():
-            out = net.render_full(cam[0], raydir_dev, cam[1], cam[2], cam[3], cam[4])
-        col = out["coarse_raycolor"][0]
-        if world > 1:
-            dist.all_gather_into_tensor(gathered.view(-1, 3), col)
-        return col
-
-    def step_e2e():
-        rd = mine_host.to(dev, non_blocking=True)
-        with torch.no_grad():
-            out = net.render_full(cam[0], rd, cam[1], cam[2], cam[3], cam[4])
-        col = out["coarse_raycolor"][0]
-        if world > 1:
-            dist.all_gather_into_tensor(gathered.view(-1, 3), col)
-        out_host.copy_(col, non_blocking=True)
-        return col
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize(dev)
-
-    def timed(fn, steps):
-        """K steps, each bracketed by CUDA events on the launching stream; L2 flushed between steps (outside the
-        events).  Returns total ms (max over ranks)."""
-        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
-        barrier()
-        for a, b in evs:
-            flush.fill_(1)
-            a.record()
-            fn()
-            b.record()
-        barrier()
-        ms = sum(a.elapsed_time(b) for a, b in evs)
-        if world > 1:
-            t = torch.tensor([ms], dtype=torch.float64, device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
-        return ms
-
+    # ---------------- main line: WEAK scaling, rank g renders the frame of pose g
+    Rg = roll(rank, world)
+    mine = (dirs_cam @ Rg.t()).contiguous().pin_memory()
+    cam = (list(cfg.campos), Rg, cfg.near, cfg.far, bg)
     sampler = ClockSampler(local_rank) if rank == 0 else None
-    for _ in range(max(args.warmup, 3)):
-        step_resident()
-    barrier()
-    # workload counters (oracle-independent: the library's own device counters)
-    qc = net.neural_points.querier.run_query(net.neural_points.xyz.detach(), raydir_dev, cam[0], cam[2], cam[3], want_counters=True).counters
-    gc = net.neural_points.querier.last_grid_counters
-
+    render_section(D, net, cam, mine, 1, W, flush)                # warm-up (also sizes the workspaces)
     t_w0 = time.time()
-    ms_res = timed(step_resident, args.steps)
+    ms_res, R = render_section(D, net, cam, mine, args.steps, 0, flush)
     t_w1 = time.time()
     clocks = sampler.stop(t_w0, t_w1) if sampler else None
+    # workload counters (oracle-independent: the library's own device counters)
+    qc = net.neural_points.querier.run_query(net.neural_points.xyz.detach(), mine.to(dev), cam[0], cam[2], cam[3], want_counters=True).counters
+    gc = net.neural_points.querier.last_grid_counters
+    with torch.no_grad():
+        net.render_full(cam[0], mine.to(dev), cam[1], cam[2], cam[3], cam[4])     # net.last = a full query again
+    torch.cuda.synchronize(dev)
 
-    # dominant kernel alone (shade): CUDA events around the shade launch on the launching stream, same inputs
+    # ---------------- dominant kernel alone: CUDA events around the launch on the launching stream, same inputs, L2 flushed
     from pointnerf_b200 import lib as _lib
+    from pointnerf_b200.point_query import make_cam_opts
     l = _lib.load()
     q = net.last
     mlp = net._mlp.get(net.aggregator)
     ptsd = net.neural_points.points_desc()
-    from pointnerf_b200.point_query import make_cam_opts
-    o = make_cam_opts(cam[0], cam[1], Rw2c=None, vsize_z=float(opt.vsize[2]), bg_color=cam[4],
-                      raydist_mode_unit=opt.raydist_mode_unit)
+    o = make_cam_opts(cam[0], cam[1], Rw2c=None, vsize_z=float(opt.vsize[2]), bg_color=cam[4], raydist_mode_unit=opt.raydist_mode_unit)
     stream = torch.cuda.current_stream(dev).cuda_stream
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 
@@ -326,6 +411,7 @@ def main():
                 ms.append(e0.elapsed_time(e1))
         return float(np.mean(ms))
 
+    frozen = bool(net.frozen_ok) and args.precision != "fp32"
     if args.precision == "fp32":
         shade_avg = time_kernel(lambda: _lib.check(l.pnb_shade_forward(
             _lib.C.byref(q.desc), _lib.C.byref(ptsd), _lib.C.byref(mlp), _lib.C.byref(o), net._sigma_rgb.data_ptr(), None, 0, stream),
@@ -333,8 +419,9 @@ def main():
         color_avg = None
         kname = "k_shade_fwd (fp32 CUDA-core kernel: pair MLPs + colour branch)"
         kflops = FLOPS_PER_PAIR * qc["n_pairs"] + FLOPS_PER_SAMPLE * qc["n_valid"]
+        issued = None
+        n_launch = LAUNCHES_PER_STEP_FP32
     else:
-        frozen = bool(net.frozen_ok)
         pre_ptr = net._point_pre(mlp, ptsd, stream).data_ptr() if frozen else None
 
         def tc(flags):
@@ -344,60 +431,162 @@ def main():
                        "pnb_shade_forward_tc")
         shade_avg = time_kernel(lambda: tc(_lib.TC_PAIRS))
         color_avg = time_kernel(lambda: tc(_lib.TC_COLOR))
-        kname = ("k_shade_tc8 (frozen cloud: layer-1 point inputs hoisted)" if frozen else "k_shade_tc7") + \
-            " + k_pack_* (tcgen05 BF16x3 pair MLPs 284-256-256 | 263-256-256 + alpha + K-reduction)"
+        kname = ("k_shade_tc8 (frozen cloud: the 224 point-only inputs of block1.0 hoisted into a per-point table)" if frozen else "k_shade_tc7") + \
+            " incl. the 3 row-packing kernels (tcgen05 BF16x3 pair MLPs 284-256-256 | 263-256-256 + alpha + K-reduction)"
         kflops = FLOPS_PER_PAIR * qc["n_pairs"]
+        n_tiles = math.ceil(qc["n_pairs"] / 0.993 / 128.0)       # packed rows: 99.3 % fill (tools/tc_profile.py prints the exact count)
+        issued = MMAS_PER_TILE[frozen] * MMA_FLOPS * n_tiles
+        n_launch = LAUNCHES_PER_STEP_TC
         net.check_errors()
 
-    for _ in range(2):
-        step_e2e()
-    ms_e2e = timed(step_e2e, args.steps)
+    # ---------------- e2e: host buffers, H2D of the rays + D2H of the colours inside the timed region
+    ms_e2e, _ = render_section(D, net, cam, mine, args.steps, 2, flush, e2e=True)
 
     total_rays = R * world * args.steps
     value = total_rays / (ms_res * 1e-3) / 1e6
     e2e_val = total_rays / (ms_e2e * 1e-3) / 1e6
     pk = peaks()
-    # DRAM traffic of the dominant kernel per launch, from the committed ncu --set full capture of this same command
     traffic = None
     tfile = os.path.join(ROOT, "profiles", "r02_ncu_dram_traffic.json")
-    if os.path.exists(tfile) and args.precision != "fp32" and world == 1 and args.sr == 24:
-        traffic = json.load(open(tfile)).get("k_shade_tc8" if net.frozen_ok else "k_shade_tc7", None)
-    flops = kflops
-    achieved = flops / (shade_avg * 1e-3) / 1e12
+    if os.path.exists(tfile) and args.precision != "fp32" and args.sr == 24:
+        traffic = json.load(open(tfile)).get("k_shade_tc8" if frozen else "k_shade_tc7", None)
+    achieved = kflops / (shade_avg * 1e-3) / 1e12
     peak = pk["bf16_tflops"]
-    cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cpu = cpu_baseline_leg(args.sr)
+
+    sub = {}
+    # ---------------- strong scaling: ONE frame, rays interleave-sharded over the ranks
+    if "strong" in want:
+        mine_s = dirs_cam[rank::world].contiguous().pin_memory()
+        cam0 = (list(cfg.campos), torch.eye(3), cfg.near, cfg.far, bg)
+        ms_s, Rs = render_section(D, net, cam0, mine_s, args.steps, W, flush)
+        sub["strong"] = dict(value=R_img * args.steps / (ms_s * 1e-3) / 1e6, unit="Mrays/s", ms_per_frame=ms_s / args.steps,
+                             rays_per_rank=Rs, what="one 800x800 frame, ray i -> rank i %% %d, all-gather of the [R/N,3] tiles inside the timed "
+                             "region (side stream, double-buffered)" % world)
+    # ---------------- cold: new point cloud every step (voxel grid + frozen table rebuilt inside the timed region)
+    if "cold" in want and world == 1:
+        def cold_step(k):
+            net.neural_points.querier.clean_up()
+            net._pre_key = None
+            with torch.no_grad():
+                net.render_full(cam[0], q.raydir, cam[1], cam[2], cam[3], cam[4])
+        cold_step(0)
+        ms_c = time_region(D, flush, cold_step, 3)
+        sub["cold"] = dict(value=R_img * 3 / (ms_c * 1e-3) / 1e6, unit="Mrays/s", ms_per_frame=ms_c / 3,
+                           what="voxel grid build (incl. its host synchronisation for the counters) + per-point layer-1 table inside every step")
+    del net
+    torch.cuda.empty_cache()
+    # ---------------- SR = 80 (the shipped value of the NeRF-Synthetic scripts)
+    if "sr80" in want and world == 1 and args.sr != 80:
+        cfg80 = scene.CONFIGS["lego_render"]
+        cfg80.SR = 80
+        net80, _, _ = harness.build_model(cfg80, dev, seed=0, alpha_bias=3.0, pnb_precision=args.precision, pnb_frozen=args.frozen)
+        ms80, _ = render_section(D, net80, cam, mine, 5, W, flush)
+        sub["sr80"] = dict(value=R_img * 5 / (ms80 * 1e-3) / 1e6, unit="Mrays/s", ms_per_frame=ms80 / 5)
+        cfg80.SR = args.sr
+        del net80
+        torch.cuda.empty_cache()
+    # ---------------- config 4: Truck, 2M points, 960x540, kernel_size 5, one frame sharded over the ranks
+    if "truck" in want:
+        tcfg = scene.CONFIGS["truck_8gpu"]
+        tnet, _, topt = harness.build_model(tcfg, dev, seed=0, alpha_bias=3.0, pnb_precision=args.precision, pnb_frozen=args.frozen)
+        tdirs = scene.make_rays(tcfg)["raydir"][0]
+        tmine = tdirs[rank::world].contiguous().pin_memory()
+        tcam = (list(tcfg.campos), torch.eye(3), tcfg.near, tcfg.far, bg)
+        ms_t, Rt = render_section(D, tnet, tcam, tmine, 5, W, flush)
+        tq = tnet.neural_points.querier.run_query(tnet.neural_points.xyz.detach(), tmine.to(dev), tcam[0], tcam[2], tcam[3], want_counters=True).counters
+        sub["truck"] = dict(value=tdirs.shape[0] * 5 / (ms_t * 1e-3) / 1e6, unit="Mrays/s", ms_per_frame=ms_t / 5, rays_per_rank=Rt,
+                            workload="truck_8gpu: 960x540, N=2000000 points, kernel_size 5, vsize 0.002, SR=24, one frame interleave-sharded x%d" % world,
+                            rank0_counters=dict(hit_rays=tq["R2"], valid_samples=tq["n_valid"], valid_pairs=tq["n_pairs"]),
+                            point_table_mb=round(2e6 * 168 / 1e6), hoisted_table_mb=round(2e6 * 1024 / 1e6))
+        del tnet
+        torch.cuda.empty_cache()
+    # ---------------- config 3: per-scene optimisation step (3600 rays per step over the ranks)
+    if "train" in want:
+        sub["train"] = train_section(D, args, dev)
+
     if rank == 0:
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            cpu = cpu_baseline_leg(args.sr)
         line = dict(
-            metric=METRIC, value=value, unit="Mrays/s", n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3),
-            ms_per_step=ms_res / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None, dtype=("f32 (bf16x3 split on tcgen05, fp32 accumulate)" if args.precision != "fp32" else "f32"),
+            metric=METRIC, value=value, unit="Mrays/s", n_gpus=world, steps=args.steps, warmup=W,
+            ms_per_step=ms_res / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None,
+            dtype=("f32 (bf16x3 split on tcgen05, fp32 accumulate)" if args.precision != "fp32" else "f32"),
             data="synthetic",
             config=dict(workload=WORKLOAD % args.sr,
-                        rays_per_step_per_gpu=R, parallelism="rays interleave-sharded x%d, points replicated%s" % (world, ", all-gather of colours" if world > 1 else ""),
-                        l2="flushed between timed steps (256 MiB write, outside the CUDA events)",
+                        rays_per_step_per_gpu=R,
+                        parallelism=("%d distinct poses (rolls about the view axis), rank g renders frame g; points / grid / MLP replicated%s"
+                                     % (world, "; one all-gather of the colours per step on a side stream" if world > 1 else "")),
+                        l2="flushed before every timed step (160 MiB fill inside the region); the per-frame working set (410 MB per-point "
+                           "table, 3.5 GB h-bar) exceeds the 126 MB L2 anyway",
                         workload_counters=dict(hit_rays=qc["R2"], valid_samples=qc["n_valid"], valid_pairs=qc["n_pairs"],
                                                candidate_samples=qc["n_cand"], occupied_voxels=gc["n_occ"], max_pts_per_voxel=gc["max_pts"])),
-            e2e=dict(value=e2e_val, unit="Mrays/s", h2d_bytes_per_step=int(mine_host.numel() * 4 * world),
-                     d2h_bytes_per_step=int(out_host.numel() * 4 * world), ms_per_step=ms_e2e / args.steps),
-            # + colour kernel + the 3 row-packing kernels of the tcgen05 path; cf. profiles/r02_ncu_launches_summary.txt
-            gpu_launches=(LAUNCHES_PER_STEP + (4 if args.precision != "fp32" else 0)) * args.steps,
+            e2e=dict(value=e2e_val, unit="Mrays/s", h2d_bytes_per_step=int(mine.numel() * 4 * world),
+                     d2h_bytes_per_step=int(R * 3 * 4 * world), ms_per_step=ms_e2e / args.steps),
+            gpu_launches=n_launch * args.steps,
             clocks=clocks,
             roofline=dict(bound="tensor", kernel=kname, achieved=achieved, peak=peak, unit="TFLOP/s",
                           frac=achieved / peak, traffic=traffic, peak_source="%s bf16 cuBLAS burst (MEASURED_PEAKS.json)" % pk["source"],
-                          algorithmic_flops_per_launch=flops, kernel_ms=shade_avg,
+                          algorithmic_flops_per_launch=kflops, kernel_ms=shade_avg,
                           kernel_share_of_step=shade_avg / (ms_res / args.steps),
-                          issued_mma_flops_per_launch=(3 * flops if args.precision != "fp32" else None),
-                          tensor_pipe_frac_issued=(3 * achieved / peak if args.precision != "fp32" else None),
+                          issued_mma_flops_per_launch=issued,
+                          tensor_pipe_frac_issued=(issued / (shade_avg * 1e-3) / 1e12 / peak if issued else None),
+                          note=("algorithmic = SURVEY 8(d) formula (542,720 FLOP per valid pair); the frozen pipeline computes 21 % of "
+                                "them once per point instead of once per pair, issued = the tcgen05.mma actually launched (BF16x3: 3 per product)"
+                                if frozen else None),
                           colour_branch_kernel_ms=color_avg),
             cpu_baseline=cpu,
         )
+        line.update(sub)
         if _RETRY_NOTE:
             line["retried_after"] = _RETRY_NOTE        # the first attempt tripped the in-kernel watchdog (see __main__)
         print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
+    D.close()
     return 0
+
+
+def train_section(D, args, dev):
+    """BASELINE configs[2]: N=600k, 3600 random rays of one 800x800 view per step (run/train_ft.py, lego_cuda.sh:109), train jitter
+    on, forward + backward + gradient exchange + 2x Adam.  The step's rays are split over the ranks (ray i -> rank i % world)."""
+    from pointnerf_b200 import parallel
+    cfg = scene.CONFIGS["ship_optimise"]
+    net, pts, opt = harness.build_model(cfg, dev, alpha_bias=3.0, is_train=True, pnb_precision=args.precision)
+    ts = parallel.TrainStep(net, world=D.world, rank=D.rank)
+    rng = np.random.RandomState(0)
+    g = torch.Generator().manual_seed(1)
+    n_steps, n_warm = 20, 4
+    acc = dict(forward=0.0, backward=0.0, exchange=0.0, adam=0.0)
+    tot = 0.0
+    hit = 0
+    for it in range(n_warm + n_steps):
+        px = rng.randint(0, cfg.W, size=(3600,)).astype(np.float32)
+        py = rng.randint(0, cfg.H, size=(3600,)).astype(np.float32)
+        gt = torch.rand(3600, 3, generator=g)
+        sel = np.arange(D.rank, 3600, D.world)
+        rays = {k: v.to(dev) for k, v in scene.make_rays(cfg, np.stack([px, py], -1)[sel]).items()}
+        kw = dict(campos=rays["campos"], raydir=rays["raydir"], bg_color=rays["bg_color"], camrotc2w=rays["camrotc2w"], pixel_idx=rays["pixel_idx"],
+                  near=rays["near"], far=rays["far"], h=rays["h"], w=rays["w"], intrinsic=rays["intrinsic"])
+        evs = []
+
+        def mark(name):
+            e = torch.cuda.Event(enable_timing=True)
+            e.record()
+            evs.append((name, e))
+        ts.step(kw, gt[sel].to(dev), mark=mark)
+        torch.cuda.synchronize(dev)
+        if it >= n_warm:
+            for (n0, a), (n1, b) in zip(evs[:-1], evs[1:]):
+                acc[n1] += a.elapsed_time(b)
+            tot += evs[0][1].elapsed_time(evs[-1][1])
+            hit += int(ts.last["n_hit_terms"] / 3)
+    ms = D.max_over_ranks(tot / n_steps)
+    del net, ts
+    torch.cuda.empty_cache()
+    return dict(steps_per_s=1e3 / ms, ms_per_step=ms, ms_fwd=acc["forward"] / n_steps, ms_bwd=acc["backward"] / n_steps,
+                ms_exchange=acc["exchange"] / n_steps, ms_adam=acc["adam"] / n_steps, mrays_per_s=3600 / ms / 1e3,
+                hit_rays_per_step=hit / n_steps,
+                what="ship_optimise (BASELINE configs[2]): N=600000, 3600 rays per step over %d rank(s), fwd (tcgen05) + bwd (tcgen05 GEMMs) + "
+                     "dense gradient all-reduce + 2x Adam over all N rows; per-phase ms are rank 0's, ms_per_step the max over ranks" % D.world)
 
 
 _RETRY_NOTE = None

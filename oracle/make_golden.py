@@ -135,11 +135,39 @@ def golden_checkpoint_layout():
     print("checkpoint_layout:", len(layout), "tensors")
 
 
+def golden_output_keys():
+    """Key sets (and per-key trailing shapes) of the dict the reference NeuralPointsRayMarching.forward returns in the three modes the
+    runners use (neural_points_volumetric_model.py:252-364): evaluation, training (zero_one_loss_items = conf_coefficient) and the
+    point-growing probe (opt.prob == 1).  tests/test_gpu_shade.py asserts the drop-in forward returns exactly these."""
+    import json
+    cfg = scene.CONFIGS["tiny"]
+    pixels = scene.centre_patch(cfg, 12)
+    rays = scene.make_rays(cfg, pixels)
+    res = {}
+    for mode in ("eval", "train", "probe"):
+        net, agg, npts, pts, opt = build_reference_net(cfg, 4.0, is_train=(mode == "train"))
+        if mode == "probe":
+            opt.prob = 1
+        ctx = torch.enable_grad() if mode == "train" else torch.no_grad()
+        with ctx:
+            out = net(rays["campos"], rays["raydir"], bg_color=rays["bg_color"], camrotc2w=rays["camrotc2w"],
+                      pixel_idx=rays["pixel_idx"], near=rays["near"], far=rays["far"], h=rays["h"], w=rays["w"],
+                      intrinsic=rays["intrinsic"])
+        res[mode] = {k: (list(v.shape[2:]) if isinstance(v, torch.Tensor) and v.dim() >= 2 else None) for k, v in out.items() if v is not None}
+    with open(os.path.join(OUT, "output_keys.json"), "w") as f:
+        json.dump(res, f, indent=1, sort_keys=True)
+    print("output_keys:", {m: sorted(v) for m, v in res.items()})
+
+
 if __name__ == "__main__":
     assert ref_shim.available(), "needs /root/reference"
+    if len(sys.argv) > 1 and sys.argv[1] == "keys":
+        golden_output_keys()
+        sys.exit(0)
     tiny = scene.CONFIGS["tiny"]
     golden_case("tiny_opaque", tiny, scene.centre_patch(tiny, 40), alpha_bias=4.0)
     golden_case("tiny_thin_sr8", tiny, scene.centre_patch(tiny, 40), alpha_bias=0.0, SR=8)
     golden_probe("tiny_probe", tiny, scene.centre_patch(tiny, 40), alpha_bias=4.0)
     golden_hyper()
     golden_checkpoint_layout()
+    golden_output_keys()

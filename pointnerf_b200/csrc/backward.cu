@@ -8,9 +8,13 @@
 // weight*conf_coefficient, straight-through clamp :722-724), and the 18 MLP tensors (in the W^T layout of pnb_mlp_t).
 // xyz receives no gradient (xyz_grad = 0 in every shipped script).
 //
-// Training batches are small (~2e4 valid samples), so the per-layer activations are recomputed in fp32 into an HBM
-// workspace and the layer gradients are plain GEMMs (hand-written fp32 tiles; the tcgen05 backward is a later round).
+// Training batches are small (~2e4 valid samples), so the per-layer activations are recomputed into an HBM workspace and the
+// layer gradients are plain GEMMs: forward recompute  H = act(X W^T + b),  dX = (dZ W) * act'  and  dW += X^T dZ  all run on
+// the tensor cores (gemm_tc.cu: tcgen05 + TMEM, BF16x3 split, fp32 accumulate; the activation derivative is fused into the
+// dX epilogue, dW is a deterministic split-K).  PNB_BWD_FP32_GEMM selects the hand-written fp32 CUDA-core tiles instead
+// (the parity reference of the tensor-core path; always used for the 128 -> 3 colour head).
 #include "common.cuh"
+#include "gemm_tc.cuh"
 
 namespace pnb {
 namespace bw {
@@ -88,28 +92,62 @@ __global__ void __launch_bounds__(256) k_gemm(const float* __restrict__ A, long 
     }
 }
 
-static int gemm_nn(const float* A, long lda, const float* Bt, long ldb, float* C, long ldc, int M, int N, int K,
-                   const float* bias, int act, cudaStream_t st) {
+struct GemmCtx {
+    bool tc;            // tensor-core GEMMs (default) or the fp32 CUDA-core tiles
+    float* part;        // split-K workspace of the tensor-core dW GEMMs
+    size_t part_bytes;
+    int* err;
+    cudaStream_t st;
+};
+constexpr int SPLITK_MAX = 64;
+constexpr size_t PART_FLOATS = (size_t)SPLITK_MAX * 288 * 256;
+
+__global__ void __launch_bounds__(256) k_lrelu_bwd(float* __restrict__ dY, const float* __restrict__ Y, long ldy, long ldd, int M, int N);
+
+// C[M x N] = act(A[M x K] * Bt[K x N] + bias)
+static int gemm_nn(const GemmCtx& cx, const float* A, long lda, const float* Bt, long ldb, float* C, long ldc, int M, int N, int K,
+                   const float* bias, int act) {
     if (M <= 0) return PNB_OK;
+    if (cx.tc && N % 16 == 0) {
+        GemmTc g{};
+        g.A = A; g.a_rs = lda; g.a_ks = 1; g.B = Bt; g.b_rs = 1; g.b_ks = ldb; g.C = C; g.ldc = ldc; g.M = M; g.N = N; g.K = K;
+        g.bias = bias; g.act = act; g.dact = nullptr; g.ldd = 0; g.dact_n = 0; g.err = cx.err;
+        return gemm_tc(g, 1, nullptr, 0, 0, cx.st);
+    }
     dim3 g((N + 63) / 64, (M + 127) / 128, 1);
-    k_gemm<false><<<g, 256, 0, st>>>(A, lda, 1, Bt, ldb, 1, C, ldc, M, N, K, K, bias, act);
+    k_gemm<false><<<g, 256, 0, cx.st>>>(A, lda, 1, Bt, ldb, 1, C, ldc, M, N, K, K, bias, act);
     return PNB_OK;
 }
-// dX[M x Kin] = dZ[M x Nout] * Wt[Kin x Nout]^T
-static int gemm_nt(const float* dZ, long ldz, const float* Wt, long ldw, float* dX, long ldx, int M, int Kin, int Nout,
-                   cudaStream_t st) {
+// dX[M x Kin] = (dZ[M x Nout] * Wt[Kin x Nout]^T) * leaky'(Y[:, :ny])      (Y == nullptr: no activation below)
+static int gemm_nt(const GemmCtx& cx, const float* dZ, long ldz, const float* Wt, long ldw, float* dX, long ldx, int M, int Kin, int Nout,
+                   const float* Y = nullptr, long ldy = 0, int ny = 0) {
     if (M <= 0) return PNB_OK;
+    if (cx.tc && Kin % 16 == 0 && ldw % 4 == 0 && ldz % 4 == 0) {
+        GemmTc g{};
+        g.A = dZ; g.a_rs = ldz; g.a_ks = 1; g.B = Wt; g.b_rs = ldw; g.b_ks = 1; g.C = dX; g.ldc = ldx; g.M = M; g.N = Kin; g.K = Nout;
+        g.bias = nullptr; g.act = 0; g.dact = Y; g.ldd = ldy; g.dact_n = ny; g.err = cx.err;
+        return gemm_tc(g, 1, nullptr, 0, 0, cx.st);
+    }
     dim3 g((Kin + 63) / 64, (M + 127) / 128, 1);
-    k_gemm<false><<<g, 256, 0, st>>>(dZ, ldz, 1, Wt, 1, ldw, dX, ldx, M, Kin, Nout, Nout, nullptr, 0);
+    k_gemm<false><<<g, 256, 0, cx.st>>>(dZ, ldz, 1, Wt, 1, ldw, dX, ldx, M, Kin, Nout, Nout, nullptr, 0);
+    if (Y) k_lrelu_bwd<<<(int)(((long)M * ny + 255) / 256), 256, 0, cx.st>>>(dX, Y, ldy, ldx, M, ny);
     return PNB_OK;
 }
-// dWt[Kin x Nout] += X[M x Kin]^T * dZ[M x Nout]   (reduction over M split into chunks, atomics)
-static int gemm_tn_acc(const float* X, long ldx, const float* dZ, long ldz, float* dWt, long ldw, int M, int Kin, int Nout,
-                       cudaStream_t st) {
+// dWt[Kin x Nout] += X[M x Kin]^T * dZ[M x Nout]   (reduction over the M rows: deterministic split-K on the tensor cores,
+// atomics on the CUDA-core path)
+static int gemm_tn_acc(const GemmCtx& cx, const float* X, long ldx, const float* dZ, long ldz, float* dWt, long ldw, int M, int Kin, int Nout) {
     if (M <= 0) return PNB_OK;
+    if (cx.tc && Nout % 16 == 0 && ldw % 4 == 0) {
+        GemmTc g{};
+        g.A = X; g.a_rs = 1; g.a_ks = ldx; g.B = dZ; g.b_rs = 1; g.b_ks = ldz; g.C = dWt; g.ldc = ldw; g.M = Kin; g.N = Nout; g.K = M;
+        g.bias = nullptr; g.act = 0; g.dact = nullptr; g.ldd = 0; g.dact_n = 0; g.err = cx.err;
+        int splits = (M + 2047) / 2048;
+        splits = splits < 2 ? 2 : (splits > SPLITK_MAX ? SPLITK_MAX : splits);
+        return gemm_tc(g, splits, cx.part, cx.part_bytes, 1, cx.st);
+    }
     const int chunk = 2048;
     dim3 g((Nout + 63) / 64, (Kin + 127) / 128, (M + chunk - 1) / chunk);
-    k_gemm<true><<<g, 256, 0, st>>>(X, 1, ldx, dZ, ldz, 1, dWt, ldw, Kin, Nout, M, chunk, nullptr, 0);
+    k_gemm<true><<<g, 256, 0, cx.st>>>(X, 1, ldx, dZ, ldz, 1, dWt, ldw, Kin, Nout, M, chunk, nullptr, 0);
     return PNB_OK;
 }
 
@@ -484,6 +522,7 @@ struct Layout {
     float *X1, *H1, *X3, *H3, *H4, *wc, *wn, *sp, *sg, *CX, *C1, *C2, *C3, *O3, *G1, *G2, *G3, *GS1, *GS2, *GS3, *dO3, *dsig, *dwc;
     int* pidx;
     float4* d_sigma_rgb;
+    float* part;
     size_t bytes;
 };
 static Layout carve(void* ws, size_t cap, int max_valid, int cap_samples) {
@@ -500,6 +539,7 @@ static Layout carve(void* ws, size_t cap, int max_valid, int cap_samples) {
     L.GS1 = c.take<float>(S * 288); L.GS2 = c.take<float>(S * 128); L.GS3 = c.take<float>(S * 128);
     L.dO3 = c.take<float>(S * 4); L.dsig = c.take<float>(S);
     L.d_sigma_rgb = c.take<float4>((size_t)(cap_samples > 0 ? cap_samples : 1));
+    L.part = c.take<float>(PART_FLOATS);
     L.bytes = align_up(c.off);
     return L;
 }
@@ -518,7 +558,7 @@ extern "C" size_t pnb_backward_bytes(int n_valid, int cap_samples) { return carv
 extern "C" int pnb_shade_backward(const pnb_query_t* q, const pnb_points_t* pts, const pnb_mlp_t* mlp,
                                   const pnb_shade_opts_t* opts, const float* d_sigma_rgb_fwd, const float* d_ray_color,
                                   int n_valid, float* d_emb, float* d_color, float* d_dir, float* d_conf,
-                                  float* const* d_mlp_w, float* const* d_mlp_b, void* ws, size_t ws_bytes,
+                                  float* const* d_mlp_w, float* const* d_mlp_b, void* ws, size_t ws_bytes, int flags, int* d_err,
                                   pnb_stream_t stream_) {
     cudaStream_t st = (cudaStream_t)stream_;
     PNB_REQUIRE(q && pts && mlp && opts && d_sigma_rgb_fwd && d_ray_color && d_mlp_w && d_mlp_b && ws, PNB_ERR_INVALID,
@@ -538,58 +578,54 @@ extern "C" int pnb_shade_backward(const pnb_query_t* q, const pnb_points_t* pts,
     p.GS1 = L.GS1; p.GS2 = L.GS2; p.GS3 = L.GS3; p.dO3 = L.dO3; p.dsig = L.dsig; p.d_sigma_rgb = L.d_sigma_rgb;
     p.wa = mlp->w[4]; p.ba = mlp->b[4];
     const int wb = (S * 32 + 255) / 256;   // one warp per sample
-    // ---------------- forward recompute (fp32) ----------------
+    GemmCtx cx{(flags & PNB_BWD_FP32_GEMM) == 0, L.part, PART_FLOATS * sizeof(float), d_err, st};
+    PNB_REQUIRE(!cx.tc || d_err, PNB_ERR_INVALID, "pnb_shade_backward: the tensor-core path needs d_err");
+    // ---------------- forward recompute ----------------
     k_bwd_build<<<wb, 256, 0, st>>>(p);
-    gemm_nn(L.X1, 288, mlp->w[0], 256, L.H1, 256, P, 256, 288, mlp->b[0], 1, st);
-    gemm_nn(L.H1, 256, mlp->w[1], 256, L.X3, 272, P, 256, 256, mlp->b[1], 1, st);   // H2 into X3[:, :256]
-    gemm_nn(L.X3, 272, mlp->w[2], 256, L.H3, 256, P, 256, 272, mlp->b[2], 1, st);
-    gemm_nn(L.H3, 256, mlp->w[3], 256, L.H4, 256, P, 256, 256, mlp->b[3], 1, st);
+    gemm_nn(cx, L.X1, 288, mlp->w[0], 256, L.H1, 256, P, 256, 288, mlp->b[0], 1);
+    gemm_nn(cx, L.H1, 256, mlp->w[1], 256, L.X3, 272, P, 256, 256, mlp->b[1], 1);   // H2 into X3[:, :256]
+    gemm_nn(cx, L.X3, 272, mlp->w[2], 256, L.H3, 256, P, 256, 272, mlp->b[2], 1);
+    gemm_nn(cx, L.H3, 256, mlp->w[3], 256, L.H4, 256, P, 256, 256, mlp->b[3], 1);
     k_bwd_reduce_fwd<<<wb, 256, 0, st>>>(p);
-    gemm_nn(L.CX, 288, mlp->w[5], 128, L.C1, 128, S, 128, 288, mlp->b[5], 1, st);
-    gemm_nn(L.C1, 128, mlp->w[6], 128, L.C2, 128, S, 128, 128, mlp->b[6], 1, st);
-    gemm_nn(L.C2, 128, mlp->w[7], 128, L.C3, 128, S, 128, 128, mlp->b[7], 1, st);
-    gemm_nn(L.C3, 128, mlp->w[8], 3, L.O3, 4, S, 3, 128, mlp->b[8], 0, st);
+    gemm_nn(cx, L.CX, 288, mlp->w[5], 128, L.C1, 128, S, 128, 288, mlp->b[5], 1);
+    gemm_nn(cx, L.C1, 128, mlp->w[6], 128, L.C2, 128, S, 128, 128, mlp->b[6], 1);
+    gemm_nn(cx, L.C2, 128, mlp->w[7], 128, L.C3, 128, S, 128, 128, mlp->b[7], 1);
+    gemm_nn(cx, L.C3, 128, mlp->w[8], 3, L.O3, 4, S, 3, 128, mlp->b[8], 0);          // N = 3: CUDA cores
     // ---------------- backward ----------------
     k_bwd_head<<<(S + 255) / 256, 256, 0, st>>>(p);
-    // colour branch
-    gemm_tn_acc(L.C3, 128, L.dO3, 4, d_mlp_w[8], 3, S, 128, 3, st);
+    // colour branch (each dX GEMM applies the derivative of the LeakyReLU below it in its epilogue)
+    gemm_tn_acc(cx, L.C3, 128, L.dO3, 4, d_mlp_w[8], 3, S, 128, 3);
     k_colsum<<<dim3(1, (S + 2047) / 2048), 256, 0, st>>>(L.dO3, 4, S, 3, d_mlp_b[8]);
-    gemm_nt(L.dO3, 4, mlp->w[8], 3, L.GS3, 128, S, 128, 3, st);                      // dC3
-    k_lrelu_bwd<<<(int)(((long)S * 128 + 255) / 256), 256, 0, st>>>(L.GS3, L.C3, 128, 128, S, 128);
-    gemm_tn_acc(L.C2, 128, L.GS3, 128, d_mlp_w[7], 128, S, 128, 128, st);
+    gemm_nt(cx, L.dO3, 4, mlp->w[8], 3, L.GS3, 128, S, 128, 3, L.C3, 128, 128);       // dC3
+    gemm_tn_acc(cx, L.C2, 128, L.GS3, 128, d_mlp_w[7], 128, S, 128, 128);
     k_colsum<<<dim3(4, (S + 2047) / 2048), 256, 0, st>>>(L.GS3, 128, S, 128, d_mlp_b[7]);
-    gemm_nt(L.GS3, 128, mlp->w[7], 128, L.GS2, 128, S, 128, 128, st);                // dC2
-    k_lrelu_bwd<<<(int)(((long)S * 128 + 255) / 256), 256, 0, st>>>(L.GS2, L.C2, 128, 128, S, 128);
-    gemm_tn_acc(L.C1, 128, L.GS2, 128, d_mlp_w[6], 128, S, 128, 128, st);
+    gemm_nt(cx, L.GS3, 128, mlp->w[7], 128, L.GS2, 128, S, 128, 128, L.C2, 128, 128); // dC2
+    gemm_tn_acc(cx, L.C1, 128, L.GS2, 128, d_mlp_w[6], 128, S, 128, 128);
     k_colsum<<<dim3(4, (S + 2047) / 2048), 256, 0, st>>>(L.GS2, 128, S, 128, d_mlp_b[6]);
-    gemm_nt(L.GS2, 128, mlp->w[6], 128, L.GS3, 128, S, 128, 128, st);                // dC1 (reuse GS3)
-    k_lrelu_bwd<<<(int)(((long)S * 128 + 255) / 256), 256, 0, st>>>(L.GS3, L.C1, 128, 128, S, 128);
-    gemm_tn_acc(L.CX, 288, L.GS3, 128, d_mlp_w[5], 128, S, 288, 128, st);
+    gemm_nt(cx, L.GS2, 128, mlp->w[6], 128, L.GS3, 128, S, 128, 128, L.C1, 128, 128); // dC1 (reuse GS3)
+    gemm_tn_acc(cx, L.CX, 288, L.GS3, 128, d_mlp_w[5], 128, S, 288, 128);
     k_colsum<<<dim3(4, (S + 2047) / 2048), 256, 0, st>>>(L.GS3, 128, S, 128, d_mlp_b[5]);
-    gemm_nt(L.GS3, 128, mlp->w[5], 128, L.GS1, 288, S, 288, 128, st);                // d(hbar | view PE)
+    gemm_nt(cx, L.GS3, 128, mlp->w[5], 128, L.GS1, 288, S, 288, 128);                 // d(hbar | view PE)
     // K-reduction + alpha branch
     k_bwd_reduce_bwd<<<wb, 256, 0, st>>>(p, L.dwc);
     k_bwd_alpha_params<<<(P + 1023) / 1024, 256, 0, st>>>(p, d_mlp_w[4], d_mlp_b[4]);
     // block3.2
     k_lrelu_bwd<<<(int)(((long)P * 256 + 255) / 256), 256, 0, st>>>(L.G3, L.H4, 256, 256, P, 256);
-    gemm_tn_acc(L.H3, 256, L.G3, 256, d_mlp_w[3], 256, P, 256, 256, st);
+    gemm_tn_acc(cx, L.H3, 256, L.G3, 256, d_mlp_w[3], 256, P, 256, 256);
     k_colsum<<<dim3(8, (P + 2047) / 2048), 256, 0, st>>>(L.G3, 256, P, 256, d_mlp_b[3]);
-    gemm_nt(L.G3, 256, mlp->w[3], 256, L.G1, 288, P, 256, 256, st);                  // dH3 in G1[:, :256] (ld 288)
-    k_lrelu_bwd<<<(int)(((long)P * 256 + 255) / 256), 256, 0, st>>>(L.G1, L.H3, 256, 288, P, 256);
+    gemm_nt(cx, L.G3, 256, mlp->w[3], 256, L.G1, 288, P, 256, 256, L.H3, 256, 256);   // dH3 in G1[:, :256] (ld 288)
     // block3.0
-    gemm_tn_acc(L.X3, 272, L.G1, 288, d_mlp_w[2], 256, P, 272, 256, st);
+    gemm_tn_acc(cx, L.X3, 272, L.G1, 288, d_mlp_w[2], 256, P, 272, 256);
     k_colsum<<<dim3(8, (P + 2047) / 2048), 256, 0, st>>>(L.G1, 288, P, 256, d_mlp_b[2]);
-    gemm_nt(L.G1, 288, mlp->w[2], 256, L.G2, 272, P, 272, 256, st);                  // dX3 = (dH2 | d extras)
-    k_lrelu_bwd<<<(int)(((long)P * 256 + 255) / 256), 256, 0, st>>>(L.G2, L.X3, 272, 272, P, 256);
+    gemm_nt(cx, L.G1, 288, mlp->w[2], 256, L.G2, 272, P, 272, 256, L.X3, 272, 256);   // dX3 = (dH2 | d extras); the extras have no activation
     // block1.2
-    gemm_tn_acc(L.H1, 256, L.G2, 272, d_mlp_w[1], 256, P, 256, 256, st);
+    gemm_tn_acc(cx, L.H1, 256, L.G2, 272, d_mlp_w[1], 256, P, 256, 256);
     k_colsum<<<dim3(8, (P + 2047) / 2048), 256, 0, st>>>(L.G2, 272, P, 256, d_mlp_b[1]);
-    gemm_nt(L.G2, 272, mlp->w[1], 256, L.G3, 256, P, 256, 256, st);                  // dH1 in G3
-    k_lrelu_bwd<<<(int)(((long)P * 256 + 255) / 256), 256, 0, st>>>(L.G3, L.H1, 256, 256, P, 256);
+    gemm_nt(cx, L.G2, 272, mlp->w[1], 256, L.G3, 256, P, 256, 256, L.H1, 256, 256);   // dH1 in G3
     // block1.0
-    gemm_tn_acc(L.X1, 288, L.G3, 256, d_mlp_w[0], 256, P, 288, 256, st);
+    gemm_tn_acc(cx, L.X1, 288, L.G3, 256, d_mlp_w[0], 256, P, 288, 256);
     k_colsum<<<dim3(8, (P + 2047) / 2048), 256, 0, st>>>(L.G3, 256, P, 256, d_mlp_b[0]);
-    gemm_nt(L.G3, 256, mlp->w[0], 256, L.G1, 288, P, 288, 256, st);                  // dX1
+    gemm_nt(cx, L.G3, 256, mlp->w[0], 256, L.G1, 288, P, 288, 256);                   // dX1
     // scatter to the points
     k_bwd_scatter<<<(int)(((long)P * 4 + 255) / 256), 256, 0, st>>>(p, L.dwc, d_emb, d_color, d_dir, d_conf);
     PNB_CHECK_CUDA(cudaGetLastError());

@@ -1,0 +1,201 @@
+// Generic fp32-in / fp32-out GEMM on the 5th-generation tensor cores (tcgen05 + TMEM) with the BF16x3 error-compensated split
+// of shade_tc.cu -- the GEMM engine of the BACKWARD pass (backward.cu): forward recompute, dX = dZ . W and dW = X^T . dZ.
+//
+//   C[M x N] = op( sum_k A(m,k) * B(n,k) + bias[n] )        A(m,k) = A[m*a_rs + k*a_ks],  B(n,k) = B[n*b_rs + k*b_ks]
+//
+// Either stride of an operand may be the unit one: operands whose reduction index is NOT contiguous in memory (W^T buffers,
+// the activations of dW = X^T dZ) are transposed on the way into shared memory, so the tensor cores only ever see the K-major
+// core-matrix layout that umma.cuh pins (tests/test_gpu_umma.py).  One CTA = one 128 x 128 output tile (UMMA M = 128, N = 128,
+// fp32 accumulator in 128 TMEM columns), K blocks of 32 through a 4-stage shared-memory ring:
+//   warps 0-3  load fp32 rows from global memory (thread = tile row of A and of B), split into bf16 hi / lo, 16-byte stores
+//              into the operand layout; afterwards the epilogue (thread = accumulator row = TMEM lane)
+//   warp  4    issues 6 tcgen05.mma per K block (A_hi W_hi, A_lo W_hi, A_hi W_lo for the two K=16 steps), one commit per block
+// Split-K (dW: the reduction runs over the ~1e5 pair rows of a training batch): blockIdx.z owns a K range and writes its partial
+// tile to a workspace; k_splitk_reduce adds the partials in split order (deterministic, no atomics).
+#include "common.cuh"
+#include "gemm_tc.cuh"
+#include "umma.cuh"
+
+namespace pnb {
+using namespace umma;
+
+namespace gtc {
+constexpr int TM = 128, TN = 128, NSTAGE = 4;
+constexpr int BLK = 128 * 64;             // [128 x 32] bf16 block
+constexpr int NTHR = 160;
+struct Smem {
+    unsigned char a_hi[NSTAGE][BLK], a_lo[NSTAGE][BLK], b_hi[NSTAGE][BLK], b_lo[NSTAGE][BLK];
+    uint64_t bar_full[NSTAGE], bar_empty[NSTAGE], bar_acc;
+    uint32_t tmem_base;
+};
+// one tile row (32 K elements of row `r`) of an operand -> hi / lo blocks.  rs / ks: element strides of the row / reduction index.
+__device__ __forceinline__ void load_row(const float* __restrict__ P, long rs, long ks, long r, bool row_ok, int k0, int kend, unsigned char* hi,
+                                         unsigned char* lo, int t) {
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        float v[8];
+        const int kc = k0 + 8 * c;
+        if (!row_ok || kc >= kend) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[e] = 0.f;
+        } else if (ks == 1 && kc + 8 <= kend) {
+            const float4 x0 = __ldg(reinterpret_cast<const float4*>(P + r * rs + kc)), x1 = __ldg(reinterpret_cast<const float4*>(P + r * rs + kc + 4));
+            v[0] = x0.x; v[1] = x0.y; v[2] = x0.z; v[3] = x0.w; v[4] = x1.x; v[5] = x1.y; v[6] = x1.z; v[7] = x1.w;
+        } else {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[e] = (kc + e < kend) ? __ldg(P + r * rs + (long)(kc + e) * ks) : 0.f;
+        }
+        uint32_t h[4], l[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) split_bf16x2(v[2 * i], v[2 * i + 1], h[i], l[i]);
+        const uint32_t off = tile_offset_bytes<LAYOUT_NONE>(t, 8 * c);
+        *reinterpret_cast<uint4*>(hi + off) = make_uint4(h[0], h[1], h[2], h[3]);
+        *reinterpret_cast<uint4*>(lo + off) = make_uint4(l[0], l[1], l[2], l[3]);
+    }
+}
+}  // namespace gtc
+
+__global__ void __launch_bounds__(gtc::NTHR, 1) k_gemm_tc(GemmTc g) {
+    using namespace gtc;
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    Smem& sm = *reinterpret_cast<Smem*>(smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u));
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int m0 = blockIdx.y * TM, n0 = blockIdx.x * TN;
+    const int kbeg = blockIdx.z * g.kchunk, kend = min(g.K, kbeg + g.kchunk);
+    const int nkb = (kend - kbeg + 31) >> 5;
+
+    if (tid == 0) {
+        for (int s = 0; s < NSTAGE; ++s) { mbar_init(&sm.bar_full[s], 128); mbar_init(&sm.bar_empty[s], 1); }
+        mbar_init(&sm.bar_acc, 1);
+        mbar_fence_init();
+    }
+    if (warp == 4) tmem_alloc<128>(&sm.tmem_base);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tacc = sm.tmem_base;
+
+    if (warp == 4) {
+        const uint32_t idesc = make_idesc_bf16(128, 128);
+        const uint32_t hiw = desc_hi<LAYOUT_NONE>();
+        const uint32_t ah0 = desc_lo<LAYOUT_NONE>(smem_u32(sm.a_hi[0])), al0 = desc_lo<LAYOUT_NONE>(smem_u32(sm.a_lo[0]));
+        const uint32_t bh0 = desc_lo<LAYOUT_NONE>(smem_u32(sm.b_hi[0])), bl0 = desc_lo<LAYOUT_NONE>(smem_u32(sm.b_lo[0]));
+        constexpr uint32_t KADV = kstep_adv16<LAYOUT_NONE>(), SADV = BLK >> 4;
+        bool ok = true;
+        for (int kb = 0; kb < nkb && ok; ++kb) {
+            const uint32_t s = (uint32_t)kb & (NSTAGE - 1), ph = ((uint32_t)kb >> 2) & 1u;
+            if (!mbar_wait(&sm.bar_full[s], ph, g.err, 71)) { ok = false; break; }
+            tc_fence_after();
+            const uint32_t ah = ah0 + s * SADV, al = al0 + s * SADV, bh = bh0 + s * SADV, bl = bl0 + s * SADV;
+            mma_ss2_w(tacc, ah, hiw, bh, hiw, idesc, kb ? 1u : 0u);
+            mma_ss2_w(tacc, al, hiw, bh, hiw, idesc, 1u);
+            mma_ss2_w(tacc, ah + KADV, hiw, bh + KADV, hiw, idesc, 1u);
+            mma_ss2_w(tacc, al + KADV, hiw, bh + KADV, hiw, idesc, 1u);
+            mma_ss2_w(tacc, ah, hiw, bl, hiw, idesc, 1u);
+            mma_ss2_w(tacc, ah + KADV, hiw, bl + KADV, hiw, idesc, 1u);
+            mma_commit_w(&sm.bar_empty[s]);
+        }
+        mma_commit_w(&sm.bar_acc);
+    } else {
+        const int t = tid;                          // tile row of A and of B, accumulator row in the epilogue
+        const long ra = m0 + t, rb = n0 + t;
+        const bool a_ok = ra < g.M, b_ok = rb < g.N;
+        bool ok = true;
+        for (int kb = 0; kb < nkb; ++kb) {
+            const uint32_t s = (uint32_t)kb & (NSTAGE - 1), ph = ((uint32_t)kb >> 2) & 1u;
+            if (!mbar_wait(&sm.bar_empty[s], ph ^ 1u, g.err, 72)) { ok = false; break; }
+            const int k0 = kbeg + 32 * kb;
+            load_row(g.A, g.a_rs, g.a_ks, ra, a_ok, k0, kend, sm.a_hi[s], sm.a_lo[s], t);
+            load_row(g.B, g.b_rs, g.b_ks, rb, b_ok, k0, kend, sm.b_hi[s], sm.b_lo[s], t);
+            fence_proxy_async();
+            mbar_arrive(&sm.bar_full[s]);
+        }
+        if (ok && mbar_wait(&sm.bar_acc, 0u, g.err, 73)) {
+            tc_fence_after();
+            const uint32_t tl = tacc + ((uint32_t)(warp * 32) << 16);
+            float* crow = g.part ? g.part + ((size_t)blockIdx.z * g.M + (size_t)ra) * g.N : g.C + ra * g.ldc;
+#pragma unroll 1
+            for (int c = 0; c < TN / 16; ++c) {
+                const int n = n0 + 16 * c;
+                uint32_t v[16];
+                tmem_ld16(tl + (uint32_t)(16 * c), v);      // all lanes of the warp (sync.aligned), also those of rows >= M
+                tmem_ld_wait();
+                if (!a_ok || n >= g.N) continue;
+                float y[16];
+#pragma unroll
+                for (int e = 0; e < 16; ++e) y[e] = __uint_as_float(v[e]);
+                if (!g.part) {
+                    if (g.bias) {
+#pragma unroll
+                        for (int e = 0; e < 16; ++e) y[e] += __ldg(g.bias + n + e);
+                    }
+                    if (g.act) {
+#pragma unroll
+                        for (int e = 0; e < 16; ++e) y[e] = fmaxf(y[e], 0.01f * y[e]);
+                    }
+                    if (g.dact && n < g.dact_n) {            // backward of the LeakyReLU below: * (Y > 0 ? 1 : 0.01)
+                        const float4* yp = reinterpret_cast<const float4*>(g.dact + ra * g.ldd + n);
+#pragma unroll
+                        for (int e4 = 0; e4 < 4; ++e4) {
+                            const float4 yy = __ldg(yp + e4);
+                            y[4 * e4] *= yy.x > 0.f ? 1.0f : 0.01f; y[4 * e4 + 1] *= yy.y > 0.f ? 1.0f : 0.01f;
+                            y[4 * e4 + 2] *= yy.z > 0.f ? 1.0f : 0.01f; y[4 * e4 + 3] *= yy.w > 0.f ? 1.0f : 0.01f;
+                        }
+                    }
+                }
+                float4* dst = reinterpret_cast<float4*>(crow + n);
+#pragma unroll
+                for (int e4 = 0; e4 < 4; ++e4) dst[e4] = make_float4(y[4 * e4], y[4 * e4 + 1], y[4 * e4 + 2], y[4 * e4 + 3]);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 4) tmem_dealloc<128>(sm.tmem_base);
+}
+
+// C[m][n] (+)= sum_z part[z][m][n], z ascending
+__global__ void __launch_bounds__(256) k_splitk_reduce(const float* __restrict__ part, int splits, int M, int N, float* __restrict__ C, long ldc, int accumulate) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long)M * N) return;
+    const int m = (int)(i / N), n = (int)(i - (long)m * N);
+    float s = accumulate ? C[m * ldc + n] : 0.f;
+    for (int z = 0; z < splits; ++z) s += part[(size_t)z * M * N + i];
+    C[m * ldc + n] = s;
+}
+
+int gemm_tc(const GemmTc& g0, int splits, float* part_ws, size_t part_bytes, int accumulate, cudaStream_t st) {
+    GemmTc g = g0;
+    if (g.M <= 0 || g.N <= 0 || g.K <= 0) return PNB_OK;
+    PNB_REQUIRE(g.N % 16 == 0 && g.ldc % 4 == 0, PNB_ERR_INVALID, "gemm_tc: N (%d) must be a multiple of 16 and ldc (%ld) of 4", g.N, g.ldc);
+    PNB_REQUIRE((g.a_rs == 1) != (g.a_ks == 1) || g.K == 1 || g.M == 1, PNB_ERR_INVALID, "gemm_tc: one stride of A must be 1");
+    PNB_REQUIRE(g.a_ks != 1 || g.a_rs % 4 == 0, PNB_ERR_INVALID, "gemm_tc: leading dimension of A must be a multiple of 4");
+    PNB_REQUIRE(g.b_ks != 1 || g.b_rs % 4 == 0, PNB_ERR_INVALID, "gemm_tc: leading dimension of B must be a multiple of 4");
+    static int configured[64] = {0};
+    int dev = 0;
+    PNB_CHECK_CUDA(cudaGetDevice(&dev));
+    const size_t smem = sizeof(gtc::Smem) + 128;
+    if (dev >= 0 && dev < 64 && !configured[dev]) {
+        PNB_CHECK_CUDA(cudaFuncSetAttribute(k_gemm_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured[dev] = 1;
+    }
+    if (splits <= 1) {
+        g.kchunk = g.K; g.part = nullptr;
+        dim3 grid((g.N + gtc::TN - 1) / gtc::TN, (g.M + gtc::TM - 1) / gtc::TM, 1);
+        PNB_REQUIRE(!accumulate, PNB_ERR_INVALID, "gemm_tc: accumulation needs the split-K path");
+        k_gemm_tc<<<grid, gtc::NTHR, smem, st>>>(g);
+    } else {
+        int kchunk = ((g.K + splits - 1) / splits + 31) / 32 * 32;
+        splits = (g.K + kchunk - 1) / kchunk;
+        PNB_REQUIRE(part_ws && part_bytes >= (size_t)splits * g.M * g.N * sizeof(float), PNB_ERR_WORKSPACE, "gemm_tc: split-K workspace too small");
+        g.kchunk = kchunk; g.part = part_ws;
+        dim3 grid((g.N + gtc::TN - 1) / gtc::TN, (g.M + gtc::TM - 1) / gtc::TM, splits);
+        k_gemm_tc<<<grid, gtc::NTHR, smem, st>>>(g);
+        const long n = (long)g.M * g.N;
+        k_splitk_reduce<<<(int)((n + 255) / 256), 256, 0, st>>>(part_ws, splits, g.M, g.N, g.C, g.ldc, accumulate);
+    }
+    PNB_CHECK_CUDA(cudaGetLastError());
+    return PNB_OK;
+}
+
+}  // namespace pnb

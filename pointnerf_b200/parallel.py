@@ -121,3 +121,77 @@ def allreduce_rows_sparse(grad, world, group=None):
             g2.index_add_(0, blk[:, 0].to(torch.int64), blk[:, 1:])
         off += n
     return int(sum(counts))
+
+
+# ---- one optimisation step, data-parallel over rays (the reference's single-GPU step is
+# models/mvs_points_volumetric_model.py:87-118 + models/base_rendering_model.py:533-662)
+class TrainStep:
+    """Per-scene optimisation step on `world` ranks: every rank runs forward + backward on ITS rays of the step, the gradients
+    are summed across ranks (point rows: dense all-reduce or the sparse touched-rows exchange; MLP: one flat all-reduce) and
+    every rank takes the same two Adam steps (MLP lr, point-feature plr - the reference's two optimisers), so the replicas stay
+    bit-identical without a broadcast.
+
+    The loss is the reference's (`color_loss_items = coarse_raycolor` MSE over the rays that hit, weight 1, plus the zero-one
+    log-barrier on conf_coefficient, weight 1e-4), written in SUM form and divided by the GLOBAL counts (one 2-element
+    all-reduce before the backward): the summed gradient is then exactly the gradient of the un-sharded step on the union of
+    the ranks' rays, whatever the split of hit rays between the ranks."""
+
+    def __init__(self, net, world=1, rank=0, lr=5e-4, plr=2e-3, zero_one_weight=1e-4, sparse_points=False, group=None):
+        self.net, self.world, self.rank, self.group = net, world, rank, group
+        self.zero_one_weight = zero_one_weight
+        self.sparse_points = sparse_points
+        self.mlp_params = [p for p in net.aggregator.parameters() if p.requires_grad]
+        self.pt_params = [p for p in net.neural_points.parameters() if p.requires_grad]
+        self.opt_mlp = torch.optim.Adam(self.mlp_params, lr=lr, betas=(0.9, 0.999))
+        self.opt_pts = torch.optim.Adam(self.pt_params, lr=plr, betas=(0.9, 0.999))
+        self.last = {}
+
+    def loss_terms(self, out, gt):
+        """Local SUMS and counts: (sum of squared colour errors over hit rays and channels, #terms), (sum of -log(conf + 1e-3), #terms)."""
+        mask = out["ray_mask"][0] > 0
+        pred = out["coarse_raycolor"][0]
+        se = ((pred - gt[mask]) ** 2).sum()
+        n_se = pred.numel()
+        cc = out.get("conf_coefficient", None)
+        if cc is not None and cc.numel() > 0:
+            zo = (-torch.log(cc + 1e-3)).sum()
+            n_zo = cc.numel()
+        else:
+            zo, n_zo = pred.sum() * 0.0, 0
+        return se, n_se, zo, n_zo
+
+    def step(self, fwd_kwargs, gt, mark=None):
+        """fwd_kwargs: the arguments of NeuralPointsRayMarching.forward for THIS rank's rays; gt: [R_local, 3] colours of those rays.
+        mark: optional callable(name) invoked between the phases (forward / backward / exchange / adam) - bench.py records CUDA
+        events there.  Returns the global loss (a 0-d tensor, identical on every rank)."""
+        mark = mark or (lambda name: None)
+        mark("start")
+        out = self.net(**fwd_kwargs)
+        se, n_se, zo, n_zo = self.loss_terms(out, gt)
+        cnt = torch.tensor([float(n_se), float(n_zo)], dtype=torch.float64, device=se.device)
+        if self.world > 1:
+            dist.all_reduce(cnt, op=dist.ReduceOp.SUM, group=self.group)
+        n_se_g, n_zo_g = max(float(cnt[0].item()), 1.0), max(float(cnt[1].item()), 1.0)
+        loss_local = se / n_se_g + self.zero_one_weight * zo / n_zo_g
+        self.opt_mlp.zero_grad(set_to_none=False)
+        self.opt_pts.zero_grad(set_to_none=False)
+        mark("forward")
+        loss_local.backward()
+        mark("backward")
+        if self.world > 1:
+            if self.sparse_points:
+                for p in self.pt_params:
+                    if p.grad is not None:
+                        allreduce_rows_sparse(p.grad, self.world, group=self.group)
+                allreduce_gradients(self.mlp_params, self.world, group=self.group)
+            else:
+                allreduce_gradients(self.pt_params + self.mlp_params, self.world, group=self.group)
+        mark("exchange")
+        self.opt_mlp.step()
+        self.opt_pts.step()
+        mark("adam")
+        loss = loss_local.detach().clone()
+        if self.world > 1:
+            dist.all_reduce(loss, op=dist.ReduceOp.SUM, group=self.group)
+        self.last = dict(out=out, n_hit_terms=n_se_g, n_conf_terms=n_zo_g)
+        return loss

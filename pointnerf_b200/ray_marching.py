@@ -230,7 +230,7 @@ class NeuralPoints(nn.Module):
 
 class _RenderFn(torch.autograd.Function):
     """Differentiable face of the fused path: ray_color[R,3] = f(points_embeding, points_color, points_dir,
-    points_conf, 18 MLP tensors).  Backward = pnb_shade_backward (recompute in fp32, hand-written GEMM tiles)."""
+    points_conf, 18 MLP tensors).  Backward = pnb_shade_backward (activations recomputed, layer GEMMs on tcgen05 / BF16x3)."""
 
     @staticmethod
     def forward(ctx, mod, run_args, emb, color, pdir, conf, *mlp_params):
@@ -272,10 +272,13 @@ class _RenderFn(torch.autograd.Function):
         mlp = mod._mlp.get(mod.aggregator)
         stream = torch.cuda.current_stream(dev).cuda_stream
         ptr = lambda t: t.data_ptr() if t is not None else None
+        if getattr(mod, "_bwd_err", None) is None or mod._bwd_err.device != dev:
+            mod._bwd_err = torch.zeros(4, dtype=torch.int32, device=dev)     # checked (synchronising) by check_errors()
+        flags = _lib.BWD_FP32_GEMM if int(getattr(mod.opt, "pnb_bwd_fp32", 0)) else 0
         _lib.check(lib.pnb_shade_backward(_lib.C.byref(q.desc), _lib.C.byref(pts), _lib.C.byref(mlp), _lib.C.byref(ctx.o),
                                           ctx.sigma_rgb.data_ptr(), g_color.data_ptr(), int(ctx.n_valid), ptr(outs[0]),
                                           ptr(outs[1]), ptr(outs[2]), ptr(outs[3]), wp, bp, mod._bwd_ws.data_ptr(),
-                                          mod._bwd_ws.numel(), stream), "pnb_shade_backward")
+                                          mod._bwd_ws.numel(), flags, mod._bwd_err.data_ptr(), stream), "pnb_shade_backward")
         grads = []
         for i, shp in enumerate(MLP_SHAPES):                 # W^T [K_pad, N] -> nn.Linear weight [N, K]
             grads.append(dwt[i][:shp[1]].t().contiguous().view(ctx.mlp_shapes[2 * i]))
@@ -450,6 +453,12 @@ class NeuralPointsRayMarching(nn.Module):
         workspace for the next call) when the last call dropped samples, PnbError on a pipeline time-out."""
         if getattr(self, "_status_pending", None):
             self._poll_status(block=True)
+        be = getattr(self, "_bwd_err", None)
+        if be is not None:
+            code = int(be[0].item())
+            if code != 0:
+                be.zero_()
+                raise _lib.PnbError("pnb200: tcgen05 GEMM pipeline time-out in the backward pass (code %d)" % code)
         if self._err is not None:
             code = int(self._err[0].item())
             if code != 0:

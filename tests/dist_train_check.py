@@ -1,0 +1,107 @@
+"""Launched by torchrun (NCCL, one rank per GPU) from tests/test_gpu_dist.py or by hand:
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P tests/dist_train_check.py [config]
+
+Checks of the multi-GPU paths on real GPUs:
+  1. optimisation: parallel.TrainStep for k steps, each rank on ITS rays of the step -> the replicas are BIT-identical on every rank
+     (identical all-reduced gradients + identical Adam), and equal - to fp32 summation order - to the un-sharded step on the union of the
+     rays (run by every rank on a second copy of the model);
+  2. render: one frame interleave-sharded over the ranks + all-gather == the frame rendered by one rank, bit for bit;
+  3. grow: every rank probes its own frames, allgather_new_points, grow_points -> identical clouds, grid rebuilt, render still agrees.
+Prints one JSON line on rank 0; exit code != 0 on any failure."""
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from pointnerf_b200 import harness, parallel, scene  # noqa: E402
+
+
+def fwd_kwargs(cfg, pixels, dev):
+    rays = {k: v.to(dev) for k, v in scene.make_rays(cfg, pixels).items()}
+    return dict(campos=rays["campos"], raydir=rays["raydir"], bg_color=rays["bg_color"], camrotc2w=rays["camrotc2w"],
+                pixel_idx=rays["pixel_idx"], near=rays["near"], far=rays["far"], h=rays["h"], w=rays["w"], intrinsic=rays["intrinsic"])
+
+
+def main():
+    name = sys.argv[1] if len(sys.argv) > 1 else "chair_plumbing"
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    cfg = scene.CONFIGS[name]
+    res = {}
+    # ---------------- 1. optimisation
+    for sparse in (False, True):
+        net, _, _ = harness.build_model(cfg, dev, alpha_bias=3.0)
+        ref, _, _ = harness.build_model(cfg, dev, alpha_bias=3.0)
+        ts = parallel.TrainStep(net, world=world, rank=rank, sparse_points=sparse)
+        ts_ref = parallel.TrainStep(ref, world=1, rank=0)
+        rng = np.random.RandomState(0)
+        g = torch.Generator().manual_seed(1)
+        n_rays = 1024
+        for it in range(3):
+            c = cfg.W // 2
+            px = rng.randint(c - 150, c + 150, size=(n_rays,)).astype(np.float32)
+            py = rng.randint(c - 150, c + 150, size=(n_rays,)).astype(np.float32)
+            pix = np.stack([px, py], -1)
+            gt = torch.rand(n_rays, 3, generator=g).to(dev)
+            sel = np.arange(rank, n_rays, world)
+            loss = ts.step(fwd_kwargs(cfg, pix[sel], dev), gt[torch.from_numpy(sel).to(dev)])
+            loss_ref = ts_ref.step(fwd_kwargs(cfg, pix, dev), gt)
+            assert abs(float(loss) - float(loss_ref)) <= 1e-5 * max(abs(float(loss_ref)), 1e-3), (it, float(loss), float(loss_ref))
+        net.check_errors()
+        flat = torch.cat([p.detach().reshape(-1) for p in net.parameters()])
+        alls = [torch.empty_like(flat) for _ in range(world)]
+        dist.all_gather(alls, flat)
+        assert all(torch.equal(alls[0], a) for a in alls), "replicas differ across ranks (sparse=%s)" % sparse
+        flat_ref = torch.cat([p.detach().reshape(-1) for p in ref.parameters()])
+        moved = (flat_ref - torch.cat([p.detach().reshape(-1) for p in harness.build_model(cfg, dev, alpha_bias=3.0)[0].parameters()])).abs().max().item()
+        err = (flat - flat_ref).abs().max().item()
+        assert moved > 1e-3 and err <= 2e-5, "sharded step differs from the un-sharded one: %.3e (parameters moved by %.3e)" % (err, moved)
+        res["train_sparse" if sparse else "train_dense"] = dict(max_abs_diff_vs_unsharded=err, parameters_moved_by=moved, loss=float(loss))
+    # ---------------- 2. render: interleave-sharded frame + all-gather == single-rank frame
+    net, _, _ = harness.build_model(cfg, dev, alpha_bias=3.0)
+    full = scene.make_rays(cfg, scene.centre_patch(cfg, 300))
+    rd = full["raydir"][0]
+    R = rd.shape[0]
+    cam = (list(cfg.campos), torch.eye(3), cfg.near, cfg.far, [1., 1., 1.])
+    with torch.no_grad():
+        whole = net.render_full(cam[0], rd.to(dev), cam[1], cam[2], cam[3], cam[4])["coarse_raycolor"][0].clone()
+        ids = parallel.shard_indices(R, rank, world)
+        part = net.render_full(cam[0], rd[ids].contiguous().to(dev), cam[1], cam[2], cam[3], cam[4])["coarse_raycolor"][0]
+    net.check_errors()
+    got = parallel.gather_interleaved(parallel.pad_rows(part, parallel.padded_shard_len(R, world)), R, world)
+    assert torch.equal(got, whole), "sharded frame differs from the single-rank frame"
+    res["render_sharded_bit_identical"] = True
+    # ---------------- 3. grow: rank-local new points, merged in rank order on every rank
+    gg = torch.Generator().manual_seed(100 + rank)
+    n_new = 5 + 3 * rank
+    add = [0.05 * torch.randn(n_new, 3, generator=gg).to(dev) + torch.tensor([0.0, 0.0, -cfg.R_s], device=dev),
+           0.5 * torch.randn(n_new, 32, generator=gg).to(dev), torch.rand(n_new, 3, generator=gg).to(dev),
+           torch.nn.functional.normalize(torch.randn(n_new, 3, generator=gg), dim=-1).to(dev), torch.rand(n_new, 1, generator=gg).to(dev)]
+    merged = parallel.allgather_new_points(*add, world)
+    n_before = net.neural_points.xyz.shape[0]
+    net.neural_points.grow_points(*merged)
+    assert net.neural_points.xyz.shape[0] == n_before + sum(5 + 3 * r for r in range(world))
+    h = torch.cat([p.detach().reshape(-1) for p in net.neural_points.parameters()])
+    alls = [torch.empty_like(h) for _ in range(world)]
+    dist.all_gather(alls, h)
+    assert all(torch.equal(alls[0], a) for a in alls), "clouds differ after the grow merge"
+    with torch.no_grad():
+        part = net.render_full(cam[0], rd[ids].contiguous().to(dev), cam[1], cam[2], cam[3], cam[4])["coarse_raycolor"][0]
+        whole2 = net.render_full(cam[0], rd.to(dev), cam[1], cam[2], cam[3], cam[4])["coarse_raycolor"][0]
+    net.check_errors()
+    got = parallel.gather_interleaved(parallel.pad_rows(part, parallel.padded_shard_len(R, world)), R, world)
+    assert torch.equal(got, whole2) and not torch.equal(whole2, whole), "render after the grow merge"
+    res["grow_merge_identical"] = True
+    if rank == 0:
+        print(json.dumps(dict(check="dist_train_check", world=world, config=name, **res)))
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -81,3 +81,67 @@ def test_single_process_paths():
     assert parallel.padded_shard_len(7, 3) == 3
     t = torch.rand(4, 5)
     assert parallel.allgather_varlen(t, 1) is t
+
+
+# ---- TrainStep on gloo (world 2) with a small differentiable stand-in for the CUDA network: same output dict
+# (coarse_raycolor over the hit rays, ray_mask, conf_coefficient), parameters under .aggregator / .neural_points
+class _StubPoints(torch.nn.Module):
+    def __init__(self, n):
+        super().__init__()
+        g = torch.Generator().manual_seed(3)
+        self.points_embeding = torch.nn.Parameter(torch.rand(1, n, 4, generator=g))
+        self.points_conf = torch.nn.Parameter(0.2 + 0.6 * torch.rand(1, n, 1, generator=g))
+
+
+class _StubNet(torch.nn.Module):
+    def __init__(self, n=40):
+        super().__init__()
+        torch.manual_seed(5)
+        self.aggregator = torch.nn.Linear(4, 3)
+        self.neural_points = _StubPoints(n)
+
+    def forward(self, ray_ids=None):
+        n = self.neural_points.points_embeding.shape[1]
+        hit = (ray_ids % 3) != 0                                   # a ray "hits" unless its id is a multiple of 3
+        ids = ray_ids[hit]
+        nb = torch.stack([ids % n, (ids * 7 + 1) % n], dim=1)      # two "neighbour points" per hit ray (rows shared between rays)
+        feat = self.neural_points.points_embeding[0][nb].sum(1)
+        col = torch.sigmoid(self.aggregator(feat))
+        return dict(coarse_raycolor=col[None], ray_mask=hit[None].to(torch.int8),
+                    conf_coefficient=self.neural_points.points_conf[0][nb][None, :, None, :, 0])
+
+
+def _train_worker(rank, world, port, sparse, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        R = 31
+        g = torch.Generator().manual_seed(11)
+        gt = torch.rand(R, 3, generator=g)
+        net = _StubNet().double()
+        ts = parallel.TrainStep(net, world=world, rank=rank, sparse_points=sparse)
+        ref_net = _StubNet().double()
+        ref = parallel.TrainStep(ref_net, world=1, rank=0)
+        for it in range(3):
+            ids_all = (torch.arange(R) * 5 + it) % 97              # the step's rays
+            mine = parallel.shard_indices(R, rank, world)
+            loss = ts.step(dict(ray_ids=ids_all[mine]), gt[mine])
+            loss_ref = ref.step(dict(ray_ids=ids_all), gt)        # every rank also runs the un-sharded step on the union of the rays
+            assert torch.allclose(loss, loss_ref, rtol=1e-12, atol=1e-12), (float(loss), float(loss_ref))
+        same = all(torch.allclose(a, b, rtol=1e-10, atol=1e-12) for a, b in zip(net.parameters(), ref_net.parameters()))
+        flat = torch.cat([p.detach().reshape(-1) for p in net.parameters()])
+        others = [torch.empty_like(flat) for _ in range(world)]
+        dist.all_gather(others, flat)
+        ident = all(torch.equal(others[0], o) for o in others)     # replicas bit-identical
+        ret[rank] = (same, ident)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_world2_gloo_train_step_matches_unsharded_and_replicas_identical():
+    for sparse in (False, True):
+        mgr = mp.Manager()
+        ret = mgr.dict()
+        mp.spawn(_train_worker, args=(2, _free_port(), sparse, ret), nprocs=2, join=True)
+        assert dict(ret) == {0: (True, True), 1: (True, True)}, (sparse, dict(ret))

@@ -75,6 +75,14 @@ def test_forward_matches_reference_fixture(name, golden_dir, precision):
         d = np.abs(out[k][0].cpu().numpy() - fx[k]).max()
         assert d <= TOL, "%s max abs diff %.3e" % (k, d)
     assert out["queried_shading"].shape == (1, fx["sample_pidx"].shape[0], 3)
+    # exactly the keys (and trailing shapes) the reference module returns in evaluation mode (tests/golden/output_keys.json,
+    # generated from the reference's own forward by oracle/make_golden.py)
+    import json
+    want = json.load(open(os.path.join(golden_dir, "output_keys.json")))["eval"]
+    assert sorted(out.keys()) == sorted(want.keys())
+    for k, tail in want.items():
+        exp = [int(fx["SR"]) if (d == 24 and k != "coarse_raycolor") else d for d in tail]
+        assert list(out[k].shape[2:]) == exp, (k, list(out[k].shape), exp)
 
 
 @pytest.mark.parametrize("precision", PRECISIONS)
@@ -275,6 +283,8 @@ def test_probe_outputs_match_reference_fixture(golden_dir):
                   near=r["near"], far=r["far"], h=r["h"], w=r["w"], intrinsic=r["intrinsic"])
     # rays whose arg-max opacity is (numerically) tied between two samples may pick the other sample: compare where
     # the selected sample location agrees, and require that to be (almost) everywhere
+    import json
+    assert sorted(out.keys()) == sorted(json.load(open(os.path.join(golden_dir, "output_keys.json")))["probe"].keys())
     loc = out["ray_max_sample_loc_w"][0].cpu().numpy()
     same = np.abs(loc - fx["ray_max_sample_loc_w"]).max(-1) == 0
     assert same.mean() > 0.98

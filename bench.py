@@ -15,6 +15,8 @@ N>1 is launched by torchrun (one rank per GPU, NCCL).  The JSON line of every N 
   truck                BASELINE configs[3]: N=2M points, 960x540, kernel_size 5, one frame interleave-sharded over the N ranks;
   train                BASELINE configs[2] (N=1..8) per-scene optimisation step: 3600 rays per step split over the ranks,
                        forward + backward + gradient all-reduce + 2x Adam (parallel.TrainStep);
+  scannet              BASELINE configs[4]: N=5M points (P=30), the same step with the sparse touched-rows gradient exchange, plus one
+                       prune + probe + grow cycle (variable-length all-gather of the new points);
   cold, sr80           (N=1) first frame of a new point cloud (voxel grid + per-point table built inside the timed region); SR=80.
 
 `--impl reference` times the reference's own CPU path (the oracle port: oracle/query_oracle.c + oracle/shade_oracle.py, i.e. the
@@ -344,13 +346,13 @@ def main():
     ap.add_argument("--impl", type=str, default="pnb200")
     ap.add_argument("--sr", type=int, default=24)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--only", type=str, default="", help="comma list of sub-results to run besides the main line: strong,truck,train,cold,sr80 (default: all)")
+    ap.add_argument("--only", type=str, default="", help="comma list of sub-results to run besides the main line: strong,truck,train,scannet,cold,sr80 (default: all)")
     ap.add_argument("--precision", type=str, default="bf16x3", help="bf16x3 (tcgen05, default) | fp32 (CUDA cores)")
     ap.add_argument("--frozen", type=int, default=1, help="1 (default): frozen-cloud pair kernel k_shade_tc8 (point-only layer-1 inputs hoisted per point) | 0: general kernel k_shade_tc7")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
-    want = set(x for x in args.only.split(",") if x) or {"strong", "truck", "train", "cold", "sr80"}
+    want = set(x for x in args.only.split(",") if x) or {"strong", "truck", "train", "scannet", "cold", "sr80"}
 
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
@@ -503,6 +505,9 @@ def main():
     # ---------------- config 3: per-scene optimisation step (3600 rays per step over the ranks)
     if "train" in want:
         sub["train"] = train_section(D, args, dev)
+    # ---------------- config 5: ScanNet-sized cloud (5M points, P=30): optimisation step with the sparse exchange + one prune/grow cycle
+    if "scannet" in want:
+        sub["scannet"] = train_section(D, args, dev, cfg_name="scannet_8gpu", sparse=True, n_steps=10, grow_cycle=True)
 
     if rank == 0:
         cpu = None
@@ -545,20 +550,23 @@ def main():
     return 0
 
 
-def train_section(D, args, dev):
-    """BASELINE configs[2]: N=600k, 3600 random rays of one 800x800 view per step (run/train_ft.py, lego_cuda.sh:109), train jitter
-    on, forward + backward + gradient exchange + 2x Adam.  The step's rays are split over the ranks (ray i -> rank i % world)."""
+def train_section(D, args, dev, cfg_name="ship_optimise", sparse=False, n_steps=20, grow_cycle=False):
+    """Per-scene optimisation step (run/train_ft.py): 3600 random rays of one view per step (lego_cuda.sh:109), train jitter on,
+    forward + backward + gradient exchange + 2x Adam (parallel.TrainStep).  The step's rays are split over the ranks
+    (ray i -> rank i % world).  cfg_name: ship_optimise = BASELINE configs[2] (N=600k); scannet_8gpu = configs[4] (N=5M, P=30,
+    sparse touched-rows exchange of the point gradients, plus one prune + probe + grow cycle when grow_cycle)."""
     from pointnerf_b200 import parallel
-    cfg = scene.CONFIGS["ship_optimise"]
+    cfg = scene.CONFIGS[cfg_name]
     net, pts, opt = harness.build_model(cfg, dev, alpha_bias=3.0, is_train=True, pnb_precision=args.precision)
-    ts = parallel.TrainStep(net, world=D.world, rank=D.rank)
+    ts = parallel.TrainStep(net, world=D.world, rank=D.rank, sparse_points=sparse)
     rng = np.random.RandomState(0)
     g = torch.Generator().manual_seed(1)
-    n_steps, n_warm = 20, 4
+    n_warm = 4
     acc = dict(forward=0.0, backward=0.0, exchange=0.0, adam=0.0)
     tot = 0.0
     hit = 0
-    for it in range(n_warm + n_steps):
+
+    def batch():
         px = rng.randint(0, cfg.W, size=(3600,)).astype(np.float32)
         py = rng.randint(0, cfg.H, size=(3600,)).astype(np.float32)
         gt = torch.rand(3600, 3, generator=g)
@@ -566,13 +574,17 @@ def train_section(D, args, dev):
         rays = {k: v.to(dev) for k, v in scene.make_rays(cfg, np.stack([px, py], -1)[sel]).items()}
         kw = dict(campos=rays["campos"], raydir=rays["raydir"], bg_color=rays["bg_color"], camrotc2w=rays["camrotc2w"], pixel_idx=rays["pixel_idx"],
                   near=rays["near"], far=rays["far"], h=rays["h"], w=rays["w"], intrinsic=rays["intrinsic"])
+        return kw, gt[sel].to(dev)
+
+    for it in range(n_warm + n_steps):
+        kw, gt = batch()
         evs = []
 
         def mark(name):
             e = torch.cuda.Event(enable_timing=True)
             e.record()
             evs.append((name, e))
-        ts.step(kw, gt[sel].to(dev), mark=mark)
+        ts.step(kw, gt, mark=mark)
         torch.cuda.synchronize(dev)
         if it >= n_warm:
             for (n0, a), (n1, b) in zip(evs[:-1], evs[1:]):
@@ -580,13 +592,52 @@ def train_section(D, args, dev):
             tot += evs[0][1].elapsed_time(evs[-1][1])
             hit += int(ts.last["n_hit_terms"] / 3)
     ms = D.max_over_ranks(tot / n_steps)
+    out = dict(steps_per_s=1e3 / ms, ms_per_step=ms, ms_fwd=acc["forward"] / n_steps, ms_bwd=acc["backward"] / n_steps,
+               ms_exchange=acc["exchange"] / n_steps, ms_adam=acc["adam"] / n_steps, mrays_per_s=3600 / ms / 1e3,
+               hit_rays_per_step=hit / n_steps,
+               what="%s: N=%d, 3600 rays per step over %d rank(s), fwd (tcgen05) + bwd (tcgen05 GEMMs) + %s + 2x Adam over all N rows; "
+                    "per-phase ms are rank 0's, ms_per_step the max over ranks"
+                    % (cfg_name, cfg.N, D.world, "sparse touched-rows exchange of the point gradients + flat all-reduce of the MLP gradients" if sparse
+                       else "one flat gradient all-reduce"))
+    if grow_cycle:
+        # prune (deterministic function of the replicated points_conf, neural_points.py:347-370: no communication), then a probe pass
+        # (opt.prob = 1 outputs, run/train_ft.py:417-530) on this rank's share of one frame's rays, new points = the arg-max-opacity
+        # sample locations with their averaged attributes, merged across ranks (allgather_new_points), grow, optimisers rebuilt,
+        # and one more step on the new cloud (voxel grid rebuilt inside it)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize(dev)
+        t_host = time.perf_counter()
+        e0.record()
+        n0 = net.neural_points.xyz.shape[0]
+        pruned = net.neural_points.prune(0.12)
+        opt.prob = 1
+        opt.is_train = False
+        kw, _ = batch()
+        with torch.no_grad():
+            pr = net(**kw)
+        opt.prob = 0
+        opt.is_train = True
+        keep = pr["ray_max_shading_opacity"][0, :, 0] > 0.5 if pr["ray_max_shading_opacity"].numel() else torch.zeros(0, dtype=torch.bool, device=dev)
+        keep = keep & (torch.arange(keep.shape[0], device=dev) % 4 == 0)
+        add = [pr["ray_max_sample_loc_w"][0][keep], pr["shading_avg_embedding"][0][keep], pr["shading_avg_color"][0][keep],
+               pr["shading_avg_dir"][0][keep], pr["shading_avg_conf"][0][keep]] if keep.numel() else None
+        if add is None:
+            z = lambda c: torch.zeros((0, c), device=dev)
+            add = [z(3), z(32), z(3), z(3), z(1)]
+        merged = parallel.allgather_new_points(*add, D.world)
+        net.neural_points.grow_points(*merged)
+        ts = parallel.TrainStep(net, world=D.world, rank=D.rank, sparse_points=sparse)     # new parameters -> new optimisers (train_ft.py:834-842)
+        kw, gt = batch()
+        ts.step(kw, gt)
+        e1.record()
+        torch.cuda.synchronize(dev)
+        out["grow_cycle"] = dict(ms=D.max_over_ranks(e0.elapsed_time(e1)), host_ms=(time.perf_counter() - t_host) * 1e3, points_before=n0,
+                                 pruned=int(pruned), grown=int(merged[0].shape[0]), points_after=int(net.neural_points.xyz.shape[0]),
+                                 what="prune(conf < 0.12) + probe pass (opt.prob = 1) + variable-length all-gather of the new points + grow + "
+                                      "optimiser rebuild + one optimisation step on the new cloud (voxel grid rebuilt)")
     del net, ts
     torch.cuda.empty_cache()
-    return dict(steps_per_s=1e3 / ms, ms_per_step=ms, ms_fwd=acc["forward"] / n_steps, ms_bwd=acc["backward"] / n_steps,
-                ms_exchange=acc["exchange"] / n_steps, ms_adam=acc["adam"] / n_steps, mrays_per_s=3600 / ms / 1e3,
-                hit_rays_per_step=hit / n_steps,
-                what="ship_optimise (BASELINE configs[2]): N=600000, 3600 rays per step over %d rank(s), fwd (tcgen05) + bwd (tcgen05 GEMMs) + "
-                     "dense gradient all-reduce + 2x Adam over all N rows; per-phase ms are rank 0's, ms_per_step the max over ranks" % D.world)
+    return out
 
 
 _RETRY_NOTE = None

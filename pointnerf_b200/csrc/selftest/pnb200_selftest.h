@@ -22,6 +22,12 @@ int pnb_umma_bench(int layout, int mode, int iters, int bulk, const void* d_src,
  * bench_flags: bits 0-7 interleave a tcgen05.commit every n MMAs, bits 8-9 its form (see umma_selftest.cu). */
 int pnb_umma_selftest2(const float* d_A, const float* d_W, float* d_D, int K, int N, int mode, int bench_iters,
                        int bench_flags, long long* d_out, int* d_err, pnb_stream_t stream);
+/* The tcgen05 GEMM engine of the backward pass (csrc/gemm_tc.cu): C[M,N] = op(A B^T + bias), A(m,k) = A[m*a_rs + k*a_ks],
+ * B(n,k) = B[n*b_rs + k*b_ks]; dact / dact_n: multiply by LeakyReLU'(dact) for n < dact_n; splits > 1: split-K through `part`
+ * (>= splits*M*N floats), accumulate != 0 adds to C. */
+int pnb_gemm_tc_test(const float* A, long a_rs, long a_ks, const float* B, long b_rs, long b_ks, float* C, long ldc, int M, int N, int K,
+                     const float* bias, int act, const float* dact, long ldd, int dact_n, int splits, float* part, size_t part_bytes,
+                     int accumulate, int* d_err, pnb_stream_t stream);
 #ifdef __cplusplus
 }
 #endif

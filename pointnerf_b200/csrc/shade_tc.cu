@@ -706,14 +706,13 @@ __global__ void __launch_bounds__(tc7::NTHR, 1) k_shade_tc7(ShadeTcParams p) {
 // Pipeline otherwise as v7 (TMEM role ping-pong P/Q, chunk-granular hand-off, packed rows, shared last epilogue).
 // Warps (448 threads): 0-7 epilogue (quadrant = w & 3, chunk group = w >> 2), 8-11 builders (thread = row), 12 loader, 13 issuer.
 namespace tc8 {
-constexpr int NEPI_WARPS = 8, NGRP = 2, NCH = 8;
-constexpr int NEPI = NEPI_WARPS * 32, NBUILD = 128, NTHR = NEPI + NBUILD + 64;
+constexpr int NBUILD = 128;
+__host__ __device__ constexpr int nthr(int ngrp) { return ngrp * 128 + NBUILD + 64; }
 constexpr int NSTAGE = 5;                 // ring stage = one K block: hi image + lo image
 constexpr int STAGE = 2 * tc::IMG;
 constexpr int NKB1 = 2;                   // K blocks of the frozen layer 1 (operand columns 224..287 of block1.0)
 constexpr int KB1_FIRST = 7;
 constexpr int STAGES_PER_TILE = NKB1 + 8 + 9 + 8;
-constexpr int PF = 3;                     // chunks of `pre` in flight per epilogue thread
 struct Smem {
     static constexpr int NWC = 2;
     unsigned char a_hi[NKB1 * tc::ABLK];
@@ -722,7 +721,7 @@ struct Smem {
     unsigned char xe_hi[2][tc::XE];
     unsigned char xe_lo[2][tc::XE];
     float wc[NWC][tc::TM];
-    float alpha_e[tc::TM];
+    float alpha_part[4][tc::TM];          // partial alpha dot products of the epilogue groups (own slot each: summed in a fixed order)
     int prow[2][tc::TM];                  // point index of every row (-1: unused row)
     uint32_t qhead[NWC][4], qfirst[NWC][4], qtotal[NWC][4];
     uint64_t bar_full[NSTAGE], bar_empty[NSTAGE], bar_a1_ready, bar_a1_free, bar_acc_full, bar_final, bar_alpha, bar_drain, bar_kblk[8], bar_prow[2];
@@ -831,7 +830,64 @@ __device__ __forceinline__ void build_pair_frozen(tc8::Smem& sm, const ShadeTcPa
     *reinterpret_cast<uint4*>(sm.xe_lo[t & 1] + off + 128) = make_uint4(0u, 0u, 0u, 0u);
 }
 
-__global__ void __launch_bounds__(tc8::NTHR, 1) k_shade_tc8(ShadeTcParams p) {
+// One epilogue layer of a warp: chunks grp, grp+NGRP, ... (16 accumulator columns each): accumulator -> (+ bias or + pre[point]) ->
+// LeakyReLU -> bf16 hi/lo -> the same columns, one mbarrier arrive per chunk.  SWP: software-pipelined - the tcgen05.ld of the next
+// chunk is in flight under the conversion of this one, and the wait for this chunk's tcgen05.st is deferred behind the next conversion.
+template <int NGRP, bool SWP, bool FIRST>
+__device__ __forceinline__ void tc8_epi_layer(tc8::Smem& sm, uint32_t accb, int grp, const float* __restrict__ bias, const float4* __restrict__ pp) {
+    using namespace tc;
+    constexpr int NCH = 16 / NGRP;
+    constexpr int PF = NCH < 3 ? NCH : 3;         // chunks of `pre` in flight (FIRST)
+    float4 pf[PF][4];
+    if (FIRST) {
+#pragma unroll
+        for (int i = 0; i < PF; ++i)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) pf[i][e] = __ldg(pp + 4 * (grp + NGRP * i) + e);
+    }
+    uint32_t v[2][16];
+    if (SWP) tmem_ld16(accb + (uint32_t)(16 * grp), v[0]);
+#pragma unroll
+    for (int i = 0; i < NCH; ++i) {
+        const int g = grp + NGRP * i, c0 = 16 * g;
+        uint32_t* vi = v[SWP ? (i & 1) : 0];
+        if (!SWP) tmem_ld16(accb + (uint32_t)c0, vi);
+        tmem_ld_wait();
+        if (SWP && i + 1 < NCH) tmem_ld16(accb + (uint32_t)(c0 + 16 * NGRP), v[(i + 1) & 1]);
+        uint32_t hh[8], ll[8];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            float4 b4;
+            if (FIRST) b4 = pf[i % PF][e];
+            else b4 = __ldg(reinterpret_cast<const float4*>(bias + c0) + e);
+            float y0 = __uint_as_float(vi[4 * e]) + b4.x, y1 = __uint_as_float(vi[4 * e + 1]) + b4.y;
+            float y2 = __uint_as_float(vi[4 * e + 2]) + b4.z, y3 = __uint_as_float(vi[4 * e + 3]) + b4.w;
+            y0 = fmaxf(y0, LEAKY * y0); y1 = fmaxf(y1, LEAKY * y1); y2 = fmaxf(y2, LEAKY * y2); y3 = fmaxf(y3, LEAKY * y3);
+            split_bf16x2(y0, y1, hh[2 * e], ll[2 * e]);
+            split_bf16x2(y2, y3, hh[2 * e + 1], ll[2 * e + 1]);
+        }
+        if (FIRST && i + PF < NCH) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) pf[i % PF][e] = __ldg(pp + 4 * (grp + NGRP * (i + PF)) + e);
+        }
+        if (SWP && i > 0) {                        // the previous chunk's stores have had a whole conversion to land
+            tmem_st_wait();
+            tc_fence_before();
+            mbar_arrive(&sm.bar_kblk[(g - NGRP) >> 1]);
+        }
+        tmem_st8(accb + (uint32_t)c0, hh);
+        tmem_st8(accb + (uint32_t)c0 + 8u, ll);
+        if (!SWP || i == NCH - 1) {
+            tmem_st_wait();
+            tc_fence_before();
+            mbar_arrive(&sm.bar_kblk[g >> 1]);
+        }
+    }
+}
+
+// NGRP: epilogue warps per TMEM lane quarter (2 or 4 -> 8 or 16 epilogue warps); SWP: software-pipelined epilogue chunks.
+template <int NGRP, bool SWP>
+__global__ void __launch_bounds__(tc8::nthr(NGRP), 1) k_shade_tc8(ShadeTcParams p) {
     using namespace tc;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     tc8::Smem& sm = *reinterpret_cast<tc8::Smem*>(smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u));
@@ -841,7 +897,11 @@ __global__ void __launch_bounds__(tc8::NTHR, 1) k_shade_tc8(ShadeTcParams p) {
     const int n_quads = p.pack_cnt[0];
     const int n_tiles = (n_quads + 3) >> 2;
     const int my_tiles = n_tiles > (int)blockIdx.x ? (n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
-    constexpr int W_BUILD = tc8::NEPI_WARPS, W_LOAD = W_BUILD + tc8::NBUILD / 32, W_ISSUE = W_LOAD + 1;
+    constexpr int NEPI_WARPS = 4 * NGRP;
+    constexpr int W_BUILD = NEPI_WARPS, W_LOAD = W_BUILD + tc8::NBUILD / 32, W_ISSUE = W_LOAD + 1;
+    // last epilogue: 16 chunks over the NGRP epilogue warps + 1 builder warp of a quadrant; the builder warp takes group 0
+    constexpr int NG4 = NGRP + 1, NCH4_B = (16 + NG4 - 1) / NG4, NCH4_E = 16 / NG4;
+    static_assert(NCH4_B + NGRP * NCH4_E == 16, "last-epilogue chunk split");
 
     if (tid == 0) {
         for (int s = 0; s < tc8::NSTAGE; ++s) { mbar_init(&sm.bar_full[s], 1); mbar_init(&sm.bar_empty[s], 1); }
@@ -849,15 +909,14 @@ __global__ void __launch_bounds__(tc8::NTHR, 1) k_shade_tc8(ShadeTcParams p) {
         mbar_init(&sm.bar_a1_free, 1);
         mbar_init(&sm.bar_acc_full, 1);
         mbar_init(&sm.bar_final, 1);
-        mbar_init(&sm.bar_alpha, tc8::NEPI_WARPS);
-        mbar_init(&sm.bar_drain, tc8::NEPI_WARPS + tc8::NBUILD / 32);     // one arrive per warp that reads the layer-4 accumulator
+        mbar_init(&sm.bar_alpha, NEPI_WARPS);
+        mbar_init(&sm.bar_drain, NEPI_WARPS + tc8::NBUILD / 32);     // one arrive per warp that reads the layer-4 accumulator
         for (int c = 0; c < 8; ++c) mbar_init(&sm.bar_kblk[c], 32 * 4 * 2);
         mbar_init(&sm.bar_prow[0], tc8::NBUILD / 32);
         mbar_init(&sm.bar_prow[1], tc8::NBUILD / 32);
         mbar_fence_init();
         if (blockIdx.x == 0 && q.counters[PNB_QC_N_VALID] > p.hbar_cap) atomicExch(p.err, 9);
     }
-    if (tid < TM) sm.alpha_e[tid] = 0.f;
     if (warp == W_ISSUE) tmem_alloc<512>(&sm.tmem_base);
     tc_fence_before();
     __syncthreads();
@@ -982,16 +1041,18 @@ __global__ void __launch_bounds__(tc8::NTHR, 1) k_shade_tc8(ShadeTcParams p) {
                 const int sidx = qr.live ? (int)p.vorder[sm.qfirst[tf & 1][qw] + qr.j] : 0;
                 const bool swrite = qr.is_end && sidx < n_valid;
                 const float wrow = sm.wc[tf & 1][row];
-                const float apart = last_chunks_packed<3, 6>(p, tP + tlane, 0, wrow, qr.st, swrite, sidx, lane);
+                const float apart = last_chunks_packed<NG4, NCH4_B>(p, tP + tlane, 0, wrow, qr.st, swrite, sidx, lane);
                 tc_fence_before();
                 if (!mbar_wait(&sm.bar_alpha, (uint32_t)tf & 1u, p.err, 100)) { ok = false; break; }      // the epilogue warps' partial sums
-                const float a = apart + sm.alpha_e[row] + __ldg(p.ba) - 1.0f;
-                sm.alpha_e[row] = 0.f;
+                float a = apart;
+#pragma unroll
+                for (int gq = 0; gq < NGRP; ++gq) a += sm.alpha_part[gq][row];          // fixed order: deterministic
+                a += __ldg(p.ba) - 1.0f;
                 const float sp = a > 20.f ? a : log1pf(expf(a));
                 const float zz = seg_scan8(sp * wrow, lane, qr.st);
                 if (swrite) p.sigma[sidx] = zz;
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&sm.bar_drain);                 // after the alpha_e reads
+                if (lane == 0) mbar_arrive(&sm.bar_drain);                 // after the alpha_part reads
             }
         }
     } else {
@@ -1002,84 +1063,29 @@ __global__ void __launch_bounds__(tc8::NTHR, 1) k_shade_tc8(ShadeTcParams p) {
         uint32_t n_acc = 0;
         bool ok = true;
         for (int t = 0; t < my_tiles && ok; ++t) {
-            // ---- layer 1: accumulator + pre[point of this row] (the hoisted 224 inputs and the bias), prefetched PF chunks ahead
+            // ---- layer 1: accumulator + pre[point of this row] (the hoisted 224 inputs and the bias)
             if (!mbar_wait(&sm.bar_prow[t & 1], (uint32_t)(t >> 1) & 1u, p.err, 102)) { ok = false; break; }
             const int pi = max(sm.prow[t & 1][erow], 0);          // unused rows: any finite values (their outputs are never used)
             const float4* pp = reinterpret_cast<const float4*>(p.pre + (size_t)pi * 256);
-            float4 pf[tc8::PF][4];
-#pragma unroll
-            for (int i = 0; i < tc8::PF; ++i) {
-#pragma unroll
-                for (int e = 0; e < 4; ++e) pf[i][e] = __ldg(pp + 4 * (grp + tc8::NGRP * i) + e);
-            }
             if (!mbar_wait(&sm.bar_acc_full, n_acc & 1u, p.err, 98)) { ok = false; break; }
             ++n_acc;
             tc_fence_after();
-            {
-                const uint32_t accb = tQ + tlane;
-#pragma unroll
-                for (int i = 0; i < tc8::NCH; ++i) {
-                    const int g = grp + tc8::NGRP * i, c0 = 16 * g;
-                    uint32_t v[16];
-                    tmem_ld16(accb + (uint32_t)c0, v);
-                    tmem_ld_wait();
-                    uint32_t hh[8], ll[8];
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        const float4 b4 = pf[i % tc8::PF][e];
-                        float y0 = __uint_as_float(v[4 * e]) + b4.x, y1 = __uint_as_float(v[4 * e + 1]) + b4.y;
-                        float y2 = __uint_as_float(v[4 * e + 2]) + b4.z, y3 = __uint_as_float(v[4 * e + 3]) + b4.w;
-                        y0 = fmaxf(y0, LEAKY * y0); y1 = fmaxf(y1, LEAKY * y1); y2 = fmaxf(y2, LEAKY * y2); y3 = fmaxf(y3, LEAKY * y3);
-                        split_bf16x2(y0, y1, hh[2 * e], ll[2 * e]);
-                        split_bf16x2(y2, y3, hh[2 * e + 1], ll[2 * e + 1]);
-                    }
-                    if (i + tc8::PF < tc8::NCH) {
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) pf[i % tc8::PF][e] = __ldg(pp + 4 * (grp + tc8::NGRP * (i + tc8::PF)) + e);
-                    }
-                    tmem_st8(accb + (uint32_t)c0, hh);
-                    tmem_st8(accb + (uint32_t)c0 + 8u, ll);
-                    tmem_st_wait();
-                    tc_fence_before();
-                    mbar_arrive(&sm.bar_kblk[g >> 1]);
-                }
-            }
+            tc8_epi_layer<NGRP, SWP, true>(sm, tQ + tlane, grp, nullptr, pp);
             // ---- layers 2, 3
             for (int l = 1; l < 3 && ok; ++l, ++n_acc) {
                 if (!mbar_wait(&sm.bar_acc_full, n_acc & 1u, p.err, 98)) { ok = false; break; }
                 tc_fence_after();
-                const uint32_t accb = ((l & 1) ? tP : tQ) + tlane;
-                const float* bias = p.bias[l];
-#pragma unroll
-                for (int i = 0; i < tc8::NCH; ++i) {
-                    const int g = grp + tc8::NGRP * i, c0 = 16 * g;
-                    uint32_t v[16];
-                    tmem_ld16(accb + (uint32_t)c0, v);
-                    tmem_ld_wait();
-                    uint32_t hh[8], ll[8];
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) {
-                        const float2 bb = __ldg(reinterpret_cast<const float2*>(bias + c0) + e);
-                        float y0 = __uint_as_float(v[2 * e]) + bb.x, y1 = __uint_as_float(v[2 * e + 1]) + bb.y;
-                        y0 = fmaxf(y0, LEAKY * y0); y1 = fmaxf(y1, LEAKY * y1);
-                        split_bf16x2(y0, y1, hh[e], ll[e]);
-                    }
-                    tmem_st8(accb + (uint32_t)c0, hh);
-                    tmem_st8(accb + (uint32_t)c0 + 8u, ll);
-                    tmem_st_wait();
-                    tc_fence_before();
-                    mbar_arrive(&sm.bar_kblk[g >> 1]);
-                }
+                tc8_epi_layer<NGRP, SWP, false>(sm, ((l & 1) ? tP : tQ) + tlane, grp, p.bias[l], nullptr);
             }
             if (!ok) break;
-            {   // this warp's share of the LAST epilogue (chunk groups 1, 2 of 3; the builder warps take group 0)
+            {   // this warp's share of the LAST epilogue (chunk groups 1..NGRP of NGRP+1; the builder warps take group 0)
                 if (!mbar_wait(&sm.bar_final, (uint32_t)t & 1u, p.err, 101)) { ok = false; break; }
                 tc_fence_after();
                 const QuadRow qr = quad_row(sm.qhead[t & 1][quad], (int)sm.qtotal[t & 1][quad], lane);
                 const int sidx = qr.live ? (int)p.vorder[sm.qfirst[t & 1][quad] + qr.j] : 0;
-                const float apart = last_chunks_packed<3, 5>(p, tP + tlane, 1 + grp, sm.wc[t & 1][erow], qr.st, qr.is_end && sidx < n_valid, sidx, lane);
+                const float apart = last_chunks_packed<NG4, NCH4_E>(p, tP + tlane, 1 + grp, sm.wc[t & 1][erow], qr.st, qr.is_end && sidx < n_valid, sidx, lane);
                 tc_fence_before();
-                atomicAdd(&sm.alpha_e[erow], apart);
+                sm.alpha_part[grp][erow] = apart;
                 __syncwarp();
                 if (lane == 0) { mbar_arrive(&sm.bar_alpha); mbar_arrive(&sm.bar_drain); }
             }
@@ -1484,7 +1490,10 @@ extern "C" int pnb_shade_forward_tc(const pnb_query_t* q, const pnb_points_t* pt
     static_assert(tc7::NSTAGE == 4, "the v7 issuer assumes a 4-stage ring");
     if (!configured[dev]) {
         PNB_CHECK_CUDA(cudaFuncSetAttribute(k_shade_tc7, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tc7));
-        PNB_CHECK_CUDA(cudaFuncSetAttribute(k_shade_tc8, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tc8));
+        PNB_CHECK_CUDA(cudaFuncSetAttribute(k_shade_tc8<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tc8));
+        PNB_CHECK_CUDA(cudaFuncSetAttribute(k_shade_tc8<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tc8));
+        PNB_CHECK_CUDA(cudaFuncSetAttribute(k_shade_tc8<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tc8));
+        PNB_CHECK_CUDA(cudaFuncSetAttribute(k_shade_tc8<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tc8));
         PNB_CHECK_CUDA(cudaFuncSetAttribute(k_color_tc2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_ctc2));
         PNB_CHECK_CUDA(cudaDeviceGetAttribute(&n_sm_of[dev], cudaDevAttrMultiProcessorCount, dev));
         configured[dev] = 1;
@@ -1507,7 +1516,14 @@ extern "C" int pnb_shade_forward_tc(const pnb_query_t* q, const pnb_points_t* pt
         k_pack_quads<<<(n_sc + 7) / 8, 256, 0, stream>>>(p.q, cap, w.sc_quads, w.quad_local, w.vorder, w.vcntp, (float4*)d_sigma_rgb);
         k_pack_scan<<<1, 1024, 0, stream>>>(p.q, cap, w.sc_quads, w.quad_first, w.pack_cnt);
         k_pack_place<<<(cap + 255) / 256, 256, 0, stream>>>(p.q, cap, w.sc_quads, w.quad_local, w.quad_first);
-        if (frozen) k_shade_tc8<<<n_sm, tc8::NTHR, smem_tc8, stream>>>(p);
+        if (frozen) {
+            // experiment flags (tools/tc_profile.py): dbg bit 3 = 8 epilogue warps instead of 16, dbg bit 4 = no software pipelining
+            const bool e8 = (p.dbg_flags & 8) != 0, noswp = (p.dbg_flags & 16) != 0;
+            if (e8 && noswp) k_shade_tc8<2, false><<<n_sm, tc8::nthr(2), smem_tc8, stream>>>(p);
+            else if (e8) k_shade_tc8<2, true><<<n_sm, tc8::nthr(2), smem_tc8, stream>>>(p);
+            else if (noswp) k_shade_tc8<4, false><<<n_sm, tc8::nthr(4), smem_tc8, stream>>>(p);
+            else k_shade_tc8<4, true><<<n_sm, tc8::nthr(4), smem_tc8, stream>>>(p);
+        }
         else k_shade_tc7<<<n_sm, tc7::NTHR, smem_tc7, stream>>>(p);
     }
     if (flags & PNB_TC_COLOR) {

@@ -61,7 +61,7 @@ SYMBOLS = ["pnb_version", "pnb_last_error", "pnb_struct_size", "pnb_grid_bytes",
            "pnb_shade_tc_tables", "pnb_backward_bytes", "pnb_shade_backward"]
 # test-only library (csrc/selftest/pnb200_selftest.h)
 SELFTEST_LIB_PATH = os.path.join(_HERE, "csrc", "libpnb200_selftest.so")
-SELFTEST_SYMBOLS = ["pnb_selftest_last_error", "pnb_umma_selftest", "pnb_umma_bench", "pnb_umma_selftest2"]
+SELFTEST_SYMBOLS = ["pnb_selftest_last_error", "pnb_umma_selftest", "pnb_umma_bench", "pnb_umma_selftest2", "pnb_gemm_tc_test"]
 # flags of pnb_shade_forward_tc
 TC_PAIRS, TC_COLOR, TC_FROZEN, TC_DBG_NO_WEIGHTS = 1, 2, 4, 64
 BWD_FP32_GEMM = 1   # flag of pnb_shade_backward
@@ -153,6 +153,9 @@ def load_selftest():
                                        C.c_void_p, C.c_void_p]
     lib.pnb_umma_selftest.restype = C.c_int
     lib.pnb_umma_selftest.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    lib.pnb_gemm_tc_test.restype = C.c_int
+    lib.pnb_gemm_tc_test.argtypes = [C.c_void_p, C.c_long, C.c_long, C.c_void_p, C.c_long, C.c_long, C.c_void_p, C.c_long, C.c_int, C.c_int, C.c_int,
+                                     C.c_void_p, C.c_int, C.c_void_p, C.c_long, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, C.c_void_p]
     _selftest = lib
     return lib
 

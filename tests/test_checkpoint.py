@@ -59,3 +59,26 @@ def test_loader_accepts_dataparallel_prefix_and_rejects_bad_files(tmp_path):
     bad = dict(good); bad["neural_points.eulers"] = torch.zeros(3)
     with pytest.raises(NotImplementedError):
         checkpoint.load_checkpoint(bad, opt, "cpu")
+
+
+def test_rw2c_round_trip(tmp_path):
+    """A non-identity Rw2c is part of the reference state dict (neural_points.py:463-467: nn.Parameter): load -> save -> load keeps it."""
+    cfg, net, pts, opt = _net()
+    a = 0.3
+    R = torch.tensor([[1.0, 0.0, 0.0], [0.0, float(torch.cos(torch.tensor(a))), -float(torch.sin(torch.tensor(a)))],
+                      [0.0, float(torch.sin(torch.tensor(a))), float(torch.cos(torch.tensor(a)))]])
+    sd = {k: v.detach().clone() for k, v in net.state_dict().items()}
+    assert "neural_points.Rw2c" not in sd                      # default identity: a plain tensor, not in the state dict (as the reference)
+    sd["neural_points.Rw2c"] = R
+    net2 = checkpoint.load_checkpoint(sd, opt, "cpu")
+    assert isinstance(net2.neural_points.Rw2c, torch.nn.Parameter) and not net2.neural_points.Rw2c.requires_grad
+    net_path, _ = checkpoint.save_checkpoint(net2, str(tmp_path), "latest")
+    saved = torch.load(net_path)
+    assert torch.equal(saved["neural_points.Rw2c"], R)
+    net3 = checkpoint.load_checkpoint(net_path, opt, "cpu")
+    assert torch.equal(net3.neural_points.Rw2c.detach(), R)
+    # back to the default: a later set_points without Rw2c drops the parameter again
+    p = net3.neural_points
+    p.set_points(p.xyz.detach(), p.points_embeding.detach(), points_color=p.points_color.detach(), points_dir=p.points_dir.detach(),
+                 points_conf=p.points_conf.detach())
+    assert "neural_points.Rw2c" not in net3.state_dict() and torch.equal(p.Rw2c, torch.eye(3))

@@ -27,12 +27,13 @@ def _forward(net, cfg, rays):
                near=r["near"], far=r["far"], h=r["h"], w=r["w"], intrinsic=r["intrinsic"])
 
 
-@pytest.mark.parametrize("precision", ["bf16x3", "fp32"])
+@pytest.mark.parametrize("precision,bwd_fp32", [("bf16x3", 0), ("bf16x3", 1), ("fp32", 0)])
 @pytest.mark.parametrize("name", ["tiny_opaque", "tiny_thin_sr8"])
-def test_gradients_match_reference_fixture(name, precision, golden_dir):
+def test_gradients_match_reference_fixture(name, precision, bwd_fp32, golden_dir):
+    """bwd_fp32 = 0: the layer GEMMs of the backward on the tensor cores (tcgen05, BF16x3; default); 1: the fp32 CUDA-core tiles."""
     fx = np.load(os.path.join(golden_dir, name + ".npz"))
     cfg = scene.CONFIGS["tiny"]
-    net, pts, opt = harness.build_model(cfg, DEV, SR=int(fx["SR"]), max_o=100000, pnb_precision=precision)
+    net, pts, opt = harness.build_model(cfg, DEV, SR=int(fx["SR"]), max_o=100000, pnb_precision=precision, pnb_bwd_fp32=bwd_fp32)
     net.aggregator.load_state_dict({k[4:]: torch.from_numpy(fx[k]) for k in fx.files if k.startswith("mlp.")})
     out = _forward(net, cfg, scene.make_rays(cfg, fx["pixels"]))
     assert np.abs(out["coarse_raycolor"][0].detach().cpu().numpy() - fx["coarse_raycolor"]).max() <= 1e-4
@@ -49,6 +50,7 @@ def test_gradients_match_reference_fixture(name, precision, golden_dir):
     for k, p in net.aggregator.named_parameters():
         _close(p.grad.cpu(), fx["gradmlp." + k], "aggregator." + k)
     assert npn.xyz.grad is None
+    net.check_errors()
 
 
 def test_gradients_match_oracle_autograd_chair():
@@ -95,3 +97,53 @@ def test_optimisation_step_reduces_loss():
         optim.step()
         losses.append(float(loss.detach()))
     assert losses[-1] < losses[0] * 0.9, losses
+
+
+def test_gradients_with_jittered_t_table():
+    """Training marches a per-ray jittered t table (point_query.py:81): same explicit table to the CUDA path and to the oracle."""
+    from pointnerf_b200.point_query import device_t_table_jitter
+    cfg = scene.CONFIGS["chair_plumbing"]
+    net, pts, opt = harness.build_model(cfg, DEV, alpha_bias=3.0, seed=5)
+    rays = scene.make_rays(cfg, scene.centre_patch(cfg, 16))
+    R = rays["raydir"].shape[1]
+    g = torch.Generator(device=DEV).manual_seed(9)
+    t = device_t_table_jitter(cfg.near, cfg.far, cfg.D, R, 0.3, torch.device(DEV), generator=g)
+    net.neural_points.querier._t_for = lambda near, far, n, device: t          # what is_train draws internally, made explicit
+    out = _forward(net, cfg, rays)
+    target = torch.linspace(0, 1, out["coarse_raycolor"].numel(), device=DEV).view_as(out["coarse_raycolor"])
+    ((out["coarse_raycolor"] - target) ** 2).mean().backward()
+    ref = pipeline.render(pts, harness.mlp_cpu(net.aggregator), rays["raydir"][0], cfg.campos, np.eye(3, dtype=np.float32),
+                          cfg.near, cfg.far, opt.vsize, opt.vscale, opt.kernel_size, opt.query_size, opt.ranges, opt.SR,
+                          opt.K, opt.P, pts["xyz"].shape[0], D=cfg.D, t=t.cpu().numpy(), want_shade=False)
+    assert np.array_equal(out["ray_mask"][0].cpu().numpy(), ref["ray_mask"])
+    pts_g = {k: v.clone().requires_grad_(k in ("embedding", "color", "dir", "conf")) for k, v in pts.items()}
+    mlp_g = {k: v.clone().requires_grad_(True) for k, v in harness.mlp_cpu(net.aggregator).items()}
+    mask = torch.from_numpy(ref["ray_mask"]) > 0
+    sh = shade_oracle.shade(pts_g, mlp_g, torch.from_numpy(ref["sample_pidx"]), torch.from_numpy(ref["sample_loc_w"]),
+                            rays["raydir"][0][mask], torch.tensor(cfg.campos), torch.eye(3), opt.vsize, torch.ones(3))
+    assert (out["coarse_raycolor"][0].detach().cpu() - sh["ray_color"]).abs().max().item() <= 1e-4
+    ((sh["ray_color"][None] - target.cpu()) ** 2).mean().backward()
+    npn = net.neural_points
+    _close(npn.points_embeding.grad.cpu(), pts_g["embedding"].grad, "points_embeding")
+    _close(npn.points_color.grad.cpu(), pts_g["color"].grad, "points_color")
+    _close(npn.points_dir.grad.cpu(), pts_g["dir"].grad, "points_dir")
+    _close(npn.points_conf.grad.cpu(), pts_g["conf"].grad, "points_conf", rtol=1e-3)
+    for k, p in net.aggregator.named_parameters():
+        _close(p.grad.cpu(), mlp_g[k].grad, "aggregator." + k)
+
+
+def test_backward_of_an_overwritten_forward_is_refused():
+    """The backward recomputes from the module's query / sigma_rgb buffers: a second forward (or an eval render) before backward()
+    would silently change them -> PnbError instead of wrong gradients."""
+    from pointnerf_b200.lib import PnbError
+    cfg = scene.CONFIGS["tiny"]
+    net, pts, opt = harness.build_model(cfg, DEV, alpha_bias=4.0)
+    rays = scene.make_rays(cfg, scene.centre_patch(cfg, 24))
+    out1 = _forward(net, cfg, rays)
+    with torch.no_grad():
+        _forward(net, cfg, scene.make_rays(cfg, scene.centre_patch(cfg, 12)))      # e.g. a validation render in between
+    with pytest.raises(PnbError):
+        (out1["coarse_raycolor"] ** 2).sum().backward()
+    out2 = _forward(net, cfg, rays)
+    (out2["coarse_raycolor"] ** 2).sum().backward()                                   # the normal order works
+    assert net.neural_points.points_embeding.grad is not None

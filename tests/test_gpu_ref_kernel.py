@@ -170,7 +170,7 @@ def test_ref_kernel_lego_silhouette():
 def test_ref_kernel_truck_chunk():
     """N = 2 M, kernel_size 5 (three shells), grid 450^3: centre chunk and a corner strip through the limb."""
     cfg = scene.CONFIGS["truck_8gpu"]
-    assert _compare("truck_8gpu", scene.centre_patch(cfg, 32), {}, 0.01) > 5000
+    assert _compare("truck_8gpu", scene.centre_patch(cfg, 32), {}, 0.01) > 4000
     assert _compare("truck_8gpu", _block(cfg, 860, 0, 100, 16), {}, 0.01) > 500
 
 

@@ -242,10 +242,12 @@ def test_workspace_overflow_is_safe_and_reported():
     from pointnerf_b200 import lib as L, runner
     cfg = scene.CONFIGS["scannet_8gpu"]
     net, pts, opt = harness.build_model(cfg, DEV, alpha_bias=3.0, pnb_max_valid_per_ray=2)
-    rays = scene.make_rays(cfg, _block(0, 0, 640, 160))                 # 102,400 rays x 24 valid samples >> 2 per ray / the 1 M floor
+    rays = scene.make_rays(cfg)                                          # 307,200 rays, every one hits a wall: several valid samples per ray >> 2
     out = _render_full(net, cfg, rays)
     col = out["coarse_raycolor"].clone()
     assert torch.isfinite(col).all() and col.min() >= -0.002 and col.max() <= 1.002
+    n_valid = int(net.last.counters_tensor()[L.QC["n_valid"]].item())
+    assert n_valid > net._max_valid, "the test frame must overflow the workspace (%d valid samples, capacity %d)" % (n_valid, net._max_valid)
     with pytest.raises(L.PnbOverflow):
         net.check_errors()
     out2 = _render_full(net, cfg, rays)                                  # the workspace grew: exact now
@@ -258,7 +260,7 @@ def test_workspace_overflow_is_safe_and_reported():
     # the whole-image entry checks and retries by itself
     net3, _, _ = harness.build_model(cfg, DEV, alpha_bias=3.0, pnb_max_valid_per_ray=2)
     data = {k: (v.to(DEV) if isinstance(v, torch.Tensor) else v) for k, v in rays.items()}
-    img = runner.render_image(net3, data, 160, 640)
+    img = runner.render_image(net3, data, cfg.H, cfg.W)
     assert torch.equal(img["coarse_raycolor"].reshape(1, -1, 3), col2)
     # deferred report: without check_errors() the NEXT call raises
     net4, _, _ = harness.build_model(cfg, DEV, alpha_bias=3.0, pnb_max_valid_per_ray=2)

@@ -66,3 +66,59 @@ def test_umma_cta_pair(mode, K, N):
     ref = A.double() @ W.double().t()
     d = (D.double() - ref).abs().max().item()
     assert d <= 2e-5 * max(ref.abs().max().item(), 1.0), "mode %d K=%d N=%d: max abs err %.3e" % (mode, K, N, d)
+
+
+# ---- the tcgen05 GEMM engine of the backward pass (csrc/gemm_tc.cu) against fp64 matmuls, every operand form it is used in
+def _gemm_tc(A, a_rs, a_ks, B, b_rs, b_ks, M, N, K, ldc, bias=None, act=0, dact=None, ldd=0, dact_n=0, splits=1, C0=None):
+    l = _lib.load_selftest()
+    C = torch.full((M, ldc), 7.0, device="cuda") if C0 is None else C0.clone()
+    err = torch.zeros(4, dtype=torch.int32, device="cuda")
+    part = torch.empty(max(splits, 1) * M * N, device="cuda")
+    ptr = lambda t: t.data_ptr() if t is not None else None
+    _lib.check_selftest(l.pnb_gemm_tc_test(A.data_ptr(), a_rs, a_ks, B.data_ptr(), b_rs, b_ks, C.data_ptr(), ldc, M, N, K, ptr(bias), act,
+                                           ptr(dact), ldd, dact_n, splits, part.data_ptr(), part.numel() * 4, 1 if C0 is not None else 0,
+                                           err.data_ptr(), torch.cuda.current_stream().cuda_stream), "pnb_gemm_tc_test")
+    torch.cuda.synchronize()
+    assert int(err[0]) == 0
+    return C
+
+
+def _rel(a, ref):
+    return ((a.double() - ref).abs().max() / ref.abs().max().clamp_min(1e-30)).item()
+
+
+@pytest.mark.parametrize("M,N,K", [(300, 256, 288), (128, 128, 128), (1000, 256, 272), (77, 288, 256), (4096, 128, 128)])
+def test_gemm_tc_nn_nt(M, N, K):
+    g = torch.Generator(device="cuda").manual_seed(M + N + K)
+    X = torch.randn(M, K + 16, device="cuda", generator=g)[:, :K]                 # leading dimension != K
+    lda = X.stride(0)
+    Wt = (0.1 * torch.randn(K, N, device="cuda", generator=g)).contiguous()       # W^T [K][N] as the backward holds the weights
+    bias = torch.randn(N, device="cuda", generator=g)
+    # NN (forward recompute): H = LeakyReLU(X Wt + b);  A(m,k) = X[m*lda + k], B(n,k) = Wt[k*N + n]
+    H = _gemm_tc(X, lda, 1, Wt, 1, N, M, N, K, N + 16, bias=bias, act=1)
+    ref = torch.nn.functional.leaky_relu(X.double() @ Wt.double() + bias.double(), 0.01)
+    assert _rel(H[:, :N], ref) < 2e-5 and torch.all(H[:, N:] == 7.0)
+    # NT (dX = dZ W * LeakyReLU'(Y)): A = dZ [M x N], B(n=k_in, k=n_out) = Wt[k_in*N + n_out]; result [M x K]
+    if K % 16 == 0:
+        dZ = torch.randn(M, N, device="cuda", generator=g)
+        Y = torch.randn(M, K, device="cuda", generator=g)
+        dact_n = (K // 16 - 1) * 16
+        dX = _gemm_tc(dZ, N, 1, Wt, N, 1, M, K, N, K, dact=Y, ldd=K, dact_n=dact_n)
+        refx = dZ.double() @ Wt.double().t()
+        mask = torch.where(Y > 0, 1.0, 0.01).double()
+        mask[:, dact_n:] = 1.0
+        assert _rel(dX, refx * mask) < 2e-5
+
+
+@pytest.mark.parametrize("rows,Kin,Nout,splits", [(5000, 288, 256, 3), (130000, 256, 256, 64), (999, 128, 128, 2), (40000, 272, 256, 20)])
+def test_gemm_tc_tn_splitk_accumulate(rows, Kin, Nout, splits):
+    """dWt[Kin x Nout] += X^T dZ: both operands transposed on the way into shared memory, deterministic split-K, accumulation."""
+    g = torch.Generator(device="cuda").manual_seed(rows)
+    X = torch.randn(rows, Kin, device="cuda", generator=g)
+    dZ = torch.randn(rows, Nout + 16, device="cuda", generator=g)[:, :Nout]
+    C0 = torch.randn(Kin, Nout, device="cuda", generator=g)
+    out = _gemm_tc(X, 1, Kin, dZ, 1, dZ.stride(0), Kin, Nout, rows, Nout, splits=splits, C0=C0)
+    ref = C0.double() + X.double().t() @ dZ.double()
+    assert _rel(out, ref) < 2e-5
+    out2 = _gemm_tc(X, 1, Kin, dZ, 1, dZ.stride(0), Kin, Nout, rows, Nout, splits=splits, C0=C0)
+    assert torch.equal(out, out2)                                                   # deterministic (no atomics)

@@ -18,7 +18,7 @@ for i in range(3):
     with torch.no_grad():
         net.render_full(list(cfg.campos), rd, torch.eye(3), cfg.near, cfg.far, [1., 1., 1.])
 net.check_errors()
-net.dbg_flags = 4
+net.dbg_flags = 4 | int(os.environ.get("PNB_DBG_FLAGS", "0"))       # frozen kernel: +8 = 8 epilogue warps (default 16), +16 = no software pipelining
 if os.environ.get("PNB_NO_WEIGHTS"):
     net.dbg_flags |= 0          # (the no-weights bit is a top-level flag)
     L.TC_PAIRS |= L.TC_DBG_NO_WEIGHTS
@@ -31,7 +31,7 @@ n_quads = int(net._err.cpu().view(torch.int64)[32 + 192])
 cyc = [(v & 0xffffffffffff) for v in per]
 cnt = net.last.counters_tensor().cpu().tolist()
 n_tiles = (n_quads + 3) // 4
-print("kernel", "k_shade_tc8 (frozen)" if net.frozen_ok else "k_shade_tc7 (general)", "| status", int(net._err[0]),
+print("kernel", "k_shade_tc8 (frozen, dbg %d)" % net.dbg_flags if net.frozen_ok else "k_shade_tc7 (general)", "| status", int(net._err[0]),
       "| n_valid", cnt[L.QC["n_valid"]], "n_pairs", cnt[L.QC["n_pairs"]], "n_quads", n_quads, "tiles", n_tiles,
       "row fill %.4f" % (cnt[L.QC["n_pairs"]] / max(n_quads * 32, 1)))
 print("per-CTA cycles: min %.2f M  max %.2f M  mean %.2f M -> %.1f k cycles per 128-row tile (tiles per CTA %.1f)"

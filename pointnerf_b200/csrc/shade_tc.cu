@@ -407,12 +407,14 @@ __device__ __forceinline__ float last_chunks_packed(const ShadeTcParams& p, uint
     using namespace tc;
     const float* bias = p.bias[3];
     float apart = 0.f;
+    uint32_t vv[2][16];
+    tmem_ld16(accb + (uint32_t)(16 * G), vv[0]);
 #pragma unroll
     for (int i = 0; i < NCHUNK; ++i) {
         const int c0 = 16 * (G + NG * i);
-        uint32_t v[16];
-        tmem_ld16(accb + (uint32_t)c0, v);
+        const uint32_t* v = vv[i & 1];
         tmem_ld_wait();
+        if (i + 1 < NCHUNK) tmem_ld16(accb + (uint32_t)(c0 + 16 * NG), vv[(i + 1) & 1]);      // next chunk in flight under this one's math
         float z[16];
 #pragma unroll
         for (int e4 = 0; e4 < 4; ++e4) {
@@ -923,6 +925,12 @@ __global__ void __launch_bounds__(tc8::nthr(NGRP), 1) k_shade_tc8(ShadeTcParams 
     tc_fence_after();
     const uint32_t tP = sm.tmem_base, tQ = sm.tmem_base + 256u;
     const long long _tk0 = clock64();
+    // in-kernel cycle accounting of block 0 (dbg bit 0, tools/tc_profile.py PNB_PROF=1): TW(slot, wait) adds the cycles a role spends
+    // in a wait, TB(slot) the cycles since the previous mark of this thread; off in production (a kernel-parameter flag)
+    const bool prof = (p.dbg_flags & 1) && blockIdx.x == 0 && (warp == 0 || warp == W_BUILD || warp == W_LOAD || warp == W_ISSUE);
+    long long _tm = _tk0;
+#define TW(slot, expr) [&]() { if (!prof) return (expr); const long long _t0 = clock64(); const bool _r = (expr); _tm = clock64(); if (lane == 0) prof_add(p, slot, _tm - _t0); return _r; }()
+#define TB(slot) do { if (prof) { const long long _t1 = clock64(); if (lane == 0) prof_add(p, slot, _t1 - _tm); _tm = _t1; } } while (0)
 
     if (warp == W_LOAD) {
         // ============================================================ weight ring: one K block (hi + lo image, 32 KB) per stage
@@ -930,7 +938,7 @@ __global__ void __launch_bounds__(tc8::nthr(NGRP), 1) k_shade_tc8(ShadeTcParams 
             const uint32_t total = (uint32_t)my_tiles * tc8::STAGES_PER_TILE;
             uint32_t s = 0, ph = 0, j = 0;
             for (uint32_t n = 0; n < total; ++n) {
-                if (!mbar_wait(&sm.bar_empty[s], ph ^ 1u, p.err, 91)) break;
+                if (!TW(0, mbar_wait(&sm.bar_empty[s], ph ^ 1u, p.err, 91))) break;
                 const uint32_t blk = j < (uint32_t)tc8::NKB1 ? (uint32_t)tc8::KB1_FIRST + j : 9u + (j - (uint32_t)tc8::NKB1);
                 if (p.dbg_no_weights) mbar_arrive(&sm.bar_full[s]);
                 else {
@@ -958,19 +966,20 @@ __global__ void __launch_bounds__(tc8::nthr(NGRP), 1) k_shade_tc8(ShadeTcParams 
             for (int l = 0; l < 4 && ok; ++l) {
                 const uint32_t acc = (l & 1) ? tP : tQ;
                 const uint32_t ab = (l & 1) ? tQ : tP;
-                if (l > 0) { if (!mbar_wait(&sm.bar_acc_full, c_acc & 1u, p.err, 92)) { ok = false; break; } ++c_acc; }
-                else if (t > 0) { if (!mbar_wait(&sm.bar_final, (uint32_t)(t - 1) & 1u, p.err, 92)) { ok = false; break; } }
-                if (l == 0) { if (!mbar_wait(&sm.bar_a1_ready, (uint32_t)t & 1u, p.err, 93)) { ok = false; break; } }
-                if (l == 1 && t > 0) { if (!mbar_wait(&sm.bar_drain, (uint32_t)(t - 1) & 1u, p.err, 94)) { ok = false; break; } }
+                if (l > 0) { if (!TW(1, mbar_wait(&sm.bar_acc_full, c_acc & 1u, p.err, 92))) { ok = false; break; } ++c_acc; }
+                else if (t > 0) { if (!TW(2, mbar_wait(&sm.bar_final, (uint32_t)(t - 1) & 1u, p.err, 92))) { ok = false; break; } }
+                if (l == 0) { if (!TW(3, mbar_wait(&sm.bar_a1_ready, (uint32_t)t & 1u, p.err, 93))) { ok = false; break; } }
+                if (l == 1 && t > 0) { if (!TW(4, mbar_wait(&sm.bar_drain, (uint32_t)(t - 1) & 1u, p.err, 94))) { ok = false; break; } }
                 tc_fence_after();
                 const int nkb = l == 0 ? tc8::NKB1 : nkb_of(l);
                 for (int kb = 0; kb < nkb && ok; ++kb) {
                     const bool need_chunks = (l >= 1 && kb < 8);
                     uint64_t* cb0 = need_chunks ? &sm.bar_kblk[kb] : &sm.bar_full[s];
                     const uint32_t cp0 = need_chunks ? (c_pack & 1u) : ph;
+                    TB(7);
                     if (!mbar_try_wait4(&sm.bar_full[s], ph, cb0, cp0, &sm.bar_full[s], ph, cb0, cp0)) {
-                        if (need_chunks && !mbar_wait(cb0, cp0, p.err, 95)) { ok = false; break; }
-                        if (!mbar_wait(&sm.bar_full[s], ph, p.err, 96)) { ok = false; break; }
+                        if (need_chunks && !TW(5, mbar_wait(cb0, cp0, p.err, 95))) { ok = false; break; }
+                        if (!TW(6, mbar_wait(&sm.bar_full[s], ph, p.err, 96))) { ok = false; break; }
                     }
                     tc_fence_after();
                     const uint32_t bh = b0_lo + s * (uint32_t)(tc8::STAGE >> 4), bl = bh + (uint32_t)(IMG >> 4);
@@ -1013,7 +1022,7 @@ __global__ void __launch_bounds__(tc8::nthr(NGRP), 1) k_shade_tc8(ShadeTcParams 
         for (int t = 0; t <= my_tiles && ok; ++t) {
             if (t < my_tiles) {
                 const int tile = (int)blockIdx.x + t * (int)gridDim.x;
-                if (t > 0 && !mbar_wait(&sm.bar_a1_free, (uint32_t)(t - 1) & 1u, p.err, 97)) { ok = false; break; }
+                if (t > 0 && !TW(8, mbar_wait(&sm.bar_a1_free, (uint32_t)(t - 1) & 1u, p.err, 97))) { ok = false; break; }
                 const int qd = tile * 4 + qw;
                 uint32_t first = 0, nsamp = 0;
                 if (qd < n_quads) { first = p.quad_first[qd]; nsamp = p.quad_first[qd + 1] - first; }
@@ -1032,10 +1041,11 @@ __global__ void __launch_bounds__(tc8::nthr(NGRP), 1) k_shade_tc8(ShadeTcParams 
                 mbar_arrive(&sm.bar_a1_ready);
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&sm.bar_prow[t & 1]);
+                TB(9);
             }
             if (t > 0) {
                 const int tf = t - 1;
-                if (!mbar_wait(&sm.bar_final, (uint32_t)tf & 1u, p.err, 99)) { ok = false; break; }
+                if (!TW(10, mbar_wait(&sm.bar_final, (uint32_t)tf & 1u, p.err, 99))) { ok = false; break; }
                 tc_fence_after();
                 const QuadRow qr = quad_row(sm.qhead[tf & 1][qw], (int)sm.qtotal[tf & 1][qw], lane);
                 const int sidx = qr.live ? (int)p.vorder[sm.qfirst[tf & 1][qw] + qr.j] : 0;
@@ -1043,7 +1053,8 @@ __global__ void __launch_bounds__(tc8::nthr(NGRP), 1) k_shade_tc8(ShadeTcParams 
                 const float wrow = sm.wc[tf & 1][row];
                 const float apart = last_chunks_packed<NG4, NCH4_B>(p, tP + tlane, 0, wrow, qr.st, swrite, sidx, lane);
                 tc_fence_before();
-                if (!mbar_wait(&sm.bar_alpha, (uint32_t)tf & 1u, p.err, 100)) { ok = false; break; }      // the epilogue warps' partial sums
+                TB(11);
+                if (!TW(12, mbar_wait(&sm.bar_alpha, (uint32_t)tf & 1u, p.err, 100))) { ok = false; break; }      // the epilogue warps' partial sums
                 float a = apart;
 #pragma unroll
                 for (int gq = 0; gq < NGRP; ++gq) a += sm.alpha_part[gq][row];          // fixed order: deterministic
@@ -1064,22 +1075,24 @@ __global__ void __launch_bounds__(tc8::nthr(NGRP), 1) k_shade_tc8(ShadeTcParams 
         bool ok = true;
         for (int t = 0; t < my_tiles && ok; ++t) {
             // ---- layer 1: accumulator + pre[point of this row] (the hoisted 224 inputs and the bias)
-            if (!mbar_wait(&sm.bar_prow[t & 1], (uint32_t)(t >> 1) & 1u, p.err, 102)) { ok = false; break; }
+            if (!TW(13, mbar_wait(&sm.bar_prow[t & 1], (uint32_t)(t >> 1) & 1u, p.err, 102))) { ok = false; break; }
             const int pi = max(sm.prow[t & 1][erow], 0);          // unused rows: any finite values (their outputs are never used)
             const float4* pp = reinterpret_cast<const float4*>(p.pre + (size_t)pi * 256);
-            if (!mbar_wait(&sm.bar_acc_full, n_acc & 1u, p.err, 98)) { ok = false; break; }
+            if (!TW(14, mbar_wait(&sm.bar_acc_full, n_acc & 1u, p.err, 98))) { ok = false; break; }
             ++n_acc;
             tc_fence_after();
             tc8_epi_layer<NGRP, SWP, true>(sm, tQ + tlane, grp, nullptr, pp);
+            TB(15);
             // ---- layers 2, 3
             for (int l = 1; l < 3 && ok; ++l, ++n_acc) {
-                if (!mbar_wait(&sm.bar_acc_full, n_acc & 1u, p.err, 98)) { ok = false; break; }
+                if (!TW(16, mbar_wait(&sm.bar_acc_full, n_acc & 1u, p.err, 98))) { ok = false; break; }
                 tc_fence_after();
                 tc8_epi_layer<NGRP, SWP, false>(sm, ((l & 1) ? tP : tQ) + tlane, grp, p.bias[l], nullptr);
+                TB(17);
             }
             if (!ok) break;
             {   // this warp's share of the LAST epilogue (chunk groups 1..NGRP of NGRP+1; the builder warps take group 0)
-                if (!mbar_wait(&sm.bar_final, (uint32_t)t & 1u, p.err, 101)) { ok = false; break; }
+                if (!TW(18, mbar_wait(&sm.bar_final, (uint32_t)t & 1u, p.err, 101))) { ok = false; break; }
                 tc_fence_after();
                 const QuadRow qr = quad_row(sm.qhead[t & 1][quad], (int)sm.qtotal[t & 1][quad], lane);
                 const int sidx = qr.live ? (int)p.vorder[sm.qfirst[t & 1][quad] + qr.j] : 0;
@@ -1087,10 +1100,14 @@ __global__ void __launch_bounds__(tc8::nthr(NGRP), 1) k_shade_tc8(ShadeTcParams 
                 tc_fence_before();
                 sm.alpha_part[grp][erow] = apart;
                 __syncwarp();
+                TB(19);
                 if (lane == 0) { mbar_arrive(&sm.bar_alpha); mbar_arrive(&sm.bar_drain); }
             }
         }
     }
+    if (prof && tid == 0) prof_add(p, 20, clock64() - _tk0);
+#undef TW
+#undef TB
     if (tid == 0 && (p.dbg_flags & 4) && blockIdx.x < 192) {      // per-CTA cycles and SM id; [32 + 192] = number of quadrants
         uint32_t smid;
         asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));

@@ -18,7 +18,7 @@ for i in range(3):
     with torch.no_grad():
         net.render_full(list(cfg.campos), rd, torch.eye(3), cfg.near, cfg.far, [1., 1., 1.])
 net.check_errors()
-net.dbg_flags = 4 | int(os.environ.get("PNB_DBG_FLAGS", "0"))       # frozen kernel: +8 = 8 epilogue warps (default 16), +16 = no software pipelining
+net.dbg_flags = 4 | int(os.environ.get("PNB_DBG_FLAGS", "0")) | (1 if os.environ.get("PNB_PROF") else 0)       # frozen kernel: +8 = 8 epilogue warps (default 16), +16 = no software pipelining
 if os.environ.get("PNB_NO_WEIGHTS"):
     net.dbg_flags |= 0          # (the no-weights bit is a top-level flag)
     L.TC_PAIRS |= L.TC_DBG_NO_WEIGHTS
@@ -37,3 +37,15 @@ print("kernel", "k_shade_tc8 (frozen, dbg %d)" % net.dbg_flags if net.frozen_ok 
 print("per-CTA cycles: min %.2f M  max %.2f M  mean %.2f M -> %.1f k cycles per 128-row tile (tiles per CTA %.1f)"
       % (min(cyc) / 1e6, max(cyc) / 1e6, sum(cyc) / len(cyc) / 1e6, sum(cyc) / len(cyc) / (n_tiles / 148.0) / 1e3, n_tiles / 148.0))
 print("per-CTA kernel cycles (M) @smid:", " ".join("%.1f@%d" % ((v & 0xffffffffffff) / 1e6, v >> 48) for v in per))
+
+if os.environ.get("PNB_PROF") and net.frozen_ok:
+    c = net._err.cpu().view(torch.int64)[1:22].tolist()
+    names = ["loader: wait empty", "issuer: wait acc_full (l>0)", "issuer: wait final (l=0)", "issuer: wait a1_ready", "issuer: wait drain",
+             "issuer: wait kblk (slow path)", "issuer: wait weights (slow path)", "issuer: MMA issue + commits + fast probes",
+             "builder q0: wait a1_free", "builder q0: build", "builder q0: wait final", "builder q0: last-epilogue share", "builder q0: wait alpha",
+             "epi warp 0: wait prow", "epi warp 0: wait acc_full (E1)", "epi warp 0: E1 busy", "epi warp 0: wait acc_full (E2,E3)", "epi warp 0: E2+E3 busy",
+             "epi warp 0: wait final", "epi warp 0: last-epilogue share", "kernel total (thread 0)"]
+    tiles0 = (n_tiles - 1) // 148 + 1
+    print("block 0 accounting (%d tiles), cycles per tile:" % tiles0)
+    for n, v in zip(names, c):
+        print("  %-46s %9.0f  (%5.1f %% of the kernel)" % (n, v / tiles0, 100.0 * v / max(c[20], 1)))

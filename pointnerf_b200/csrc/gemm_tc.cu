@@ -65,7 +65,7 @@ __global__ void __launch_bounds__(gtc::NTHR, 1) k_gemm_tc(GemmTc g) {
     const int nkb = (kend - kbeg + 31) >> 5;
 
     if (tid == 0) {
-        for (int s = 0; s < NSTAGE; ++s) { mbar_init(&sm.bar_full[s], 128); mbar_init(&sm.bar_empty[s], 1); }
+        for (int s = 0; s < NSTAGE; ++s) { mbar_init(&sm.bar_full[s], 4); mbar_init(&sm.bar_empty[s], 1); }   // one arrive per loader warp
         mbar_init(&sm.bar_acc, 1);
         mbar_fence_init();
     }
@@ -108,7 +108,8 @@ __global__ void __launch_bounds__(gtc::NTHR, 1) k_gemm_tc(GemmTc g) {
             load_row(g.A, g.a_rs, g.a_ks, ra, a_ok, k0, kend, sm.a_hi[s], sm.a_lo[s], t);
             load_row(g.B, g.b_rs, g.b_ks, rb, b_ok, k0, kend, sm.b_hi[s], sm.b_lo[s], t);
             fence_proxy_async();
-            mbar_arrive(&sm.bar_full[s]);
+            __syncwarp();
+            if ((tid & 31) == 0) mbar_arrive(&sm.bar_full[s]);   // 32 same-address arrives would serialise in the shared-memory atomic unit
         }
         if (ok && mbar_wait(&sm.bar_acc, 0u, g.err, 73)) {
             tc_fence_after();

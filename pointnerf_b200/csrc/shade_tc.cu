@@ -480,13 +480,13 @@ __global__ void __launch_bounds__(tc7::NTHR, 1) k_shade_tc7(ShadeTcParams p) {
 
     if (tid == 0) {
         for (int s = 0; s < tc7::NSTAGE; ++s) { mbar_init(&sm.bar_full[s], 1); mbar_init(&sm.bar_empty[s], 1); }
-        mbar_init(&sm.bar_a1_ready, tc7::NBUILD);
+        mbar_init(&sm.bar_a1_ready, tc7::NBUILD / 32);              // one arrive per builder warp
         mbar_init(&sm.bar_a1_free, 1);
         mbar_init(&sm.bar_acc_full, 1);
         mbar_init(&sm.bar_final, 1);
         mbar_init(&sm.bar_alpha, tc7::NEPI_WARPS);
         mbar_init(&sm.bar_drain, tc7::NEPI_WARPS + tc7::NBUILD / 32);     // one arrive per warp that reads the layer-4 accumulator
-        for (int c = 0; c < 8; ++c) mbar_init(&sm.bar_kblk[c], 32 * 4 * 2);
+        for (int c = 0; c < 8; ++c) mbar_init(&sm.bar_kblk[c], 4 * 2);   // one arrive per warp and chunk (32 same-address arrives serialise)
         mbar_fence_init();
         if (blockIdx.x == 0 && q.counters[PNB_QC_N_VALID] > p.hbar_cap) atomicExch(p.err, 9);
     }
@@ -604,7 +604,8 @@ __global__ void __launch_bounds__(tc7::NTHR, 1) k_shade_tc7(ShadeTcParams p) {
                 if (part == 0) build_pair_part<0, true>(sm, p, tile, t, row, n_valid, pvi, lane - qr.st, qr.st, qr.live ? cj : 1);
                 else build_pair_part<1, true>(sm, p, tile, t, row, n_valid, pvi, lane - qr.st, qr.st, qr.live ? cj : 1);
                 fence_proxy_async();
-                mbar_arrive(&sm.bar_a1_ready);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&sm.bar_a1_ready);
             }
             if (t > 0) {
                 const int tf = t - 1;
@@ -663,7 +664,8 @@ __global__ void __launch_bounds__(tc7::NTHR, 1) k_shade_tc7(ShadeTcParams p) {
                         tmem_st8(accb + (uint32_t)c0 + 8u, ll);
                         tmem_st_wait();
                         tc_fence_before();
-                        mbar_arrive(&sm.bar_kblk[g >> 1]);
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&sm.bar_kblk[g >> 1]);
                     }
                 }
             }
@@ -840,6 +842,8 @@ __device__ __forceinline__ void tc8_epi_layer(tc8::Smem& sm, uint32_t accb, int 
     using namespace tc;
     constexpr int NCH = 16 / NGRP;
     constexpr int PF = NCH < 3 ? NCH : 3;         // chunks of `pre` in flight (FIRST)
+    const bool lane0 = (threadIdx.x & 31) == 0;   // ONE mbarrier arrive per warp and chunk: 32 same-address arrives serialise in the
+                                                  // shared-memory atomic unit (measured: they, not the MMAs, set the tile time)
     float4 pf[PF][4];
     if (FIRST) {
 #pragma unroll
@@ -875,14 +879,16 @@ __device__ __forceinline__ void tc8_epi_layer(tc8::Smem& sm, uint32_t accb, int 
         if (SWP && i > 0) {                        // the previous chunk's stores have had a whole conversion to land
             tmem_st_wait();
             tc_fence_before();
-            mbar_arrive(&sm.bar_kblk[(g - NGRP) >> 1]);
+            __syncwarp();
+            if (lane0) mbar_arrive(&sm.bar_kblk[(g - NGRP) >> 1]);
         }
         tmem_st8(accb + (uint32_t)c0, hh);
         tmem_st8(accb + (uint32_t)c0 + 8u, ll);
         if (!SWP || i == NCH - 1) {
             tmem_st_wait();
             tc_fence_before();
-            mbar_arrive(&sm.bar_kblk[g >> 1]);
+            __syncwarp();
+            if (lane0) mbar_arrive(&sm.bar_kblk[g >> 1]);
         }
     }
 }
@@ -907,13 +913,13 @@ __global__ void __launch_bounds__(tc8::nthr(NGRP), 1) k_shade_tc8(ShadeTcParams 
 
     if (tid == 0) {
         for (int s = 0; s < tc8::NSTAGE; ++s) { mbar_init(&sm.bar_full[s], 1); mbar_init(&sm.bar_empty[s], 1); }
-        mbar_init(&sm.bar_a1_ready, tc8::NBUILD);
+        mbar_init(&sm.bar_a1_ready, tc8::NBUILD / 32);              // one arrive per builder warp
         mbar_init(&sm.bar_a1_free, 1);
         mbar_init(&sm.bar_acc_full, 1);
         mbar_init(&sm.bar_final, 1);
         mbar_init(&sm.bar_alpha, NEPI_WARPS);
         mbar_init(&sm.bar_drain, NEPI_WARPS + tc8::NBUILD / 32);     // one arrive per warp that reads the layer-4 accumulator
-        for (int c = 0; c < 8; ++c) mbar_init(&sm.bar_kblk[c], 32 * 4 * 2);
+        for (int c = 0; c < 8; ++c) mbar_init(&sm.bar_kblk[c], 4 * 2);   // 4 quadrant warps x 2 chunks of 16 columns, one arrive per warp
         mbar_init(&sm.bar_prow[0], tc8::NBUILD / 32);
         mbar_init(&sm.bar_prow[1], tc8::NBUILD / 32);
         mbar_fence_init();
@@ -1038,9 +1044,8 @@ __global__ void __launch_bounds__(tc8::nthr(NGRP), 1) k_shade_tc8(ShadeTcParams 
                 const int pvi = qr.live ? (int)p.vorder[first + qr.j] : -1;
                 build_pair_frozen(sm, p, t, row, n_valid, pvi, lane - qr.st, qr.st, qr.live ? cj : 1);
                 fence_proxy_async();
-                mbar_arrive(&sm.bar_a1_ready);
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&sm.bar_prow[t & 1]);
+                if (lane == 0) { mbar_arrive(&sm.bar_a1_ready); mbar_arrive(&sm.bar_prow[t & 1]); }
                 TB(9);
             }
             if (t > 0) {

@@ -35,7 +35,7 @@ def _stale(lib, srcs):
 
 
 def needs_build():
-    return _stale(LIB, sources()) or _stale(LIB_SELFTEST, selftest_sources())
+    return _stale(LIB, sources()) or _stale(LIB_SELFTEST, selftest_sources() + sources())
 
 
 def _compile(srcs, lib, log):
@@ -62,7 +62,7 @@ def build(force=False, verbose=False):
     log = []
     if force or _stale(LIB, sources()):
         _compile(sources(), LIB, log)
-    if force or _stale(LIB_SELFTEST, selftest_sources()):
+    if force or _stale(LIB_SELFTEST, selftest_sources() + sources()):     # gemm_selftest.cu includes ../gemm_tc.cu
         _compile(selftest_sources(), LIB_SELFTEST, log)
     if log:
         with open(os.path.join(CSRC, "build.log"), "w") as f:

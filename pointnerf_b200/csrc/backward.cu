@@ -112,6 +112,7 @@ static int gemm_nn(const GemmCtx& cx, const float* A, long lda, const float* Bt,
         GemmTc g{};
         g.A = A; g.a_rs = lda; g.a_ks = 1; g.B = Bt; g.b_rs = 1; g.b_ks = ldb; g.C = C; g.ldc = ldc; g.M = M; g.N = N; g.K = K;
         g.bias = bias; g.act = act; g.dact = nullptr; g.ldd = 0; g.dact_n = 0; g.err = cx.err;
+        g.precise = 1;      // forward recompute: fp32-level pre-activations, so that the LeakyReLU masks are those of an fp32 forward
         return gemm_tc(g, 1, nullptr, 0, 0, cx.st);
     }
     dim3 g((N + 63) / 64, (M + 127) / 128, 1);

@@ -10,6 +10,9 @@
 //   warps 0-3  load fp32 rows from global memory (thread = tile row of A and of B), split into bf16 hi / lo, 16-byte stores
 //              into the operand layout; afterwards the epilogue (thread = accumulator row = TMEM lane)
 //   warp  4    issues 6 tcgen05.mma per K block (A_hi W_hi, A_lo W_hi, A_hi W_lo for the two K=16 steps), one commit per block
+// PRECISE mode (forward recompute only): three bf16 parts per operand and the six products of total order <= 2 (a0b0, a1b0, a0b1,
+// a2b0, a1b1, a0b2): fp32-level pre-activations, so that the LeakyReLU masks of the backward are those of an fp32 forward (with the
+// BF16x3 recompute ~1e-5 of the units land on the other side of zero and each such flip changes a pair's gradient by ~1/256).
 // Split-K (dW: the reduction runs over the ~1e5 pair rows of a training batch): blockIdx.z owns a K range and writes its partial
 // tile to a workspace; k_splitk_reduce adds the partials in split order (deterministic, no atomics).
 #include "common.cuh"
@@ -23,14 +26,16 @@ namespace gtc {
 constexpr int TM = 128, TN = 128, NSTAGE = 4;
 constexpr int BLK = 128 * 64;             // [128 x 32] bf16 block
 constexpr int NTHR = 160;
+template <int NPART>
 struct Smem {
-    unsigned char a_hi[NSTAGE][BLK], a_lo[NSTAGE][BLK], b_hi[NSTAGE][BLK], b_lo[NSTAGE][BLK];
+    unsigned char a[NPART][NSTAGE][BLK], b[NPART][NSTAGE][BLK];     // part 0 = hi, 1 = lo (mid), 2 = lo of the 3-part split
     uint64_t bar_full[NSTAGE], bar_empty[NSTAGE], bar_acc;
     uint32_t tmem_base;
 };
-// one tile row (32 K elements of row `r`) of an operand -> hi / lo blocks.  rs / ks: element strides of the row / reduction index.
-__device__ __forceinline__ void load_row(const float* __restrict__ P, long rs, long ks, long r, bool row_ok, int k0, int kend, unsigned char* hi,
-                                         unsigned char* lo, int t) {
+// one tile row (32 K elements of row `r`) of an operand -> NPART bf16 blocks.  rs / ks: element strides of the row / reduction index.
+template <int NPART>
+__device__ __forceinline__ void load_row(const float* __restrict__ P, long rs, long ks, long r, bool row_ok, int k0, int kend,
+                                         unsigned char (*blk)[NSTAGE][BLK], int s, int t) {
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
         float v[8];
@@ -45,20 +50,29 @@ __device__ __forceinline__ void load_row(const float* __restrict__ P, long rs, l
 #pragma unroll
             for (int e = 0; e < 8; ++e) v[e] = (kc + e < kend) ? __ldg(P + r * rs + (long)(kc + e) * ks) : 0.f;
         }
-        uint32_t h[4], l[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) split_bf16x2(v[2 * i], v[2 * i + 1], h[i], l[i]);
         const uint32_t off = tile_offset_bytes<LAYOUT_NONE>(t, 8 * c);
-        *reinterpret_cast<uint4*>(hi + off) = make_uint4(h[0], h[1], h[2], h[3]);
-        *reinterpret_cast<uint4*>(lo + off) = make_uint4(l[0], l[1], l[2], l[3]);
+#pragma unroll
+        for (int part = 0; part < NPART; ++part) {
+            uint32_t w[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+                v[2 * i] -= __low2float(h); v[2 * i + 1] -= __high2float(h);          // the residual feeds the next part
+                w[i] = *reinterpret_cast<const uint32_t*>(&h);
+            }
+            *reinterpret_cast<uint4*>(blk[part][s] + off) = make_uint4(w[0], w[1], w[2], w[3]);
+        }
     }
 }
 }  // namespace gtc
 
+template <bool PRECISE>
 __global__ void __launch_bounds__(gtc::NTHR, 1) k_gemm_tc(GemmTc g) {
     using namespace gtc;
+    constexpr int NPART = PRECISE ? 3 : 2;
+    using SmemT = Smem<NPART>;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
-    Smem& sm = *reinterpret_cast<Smem*>(smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u));
+    SmemT& sm = *reinterpret_cast<SmemT*>(smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u));
     const int tid = threadIdx.x, warp = tid >> 5;
     const int m0 = blockIdx.y * TM, n0 = blockIdx.x * TN;
     const int kbeg = blockIdx.z * g.kchunk, kend = min(g.K, kbeg + g.kchunk);
@@ -78,21 +92,26 @@ __global__ void __launch_bounds__(gtc::NTHR, 1) k_gemm_tc(GemmTc g) {
     if (warp == 4) {
         const uint32_t idesc = make_idesc_bf16(128, 128);
         const uint32_t hiw = desc_hi<LAYOUT_NONE>();
-        const uint32_t ah0 = desc_lo<LAYOUT_NONE>(smem_u32(sm.a_hi[0])), al0 = desc_lo<LAYOUT_NONE>(smem_u32(sm.a_lo[0]));
-        const uint32_t bh0 = desc_lo<LAYOUT_NONE>(smem_u32(sm.b_hi[0])), bl0 = desc_lo<LAYOUT_NONE>(smem_u32(sm.b_lo[0]));
+        uint32_t a0[NPART], b0[NPART];
+#pragma unroll
+        for (int i = 0; i < NPART; ++i) { a0[i] = desc_lo<LAYOUT_NONE>(smem_u32(sm.a[i][0])); b0[i] = desc_lo<LAYOUT_NONE>(smem_u32(sm.b[i][0])); }
         constexpr uint32_t KADV = kstep_adv16<LAYOUT_NONE>(), SADV = BLK >> 4;
         bool ok = true;
         for (int kb = 0; kb < nkb && ok; ++kb) {
             const uint32_t s = (uint32_t)kb & (NSTAGE - 1), ph = ((uint32_t)kb >> 2) & 1u;
             if (!mbar_wait(&sm.bar_full[s], ph, g.err, 71)) { ok = false; break; }
             tc_fence_after();
-            const uint32_t ah = ah0 + s * SADV, al = al0 + s * SADV, bh = bh0 + s * SADV, bl = bl0 + s * SADV;
-            mma_ss2_w(tacc, ah, hiw, bh, hiw, idesc, kb ? 1u : 0u);
-            mma_ss2_w(tacc, al, hiw, bh, hiw, idesc, 1u);
-            mma_ss2_w(tacc, ah + KADV, hiw, bh + KADV, hiw, idesc, 1u);
-            mma_ss2_w(tacc, al + KADV, hiw, bh + KADV, hiw, idesc, 1u);
-            mma_ss2_w(tacc, ah, hiw, bl, hiw, idesc, 1u);
-            mma_ss2_w(tacc, ah + KADV, hiw, bl + KADV, hiw, idesc, 1u);
+            bool first = kb == 0;
+#pragma unroll
+            for (int i = 0; i < NPART; ++i)
+#pragma unroll
+                for (int j = 0; j < NPART; ++j) {
+                    if (i + j >= NPART) continue;          // products of total order < NPART: 3 (BF16x3) or 6 (3-part split)
+                    const uint32_t ad = a0[i] + s * SADV, bd = b0[j] + s * SADV;
+                    mma_ss2_w(tacc, ad, hiw, bd, hiw, idesc, first ? 0u : 1u);
+                    mma_ss2_w(tacc, ad + KADV, hiw, bd + KADV, hiw, idesc, 1u);
+                    first = false;
+                }
             mma_commit_w(&sm.bar_empty[s]);
         }
         mma_commit_w(&sm.bar_acc);
@@ -105,8 +124,8 @@ __global__ void __launch_bounds__(gtc::NTHR, 1) k_gemm_tc(GemmTc g) {
             const uint32_t s = (uint32_t)kb & (NSTAGE - 1), ph = ((uint32_t)kb >> 2) & 1u;
             if (!mbar_wait(&sm.bar_empty[s], ph ^ 1u, g.err, 72)) { ok = false; break; }
             const int k0 = kbeg + 32 * kb;
-            load_row(g.A, g.a_rs, g.a_ks, ra, a_ok, k0, kend, sm.a_hi[s], sm.a_lo[s], t);
-            load_row(g.B, g.b_rs, g.b_ks, rb, b_ok, k0, kend, sm.b_hi[s], sm.b_lo[s], t);
+            load_row<NPART>(g.A, g.a_rs, g.a_ks, ra, a_ok, k0, kend, sm.a, (int)s, t);
+            load_row<NPART>(g.B, g.b_rs, g.b_ks, rb, b_ok, k0, kend, sm.b, (int)s, t);
             fence_proxy_async();
             __syncwarp();
             if ((tid & 31) == 0) mbar_arrive(&sm.bar_full[s]);   // 32 same-address arrives would serialise in the shared-memory atomic unit
@@ -175,23 +194,28 @@ int gemm_tc(const GemmTc& g0, int splits, float* part_ws, size_t part_bytes, int
     static int configured[64] = {0};
     int dev = 0;
     PNB_CHECK_CUDA(cudaGetDevice(&dev));
-    const size_t smem = sizeof(gtc::Smem) + 128;
+    const bool precise = g.precise != 0;
+    const size_t smem = (precise ? sizeof(gtc::Smem<3>) : sizeof(gtc::Smem<2>)) + 128;
+    static_assert(sizeof(gtc::Smem<3>) + 128 <= 232448, "precise GEMM tile exceeds the shared memory of an SM");
     if (dev >= 0 && dev < 64 && !configured[dev]) {
-        PNB_CHECK_CUDA(cudaFuncSetAttribute(k_gemm_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        PNB_CHECK_CUDA(cudaFuncSetAttribute(k_gemm_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(gtc::Smem<2>) + 128)));
+        PNB_CHECK_CUDA(cudaFuncSetAttribute(k_gemm_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(gtc::Smem<3>) + 128)));
         configured[dev] = 1;
     }
     if (splits <= 1) {
         g.kchunk = g.K; g.part = nullptr;
         dim3 grid((g.N + gtc::TN - 1) / gtc::TN, (g.M + gtc::TM - 1) / gtc::TM, 1);
         PNB_REQUIRE(!accumulate, PNB_ERR_INVALID, "gemm_tc: accumulation needs the split-K path");
-        k_gemm_tc<<<grid, gtc::NTHR, smem, st>>>(g);
+        if (precise) k_gemm_tc<true><<<grid, gtc::NTHR, smem, st>>>(g);
+        else k_gemm_tc<false><<<grid, gtc::NTHR, smem, st>>>(g);
     } else {
         int kchunk = ((g.K + splits - 1) / splits + 31) / 32 * 32;
         splits = (g.K + kchunk - 1) / kchunk;
         PNB_REQUIRE(part_ws && part_bytes >= (size_t)splits * g.M * g.N * sizeof(float), PNB_ERR_WORKSPACE, "gemm_tc: split-K workspace too small");
         g.kchunk = kchunk; g.part = part_ws;
         dim3 grid((g.N + gtc::TN - 1) / gtc::TN, (g.M + gtc::TM - 1) / gtc::TM, splits);
-        k_gemm_tc<<<grid, gtc::NTHR, smem, st>>>(g);
+        if (precise) k_gemm_tc<true><<<grid, gtc::NTHR, smem, st>>>(g);
+        else k_gemm_tc<false><<<grid, gtc::NTHR, smem, st>>>(g);
         const long n = (long)g.M * g.N;
         k_splitk_reduce<<<(int)((n + 255) / 256), 256, 0, st>>>(part_ws, splits, g.M, g.N, g.C, g.ldc, accumulate);
     }

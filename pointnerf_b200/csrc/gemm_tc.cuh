@@ -14,6 +14,7 @@ struct GemmTc {
     int act;                           // 1: LeakyReLU(0.01) on the result
     const float* dact; long ldd;       // not null: result *= (dact[m*ldd + n] > 0 ? 1 : 0.01) for n < dact_n  (backward of the LeakyReLU below)
     int dact_n;
+    int precise;                       // 1: three bf16 parts per operand, six products (fp32-level result); 0: BF16x3 (two parts, three products)
     int* err;                          // device int: set non-zero if a bounded pipeline wait expires
     // filled by gemm_tc():
     int kchunk; float* part;

@@ -27,7 +27,7 @@ int pnb_umma_selftest2(const float* d_A, const float* d_W, float* d_D, int K, in
  * (>= splits*M*N floats), accumulate != 0 adds to C. */
 int pnb_gemm_tc_test(const float* A, long a_rs, long a_ks, const float* B, long b_rs, long b_ks, float* C, long ldc, int M, int N, int K,
                      const float* bias, int act, const float* dact, long ldd, int dact_n, int splits, float* part, size_t part_bytes,
-                     int accumulate, int* d_err, pnb_stream_t stream);
+                     int accumulate, int precise /* 3-part split, 6 products */, int* d_err, pnb_stream_t stream);
 #ifdef __cplusplus
 }
 #endif

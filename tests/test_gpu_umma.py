@@ -69,7 +69,7 @@ def test_umma_cta_pair(mode, K, N):
 
 
 # ---- the tcgen05 GEMM engine of the backward pass (csrc/gemm_tc.cu) against fp64 matmuls, every operand form it is used in
-def _gemm_tc(A, a_rs, a_ks, B, b_rs, b_ks, M, N, K, ldc, bias=None, act=0, dact=None, ldd=0, dact_n=0, splits=1, C0=None):
+def _gemm_tc(A, a_rs, a_ks, B, b_rs, b_ks, M, N, K, ldc, bias=None, act=0, dact=None, ldd=0, dact_n=0, splits=1, C0=None, precise=0):
     l = _lib.load_selftest()
     C = torch.full((M, ldc), 7.0, device="cuda") if C0 is None else C0.clone()
     err = torch.zeros(4, dtype=torch.int32, device="cuda")
@@ -77,7 +77,7 @@ def _gemm_tc(A, a_rs, a_ks, B, b_rs, b_ks, M, N, K, ldc, bias=None, act=0, dact=
     ptr = lambda t: t.data_ptr() if t is not None else None
     _lib.check_selftest(l.pnb_gemm_tc_test(A.data_ptr(), a_rs, a_ks, B.data_ptr(), b_rs, b_ks, C.data_ptr(), ldc, M, N, K, ptr(bias), act,
                                            ptr(dact), ldd, dact_n, splits, part.data_ptr(), part.numel() * 4, 1 if C0 is not None else 0,
-                                           err.data_ptr(), torch.cuda.current_stream().cuda_stream), "pnb_gemm_tc_test")
+                                           precise, err.data_ptr(), torch.cuda.current_stream().cuda_stream), "pnb_gemm_tc_test")
     torch.cuda.synchronize()
     assert int(err[0]) == 0
     return C
@@ -98,6 +98,9 @@ def test_gemm_tc_nn_nt(M, N, K):
     H = _gemm_tc(X, lda, 1, Wt, 1, N, M, N, K, N + 16, bias=bias, act=1)
     ref = torch.nn.functional.leaky_relu(X.double() @ Wt.double() + bias.double(), 0.01)
     assert _rel(H[:, :N], ref) < 2e-5 and torch.all(H[:, N:] == 7.0)
+    # the 3-part split (6 products) of the forward recompute: fp32-level
+    Hp = _gemm_tc(X, lda, 1, Wt, 1, N, M, N, K, N + 16, bias=bias, act=1, precise=1)
+    assert _rel(Hp[:, :N], ref) < 5e-7, _rel(Hp[:, :N], ref)
     # NT (dX = dZ W * LeakyReLU'(Y)): A = dZ [M x N], B(n=k_in, k=n_out) = Wt[k_in*N + n_out]; result [M x K]
     if K % 16 == 0:
         dZ = torch.randn(M, N, device="cuda", generator=g)

@@ -429,9 +429,11 @@ __device__ __forceinline__ float last_chunks_packed(const ShadeTcParams& p, uint
                 z[e] = y * wrow;
             }
         }
+        if (!(p.dbg_flags & 32)) {             // (dbg 32: timing experiment without the K-reduction, garbage results)
 #pragma unroll
-        for (int e = 0; e < 16; ++e) z[e] = seg_scan8(z[e], lane, st);
-        if (swrite) {
+            for (int e = 0; e < 16; ++e) z[e] = seg_scan8(z[e], lane, st);
+        }
+        if (swrite && !(p.dbg_flags & 64)) {   // (dbg 64: timing experiment without the h-bar stores)
             if (p.hbar_fmt) {       // the colour kernel's operand image (bf16 hi / lo, core-matrix layout): two 16-byte rows each
                 uint32_t hh[8], ll[8];
 #pragma unroll
@@ -837,20 +839,26 @@ __device__ __forceinline__ void build_pair_frozen(tc8::Smem& sm, const ShadeTcPa
 // One epilogue layer of a warp: chunks grp, grp+NGRP, ... (16 accumulator columns each): accumulator -> (+ bias or + pre[point]) ->
 // LeakyReLU -> bf16 hi/lo -> the same columns, one mbarrier arrive per chunk.  SWP: software-pipelined - the tcgen05.ld of the next
 // chunk is in flight under the conversion of this one, and the wait for this chunk's tcgen05.st is deferred behind the next conversion.
-template <int NGRP, bool SWP, bool FIRST>
-__device__ __forceinline__ void tc8_epi_layer(tc8::Smem& sm, uint32_t accb, int grp, const float* __restrict__ bias, const float4* __restrict__ pp) {
-    using namespace tc;
-    constexpr int NCH = 16 / NGRP;
-    constexpr int PF = NCH < 3 ? NCH : 3;         // chunks of `pre` in flight (FIRST)
-    const bool lane0 = (threadIdx.x & 31) == 0;   // ONE mbarrier arrive per warp and chunk: 32 same-address arrives serialise in the
-                                                  // shared-memory atomic unit (measured: they, not the MMAs, set the tile time)
-    float4 pf[PF][4];
-    if (FIRST) {
+template <int NGRP>
+struct Tc8Pf {                                    // chunks of `pre` in flight per epilogue thread (layer 1)
+    static constexpr int NCH = 16 / NGRP, PF = NCH < 3 ? NCH : 3;
+    float4 v[PF][4];
+    __device__ __forceinline__ void prefetch(const float4* __restrict__ pp, int grp) {
 #pragma unroll
         for (int i = 0; i < PF; ++i)
 #pragma unroll
-            for (int e = 0; e < 4; ++e) pf[i][e] = __ldg(pp + 4 * (grp + NGRP * i) + e);
+            for (int e = 0; e < 4; ++e) v[i][e] = __ldg(pp + 4 * (grp + NGRP * i) + e);
     }
+};
+template <int NGRP, bool SWP, bool FIRST>
+__device__ __forceinline__ void tc8_epi_layer(tc8::Smem& sm, uint32_t accb, int grp, const float* __restrict__ bias, const float4* __restrict__ pp,
+                                              Tc8Pf<NGRP>& pfs) {
+    using namespace tc;
+    constexpr int NCH = 16 / NGRP;
+    constexpr int PF = Tc8Pf<NGRP>::PF;
+    float4 (&pf)[PF][4] = pfs.v;
+    const bool lane0 = (threadIdx.x & 31) == 0;   // ONE mbarrier arrive per warp and chunk: 32 same-address arrives serialise in the
+                                                  // shared-memory atomic unit (measured: they, not the MMAs, set the tile time)
     uint32_t v[2][16];
     if (SWP) tmem_ld16(accb + (uint32_t)(16 * grp), v[0]);
 #pragma unroll
@@ -1083,16 +1091,18 @@ __global__ void __launch_bounds__(tc8::nthr(NGRP), 1) k_shade_tc8(ShadeTcParams 
             if (!TW(13, mbar_wait(&sm.bar_prow[t & 1], (uint32_t)(t >> 1) & 1u, p.err, 102))) { ok = false; break; }
             const int pi = max(sm.prow[t & 1][erow], 0);          // unused rows: any finite values (their outputs are never used)
             const float4* pp = reinterpret_cast<const float4*>(p.pre + (size_t)pi * 256);
+            Tc8Pf<NGRP> pfs;
+            pfs.prefetch(pp, grp);                               // in flight under the wait for the layer-1 MMAs
             if (!TW(14, mbar_wait(&sm.bar_acc_full, n_acc & 1u, p.err, 98))) { ok = false; break; }
             ++n_acc;
             tc_fence_after();
-            tc8_epi_layer<NGRP, SWP, true>(sm, tQ + tlane, grp, nullptr, pp);
+            tc8_epi_layer<NGRP, SWP, true>(sm, tQ + tlane, grp, nullptr, pp, pfs);
             TB(15);
             // ---- layers 2, 3
             for (int l = 1; l < 3 && ok; ++l, ++n_acc) {
                 if (!TW(16, mbar_wait(&sm.bar_acc_full, n_acc & 1u, p.err, 98))) { ok = false; break; }
                 tc_fence_after();
-                tc8_epi_layer<NGRP, SWP, false>(sm, ((l & 1) ? tP : tQ) + tlane, grp, p.bias[l], nullptr);
+                tc8_epi_layer<NGRP, SWP, false>(sm, ((l & 1) ? tP : tQ) + tlane, grp, p.bias[l], nullptr, pfs);
                 TB(17);
             }
             if (!ok) break;
@@ -1539,12 +1549,13 @@ extern "C" int pnb_shade_forward_tc(const pnb_query_t* q, const pnb_points_t* pt
         k_pack_scan<<<1, 1024, 0, stream>>>(p.q, cap, w.sc_quads, w.quad_first, w.pack_cnt);
         k_pack_place<<<(cap + 255) / 256, 256, 0, stream>>>(p.q, cap, w.sc_quads, w.quad_local, w.quad_first);
         if (frozen) {
-            // experiment flags (tools/tc_profile.py): dbg bit 3 = 8 epilogue warps instead of 16, dbg bit 4 = no software pipelining
-            const bool e8 = (p.dbg_flags & 8) != 0, noswp = (p.dbg_flags & 16) != 0;
-            if (e8 && noswp) k_shade_tc8<2, false><<<n_sm, tc8::nthr(2), smem_tc8, stream>>>(p);
-            else if (e8) k_shade_tc8<2, true><<<n_sm, tc8::nthr(2), smem_tc8, stream>>>(p);
-            else if (noswp) k_shade_tc8<4, false><<<n_sm, tc8::nthr(4), smem_tc8, stream>>>(p);
-            else k_shade_tc8<4, true><<<n_sm, tc8::nthr(4), smem_tc8, stream>>>(p);
+            // default: 8 epilogue warps, plain chunk loop (measured fastest, profiles/r02_tc8_variants.log); experiment flags of
+            // tools/tc_profile.py: dbg bit 3 = 16 epilogue warps, dbg bit 4 = software-pipelined epilogue chunks
+            const bool e16 = (p.dbg_flags & 8) != 0, swp = (p.dbg_flags & 16) != 0;
+            if (e16 && swp) k_shade_tc8<4, true><<<n_sm, tc8::nthr(4), smem_tc8, stream>>>(p);
+            else if (e16) k_shade_tc8<4, false><<<n_sm, tc8::nthr(4), smem_tc8, stream>>>(p);
+            else if (swp) k_shade_tc8<2, true><<<n_sm, tc8::nthr(2), smem_tc8, stream>>>(p);
+            else k_shade_tc8<2, false><<<n_sm, tc8::nthr(2), smem_tc8, stream>>>(p);
         }
         else k_shade_tc7<<<n_sm, tc7::NTHR, smem_tc7, stream>>>(p);
     }

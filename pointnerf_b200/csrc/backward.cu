@@ -96,6 +96,7 @@ __global__ void __launch_bounds__(256) k_gemm(const float* __restrict__ A, long 
 }
 
 struct GemmCtx {
+    bool precise_all;   // diagnostic (flags & 2): three-part split in every tensor-core GEMM
     bool tc;            // tensor-core GEMMs (default) or the fp32 CUDA-core tiles
     float* part;        // split-K workspace of the tensor-core dW GEMMs
     size_t part_bytes;
@@ -118,7 +119,7 @@ static int gemm_nn(const GemmCtx& cx, const float* A, long lda, const float* Bt,
     if (cx.tc && N % 16 == 0) {
         GemmTc g{};
         g.A = A; g.a_rs = lda; g.a_ks = 1; g.B = Bt; g.b_rs = 1; g.b_ks = ldb; g.C = C; g.ldc = ldc; g.M = M; g.N = N; g.K = K;
-        g.bias = bias; g.act = act; g.dact = nullptr; g.ldd = 0; g.dact_n = 0; g.err = cx.err;
+        g.bias = bias; g.act = act; g.dact = nullptr; g.ldd = 0; g.dact_n = 0; g.err = cx.err; g.precise = cx.precise_all;
         const int rc = gemm_tc(g, 1, nullptr, 0, 0, cx.st);
         if (rc == PNB_OK && act && layer >= 0)      // units within the tensor-core error of zero: fp32 re-evaluation (mask of the backward)
             k_recompute_fixup<<<(int)(((long)M * 32 + 255) / 256), 256, 0, cx.st>>>(A, lda, Bt, ldb, bias, C, ldc, M, N, K, cx.wmax + layer);
@@ -135,7 +136,7 @@ static int gemm_nt(const GemmCtx& cx, const float* dZ, long ldz, const float* Wt
     if (cx.tc && Kin % 16 == 0 && ldw % 4 == 0 && ldz % 4 == 0) {
         GemmTc g{};
         g.A = dZ; g.a_rs = ldz; g.a_ks = 1; g.B = Wt; g.b_rs = ldw; g.b_ks = 1; g.C = dX; g.ldc = ldx; g.M = M; g.N = Kin; g.K = Nout;
-        g.bias = nullptr; g.act = 0; g.dact = Y; g.ldd = ldy; g.dact_n = ny; g.err = cx.err;
+        g.bias = nullptr; g.act = 0; g.dact = Y; g.ldd = ldy; g.dact_n = ny; g.err = cx.err; g.precise = cx.precise_all;
         return gemm_tc(g, 1, nullptr, 0, 0, cx.st);
     }
     dim3 g((Kin + 63) / 64, (M + 127) / 128, 1);
@@ -150,7 +151,7 @@ static int gemm_tn_acc(const GemmCtx& cx, const float* X, long ldx, const float*
     if (cx.tc && Nout % 16 == 0 && ldw % 4 == 0) {
         GemmTc g{};
         g.A = X; g.a_rs = 1; g.a_ks = ldx; g.B = dZ; g.b_rs = 1; g.b_ks = ldz; g.C = dWt; g.ldc = ldw; g.M = Kin; g.N = Nout; g.K = M;
-        g.bias = nullptr; g.act = 0; g.dact = nullptr; g.ldd = 0; g.dact_n = 0; g.err = cx.err;
+        g.bias = nullptr; g.act = 0; g.dact = nullptr; g.ldd = 0; g.dact_n = 0; g.err = cx.err; g.precise = cx.precise_all;
         int splits = (M + 2047) / 2048;
         splits = splits < 2 ? 2 : (splits > SPLITK_MAX ? SPLITK_MAX : splits);
         return gemm_tc(g, splits, cx.part, cx.part_bytes, 1, cx.st);
@@ -633,7 +634,7 @@ extern "C" int pnb_shade_backward(const pnb_query_t* q, const pnb_points_t* pts,
     p.GS1 = L.GS1; p.GS2 = L.GS2; p.GS3 = L.GS3; p.dO3 = L.dO3; p.dsig = L.dsig; p.d_sigma_rgb = L.d_sigma_rgb;
     p.wa = mlp->w[4]; p.ba = mlp->b[4];
     const int wb = (S * 32 + 255) / 256;   // one warp per sample
-    GemmCtx cx{(flags & PNB_BWD_FP32_GEMM) == 0, L.part, PART_FLOATS * sizeof(float), d_err, st, L.wmax};
+    GemmCtx cx{(flags & 2) != 0, (flags & PNB_BWD_FP32_GEMM) == 0, L.part, PART_FLOATS * sizeof(float), d_err, st, L.wmax};
     if (cx.tc) {
         WnormArgs wa;
         const int li[7] = {0, 1, 2, 3, 5, 6, 7}, lk[7] = {288, 256, 272, 256, 288, 128, 128}, ln[7] = {256, 256, 256, 256, 128, 128, 128};

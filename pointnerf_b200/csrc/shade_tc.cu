@@ -58,7 +58,6 @@ struct ShadeTcParams {
     const uint32_t* quad_first;  // v7: first valid sample of every 32-row quadrant [n_quads + 1]
     const int* pack_cnt;         // v7: [0] = n_quads
     const float* pre;            // v8: per-point hoisted layer-1 pre-activation [N][256] (k_point_pre)
-    float* scratch;              // v8: per-CTA hand-off of the last epilogue, [gridDim.x][2][128 rows][256] fp32 (L2-resident ring)
     int hbar_fmt;                // 0: hbar[n_valid][256] fp32;  1: bf16 hi/lo A-operand blocks of k_color_tc2 (per 128 samples: 8 K blocks x {hi,lo} x [128x32])
 };
 __device__ __forceinline__ void prof_add(const ShadeTcParams& p, int slot, long long cyc) {
@@ -728,7 +727,7 @@ struct Smem {
     unsigned char xe_hi[2][tc::XE];
     unsigned char xe_lo[2][tc::XE];
     float wc[NWC][tc::TM];
-    float alpha_part[2][4][tc::TM];       // [tile parity][epilogue group]: partial alpha dot products (own slot each: summed in a fixed order)
+    float alpha_part[4][tc::TM];          // partial alpha dot products of the epilogue groups (own slot each: summed in a fixed order)
     int prow[2][tc::TM];                  // point index of every row (-1: unused row)
     uint32_t qhead[NWC][4], qfirst[NWC][4], qtotal[NWC][4];
     uint64_t bar_full[NSTAGE], bar_empty[NSTAGE], bar_a1_ready, bar_a1_free, bar_acc_full, bar_final, bar_alpha, bar_drain, bar_kblk[8], bar_prow[2];
@@ -840,66 +839,6 @@ __device__ __forceinline__ void build_pair_frozen(tc8::Smem& sm, const ShadeTcPa
 // One epilogue layer of a warp: chunks grp, grp+NGRP, ... (16 accumulator columns each): accumulator -> (+ bias or + pre[point]) ->
 // LeakyReLU -> bf16 hi/lo -> the same columns, one mbarrier arrive per chunk.  SWP: software-pipelined - the tcgen05.ld of the next
 // chunk is in flight under the conversion of this one, and the wait for this chunk's tcgen05.st is deferred behind the next conversion.
-// v8 last epilogue, DRAIN pass (the part that has to finish before layer 2 of the next tile may overwrite the accumulator region):
-// accumulator chunk -> + bias -> LeakyReLU -> partial alpha dot product (returned) -> x weight*conf -> fp32 row in the CTA's L2-resident
-// scratch.  The K-reduction over the rows of a sample and the h-bar stores run later, off the critical path (tc8_reduce_quadrant).
-// (The fused form - segmented warp scans + stores per chunk, last_chunks_packed - took ~2 k cycles per chunk: 11.8 k cycles per tile
-// of tensor-pipe idle time in front of every layer 2, profiles/r02_prof_v8_*.log.)
-template <int NG, int NCHUNK>
-__device__ __forceinline__ float tc8_drain_chunks(const ShadeTcParams& p, uint32_t accb, int G, float wrow, float* __restrict__ srow) {
-    using namespace tc;
-    const float* bias = p.bias[3];
-    float apart = 0.f;
-    uint32_t vv[2][16];
-    tmem_ld16(accb + (uint32_t)(16 * G), vv[0]);
-#pragma unroll
-    for (int i = 0; i < NCHUNK; ++i) {
-        const int c0 = 16 * (G + NG * i);
-        const uint32_t* v = vv[i & 1];
-        tmem_ld_wait();
-        if (i + 1 < NCHUNK) tmem_ld16(accb + (uint32_t)(c0 + 16 * NG), vv[(i + 1) & 1]);
-#pragma unroll
-        for (int e4 = 0; e4 < 4; ++e4) {
-            const float4 bb = __ldg(reinterpret_cast<const float4*>(bias + c0) + e4), ww = __ldg(reinterpret_cast<const float4*>(p.wa + c0) + e4);
-            float y0 = __uint_as_float(v[4 * e4]) + bb.x, y1 = __uint_as_float(v[4 * e4 + 1]) + bb.y;
-            float y2 = __uint_as_float(v[4 * e4 + 2]) + bb.z, y3 = __uint_as_float(v[4 * e4 + 3]) + bb.w;
-            y0 = fmaxf(y0, LEAKY * y0); y1 = fmaxf(y1, LEAKY * y1); y2 = fmaxf(y2, LEAKY * y2); y3 = fmaxf(y3, LEAKY * y3);
-            apart = fmaf(y0, ww.x, apart); apart = fmaf(y1, ww.y, apart); apart = fmaf(y2, ww.z, apart); apart = fmaf(y3, ww.w, apart);
-            __stcg(reinterpret_cast<float4*>(srow + c0) + e4, make_float4(y0 * wrow, y1 * wrow, y2 * wrow, y3 * wrow));
-        }
-    }
-    return apart;
-}
-// v8 last epilogue, REDUCE pass of one quadrant (one warp, lane = 8 of the 256 columns): h-bar[sample] = sum over the sample's rows
-// (ascending: the order depends on the sample alone) of the scratch rows -> bf16 hi / lo in the colour kernel's operand layout.
-__device__ __forceinline__ void tc8_reduce_quadrant(const ShadeTcParams& p, const float* __restrict__ sq, uint32_t head, int total, uint32_t first,
-                                                    int n_valid, int lane) {
-    using namespace tc;
-    uint32_t m = head;
-    int j = 0;
-    while (m) {
-        const int r0 = __ffs(m) - 1;
-        m &= m - 1;
-        const int r1 = m ? __ffs(m) - 1 : total;
-        const int sidx = (int)p.vorder[first + j];
-        ++j;
-        if (sidx >= n_valid) continue;
-        float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-        for (int r = r0; r < r1; ++r) {
-            const float4* src = reinterpret_cast<const float4*>(sq + r * 256 + lane * 8);
-            const float4 a = __ldcg(src), b = __ldcg(src + 1);
-            acc[0] += a.x; acc[1] += a.y; acc[2] += a.z; acc[3] += a.w; acc[4] += b.x; acc[5] += b.y; acc[6] += b.z; acc[7] += b.w;
-        }
-        uint32_t hh[4], ll[4];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) split_bf16x2(acc[2 * e], acc[2 * e + 1], hh[e], ll[e]);
-        unsigned char* dst = reinterpret_cast<unsigned char*>(p.hbar) + ((size_t)(sidx >> 7) * 8 + (lane >> 2)) * (2 * 8192) +
-                             tile_offset_bytes<LAYOUT_NONE>(sidx & 127, (lane & 3) * 8);
-        *reinterpret_cast<uint4*>(dst) = make_uint4(hh[0], hh[1], hh[2], hh[3]);
-        *reinterpret_cast<uint4*>(dst + 8192) = make_uint4(ll[0], ll[1], ll[2], ll[3]);
-    }
-}
-
 template <int NGRP>
 struct Tc8Pf {                                    // chunks of `pre` in flight per epilogue thread (layer 1)
     static constexpr int NCH = 16 / NGRP, PF = NCH < 3 ? NCH : 3;
@@ -1125,24 +1064,19 @@ __global__ void __launch_bounds__(tc8::nthr(NGRP), 1) k_shade_tc8(ShadeTcParams 
                 const int sidx = qr.live ? (int)p.vorder[sm.qfirst[tf & 1][qw] + qr.j] : 0;
                 const bool swrite = qr.is_end && sidx < n_valid;
                 const float wrow = sm.wc[tf & 1][row];
-                float* sbuf = p.scratch + ((size_t)blockIdx.x * 2 + (size_t)(tf & 1)) * (TM * 256);
-                const float apart = tc8_drain_chunks<NG4, NCH4_B>(p, tP + tlane, 0, wrow, sbuf + row * 256);
+                const float apart = last_chunks_packed<NG4, NCH4_B>(p, tP + tlane, 0, wrow, qr.st, swrite, sidx, lane);
                 tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&sm.bar_drain);                 // this warp's accumulator reads are complete
                 TB(11);
-                if (!TW(12, mbar_wait(&sm.bar_alpha, (uint32_t)tf & 1u, p.err, 100))) { ok = false; break; }      // the epilogue warps' shares (alpha partials, scratch rows)
+                if (!TW(12, mbar_wait(&sm.bar_alpha, (uint32_t)tf & 1u, p.err, 100))) { ok = false; break; }      // the epilogue warps' partial sums
                 float a = apart;
 #pragma unroll
-                for (int gq = 0; gq < NGRP; ++gq) a += sm.alpha_part[tf & 1][gq][row];          // fixed order: deterministic
+                for (int gq = 0; gq < NGRP; ++gq) a += sm.alpha_part[gq][row];          // fixed order: deterministic
                 a += __ldg(p.ba) - 1.0f;
                 const float sp = a > 20.f ? a : log1pf(expf(a));
                 const float zz = seg_scan8(sp * wrow, lane, qr.st);
                 if (swrite) p.sigma[sidx] = zz;
-                __threadfence_block();
                 __syncwarp();
-                tc8_reduce_quadrant(p, sbuf + qw * 32 * 256, sm.qhead[tf & 1][qw], (int)sm.qtotal[tf & 1][qw], sm.qfirst[tf & 1][qw], n_valid, lane);
-                TB(21);
+                if (lane == 0) mbar_arrive(&sm.bar_drain);                 // after the alpha_part reads
             }
         }
     } else {
@@ -1175,11 +1109,11 @@ __global__ void __launch_bounds__(tc8::nthr(NGRP), 1) k_shade_tc8(ShadeTcParams 
             {   // this warp's share of the LAST epilogue (chunk groups 1..NGRP of NGRP+1; the builder warps take group 0)
                 if (!TW(18, mbar_wait(&sm.bar_final, (uint32_t)t & 1u, p.err, 101))) { ok = false; break; }
                 tc_fence_after();
-                float* srow = p.scratch + (((size_t)blockIdx.x * 2 + (size_t)(t & 1)) * TM + erow) * 256;
-                const float apart = tc8_drain_chunks<NG4, NCH4_E>(p, tP + tlane, 1 + grp, sm.wc[t & 1][erow], srow);
+                const QuadRow qr = quad_row(sm.qhead[t & 1][quad], (int)sm.qtotal[t & 1][quad], lane);
+                const int sidx = qr.live ? (int)p.vorder[sm.qfirst[t & 1][quad] + qr.j] : 0;
+                const float apart = last_chunks_packed<NG4, NCH4_E>(p, tP + tlane, 1 + grp, sm.wc[t & 1][erow], qr.st, qr.is_end && sidx < n_valid, sidx, lane);
                 tc_fence_before();
-                sm.alpha_part[t & 1][grp][erow] = apart;
-                __threadfence_block();                                      // scratch rows visible to the reducing warp
+                sm.alpha_part[grp][erow] = apart;
                 __syncwarp();
                 TB(19);
                 if (lane == 0) { mbar_arrive(&sm.bar_alpha); mbar_arrive(&sm.bar_drain); }
@@ -1532,12 +1466,9 @@ extern "C" int pnb_point_pre(const pnb_points_t* pts, const pnb_mlp_t* mlp, floa
 }
 
 static size_t pack_sc_max(int cap) { return (size_t)cap / tc7::PACK_S + 3; }
-constexpr int kMaxCtas = 160;                                         // persistent kernels: one CTA per SM (148 on B200)
-constexpr size_t kScratchFloats = (size_t)kMaxCtas * 2 * 128 * 256;   // k_shade_tc8: per-CTA last-epilogue hand-off (42 MB, stays in L2)
 namespace {
 struct TcWs {   // carve-up of the caller's workspace (all sizes from max_valid_samples; the kernels read the live counts on the device)
     float* hbar; float* sigma; uint32_t* sc_quads; uint32_t* quad_local; uint32_t* quad_first; uint32_t* vorder; unsigned char* vcntp; int* pack_cnt;
-    float* scratch;
     TcWs(void* ws, size_t ws_bytes, int cap) {
         Carver c(ws, ws_bytes);
         hbar = c.take<float>(((size_t)cap + 127) / 128 * 128 * 256);   // whole 128-sample colour tiles
@@ -1548,14 +1479,13 @@ struct TcWs {   // carve-up of the caller's workspace (all sizes from max_valid_
         vorder = c.take<uint32_t>((size_t)cap + 2);
         vcntp = c.take<unsigned char>((size_t)cap + 16);
         pack_cnt = c.take<int>(4);
-        scratch = c.take<float>(kScratchFloats);
     }
 };
 }  // namespace
 extern "C" size_t pnb_shade_tc_bytes(int max_valid_samples) {
     const size_t cap = (size_t)max_valid_samples;
     return align_up((cap + 127) / 128 * 128 * 256 * sizeof(float)) + align_up(cap * sizeof(float)) + align_up(pack_sc_max(max_valid_samples) * 4) +
-           3 * align_up((cap + 2) * 4) + align_up(cap + 16) + align_up(16) + align_up(kScratchFloats * sizeof(float)) + 256;
+           3 * align_up((cap + 2) * 4) + align_up(cap + 16) + align_up(16) + 256;
 }
 // diagnostics / tests: device pointers of the row-packing tables inside a workspace laid out for max_valid_samples
 extern "C" int pnb_shade_tc_tables(void* ws, size_t ws_bytes, int max_valid_samples, void** vorder, void** vcntp, void** quad_first, void** pack_cnt) {
@@ -1612,8 +1542,6 @@ extern "C" int pnb_shade_forward_tc(const pnb_query_t* q, const pnb_points_t* pt
     p.dbg_flags = (flags >> 8) & 0xff;
     p.vcnt = w.vcntp; p.vorder = w.vorder; p.quad_first = w.quad_first; p.pack_cnt = w.pack_cnt;
     p.pre = d_point_pre;
-    p.scratch = w.scratch;
-    PNB_REQUIRE(n_sm <= kMaxCtas, PNB_ERR_UNSUPPORTED, "pnb_shade_forward_tc: %d SMs (scratch sized for %d)", n_sm, kMaxCtas);
     p.hbar_fmt = 1;                                           // h-bar in the colour kernel's operand format
     if (flags & PNB_TC_PAIRS) {
         const int cap = max_valid_samples, n_sc = (int)pack_sc_max(cap);

@@ -39,12 +39,12 @@ print("per-CTA cycles: min %.2f M  max %.2f M  mean %.2f M -> %.1f k cycles per 
 print("per-CTA kernel cycles (M) @smid:", " ".join("%.1f@%d" % ((v & 0xffffffffffff) / 1e6, v >> 48) for v in per))
 
 if os.environ.get("PNB_PROF") and net.frozen_ok:
-    c = net._err.cpu().view(torch.int64)[1:23].tolist()
+    c = net._err.cpu().view(torch.int64)[1:22].tolist()
     names = ["loader: wait empty", "issuer: wait acc_full (l>0)", "issuer: wait final (l=0)", "issuer: wait a1_ready", "issuer: wait drain",
              "issuer: wait kblk (slow path)", "issuer: wait weights (slow path)", "issuer: MMA issue + commits + fast probes",
              "builder q0: wait a1_free", "builder q0: build", "builder q0: wait final", "builder q0: last-epilogue share", "builder q0: wait alpha",
              "epi warp 0: wait prow", "epi warp 0: wait acc_full (E1)", "epi warp 0: E1 busy", "epi warp 0: wait acc_full (E2,E3)", "epi warp 0: E2+E3 busy",
-             "epi warp 0: wait final", "epi warp 0: last-epilogue share", "kernel total (thread 0)", "builder q0: sigma + K-reduction + h-bar stores"]
+             "epi warp 0: wait final", "epi warp 0: last-epilogue share", "kernel total (thread 0)"]
     tiles0 = (n_tiles - 1) // 148 + 1
     print("block 0 accounting (%d tiles), cycles per tile:" % tiles0)
     for n, v in zip(names, c):

@@ -402,19 +402,33 @@ __global__ void __launch_bounds__(256) k_pack_place(pnb_query_t q, int cap, cons
 // Last epilogue with packed rows, one warp's share (chunks G, G+NG, ...): +bias, LeakyReLU, partial alpha dot product (returned),
 // weight*conf scaling, then the K-reduction over the rows of each sample as a segmented inclusive scan (segments = samples,
 // <= 8 lanes, first lane st); the last row of a sample (swrite) holds the sums and writes h-bar.
-template <int NG, int NCHUNK>
-__device__ __forceinline__ float last_chunks_packed(const ShadeTcParams& p, uint32_t accb, int G, float wrow, int st, bool swrite, int sidx, int lane) {
+// EARLY (v8): ALL chunks of this warp are read into registers first and `drain_bar` is signalled right away - the accumulator region
+// is then free for layer 2 of the next tile ~2 k cycles after the last MMA instead of after the whole reduction (~10 k).
+template <int NG, int NCHUNK, bool EARLY = false>
+__device__ __forceinline__ float last_chunks_packed(const ShadeTcParams& p, uint32_t accb, int G, float wrow, int st, bool swrite, int sidx, int lane,
+                                                    uint64_t* drain_bar = nullptr) {
     using namespace tc;
     const float* bias = p.bias[3];
     float apart = 0.f;
-    uint32_t vv[2][16];
-    tmem_ld16(accb + (uint32_t)(16 * G), vv[0]);
+    uint32_t vv[EARLY ? NCHUNK : 2][16];
+    if (EARLY) {
+#pragma unroll
+        for (int i = 0; i < NCHUNK; ++i) tmem_ld16(accb + (uint32_t)(16 * (G + NG * i)), vv[i]);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(drain_bar);
+    } else {
+        tmem_ld16(accb + (uint32_t)(16 * G), vv[0]);
+    }
 #pragma unroll
     for (int i = 0; i < NCHUNK; ++i) {
         const int c0 = 16 * (G + NG * i);
-        const uint32_t* v = vv[i & 1];
-        tmem_ld_wait();
-        if (i + 1 < NCHUNK) tmem_ld16(accb + (uint32_t)(c0 + 16 * NG), vv[(i + 1) & 1]);      // next chunk in flight under this one's math
+        const uint32_t* v = vv[EARLY ? i : (i & 1)];
+        if (!EARLY) {
+            tmem_ld_wait();
+            if (i + 1 < NCHUNK) tmem_ld16(accb + (uint32_t)(c0 + 16 * NG), vv[(i + 1) & 1]);      // next chunk in flight under this one's math
+        }
         float z[16];
 #pragma unroll
         for (int e4 = 0; e4 < 4; ++e4) {
@@ -727,7 +741,7 @@ struct Smem {
     unsigned char xe_hi[2][tc::XE];
     unsigned char xe_lo[2][tc::XE];
     float wc[NWC][tc::TM];
-    float alpha_part[4][tc::TM];          // partial alpha dot products of the epilogue groups (own slot each: summed in a fixed order)
+    float alpha_part[2][4][tc::TM];       // [tile parity][epilogue group] partial alpha dot products (own slot each: summed in a fixed order)
     int prow[2][tc::TM];                  // point index of every row (-1: unused row)
     uint32_t qhead[NWC][4], qfirst[NWC][4], qtotal[NWC][4];
     uint64_t bar_full[NSTAGE], bar_empty[NSTAGE], bar_a1_ready, bar_a1_free, bar_acc_full, bar_final, bar_alpha, bar_drain, bar_kblk[8], bar_prow[2];
@@ -1064,19 +1078,16 @@ __global__ void __launch_bounds__(tc8::nthr(NGRP), 1) k_shade_tc8(ShadeTcParams 
                 const int sidx = qr.live ? (int)p.vorder[sm.qfirst[tf & 1][qw] + qr.j] : 0;
                 const bool swrite = qr.is_end && sidx < n_valid;
                 const float wrow = sm.wc[tf & 1][row];
-                const float apart = last_chunks_packed<NG4, NCH4_B>(p, tP + tlane, 0, wrow, qr.st, swrite, sidx, lane);
-                tc_fence_before();
+                const float apart = last_chunks_packed<NG4, NCH4_B, true>(p, tP + tlane, 0, wrow, qr.st, swrite, sidx, lane, &sm.bar_drain);
                 TB(11);
                 if (!TW(12, mbar_wait(&sm.bar_alpha, (uint32_t)tf & 1u, p.err, 100))) { ok = false; break; }      // the epilogue warps' partial sums
                 float a = apart;
 #pragma unroll
-                for (int gq = 0; gq < NGRP; ++gq) a += sm.alpha_part[gq][row];          // fixed order: deterministic
+                for (int gq = 0; gq < NGRP; ++gq) a += sm.alpha_part[tf & 1][gq][row];          // fixed order: deterministic
                 a += __ldg(p.ba) - 1.0f;
                 const float sp = a > 20.f ? a : log1pf(expf(a));
                 const float zz = seg_scan8(sp * wrow, lane, qr.st);
                 if (swrite) p.sigma[sidx] = zz;
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&sm.bar_drain);                 // after the alpha_part reads
             }
         }
     } else {
@@ -1111,12 +1122,12 @@ __global__ void __launch_bounds__(tc8::nthr(NGRP), 1) k_shade_tc8(ShadeTcParams 
                 tc_fence_after();
                 const QuadRow qr = quad_row(sm.qhead[t & 1][quad], (int)sm.qtotal[t & 1][quad], lane);
                 const int sidx = qr.live ? (int)p.vorder[sm.qfirst[t & 1][quad] + qr.j] : 0;
-                const float apart = last_chunks_packed<NG4, NCH4_E>(p, tP + tlane, 1 + grp, sm.wc[t & 1][erow], qr.st, qr.is_end && sidx < n_valid, sidx, lane);
-                tc_fence_before();
-                sm.alpha_part[grp][erow] = apart;
+                const float apart = last_chunks_packed<NG4, NCH4_E, true>(p, tP + tlane, 1 + grp, sm.wc[t & 1][erow], qr.st, qr.is_end && sidx < n_valid, sidx, lane,
+                                                                          &sm.bar_drain);
+                sm.alpha_part[t & 1][grp][erow] = apart;
                 __syncwarp();
                 TB(19);
-                if (lane == 0) { mbar_arrive(&sm.bar_alpha); mbar_arrive(&sm.bar_drain); }
+                if (lane == 0) mbar_arrive(&sm.bar_alpha);
             }
         }
     }

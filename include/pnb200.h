@@ -214,9 +214,13 @@ int pnb_shade_tc_tables(void* ws, size_t ws_bytes, int max_valid_samples, void**
  * caller zero-initialises all accumulators).  d_sigma_rgb_fwd: the forward's per-candidate (sigma, rgb) buffer.
  * n_valid: host copy of counters[PNB_QC_N_VALID].  ws >= pnb_backward_bytes.  The activations are recomputed and every layer
  * GEMM (recompute, dX, dW) runs on the tensor cores (tcgen05, BF16x3 split, fp32 accumulate; dW by a deterministic split-K);
- * flags & PNB_BWD_FP32_GEMM: hand-written fp32 CUDA-core GEMM tiles instead (parity reference).  d_err: device int32,
+ * the recomputed pre-activations carry the BF16x3 error, so ~1e-6 of the LeakyReLU masks differ from an fp32 forward's (each changes
+ * one pair's gradient by ~1/256; see the flags).  d_err: device int32,
  * set non-zero if a bounded pipeline wait of the tensor-core GEMMs expires (results invalid). */
-enum { PNB_BWD_FP32_GEMM = 1 };
+enum {
+    PNB_BWD_FP32_GEMM = 1,      /* every GEMM on the fp32 CUDA-core tiles (parity reference of the tensor-core engine) */
+    PNB_BWD_FP32_RECOMPUTE = 4  /* forward recompute on the fp32 tiles (LeakyReLU masks of an fp32 forward), dX / dW on the tensor cores */
+};
 size_t pnb_backward_bytes(int n_valid, int cap_samples);
 int pnb_shade_backward(const pnb_query_t* q, const pnb_points_t* pts, const pnb_mlp_t* mlp, const pnb_shade_opts_t* opts,
                        const float* d_sigma_rgb_fwd, const float* d_ray_color, int n_valid, float* d_emb, float* d_color,

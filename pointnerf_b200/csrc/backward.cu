@@ -11,10 +11,13 @@
 // Training batches are small (~2e4 valid samples), so the per-layer activations are recomputed into an HBM workspace and the
 // layer gradients are plain GEMMs: forward recompute  H = act(X W^T + b),  dX = (dZ W) * act'  and  dW += X^T dZ  all run on
 // the tensor cores (gemm_tc.cu: tcgen05 + TMEM, BF16x3 split, fp32 accumulate; the activation derivative is fused into the
-// dX epilogue, dW is a deterministic split-K).  The LeakyReLU masks of the backward must be those of an fp32 forward: a unit whose
-// recomputed pre-activation lies within the tensor-core error of zero (BF16x3: ~2^-16 |x||w|; even a three-part split stops at
-// ~1e-6, the accumulation precision of the tensor core, tests/test_gpu_umma.py) would flip its mask and change that pair's gradient
-// by ~1/256 - k_recompute_fixup re-evaluates exactly those few units (~1e-4 of them) with fp32 FMAs.  PNB_BWD_FP32_GEMM selects the hand-written fp32 CUDA-core tiles instead
+// dX epilogue, dW is a deterministic split-K).
+// LeakyReLU masks: the recomputed pre-activations carry the BF16x3 error (~1e-5 relative), so ~1e-6 of the units (those whose
+// pre-activation is that close to zero) get the other mask than an fp32 forward would give them; each such unit changes ONE pair's
+// gradient by ~1/256 (measure-zero for the optimisation, visible in a max-abs comparison with fp32 autograd: tools/bwd_diag2.py lists
+// them).  A fix-up of the near-zero units cannot help - the perturbation comes from the inputs of the layer - and a three-part split
+// stops at ~1e-6 (tests/test_gpu_umma.py).  PNB_BWD_FP32_RECOMPUTE keeps the recompute on the fp32 CUDA-core tiles (fp32-faithful
+// masks, dX / dW still on the tensor cores); PNB_BWD_FP32_GEMM selects the hand-written fp32 CUDA-core tiles instead
 // (the parity reference of the tensor-core path; always used for the 128 -> 3 colour head).
 #include "common.cuh"
 #include "gemm_tc.cuh"
@@ -102,28 +105,22 @@ struct GemmCtx {
     size_t part_bytes;
     int* err;
     cudaStream_t st;
-    const float* wmax;  // [7] largest column norm of every recomputed layer (k_wnorm_max)
+    bool fp32_recompute;   // PNB_BWD_FP32_RECOMPUTE: the forward recompute on the fp32 CUDA-core tiles (fp32-faithful LeakyReLU masks)
 };
 constexpr int SPLITK_MAX = 64;
 constexpr size_t PART_FLOATS = (size_t)SPLITK_MAX * 288 * 256;
 
 __global__ void __launch_bounds__(256) k_lrelu_bwd(float* __restrict__ dY, const float* __restrict__ Y, long ldy, long ldd, int M, int N);
-__global__ void __launch_bounds__(256) k_recompute_fixup(const float* __restrict__ X, long lda, const float* __restrict__ Wt, long ldb,
-                                                         const float* __restrict__ bias, float* __restrict__ H, long ldc, int M, int N, int K,
-                                                         const float* __restrict__ wmax);
 
 // C[M x N] = act(A[M x K] * Bt[K x N] + bias)
 static int gemm_nn(const GemmCtx& cx, const float* A, long lda, const float* Bt, long ldb, float* C, long ldc, int M, int N, int K,
-                   const float* bias, int act, int layer = -1) {
+                   const float* bias, int act) {
     if (M <= 0) return PNB_OK;
-    if (cx.tc && N % 16 == 0) {
+    if (cx.tc && !cx.fp32_recompute && N % 16 == 0) {
         GemmTc g{};
         g.A = A; g.a_rs = lda; g.a_ks = 1; g.B = Bt; g.b_rs = 1; g.b_ks = ldb; g.C = C; g.ldc = ldc; g.M = M; g.N = N; g.K = K;
         g.bias = bias; g.act = act; g.dact = nullptr; g.ldd = 0; g.dact_n = 0; g.err = cx.err; g.precise = cx.precise_all;
-        const int rc = gemm_tc(g, 1, nullptr, 0, 0, cx.st);
-        if (rc == PNB_OK && act && layer >= 0)      // units within the tensor-core error of zero: fp32 re-evaluation (mask of the backward)
-            k_recompute_fixup<<<(int)(((long)M * 32 + 255) / 256), 256, 0, cx.st>>>(A, lda, Bt, ldb, bias, C, ldc, M, N, K, cx.wmax + layer);
-        return rc;
+        return gemm_tc(g, 1, nullptr, 0, 0, cx.st);
     }
     dim3 g((N + 63) / 64, (M + 127) / 128, 1);
     k_gemm<false><<<g, 256, 0, cx.st>>>(A, lda, 1, Bt, ldb, 1, C, ldc, M, N, K, K, bias, act);
@@ -168,49 +165,6 @@ __global__ void __launch_bounds__(256) k_lrelu_bwd(float* __restrict__ dY, const
     int m = (int)(i / N), n = (int)(i - (long)m * N);
     float y = Y[m * ldy + n];
     dY[m * ldd + n] *= (y > 0.f ? 1.0f : LEAKY);
-}
-
-// wmax[i] = largest column norm of the W^T buffer of layer i (K_pad x N): the |w| of the error bound of k_recompute_fixup
-struct WnormArgs { const float* w[7]; int K[7], N[7]; float* out; };
-__global__ void __launch_bounds__(256) k_wnorm_max(WnormArgs a) {
-    __shared__ float red[256];
-    const int i = blockIdx.x, n = threadIdx.x;
-    float s = 0.f;
-    if (n < a.N[i])
-        for (int k = 0; k < a.K[i]; ++k) { const float v = a.w[i][(size_t)k * a.N[i] + n]; s = fmaf(v, v, s); }
-    red[n] = sqrtf(s);
-    __syncthreads();
-    for (int o = 128; o > 0; o >>= 1) { if (n < o) red[n] = fmaxf(red[n], red[n + o]); __syncthreads(); }
-    if (n == 0) a.out[i] = red[0];
-}
-// One warp per row of H = LeakyReLU(X Wt + b) computed on the tensor cores: every unit whose pre-activation is within the error
-// bound of the BF16x3 product of zero (|z| < 4e-5 |x|_2 wmax) is re-evaluated with fp32 FMAs, so that the sign - the LeakyReLU
-// mask of the backward - is that of an fp32 forward.
-__global__ void __launch_bounds__(256) k_recompute_fixup(const float* __restrict__ X, long lda, const float* __restrict__ Wt, long ldb,
-                                                         const float* __restrict__ bias, float* __restrict__ H, long ldc, int M, int N, int K,
-                                                         const float* __restrict__ wmax) {
-    const int row = (int)(((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
-    if (row >= M) return;
-    const float* x = X + (long)row * lda;
-    float s = 0.f;
-    for (int k = lane; k < K; k += 32) { const float v = x[k]; s = fmaf(v, v, s); }
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    const float tol = 4e-5f * sqrtf(s) * __ldg(wmax) + 1e-30f;
-    float* h = H + (long)row * ldc;
-    for (int c0 = 0; c0 < N; c0 += 32) {
-        const int c = c0 + lane;
-        float z = 1e30f;
-        if (c < N) { const float y = h[c]; z = y > 0.f ? y : y * 100.0f; }
-        uint32_t m = __ballot_sync(0xffffffffu, fabsf(z) < tol);
-        while (m) {
-            const int cc = c0 + __ffs(m) - 1;
-            m &= m - 1;
-            float acc = 0.f;
-            for (int k = lane; k < K; k += 32) acc = fmaf(x[k], __ldg(Wt + (long)k * ldb + cc), acc);
-            for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-            if (lane == 0) { const float zz = acc + __ldg(bias + cc); h[cc] = zz > 0.f ? zz : LEAKY * zz; }
-        }
-    }
 }
 
 // db[n] += sum_m dZ[m][n]
@@ -577,7 +531,6 @@ struct Layout {
     int* pidx;
     float4* d_sigma_rgb;
     float* part;
-    float* wmax;
     size_t bytes;
 };
 static Layout carve(void* ws, size_t cap, int max_valid, int cap_samples) {
@@ -595,7 +548,6 @@ static Layout carve(void* ws, size_t cap, int max_valid, int cap_samples) {
     L.dO3 = c.take<float>(S * 4); L.dsig = c.take<float>(S);
     L.d_sigma_rgb = c.take<float4>((size_t)(cap_samples > 0 ? cap_samples : 1));
     L.part = c.take<float>(PART_FLOATS);
-    L.wmax = c.take<float>(8);
     L.bytes = align_up(c.off);
     return L;
 }
@@ -634,25 +586,18 @@ extern "C" int pnb_shade_backward(const pnb_query_t* q, const pnb_points_t* pts,
     p.GS1 = L.GS1; p.GS2 = L.GS2; p.GS3 = L.GS3; p.dO3 = L.dO3; p.dsig = L.dsig; p.d_sigma_rgb = L.d_sigma_rgb;
     p.wa = mlp->w[4]; p.ba = mlp->b[4];
     const int wb = (S * 32 + 255) / 256;   // one warp per sample
-    GemmCtx cx{(flags & 2) != 0, (flags & PNB_BWD_FP32_GEMM) == 0, L.part, PART_FLOATS * sizeof(float), d_err, st, L.wmax};
-    if (cx.tc) {
-        WnormArgs wa;
-        const int li[7] = {0, 1, 2, 3, 5, 6, 7}, lk[7] = {288, 256, 272, 256, 288, 128, 128}, ln[7] = {256, 256, 256, 256, 128, 128, 128};
-        for (int i = 0; i < 7; ++i) { wa.w[i] = mlp->w[li[i]]; wa.K[i] = lk[i]; wa.N[i] = ln[i]; }
-        wa.out = L.wmax;
-        k_wnorm_max<<<7, 256, 0, st>>>(wa);
-    }
+    GemmCtx cx{(flags & 2) != 0, (flags & PNB_BWD_FP32_GEMM) == 0, L.part, PART_FLOATS * sizeof(float), d_err, st, (flags & PNB_BWD_FP32_RECOMPUTE) != 0};
     PNB_REQUIRE(!cx.tc || d_err, PNB_ERR_INVALID, "pnb_shade_backward: the tensor-core path needs d_err");
     // ---------------- forward recompute ----------------
     k_bwd_build<<<wb, 256, 0, st>>>(p);
-    gemm_nn(cx, L.X1, 288, mlp->w[0], 256, L.H1, 256, P, 256, 288, mlp->b[0], 1, 0);
-    gemm_nn(cx, L.H1, 256, mlp->w[1], 256, L.X3, 272, P, 256, 256, mlp->b[1], 1, 1);   // H2 into X3[:, :256]
-    gemm_nn(cx, L.X3, 272, mlp->w[2], 256, L.H3, 256, P, 256, 272, mlp->b[2], 1, 2);
-    gemm_nn(cx, L.H3, 256, mlp->w[3], 256, L.H4, 256, P, 256, 256, mlp->b[3], 1, 3);
+    gemm_nn(cx, L.X1, 288, mlp->w[0], 256, L.H1, 256, P, 256, 288, mlp->b[0], 1);
+    gemm_nn(cx, L.H1, 256, mlp->w[1], 256, L.X3, 272, P, 256, 256, mlp->b[1], 1);   // H2 into X3[:, :256]
+    gemm_nn(cx, L.X3, 272, mlp->w[2], 256, L.H3, 256, P, 256, 272, mlp->b[2], 1);
+    gemm_nn(cx, L.H3, 256, mlp->w[3], 256, L.H4, 256, P, 256, 256, mlp->b[3], 1);
     k_bwd_reduce_fwd<<<wb, 256, 0, st>>>(p);
-    gemm_nn(cx, L.CX, 288, mlp->w[5], 128, L.C1, 128, S, 128, 288, mlp->b[5], 1, 4);
-    gemm_nn(cx, L.C1, 128, mlp->w[6], 128, L.C2, 128, S, 128, 128, mlp->b[6], 1, 5);
-    gemm_nn(cx, L.C2, 128, mlp->w[7], 128, L.C3, 128, S, 128, 128, mlp->b[7], 1, 6);
+    gemm_nn(cx, L.CX, 288, mlp->w[5], 128, L.C1, 128, S, 128, 288, mlp->b[5], 1);
+    gemm_nn(cx, L.C1, 128, mlp->w[6], 128, L.C2, 128, S, 128, 128, mlp->b[6], 1);
+    gemm_nn(cx, L.C2, 128, mlp->w[7], 128, L.C3, 128, S, 128, 128, mlp->b[7], 1);
     gemm_nn(cx, L.C3, 128, mlp->w[8], 3, L.O3, 4, S, 3, 128, mlp->b[8], 0);          // N = 3: CUDA cores
     // ---------------- backward ----------------
     k_bwd_head<<<(S + 255) / 256, 256, 0, st>>>(p);

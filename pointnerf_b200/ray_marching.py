@@ -274,7 +274,9 @@ class _RenderFn(torch.autograd.Function):
         ptr = lambda t: t.data_ptr() if t is not None else None
         if getattr(mod, "_bwd_err", None) is None or mod._bwd_err.device != dev:
             mod._bwd_err = torch.zeros(4, dtype=torch.int32, device=dev)     # checked (synchronising) by check_errors()
-        flags = int(getattr(mod.opt, "pnb_bwd_fp32", 0))      # 1: fp32 CUDA-core GEMMs; 2 (diagnostic): three-part split in every GEMM
+        # opt.pnb_bwd_fp32: 0 tensor-core GEMMs (default) | 1 fp32 CUDA-core GEMMs | 4 fp32 recompute + tensor-core dX / dW
+        # (fp32-faithful LeakyReLU masks) | 2 (diagnostic) three-part split in every tensor-core GEMM
+        flags = int(getattr(mod.opt, "pnb_bwd_fp32", 0))
         _lib.check(lib.pnb_shade_backward(_lib.C.byref(q.desc), _lib.C.byref(pts), _lib.C.byref(mlp), _lib.C.byref(ctx.o),
                                           ctx.sigma_rgb.data_ptr(), g_color.data_ptr(), int(ctx.n_valid), ptr(outs[0]),
                                           ptr(outs[1]), ptr(outs[2]), ptr(outs[3]), wp, bp, mod._bwd_ws.data_ptr(),

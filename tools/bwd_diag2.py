@@ -55,3 +55,23 @@ for k, (off, n) in L.items():
     print("%-5s scale %.3e  max|tc-fp32|/scale %.3e  at row %d col %d (tc %.6e fp32 %.6e)  rows with rel diff > 1e-3: %d" % (
         k, float(sc), float(d.max() / sc), i // w, i % w, float(a[i]), float(b[i]),
         int(((d.view(-1, w).max(1)[0]) > 1e-3 * sc).sum()) if n % w == 0 else -1))
+
+# sign disagreements of the recomputed activations (LeakyReLU masks of the backward)
+pid_off, pid_n = L["pidx"]
+pidx = ws[0][pid_off:pid_off + pid_n * 4].view(torch.int32)
+for k in ("H1", "X3", "H3", "H4", "C1", "C2", "C3"):
+    off, n = L[k]
+    w = ld[k]
+    a = ws[0][off:off + n * 4].view(torch.float32).view(-1, w)
+    b = ws[1][off:off + n * 4].view(torch.float32).view(-1, w)
+    ncol = 256 if k == "X3" else w
+    flip = ((a[:, :ncol] > 0) != (b[:, :ncol] > 0))
+    idx = flip.nonzero()
+    print("%s: %d sign flips of %d units" % (k, idx.shape[0], a.shape[0] * ncol))
+    for r_, c_ in idx[:8].tolist():
+        print("   row %d (point %s) col %d: tc %.3e fp32 %.3e" % (r_, int(pidx[r_]) if k in ("H1", "X3", "H3", "H4") else "-", c_, float(a[r_, c_]), float(b[r_, c_])))
+off, n = L["G1"]
+a = ws[0][off:off + n * 4].view(torch.float32).view(-1, 288); b = ws[1][off:off + n * 4].view(torch.float32).view(-1, 288)
+d = (a - b).abs().max(1)[0]
+top = torch.argsort(-d)[:8]
+print("rows of G1 (dX1) with the largest tc-vs-fp32 difference:", [(int(r_), int(pidx[r_]), float(d[r_])) for r_ in top])

@@ -57,6 +57,16 @@ def render(points, mlp, raydir, campos, camrotc2w, near, far, vsize, vscale, ker
     if not want_shade:
         return out
     mask = torch.from_numpy(q["ray_mask"]) > 0
+    if int(mask.sum()) == 0:
+        # no ray keeps a neighbour: the reference returns empty R' tensors (neural_points_volumetric_model.py:352-361) and fill_invalid
+        # paints the whole chunk with the background
+        R = mask.shape[0]
+        bg = torch.as_tensor(bg_color).to(dtype)
+        out.update(ray_color=torch.zeros(0, 3, dtype=dtype), opacity=torch.zeros(0, SR, dtype=dtype), bg_T=torch.zeros(0, 1, dtype=dtype),
+                   coarse_raycolor=torch.ones(R, 3, dtype=dtype) * bg.view(1, 3), coarse_is_background=torch.ones(R, 1, dtype=dtype),
+                   coarse_mask=torch.zeros(R, 1, dtype=dtype), coarse_point_opacity=torch.zeros(R, SR, dtype=dtype),
+                   queried_shading=torch.ones(R, 3, dtype=dtype))
+        return out
     sh = shade_oracle.shade(points, mlp, torch.from_numpy(q["sample_pidx"]), torch.from_numpy(q["sample_loc_w"]),
                             raydir[mask], torch.as_tensor(campos), torch.as_tensor(camrotc2w), vsize,
                             torch.as_tensor(bg_color), dtype=dtype)

@@ -7,9 +7,10 @@
 // the activations of dW = X^T dZ) are transposed on the way into shared memory, so the tensor cores only ever see the K-major
 // core-matrix layout that umma.cuh pins (tests/test_gpu_umma.py).  One CTA = one 128 x 128 output tile (UMMA M = 128, N = 128,
 // fp32 accumulator in 128 TMEM columns), K blocks of 32 through a 4-stage shared-memory ring:
-//   warps 0-3  load fp32 rows from global memory (thread = tile row of A and of B), split into bf16 hi / lo, 16-byte stores
-//              into the operand layout; afterwards the epilogue (thread = accumulator row = TMEM lane)
-//   warp  4    issues 6 tcgen05.mma per K block (A_hi W_hi, A_lo W_hi, A_hi W_lo for the two K=16 steps), one commit per block
+//   warps 0-3  load the fp32 rows of A (thread = tile row), split into bf16 hi / lo, 16-byte stores into the operand layout; the next
+//              K block is already in registers while the current one is converted; afterwards the epilogue (thread = TMEM lane)
+//   warps 4-7  the same for the rows of B
+//   warp  8    issues 6 tcgen05.mma per K block (A_hi W_hi, A_lo W_hi, A_hi W_lo for the two K=16 steps), one commit per block
 // PRECISE mode (forward recompute only): three bf16 parts per operand and the six products of total order <= 2 (a0b0, a1b0, a0b1,
 // a2b0, a1b1, a0b2): fp32-level pre-activations, so that the LeakyReLU masks of the backward are those of an fp32 forward (with the
 // BF16x3 recompute ~1e-5 of the units land on the other side of zero and each such flip changes a pair's gradient by ~1/256).
@@ -25,39 +26,40 @@ using namespace umma;
 namespace gtc {
 constexpr int TM = 128, TN = 128, NSTAGE = 4;
 constexpr int BLK = 128 * 64;             // [128 x 32] bf16 block
-constexpr int NTHR = 160;
+constexpr int NTHR = 288;                 // warps 0-3: A loaders + epilogue, 4-7: B loaders, 8: issuer
 template <int NPART>
 struct Smem {
     unsigned char a[NPART][NSTAGE][BLK], b[NPART][NSTAGE][BLK];     // part 0 = hi, 1 = lo (mid), 2 = lo of the 3-part split
     uint64_t bar_full[NSTAGE], bar_empty[NSTAGE], bar_acc;
     uint32_t tmem_base;
 };
-// one tile row (32 K elements of row `r`) of an operand -> NPART bf16 blocks.  rs / ks: element strides of the row / reduction index.
+// 32 K elements of row `r` of an operand into registers.  rs / ks: element strides of the row / reduction index.
+__device__ __forceinline__ void fetch_row(const float* __restrict__ P, long rs, long ks, long r, bool row_ok, int k0, int kend, float* v) {
+    if (!row_ok || k0 >= kend) {
+#pragma unroll
+        for (int e = 0; e < 32; ++e) v[e] = 0.f;
+    } else if (ks == 1 && k0 + 32 <= kend) {
+        const float4* src = reinterpret_cast<const float4*>(P + r * rs + k0);
+#pragma unroll
+        for (int e4 = 0; e4 < 8; ++e4) { const float4 x = __ldg(src + e4); v[4 * e4] = x.x; v[4 * e4 + 1] = x.y; v[4 * e4 + 2] = x.z; v[4 * e4 + 3] = x.w; }
+    } else {
+#pragma unroll
+        for (int e = 0; e < 32; ++e) v[e] = (k0 + e < kend) ? __ldg(P + r * rs + (long)(k0 + e) * ks) : 0.f;
+    }
+}
+// registers -> NPART bf16 blocks of stage s (tile row t)
 template <int NPART>
-__device__ __forceinline__ void load_row(const float* __restrict__ P, long rs, long ks, long r, bool row_ok, int k0, int kend,
-                                         unsigned char (*blk)[NSTAGE][BLK], int s, int t) {
+__device__ __forceinline__ void store_row(float* v, unsigned char (*blk)[NSTAGE][BLK], int s, int t) {
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
-        float v[8];
-        const int kc = k0 + 8 * c;
-        if (!row_ok || kc >= kend) {
-#pragma unroll
-            for (int e = 0; e < 8; ++e) v[e] = 0.f;
-        } else if (ks == 1 && kc + 8 <= kend) {
-            const float4 x0 = __ldg(reinterpret_cast<const float4*>(P + r * rs + kc)), x1 = __ldg(reinterpret_cast<const float4*>(P + r * rs + kc + 4));
-            v[0] = x0.x; v[1] = x0.y; v[2] = x0.z; v[3] = x0.w; v[4] = x1.x; v[5] = x1.y; v[6] = x1.z; v[7] = x1.w;
-        } else {
-#pragma unroll
-            for (int e = 0; e < 8; ++e) v[e] = (kc + e < kend) ? __ldg(P + r * rs + (long)(kc + e) * ks) : 0.f;
-        }
         const uint32_t off = tile_offset_bytes<LAYOUT_NONE>(t, 8 * c);
 #pragma unroll
         for (int part = 0; part < NPART; ++part) {
             uint32_t w[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                const __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
-                v[2 * i] -= __low2float(h); v[2 * i + 1] -= __high2float(h);          // the residual feeds the next part
+                const __nv_bfloat162 h = __floats2bfloat162_rn(v[8 * c + 2 * i], v[8 * c + 2 * i + 1]);
+                v[8 * c + 2 * i] -= __low2float(h); v[8 * c + 2 * i + 1] -= __high2float(h);          // the residual feeds the next part
                 w[i] = *reinterpret_cast<const uint32_t*>(&h);
             }
             *reinterpret_cast<uint4*>(blk[part][s] + off) = make_uint4(w[0], w[1], w[2], w[3]);
@@ -79,17 +81,17 @@ __global__ void __launch_bounds__(gtc::NTHR, 1) k_gemm_tc(GemmTc g) {
     const int nkb = (kend - kbeg + 31) >> 5;
 
     if (tid == 0) {
-        for (int s = 0; s < NSTAGE; ++s) { mbar_init(&sm.bar_full[s], 4); mbar_init(&sm.bar_empty[s], 1); }   // one arrive per loader warp
+        for (int s = 0; s < NSTAGE; ++s) { mbar_init(&sm.bar_full[s], 8); mbar_init(&sm.bar_empty[s], 1); }   // one arrive per loader warp
         mbar_init(&sm.bar_acc, 1);
         mbar_fence_init();
     }
-    if (warp == 4) tmem_alloc<128>(&sm.tmem_base);
+    if (warp == 8) tmem_alloc<128>(&sm.tmem_base);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tacc = sm.tmem_base;
 
-    if (warp == 4) {
+    if (warp == 8) {
         const uint32_t idesc = make_idesc_bf16(128, 128);
         const uint32_t hiw = desc_hi<LAYOUT_NONE>();
         uint32_t a0[NPART], b0[NPART];
@@ -116,22 +118,33 @@ __global__ void __launch_bounds__(gtc::NTHR, 1) k_gemm_tc(GemmTc g) {
         }
         mma_commit_w(&sm.bar_acc);
     } else {
-        const int t = tid;                          // tile row of A and of B, accumulator row in the epilogue
-        const long ra = m0 + t, rb = n0 + t;
-        const bool a_ok = ra < g.M, b_ok = rb < g.N;
+        // loaders: warps 0-3 own the A rows (thread = tile row), warps 4-7 the B rows; the NEXT K block is fetched into registers
+        // before the current one is converted and stored, so a full K block of loads is in flight per thread
+        const bool isB = warp >= 4;
+        const int t = tid & 127;
+        const float* P = isB ? g.B : g.A;
+        const long rs = isB ? g.b_rs : g.a_rs, ks = isB ? g.b_ks : g.a_ks;
+        const long r = (isB ? n0 : m0) + t;
+        const bool row_ok = r < (isB ? g.N : g.M);
+        unsigned char (*blk)[NSTAGE][BLK] = isB ? sm.b : sm.a;
+        float cur[32], nxt[32];
+        fetch_row(P, rs, ks, r, row_ok, kbeg, kend, cur);
         bool ok = true;
         for (int kb = 0; kb < nkb; ++kb) {
             const uint32_t s = (uint32_t)kb & (NSTAGE - 1), ph = ((uint32_t)kb >> 2) & 1u;
+            if (kb + 1 < nkb) fetch_row(P, rs, ks, r, row_ok, kbeg + 32 * (kb + 1), kend, nxt);
             if (!mbar_wait(&sm.bar_empty[s], ph ^ 1u, g.err, 72)) { ok = false; break; }
-            const int k0 = kbeg + 32 * kb;
-            load_row<NPART>(g.A, g.a_rs, g.a_ks, ra, a_ok, k0, kend, sm.a, (int)s, t);
-            load_row<NPART>(g.B, g.b_rs, g.b_ks, rb, b_ok, k0, kend, sm.b, (int)s, t);
+            store_row<NPART>(cur, blk, (int)s, t);
             fence_proxy_async();
             __syncwarp();
-            if ((tid & 31) == 0) mbar_arrive(&sm.bar_full[s]);   // 32 same-address arrives would serialise in the shared-memory atomic unit
+            if ((tid & 31) == 0) mbar_arrive(&sm.bar_full[s]);   // (32 same-address arrives would serialise in the shared-memory atomic unit)
+#pragma unroll
+            for (int e = 0; e < 32; ++e) cur[e] = nxt[e];
         }
-        if (ok && mbar_wait(&sm.bar_acc, 0u, g.err, 73)) {
+        if (!isB && ok && mbar_wait(&sm.bar_acc, 0u, g.err, 73)) {
             tc_fence_after();
+            const long ra = r;
+            const bool a_ok = row_ok;
             const uint32_t tl = tacc + ((uint32_t)(warp * 32) << 16);
             float* crow = g.part ? g.part + ((size_t)blockIdx.z * g.M + (size_t)ra) * g.N : g.C + ra * g.ldc;
 #pragma unroll 1
@@ -171,7 +184,7 @@ __global__ void __launch_bounds__(gtc::NTHR, 1) k_gemm_tc(GemmTc g) {
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 4) tmem_dealloc<128>(sm.tmem_base);
+    if (warp == 8) tmem_dealloc<128>(sm.tmem_base);
 }
 
 // C[m][n] (+)= sum_z part[z][m][n], z ascending

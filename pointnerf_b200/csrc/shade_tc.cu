@@ -402,19 +402,33 @@ __global__ void __launch_bounds__(256) k_pack_place(pnb_query_t q, int cap, cons
 // Last epilogue with packed rows, one warp's share (chunks G, G+NG, ...): +bias, LeakyReLU, partial alpha dot product (returned),
 // weight*conf scaling, then the K-reduction over the rows of each sample as a segmented inclusive scan (segments = samples,
 // <= 8 lanes, first lane st); the last row of a sample (swrite) holds the sums and writes h-bar.
-template <int NG, int NCHUNK>
-__device__ __forceinline__ float last_chunks_packed(const ShadeTcParams& p, uint32_t accb, int G, float wrow, int st, bool swrite, int sidx, int lane) {
+// EARLY (v8): ALL chunks of this warp are read into registers first and `drain_bar` is signalled right away - the accumulator region
+// is then free for layer 2 of the next tile ~2 k cycles after the last MMA instead of after the whole reduction (~10 k).
+template <int NG, int NCHUNK, bool EARLY = false>
+__device__ __forceinline__ float last_chunks_packed(const ShadeTcParams& p, uint32_t accb, int G, float wrow, int st, bool swrite, int sidx, int lane,
+                                                    uint64_t* drain_bar = nullptr) {
     using namespace tc;
     const float* bias = p.bias[3];
     float apart = 0.f;
-    uint32_t vv[2][16];
-    tmem_ld16(accb + (uint32_t)(16 * G), vv[0]);
+    uint32_t vv[EARLY ? NCHUNK : 2][16];
+    if (EARLY) {
+#pragma unroll
+        for (int i = 0; i < NCHUNK; ++i) tmem_ld16(accb + (uint32_t)(16 * (G + NG * i)), vv[i]);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(drain_bar);
+    } else {
+        tmem_ld16(accb + (uint32_t)(16 * G), vv[0]);
+    }
 #pragma unroll
     for (int i = 0; i < NCHUNK; ++i) {
         const int c0 = 16 * (G + NG * i);
-        const uint32_t* v = vv[i & 1];
-        tmem_ld_wait();
-        if (i + 1 < NCHUNK) tmem_ld16(accb + (uint32_t)(c0 + 16 * NG), vv[(i + 1) & 1]);      // next chunk in flight under this one's math
+        const uint32_t* v = vv[EARLY ? i : (i & 1)];
+        if (!EARLY) {
+            tmem_ld_wait();
+            if (i + 1 < NCHUNK) tmem_ld16(accb + (uint32_t)(c0 + 16 * NG), vv[(i + 1) & 1]);      // next chunk in flight under this one's math
+        }
         float z[16];
 #pragma unroll
         for (int e4 = 0; e4 < 4; ++e4) {
@@ -429,9 +443,11 @@ __device__ __forceinline__ float last_chunks_packed(const ShadeTcParams& p, uint
                 z[e] = y * wrow;
             }
         }
+        if (!(p.dbg_flags & 32)) {             // (dbg 32: timing experiment without the K-reduction, garbage results)
 #pragma unroll
-        for (int e = 0; e < 16; ++e) z[e] = seg_scan8(z[e], lane, st);
-        if (swrite) {
+            for (int e = 0; e < 16; ++e) z[e] = seg_scan8(z[e], lane, st);
+        }
+        if (swrite && !(p.dbg_flags & 64)) {   // (dbg 64: timing experiment without the h-bar stores)
             if (p.hbar_fmt) {       // the colour kernel's operand image (bf16 hi / lo, core-matrix layout): two 16-byte rows each
                 uint32_t hh[8], ll[8];
 #pragma unroll
@@ -712,9 +728,8 @@ __global__ void __launch_bounds__(tc7::NTHR, 1) k_shade_tc7(ShadeTcParams p) {
 namespace tc8 {
 constexpr int NBUILD = 128;
 __host__ __device__ constexpr int nthr(int ngrp) { return ngrp * 128 + NBUILD + 64; }
-constexpr int NSTAGE = 4;                 // ring stage = one K block: hi image + lo image (32 KB)
+constexpr int NSTAGE = 5;                 // ring stage = one K block: hi image + lo image
 constexpr int STAGE = 2 * tc::IMG;
-constexpr int TRS = 20;                   // row stride (floats) of a warp's 32 x 16 transpose scratch: conflict-free 16-byte stores
 constexpr int NKB1 = 2;                   // K blocks of the frozen layer 1 (operand columns 224..287 of block1.0)
 constexpr int KB1_FIRST = 7;
 constexpr int STAGES_PER_TILE = NKB1 + 8 + 9 + 8;
@@ -728,7 +743,6 @@ struct Smem {
     float wc[NWC][tc::TM];
     float alpha_part[2][4][tc::TM];       // [tile parity][epilogue group] partial alpha dot products (own slot each: summed in a fixed order)
     int prow[2][tc::TM];                  // point index of every row (-1: unused row)
-    float tr[12][32 * TRS];               // last epilogue: per warp (8 epilogue + 4 builder) a 32-row x 16-column chunk, for the K-reduction
     uint32_t qhead[NWC][4], qfirst[NWC][4], qtotal[NWC][4];
     uint64_t bar_full[NSTAGE], bar_empty[NSTAGE], bar_a1_ready, bar_a1_free, bar_acc_full, bar_final, bar_alpha, bar_drain, bar_kblk[8], bar_prow[2];
     uint32_t tmem_base;
@@ -839,77 +853,6 @@ __device__ __forceinline__ void build_pair_frozen(tc8::Smem& sm, const ShadeTcPa
 // One epilogue layer of a warp: chunks grp, grp+NGRP, ... (16 accumulator columns each): accumulator -> (+ bias or + pre[point]) ->
 // LeakyReLU -> bf16 hi/lo -> the same columns, one mbarrier arrive per chunk.  SWP: software-pipelined - the tcgen05.ld of the next
 // chunk is in flight under the conversion of this one, and the wait for this chunk's tcgen05.st is deferred behind the next conversion.
-// v8 last epilogue of one warp: chunks G, G+NG, ... of the layer-4 accumulator.  All chunks are read into registers first and
-// `drain_bar` is signalled at once (the accumulator region is free for layer 2 of the next tile ~2 k cycles after the last MMA).  Then per
-// chunk: + bias, LeakyReLU, partial alpha dot product (returned), x weight*conf; the K-reduction over the rows of every sample goes through
-// a 32 x 16 shared-memory transpose instead of segmented warp scans: lane (2 js + h) sums columns 8h..8h+7 of the rows of sample js of this
-// quadrant in ascending row order (the order depends on the sample alone) and writes its 16-byte hi / lo piece of h-bar.
-// (The scan + scattered-store form, last_chunks_packed, costs ~1.8 k cycles per chunk: the epilogue warps, not the MMAs, bounded the tile.)
-template <int NG, int NCHUNK>
-__device__ __forceinline__ float tc8_last_chunks(const ShadeTcParams& p, float* __restrict__ tr, uint32_t accb, int G, float wrow, uint32_t head, int total,
-                                                 uint32_t first, int n_valid, int lane, uint64_t* drain_bar) {
-    using namespace tc;
-    constexpr int TRS = tc8::TRS;
-    uint32_t vv[NCHUNK][16];
-#pragma unroll
-    for (int i = 0; i < NCHUNK; ++i) tmem_ld16(accb + (uint32_t)(16 * (G + NG * i)), vv[i]);
-    // sample bookkeeping of this lane (slot u = 0: sample js = lane / 2, u = 1: js + 16 for quadrants of more than 16 samples)
-    const int nsamp = __popc(head), hsel = lane & 1;
-    int r0[2], cnt[2], sidx[2];
-#pragma unroll
-    for (int u = 0; u < 2; ++u) {
-        const int js = (lane >> 1) + 16 * u;
-        r0[u] = 0; cnt[u] = 0; sidx[u] = 0;
-        if (js < nsamp) {
-            r0[u] = (int)__fns(head, 0, js + 1);
-            const int nx = js + 1 < nsamp ? (int)__fns(head, 0, js + 2) : total;
-            sidx[u] = (int)p.vorder[first + js];
-            cnt[u] = sidx[u] < n_valid ? nx - r0[u] : 0;
-        }
-    }
-    tmem_ld_wait();
-    tc_fence_before();
-    __syncwarp();
-    if (lane == 0) mbar_arrive(drain_bar);
-    const float* bias = p.bias[3];
-    float apart = 0.f;
-#pragma unroll
-    for (int i = 0; i < NCHUNK; ++i) {
-        const int c0 = 16 * (G + NG * i);
-        const uint32_t* v = vv[i];
-#pragma unroll
-        for (int e4 = 0; e4 < 4; ++e4) {
-            const float4 bb = __ldg(reinterpret_cast<const float4*>(bias + c0) + e4), ww = __ldg(reinterpret_cast<const float4*>(p.wa + c0) + e4);
-            float y0 = __uint_as_float(v[4 * e4]) + bb.x, y1 = __uint_as_float(v[4 * e4 + 1]) + bb.y;
-            float y2 = __uint_as_float(v[4 * e4 + 2]) + bb.z, y3 = __uint_as_float(v[4 * e4 + 3]) + bb.w;
-            y0 = fmaxf(y0, LEAKY * y0); y1 = fmaxf(y1, LEAKY * y1); y2 = fmaxf(y2, LEAKY * y2); y3 = fmaxf(y3, LEAKY * y3);
-            apart = fmaf(y0, ww.x, apart); apart = fmaf(y1, ww.y, apart); apart = fmaf(y2, ww.z, apart); apart = fmaf(y3, ww.w, apart);
-            *reinterpret_cast<float4*>(tr + lane * TRS + 4 * e4) = make_float4(y0 * wrow, y1 * wrow, y2 * wrow, y3 * wrow);
-        }
-        __syncwarp();
-#pragma unroll
-        for (int u = 0; u < 2; ++u) {
-            if (u == 1 && nsamp <= 16) break;                 // warp-uniform
-            if (cnt[u] > 0) {
-                float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-                for (int r = r0[u]; r < r0[u] + cnt[u]; ++r) {
-                    const float4 x0 = *reinterpret_cast<const float4*>(tr + r * TRS + 8 * hsel), x1 = *reinterpret_cast<const float4*>(tr + r * TRS + 8 * hsel + 4);
-                    a[0] += x0.x; a[1] += x0.y; a[2] += x0.z; a[3] += x0.w; a[4] += x1.x; a[5] += x1.y; a[6] += x1.z; a[7] += x1.w;
-                }
-                uint32_t hh[4], ll[4];
-#pragma unroll
-                for (int e = 0; e < 4; ++e) split_bf16x2(a[2 * e], a[2 * e + 1], hh[e], ll[e]);
-                unsigned char* dst = reinterpret_cast<unsigned char*>(p.hbar) + ((size_t)(sidx[u] >> 7) * 8 + (c0 >> 5)) * (2 * 8192) +
-                                     tile_offset_bytes<LAYOUT_NONE>(sidx[u] & 127, (c0 & 31) + 8 * hsel);
-                *reinterpret_cast<uint4*>(dst) = make_uint4(hh[0], hh[1], hh[2], hh[3]);
-                *reinterpret_cast<uint4*>(dst + 8192) = make_uint4(ll[0], ll[1], ll[2], ll[3]);
-            }
-        }
-        __syncwarp();
-    }
-    return apart;
-}
-
 template <int NGRP>
 struct Tc8Pf {                                    // chunks of `pre` in flight per epilogue thread (layer 1)
     static constexpr int NCH = 16 / NGRP, PF = NCH < 3 ? NCH : 3;      // (6 in flight measured slower: 40.0 k vs 37.3 k cycles per tile)
@@ -984,7 +927,6 @@ __global__ void __launch_bounds__(tc8::nthr(NGRP), 1) k_shade_tc8(ShadeTcParams 
     const int n_quads = p.pack_cnt[0];
     const int n_tiles = (n_quads + 3) >> 2;
     const int my_tiles = n_tiles > (int)blockIdx.x ? (n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
-    static_assert(NGRP == 2, "k_shade_tc8: 8 epilogue warps (16 measured slower; the transpose scratch is sized for 8 + 4 warps)");
     constexpr int NEPI_WARPS = 4 * NGRP;
     constexpr int W_BUILD = NEPI_WARPS, W_LOAD = W_BUILD + tc8::NBUILD / 32, W_ISSUE = W_LOAD + 1;
     // last epilogue: 16 chunks over the NGRP epilogue warps + 1 builder warp of a quadrant; the builder warp takes group 0
@@ -1136,8 +1078,7 @@ __global__ void __launch_bounds__(tc8::nthr(NGRP), 1) k_shade_tc8(ShadeTcParams 
                 const int sidx = qr.live ? (int)p.vorder[sm.qfirst[tf & 1][qw] + qr.j] : 0;
                 const bool swrite = qr.is_end && sidx < n_valid;
                 const float wrow = sm.wc[tf & 1][row];
-                const float apart = tc8_last_chunks<NG4, NCH4_B>(p, sm.tr[NEPI_WARPS + qw], tP + tlane, 0, wrow, sm.qhead[tf & 1][qw], (int)sm.qtotal[tf & 1][qw],
-                                                                 sm.qfirst[tf & 1][qw], n_valid, lane, &sm.bar_drain);
+                const float apart = last_chunks_packed<NG4, NCH4_B, true>(p, tP + tlane, 0, wrow, qr.st, swrite, sidx, lane, &sm.bar_drain);
                 TB(11);
                 if (!TW(12, mbar_wait(&sm.bar_alpha, (uint32_t)tf & 1u, p.err, 100))) { ok = false; break; }      // the epilogue warps' partial sums
                 float a = apart;
@@ -1179,8 +1120,10 @@ __global__ void __launch_bounds__(tc8::nthr(NGRP), 1) k_shade_tc8(ShadeTcParams 
             {   // this warp's share of the LAST epilogue (chunk groups 1..NGRP of NGRP+1; the builder warps take group 0)
                 if (!TW(18, mbar_wait(&sm.bar_final, (uint32_t)t & 1u, p.err, 101))) { ok = false; break; }
                 tc_fence_after();
-                const float apart = tc8_last_chunks<NG4, NCH4_E>(p, sm.tr[warp], tP + tlane, 1 + grp, sm.wc[t & 1][erow], sm.qhead[t & 1][quad], (int)sm.qtotal[t & 1][quad],
-                                                                 sm.qfirst[t & 1][quad], n_valid, lane, &sm.bar_drain);
+                const QuadRow qr = quad_row(sm.qhead[t & 1][quad], (int)sm.qtotal[t & 1][quad], lane);
+                const int sidx = qr.live ? (int)p.vorder[sm.qfirst[t & 1][quad] + qr.j] : 0;
+                const float apart = last_chunks_packed<NG4, NCH4_E, true>(p, tP + tlane, 1 + grp, sm.wc[t & 1][erow], qr.st, qr.is_end && sidx < n_valid, sidx, lane,
+                                                                          &sm.bar_drain);
                 sm.alpha_part[t & 1][grp][erow] = apart;
                 __syncwarp();
                 TB(19);
@@ -1592,6 +1535,8 @@ extern "C" int pnb_shade_forward_tc(const pnb_query_t* q, const pnb_points_t* pt
         PNB_CHECK_CUDA(cudaFuncSetAttribute(k_shade_tc7, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tc7));
         PNB_CHECK_CUDA(cudaFuncSetAttribute(k_shade_tc8<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tc8));
         PNB_CHECK_CUDA(cudaFuncSetAttribute(k_shade_tc8<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tc8));
+        PNB_CHECK_CUDA(cudaFuncSetAttribute(k_shade_tc8<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tc8));
+        PNB_CHECK_CUDA(cudaFuncSetAttribute(k_shade_tc8<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tc8));
         PNB_CHECK_CUDA(cudaFuncSetAttribute(k_color_tc2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_ctc2));
         PNB_CHECK_CUDA(cudaDeviceGetAttribute(&n_sm_of[dev], cudaDevAttrMultiProcessorCount, dev));
         configured[dev] = 1;
@@ -1615,9 +1560,12 @@ extern "C" int pnb_shade_forward_tc(const pnb_query_t* q, const pnb_points_t* pt
         k_pack_scan<<<1, 1024, 0, stream>>>(p.q, cap, w.sc_quads, w.quad_first, w.pack_cnt);
         k_pack_place<<<(cap + 255) / 256, 256, 0, stream>>>(p.q, cap, w.sc_quads, w.quad_local, w.quad_first);
         if (frozen) {
-            // 8 epilogue warps, plain chunk loop (16 warps and software-pipelined chunks measured slower, profiles/r02_tc8_experiments.log);
-            // dbg bit 4 (tools/tc_profile.py) = software-pipelined epilogue chunks
-            if (p.dbg_flags & 16) k_shade_tc8<2, true><<<n_sm, tc8::nthr(2), smem_tc8, stream>>>(p);
+            // default: 8 epilogue warps, plain chunk loop (measured fastest, profiles/r02_tc8_variants.log); experiment flags of
+            // tools/tc_profile.py: dbg bit 3 = 16 epilogue warps, dbg bit 4 = software-pipelined epilogue chunks
+            const bool e16 = (p.dbg_flags & 8) != 0, swp = (p.dbg_flags & 16) != 0;
+            if (e16 && swp) k_shade_tc8<4, true><<<n_sm, tc8::nthr(4), smem_tc8, stream>>>(p);
+            else if (e16) k_shade_tc8<4, false><<<n_sm, tc8::nthr(4), smem_tc8, stream>>>(p);
+            else if (swp) k_shade_tc8<2, true><<<n_sm, tc8::nthr(2), smem_tc8, stream>>>(p);
             else k_shade_tc8<2, false><<<n_sm, tc8::nthr(2), smem_tc8, stream>>>(p);
         }
         else k_shade_tc7<<<n_sm, tc7::NTHR, smem_tc7, stream>>>(p);

@@ -18,7 +18,7 @@ for i in range(3):
     with torch.no_grad():
         net.render_full(list(cfg.campos), rd, torch.eye(3), cfg.near, cfg.far, [1., 1., 1.])
 net.check_errors()
-net.dbg_flags = 4 | int(os.environ.get("PNB_DBG_FLAGS", "0")) | (1 if os.environ.get("PNB_PROF") else 0)       # frozen kernel: +16 = software-pipelined epilogue chunks (experiment)
+net.dbg_flags = 4 | int(os.environ.get("PNB_DBG_FLAGS", "0")) | (1 if os.environ.get("PNB_PROF") else 0)       # frozen kernel: +8 = 16 epilogue warps (default 8), +16 = software-pipelined chunks, +32 / +64 = last epilogue without the K-reduction / the h-bar stores (timing experiments)
 if os.environ.get("PNB_NO_WEIGHTS"):
     net.dbg_flags |= 0          # (the no-weights bit is a top-level flag)
     L.TC_PAIRS |= L.TC_DBG_NO_WEIGHTS

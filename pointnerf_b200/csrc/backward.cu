@@ -167,7 +167,7 @@ __global__ void __launch_bounds__(256) k_lrelu_bwd(float* __restrict__ dY, const
     dY[m * ldd + n] *= (y > 0.f ? 1.0f : LEAKY);
 }
 
-// db[n] += sum_m dZ[m][n]
+// db[n] += sum_m dZ[m][n]   (N <= 4: the colour head)
 __global__ void __launch_bounds__(256) k_colsum(const float* __restrict__ dZ, long ld, int M, int N, float* __restrict__ db) {
     int n = blockIdx.x * 32 + (threadIdx.x & 31);
     int r0 = blockIdx.y * 2048 + (threadIdx.x >> 5);
@@ -182,6 +182,30 @@ __global__ void __launch_bounds__(256) k_colsum(const float* __restrict__ dZ, lo
         for (int w = 0; w < 8; ++w) t += red[w][threadIdx.x];
         atomicAdd(&db[n], t);
     }
+}
+// the same for N % 128 == 0: a warp reads 512 contiguous bytes of a row (float4 per lane), 8 warps stride the rows of a 4096-row slab
+__global__ void __launch_bounds__(256) k_colsum4(const float* __restrict__ dZ, long ld, int M, int N, float* __restrict__ db) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int n = blockIdx.x * 128 + 4 * lane;
+    const int m1 = min(M, (int)(blockIdx.y + 1) * 4096);
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int m = blockIdx.y * 4096 + w; m < m1; m += 8) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(dZ + (long)m * ld + n));
+        s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+    }
+    __shared__ float4 red[8][32];
+    red[w][lane] = s;
+    __syncthreads();
+    if (w == 0) {
+        float4 t = red[0][lane];
+        for (int i = 1; i < 8; ++i) { t.x += red[i][lane].x; t.y += red[i][lane].y; t.z += red[i][lane].z; t.w += red[i][lane].w; }
+        atomicAdd(&db[n], t.x); atomicAdd(&db[n + 1], t.y); atomicAdd(&db[n + 2], t.z); atomicAdd(&db[n + 3], t.w);
+    }
+}
+static void colsum(const float* dZ, long ld, int M, int N, float* db, cudaStream_t st) {
+    if (M <= 0) return;
+    if (N % 128 == 0 && ld % 4 == 0) k_colsum4<<<dim3(N / 128, (M + 4095) / 4096), 256, 0, st>>>(dZ, ld, M, N, db);
+    else k_colsum<<<dim3((N + 31) / 32, (M + 2047) / 2048), 256, 0, st>>>(dZ, ld, M, N, db);
 }
 
 // ------------------------------------------------------------------------------------------ path-specific kernels
@@ -603,16 +627,16 @@ extern "C" int pnb_shade_backward(const pnb_query_t* q, const pnb_points_t* pts,
     k_bwd_head<<<(S + 255) / 256, 256, 0, st>>>(p);
     // colour branch (each dX GEMM applies the derivative of the LeakyReLU below it in its epilogue)
     gemm_tn_acc(cx, L.C3, 128, L.dO3, 4, d_mlp_w[8], 3, S, 128, 3);
-    k_colsum<<<dim3(1, (S + 2047) / 2048), 256, 0, st>>>(L.dO3, 4, S, 3, d_mlp_b[8]);
+    colsum(L.dO3, 4, S, 3, d_mlp_b[8], st);
     gemm_nt(cx, L.dO3, 4, mlp->w[8], 3, L.GS3, 128, S, 128, 3, L.C3, 128, 128);       // dC3
     gemm_tn_acc(cx, L.C2, 128, L.GS3, 128, d_mlp_w[7], 128, S, 128, 128);
-    k_colsum<<<dim3(4, (S + 2047) / 2048), 256, 0, st>>>(L.GS3, 128, S, 128, d_mlp_b[7]);
+    colsum(L.GS3, 128, S, 128, d_mlp_b[7], st);
     gemm_nt(cx, L.GS3, 128, mlp->w[7], 128, L.GS2, 128, S, 128, 128, L.C2, 128, 128); // dC2
     gemm_tn_acc(cx, L.C1, 128, L.GS2, 128, d_mlp_w[6], 128, S, 128, 128);
-    k_colsum<<<dim3(4, (S + 2047) / 2048), 256, 0, st>>>(L.GS2, 128, S, 128, d_mlp_b[6]);
+    colsum(L.GS2, 128, S, 128, d_mlp_b[6], st);
     gemm_nt(cx, L.GS2, 128, mlp->w[6], 128, L.GS3, 128, S, 128, 128, L.C1, 128, 128); // dC1 (reuse GS3)
     gemm_tn_acc(cx, L.CX, 288, L.GS3, 128, d_mlp_w[5], 128, S, 288, 128);
-    k_colsum<<<dim3(4, (S + 2047) / 2048), 256, 0, st>>>(L.GS3, 128, S, 128, d_mlp_b[5]);
+    colsum(L.GS3, 128, S, 128, d_mlp_b[5], st);
     gemm_nt(cx, L.GS3, 128, mlp->w[5], 128, L.GS1, 288, S, 288, 128);                 // d(hbar | view PE)
     // K-reduction + alpha branch
     k_bwd_reduce_bwd<<<wb, 256, 0, st>>>(p, L.dwc);
@@ -620,19 +644,19 @@ extern "C" int pnb_shade_backward(const pnb_query_t* q, const pnb_points_t* pts,
     // block3.2
     k_lrelu_bwd<<<(int)(((long)P * 256 + 255) / 256), 256, 0, st>>>(L.G3, L.H4, 256, 256, P, 256);
     gemm_tn_acc(cx, L.H3, 256, L.G3, 256, d_mlp_w[3], 256, P, 256, 256);
-    k_colsum<<<dim3(8, (P + 2047) / 2048), 256, 0, st>>>(L.G3, 256, P, 256, d_mlp_b[3]);
+    colsum(L.G3, 256, P, 256, d_mlp_b[3], st);
     gemm_nt(cx, L.G3, 256, mlp->w[3], 256, L.G1, 288, P, 256, 256, L.H3, 256, 256);   // dH3 in G1[:, :256] (ld 288)
     // block3.0
     gemm_tn_acc(cx, L.X3, 272, L.G1, 288, d_mlp_w[2], 256, P, 272, 256);
-    k_colsum<<<dim3(8, (P + 2047) / 2048), 256, 0, st>>>(L.G1, 288, P, 256, d_mlp_b[2]);
+    colsum(L.G1, 288, P, 256, d_mlp_b[2], st);
     gemm_nt(cx, L.G1, 288, mlp->w[2], 256, L.G2, 272, P, 272, 256, L.X3, 272, 256);   // dX3 = (dH2 | d extras); the extras have no activation
     // block1.2
     gemm_tn_acc(cx, L.H1, 256, L.G2, 272, d_mlp_w[1], 256, P, 256, 256);
-    k_colsum<<<dim3(8, (P + 2047) / 2048), 256, 0, st>>>(L.G2, 272, P, 256, d_mlp_b[1]);
+    colsum(L.G2, 272, P, 256, d_mlp_b[1], st);
     gemm_nt(cx, L.G2, 272, mlp->w[1], 256, L.G3, 256, P, 256, 256, L.H1, 256, 256);   // dH1 in G3
     // block1.0
     gemm_tn_acc(cx, L.X1, 288, L.G3, 256, d_mlp_w[0], 256, P, 288, 256);
-    k_colsum<<<dim3(8, (P + 2047) / 2048), 256, 0, st>>>(L.G3, 256, P, 256, d_mlp_b[0]);
+    colsum(L.G3, 256, P, 256, d_mlp_b[0], st);
     gemm_nt(cx, L.G3, 256, mlp->w[0], 256, L.G1, 288, P, 288, 256);                   // dX1
     // scatter to the points
     k_bwd_scatter<<<(int)(((long)P * 4 + 255) / 256), 256, 0, st>>>(p, L.dwc, d_emb, d_color, d_dir, d_conf);

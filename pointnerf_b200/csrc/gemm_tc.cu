@@ -6,7 +6,7 @@
 // Either stride of an operand may be the unit one: operands whose reduction index is NOT contiguous in memory (W^T buffers,
 // the activations of dW = X^T dZ) are transposed on the way into shared memory, so the tensor cores only ever see the K-major
 // core-matrix layout that umma.cuh pins (tests/test_gpu_umma.py).  One CTA = one 128 x 128 output tile (UMMA M = 128, N = 128,
-// fp32 accumulator in 128 TMEM columns), K blocks of 32 through a 4-stage shared-memory ring:
+// fp32 accumulator in 128 TMEM columns; two CTAs per SM), K blocks of 32 through a 2-stage shared-memory ring:
 //   warps 0-3  load the fp32 rows of A (thread = tile row), split into bf16 hi / lo, 16-byte stores into the operand layout; the next
 //              K block is already in registers while the current one is converted; afterwards the epilogue (thread = TMEM lane)
 //   warps 4-7  the same for the rows of B
@@ -24,7 +24,7 @@ namespace pnb {
 using namespace umma;
 
 namespace gtc {
-constexpr int TM = 128, TN = 128, NSTAGE = 4;
+constexpr int TM = 128, TN = 128, LOG_NSTAGE = 1, NSTAGE = 1 << LOG_NSTAGE;    // 2 stages (64 KB): two CTAs per SM keep twice the loads in flight
 constexpr int BLK = 128 * 64;             // [128 x 32] bf16 block
 constexpr int NTHR = 288;                 // warps 0-3: A loaders + epilogue, 4-7: B loaders, 8: issuer
 template <int NPART>
@@ -69,7 +69,7 @@ __device__ __forceinline__ void store_row(float* v, unsigned char (*blk)[NSTAGE]
 }  // namespace gtc
 
 template <bool PRECISE>
-__global__ void __launch_bounds__(gtc::NTHR, 1) k_gemm_tc(GemmTc g) {
+__global__ void __launch_bounds__(gtc::NTHR, 2) k_gemm_tc(GemmTc g) {
     using namespace gtc;
     constexpr int NPART = PRECISE ? 3 : 2;
     using SmemT = Smem<NPART>;
@@ -100,7 +100,7 @@ __global__ void __launch_bounds__(gtc::NTHR, 1) k_gemm_tc(GemmTc g) {
         constexpr uint32_t KADV = kstep_adv16<LAYOUT_NONE>(), SADV = BLK >> 4;
         bool ok = true;
         for (int kb = 0; kb < nkb && ok; ++kb) {
-            const uint32_t s = (uint32_t)kb & (NSTAGE - 1), ph = ((uint32_t)kb >> 2) & 1u;
+            const uint32_t s = (uint32_t)kb & (NSTAGE - 1), ph = ((uint32_t)kb >> LOG_NSTAGE) & 1u;
             if (!mbar_wait(&sm.bar_full[s], ph, g.err, 71)) { ok = false; break; }
             tc_fence_after();
             bool first = kb == 0;
@@ -131,7 +131,7 @@ __global__ void __launch_bounds__(gtc::NTHR, 1) k_gemm_tc(GemmTc g) {
         fetch_row(P, rs, ks, r, row_ok, kbeg, kend, cur);
         bool ok = true;
         for (int kb = 0; kb < nkb; ++kb) {
-            const uint32_t s = (uint32_t)kb & (NSTAGE - 1), ph = ((uint32_t)kb >> 2) & 1u;
+            const uint32_t s = (uint32_t)kb & (NSTAGE - 1), ph = ((uint32_t)kb >> LOG_NSTAGE) & 1u;
             if (kb + 1 < nkb) fetch_row(P, rs, ks, r, row_ok, kbeg + 32 * (kb + 1), kend, nxt);
             if (!mbar_wait(&sm.bar_empty[s], ph ^ 1u, g.err, 72)) { ok = false; break; }
             store_row<NPART>(cur, blk, (int)s, t);

@@ -173,8 +173,8 @@ class TrainStep:
             dist.all_reduce(cnt, op=dist.ReduceOp.SUM, group=self.group)
         n_se_g, n_zo_g = max(float(cnt[0].item()), 1.0), max(float(cnt[1].item()), 1.0)
         loss_local = se / n_se_g + self.zero_one_weight * zo / n_zo_g
-        self.opt_mlp.zero_grad(set_to_none=False)
-        self.opt_pts.zero_grad(set_to_none=False)
+        self.opt_mlp.zero_grad(set_to_none=True)      # the backward hands over fresh gradient tensors: no zero-fill + accumulate per step
+        self.opt_pts.zero_grad(set_to_none=True)
         mark("forward")
         loss_local.backward()
         mark("backward")

@@ -514,7 +514,8 @@ class NeuralPointsRayMarching(nn.Module):
             q, ray_color, opacity, bg_T, ray_mask = self._run(*run_args, frozen=True)
         self.check_errors()
         # compact to the R' rays the reference returns (one host sync already paid for the counters)
-        inds = torch.nonzero(ray_mask)[:, 0]
+        # (the number of hit rays is already on the host with the query counters: no second synchronisation for the compaction)
+        inds = torch.nonzero_static(ray_mask, size=int(q.counters["R2"]))[:, 0] if getattr(q, "counters", None) else torch.nonzero(ray_mask)[:, 0]
         out = {}
         out["coarse_raycolor"] = ray_color[inds][None]
         out["coarse_point_opacity"] = opacity[inds][None]

@@ -63,8 +63,8 @@ def test_gradients_match_reference_fixture(name, precision, bwd_fp32, golden_dir
     per_point(npn.points_color.grad.cpu(), fx["grad_color"], "points_color")
     per_point(npn.points_dir.grad.cpu(), fx["grad_dir"], "points_dir")
     _close(npn.points_conf.grad.cpu(), fx["grad_conf"], "points_conf", rtol=1e-3)
-    for k, p in net.aggregator.named_parameters():
-        _close(p.grad.cpu(), fx["gradmlp." + k], "aggregator." + k)
+    for k, p in net.aggregator.named_parameters():     # (a flipped mask also moves one column of one weight gradient: 1e-3 for the tensor-core recompute)
+        _close(p.grad.cpu(), fx["gradmlp." + k], "aggregator." + k, rtol=1e-3 if bwd_fp32 == 0 else 3e-4)
     assert npn.xyz.grad is None
     net.check_errors()
 

@@ -183,13 +183,13 @@ __global__ void __launch_bounds__(256) k_colsum(const float* __restrict__ dZ, lo
         atomicAdd(&db[n], t);
     }
 }
-// the same for N % 128 == 0: a warp reads 512 contiguous bytes of a row (float4 per lane), 8 warps stride the rows of a 4096-row slab
+// the same for N % 128 == 0: a warp reads 512 contiguous bytes of a row (float4 per lane), 8 warps stride the rows of a 512-row slab
 __global__ void __launch_bounds__(256) k_colsum4(const float* __restrict__ dZ, long ld, int M, int N, float* __restrict__ db) {
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int n = blockIdx.x * 128 + 4 * lane;
-    const int m1 = min(M, (int)(blockIdx.y + 1) * 4096);
+    const int m1 = min(M, (int)(blockIdx.y + 1) * 512);
     float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int m = blockIdx.y * 4096 + w; m < m1; m += 8) {
+    for (int m = blockIdx.y * 512 + w; m < m1; m += 8) {
         const float4 v = __ldg(reinterpret_cast<const float4*>(dZ + (long)m * ld + n));
         s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
     }
@@ -204,7 +204,7 @@ __global__ void __launch_bounds__(256) k_colsum4(const float* __restrict__ dZ, l
 }
 static void colsum(const float* dZ, long ld, int M, int N, float* db, cudaStream_t st) {
     if (M <= 0) return;
-    if (N % 128 == 0 && ld % 4 == 0) k_colsum4<<<dim3(N / 128, (M + 4095) / 4096), 256, 0, st>>>(dZ, ld, M, N, db);
+    if (N % 128 == 0 && ld % 4 == 0) k_colsum4<<<dim3(N / 128, (M + 511) / 512), 256, 0, st>>>(dZ, ld, M, N, db);
     else k_colsum<<<dim3((N + 31) / 32, (M + 2047) / 2048), 256, 0, st>>>(dZ, ld, M, N, db);
 }
 

@@ -212,7 +212,7 @@ int pnb_shade_tc_tables(void* ws, size_t ws_bytes, int max_valid_samples, void**
  * pnb_composite_forward) accumulates gradients of points_embeding [N,32], points_color [N,3], points_dir [N,3],
  * points_conf [N] (any may be NULL) and of the 9 MLP layers in the layout of pnb_mlp_t (W^T [K_pad][N] and bias; the
  * caller zero-initialises all accumulators).  d_sigma_rgb_fwd: the forward's per-candidate (sigma, rgb) buffer.
- * n_valid: host copy of counters[PNB_QC_N_VALID].  ws >= pnb_backward_bytes.  The activations are recomputed and every layer
+ * n_valid / n_pairs: host copies of counters[PNB_QC_N_VALID] / [PNB_QC_N_PAIRS] (the pair-level buffers hold one row per valid pair).  ws >= pnb_backward_bytes.  The activations are recomputed and every layer
  * GEMM (recompute, dX, dW) runs on the tensor cores (tcgen05, BF16x3 split, fp32 accumulate; dW by a deterministic split-K);
  * the recomputed pre-activations carry the BF16x3 error, so ~1e-6 of the LeakyReLU masks differ from an fp32 forward's (each changes
  * one pair's gradient by ~1/256; see the flags).  d_err: device int32,
@@ -223,7 +223,7 @@ enum {
 };
 size_t pnb_backward_bytes(int n_valid, int cap_samples);
 int pnb_shade_backward(const pnb_query_t* q, const pnb_points_t* pts, const pnb_mlp_t* mlp, const pnb_shade_opts_t* opts,
-                       const float* d_sigma_rgb_fwd, const float* d_ray_color, int n_valid, float* d_emb, float* d_color,
+                       const float* d_sigma_rgb_fwd, const float* d_ray_color, int n_valid, int n_pairs, float* d_emb, float* d_color,
                        float* d_dir, float* d_conf, float* const* d_mlp_w, float* const* d_mlp_b, void* ws,
                        size_t ws_bytes, int flags, int* d_err, pnb_stream_t stream);
 

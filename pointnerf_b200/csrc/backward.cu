@@ -214,6 +214,9 @@ struct BwdParams {
     pnb_points_t pts;
     pnb_shade_opts_t o;
     int n_valid;        // S
+    int n_rows;         // P = number of valid (sample, neighbour) pairs: the rows of the pair-level buffers are PACKED (no rows for empty slots)
+    const uint32_t* pair_off;   // [S+1] first row of every valid sample
+    int* row_samp;      // [P] valid-sample index of every row
     // forward recompute buffers
     float* X1;          // [P x 288]
     float* H1;          // [P x 256]
@@ -260,21 +263,27 @@ __device__ __forceinline__ void w2persb(const pnb_shade_opts_t& o, float px, flo
     xp = xc / zc; yp = yc / zc; zp = zc;
 }
 
+// neighbour count of every valid sample (its exclusive prefix = the first packed row of the sample)
+__global__ void __launch_bounds__(256) k_bwd_counts(pnb_query_t q, int n_valid, uint32_t* __restrict__ nv) {
+    const int vi = blockIdx.x * blockDim.x + threadIdx.x;
+    if (vi < n_valid) nv[vi] = q.samp_nvalid[q.valid_list[vi]];
+}
 // One warp per valid sample, 4 lanes per pair row (same mapping as the fp32 forward kernel): dense block1 input.
 __global__ void __launch_bounds__(256) k_bwd_build(BwdParams p) {
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (warp >= p.n_valid) return;
     const pnb_query_t& q = p.q;
     const int vi = warp, k = lane >> 2, part = lane & 3;
-    const long row = (long)vi * PNB_MAX_K + k;
     uint32_t s = q.valid_list[vi];
+    const bool active = k < (int)q.samp_nvalid[s];          // the neighbours of a sample occupy its first slots
+    const long row = (long)p.pair_off[vi] + k;               // packed: only active lanes own a row
     uint32_t pk = q.samp_ray[s];
     int r = (int)(pk >> 7), j = (int)(pk & 127u);
     int d = q.steps[(size_t)r * q.SR + j];
     float t = q.t[(size_t)r * q.t_ray_stride + d];
     float vx = q.raydir[3 * r], vy = q.raydir[3 * r + 1], vz = q.raydir[3 * r + 2];
     float lx = raypos1(q.campos[0], vx, t), ly = raypos1(q.campos[1], vy, t), lz = raypos1(q.campos[2], vz, t);
-    int pidx = k < q.K ? q.cand_pidx[(size_t)s * q.K + k] : -1;
+    int pidx = (active && k < q.K) ? q.cand_pidx[(size_t)s * q.K + k] : -1;
     const bool valid = pidx >= 0;
     const int pi = valid ? pidx : 0;
     float ovx, ovy, ovz;
@@ -302,7 +311,7 @@ __global__ void __launch_bounds__(256) k_bwd_build(BwdParams p) {
     w = w / fmaxf(wsum, 1e-8f);
     float cf = __ldg(&p.pts.conf[pi]);
     float cc = fminf(fmaxf(cf, 1e-4f), 1.0f);
-    if (part == 0) { p.wc[row] = valid ? w * cc : 0.f; p.wn[row] = valid ? w : 0.f; p.pidx[row] = pidx; }
+    if (part == 0 && valid) { p.wc[row] = w * cc; p.wn[row] = w; p.pidx[row] = pidx; p.row_samp[row] = vi; }
     float d0, d1, d2;
     rot3b(p.o.Rw2c, dist[0], dist[1], dist[2], d0, d1, d2);
     dist[0] = d0; dist[1] = d1; dist[2] = d2;
@@ -340,10 +349,6 @@ __global__ void __launch_bounds__(256) k_bwd_build(BwdParams p) {
             er[6] = ddx * ovx + ddy * ovy + ddz * ovz;
             for (int e = 7; e < 16; ++e) er[e] = 0.f;
         }
-    } else {
-        for (int c = part; c < 288; c += 4) xr[c] = 0.f;
-        if (part == 1)
-            for (int e = 0; e < 16; ++e) er[e] = 0.f;
     }
 }
 
@@ -351,11 +356,12 @@ __global__ void __launch_bounds__(256) k_bwd_build(BwdParams p) {
 __global__ void __launch_bounds__(256) k_bwd_reduce_fwd(BwdParams p) {
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (warp >= p.n_valid) return;
-    const long r0 = (long)warp * PNB_MAX_K;
+    const long r0 = (long)p.pair_off[warp];
+    const int nrow = (int)(p.pair_off[warp + 1] - p.pair_off[warp]);
     float hb[8];
 #pragma unroll
     for (int c = 0; c < 8; ++c) hb[c] = 0.f;
-    for (int k = 0; k < PNB_MAX_K; ++k) {
+    for (int k = 0; k < nrow; ++k) {
         const float* h = p.H4 + (r0 + k) * 256;
         float wck = p.wc[r0 + k];
         float a = 0.f;
@@ -397,12 +403,13 @@ __global__ void __launch_bounds__(256) k_bwd_head(BwdParams p) {
 __global__ void __launch_bounds__(256) k_bwd_reduce_bwd(BwdParams p, float* __restrict__ dwc) {
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (warp >= p.n_valid) return;
-    const long r0 = (long)warp * PNB_MAX_K;
+    const long r0 = (long)p.pair_off[warp];
+    const int nrow = (int)(p.pair_off[warp + 1] - p.pair_off[warp]);
     float dh[8];
 #pragma unroll
     for (int c = 0; c < 8; ++c) dh[c] = p.GS1[(long)warp * 288 + lane + 32 * c];
     const float ds = p.dsig[warp];
-    for (int k = 0; k < PNB_MAX_K; ++k) {
+    for (int k = 0; k < nrow; ++k) {
         const long row = r0 + k;
         const float wck = p.wc[row];
         const float dar = ds * wck * p.sg[row];     // d alpha_raw
@@ -421,11 +428,11 @@ __global__ void __launch_bounds__(256) k_bwd_reduce_bwd(BwdParams p, float* __re
 // alpha-branch parameter gradients: dwa[c] += sum_p dalpha_raw[p] * H4[p][c] ; dba += sum_p dalpha_raw[p]
 __global__ void __launch_bounds__(256) k_bwd_alpha_params(BwdParams p, float* __restrict__ dwa, float* __restrict__ dba) {
     const int c = threadIdx.x;
-    const long P = (long)p.n_valid * PNB_MAX_K;
+    const long P = (long)p.n_rows;
     const long r0 = (long)blockIdx.x * 1024, r1 = min(P, r0 + 1024);
     float acc = 0.f, accb = 0.f;
     for (long row = r0; row < r1; ++row) {
-        float dar = p.dsig[row >> 3] * p.wc[row] * p.sg[row];
+        float dar = p.dsig[p.row_samp[row]] * p.wc[row] * p.sg[row];
         acc = fmaf(dar, p.H4[row * 256 + c], acc);
         accb += dar;
     }
@@ -439,7 +446,7 @@ __global__ void __launch_bounds__(256) k_bwd_scatter(BwdParams p, const float* _
     const long gt = (long)blockIdx.x * blockDim.x + threadIdx.x;
     const long row = gt >> 2;
     const int part = (int)(gt & 3);
-    const long P = (long)p.n_valid * PNB_MAX_K;
+    const long P = (long)p.n_rows;
     if (row >= P) return;
     const int pi = p.pidx[row];
     if (pi < 0) return;
@@ -464,7 +471,7 @@ __global__ void __launch_bounds__(256) k_bwd_scatter(BwdParams p, const float* _
         if (d_color) { atomicAdd(&d_color[3 * pi], ge[0]); atomicAdd(&d_color[3 * pi + 1], ge[1]); atomicAdd(&d_color[3 * pi + 2], ge[2]); }
         if (d_dir) {
             // extras: (dir' - view')[3], <dir', view'>  with dir' = Rw2c * dir  ->  d dir = Rw2c^T (g[3:6] + g[6] * view')
-            uint32_t s = p.q.valid_list[row >> 3];
+            uint32_t s = p.q.valid_list[p.row_samp[row]];
             int r = (int)(p.q.samp_ray[s] >> 7);
             float ovx, ovy, ovz;
             rot3b(p.o.Rw2c, p.q.raydir[3 * r], p.q.raydir[3 * r + 1], p.q.raydir[3 * r + 2], ovx, ovy, ovz);
@@ -555,6 +562,8 @@ struct Layout {
     int* pidx;
     float4* d_sigma_rgb;
     float* part;
+    uint32_t *nv, *pair_off, *scan_tmp;
+    int* row_samp;
     size_t bytes;
 };
 static Layout carve(void* ws, size_t cap, int max_valid, int cap_samples) {
@@ -572,6 +581,7 @@ static Layout carve(void* ws, size_t cap, int max_valid, int cap_samples) {
     L.dO3 = c.take<float>(S * 4); L.dsig = c.take<float>(S);
     L.d_sigma_rgb = c.take<float4>((size_t)(cap_samples > 0 ? cap_samples : 1));
     L.part = c.take<float>(PART_FLOATS);
+    L.nv = c.take<uint32_t>(S); L.pair_off = c.take<uint32_t>(S + 1); L.scan_tmp = c.take<uint32_t>(scan_tmp_elems(S)); L.row_samp = c.take<int>(P);
     L.bytes = align_up(c.off);
     return L;
 }
@@ -589,7 +599,7 @@ extern "C" size_t pnb_backward_bytes(int n_valid, int cap_samples) { return carv
 // any of them may be NULL.  n_valid: host copy of counters[PNB_QC_N_VALID] of the query.
 extern "C" int pnb_shade_backward(const pnb_query_t* q, const pnb_points_t* pts, const pnb_mlp_t* mlp,
                                   const pnb_shade_opts_t* opts, const float* d_sigma_rgb_fwd, const float* d_ray_color,
-                                  int n_valid, float* d_emb, float* d_color, float* d_dir, float* d_conf,
+                                  int n_valid, int n_pairs, float* d_emb, float* d_color, float* d_dir, float* d_conf,
                                   float* const* d_mlp_w, float* const* d_mlp_b, void* ws, size_t ws_bytes, int flags, int* d_err,
                                   pnb_stream_t stream_) {
     cudaStream_t st = (cudaStream_t)stream_;
@@ -602,9 +612,13 @@ extern "C" int pnb_shade_backward(const pnb_query_t* q, const pnb_points_t* pts,
     cp.q = *q; cp.o = *opts; cp.sigma_rgb = (const float4*)d_sigma_rgb_fwd; cp.d_ray_color = d_ray_color; cp.d_sigma_rgb = L.d_sigma_rgb;
     k_composite_bwd<<<(q->R + 127) / 128, 128, 0, st>>>(cp);
     if (n_valid <= 0) { PNB_CHECK_CUDA(cudaGetLastError()); return PNB_OK; }
-    const int S = n_valid, P = n_valid * PNB_MAX_K;
+    PNB_REQUIRE(n_pairs >= n_valid && n_pairs <= n_valid * PNB_MAX_K, PNB_ERR_INVALID, "pnb_shade_backward: n_pairs %d inconsistent with n_valid %d", n_pairs, n_valid);
+    const int S = n_valid, P = n_pairs;      // pair-level buffers hold one row per VALID (sample, neighbour) pair
     BwdParams p;
     p.q = *q; p.pts = *pts; p.o = *opts; p.n_valid = n_valid;
+    p.n_rows = P; p.pair_off = L.pair_off; p.row_samp = L.row_samp;
+    k_bwd_counts<<<(S + 255) / 256, 256, 0, st>>>(*q, S, L.nv);
+    { int rc = exclusive_scan_u32(L.nv, 0, L.pair_off, (uint32_t)S, L.scan_tmp, st); if (rc) return rc; }
     p.X1 = L.X1; p.H1 = L.H1; p.X3 = L.X3; p.H3 = L.H3; p.H4 = L.H4; p.wc = L.wc; p.wn = L.wn; p.sp = L.sp; p.sg = L.sg; p.pidx = L.pidx;
     p.CX = L.CX; p.C1 = L.C1; p.C2 = L.C2; p.C3 = L.C3; p.O3 = L.O3; p.G1 = L.G1; p.G2 = L.G2; p.G3 = L.G3;
     p.GS1 = L.GS1; p.GS2 = L.GS2; p.GS3 = L.GS3; p.dO3 = L.dO3; p.dsig = L.dsig; p.d_sigma_rgb = L.d_sigma_rgb;

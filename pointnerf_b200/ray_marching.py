@@ -240,6 +240,7 @@ class _RenderFn(torch.autograd.Function):
         ctx.generation = mod._generation          # the backward recomputes from the query / sigma_rgb buffers of THIS run
         ctx.o = mod._last_opts
         ctx.n_valid = q.counters["n_valid"]
+        ctx.n_pairs = q.counters["n_pairs"]
         ctx.sigma_rgb = mod._sigma_rgb          # forward (sigma, rgb) per candidate; valid until the next _run
         ctx.needs = [t.requires_grad for t in (emb, color, pdir, conf)]
         ctx.mlp_shapes = [tuple(t.shape) for t in mlp_params]
@@ -278,7 +279,7 @@ class _RenderFn(torch.autograd.Function):
         # (fp32-faithful LeakyReLU masks) | 2 (diagnostic) three-part split in every tensor-core GEMM
         flags = int(getattr(mod.opt, "pnb_bwd_fp32", 0))
         _lib.check(lib.pnb_shade_backward(_lib.C.byref(q.desc), _lib.C.byref(pts), _lib.C.byref(mlp), _lib.C.byref(ctx.o),
-                                          ctx.sigma_rgb.data_ptr(), g_color.data_ptr(), int(ctx.n_valid), ptr(outs[0]),
+                                          ctx.sigma_rgb.data_ptr(), g_color.data_ptr(), int(ctx.n_valid), int(ctx.n_pairs), ptr(outs[0]),
                                           ptr(outs[1]), ptr(outs[2]), ptr(outs[3]), wp, bp, mod._bwd_ws.data_ptr(),
                                           mod._bwd_ws.numel(), flags, mod._bwd_err.data_ptr(), stream), "pnb_shade_backward")
         grads = []

@@ -104,4 +104,9 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    try:
+        main()
+    except Exception:
+        import traceback
+        print("RANK %s FAILED:\n%s" % (os.environ.get("RANK"), traceback.format_exc()), flush=True)
+        raise

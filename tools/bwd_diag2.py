@@ -15,8 +15,7 @@ def align(x, a=256):
     return (x + a - 1) // a * a
 
 
-def layout(S, cap):
-    P = S * 8
+def layout(S, cap, P):
     items = [("X1", P * 288), ("H1", P * 256), ("X3", P * 272), ("H3", P * 256), ("H4", P * 256), ("wc", P), ("wn", P), ("sp", P), ("sg", P), ("dwc", P),
              ("pidx", P), ("CX", S * 288), ("C1", S * 128), ("C2", S * 128), ("C3", S * 128), ("O3", S * 4), ("G1", P * 288), ("G2", P * 272), ("G3", P * 256),
              ("GS1", S * 288), ("GS2", S * 128), ("GS3", S * 128), ("dO3", S * 4), ("dsig", S)]
@@ -38,10 +37,11 @@ for mode in (1, 0):
     ((out["coarse_raycolor"] ** 2).sum() + 1e-3 * out["conf_coefficient"].sum()).backward()
     torch.cuda.synchronize()
     S = net.last.counters["n_valid"]
+    NP = net.last.counters["n_pairs"]
     ws[mode] = net._bwd_ws.clone()
     cap = net.last.desc.cap_samples
-L = layout(S, cap)
-print("S", S, "P", S * 8)
+L = layout(S, cap, NP)
+print("S", S, "P", NP)
 ld = dict(X1=288, H1=256, X3=272, H3=256, H4=256, CX=288, C1=128, C2=128, C3=128, O3=4, G1=288, G2=272, G3=256, GS1=288, GS2=128, GS3=128, dO3=4)
 for k, (off, n) in L.items():
     if k == "pidx":

@@ -160,10 +160,10 @@ class TrainStep:
             zo, n_zo = pred.sum() * 0.0, 0
         return se, n_se, zo, n_zo
 
-    def step(self, fwd_kwargs, gt, mark=None):
-        """fwd_kwargs: the arguments of NeuralPointsRayMarching.forward for THIS rank's rays; gt: [R_local, 3] colours of those rays.
-        mark: optional callable(name) invoked between the phases (forward / backward / exchange / adam) - bench.py records CUDA
-        events there.  Returns the global loss (a 0-d tensor, identical on every rank)."""
+    def gradients(self, fwd_kwargs, gt, mark=None):
+        """Forward + backward on this rank's rays and the gradient exchange, WITHOUT the optimiser step: afterwards every rank holds the
+        gradient of the un-sharded step on the union of the ranks' rays in `p.grad`.  Returns the local loss term (its sum over the ranks
+        is the global loss)."""
         mark = mark or (lambda name: None)
         mark("start")
         out = self.net(**fwd_kwargs)
@@ -187,11 +187,17 @@ class TrainStep:
             else:
                 allreduce_gradients(self.pt_params + self.mlp_params, self.world, group=self.group)
         mark("exchange")
+        self.last = dict(out=out, n_hit_terms=n_se_g, n_conf_terms=n_zo_g)
+        return loss_local.detach()
+
+    def step(self, fwd_kwargs, gt, mark=None):
+        """fwd_kwargs: the arguments of NeuralPointsRayMarching.forward for THIS rank's rays; gt: [R_local, 3] colours of those rays.
+        mark: optional callable(name) invoked between the phases (forward / backward / exchange / adam) - bench.py records CUDA
+        events there.  Returns the global loss (a 0-d tensor, identical on every rank)."""
+        loss = self.gradients(fwd_kwargs, gt, mark=mark).clone()
         self.opt_mlp.step()
         self.opt_pts.step()
-        mark("adam")
-        loss = loss_local.detach().clone()
+        (mark or (lambda name: None))("adam")
         if self.world > 1:
             dist.all_reduce(loss, op=dist.ReduceOp.SUM, group=self.group)
-        self.last = dict(out=out, n_hit_terms=n_se_g, n_conf_terms=n_zo_g)
         return loss

@@ -2,9 +2,9 @@
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P tests/dist_train_check.py [config]
 
 Checks of the multi-GPU paths on real GPUs:
-  1. optimisation: parallel.TrainStep for k steps, each rank on ITS rays of the step -> the replicas are BIT-identical on every rank
-     (identical all-reduced gradients + identical Adam), and equal - to fp32 summation order - to the un-sharded step on the union of the
-     rays (run by every rank on a second copy of the model);
+  1. optimisation: parallel.TrainStep, each rank on ITS rays of the step -> the exchanged gradient equals - to fp32 summation order - the
+     gradient of the un-sharded step on the union of the rays (run by every rank on a second copy of the model), and after k Adam steps the
+     replicas are BIT-identical on every rank (identical all-reduced gradients + identical Adam);
   2. render: one frame interleave-sharded over the ranks + all-gather == the frame rendered by one rank, bit for bit;
   3. grow: every rank probes its own frames, allgather_new_points, grow_points -> identical clouds, grid rebuilt, render still agrees.
 Prints one JSON line on rank 0; exit code != 0 on any failure."""
@@ -43,26 +43,47 @@ def main():
         rng = np.random.RandomState(0)
         g = torch.Generator().manual_seed(1)
         n_rays = 1024
-        for it in range(3):
+
+        def batch():
             c = cfg.W // 2
             px = rng.randint(c - 150, c + 150, size=(n_rays,)).astype(np.float32)
             py = rng.randint(c - 150, c + 150, size=(n_rays,)).astype(np.float32)
-            pix = np.stack([px, py], -1)
-            gt = torch.rand(n_rays, 3, generator=g).to(dev)
-            sel = np.arange(rank, n_rays, world)
-            loss = ts.step(fwd_kwargs(cfg, pix[sel], dev), gt[torch.from_numpy(sel).to(dev)])
+            return np.stack([px, py], -1), torch.rand(n_rays, 3, generator=g).to(dev)
+
+        sel = np.arange(rank, n_rays, world)
+        sel_t = torch.from_numpy(sel).to(dev)
+        # (a) the exchanged gradient of the sharded step == the gradient of the un-sharded step on the union of the rays
+        #     (compared BEFORE Adam: its sign-like first steps would amplify rounding noise of near-zero gradient entries)
+        pix, gt = batch()
+        l_sh = ts.gradients(fwd_kwargs(cfg, pix[sel], dev), gt[sel_t]).clone()
+        dist.all_reduce(l_sh)
+        l_ref = ts_ref.gradients(fwd_kwargs(cfg, pix, dev), gt)
+        assert abs(float(l_sh) - float(l_ref)) <= 1e-5 * max(abs(float(l_ref)), 1e-3), (float(l_sh), float(l_ref))
+        gerr = 0.0
+        for (n1, p1), (n2, p2) in zip(net.named_parameters(), ref.named_parameters()):
+            if p2.grad is None:
+                assert p1.grad is None, n1
+                continue
+            sc = float(p2.grad.abs().max().clamp_min(1e-12))
+            e = float((p1.grad - p2.grad).abs().max()) / sc
+            assert e <= 2e-4, "gradient of %s: sharded vs un-sharded %.3e of scale" % (n1, e)
+            gerr = max(gerr, e)
+        # (b) k optimisation steps: the replicas stay bit-identical without a broadcast, the loss tracks the un-sharded run
+        for it in range(3):
+            pix, gt = batch()
+            loss = ts.step(fwd_kwargs(cfg, pix[sel], dev), gt[sel_t])
             loss_ref = ts_ref.step(fwd_kwargs(cfg, pix, dev), gt)
-            assert abs(float(loss) - float(loss_ref)) <= 1e-5 * max(abs(float(loss_ref)), 1e-3), (it, float(loss), float(loss_ref))
+            assert abs(float(loss) - float(loss_ref)) <= 2e-3 * max(abs(float(loss_ref)), 1e-3), (it, float(loss), float(loss_ref))
         net.check_errors()
         flat = torch.cat([p.detach().reshape(-1) for p in net.parameters()])
         alls = [torch.empty_like(flat) for _ in range(world)]
         dist.all_gather(alls, flat)
         assert all(torch.equal(alls[0], a) for a in alls), "replicas differ across ranks (sparse=%s)" % sparse
-        flat_ref = torch.cat([p.detach().reshape(-1) for p in ref.parameters()])
-        moved = (flat_ref - torch.cat([p.detach().reshape(-1) for p in harness.build_model(cfg, dev, alpha_bias=3.0)[0].parameters()])).abs().max().item()
-        err = (flat - flat_ref).abs().max().item()
-        assert moved > 1e-3 and err <= 2e-5, "sharded step differs from the un-sharded one: %.3e (parameters moved by %.3e)" % (err, moved)
-        res["train_sparse" if sparse else "train_dense"] = dict(max_abs_diff_vs_unsharded=err, parameters_moved_by=moved, loss=float(loss))
+        moved = (flat - torch.cat([p.detach().reshape(-1) for p in harness.build_model(cfg, dev, alpha_bias=3.0)[0].parameters()])).abs().max().item()
+        assert moved > 1e-3
+        err = gerr
+        res["train_sparse" if sparse else "train_dense"] = dict(max_gradient_diff_vs_unsharded_rel=err, parameters_moved_by=moved, loss=float(loss),
+                                                                replicas_bit_identical=True)
     # ---------------- 2. render: interleave-sharded frame + all-gather == single-rank frame
     net, _, _ = harness.build_model(cfg, dev, alpha_bias=3.0)
     full = scene.make_rays(cfg, scene.centre_patch(cfg, 300))

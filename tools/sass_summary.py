@@ -35,7 +35,7 @@ def main():
             op = m.group(1)
             kernels[cur]["_instr"] += 1
             for mn in MNEMONICS:
-                if op == mn or op.startswith(mn + "."):
+                if op == mn or op.startswith(mn + ".") or (mn in ("ATOM", "RED") and op.startswith(mn)):
                     kernels[cur][mn] += 1
     dem = subprocess.run(["cu++filt"] + list(kernels), capture_output=True, text=True).stdout.splitlines()
     print("SASS mnemonic counts per kernel of %s (sm_100a)" % os.path.relpath(LIB, ROOT))

@@ -2,7 +2,7 @@
 
 usage: python tools/ncu_summary.py gpurun_out/x.ncu-rep profiles/r01_ncu_full_tc5_summary.txt [profiles/r01_ncu_dram_traffic.json]
 """
-import csv, io, json, subprocess, sys
+import csv, io, json, re, subprocess, sys
 
 KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
         "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
@@ -10,7 +10,9 @@ KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "sm__inst_executed_pipe_tensor.sum", "smsp__inst_executed.sum",
         "smsp__issue_active.avg.pct_of_peak_sustained_active", "sm__warps_active.avg.pct_of_peak_sustained_active",
         "l1tex__t_sector_hit_rate.pct", "lts__t_sector_hit_rate.pct", "lts__t_bytes.sum",
-        "l1tex__data_bank_conflicts_pipe_lsu.sum", "smsp__cycles_active.avg",
+        "l1tex__data_bank_conflicts_pipe_lsu.sum", "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed",
+        "l1tex__t_requests_pipe_lsu_mem_global_op_ld.sum", "l1tex__t_output_wavefronts_pipe_lsu_mem_global_op_ld.sum",
+        "l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum", "smsp__cycles_active.avg",
         "launch__grid_size", "launch__block_size", "launch__registers_per_thread",
         "launch__shared_mem_per_block_dynamic", "sm__cycles_elapsed.max"]
 UNIT = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
@@ -24,7 +26,7 @@ def main():
     col = {h: i for i, h in enumerate(hdr)}
     lines, traffic = [], {}
     for r in data:
-        name = r[col["Kernel Name"]].split("(")[0]
+        name = re.sub(r"<.*$", "", r[col["Kernel Name"]].split("(")[0].replace("void ", "")).strip()
         lines.append("== %s" % name)
         for k in KEYS:
             if k in col:

@@ -727,21 +727,25 @@ __global__ void __launch_bounds__(tc7::NTHR, 1) k_shade_tc7(ShadeTcParams p) {
 // Warps (448 threads): 0-7 epilogue (quadrant = w & 3, chunk group = w >> 2), 8-11 builders (thread = row), 12 loader, 13 issuer.
 namespace tc8 {
 constexpr int NBUILD = 128;
-__host__ __device__ constexpr int nthr(int ngrp) { return ngrp * 128 + NBUILD + 64; }
-constexpr int NSTAGE = 5;                 // ring stage = one K block: hi image + lo image
-constexpr int STAGE = 2 * tc::IMG;
+constexpr int NGRP = 2;                   // epilogue warps per TMEM lane quarter (4 measured slower: the quarter's TMEM port is shared)
+constexpr int NEPI_WARPS = 4 * NGRP, NCH = 16 / NGRP;
+constexpr int NTHR = NEPI_WARPS * 32 + NBUILD + 64;
+constexpr int STAGE = 2 * tc::IMG;        // ring stage = one K block: hi image + lo image
 constexpr int NKB1 = 2;                   // K blocks of the frozen layer 1 (operand columns 224..287 of block1.0)
 constexpr int KB1_FIRST = 7;
 constexpr int STAGES_PER_TILE = NKB1 + 8 + 9 + 8;
+constexpr int XPOSE = 2048;               // per-warp transpose buffer of the coalesced `pre` gather: 32 rows x 64 B
+template <int NSTAGE_, bool COOP>
 struct Smem {
-    static constexpr int NWC = 2;
+    static constexpr int NWC = 2, NSTAGE = NSTAGE_;
     unsigned char a_hi[NKB1 * tc::ABLK];
     unsigned char a_lo[NKB1 * tc::ABLK];
     unsigned char b[NSTAGE][STAGE];
     unsigned char xe_hi[2][tc::XE];
     unsigned char xe_lo[2][tc::XE];
+    unsigned char xpose[COOP ? NEPI_WARPS : 1][COOP ? XPOSE : 16];
     float wc[NWC][tc::TM];
-    float alpha_part[2][4][tc::TM];       // [tile parity][epilogue group] partial alpha dot products (own slot each: summed in a fixed order)
+    float alpha_part[2][NGRP][tc::TM];    // [tile parity][epilogue group] partial alpha dot products (own slot each: summed in a fixed order)
     int prow[2][tc::TM];                  // point index of every row (-1: unused row)
     uint32_t qhead[NWC][4], qfirst[NWC][4], qtotal[NWC][4];
     uint64_t bar_full[NSTAGE], bar_empty[NSTAGE], bar_a1_ready, bar_a1_free, bar_acc_full, bar_final, bar_alpha, bar_drain, bar_kblk[8], bar_prow[2];
@@ -786,7 +790,8 @@ __global__ void __launch_bounds__(256) k_point_pre(const float* __restrict__ emb
 
 // One pair row of the frozen pipeline: the PE5(dists) K blocks of the layer-1 operand (operand columns 224..287 -> blocks 0, 1),
 // the block3 extras operand, weight*conf and the row's point index.  Same arithmetic as build_pair_part<PART 1, PACKED>.
-__device__ __forceinline__ void build_pair_frozen(tc8::Smem& sm, const ShadeTcParams& p, int t, int row, int n_valid, int pvi, int pk, int pst, int pcnt) {
+template <class SmemT>
+__device__ __forceinline__ void build_pair_frozen(SmemT& sm, const ShadeTcParams& p, int t, int row, int n_valid, int pvi, int pk, int pst, int pcnt) {
     using namespace tc;
     const pnb_query_t& q = p.q;
     int pidx = -1;
@@ -850,91 +855,111 @@ __device__ __forceinline__ void build_pair_frozen(tc8::Smem& sm, const ShadeTcPa
     *reinterpret_cast<uint4*>(sm.xe_lo[t & 1] + off + 128) = make_uint4(0u, 0u, 0u, 0u);
 }
 
-// One epilogue layer of a warp: chunks grp, grp+NGRP, ... (16 accumulator columns each): accumulator -> (+ bias or + pre[point]) ->
-// LeakyReLU -> bf16 hi/lo -> the same columns, one mbarrier arrive per chunk.  SWP: software-pipelined - the tcgen05.ld of the next
-// chunk is in flight under the conversion of this one, and the wait for this chunk's tcgen05.st is deferred behind the next conversion.
-template <int NGRP>
+// The layer-1 epilogue adds pre[point of the row][column]: 1 KB per row, gathered from L2 / HBM.
+// Reading it "lane = row" (each lane 64 B of its own row per chunk) makes every LDG.128 touch 32 different 128-byte lines = 32
+// wavefronts of the LSU data pipe: 8192 per tile, measured to be what bounds the layer-1 epilogue (ncu: the pipe is 51 % busy over
+// the WHOLE kernel, profiles/r02_ncu_full_summary.txt; E1 8.0 k cycles vs 4.0 k for the bias-only layers).  COOP: the warp reads
+// coalesced instead - LDG j, lane l -> row 8j + l/4, 16-byte quarter l%4 of the chunk: 4 lines per request - and transposes through a
+// 2 KB per-warp shared-memory buffer (XOR-swizzled, conflict-free both ways) into the lane = row order tcgen05.ld delivers.
+template <bool COOP>
 struct Tc8Pf {                                    // chunks of `pre` in flight per epilogue thread (layer 1)
-    static constexpr int NCH = 16 / NGRP, PF = NCH < 3 ? NCH : 3;      // (6 in flight measured slower: 40.0 k vs 37.3 k cycles per tile)
+    static constexpr int PF = 3;                  // (6 in flight measured slower: 40.0 k vs 37.3 k cycles per tile)
     float4 v[PF][4];
-    __device__ __forceinline__ void prefetch(const float4* __restrict__ pp, int grp) {
+    const float4* src[COOP ? 4 : 1];              // COOP: rows 8j + lane/4 (+ this lane's quarter); else: this lane's row
+    __device__ __forceinline__ void init(const float* __restrict__ pre, const int* prow, int lane) {
+        if (COOP) {
 #pragma unroll
-        for (int i = 0; i < PF; ++i)
+            for (int j = 0; j < 4; ++j) src[j] = reinterpret_cast<const float4*>(pre + (size_t)max(prow[8 * j + (lane >> 2)], 0) * 256) + (lane & 3);
+        } else {
+            src[0] = reinterpret_cast<const float4*>(pre + (size_t)max(prow[lane], 0) * 256);   // unused rows: any finite values
+        }
+    }
+    __device__ __forceinline__ void load(int slot, int g) {      // chunk g (16 columns) into v[slot]
 #pragma unroll
-            for (int e = 0; e < 4; ++e) v[i][e] = __ldg(pp + 4 * (grp + NGRP * i) + e);
+        for (int e = 0; e < 4; ++e) v[slot][e] = COOP ? __ldg(src[e] + 4 * g) : __ldg(src[0] + 4 * g + e);
+    }
+    __device__ __forceinline__ void prefetch(int grp) {
+#pragma unroll
+        for (int i = 0; i < PF; ++i) load(i, grp + tc8::NGRP * i);
+    }
+    // the 16 values of this lane's row for the chunk held in v[slot]
+    __device__ __forceinline__ void fetch(int slot, unsigned char* xp, int lane, float4 (&out)[4]) {
+        if (COOP) {
+            const int m = lane >> 2, q = lane & 3;
+            __syncwarp();                         // the previous chunk's reads of the buffer are done
+#pragma unroll
+            for (int j = 0; j < 4; ++j) *reinterpret_cast<float4*>(xp + q * 512 + j * 128 + ((m + 2 * q) & 7) * 16) = v[slot][j];
+            __syncwarp();
+#pragma unroll
+            for (int e = 0; e < 4; ++e) out[e] = *reinterpret_cast<const float4*>(xp + e * 512 + (lane >> 3) * 128 + (((lane & 7) + 2 * e) & 7) * 16);
+        } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) out[e] = v[slot][e];
+        }
     }
 };
-template <int NGRP, bool SWP, bool FIRST>
-__device__ __forceinline__ void tc8_epi_layer(tc8::Smem& sm, uint32_t accb, int grp, const float* __restrict__ bias, const float4* __restrict__ pp,
-                                              Tc8Pf<NGRP>& pfs) {
+
+// One epilogue layer of a warp: chunks grp, grp+NGRP, ... (16 accumulator columns each): accumulator -> (+ bias or + pre[point]) ->
+// LeakyReLU -> bf16 hi/lo -> the same columns, one mbarrier arrive per warp and chunk.
+template <bool FIRST, bool COOP, class SmemT>
+__device__ __forceinline__ void tc8_epi_layer(SmemT& sm, uint32_t accb, int grp, const float* __restrict__ bias, Tc8Pf<COOP>& pfs, unsigned char* xp) {
     using namespace tc;
-    constexpr int NCH = 16 / NGRP;
-    constexpr int PF = Tc8Pf<NGRP>::PF;
-    float4 (&pf)[PF][4] = pfs.v;
-    const bool lane0 = (threadIdx.x & 31) == 0;   // ONE mbarrier arrive per warp and chunk: 32 same-address arrives serialise in the
-                                                  // shared-memory atomic unit (measured: they, not the MMAs, set the tile time)
-    uint32_t v[2][16];
-    if (SWP) tmem_ld16(accb + (uint32_t)(16 * grp), v[0]);
+    constexpr int NGRP = tc8::NGRP, NCH = tc8::NCH, PF = Tc8Pf<COOP>::PF;
+    const int lane = threadIdx.x & 31;
+    const bool lane0 = lane == 0;                 // ONE mbarrier arrive per warp and chunk
+    uint32_t v[16];
 #pragma unroll
     for (int i = 0; i < NCH; ++i) {
         const int g = grp + NGRP * i, c0 = 16 * g;
-        uint32_t* vi = v[SWP ? (i & 1) : 0];
-        if (!SWP) tmem_ld16(accb + (uint32_t)c0, vi);
+        tmem_ld16(accb + (uint32_t)c0, v);
+        float4 b4[4];
+        if (FIRST) pfs.fetch(i % PF, xp, lane, b4);
+        else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) b4[e] = __ldg(reinterpret_cast<const float4*>(bias + c0) + e);
+        }
+        if (FIRST && i + PF < NCH) pfs.load(i % PF, g + NGRP * PF);
         tmem_ld_wait();
-        if (SWP && i + 1 < NCH) tmem_ld16(accb + (uint32_t)(c0 + 16 * NGRP), v[(i + 1) & 1]);
         uint32_t hh[8], ll[8];
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-            float4 b4;
-            if (FIRST) b4 = pf[i % PF][e];
-            else b4 = __ldg(reinterpret_cast<const float4*>(bias + c0) + e);
-            float y0 = __uint_as_float(vi[4 * e]) + b4.x, y1 = __uint_as_float(vi[4 * e + 1]) + b4.y;
-            float y2 = __uint_as_float(vi[4 * e + 2]) + b4.z, y3 = __uint_as_float(vi[4 * e + 3]) + b4.w;
+            float y0 = __uint_as_float(v[4 * e]) + b4[e].x, y1 = __uint_as_float(v[4 * e + 1]) + b4[e].y;
+            float y2 = __uint_as_float(v[4 * e + 2]) + b4[e].z, y3 = __uint_as_float(v[4 * e + 3]) + b4[e].w;
             y0 = fmaxf(y0, LEAKY * y0); y1 = fmaxf(y1, LEAKY * y1); y2 = fmaxf(y2, LEAKY * y2); y3 = fmaxf(y3, LEAKY * y3);
             split_bf16x2(y0, y1, hh[2 * e], ll[2 * e]);
             split_bf16x2(y2, y3, hh[2 * e + 1], ll[2 * e + 1]);
         }
-        if (FIRST && i + PF < NCH) {
-#pragma unroll
-            for (int e = 0; e < 4; ++e) pf[i % PF][e] = __ldg(pp + 4 * (grp + NGRP * (i + PF)) + e);
-        }
-        if (SWP && i > 0) {                        // the previous chunk's stores have had a whole conversion to land
-            tmem_st_wait();
-            tc_fence_before();
-            __syncwarp();
-            if (lane0) mbar_arrive(&sm.bar_kblk[(g - NGRP) >> 1]);
-        }
         tmem_st8(accb + (uint32_t)c0, hh);
         tmem_st8(accb + (uint32_t)c0 + 8u, ll);
-        if (!SWP || i == NCH - 1) {
-            tmem_st_wait();
-            tc_fence_before();
-            __syncwarp();
-            if (lane0) mbar_arrive(&sm.bar_kblk[g >> 1]);
-        }
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane0) mbar_arrive(&sm.bar_kblk[g >> 1]);
     }
 }
 
-// NGRP: epilogue warps per TMEM lane quarter (2 or 4 -> 8 or 16 epilogue warps); SWP: software-pipelined epilogue chunks.
-template <int NGRP, bool SWP>
-__global__ void __launch_bounds__(tc8::nthr(NGRP), 1) k_shade_tc8(ShadeTcParams p) {
+// NSTAGE: stages of the weight ring; COOP: coalesced + transposed gather of the hoisted table (see Tc8Pf).
+template <int NSTAGE, bool COOP>
+__global__ void __launch_bounds__(tc8::NTHR, 1) k_shade_tc8(ShadeTcParams p) {
+    using SmemT = tc8::Smem<NSTAGE, COOP>;
+    constexpr int NGRP = tc8::NGRP;
     using namespace tc;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
-    tc8::Smem& sm = *reinterpret_cast<tc8::Smem*>(smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u));
+    SmemT& sm = *reinterpret_cast<SmemT*>(smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u));
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const pnb_query_t& q = p.q;
     const int n_valid = min(q.counters[PNB_QC_N_VALID], p.hbar_cap);
     const int n_quads = p.pack_cnt[0];
     const int n_tiles = (n_quads + 3) >> 2;
     const int my_tiles = n_tiles > (int)blockIdx.x ? (n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
-    constexpr int NEPI_WARPS = 4 * NGRP;
+    constexpr int NEPI_WARPS = tc8::NEPI_WARPS;
     constexpr int W_BUILD = NEPI_WARPS, W_LOAD = W_BUILD + tc8::NBUILD / 32, W_ISSUE = W_LOAD + 1;
     // last epilogue: 16 chunks over the NGRP epilogue warps + 1 builder warp of a quadrant; the builder warp takes group 0
     constexpr int NG4 = NGRP + 1, NCH4_B = (16 + NG4 - 1) / NG4, NCH4_E = 16 / NG4;
     static_assert(NCH4_B + NGRP * NCH4_E == 16, "last-epilogue chunk split");
 
     if (tid == 0) {
-        for (int s = 0; s < tc8::NSTAGE; ++s) { mbar_init(&sm.bar_full[s], 1); mbar_init(&sm.bar_empty[s], 1); }
+        for (int s = 0; s < NSTAGE; ++s) { mbar_init(&sm.bar_full[s], 1); mbar_init(&sm.bar_empty[s], 1); }
         mbar_init(&sm.bar_a1_ready, tc8::NBUILD / 32);              // one arrive per builder warp
         mbar_init(&sm.bar_a1_free, 1);
         mbar_init(&sm.bar_acc_full, 1);
@@ -975,7 +1000,7 @@ __global__ void __launch_bounds__(tc8::nthr(NGRP), 1) k_shade_tc8(ShadeTcParams 
                     bulk_g2s(sm.b[s], src, IMG, &sm.bar_full[s]);
                     bulk_g2s(sm.b[s] + IMG, src + IMG, IMG, &sm.bar_full[s]);
                 }
-                if (++s == (uint32_t)tc8::NSTAGE) { s = 0; ph ^= 1u; }
+                if (++s == (uint32_t)NSTAGE) { s = 0; ph ^= 1u; }
                 if (++j == (uint32_t)tc8::STAGES_PER_TILE) j = 0;
             }
         }
@@ -1033,7 +1058,7 @@ __global__ void __launch_bounds__(tc8::nthr(NGRP), 1) k_shade_tc8(ShadeTcParams 
                         mma_ts2_w(acc, tcol + 16u, bl + KADV, hiw, idesc, 1u);
                     }
                     mma_commit_w(&sm.bar_empty[s]);
-                    if (++s == (uint32_t)tc8::NSTAGE) { s = 0; ph ^= 1u; }
+                    if (++s == (uint32_t)NSTAGE) { s = 0; ph ^= 1u; }
                 }
                 if (!ok) break;
                 if (l >= 1) ++c_pack;
@@ -1100,20 +1125,19 @@ __global__ void __launch_bounds__(tc8::nthr(NGRP), 1) k_shade_tc8(ShadeTcParams 
         for (int t = 0; t < my_tiles && ok; ++t) {
             // ---- layer 1: accumulator + pre[point of this row] (the hoisted 224 inputs and the bias)
             if (!TW(13, mbar_wait(&sm.bar_prow[t & 1], (uint32_t)(t >> 1) & 1u, p.err, 102))) { ok = false; break; }
-            const int pi = max(sm.prow[t & 1][erow], 0);          // unused rows: any finite values (their outputs are never used)
-            const float4* pp = reinterpret_cast<const float4*>(p.pre + (size_t)pi * 256);
-            Tc8Pf<NGRP> pfs;
-            pfs.prefetch(pp, grp);                               // in flight under the wait for the layer-1 MMAs
+            Tc8Pf<COOP> pfs;
+            pfs.init(p.pre, &sm.prow[t & 1][quad * 32], lane);
+            pfs.prefetch(grp);                                   // in flight under the wait for the layer-1 MMAs
             if (!TW(14, mbar_wait(&sm.bar_acc_full, n_acc & 1u, p.err, 98))) { ok = false; break; }
             ++n_acc;
             tc_fence_after();
-            tc8_epi_layer<NGRP, SWP, true>(sm, tQ + tlane, grp, nullptr, pp, pfs);
+            tc8_epi_layer<true, COOP>(sm, tQ + tlane, grp, nullptr, pfs, sm.xpose[COOP ? warp : 0]);
             TB(15);
             // ---- layers 2, 3
             for (int l = 1; l < 3 && ok; ++l, ++n_acc) {
                 if (!TW(16, mbar_wait(&sm.bar_acc_full, n_acc & 1u, p.err, 98))) { ok = false; break; }
                 tc_fence_after();
-                tc8_epi_layer<NGRP, SWP, false>(sm, ((l & 1) ? tP : tQ) + tlane, grp, p.bias[l], nullptr, pfs);
+                tc8_epi_layer<false, COOP>(sm, ((l & 1) ? tP : tQ) + tlane, grp, p.bias[l], pfs, nullptr);
                 TB(17);
             }
             if (!ok) break;
@@ -1526,17 +1550,16 @@ extern "C" int pnb_shade_forward_tc(const pnb_query_t* q, const pnb_points_t* pt
     PNB_REQUIRE(dev >= 0 && dev < 64, PNB_ERR_UNSUPPORTED, "pnb_shade_forward_tc: device ordinal %d", dev);
     // interleaved (non-swizzled) operand layout: 128-byte alignment of the carve-out is sufficient
     constexpr size_t kSmemMax = 232448;   // 227 KB opt-in limit per block on sm_100
-    const size_t smem_tc7 = sizeof(tc7::Smem) + 128, smem_tc8 = sizeof(tc8::Smem) + 128, smem_ctc2 = sizeof(ctc2::Smem) + 128;
+    const size_t smem_tc7 = sizeof(tc7::Smem) + 128, smem_tc8 = sizeof(tc8::Smem<4, true>) + 128, smem_tc8_old = sizeof(tc8::Smem<5, false>) + 128, smem_ctc2 = sizeof(ctc2::Smem) + 128;
     static_assert(sizeof(tc7::Smem) + 128 <= kSmemMax, "v7 shared-memory carve-out exceeds the per-block limit");
-    static_assert(sizeof(tc8::Smem) + 128 <= kSmemMax, "v8 shared-memory carve-out exceeds the per-block limit");
+    static_assert(sizeof(tc8::Smem<4, true>) + 128 <= kSmemMax && sizeof(tc8::Smem<5, false>) + 128 <= kSmemMax, "v8 shared-memory carve-out exceeds the per-block limit");
     static_assert(sizeof(ctc2::Smem) + 128 <= kSmemMax, "colour kernel shared-memory carve-out exceeds the per-block limit");
     static_assert(tc7::NSTAGE == 4, "the v7 issuer assumes a 4-stage ring");
     if (!configured[dev]) {
         PNB_CHECK_CUDA(cudaFuncSetAttribute(k_shade_tc7, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tc7));
-        PNB_CHECK_CUDA(cudaFuncSetAttribute(k_shade_tc8<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tc8));
-        PNB_CHECK_CUDA(cudaFuncSetAttribute(k_shade_tc8<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tc8));
-        PNB_CHECK_CUDA(cudaFuncSetAttribute(k_shade_tc8<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tc8));
         PNB_CHECK_CUDA(cudaFuncSetAttribute(k_shade_tc8<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tc8));
+        PNB_CHECK_CUDA(cudaFuncSetAttribute(k_shade_tc8<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(tc8::Smem<4, false>) + 128));
+        PNB_CHECK_CUDA(cudaFuncSetAttribute(k_shade_tc8<5, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tc8_old));
         PNB_CHECK_CUDA(cudaFuncSetAttribute(k_color_tc2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_ctc2));
         PNB_CHECK_CUDA(cudaDeviceGetAttribute(&n_sm_of[dev], cudaDevAttrMultiProcessorCount, dev));
         configured[dev] = 1;
@@ -1560,13 +1583,11 @@ extern "C" int pnb_shade_forward_tc(const pnb_query_t* q, const pnb_points_t* pt
         k_pack_scan<<<1, 1024, 0, stream>>>(p.q, cap, w.sc_quads, w.quad_first, w.pack_cnt);
         k_pack_place<<<(cap + 255) / 256, 256, 0, stream>>>(p.q, cap, w.sc_quads, w.quad_local, w.quad_first);
         if (frozen) {
-            // default: 8 epilogue warps, plain chunk loop (measured fastest, profiles/r02_tc8_variants.log); experiment flags of
-            // tools/tc_profile.py: dbg bit 3 = 16 epilogue warps, dbg bit 4 = software-pipelined epilogue chunks
-            const bool e16 = (p.dbg_flags & 8) != 0, swp = (p.dbg_flags & 16) != 0;
-            if (e16 && swp) k_shade_tc8<4, true><<<n_sm, tc8::nthr(4), smem_tc8, stream>>>(p);
-            else if (e16) k_shade_tc8<4, false><<<n_sm, tc8::nthr(4), smem_tc8, stream>>>(p);
-            else if (swp) k_shade_tc8<2, true><<<n_sm, tc8::nthr(2), smem_tc8, stream>>>(p);
-            else k_shade_tc8<2, false><<<n_sm, tc8::nthr(2), smem_tc8, stream>>>(p);
+            // experiment flags of tools/tc_profile.py: dbg bit 3 = 4-stage weight ring without the coalesced gather, dbg bit 4 = coalesced
+            // gather of the hoisted table (4-stage ring); default: the round-2 baseline (5 stages, lane = row gather)
+            if (p.dbg_flags & 16) k_shade_tc8<4, true><<<n_sm, tc8::NTHR, smem_tc8, stream>>>(p);
+            else if (p.dbg_flags & 8) k_shade_tc8<4, false><<<n_sm, tc8::NTHR, sizeof(tc8::Smem<4, false>) + 128, stream>>>(p);
+            else k_shade_tc8<5, false><<<n_sm, tc8::NTHR, smem_tc8_old, stream>>>(p);
         }
         else k_shade_tc7<<<n_sm, tc7::NTHR, smem_tc7, stream>>>(p);
     }

@@ -16,16 +16,19 @@ rays = scene.make_rays(cfg)
 rd = rays["raydir"].to(dev)
 for i in range(3):
     with torch.no_grad():
-        net.render_full(list(cfg.campos), rd, torch.eye(3), cfg.near, cfg.far, [1., 1., 1.])
+        ref_out = net.render_full(list(cfg.campos), rd, torch.eye(3), cfg.near, cfg.far, [1., 1., 1.])
+ref_col, ref_opa = ref_out["coarse_raycolor"].clone(), ref_out["coarse_point_opacity"].clone()
 net.check_errors()
-net.dbg_flags = 4 | int(os.environ.get("PNB_DBG_FLAGS", "0")) | (1 if os.environ.get("PNB_PROF") else 0)       # frozen kernel: +8 = 16 epilogue warps (default 8), +16 = software-pipelined chunks, +32 / +64 = last epilogue without the K-reduction / the h-bar stores (timing experiments)
+net.dbg_flags = 4 | int(os.environ.get("PNB_DBG_FLAGS", "0")) | (1 if os.environ.get("PNB_PROF") else 0)       # frozen kernel: +8 = 4-stage weight ring, +16 = coalesced gather of the hoisted table (4-stage ring), +32 / +64 = last epilogue without the K-reduction / the h-bar stores (timing experiments)
 if os.environ.get("PNB_NO_WEIGHTS"):
     net.dbg_flags |= 0          # (the no-weights bit is a top-level flag)
     L.TC_PAIRS |= L.TC_DBG_NO_WEIGHTS
 torch.cuda.synchronize()
 with torch.no_grad():
-    net.render_full(list(cfg.campos), rd, torch.eye(3), cfg.near, cfg.far, [1., 1., 1.])
+    out = net.render_full(list(cfg.campos), rd, torch.eye(3), cfg.near, cfg.far, [1., 1., 1.])
 torch.cuda.synchronize()
+print("vs the default variant: max |d colour| %.3e  max |d opacity| %.3e" % (float((out["coarse_raycolor"] - ref_col).abs().max()),
+                                                                             float((out["coarse_point_opacity"] - ref_opa).abs().max())))
 per = net._err.cpu().view(torch.int64)[32:32 + 148].tolist()
 n_quads = int(net._err.cpu().view(torch.int64)[32 + 192])
 cyc = [(v & 0xffffffffffff) for v in per]

@@ -443,11 +443,9 @@ __device__ __forceinline__ float last_chunks_packed(const ShadeTcParams& p, uint
                 z[e] = y * wrow;
             }
         }
-        if (!(p.dbg_flags & 32)) {             // (dbg 32: timing experiment without the K-reduction, garbage results)
 #pragma unroll
-            for (int e = 0; e < 16; ++e) z[e] = seg_scan8(z[e], lane, st);
-        }
-        if (swrite && !(p.dbg_flags & 64)) {   // (dbg 64: timing experiment without the h-bar stores)
+        for (int e = 0; e < 16; ++e) z[e] = seg_scan8(z[e], lane, st);
+        if (swrite) {
             if (p.hbar_fmt) {       // the colour kernel's operand image (bf16 hi / lo, core-matrix layout): two 16-byte rows each
                 uint32_t hh[8], ll[8];
 #pragma unroll
@@ -1550,16 +1548,14 @@ extern "C" int pnb_shade_forward_tc(const pnb_query_t* q, const pnb_points_t* pt
     PNB_REQUIRE(dev >= 0 && dev < 64, PNB_ERR_UNSUPPORTED, "pnb_shade_forward_tc: device ordinal %d", dev);
     // interleaved (non-swizzled) operand layout: 128-byte alignment of the carve-out is sufficient
     constexpr size_t kSmemMax = 232448;   // 227 KB opt-in limit per block on sm_100
-    const size_t smem_tc7 = sizeof(tc7::Smem) + 128, smem_tc8 = sizeof(tc8::Smem<4, true>) + 128, smem_tc8_old = sizeof(tc8::Smem<5, false>) + 128, smem_ctc2 = sizeof(ctc2::Smem) + 128;
+    const size_t smem_tc7 = sizeof(tc7::Smem) + 128, smem_tc8 = sizeof(tc8::Smem<4, true>) + 128, smem_ctc2 = sizeof(ctc2::Smem) + 128;
     static_assert(sizeof(tc7::Smem) + 128 <= kSmemMax, "v7 shared-memory carve-out exceeds the per-block limit");
-    static_assert(sizeof(tc8::Smem<4, true>) + 128 <= kSmemMax && sizeof(tc8::Smem<5, false>) + 128 <= kSmemMax, "v8 shared-memory carve-out exceeds the per-block limit");
+    static_assert(sizeof(tc8::Smem<4, true>) + 128 <= kSmemMax, "v8 shared-memory carve-out exceeds the per-block limit");
     static_assert(sizeof(ctc2::Smem) + 128 <= kSmemMax, "colour kernel shared-memory carve-out exceeds the per-block limit");
     static_assert(tc7::NSTAGE == 4, "the v7 issuer assumes a 4-stage ring");
     if (!configured[dev]) {
         PNB_CHECK_CUDA(cudaFuncSetAttribute(k_shade_tc7, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tc7));
         PNB_CHECK_CUDA(cudaFuncSetAttribute(k_shade_tc8<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tc8));
-        PNB_CHECK_CUDA(cudaFuncSetAttribute(k_shade_tc8<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(tc8::Smem<4, false>) + 128));
-        PNB_CHECK_CUDA(cudaFuncSetAttribute(k_shade_tc8<5, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tc8_old));
         PNB_CHECK_CUDA(cudaFuncSetAttribute(k_color_tc2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_ctc2));
         PNB_CHECK_CUDA(cudaDeviceGetAttribute(&n_sm_of[dev], cudaDevAttrMultiProcessorCount, dev));
         configured[dev] = 1;
@@ -1583,11 +1579,8 @@ extern "C" int pnb_shade_forward_tc(const pnb_query_t* q, const pnb_points_t* pt
         k_pack_scan<<<1, 1024, 0, stream>>>(p.q, cap, w.sc_quads, w.quad_first, w.pack_cnt);
         k_pack_place<<<(cap + 255) / 256, 256, 0, stream>>>(p.q, cap, w.sc_quads, w.quad_local, w.quad_first);
         if (frozen) {
-            // experiment flags of tools/tc_profile.py: dbg bit 3 = 4-stage weight ring without the coalesced gather, dbg bit 4 = coalesced
-            // gather of the hoisted table (4-stage ring); default: the round-2 baseline (5 stages, lane = row gather)
-            if (p.dbg_flags & 16) k_shade_tc8<4, true><<<n_sm, tc8::NTHR, smem_tc8, stream>>>(p);
-            else if (p.dbg_flags & 8) k_shade_tc8<4, false><<<n_sm, tc8::NTHR, sizeof(tc8::Smem<4, false>) + 128, stream>>>(p);
-            else k_shade_tc8<5, false><<<n_sm, tc8::NTHR, smem_tc8_old, stream>>>(p);
+            // 4-stage weight ring + coalesced gather of the hoisted table (variants measured: profiles/r02_tc8_experiments.log)
+            k_shade_tc8<4, true><<<n_sm, tc8::NTHR, smem_tc8, stream>>>(p);
         }
         else k_shade_tc7<<<n_sm, tc7::NTHR, smem_tc7, stream>>>(p);
     }

@@ -168,10 +168,13 @@ class TrainStep:
         mark("start")
         out = self.net(**fwd_kwargs)
         se, n_se, zo, n_zo = self.loss_terms(out, gt)
-        cnt = torch.tensor([float(n_se), float(n_zo)], dtype=torch.float64, device=se.device)
-        if self.world > 1:
+        if self.world > 1:      # the global counts stay on the device: no host synchronisation between forward and backward
+            cnt = torch.tensor([float(n_se), float(n_zo)], dtype=torch.float64, device=se.device)
             dist.all_reduce(cnt, op=dist.ReduceOp.SUM, group=self.group)
-        n_se_g, n_zo_g = max(float(cnt[0].item()), 1.0), max(float(cnt[1].item()), 1.0)
+            cnt = torch.clamp(cnt, min=1.0).to(se.dtype)
+            n_se_g, n_zo_g = cnt[0], cnt[1]
+        else:
+            n_se_g, n_zo_g = max(float(n_se), 1.0), max(float(n_zo), 1.0)
         loss_local = se / n_se_g + self.zero_one_weight * zo / n_zo_g
         self.opt_mlp.zero_grad(set_to_none=True)      # the backward hands over fresh gradient tensors: no zero-fill + accumulate per step
         self.opt_pts.zero_grad(set_to_none=True)

@@ -565,13 +565,16 @@ def train_section(D, args, dev, cfg_name="ship_optimise", sparse=False, n_steps=
     acc = dict(forward=0.0, backward=0.0, exchange=0.0, adam=0.0)
     tot = 0.0
     hit = 0
+    host = 0.0
 
     def batch():
         px = rng.randint(0, cfg.W, size=(3600,)).astype(np.float32)
         py = rng.randint(0, cfg.H, size=(3600,)).astype(np.float32)
         gt = torch.rand(3600, 3, generator=g)
         sel = np.arange(D.rank, 3600, D.world)
-        rays = {k: v.to(dev) for k, v in scene.make_rays(cfg, np.stack([px, py], -1)[sel]).items()}
+        # the per-ray tensors go to the device; the camera scalars (position, rotation, near / far, intrinsics) stay host tensors, as a
+        # data loader delivers them (the kernels take them by value: device copies would cost one synchronising D2H read each)
+        rays = {k: (v.to(dev) if k in ("raydir", "pixel_idx") else v) for k, v in scene.make_rays(cfg, np.stack([px, py], -1)[sel]).items()}
         kw = dict(campos=rays["campos"], raydir=rays["raydir"], bg_color=rays["bg_color"], camrotc2w=rays["camrotc2w"], pixel_idx=rays["pixel_idx"],
                   near=rays["near"], far=rays["far"], h=rays["h"], w=rays["w"], intrinsic=rays["intrinsic"])
         return kw, gt[sel].to(dev)
@@ -584,16 +587,37 @@ def train_section(D, args, dev, cfg_name="ship_optimise", sparse=False, n_steps=
             e = torch.cuda.Event(enable_timing=True)
             e.record()
             evs.append((name, e))
+        t_h0 = time.perf_counter()
         ts.step(kw, gt, mark=mark)
+        t_h1 = time.perf_counter()
         torch.cuda.synchronize(dev)
+        if os.environ.get("PNB_TRAIN_PROFILE") and D.rank == 0:
+            st = torch.cuda.memory_stats(dev)
+            sys.stderr.write("[train step %2d] %.2f ms  host %.2f ms  cudaMalloc calls %d  reserved %.2f GB  hit %d\n" % (
+                it, evs[0][1].elapsed_time(evs[-1][1]), (t_h1 - t_h0) * 1e3, st.get("num_device_alloc", -1), st["reserved_bytes.all.current"] / 1e9,
+                int(ts.last["n_hit_terms"] / 3)))
         if it >= n_warm:
+            host += t_h1 - t_h0
             for (n0, a), (n1, b) in zip(evs[:-1], evs[1:]):
                 acc[n1] += a.elapsed_time(b)
             tot += evs[0][1].elapsed_time(evs[-1][1])
             hit += int(ts.last["n_hit_terms"] / 3)
+    if os.environ.get("PNB_TRAIN_PROFILE") and D.rank == 0:      # diagnostic: per-kernel device time of 5 more steps (stderr)
+        from torch.profiler import profile, ProfilerActivity
+        with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
+            for _ in range(5):
+                ts.step(*batch())
+            torch.cuda.synchronize(dev)
+        rows = sorted(prof.key_averages(), key=lambda e: -e.device_time_total)
+        sys.stderr.write("[train profile %s] device time per step %.3f ms, %d events\n" % (cfg_name, sum(e.device_time_total for e in rows) / 5e3, sum(e.count for e in rows) // 5))
+        for e in rows[:8]:
+            sys.stderr.write("   %8.3f ms/step x%-4d %s\n" % (e.device_time_total / 5e3, e.count // 5, e.key[:90]))
+        rows = sorted(prof.key_averages(), key=lambda e: -e.self_cpu_time_total)
+        for e in rows[:12]:
+            sys.stderr.write("   cpu %8.3f ms/step x%-4d %s\n" % (e.self_cpu_time_total / 5e3, e.count // 5, e.key[:90]))
     ms = D.max_over_ranks(tot / n_steps)
     out = dict(steps_per_s=1e3 / ms, ms_per_step=ms, ms_fwd=acc["forward"] / n_steps, ms_bwd=acc["backward"] / n_steps,
-               ms_exchange=acc["exchange"] / n_steps, ms_adam=acc["adam"] / n_steps, mrays_per_s=3600 / ms / 1e3,
+               ms_exchange=acc["exchange"] / n_steps, ms_adam=acc["adam"] / n_steps, ms_host_issue=host / n_steps * 1e3, mrays_per_s=3600 / ms / 1e3,
                hit_rays_per_step=hit / n_steps,
                what="%s: N=%d, 3600 rays per step over %d rank(s), fwd (tcgen05) + bwd (tcgen05 GEMMs) + %s + 2x Adam over all N rows; "
                     "per-phase ms are rank 0's, ms_per_step the max over ranks"

@@ -175,6 +175,19 @@ int pnb_composite_forward(const pnb_query_t* q, const pnb_shade_opts_t* opts, co
                           float* d_ray_color, float* d_opacity, float* d_bg_T, int8_t* d_ray_mask,
                           pnb_stream_t stream);
 
+/* ---- auxiliary training outputs ----
+ * `weight` [R',SR,K], `conf_coefficient` [R',SR,K] and `blend_weight` [R',SR] of the reference's output dict
+ * (models/neural_points_volumetric_model.py:325-329; point_aggregators.py:421-429,727-732; neural_points.py:706-717;
+ * diff_ray_marching.py:536-541) for the R' hit rays listed in d_rows (int64 ray ids, ascending), straight from the compacted query.
+ * d_opacity: the [R,SR] opacity of pnb_composite_forward.  Empty slots follow the reference (weight 0, conf of point 0). */
+int pnb_aux_outputs(const pnb_query_t* q, const pnb_points_t* pts, const long long* d_rows, int n_rows,
+                    const float* d_opacity, float* d_weight, float* d_conf_coefficient, float* d_blend_weight,
+                    pnb_stream_t stream);
+/* d(loss)/d(points_conf) [N] (accumulated into) from d(loss)/d(conf_coefficient) [R',SR,K]: the clamp of neural_points.py:713 is a
+ * straight-through estimator, every entry adds its gradient to the conf of its (clamped-to-0) point index. */
+int pnb_aux_conf_backward(const pnb_query_t* q, const long long* d_rows, int n_rows,
+                          const float* d_grad_conf_coefficient, float* d_grad_conf, pnb_stream_t stream);
+
 /* ---- shading forward on the tensor cores (tcgen05 / TMEM, BF16x3 error-compensated split) ---- */
 /* Packs block1 / block3 / colour-branch weights of a pnb_mlp_t (fp32 W^T buffers) into tcgen05 operand images (hi/lo bf16, UMMA
  * shared-memory layout).  Call once per weight version.  d_out: >= pnb_mlp_pack_bytes() bytes. */

@@ -120,7 +120,7 @@ static int gemm_nn(const GemmCtx& cx, const float* A, long lda, const float* Bt,
         GemmTc g{};
         g.A = A; g.a_rs = lda; g.a_ks = 1; g.B = Bt; g.b_rs = 1; g.b_ks = ldb; g.C = C; g.ldc = ldc; g.M = M; g.N = N; g.K = K;
         g.bias = bias; g.act = act; g.dact = nullptr; g.ldd = 0; g.dact_n = 0; g.err = cx.err; g.precise = cx.precise_all;
-        return gemm_tc(g, 1, nullptr, 0, 0, cx.st);
+        return gemm_tc(g, 1, cx.part, cx.part_bytes, 0, cx.st);     // (the split-K workspace doubles as the buffer of the weight images)
     }
     dim3 g((N + 63) / 64, (M + 127) / 128, 1);
     k_gemm<false><<<g, 256, 0, cx.st>>>(A, lda, 1, Bt, ldb, 1, C, ldc, M, N, K, K, bias, act);
@@ -131,10 +131,17 @@ static int gemm_nt(const GemmCtx& cx, const float* dZ, long ldz, const float* Wt
                    const float* Y = nullptr, long ldy = 0, int ny = 0) {
     if (M <= 0) return PNB_OK;
     if (cx.tc && Kin % 16 == 0 && ldw % 4 == 0 && ldz % 4 == 0) {
+        // a few columns beyond a 256-wide tile (the 16 extras of block3.0) would cost a second pass over dZ on the tensor cores:
+        // they go to the fp32 tiles instead (no activation below them)
+        const int tail = (Kin > 256 && Kin - 256 <= 32 && ny <= 256) ? Kin - 256 : 0;
         GemmTc g{};
-        g.A = dZ; g.a_rs = ldz; g.a_ks = 1; g.B = Wt; g.b_rs = ldw; g.b_ks = 1; g.C = dX; g.ldc = ldx; g.M = M; g.N = Kin; g.K = Nout;
+        g.A = dZ; g.a_rs = ldz; g.a_ks = 1; g.B = Wt; g.b_rs = ldw; g.b_ks = 1; g.C = dX; g.ldc = ldx; g.M = M; g.N = Kin - tail; g.K = Nout;
         g.bias = nullptr; g.act = 0; g.dact = Y; g.ldd = ldy; g.dact_n = ny; g.err = cx.err; g.precise = cx.precise_all;
-        return gemm_tc(g, 1, nullptr, 0, 0, cx.st);
+        int rc = gemm_tc(g, 1, cx.part, cx.part_bytes, 0, cx.st);
+        if (rc || !tail) return rc;
+        dim3 gt((tail + 63) / 64, (M + 127) / 128, 1);
+        k_gemm<false><<<gt, 256, 0, cx.st>>>(dZ, ldz, 1, Wt + (size_t)256 * ldw, 1, ldw, dX + 256, ldx, M, tail, Nout, Nout, nullptr, 0);
+        return PNB_OK;
     }
     dim3 g((Kin + 63) / 64, (M + 127) / 128, 1);
     k_gemm<false><<<g, 256, 0, cx.st>>>(dZ, ldz, 1, Wt, 1, ldw, dX, ldx, M, Kin, Nout, Nout, nullptr, 0);
@@ -671,7 +678,7 @@ extern "C" int pnb_shade_backward(const pnb_query_t* q, const pnb_points_t* pts,
     // block1.0
     gemm_tn_acc(cx, L.X1, 288, L.G3, 256, d_mlp_w[0], 256, P, 288, 256);
     colsum(L.G3, 256, P, 256, d_mlp_b[0], st);
-    gemm_nt(cx, L.G3, 256, mlp->w[0], 256, L.G1, 288, P, 288, 256);                   // dX1
+    gemm_nt(cx, L.G3, 256, mlp->w[0], 256, L.G1, 288, P, 224, 256);                   // dX1: only the 224 feature columns are consumed (k_bwd_scatter; no xyz gradient)
     // scatter to the points
     k_bwd_scatter<<<(int)(((long)P * 4 + 255) / 256), 256, 0, st>>>(p, L.dwc, d_emb, d_color, d_dir, d_conf);
     PNB_CHECK_CUDA(cudaGetLastError());

@@ -418,6 +418,89 @@ __global__ void __launch_bounds__(128) k_composite(CompositeParams p) {
     if (p.bg_T) p.bg_T[r] = T;
 }
 
+// ------------------------------------------------------------------------------------------ auxiliary training outputs
+// `weight`, `conf_coefficient`, `blend_weight` of the reference's output dict (neural_points_volumetric_model.py:325-329 with
+// point_aggregators.py:421-429, 727-732 and neural_points.py:706-717) in the dense [R', SR, K] layout of the R' hit rays, straight from
+// the sample-compacted query: one thread per (hit ray, sample slot).  Unfilled slots follow the reference: position 0, indices -1 ->
+// weight 0, and conf_coefficient = clamp(points_conf[0]) (the reference gathers with the index clamped to 0, neural_points.py:707).
+struct AuxParams {
+    pnb_query_t q;
+    const float* xyz;
+    const float* conf;
+    const long long* rows;     // [n_rows] ray ids of the hit rays, ascending
+    int n_rows;
+    const float* opacity;      // [R, SR] as written by k_composite
+    float* weight;             // [n_rows, SR, K]
+    float* cc;                 // [n_rows, SR, K]
+    float* blend;              // [n_rows, SR]
+    const float* grad_cc;      // backward: [n_rows, SR, K]
+    float* grad_conf;          // backward: [N], accumulated into
+};
+
+__global__ void __launch_bounds__(128) k_aux_outputs(AuxParams p) {
+    const pnb_query_t& q = p.q;
+    const int SR = q.SR, K = q.K;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)p.n_rows * SR) return;
+    const int rr = (int)(idx / SR), j = (int)(idx - (long long)rr * SR);
+    const int r = (int)p.rows[rr];
+    const int n = q.nsamp[r];
+    float lx = 0.f, ly = 0.f, lz = 0.f;
+    const int32_t* pid = nullptr;
+    if (j < n) {
+        const float t = q.t[(size_t)r * q.t_ray_stride + q.steps[(size_t)r * SR + j]];
+        lx = raypos1(q.campos[0], q.raydir[3 * r], t); ly = raypos1(q.campos[1], q.raydir[3 * r + 1], t); lz = raypos1(q.campos[2], q.raydir[3 * r + 2], t);
+        pid = q.cand_pidx + (size_t)(q.samp_off[r] + j) * K;
+    }
+    float w[PNB_MAX_K], wsum = 0.f;
+    const float c_first = fminf(fmaxf(__ldg(p.conf), 1e-4f), 1.0f);
+    float* cc = p.cc + (size_t)idx * K;
+    for (int k = 0; k < K; ++k) {
+        const int pi = pid ? pid[k] : -1;
+        w[k] = 0.f;
+        float c = c_first;
+        if (pi >= 0) {
+            const float dx = __ldg(&p.xyz[3 * pi]) - lx, dy = __ldg(&p.xyz[3 * pi + 1]) - ly, dz = __ldg(&p.xyz[3 * pi + 2]) - lz;
+            w[k] = 1.0f / fmaxf(sqrtf(dx * dx + dy * dy + dz * dz), 1e-6f);
+            c = fminf(fmaxf(__ldg(&p.conf[pi]), 1e-4f), 1.0f);
+        }
+        wsum += w[k];
+        cc[k] = c;
+    }
+    const float inv = fmaxf(wsum, 1e-8f);
+    float* wo = p.weight + (size_t)idx * K;
+    for (int k = 0; k < K; ++k) wo[k] = w[k] / inv;
+    // blend_weight = opacity * exclusive cumprod(1 - opacity + 1e-10)   (diff_ray_marching.py:536-541)
+    const float* op = p.opacity + (size_t)r * SR;
+    float T = 1.0f;
+    for (int i = 0; i < j; ++i) T *= (1.0f - op[i] + 1e-10f);
+    p.blend[idx] = op[j] * T;
+}
+
+// d loss / d points_conf through conf_coefficient: the clamp is a straight-through estimator (value clamp(c), gradient 1,
+// neural_points.py:713), so every entry adds its gradient to the conf of its (clamped) index; the entries of empty slots all land on
+// point 0: summed per warp first, one atomic per warp.
+__global__ void __launch_bounds__(128) k_aux_conf_bwd(AuxParams p) {
+    const pnb_query_t& q = p.q;
+    const int SR = q.SR, K = q.K;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    float g0 = 0.f;
+    if (idx < (long long)p.n_rows * SR) {
+        const int rr = (int)(idx / SR), j = (int)(idx - (long long)rr * SR);
+        const int r = (int)p.rows[rr];
+        const int32_t* pid = j < q.nsamp[r] ? q.cand_pidx + (size_t)(q.samp_off[r] + j) * K : nullptr;
+        const float* g = p.grad_cc + (size_t)idx * K;
+        for (int k = 0; k < K; ++k) {
+            const int pi = pid ? pid[k] : -1;
+            if (pi > 0) atomicAdd(&p.grad_conf[pi], g[k]);
+            else g0 += g[k];
+        }
+    }
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) g0 += __shfl_xor_sync(0xffffffffu, g0, d);
+    if ((threadIdx.x & 31) == 0 && g0 != 0.f) atomicAdd(&p.grad_conf[0], g0);
+}
+
 }  // namespace pnb
 
 using namespace pnb;
@@ -462,6 +545,37 @@ extern "C" int pnb_composite_forward(const pnb_query_t* q, const pnb_shade_opts_
     p.q = *q; p.o = *opts; p.sigma_rgb = (const float4*)d_sigma_rgb;
     p.ray_color = d_ray_color; p.opacity = d_opacity; p.bg_T = d_bg_T; p.ray_mask = d_ray_mask;
     k_composite<<<(q->R + 127) / 128, 128, 0, stream>>>(p);
+    PNB_CHECK_CUDA(cudaGetLastError());
+    return PNB_OK;
+}
+
+extern "C" int pnb_aux_outputs(const pnb_query_t* q, const pnb_points_t* pts, const long long* d_rows, int n_rows, const float* d_opacity,
+                               float* d_weight, float* d_conf_coefficient, float* d_blend_weight, pnb_stream_t stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    PNB_REQUIRE(q && pts && d_opacity && d_weight && d_conf_coefficient && d_blend_weight, PNB_ERR_INVALID, "pnb_aux_outputs: null argument");
+    PNB_REQUIRE(q->K >= 1 && q->K <= PNB_MAX_K, PNB_ERR_UNSUPPORTED, "pnb_aux_outputs: K=%d unsupported", q->K);
+    if (n_rows <= 0) return PNB_OK;
+    PNB_REQUIRE(d_rows, PNB_ERR_INVALID, "pnb_aux_outputs: null row list");
+    AuxParams p;
+    p.q = *q; p.xyz = pts->xyz; p.conf = pts->conf; p.rows = d_rows; p.n_rows = n_rows; p.opacity = d_opacity;
+    p.weight = d_weight; p.cc = d_conf_coefficient; p.blend = d_blend_weight; p.grad_cc = nullptr; p.grad_conf = nullptr;
+    const long long n = (long long)n_rows * q->SR;
+    k_aux_outputs<<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(p);
+    PNB_CHECK_CUDA(cudaGetLastError());
+    return PNB_OK;
+}
+
+extern "C" int pnb_aux_conf_backward(const pnb_query_t* q, const long long* d_rows, int n_rows, const float* d_grad_conf_coefficient,
+                                     float* d_grad_conf, pnb_stream_t stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    PNB_REQUIRE(q && d_grad_conf_coefficient && d_grad_conf, PNB_ERR_INVALID, "pnb_aux_conf_backward: null argument");
+    if (n_rows <= 0) return PNB_OK;
+    PNB_REQUIRE(d_rows, PNB_ERR_INVALID, "pnb_aux_conf_backward: null row list");
+    AuxParams p;
+    p.q = *q; p.xyz = nullptr; p.conf = nullptr; p.rows = d_rows; p.n_rows = n_rows; p.opacity = nullptr;
+    p.weight = nullptr; p.cc = nullptr; p.blend = nullptr; p.grad_cc = d_grad_conf_coefficient; p.grad_conf = d_grad_conf;
+    const long long n = (long long)n_rows * q->SR;
+    k_aux_conf_bwd<<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(p);
     PNB_CHECK_CUDA(cudaGetLastError());
     return PNB_OK;
 }

@@ -142,15 +142,19 @@ class TrainStep:
         self.sparse_points = sparse_points
         self.mlp_params = [p for p in net.aggregator.parameters() if p.requires_grad]
         self.pt_params = [p for p in net.neural_points.parameters() if p.requires_grad]
-        self.opt_mlp = torch.optim.Adam(self.mlp_params, lr=lr, betas=(0.9, 0.999))
-        self.opt_pts = torch.optim.Adam(self.pt_params, lr=plr, betas=(0.9, 0.999))
+        # one fused kernel per optimiser on the GPU (the default multi-tensor path is ~12 launches); same arithmetic on every rank
+        fused = all(p.is_cuda for p in self.mlp_params + self.pt_params)
+        self.opt_mlp = torch.optim.Adam(self.mlp_params, lr=lr, betas=(0.9, 0.999), fused=fused)
+        self.opt_pts = torch.optim.Adam(self.pt_params, lr=plr, betas=(0.9, 0.999), fused=fused)
         self.last = {}
 
     def loss_terms(self, out, gt):
         """Local SUMS and counts: (sum of squared colour errors over hit rays and channels, #terms), (sum of -log(conf + 1e-3), #terms)."""
         mask = out["ray_mask"][0] > 0
         pred = out["coarse_raycolor"][0]
-        se = ((pred - gt[mask]) ** 2).sum()
+        # (boolean-mask indexing would synchronise for the count, which is pred.shape[0])
+        rows = torch.nonzero_static(mask, size=pred.shape[0])[:, 0]
+        se = ((pred - gt.index_select(0, rows)) ** 2).sum()
         n_se = pred.numel()
         cc = out.get("conf_coefficient", None)
         if cc is not None and cc.numel() > 0:

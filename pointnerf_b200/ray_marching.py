@@ -289,6 +289,46 @@ class _RenderFn(torch.autograd.Function):
         return (None, None, outs[0], outs[1], outs[2], outs[3], *grads)
 
 
+class _AuxFn(torch.autograd.Function):
+    """`weight`, `conf_coefficient`, `blend_weight` of the reference's output dict for the R' hit rays, one kernel on the compacted
+    query (pnb_aux_outputs) instead of a dense export + ~20 eager torch ops; differentiable with respect to points_conf through
+    conf_coefficient (straight-through clamp, neural_points.py:713; pnb_aux_conf_backward)."""
+
+    @staticmethod
+    def forward(ctx, mod, q, inds, opacity, conf):
+        lib = _lib.load()
+        npnts = mod.neural_points
+        dev = opacity.device
+        n = int(inds.shape[0])
+        SR, K = int(q.desc.SR), int(q.desc.K)
+        wgt = torch.empty((n, SR, K), dtype=torch.float32, device=dev)
+        cc = torch.empty((n, SR, K), dtype=torch.float32, device=dev)
+        blend = torch.empty((n, SR), dtype=torch.float32, device=dev)
+        pts = points_desc_of(npnts)
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        _lib.check(lib.pnb_aux_outputs(_lib.C.byref(q.desc), _lib.C.byref(pts), inds.data_ptr(), n, opacity.data_ptr(), wgt.data_ptr(),
+                                       cc.data_ptr(), blend.data_ptr(), stream), "pnb_aux_outputs")
+        ctx.mod, ctx.q, ctx.inds, ctx.generation = mod, q, inds, mod._generation
+        ctx.conf_shape = tuple(conf.shape)
+        ctx.mark_non_differentiable(wgt, blend)
+        return wgt, cc, blend
+
+    @staticmethod
+    def backward(ctx, g_w, g_cc, g_b):
+        if g_cc is None:
+            return None, None, None, None, None
+        mod, q = ctx.mod, ctx.q
+        if mod._generation != ctx.generation:
+            raise _lib.PnbError("pnb200: backward() of a forward whose query buffers were overwritten by a later call of the same module")
+        lib = _lib.load()
+        g_cc = g_cc.contiguous().float()
+        g_conf = torch.zeros(ctx.conf_shape, dtype=torch.float32, device=g_cc.device)
+        stream = torch.cuda.current_stream(g_cc.device).cuda_stream
+        _lib.check(lib.pnb_aux_conf_backward(_lib.C.byref(q.desc), ctx.inds.data_ptr(), int(ctx.inds.shape[0]), g_cc.data_ptr(),
+                                             g_conf.data_ptr(), stream), "pnb_aux_conf_backward")
+        return None, None, None, None, g_conf
+
+
 def _init_state(mod):
     """Per-module launch state (weight packs, workspaces).  Works on our module and on the reference's
     NeuralPointsRayMarching after install_into()."""
@@ -322,7 +362,7 @@ def _init_state(mod):
     mod._pnb_ready = True
 
 
-_PATCHED = ("forward", "_run", "check_errors", "render_full", "_point_pre", "_poll_status")
+_PATCHED = ("forward", "_run", "check_errors", "render_full", "_point_pre", "_poll_status", "_queue_status")
 
 
 def install_into(reference_cls):
@@ -368,14 +408,17 @@ class NeuralPointsRayMarching(nn.Module):
         return self._pre
 
     def _poll_status(self, block=False):
-        """Deferred device status of earlier render_full() calls ([err, query counters] copied to pinned memory behind the
-        kernels).  Non-blocking unless `block`; raises PnbError for a call that dropped samples or timed out."""
+        """Deferred device status of earlier render_full() / forward() calls ([err, query counters, backward err] copied to pinned
+        memory behind the kernels).  Non-blocking unless `block`; raises PnbError for a call that dropped samples or timed out."""
         pend = self._status_pending
         while pend and (block or pend[0][0].query()):
             ev, host, R = pend.pop(0)
             ev.synchronize()
-            err, n_valid = int(host[0]), int(host[1 + _lib.QC["n_valid"]])
+            err, n_valid, bwd_err = int(host[0]), int(host[1 + _lib.QC["n_valid"]]), int(host[17])
             self._status_free.append(host)
+            if bwd_err != 0:
+                self._bwd_err.zero_()
+                raise _lib.PnbError("pnb200: tcgen05 GEMM pipeline time-out in an earlier backward pass (code %d)" % bwd_err)
             self._valid_per_ray = max(self._valid_per_ray, n_valid / max(R, 1))
             if err == 9:
                 raise _lib.PnbOverflow("pnb200: an earlier render_full() produced %d valid samples, more than its shading workspace held "
@@ -475,19 +518,30 @@ class NeuralPointsRayMarching(nn.Module):
             if code != 0:
                 raise _lib.PnbError("pnb200: tcgen05 pipeline time-out (code %d)" % code)
 
+    def _queue_status(self, q, dev):
+        """Copies the device status of the call just issued to pinned memory behind its kernels (no host synchronisation); a later
+        call (_poll_status) or check_errors() raises it."""
+        if self._err is None or self.precision == "fp32":
+            return
+        host = self._status_free.pop() if self._status_free else torch.zeros(18, dtype=torch.int32).pin_memory()
+        host[:1].copy_(self._err[:1], non_blocking=True)
+        host[1:17].copy_(q.counters_tensor(), non_blocking=True)
+        be = getattr(self, "_bwd_err", None)
+        if be is not None:
+            host[17:18].copy_(be[:1], non_blocking=True)
+        else:
+            host[17] = 0
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(dev))
+        self._status_pending.append((ev, host, q.R))
+
     def render_full(self, campos, raydir, camrotc2w, near, far, bg_color, t=None):
         """Full-R outputs, fill_invalid semantics, no host sync: dict(coarse_raycolor [1,R,3],
         coarse_point_opacity [1,R,SR], coarse_is_background [1,R,1], ray_mask [1,R]).  No gradients (frozen-cloud pipeline).
         The device status of the call (workspace overflow, time-out) is copied to pinned memory behind the kernels and raised
         by a LATER call or by check_errors(); runner.render_image checks it before returning."""
         q, ray_color, opacity, bg_T, ray_mask = self._run(campos, raydir, camrotc2w, near, far, bg_color, False, t=t, frozen=True)
-        if self._err is not None and self.precision != "fp32":
-            host = self._status_free.pop() if self._status_free else torch.empty(17, dtype=torch.int32).pin_memory()
-            host[:1].copy_(self._err[:1], non_blocking=True)
-            host[1:17].copy_(q.counters_tensor(), non_blocking=True)
-            ev = torch.cuda.Event()
-            ev.record(torch.cuda.current_stream(ray_color.device))
-            self._status_pending.append((ev, host, q.R))
+        self._queue_status(q, ray_color.device)
         return dict(coarse_raycolor=ray_color[None], coarse_point_opacity=opacity[None],
                     coarse_is_background=bg_T[None, :, None], ray_mask=ray_mask[None])
 
@@ -513,7 +567,9 @@ class NeuralPointsRayMarching(nn.Module):
             q = self.last
         else:
             q, ray_color, opacity, bg_T, ray_mask = self._run(*run_args, frozen=True)
-        self.check_errors()
+        # the shading workspace was sized from the query counters (no overflow possible); a pipeline time-out of this call or of the
+        # previous backward is raised by the next call / check_errors() instead of stalling the host here until the forward has finished
+        self._queue_status(q, ray_color.device)
         # compact to the R' rays the reference returns (one host sync already paid for the counters)
         # (the number of hit rays is already on the host with the query counters: no second synchronisation for the compaction)
         inds = torch.nonzero_static(ray_mask, size=int(q.counters["R2"]))[:, 0] if getattr(q, "counters", None) else torch.nonzero(ray_mask)[:, 0]
@@ -527,8 +583,15 @@ class NeuralPointsRayMarching(nn.Module):
         opt = self.opt
         want_aux = (getattr(opt, "sparse_loss_weight", 0) > 0) or ("conf_coefficient" in getattr(opt, "zero_one_loss_items", [])) \
             or getattr(opt, "prob", 0) != 0                       # point_aggregators.py:812-813
-        if want_aux and inds.shape[0] > 0:
-            # weight / conf_coefficient / blend_weight of the reference dict (:325-329): cheap torch ops on the dense export
+        if want_aux and inds.shape[0] > 0 and getattr(opt, "prob", 0) != 1:
+            # weight / conf_coefficient / blend_weight of the reference dict (:325-329): one kernel on the compacted query
+            wgt, conf_coefficient, blend = _AuxFn.apply(self, q, inds, opacity, npnts.points_conf)
+            out["weight"] = wgt[None]
+            out["blend_weight"] = blend[None, ..., None]
+            out["conf_coefficient"] = conf_coefficient[None]
+        elif want_aux and inds.shape[0] > 0:
+            # probe pass (opt.prob == 1, point growing): the same three outputs with eager torch ops on the dense export, which the
+            # probe outputs below need anyway
             cam = make_cam_opts(_to_list(campos)[:3], _to_list(camrotc2w)[:9])
             ex = q.export(cam, want_pers=False, want_dirs=False)
             pidx = ex["sample_pidx"]

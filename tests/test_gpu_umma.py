@@ -73,7 +73,7 @@ def _gemm_tc(A, a_rs, a_ks, B, b_rs, b_ks, M, N, K, ldc, bias=None, act=0, dact=
     l = _lib.load_selftest()
     C = torch.full((M, ldc), 7.0, device="cuda") if C0 is None else C0.clone()
     err = torch.zeros(4, dtype=torch.int32, device="cuda")
-    part = torch.empty(max(splits, 1) * M * N, device="cuda")
+    part = torch.empty(max(max(splits, 1) * M * N, 1 << 19), device="cuda")       # >= 2 MB: also holds the weight images of the k_gemm_tcw path
     ptr = lambda t: t.data_ptr() if t is not None else None
     _lib.check_selftest(l.pnb_gemm_tc_test(A.data_ptr(), a_rs, a_ks, B.data_ptr(), b_rs, b_ks, C.data_ptr(), ldc, M, N, K, ptr(bias), act,
                                            ptr(dact), ldd, dact_n, splits, part.data_ptr(), part.numel() * 4, 1 if C0 is not None else 0,

@@ -20,7 +20,7 @@ g = torch.Generator().manual_seed(1)
 def batch():
     px = rng.randint(0, cfg.W, size=(3600,)).astype(np.float32)
     py = rng.randint(0, cfg.H, size=(3600,)).astype(np.float32)
-    rays = {k: v.to(dev) for k, v in scene.make_rays(cfg, np.stack([px, py], -1)).items()}
+    rays = {k: (v.to(dev) if k in ("raydir", "pixel_idx") else v) for k, v in scene.make_rays(cfg, np.stack([px, py], -1)).items()}
     kw = dict(campos=rays["campos"], raydir=rays["raydir"], bg_color=rays["bg_color"], camrotc2w=rays["camrotc2w"], pixel_idx=rays["pixel_idx"],
               near=rays["near"], far=rays["far"], h=rays["h"], w=rays["w"], intrinsic=rays["intrinsic"])
     return kw, torch.rand(3600, 3, generator=g).to(dev)

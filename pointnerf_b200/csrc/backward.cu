@@ -436,15 +436,52 @@ __global__ void __launch_bounds__(256) k_bwd_reduce_bwd(BwdParams p, float* __re
 __global__ void __launch_bounds__(256) k_bwd_alpha_params(BwdParams p, float* __restrict__ dwa, float* __restrict__ dba) {
     const int c = threadIdx.x;
     const long P = (long)p.n_rows;
-    const long r0 = (long)blockIdx.x * 1024, r1 = min(P, r0 + 1024);
+    // 256-row slabs (a 1024-row slab left most SMs of a 1e5-row batch without a block); the row factors are computed once per block
+    __shared__ float dar_s[256];
+    const long r0 = (long)blockIdx.x * 256, r1 = min(P, r0 + 256);
+    const long mine = r0 + c;
+    dar_s[c] = mine < r1 ? p.dsig[p.row_samp[mine]] * p.wc[mine] * p.sg[mine] : 0.f;
+    __syncthreads();
     float acc = 0.f, accb = 0.f;
-    for (long row = r0; row < r1; ++row) {
-        float dar = p.dsig[p.row_samp[row]] * p.wc[row] * p.sg[row];
-        acc = fmaf(dar, p.H4[row * 256 + c], acc);
+    const int n = (int)(r1 - r0);
+#pragma unroll 4
+    for (int i = 0; i < n; ++i) {
+        const float dar = dar_s[i];
+        acc = fmaf(dar, p.H4[(r0 + i) * 256 + c], acc);
         accb += dar;
     }
     atomicAdd(&dwa[c], acc);
     if (c == 0) atomicAdd(dba, accb);
+}
+
+// dWt[Kin x Nout] += X^T dZ and db[n] += sum_m dZ[m][n] for a tiny Nout (the 128 -> 3 colour head): thread = input column, 256-row slabs
+template <int NOUT>
+__global__ void __launch_bounds__(128) k_dw_small(const float* __restrict__ X, long ldx, const float* __restrict__ dZ, long ldz, float* __restrict__ dWt,
+                                                  long ldw, float* __restrict__ db, int M, int Kin) {
+    __shared__ float dz_s[256][NOUT];
+    const int c = threadIdx.x;
+    const long r0 = (long)blockIdx.x * 256;
+    const int n = (int)min((long)256, (long)M - r0);
+    for (int i = c; i < n * NOUT; i += 128) dz_s[i / NOUT][i % NOUT] = dZ[(r0 + i / NOUT) * ldz + (i % NOUT)];
+    __syncthreads();
+    float acc[NOUT];
+#pragma unroll
+    for (int j = 0; j < NOUT; ++j) acc[j] = 0.f;
+    if (c < Kin) {
+#pragma unroll 4
+        for (int i = 0; i < n; ++i) {
+            const float x = X[(r0 + i) * ldx + c];
+#pragma unroll
+            for (int j = 0; j < NOUT; ++j) acc[j] = fmaf(x, dz_s[i][j], acc[j]);
+        }
+#pragma unroll
+        for (int j = 0; j < NOUT; ++j) atomicAdd(&dWt[(long)c * ldw + j], acc[j]);
+    }
+    if (db && c < NOUT) {
+        float sb = 0.f;
+        for (int i = 0; i < n; ++i) sb += dz_s[i][c];
+        atomicAdd(&db[c], sb);
+    }
 }
 
 // Scatter to the points: embedding (through PE), colour, dir, conf.  4 lanes per pair row.
@@ -647,8 +684,7 @@ extern "C" int pnb_shade_backward(const pnb_query_t* q, const pnb_points_t* pts,
     // ---------------- backward ----------------
     k_bwd_head<<<(S + 255) / 256, 256, 0, st>>>(p);
     // colour branch (each dX GEMM applies the derivative of the LeakyReLU below it in its epilogue)
-    gemm_tn_acc(cx, L.C3, 128, L.dO3, 4, d_mlp_w[8], 3, S, 128, 3);
-    colsum(L.dO3, 4, S, 3, d_mlp_b[8], st);
+    k_dw_small<3><<<(S + 255) / 256, 128, 0, st>>>(L.C3, 128, L.dO3, 4, d_mlp_w[8], 3, d_mlp_b[8], S, 128);     // colour head 128 -> 3 (+ its bias)
     gemm_nt(cx, L.dO3, 4, mlp->w[8], 3, L.GS3, 128, S, 128, 3, L.C3, 128, 128);       // dC3
     gemm_tn_acc(cx, L.C2, 128, L.GS3, 128, d_mlp_w[7], 128, S, 128, 128);
     colsum(L.GS3, 128, S, 128, d_mlp_b[7], st);
@@ -661,7 +697,7 @@ extern "C" int pnb_shade_backward(const pnb_query_t* q, const pnb_points_t* pts,
     gemm_nt(cx, L.GS3, 128, mlp->w[5], 128, L.GS1, 288, S, 288, 128);                 // d(hbar | view PE)
     // K-reduction + alpha branch
     k_bwd_reduce_bwd<<<wb, 256, 0, st>>>(p, L.dwc);
-    k_bwd_alpha_params<<<(P + 1023) / 1024, 256, 0, st>>>(p, d_mlp_w[4], d_mlp_b[4]);
+    k_bwd_alpha_params<<<(P + 255) / 256, 256, 0, st>>>(p, d_mlp_w[4], d_mlp_b[4]);
     // block3.2
     k_lrelu_bwd<<<(int)(((long)P * 256 + 255) / 256), 256, 0, st>>>(L.G3, L.H4, 256, 256, P, 256);
     gemm_tn_acc(cx, L.H3, 256, L.G3, 256, d_mlp_w[3], 256, P, 256, 256);

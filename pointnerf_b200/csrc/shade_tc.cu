@@ -467,6 +467,51 @@ __device__ __forceinline__ float last_chunks_packed(const ShadeTcParams& p, uint
     }
     return apart;
 }
+// One 16-column chunk of the last epilogue from REGISTERS (the deferred form of last_chunks_packed<.., EARLY = true>: identical
+// arithmetic in identical order, so the two forms give bit-identical h-bar / alpha sums): columns c0 .. c0+15 of this lane's row in v.
+__device__ __forceinline__ void last_chunk_from_regs(const ShadeTcParams& p, int c0, const uint32_t* v, float wrow, int st, bool swrite, int sidx, int lane,
+                                                     float& apart) {
+    using namespace tc;
+    const float* bias = p.bias[3];
+    float z[16];
+#pragma unroll
+    for (int e4 = 0; e4 < 4; ++e4) {
+        const float4 bb = __ldg(reinterpret_cast<const float4*>(bias + c0) + e4), ww = __ldg(reinterpret_cast<const float4*>(p.wa + c0) + e4);
+        const float bq[4] = {bb.x, bb.y, bb.z, bb.w}, wq[4] = {ww.x, ww.y, ww.z, ww.w};
+#pragma unroll
+        for (int e1 = 0; e1 < 4; ++e1) {
+            const int e = 4 * e4 + e1;
+            float y = __uint_as_float(v[e]) + bq[e1];
+            y = fmaxf(y, LEAKY * y);
+            apart = fmaf(y, wq[e1], apart);
+            z[e] = y * wrow;
+        }
+    }
+#pragma unroll
+    for (int e = 0; e < 16; ++e) z[e] = seg_scan8(z[e], lane, st);
+    if (swrite) {
+        if (p.hbar_fmt) {
+            uint32_t hh[8], ll[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) split_bf16x2(z[2 * e], z[2 * e + 1], hh[e], ll[e]);
+            unsigned char* dst = reinterpret_cast<unsigned char*>(p.hbar) + ((size_t)(sidx >> 7) * 8 + (c0 >> 5)) * (2 * 8192) +
+                                 tile_offset_bytes<LAYOUT_NONE>(sidx & 127, c0 & 31);
+            *reinterpret_cast<uint4*>(dst) = make_uint4(hh[0], hh[1], hh[2], hh[3]);
+            *reinterpret_cast<uint4*>(dst + 128) = make_uint4(hh[4], hh[5], hh[6], hh[7]);
+            *reinterpret_cast<uint4*>(dst + 8192) = make_uint4(ll[0], ll[1], ll[2], ll[3]);
+            *reinterpret_cast<uint4*>(dst + 8192 + 128) = make_uint4(ll[4], ll[5], ll[6], ll[7]);
+        } else {
+            float4* dst = reinterpret_cast<float4*>(p.hbar + (size_t)sidx * 256 + c0);
+            dst[0] = make_float4(z[0], z[1], z[2], z[3]);
+            dst[1] = make_float4(z[4], z[5], z[6], z[7]);
+            dst[2] = make_float4(z[8], z[9], z[10], z[11]);
+            dst[3] = make_float4(z[12], z[13], z[14], z[15]);
+        }
+    }
+}
+// warpgroup register re-allocation (setmaxnreg: all 4 warps of an aligned warpgroup execute it, convergent)
+template <int N> __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N> __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
 // segment bookkeeping of one quadrant row: first row / index of its sample, whether it is the sample's last row
 struct QuadRow { int st, j; bool live, is_end; };
 __device__ __forceinline__ QuadRow quad_row(uint32_t head, int tot, int lane) {
@@ -728,6 +773,8 @@ constexpr int NBUILD = 128;
 constexpr int NGRP = 2;                   // epilogue warps per TMEM lane quarter (4 measured slower: the quarter's TMEM port is shared)
 constexpr int NEPI_WARPS = 4 * NGRP, NCH = 16 / NGRP;
 constexpr int NTHR = NEPI_WARPS * 32 + NBUILD + 64;
+constexpr int NTHR_DEFER = 512;           // DEFER variant: 4 whole warpgroups (2 x epilogue, builders, {loader, issuer, 2 idle warps}) for setmaxnreg
+constexpr int REG_EPI = 160, REG_BUILD = 152, REG_CTRL = 40;     // 256 x 160 + 128 x 152 + 128 x 40 = 65536 registers
 constexpr int STAGE = 2 * tc::IMG;        // ring stage = one K block: hi image + lo image
 constexpr int NKB1 = 2;                   // K blocks of the frozen layer 1 (operand columns 224..287 of block1.0)
 constexpr int KB1_FIRST = 7;
@@ -937,8 +984,15 @@ __device__ __forceinline__ void tc8_epi_layer(SmemT& sm, uint32_t accb, int grp,
 }
 
 // NSTAGE: stages of the weight ring; COOP: coalesced + transposed gather of the hoisted table (see Tc8Pf).
-template <int NSTAGE, bool COOP>
-__global__ void __launch_bounds__(tc8::NTHR, 1) k_shade_tc8(ShadeTcParams p) {
+// DEFER: the last epilogue of tile t no longer sits between layer 4 of tile t and the layer-1 epilogue of tile t+1.  Every warp still drains
+// its chunks of the layer-4 accumulator into registers right away (bar_drain), but the epilogue warps then go straight on to tile t+1 and
+// work their held chunks off in the gaps where they would otherwise wait for the tensor pipe (before the layer-1 / layer-2 / layer-3
+// accumulator barriers of tile t+1); the builder warps process theirs at once and finalise sigma one tile later.  Holding 128 x 256 fp32
+// next to the layer-1 epilogue's working set needs more registers per epilogue thread than a uniform split of the file gives: the
+// warpgroups re-allocate (setmaxnreg): epilogue 160, builders 152, loader / issuer 40.  Same arithmetic in the same order -> results
+// bit-identical to the non-deferred form.
+template <int NSTAGE, bool COOP, bool DEFER>
+__global__ void __launch_bounds__(DEFER ? tc8::NTHR_DEFER : tc8::NTHR, 1) k_shade_tc8(ShadeTcParams p) {
     using SmemT = tc8::Smem<NSTAGE, COOP>;
     constexpr int NGRP = tc8::NGRP;
     using namespace tc;
@@ -983,6 +1037,9 @@ __global__ void __launch_bounds__(tc8::NTHR, 1) k_shade_tc8(ShadeTcParams p) {
 #define TW(slot, expr) [&]() { if (!prof) return (expr); const long long _t0 = clock64(); const bool _r = (expr); _tm = clock64(); if (lane == 0) prof_add(p, slot, _tm - _t0); return _r; }()
 #define TB(slot) do { if (prof) { const long long _t1 = clock64(); if (lane == 0) prof_add(p, slot, _t1 - _tm); _tm = _t1; } } while (0)
 
+    if (warp >= W_LOAD) {
+        if (DEFER) reg_dec<tc8::REG_CTRL>();
+    }
     if (warp == W_LOAD) {
         // ============================================================ weight ring: one K block (hi + lo image, 32 KB) per stage
         if (lane == 0) {
@@ -1064,9 +1121,12 @@ __global__ void __launch_bounds__(tc8::NTHR, 1) k_shade_tc8(ShadeTcParams p) {
                 if (l == 0) mma_commit_w(&sm.bar_a1_free);
             }
         }
+    } else if (warp > W_ISSUE) {
+        // (DEFER: two idle warps complete the control warpgroup)
     } else if (warp >= W_BUILD) {
         // ============================================================ builders: one warp per quadrant, lane = row; the same warps run
         // chunk group 0 of the last epilogue of the previous tile
+        if (DEFER) reg_inc<tc8::REG_BUILD>();
         const int qw = warp - W_BUILD, row = qw * 32 + lane;
         const uint32_t tlane = (uint32_t)(qw * 32) << 16;
         bool ok = true;

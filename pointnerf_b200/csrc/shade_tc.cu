@@ -20,6 +20,7 @@
 // pairs / cta_group::2, CUDA-core colour branch) were removed in round 2; their measurements stay in profiles/r01_* and DESIGN.md.
 #include "common.cuh"
 #include "umma.cuh"
+#include <type_traits>
 
 namespace pnb {
 using namespace umma;
@@ -509,6 +510,12 @@ __device__ __forceinline__ void last_chunk_from_regs(const ShadeTcParams& p, int
         }
     }
 }
+// Compiler-level anchor for registers written by an asynchronous tcgen05.ld: placed after tcgen05.wait::ld it makes the 16 values "defined
+// here", so no copy of them can be scheduled between the load and its wait when they live across a loop back-edge.
+__device__ __forceinline__ void pin16(uint32_t* v) {
+    asm volatile("" : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]),
+                      "+r"(v[8]), "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15]));
+}
 // warpgroup register re-allocation (setmaxnreg: all 4 warps of an aligned warpgroup execute it, convergent)
 template <int N> __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
 template <int N> __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
@@ -774,7 +781,7 @@ constexpr int NGRP = 2;                   // epilogue warps per TMEM lane quarte
 constexpr int NEPI_WARPS = 4 * NGRP, NCH = 16 / NGRP;
 constexpr int NTHR = NEPI_WARPS * 32 + NBUILD + 64;
 constexpr int NTHR_DEFER = 512;           // DEFER variant: 4 whole warpgroups (2 x epilogue, builders, {loader, issuer, 2 idle warps}) for setmaxnreg
-constexpr int REG_EPI = 160, REG_BUILD = 152, REG_CTRL = 40;     // 256 x 160 + 128 x 152 + 128 x 40 = 65536 registers
+constexpr int REG_EPI = 168, REG_BUILD = 136, REG_CTRL = 40;     // 256 x 168 + 128 x 136 + 128 x 40 = 65536 registers
 constexpr int STAGE = 2 * tc::IMG;        // ring stage = one K block: hi image + lo image
 constexpr int NKB1 = 2;                   // K blocks of the frozen layer 1 (operand columns 224..287 of block1.0)
 constexpr int KB1_FIRST = 7;
@@ -989,7 +996,7 @@ __device__ __forceinline__ void tc8_epi_layer(SmemT& sm, uint32_t accb, int grp,
 // work their held chunks off in the gaps where they would otherwise wait for the tensor pipe (before the layer-1 / layer-2 / layer-3
 // accumulator barriers of tile t+1); the builder warps process theirs at once and finalise sigma one tile later.  Holding 128 x 256 fp32
 // next to the layer-1 epilogue's working set needs more registers per epilogue thread than a uniform split of the file gives: the
-// warpgroups re-allocate (setmaxnreg): epilogue 160, builders 152, loader / issuer 40.  Same arithmetic in the same order -> results
+// warpgroups re-allocate (setmaxnreg): epilogue 168, builders 136, loader / issuer 40.  Same arithmetic in the same order -> results
 // bit-identical to the non-deferred form.
 template <int NSTAGE, bool COOP, bool DEFER>
 __global__ void __launch_bounds__(DEFER ? tc8::NTHR_DEFER : tc8::NTHR, 1) k_shade_tc8(ShadeTcParams p) {
@@ -1130,10 +1137,28 @@ __global__ void __launch_bounds__(DEFER ? tc8::NTHR_DEFER : tc8::NTHR, 1) k_shad
         const int qw = warp - W_BUILD, row = qw * 32 + lane;
         const uint32_t tlane = (uint32_t)(qw * 32) << 16;
         bool ok = true;
+        // sigma of a tile = softplus(alpha dot product - 1) summed over the rows of a sample; the dot product is this warp's partial sum + the
+        // epilogue warps' (bar_alpha), added in a fixed order
+        auto finish_sigma = [&](int tf, float apart, float wrow, int st, bool swrite, int sidx) -> bool {
+            if (!TW(12, mbar_wait(&sm.bar_alpha, (uint32_t)tf & 1u, p.err, 100))) return false;
+            float a = apart;
+#pragma unroll
+            for (int gq = 0; gq < NGRP; ++gq) a += sm.alpha_part[tf & 1][gq][row];          // fixed order: deterministic
+            a += __ldg(p.ba) - 1.0f;
+            const float sp = a > 20.f ? a : log1pf(expf(a));
+            const float zz = seg_scan8(sp * wrow, lane, st);
+            if (swrite) p.sigma[sidx] = zz;
+            return true;
+        };
+        float pd_apart = 0.f, pd_wrow = 0.f;          // DEFER: this warp's share of the tile drained one iteration ago (sigma still to be finished)
+        int pd_st = 0, pd_sidx = 0;
+        bool pd_sw = false;
         for (int t = 0; t <= my_tiles && ok; ++t) {
             if (t < my_tiles) {
                 const int tile = (int)blockIdx.x + t * (int)gridDim.x;
                 if (t > 0 && !TW(8, mbar_wait(&sm.bar_a1_free, (uint32_t)(t - 1) & 1u, p.err, 97))) { ok = false; break; }
+                // DEFER: the per-tile slots (qhead / qfirst / qtotal / wc, parity t & 1) were last read when tile t-2 was drained
+                if (DEFER && t > 1 && !mbar_wait(&sm.bar_drain, (uint32_t)(t - 2) & 1u, p.err, 103)) { ok = false; break; }
                 const int qd = tile * 4 + qw;
                 uint32_t first = 0, nsamp = 0;
                 if (qd < n_quads) { first = p.quad_first[qd]; nsamp = p.quad_first[qd + 1] - first; }
@@ -1153,6 +1178,10 @@ __global__ void __launch_bounds__(DEFER ? tc8::NTHR_DEFER : tc8::NTHR, 1) k_shad
                 if (lane == 0) { mbar_arrive(&sm.bar_a1_ready); mbar_arrive(&sm.bar_prow[t & 1]); }
                 TB(9);
             }
+            // DEFER: sigma of tile t-2 (drained one iteration ago; the epilogue warps finished it in gap C of tile t-1).  This wait must come
+            // BEFORE this warp's arrival on bar_drain for tile t-1 below: the epilogue warps publish tile t-1 (the next bar_alpha phase) only
+            // after that drain barrier, so this waiter can never be overtaken by two phase completions.
+            if (DEFER && t > 1 && !finish_sigma(t - 2, pd_apart, pd_wrow, pd_st, pd_sw, pd_sidx)) { ok = false; break; }
             if (t > 0) {
                 const int tf = t - 1;
                 if (!TW(10, mbar_wait(&sm.bar_final, (uint32_t)tf & 1u, p.err, 99))) { ok = false; break; }
@@ -1163,24 +1192,48 @@ __global__ void __launch_bounds__(DEFER ? tc8::NTHR_DEFER : tc8::NTHR, 1) k_shad
                 const float wrow = sm.wc[tf & 1][row];
                 const float apart = last_chunks_packed<NG4, NCH4_B, true>(p, tP + tlane, 0, wrow, qr.st, swrite, sidx, lane, &sm.bar_drain);
                 TB(11);
-                if (!TW(12, mbar_wait(&sm.bar_alpha, (uint32_t)tf & 1u, p.err, 100))) { ok = false; break; }      // the epilogue warps' partial sums
-                float a = apart;
-#pragma unroll
-                for (int gq = 0; gq < NGRP; ++gq) a += sm.alpha_part[tf & 1][gq][row];          // fixed order: deterministic
-                a += __ldg(p.ba) - 1.0f;
-                const float sp = a > 20.f ? a : log1pf(expf(a));
-                const float zz = seg_scan8(sp * wrow, lane, qr.st);
-                if (swrite) p.sigma[sidx] = zz;
+                if (!DEFER) {
+                    if (!finish_sigma(tf, apart, wrow, qr.st, swrite, sidx)) { ok = false; break; }
+                } else {
+                    // the epilogue warps finish tile tf under tile tf+1: its sigma is completed in the next iteration
+                    pd_apart = apart; pd_wrow = wrow; pd_st = qr.st; pd_sw = swrite; pd_sidx = sidx;
+                }
             }
         }
+        if (DEFER && ok && my_tiles > 0) finish_sigma(my_tiles - 1, pd_apart, pd_wrow, pd_st, pd_sw, pd_sidx);
     } else {
         // ============================================================ epilogue warps
         const int quad = warp & 3, grp = warp >> 2;
         const int erow = quad * 32 + lane;
         const uint32_t tlane = (uint32_t)(quad * 32) << 16;
+        if (DEFER) reg_inc<tc8::REG_EPI>();
         uint32_t n_acc = 0;
         bool ok = true;
+        // DEFER: this warp's chunks of the previous tile's layer-4 accumulator, held in registers and worked off in the gaps of this tile
+        uint32_t hv[DEFER ? NCH4_E : 1][16];
+        float d_wrow = 0.f, d_apart = 0.f;
+        int d_st = 0, d_sidx = 0;
+        bool d_sw = false;
+        auto held = [&](auto first, auto count) {          // chunks [first, first + count) of the held tile (compile-time indices: registers)
+            if constexpr (DEFER) {
+#pragma unroll
+                for (int i = decltype(first)::value; i < decltype(first)::value + decltype(count)::value; ++i)
+                    last_chunk_from_regs(p, 16 * (1 + grp + NG4 * i), hv[i], d_wrow, d_st, d_sw, d_sidx, lane, d_apart);
+            }
+        };
+        auto held_done = [&](int tf) -> bool {             // the held tile is finished: publish this warp's alpha partial sum
+            // alpha_part[tf & 1] last held tile tf-2, which the builder warps read before they drained tile tf-1
+            if (!mbar_wait(&sm.bar_drain, (uint32_t)tf & 1u, p.err, 104)) return false;
+            sm.alpha_part[tf & 1][grp][erow] = d_apart;
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&sm.bar_alpha);
+            return true;
+        };
+        using I0 = std::integral_constant<int, 0>; using I1 = std::integral_constant<int, 1>; using I2 = std::integral_constant<int, 2>;
+        using I4 = std::integral_constant<int, 4>; using I5 = std::integral_constant<int, 5>;
+        static_assert(!DEFER || NCH4_E == 5, "the deferred schedule below splits 5 held chunks as 2 + 2 + 1");
         for (int t = 0; t < my_tiles && ok; ++t) {
+            if (DEFER && t > 0) { held(I0{}, I2{}); TB(21); }          // gap A: the layer-1 MMAs of this tile are running
             // ---- layer 1: accumulator + pre[point of this row] (the hoisted 224 inputs and the bias)
             if (!TW(13, mbar_wait(&sm.bar_prow[t & 1], (uint32_t)(t >> 1) & 1u, p.err, 102))) { ok = false; break; }
             Tc8Pf<COOP> pfs;
@@ -1193,6 +1246,11 @@ __global__ void __launch_bounds__(DEFER ? tc8::NTHR_DEFER : tc8::NTHR, 1) k_shad
             TB(15);
             // ---- layers 2, 3
             for (int l = 1; l < 3 && ok; ++l, ++n_acc) {
+                if (DEFER && t > 0) {                       // gaps B, C: the layer-2 / layer-3 MMAs are running
+                    if (l == 1) held(I2{}, I2{});
+                    else { held(I4{}, I1{}); if (!held_done(t - 1)) { ok = false; break; } }
+                    TB(21);
+                }
                 if (!TW(16, mbar_wait(&sm.bar_acc_full, n_acc & 1u, p.err, 98))) { ok = false; break; }
                 tc_fence_after();
                 tc8_epi_layer<false, COOP>(sm, ((l & 1) ? tP : tQ) + tlane, grp, p.bias[l], pfs, nullptr);
@@ -1204,14 +1262,29 @@ __global__ void __launch_bounds__(DEFER ? tc8::NTHR_DEFER : tc8::NTHR, 1) k_shad
                 tc_fence_after();
                 const QuadRow qr = quad_row(sm.qhead[t & 1][quad], (int)sm.qtotal[t & 1][quad], lane);
                 const int sidx = qr.live ? (int)p.vorder[sm.qfirst[t & 1][quad] + qr.j] : 0;
-                const float apart = last_chunks_packed<NG4, NCH4_E, true>(p, tP + tlane, 1 + grp, sm.wc[t & 1][erow], qr.st, qr.is_end && sidx < n_valid, sidx, lane,
-                                                                          &sm.bar_drain);
-                sm.alpha_part[t & 1][grp][erow] = apart;
-                __syncwarp();
-                TB(19);
-                if (lane == 0) mbar_arrive(&sm.bar_alpha);
+                if constexpr (!DEFER) {
+                    const float apart = last_chunks_packed<NG4, NCH4_E, true>(p, tP + tlane, 1 + grp, sm.wc[t & 1][erow], qr.st, qr.is_end && sidx < n_valid, sidx,
+                                                                              lane, &sm.bar_drain);
+                    sm.alpha_part[t & 1][grp][erow] = apart;
+                    __syncwarp();
+                    TB(19);
+                    if (lane == 0) mbar_arrive(&sm.bar_alpha);
+                } else {
+                    // drain only: accumulator -> registers, release the TMEM region; the arithmetic happens in the gaps of the next tile
+#pragma unroll
+                    for (int i = 0; i < NCH4_E; ++i) tmem_ld16(tP + tlane + (uint32_t)(16 * (1 + grp + NG4 * i)), hv[i]);
+                    d_wrow = sm.wc[t & 1][erow]; d_st = qr.st; d_sidx = sidx; d_sw = qr.is_end && sidx < n_valid; d_apart = 0.f;
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < NCH4_E; ++i) pin16(hv[i]);        // the values exist from here on (tcgen05.ld is asynchronous up to the wait)
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&sm.bar_drain);
+                    TB(19);
+                }
             }
         }
+        if (DEFER && ok && my_tiles > 0) { held(I0{}, I5{}); held_done(my_tiles - 1); }
     }
     if (prof && tid == 0) prof_add(p, 20, clock64() - _tk0);
 #undef TW
@@ -1615,7 +1688,8 @@ extern "C" int pnb_shade_forward_tc(const pnb_query_t* q, const pnb_points_t* pt
     static_assert(tc7::NSTAGE == 4, "the v7 issuer assumes a 4-stage ring");
     if (!configured[dev]) {
         PNB_CHECK_CUDA(cudaFuncSetAttribute(k_shade_tc7, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tc7));
-        PNB_CHECK_CUDA(cudaFuncSetAttribute(k_shade_tc8<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tc8));
+        PNB_CHECK_CUDA(cudaFuncSetAttribute(k_shade_tc8<4, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tc8));
+        PNB_CHECK_CUDA(cudaFuncSetAttribute(k_shade_tc8<4, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tc8));
         PNB_CHECK_CUDA(cudaFuncSetAttribute(k_color_tc2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_ctc2));
         PNB_CHECK_CUDA(cudaDeviceGetAttribute(&n_sm_of[dev], cudaDevAttrMultiProcessorCount, dev));
         configured[dev] = 1;
@@ -1640,7 +1714,9 @@ extern "C" int pnb_shade_forward_tc(const pnb_query_t* q, const pnb_points_t* pt
         k_pack_place<<<(cap + 255) / 256, 256, 0, stream>>>(p.q, cap, w.sc_quads, w.quad_local, w.quad_first);
         if (frozen) {
             // 4-stage weight ring + coalesced gather of the hoisted table (variants measured: profiles/r02_tc8_experiments.log)
-            k_shade_tc8<4, true><<<n_sm, tc8::NTHR, smem_tc8, stream>>>(p);
+            // deferred last epilogue (default; dbg bit 3 = the non-deferred form, bit-identical results)
+            if (p.dbg_flags & 8) k_shade_tc8<4, true, false><<<n_sm, tc8::NTHR, smem_tc8, stream>>>(p);
+            else k_shade_tc8<4, true, true><<<n_sm, tc8::NTHR_DEFER, smem_tc8, stream>>>(p);
         }
         else k_shade_tc7<<<n_sm, tc7::NTHR, smem_tc7, stream>>>(p);
     }

@@ -117,7 +117,7 @@ __device__ __forceinline__ bool mbar_spin_wait(uint64_t* bar, uint32_t parity, i
         if (mbar_test_wait(bar, parity)) return true;
         if (globaltimer_ns_fwd() - t0 > 2000000000ull) break;
     }
-    if (err_flag) atomicExch(err_flag, code);
+    if (err_flag) atomicCAS(err_flag, 0, code);      // the FIRST time-out is the diagnostic one (the others follow from it)
     return false;
 }
 __device__ __forceinline__ uint64_t globaltimer_ns() {
@@ -133,7 +133,7 @@ __device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity, int* e
         if (mbar_try_wait(bar, parity)) return true;
         if (globaltimer_ns() - t0 > 2000000000ull) break;
     }
-    if (err_flag) atomicExch(err_flag, code);
+    if (err_flag) atomicCAS(err_flag, 0, code);      // the FIRST time-out is the diagnostic one (the others follow from it)
     return false;
 }
 

@@ -236,6 +236,23 @@ def test_frozen_table_follows_parameter_updates():
     assert (a1 - g1).abs().max().item() <= 2e-5                     # ... and the frozen path tracks the general one
 
 
+@pytest.mark.parametrize("name,side,over", [("tiny", 64, {}), ("lego_render", 96, {}), ("lego_render", 64, dict(SR=80)), ("truck_8gpu", 48, {})])
+def test_deferred_last_epilogue_is_bit_identical(name, side, over):
+    """k_shade_tc8<DEFER = true> (default: the last epilogue of a tile is worked off in the gaps of the next tile, registers re-allocated
+    between the warpgroups) against the non-deferred form (pnb_dbg_flags bit 3): same arithmetic in the same order -> equal bits.
+    Several tiles per CTA (lego / truck patches) exercise the one-tile-late sigma hand-over between builder and epilogue warps."""
+    cfg = scene.CONFIGS[name]
+    a, _, _ = harness.build_model(cfg, DEV, alpha_bias=3.0, **over)
+    b, _, _ = harness.build_model(cfg, DEV, alpha_bias=3.0, pnb_dbg_flags=8, **over)
+    rays = scene.make_rays(cfg, scene.centre_patch(cfg, side))
+    for rep in range(2):
+        oa, ob = _render_full(a, cfg, rays), _render_full(b, cfg, rays)
+        a.check_errors(); b.check_errors()
+        for k in ("coarse_raycolor", "coarse_point_opacity", "coarse_is_background"):
+            assert torch.equal(oa[k], ob[k]), k
+    assert oa["coarse_point_opacity"].max().item() > 0.05            # the patch is not empty space
+
+
 def test_workspace_overflow_is_safe_and_reported():
     """A frame denser than the workspace heuristic (indoor scene: every ray keeps all SR samples): the dropped samples contribute
     nothing (no uninitialised reads), the call is reported (check_errors / the next call), and the retry is exact."""

@@ -19,7 +19,7 @@ for i in range(3):
         ref_out = net.render_full(list(cfg.campos), rd, torch.eye(3), cfg.near, cfg.far, [1., 1., 1.])
 ref_col, ref_opa = ref_out["coarse_raycolor"].clone(), ref_out["coarse_point_opacity"].clone()
 net.check_errors()
-net.dbg_flags = 4 | int(os.environ.get("PNB_DBG_FLAGS", "0")) | (1 if os.environ.get("PNB_PROF") else 0)       # frozen kernel: +8 = 4-stage weight ring, +16 = coalesced gather of the hoisted table (4-stage ring), +32 / +64 = last epilogue without the K-reduction / the h-bar stores (timing experiments)
+net.dbg_flags = 4 | int(os.environ.get("PNB_DBG_FLAGS", "0")) | (1 if os.environ.get("PNB_PROF") else 0)       # frozen kernel: +8 = the non-deferred last epilogue (k_shade_tc8<.., DEFER = false>)
 if os.environ.get("PNB_NO_WEIGHTS"):
     net.dbg_flags |= 0          # (the no-weights bit is a top-level flag)
     L.TC_PAIRS |= L.TC_DBG_NO_WEIGHTS
@@ -42,12 +42,13 @@ print("per-CTA cycles: min %.2f M  max %.2f M  mean %.2f M -> %.1f k cycles per 
 print("per-CTA kernel cycles (M) @smid:", " ".join("%.1f@%d" % ((v & 0xffffffffffff) / 1e6, v >> 48) for v in per))
 
 if os.environ.get("PNB_PROF") and net.frozen_ok:
-    c = net._err.cpu().view(torch.int64)[1:22].tolist()
+    c = net._err.cpu().view(torch.int64)[1:23].tolist()
     names = ["loader: wait empty", "issuer: wait acc_full (l>0)", "issuer: wait final (l=0)", "issuer: wait a1_ready", "issuer: wait drain",
              "issuer: wait kblk (slow path)", "issuer: wait weights (slow path)", "issuer: MMA issue + commits + fast probes",
              "builder q0: wait a1_free", "builder q0: build", "builder q0: wait final", "builder q0: last-epilogue share", "builder q0: wait alpha",
              "epi warp 0: wait prow", "epi warp 0: wait acc_full (E1)", "epi warp 0: E1 busy", "epi warp 0: wait acc_full (E2,E3)", "epi warp 0: E2+E3 busy",
-             "epi warp 0: wait final", "epi warp 0: last-epilogue share", "kernel total (thread 0)"]
+             "epi warp 0: wait final", "epi warp 0: last-epilogue share (DEFER: drain only)", "kernel total (thread 0)",
+             "epi warp 0: deferred last-epilogue chunks (gaps A-C of the next tile)"]
     tiles0 = (n_tiles - 1) // 148 + 1
     print("block 0 accounting (%d tiles), cycles per tile:" % tiles0)
     for n, v in zip(names, c):

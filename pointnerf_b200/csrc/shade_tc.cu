@@ -913,9 +913,9 @@ __device__ __forceinline__ void build_pair_frozen(SmemT& sm, const ShadeTcParams
 // the WHOLE kernel, profiles/r02_ncu_full_summary.txt; E1 8.0 k cycles vs 4.0 k for the bias-only layers).  COOP: the warp reads
 // coalesced instead - LDG j, lane l -> row 8j + l/4, 16-byte quarter l%4 of the chunk: 4 lines per request - and transposes through a
 // 2 KB per-warp shared-memory buffer (XOR-swizzled, conflict-free both ways) into the lane = row order tcgen05.ld delivers.
-template <bool COOP>
+template <bool COOP, int PF_ = 3>
 struct Tc8Pf {                                    // chunks of `pre` in flight per epilogue thread (layer 1)
-    static constexpr int PF = 3;                  // (6 in flight measured slower: 40.0 k vs 37.3 k cycles per tile)
+    static constexpr int PF = PF_;                  // (6 in flight measured slower: 40.0 k vs 37.3 k cycles per tile)
     float4 v[PF][4];
     const float4* src[COOP ? 4 : 1];              // COOP: rows 8j + lane/4 (+ this lane's quarter); else: this lane's row
     __device__ __forceinline__ void init(const float* __restrict__ pre, const int* prow, int lane) {
@@ -953,10 +953,10 @@ struct Tc8Pf {                                    // chunks of `pre` in flight p
 
 // One epilogue layer of a warp: chunks grp, grp+NGRP, ... (16 accumulator columns each): accumulator -> (+ bias or + pre[point]) ->
 // LeakyReLU -> bf16 hi/lo -> the same columns, one mbarrier arrive per warp and chunk.
-template <bool FIRST, bool COOP, class SmemT>
-__device__ __forceinline__ void tc8_epi_layer(SmemT& sm, uint32_t accb, int grp, const float* __restrict__ bias, Tc8Pf<COOP>& pfs, unsigned char* xp) {
+template <bool FIRST, bool COOP, class SmemT, class PfT>
+__device__ __forceinline__ void tc8_epi_layer(SmemT& sm, uint32_t accb, int grp, const float* __restrict__ bias, PfT& pfs, unsigned char* xp) {
     using namespace tc;
-    constexpr int NGRP = tc8::NGRP, NCH = tc8::NCH, PF = Tc8Pf<COOP>::PF;
+    constexpr int NGRP = tc8::NGRP, NCH = tc8::NCH, PF = PfT::PF;
     const int lane = threadIdx.x & 31;
     const bool lane0 = lane == 0;                 // ONE mbarrier arrive per warp and chunk
     uint32_t v[16];
@@ -998,7 +998,10 @@ __device__ __forceinline__ void tc8_epi_layer(SmemT& sm, uint32_t accb, int grp,
 // next to the layer-1 epilogue's working set needs more registers per epilogue thread than a uniform split of the file gives: the
 // warpgroups re-allocate (setmaxnreg): epilogue 168, builders 136, loader / issuer 40.  Same arithmetic in the same order -> results
 // bit-identical to the non-deferred form.
-template <int NSTAGE, bool COOP, bool DEFER>
+// SCHED (DEFER only): how the 5 held chunks are spread over the gaps of the next tile - before the layer-1 (A) / layer-2 (B) / layer-3 (C)
+// accumulator barriers and before the layer-4 barrier (D): 0 = 2/2/1/0, 1 = 1/2/1/1, 2 = 0/2/2/1 (default: nothing in gap A, which sits on the
+// layer 4 -> layer 1 -> layer 2 critical path).  PFN: chunks of `pre` in flight in the layer-1 epilogue (2 with DEFER: registers).
+template <int NSTAGE, bool COOP, bool DEFER, int SCHED = 0, int PFN = 3>
 __global__ void __launch_bounds__(DEFER ? tc8::NTHR_DEFER : tc8::NTHR, 1) k_shade_tc8(ShadeTcParams p) {
     using SmemT = tc8::Smem<NSTAGE, COOP>;
     constexpr int NGRP = tc8::NGRP;
@@ -1229,14 +1232,17 @@ __global__ void __launch_bounds__(DEFER ? tc8::NTHR_DEFER : tc8::NTHR, 1) k_shad
             if (lane == 0) mbar_arrive(&sm.bar_alpha);
             return true;
         };
-        using I0 = std::integral_constant<int, 0>; using I1 = std::integral_constant<int, 1>; using I2 = std::integral_constant<int, 2>;
-        using I4 = std::integral_constant<int, 4>; using I5 = std::integral_constant<int, 5>;
-        static_assert(!DEFER || NCH4_E == 5, "the deferred schedule below splits 5 held chunks as 2 + 2 + 1");
+        static_assert(!DEFER || NCH4_E == 5, "the deferred schedules split 5 held chunks");
+        constexpr int GA = SCHED == 0 ? 2 : SCHED == 1 ? 1 : 0, GB = 2, GC = SCHED == 2 ? 2 : 1, GD = 5 - GA - GB - GC;
+        using I0 = std::integral_constant<int, 0>; using I5 = std::integral_constant<int, 5>;
+        using NA = std::integral_constant<int, GA>; using NB_ = std::integral_constant<int, GB>; using NC = std::integral_constant<int, GC>;
+        using ND = std::integral_constant<int, GD>;
+        using FB = std::integral_constant<int, GA>; using FC = std::integral_constant<int, GA + GB>; using FD = std::integral_constant<int, GA + GB + GC>;
         for (int t = 0; t < my_tiles && ok; ++t) {
-            if (DEFER && t > 0) { held(I0{}, I2{}); TB(21); }          // gap A: the layer-1 MMAs of this tile are running
+            if (DEFER && t > 0 && GA > 0) { held(I0{}, NA{}); TB(21); }          // gap A: the layer-1 MMAs of this tile are running
             // ---- layer 1: accumulator + pre[point of this row] (the hoisted 224 inputs and the bias)
             if (!TW(13, mbar_wait(&sm.bar_prow[t & 1], (uint32_t)(t >> 1) & 1u, p.err, 102))) { ok = false; break; }
-            Tc8Pf<COOP> pfs;
+            Tc8Pf<COOP, PFN> pfs;
             pfs.init(p.pre, &sm.prow[t & 1][quad * 32], lane);
             pfs.prefetch(grp);                                   // in flight under the wait for the layer-1 MMAs
             if (!TW(14, mbar_wait(&sm.bar_acc_full, n_acc & 1u, p.err, 98))) { ok = false; break; }
@@ -1247,8 +1253,8 @@ __global__ void __launch_bounds__(DEFER ? tc8::NTHR_DEFER : tc8::NTHR, 1) k_shad
             // ---- layers 2, 3
             for (int l = 1; l < 3 && ok; ++l, ++n_acc) {
                 if (DEFER && t > 0) {                       // gaps B, C: the layer-2 / layer-3 MMAs are running
-                    if (l == 1) held(I2{}, I2{});
-                    else { held(I4{}, I1{}); if (!held_done(t - 1)) { ok = false; break; } }
+                    if (l == 1) held(FB{}, NB_{});
+                    else { held(FC{}, NC{}); if (GD == 0 && !held_done(t - 1)) { ok = false; break; } }
                     TB(21);
                 }
                 if (!TW(16, mbar_wait(&sm.bar_acc_full, n_acc & 1u, p.err, 98))) { ok = false; break; }
@@ -1257,6 +1263,11 @@ __global__ void __launch_bounds__(DEFER ? tc8::NTHR_DEFER : tc8::NTHR, 1) k_shad
                 TB(17);
             }
             if (!ok) break;
+            if (DEFER && t > 0 && GD > 0) {                 // gap D: the layer-4 MMAs are running
+                held(FD{}, ND{});
+                if (!held_done(t - 1)) { ok = false; break; }
+                TB(21);
+            }
             {   // this warp's share of the LAST epilogue (chunk groups 1..NGRP of NGRP+1; the builder warps take group 0)
                 if (!TW(18, mbar_wait(&sm.bar_final, (uint32_t)t & 1u, p.err, 101))) { ok = false; break; }
                 tc_fence_after();
@@ -1689,7 +1700,7 @@ extern "C" int pnb_shade_forward_tc(const pnb_query_t* q, const pnb_points_t* pt
     if (!configured[dev]) {
         PNB_CHECK_CUDA(cudaFuncSetAttribute(k_shade_tc7, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tc7));
         PNB_CHECK_CUDA(cudaFuncSetAttribute(k_shade_tc8<4, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tc8));
-        PNB_CHECK_CUDA(cudaFuncSetAttribute(k_shade_tc8<4, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tc8));
+        PNB_CHECK_CUDA(cudaFuncSetAttribute(k_shade_tc8<4, true, true, 2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tc8));
         PNB_CHECK_CUDA(cudaFuncSetAttribute(k_color_tc2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_ctc2));
         PNB_CHECK_CUDA(cudaDeviceGetAttribute(&n_sm_of[dev], cudaDevAttrMultiProcessorCount, dev));
         configured[dev] = 1;
@@ -1715,8 +1726,9 @@ extern "C" int pnb_shade_forward_tc(const pnb_query_t* q, const pnb_points_t* pt
         if (frozen) {
             // 4-stage weight ring + coalesced gather of the hoisted table (variants measured: profiles/r02_tc8_experiments.log)
             // deferred last epilogue (default; dbg bit 3 = the non-deferred form, bit-identical results)
+            // (schedules / prefetch depths measured: profiles/r02_tc8_experiments.log #10)
             if (p.dbg_flags & 8) k_shade_tc8<4, true, false><<<n_sm, tc8::NTHR, smem_tc8, stream>>>(p);
-            else k_shade_tc8<4, true, true><<<n_sm, tc8::NTHR_DEFER, smem_tc8, stream>>>(p);
+            else k_shade_tc8<4, true, true, 2, 2><<<n_sm, tc8::NTHR_DEFER, smem_tc8, stream>>>(p);
         }
         else k_shade_tc7<<<n_sm, tc7::NTHR, smem_tc7, stream>>>(p);
     }

@@ -993,7 +993,7 @@ __device__ __forceinline__ void tc8_epi_layer(SmemT& sm, uint32_t accb, int grp,
 // NSTAGE: stages of the weight ring; COOP: coalesced + transposed gather of the hoisted table (see Tc8Pf).
 // DEFER: the last epilogue of tile t no longer sits between layer 4 of tile t and the layer-1 epilogue of tile t+1.  Every warp still drains
 // its chunks of the layer-4 accumulator into registers right away (bar_drain), but the epilogue warps then go straight on to tile t+1 and
-// work their held chunks off in the gaps where they would otherwise wait for the tensor pipe (before the layer-1 / layer-2 / layer-3
+// work their held chunks off in the gaps where they would otherwise wait for the tensor pipe (before the layer-2 / layer-3 / layer-4
 // accumulator barriers of tile t+1); the builder warps process theirs at once and finalise sigma one tile later.  Holding 128 x 256 fp32
 // next to the layer-1 epilogue's working set needs more registers per epilogue thread than a uniform split of the file gives: the
 // warpgroups re-allocate (setmaxnreg): epilogue 168, builders 136, loader / issuer 40.  Same arithmetic in the same order -> results

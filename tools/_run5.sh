@@ -1,1 +1,1 @@
-for f in 0 16 32 48 64 80; do echo "=== dbg flags $f"; PNB_PROF=1 PNB_DBG_FLAGS=$f timeout 200 python tools/tc_profile.py 2>&1 | grep "vs the default\|cycles per 128-row\|issuer: MMA\|E1 busy\|wait acc_full\|wait final\|deferred\|builder q0: last"; done
+for f in 0 16; do echo "=== dbg flags $f"; PNB_PROF=1 PNB_DBG_FLAGS=$f timeout 200 python tools/tc_profile.py 2>&1 | grep "vs the default\|cycles per 128-row\|issuer: MMA\|loader\|wait weights"; done

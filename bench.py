@@ -478,8 +478,9 @@ def main():
             with torch.no_grad():
                 net.render_full(cam[0], q.raydir, cam[1], cam[2], cam[3], cam[4])
         cold_step(0)
-        ms_c = time_region(D, flush, cold_step, 3)
-        sub["cold"] = dict(value=R_img * 3 / (ms_c * 1e-3) / 1e6, unit="Mrays/s", ms_per_frame=ms_c / 3,
+        ms_cs = [time_region(D, flush, cold_step, 3) for _ in range(2)]      # host synchronisations inside: the faster of two regions (shared host)
+        ms_c = min(ms_cs)
+        sub["cold"] = dict(value=R_img * 3 / (ms_c * 1e-3) / 1e6, unit="Mrays/s", ms_per_frame=ms_c / 3, regions_ms_per_frame=[m / 3 for m in ms_cs],
                            what="voxel grid build (incl. its host synchronisation for the counters) + per-point layer-1 table inside every step")
     del net
     torch.cuda.empty_cache()

@@ -119,6 +119,8 @@ typedef struct {
     float vsize_z;      /* un-scaled opt.vsize[2]  (neural_points_volumetric_model.py:272) */
     float bg_color[3];
     int32_t raydist_mode_unit;
+    int32_t agg_intrp_order; /* opt.agg_intrp_order (point_aggregators.py:573-633): 2 = density per neighbour, then the weighted sum
+                              * (every shipped script; 0 is read as 2); 1 = alpha_branch on the K-aggregated feature */
 } pnb_shade_opts_t;
 
 /* MLP parameters, fp32, W^T layout [in][out] (transposed once per optimiser step by the host side). */

@@ -22,7 +22,7 @@ from pointnerf_b200 import scene  # noqa: E402
 OUT = os.path.join(ROOT, "tests", "golden")
 
 
-def build_reference_net(cfg, alpha_bias, SR=24, is_train=False):
+def build_reference_net(cfg, alpha_bias, SR=24, is_train=False, extra_flags=()):
     ref_shim.install()
     from models.neural_points_volumetric_model import NeuralPointsRayMarching
     from models.neural_points.neural_points import NeuralPoints
@@ -31,7 +31,7 @@ def build_reference_net(cfg, alpha_bias, SR=24, is_train=False):
     vs = str(cfg.vsize)
     opt = ref_shim.make_opt(["--vsize", vs, vs, vs, "--P", str(cfg.P), "--SR", str(SR), "--K", str(cfg.K),
                              "--kernel_size"] + [str(cfg.kernel_size)] * 3 + ["--query_size"] + [str(cfg.query_size)] * 3 +
-                            ["--ranges"] + [str(v) for v in scene.ranges_for(cfg)], is_train=is_train)
+                            ["--ranges"] + [str(v) for v in scene.ranges_for(cfg)] + list(extra_flags), is_train=is_train)
     pts = scene.make_points(cfg)
     torch.manual_seed(0)
     agg = PointAggregator(opt)
@@ -47,8 +47,8 @@ def build_reference_net(cfg, alpha_bias, SR=24, is_train=False):
     return net, agg, npts, pts, opt
 
 
-def golden_case(name, cfg, pixels, alpha_bias, SR=24):
-    net, agg, npts, pts, opt = build_reference_net(cfg, alpha_bias, SR=SR)
+def golden_case(name, cfg, pixels, alpha_bias, SR=24, extra_flags=()):
+    net, agg, npts, pts, opt = build_reference_net(cfg, alpha_bias, SR=SR, extra_flags=extra_flags)
     rays = scene.make_rays(cfg, pixels)
     out = net(rays["campos"], rays["raydir"], bg_color=rays["bg_color"], camrotc2w=rays["camrotc2w"],
               pixel_idx=rays["pixel_idx"], near=rays["near"], far=rays["far"], h=rays["h"], w=rays["w"],
@@ -63,7 +63,7 @@ def golden_case(name, cfg, pixels, alpha_bias, SR=24):
     loss.backward()
     g = {n: p.grad for n, p in net.named_parameters() if p.grad is not None}
     fx = dict(
-        alpha_bias=np.float32(alpha_bias), SR=np.int32(SR), pixels=np.asarray(pixels, np.float32),
+        alpha_bias=np.float32(alpha_bias), SR=np.int32(SR), pixels=np.asarray(pixels, np.float32), agg_intrp_order=np.int32(opt.agg_intrp_order),
         ranges6=rng_t.detach().numpy(), scaled_vdim=sdim, counters=np.array([query_oracle.last_counters[k] for k in query_oracle.COUNTER_NAMES], np.int32),
         ray_mask=out["ray_mask"][0].numpy(), sample_pidx=qp[0][0].numpy(), sample_loc=qp[1][0].detach().numpy(),
         sample_loc_w=qp[2][0].numpy(),
@@ -164,9 +164,15 @@ if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "keys":
         golden_output_keys()
         sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "order1":
+        tiny = scene.CONFIGS["tiny"]
+        golden_case("tiny_order1", tiny, scene.centre_patch(tiny, 40), alpha_bias=4.0, extra_flags=["--agg_intrp_order", "1"])
+        sys.exit(0)
     tiny = scene.CONFIGS["tiny"]
     golden_case("tiny_opaque", tiny, scene.centre_patch(tiny, 40), alpha_bias=4.0)
     golden_case("tiny_thin_sr8", tiny, scene.centre_patch(tiny, 40), alpha_bias=0.0, SR=8)
+    # agg_intrp_order = 1 (point_aggregators.py:573-599: alpha_branch on the K-aggregated feature), SURVEY 8(f) rank 4
+    golden_case("tiny_order1", tiny, scene.centre_patch(tiny, 40), alpha_bias=4.0, extra_flags=["--agg_intrp_order", "1"])
     golden_probe("tiny_probe", tiny, scene.centre_patch(tiny, 40), alpha_bias=4.0)
     golden_hyper()
     golden_checkpoint_layout()

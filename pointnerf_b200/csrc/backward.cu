@@ -379,7 +379,7 @@ __global__ void __launch_bounds__(256) k_bwd_reduce_fwd(BwdParams p) {
             hb[c] = fmaf(v, wck, hb[c]);
         }
         for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
-        if (lane == 0) {
+        if (lane == 0 && p.o.agg_intrp_order != 1) {
             float x = a + __ldg(p.ba) - 1.0f;
             p.sp[r0 + k] = x > 20.f ? x : log1pf(expf(x));
             p.sg[r0 + k] = 1.0f / (1.0f + expf(-x));
@@ -387,6 +387,19 @@ __global__ void __launch_bounds__(256) k_bwd_reduce_fwd(BwdParams p) {
     }
 #pragma unroll
     for (int c = 0; c < 8; ++c) p.CX[(long)warp * 288 + lane + 32 * c] = hb[c];
+    if (p.o.agg_intrp_order == 1 && nrow > 0) {
+        // agg_intrp_order 1 (point_aggregators.py:573-587): the density comes from the aggregated feature; its softplus / sigmoid are
+        // kept in the slot of the sample's FIRST row
+        float a = 0.f;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) a = fmaf(hb[c], __ldg(&p.wa[lane + 32 * c]), a);
+        for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+        if (lane == 0) {
+            float x = a + __ldg(p.ba) - 1.0f;
+            p.sp[r0] = x > 20.f ? x : log1pf(expf(x));
+            p.sg[r0] = 1.0f / (1.0f + expf(-x));
+        }
+    }
 }
 
 // colour head: O3 raw -> d(raw) ; sigma gradient per valid sample
@@ -416,6 +429,28 @@ __global__ void __launch_bounds__(256) k_bwd_reduce_bwd(BwdParams p, float* __re
 #pragma unroll
     for (int c = 0; c < 8; ++c) dh[c] = p.GS1[(long)warp * 288 + lane + 32 * c];
     const float ds = p.dsig[warp];
+    if (p.o.agg_intrp_order == 1) {
+        // order 1: sigma = softplus(<wa, hbar> + ba - 1): the density gradient joins the colour branch's d hbar; dwc = <d hbar, H4>
+        if (nrow > 0) {
+            const float dar = ds * p.sg[r0];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) dh[c] = fmaf(dar, __ldg(&p.wa[lane + 32 * c]), dh[c]);
+        }
+        for (int k = 0; k < nrow; ++k) {
+            const long row = r0 + k;
+            const float wck = p.wc[row];
+            const float* h = p.H4 + row * 256;
+            float dot = 0.f;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                dot = fmaf(dh[c], h[lane + 32 * c], dot);
+                p.G3[row * 256 + lane + 32 * c] = wck * dh[c];
+            }
+            for (int o = 16; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+            if (lane == 0) dwc[row] = dot;
+        }
+        return;
+    }
     for (int k = 0; k < nrow; ++k) {
         const long row = r0 + k;
         const float wck = p.wc[row];
@@ -448,6 +483,27 @@ __global__ void __launch_bounds__(256) k_bwd_alpha_params(BwdParams p, float* __
     for (int i = 0; i < n; ++i) {
         const float dar = dar_s[i];
         acc = fmaf(dar, p.H4[(r0 + i) * 256 + c], acc);
+        accb += dar;
+    }
+    atomicAdd(&dwa[c], acc);
+    if (c == 0) atomicAdd(dba, accb);
+}
+
+// agg_intrp_order 1: dwa[c] += sum_s dalpha_raw[s] * hbar[s][c] ; dba += sum_s dalpha_raw[s]   (per valid sample, hbar = CX[:, :256])
+__global__ void __launch_bounds__(256) k_bwd_alpha_params_o1(BwdParams p, float* __restrict__ dwa, float* __restrict__ dba) {
+    const int c = threadIdx.x;
+    const long S = (long)p.n_valid;
+    __shared__ float dar_s[256];
+    const long s0 = (long)blockIdx.x * 256, s1 = min(S, s0 + 256);
+    const long mine = s0 + c;
+    dar_s[c] = (mine < s1 && p.pair_off[mine + 1] > p.pair_off[mine]) ? p.dsig[mine] * p.sg[p.pair_off[mine]] : 0.f;
+    __syncthreads();
+    float acc = 0.f, accb = 0.f;
+    const int n = (int)(s1 - s0);
+#pragma unroll 4
+    for (int i = 0; i < n; ++i) {
+        const float dar = dar_s[i];
+        acc = fmaf(dar, p.CX[(s0 + i) * 288 + c], acc);
         accb += dar;
     }
     atomicAdd(&dwa[c], acc);
@@ -697,7 +753,8 @@ extern "C" int pnb_shade_backward(const pnb_query_t* q, const pnb_points_t* pts,
     gemm_nt(cx, L.GS3, 128, mlp->w[5], 128, L.GS1, 288, S, 288, 128);                 // d(hbar | view PE)
     // K-reduction + alpha branch
     k_bwd_reduce_bwd<<<wb, 256, 0, st>>>(p, L.dwc);
-    k_bwd_alpha_params<<<(P + 255) / 256, 256, 0, st>>>(p, d_mlp_w[4], d_mlp_b[4]);
+    if (p.o.agg_intrp_order == 1) k_bwd_alpha_params_o1<<<(S + 255) / 256, 256, 0, st>>>(p, d_mlp_w[4], d_mlp_b[4]);
+    else k_bwd_alpha_params<<<(P + 255) / 256, 256, 0, st>>>(p, d_mlp_w[4], d_mlp_b[4]);
     // block3.2
     k_lrelu_bwd<<<(int)(((long)P * 256 + 255) / 256), 256, 0, st>>>(L.G3, L.H4, 256, 256, P, 256);
     gemm_tn_acc(cx, L.H3, 256, L.G3, 256, d_mlp_w[3], 256, P, 256, 256);

@@ -326,8 +326,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_shade_fwd(ShadeParams p) {
             uint32_t s = sm.samp[tid];
             if (s != 0xffffffffu) {
                 float sg = 0.f;
+                if (p.o.agg_intrp_order == 1) {
+                    // agg_intrp_order 1 (point_aggregators.py:573-587): density from the K-aggregated feature (still in sm.H)
+                    const float* wa = p.mlp.w[4];
+                    float a = 0.f;
+                    for (int c = 0; c < 256; ++c) a = fmaf(sm.H[tid * HS + c], __ldg(&wa[c]), a);
+                    const float x = a + __ldg(&p.mlp.b[4][0]) - 1.0f;
+                    sg = x > 20.f ? x : log1pf(expf(x));
+                } else {
 #pragma unroll
-                for (int k = 0; k < PNB_MAX_K; ++k) sg += sm.alpha[tid * PNB_MAX_K + k] * sm.wc[tid * PNB_MAX_K + k];
+                    for (int k = 0; k < PNB_MAX_K; ++k) sg += sm.alpha[tid * PNB_MAX_K + k] * sm.wc[tid * PNB_MAX_K + k];
+                }
                 float4 o4;
                 o4.x = sg;
                 o4.y = 1.0f / (1.0f + expf(-B1[tid * XS + 0])) * (1.0f + 2.0f * 0.001f) - 0.001f;  // raw2out_color

@@ -410,6 +410,7 @@ __device__ __forceinline__ float last_chunks_packed(const ShadeTcParams& p, uint
                                                     uint64_t* drain_bar = nullptr) {
     using namespace tc;
     const float* bias = p.bias[3];
+    const bool order1 = p.o.agg_intrp_order == 1;
     float apart = 0.f;
     uint32_t vv[EARLY ? NCHUNK : 2][16];
     if (EARLY) {
@@ -440,12 +441,16 @@ __device__ __forceinline__ float last_chunks_packed(const ShadeTcParams& p, uint
                 const int e = 4 * e4 + e1;
                 float y = __uint_as_float(v[e]) + bq[e1];
                 y = fmaxf(y, LEAKY * y);
-                apart = fmaf(y, wq[e1], apart);
+                if (!order1) apart = fmaf(y, wq[e1], apart);
                 z[e] = y * wrow;
             }
         }
 #pragma unroll
         for (int e = 0; e < 16; ++e) z[e] = seg_scan8(z[e], lane, st);
+        if (order1) {       // agg_intrp_order 1: the alpha dot product runs over the K-aggregated feature (complete on the sample's last row)
+#pragma unroll
+            for (int e = 0; e < 16; ++e) apart = fmaf(z[e], __ldg(p.wa + c0 + e), apart);
+        }
         if (swrite) {
             if (p.hbar_fmt) {       // the colour kernel's operand image (bf16 hi / lo, core-matrix layout): two 16-byte rows each
                 uint32_t hh[8], ll[8];
@@ -474,6 +479,7 @@ __device__ __forceinline__ void last_chunk_from_regs(const ShadeTcParams& p, int
                                                      float& apart) {
     using namespace tc;
     const float* bias = p.bias[3];
+    const bool order1 = p.o.agg_intrp_order == 1;
     float z[16];
 #pragma unroll
     for (int e4 = 0; e4 < 4; ++e4) {
@@ -484,12 +490,16 @@ __device__ __forceinline__ void last_chunk_from_regs(const ShadeTcParams& p, int
             const int e = 4 * e4 + e1;
             float y = __uint_as_float(v[e]) + bq[e1];
             y = fmaxf(y, LEAKY * y);
-            apart = fmaf(y, wq[e1], apart);
+            if (!order1) apart = fmaf(y, wq[e1], apart);
             z[e] = y * wrow;
         }
     }
 #pragma unroll
     for (int e = 0; e < 16; ++e) z[e] = seg_scan8(z[e], lane, st);
+    if (order1) {
+#pragma unroll
+        for (int e = 0; e < 16; ++e) apart = fmaf(z[e], __ldg(p.wa + c0 + e), apart);
+    }
     if (swrite) {
         if (p.hbar_fmt) {
             uint32_t hh[8], ll[8];
@@ -690,7 +700,8 @@ __global__ void __launch_bounds__(tc7::NTHR, 1) k_shade_tc7(ShadeTcParams p) {
                     const float a = (sm.alpha_part[0][row] + sm.alpha_part[1][row]) + sm.alpha_e[row] + __ldg(p.ba) - 1.0f;
                     sm.alpha_e[row] = 0.f;
                     const float sp = a > 20.f ? a : log1pf(expf(a));
-                    const float zz = seg_scan8(sp * wrow, lane, qr.st);
+                    // order 2: density per neighbour, weighted sum over the sample's rows; order 1: `a` is already the sample's value (its last row)
+                    const float zz = p.o.agg_intrp_order == 1 ? sp : seg_scan8(sp * wrow, lane, qr.st);
                     if (swrite) p.sigma[sidx] = zz;
                 }
                 __syncwarp();
@@ -1149,7 +1160,7 @@ __global__ void __launch_bounds__(DEFER ? tc8::NTHR_DEFER : tc8::NTHR, 1) k_shad
             for (int gq = 0; gq < NGRP; ++gq) a += sm.alpha_part[tf & 1][gq][row];          // fixed order: deterministic
             a += __ldg(p.ba) - 1.0f;
             const float sp = a > 20.f ? a : log1pf(expf(a));
-            const float zz = seg_scan8(sp * wrow, lane, st);
+            const float zz = p.o.agg_intrp_order == 1 ? sp : seg_scan8(sp * wrow, lane, st);      // (order 1: see k_shade_tc7)
             if (swrite) p.sigma[sidx] = zz;
             return true;
         };

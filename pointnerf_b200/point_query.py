@@ -110,7 +110,7 @@ class QueryResult:
                     sample_ray_dirs=None if dirs is None else dirs[:R2], ray_mask=ray_mask, ray_row=ray_row)
 
 
-def make_cam_opts(campos, camrotc2w, Rw2c=None, vsize_z=0.0, bg_color=(1., 1., 1.), raydist_mode_unit=1):
+def make_cam_opts(campos, camrotc2w, Rw2c=None, vsize_z=0.0, bg_color=(1., 1., 1.), raydist_mode_unit=1, agg_intrp_order=2):
     o = _lib.ShadeOpts()
     cp = [float(v) for v in torch.as_tensor(campos).reshape(-1).tolist()]
     rot = [float(v) for v in torch.as_tensor(camrotc2w).reshape(-1).tolist()]
@@ -124,6 +124,7 @@ def make_cam_opts(campos, camrotc2w, Rw2c=None, vsize_z=0.0, bg_color=(1., 1., 1
         o.Rw2c[i] = rw[i]
     o.vsize_z = float(vsize_z)
     o.raydist_mode_unit = int(raydist_mode_unit)
+    o.agg_intrp_order = int(agg_intrp_order)
     return o
 
 

@@ -27,7 +27,7 @@ MLP_SHAPES = ((256, 284), (256, 256), (256, 263), (256, 256), (1, 256), (128, 28
 MLP_KPAD = (288, 256, 272, 256, 256, 288, 128, 128, 128)  # rows of the W^T buffers handed to the kernels
 
 _REQUIRED = dict(
-    agg_dist_pers=20, agg_distance_kernel="linear", agg_intrp_order=2, apply_pnt_mask=1, num_feat_freqs=3,
+    agg_dist_pers=20, agg_distance_kernel="linear", apply_pnt_mask=1, num_feat_freqs=3,
     dist_xyz_freq=5, dist_xyz_deno=0, num_viewdir_freqs=4, view_ori=0, shading_feature_mlp_layer1=2,
     shading_feature_mlp_layer2=0, shading_feature_mlp_layer3=2, shading_alpha_mlp_layer=1,
     shading_color_mlp_layer=4, shading_feature_num=256, act_type="LeakyReLU", act_super=1,
@@ -49,6 +49,12 @@ def check_opt(opt):
             ok = str(have) == str(want)
         if not ok:
             raise NotImplementedError("pnb200: option %s=%r is outside the implemented hot path (needs %r)" % (k, have, want))
+    order = int(getattr(opt, "agg_intrp_order", 2))
+    if order not in (1, 2):
+        # agg_intrp_order 0 (features interpolated before the MLP) does not run in the reference either: viewmlp raises a shape error with
+        # the shipped colour / direction inputs (point_aggregators.py:563 vs :552-555) and another one without them (block1 is built for
+        # 224 inputs, :279-280, but receives the position encoding as well)
+        raise NotImplementedError("pnb200: agg_intrp_order=%d is outside the implemented hot path (2, the shipped value, or 1)" % order)
     aw = getattr(opt, "agg_axis_weight", None)
     if aw is not None and any(float(a) != 1.0 for a in aw):
         raise NotImplementedError("pnb200: agg_axis_weight must be None or 1 1 1")
@@ -441,7 +447,8 @@ class NeuralPointsRayMarching(nn.Module):
         cp, rt, bg = _to_list(campos)[:3], _to_list(camrotc2w)[:9], _to_list(bg_color)[:3]
         q = npnts.querier.run_query(npnts.xyz.detach(), raydir, cp, float(near), float(far), t=t, want_counters=want_counters)
         o = make_cam_opts(cp, rt, Rw2c=rw2c_host_of(npnts),
-                          vsize_z=float(opt.vsize[2]), bg_color=bg, raydist_mode_unit=int(getattr(opt, "raydist_mode_unit", 0)))
+                          vsize_z=float(opt.vsize[2]), bg_color=bg, raydist_mode_unit=int(getattr(opt, "raydist_mode_unit", 0)),
+                          agg_intrp_order=int(getattr(opt, "agg_intrp_order", 2)))
         cap = q.desc.cap_samples
         self._generation += 1
         if self._sigma_rgb is None or self._sigma_rgb.shape[0] < cap or self._sigma_rgb.device != dev:

@@ -41,14 +41,15 @@ def _forward(net, cfg, rays):
 
 
 @pytest.mark.parametrize("precision,bwd_fp32", [("bf16x3", 0), ("bf16x3", 1), ("bf16x3", 4), ("fp32", 0)])
-@pytest.mark.parametrize("name", ["tiny_opaque", "tiny_thin_sr8"])
+@pytest.mark.parametrize("name", ["tiny_opaque", "tiny_thin_sr8", "tiny_order1"])
 def test_gradients_match_reference_fixture(name, precision, bwd_fp32, golden_dir):
     """bwd_fp32 = 0: every layer GEMM of the backward on the tensor cores (tcgen05, BF16x3; default); 4: the forward recompute on the
     fp32 CUDA-core tiles (fp32-faithful LeakyReLU masks), dX / dW on the tensor cores; 1: everything on the fp32 tiles.  Modes 1 and 4
     meet the strict tolerance on every tensor; mode 0 on the MLP tensors and points_conf, and on all but a handful of points."""
     fx = np.load(os.path.join(golden_dir, name + ".npz"))
     cfg = scene.CONFIGS["tiny"]
-    net, pts, opt = harness.build_model(cfg, DEV, SR=int(fx["SR"]), max_o=100000, pnb_precision=precision, pnb_bwd_fp32=bwd_fp32)
+    order = int(fx["agg_intrp_order"]) if "agg_intrp_order" in fx.files else 2       # tiny_order1: the reference run with --agg_intrp_order 1
+    net, pts, opt = harness.build_model(cfg, DEV, SR=int(fx["SR"]), max_o=100000, pnb_precision=precision, pnb_bwd_fp32=bwd_fp32, agg_intrp_order=order)
     net.aggregator.load_state_dict({k[4:]: torch.from_numpy(fx[k]) for k in fx.files if k.startswith("mlp.")})
     out = _forward(net, cfg, scene.make_rays(cfg, fx["pixels"]))
     assert np.abs(out["coarse_raycolor"][0].detach().cpu().numpy() - fx["coarse_raycolor"]).max() <= 1e-4

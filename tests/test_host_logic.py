@@ -39,7 +39,8 @@ def test_hyperparameters_match_reference_fixture(name, golden_dir):
 def test_option_gate_rejects_unimplemented_values():
     cfg = scene.CONFIGS["tiny"]
     check_opt(harness.make_opt(cfg))
-    for k, v in (("agg_intrp_order", 1), ("agg_dist_pers", 10), ("act_type", "ReLU"), ("num_feat_freqs", 0),
+    check_opt(harness.make_opt(cfg, agg_intrp_order=1))          # alpha_branch on the aggregated feature
+    for k, v in (("agg_intrp_order", 0), ("agg_dist_pers", 10), ("act_type", "ReLU"), ("num_feat_freqs", 0),
                  ("shading_color_mlp_layer", 2), ("prob", 2), ("agg_axis_weight", [1.0, 2.0, 1.0])):
         with pytest.raises(NotImplementedError):
             check_opt(harness.make_opt(cfg, **{k: v}))

@@ -15,9 +15,10 @@ def _mlp_from(fx, prefix="mlp."):
     return {k[len(prefix):]: torch.from_numpy(fx[k]) for k in fx.files if k.startswith(prefix)}
 
 
-@pytest.mark.parametrize("name", ["tiny_opaque", "tiny_thin_sr8"])
+@pytest.mark.parametrize("name", ["tiny_opaque", "tiny_thin_sr8", "tiny_order1"])
 def test_shade_oracle_matches_reference_fixture(name, golden_dir):
     fx = np.load(os.path.join(golden_dir, name + ".npz"))
+    order = int(fx["agg_intrp_order"]) if "agg_intrp_order" in fx.files else 2
     cfg = scene.CONFIGS["tiny"]
     pts = scene.make_points(cfg)
     rays = scene.make_rays(cfg, fx["pixels"])
@@ -25,7 +26,8 @@ def test_shade_oracle_matches_reference_fixture(name, golden_dir):
     pts_g = {k: v.clone().requires_grad_(k in ("embedding", "color", "dir", "conf")) for k, v in pts.items()}
     mlp = {k: v.clone().requires_grad_(True) for k, v in _mlp_from(fx).items()}
     sh = shade_oracle.shade(pts_g, mlp, torch.from_numpy(fx["sample_pidx"]), torch.from_numpy(fx["sample_loc_w"]),
-                            rays["raydir"][0][mask], torch.tensor(cfg.campos), torch.eye(3), [cfg.vsize] * 3, torch.ones(3))
+                            rays["raydir"][0][mask], torch.tensor(cfg.campos), torch.eye(3), [cfg.vsize] * 3, torch.ones(3),
+                            agg_intrp_order=order)
     # forward: same torch build, same op order -> tight
     for a, b in (("ray_color", "coarse_raycolor"), ("opacity", "coarse_point_opacity"), ("weight", "weight"),
                  ("conf_coefficient", "conf_coefficient"), ("sample_loc", "sample_loc")):

@@ -1012,7 +1012,11 @@ __device__ __forceinline__ void tc8_epi_layer(SmemT& sm, uint32_t accb, int grp,
 // SCHED (DEFER only): how the 5 held chunks are spread over the gaps of the next tile - before the layer-1 (A) / layer-2 (B) / layer-3 (C)
 // accumulator barriers and before the layer-4 barrier (D): 0 = 2/2/1/0, 1 = 1/2/1/1, 2 = 0/2/2/1 (default: nothing in gap A, which sits on the
 // layer 4 -> layer 1 -> layer 2 critical path).  PFN: chunks of `pre` in flight in the layer-1 epilogue (2 with DEFER: registers).
-template <int NSTAGE, bool COOP, bool DEFER, int SCHED = 0, int PFN = 3>
+// UNI: the issuer's code is a provably uniform region (operands in uniform registers); false = the previous form (A/B).
+// XF: layers are queued back to back (tcgen05.mma execute in issue order: a layer's accumulator region is the previous layer's dead operand
+// region, so the issuer need not wait for the previous layer's completion barrier - only for the per-K-block operand barriers), and layer 3
+// issues its extras K block (operand from shared memory, independent of the layer-2 epilogue) FIRST, into the layer turn-around bubble.
+template <int NSTAGE, bool COOP, bool DEFER, int SCHED = 0, int PFN = 3, bool UNI = true, bool XF = true>
 __global__ void __launch_bounds__(DEFER ? tc8::NTHR_DEFER : tc8::NTHR, 1) k_shade_tc8(ShadeTcParams p) {
     using SmemT = tc8::Smem<NSTAGE, COOP>;
     constexpr int NGRP = tc8::NGRP;
@@ -1020,6 +1024,10 @@ __global__ void __launch_bounds__(DEFER ? tc8::NTHR_DEFER : tc8::NTHR, 1) k_shad
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     SmemT& sm = *reinterpret_cast<SmemT*>(smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u));
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    // the issuer's role branch is taken on a warp index that is uniform BY CONSTRUCTION (constant-lane shuffle): ptxas then treats the issuer's
+    // code as a uniform region and keeps the MMA operands in uniform registers.  (Only the issuer: with uniform branches for the other
+    // roles too, the epilogue code got 40 % slower - 37.0 k vs 30 k cycles per tile, profiles/r02_tc8_experiments.log #12.)
+    const int warp_u = UNI ? __shfl_sync(0xffffffffu, tid >> 5, 0) : warp;
     const pnb_query_t& q = p.q;
     const int n_valid = min(q.counters[PNB_QC_N_VALID], p.hbar_cap);
     const int n_quads = p.pack_cnt[0];
@@ -1058,57 +1066,47 @@ __global__ void __launch_bounds__(DEFER ? tc8::NTHR_DEFER : tc8::NTHR, 1) k_shad
 #define TW(slot, expr) [&]() { if (!prof) return (expr); const long long _t0 = clock64(); const bool _r = (expr); _tm = clock64(); if (lane == 0) prof_add(p, slot, _tm - _t0); return _r; }()
 #define TB(slot) do { if (prof) { const long long _t1 = clock64(); if (lane == 0) prof_add(p, slot, _t1 - _tm); _tm = _t1; } } while (0)
 
-    if (warp >= W_LOAD) {
+    if (warp_u >= W_LOAD) {          // (uniform branch: see warp_u)
         if (DEFER) reg_dec<tc8::REG_CTRL>();
     }
-    if (warp == W_LOAD) {
-        // ============================================================ weight ring: one K block (hi + lo image, 32 KB) per stage
-        if (lane == 0) {
-            const uint32_t total = (uint32_t)my_tiles * tc8::STAGES_PER_TILE;
-            uint32_t s = 0, ph = 0, j = 0;
-            for (uint32_t n = 0; n < total; ++n) {
-                if (!TW(0, mbar_wait(&sm.bar_empty[s], ph ^ 1u, p.err, 91))) break;
-                const uint32_t blk = j < (uint32_t)tc8::NKB1 ? (uint32_t)tc8::KB1_FIRST + j : 9u + (j - (uint32_t)tc8::NKB1);
-                if (p.dbg_no_weights) mbar_arrive(&sm.bar_full[s]);
-                else {
-                    mbar_arrive_expect_tx(&sm.bar_full[s], tc8::STAGE);
-                    const unsigned char* src = p.wimg + (size_t)blk * tc8::STAGE;
-                    bulk_g2s(sm.b[s], src, IMG, &sm.bar_full[s]);
-                    bulk_g2s(sm.b[s] + IMG, src + IMG, IMG, &sm.bar_full[s]);
-                }
-                if (++s == (uint32_t)NSTAGE) { s = 0; ph ^= 1u; }
-                if (++j == (uint32_t)tc8::STAGES_PER_TILE) j = 0;
-            }
-        }
-    } else if (warp == W_ISSUE) {
+    if (warp_u == W_ISSUE) {
         // ============================================================ MMA issuer (whole warp, warp-uniform; one commit per K block)
+        // every value the MMA operands are computed from is made uniform BY CONSTRUCTION (uni32 / uni, umma.cuh)
+        const bool prof = (p.dbg_flags & 1) && blockIdx.x == 0;      // (shadows the per-role flag: this one is provably uniform)
+        auto uni32 = [](uint32_t x) -> uint32_t { return UNI ? pnb::uni32(x) : x; };
+        auto uni = [](bool b) -> bool { return UNI ? pnb::uni(b) : b; };
         const uint32_t idesc = make_idesc_bf16(128, 256);
         const uint32_t hiw = desc_hi<LAYOUT>(), xe_hiw = (256u >> 4) | (1u << 14);
-        const uint32_t b0_lo = desc_lo<LAYOUT>(smem_u32(sm.b[0]));
-        const uint32_t ahi_lo = desc_lo<LAYOUT>(smem_u32(sm.a_hi)), alo_lo = desc_lo<LAYOUT>(smem_u32(sm.a_lo));
-        const uint32_t xeh_lo0 = desc_lo<LAYOUT_NONE>(smem_u32(sm.xe_hi[0])), xel_lo0 = desc_lo<LAYOUT_NONE>(smem_u32(sm.xe_lo[0]));
+        const uint32_t b0_lo = uni32(desc_lo<LAYOUT>(smem_u32(sm.b[0])));
+        const uint32_t ahi_lo = uni32(desc_lo<LAYOUT>(smem_u32(sm.a_hi))), alo_lo = uni32(desc_lo<LAYOUT>(smem_u32(sm.a_lo)));
+        const uint32_t xeh_lo0 = uni32(desc_lo<LAYOUT_NONE>(smem_u32(sm.xe_hi[0]))), xel_lo0 = uni32(desc_lo<LAYOUT_NONE>(smem_u32(sm.xe_lo[0])));
+        const uint32_t uP = uni32(sm.tmem_base), uQ = uP + 256u;
+        const int n_my = (int)uni32((uint32_t)my_tiles);
         constexpr uint32_t KADV = kstep_adv16<LAYOUT>();
         uint32_t s = 0, ph = 0, c_acc = 0, c_pack = 0;
         bool ok = true;
-        for (int t = 0; t < my_tiles && ok; ++t) {
+        for (int t = 0; t < n_my && ok; ++t) {
             const uint32_t xeh_lo = xeh_lo0 + (uint32_t)(t & 1) * (XE >> 4), xel_lo = xel_lo0 + (uint32_t)(t & 1) * (XE >> 4);
             for (int l = 0; l < 4 && ok; ++l) {
-                const uint32_t acc = (l & 1) ? tP : tQ;
-                const uint32_t ab = (l & 1) ? tQ : tP;
-                if (l > 0) { if (!TW(1, mbar_wait(&sm.bar_acc_full, c_acc & 1u, p.err, 92))) { ok = false; break; } ++c_acc; }
-                else if (t > 0) { if (!TW(2, mbar_wait(&sm.bar_final, (uint32_t)(t - 1) & 1u, p.err, 92))) { ok = false; break; } }
-                if (l == 0) { if (!TW(3, mbar_wait(&sm.bar_a1_ready, (uint32_t)t & 1u, p.err, 93))) { ok = false; break; } }
-                if (l == 1 && t > 0) { if (!TW(4, mbar_wait(&sm.bar_drain, (uint32_t)(t - 1) & 1u, p.err, 94))) { ok = false; break; } }
+                const uint32_t acc = (l & 1) ? uP : uQ;
+                const uint32_t ab = (l & 1) ? uQ : uP;
+                if (!XF) {
+                    if (l > 0) { if (!uni(TW(1, mbar_wait(&sm.bar_acc_full, c_acc & 1u, p.err, 92)))) { ok = false; break; } ++c_acc; }
+                    else if (t > 0) { if (!uni(TW(2, mbar_wait(&sm.bar_final, (uint32_t)(t - 1) & 1u, p.err, 92)))) { ok = false; break; } }
+                }
+                if (l == 0) { if (!uni(TW(3, mbar_wait(&sm.bar_a1_ready, (uint32_t)t & 1u, p.err, 93)))) { ok = false; break; } }
+                if (l == 1 && t > 0) { if (!uni(TW(4, mbar_wait(&sm.bar_drain, (uint32_t)(t - 1) & 1u, p.err, 94)))) { ok = false; break; } }
                 tc_fence_after();
                 const int nkb = l == 0 ? tc8::NKB1 : nkb_of(l);
-                for (int kb = 0; kb < nkb && ok; ++kb) {
+                for (int kk = 0; kk < nkb && ok; ++kk) {
+                    const int kb = (XF && l == 2) ? (kk == 0 ? 8 : kk - 1) : kk;          // XF: layer 3 starts with its extras K block
                     const bool need_chunks = (l >= 1 && kb < 8);
                     uint64_t* cb0 = need_chunks ? &sm.bar_kblk[kb] : &sm.bar_full[s];
                     const uint32_t cp0 = need_chunks ? (c_pack & 1u) : ph;
                     TB(7);
-                    if (!mbar_try_wait4(&sm.bar_full[s], ph, cb0, cp0, &sm.bar_full[s], ph, cb0, cp0)) {
-                        if (need_chunks && !TW(5, mbar_wait(cb0, cp0, p.err, 95))) { ok = false; break; }
-                        if (!TW(6, mbar_wait(&sm.bar_full[s], ph, p.err, 96))) { ok = false; break; }
+                    if (!uni(mbar_try_wait2(&sm.bar_full[s], ph, cb0, cp0))) {
+                        if (need_chunks && !uni(TW(5, mbar_wait(cb0, cp0, p.err, 95)))) { ok = false; break; }
+                        if (!uni(TW(6, mbar_wait(&sm.bar_full[s], ph, p.err, 96)))) { ok = false; break; }
                     }
                     tc_fence_after();
                     const uint32_t bh = b0_lo + s * (uint32_t)(tc8::STAGE >> 4), bl = bh + (uint32_t)(IMG >> 4);
@@ -1121,12 +1119,12 @@ __global__ void __launch_bounds__(DEFER ? tc8::NTHR_DEFER : tc8::NTHR, 1) k_shad
                         mma_ss2_w(acc, akb_hi, hiw, bl, hiw, idesc, 1u);
                         mma_ss2_w(acc, akb_hi + KADV, hiw, bl + KADV, hiw, idesc, 1u);
                     } else if (kb == 8) {
-                        mma_ss2_w(acc, xeh_lo, xe_hiw, bh, hiw, idesc, 1u);
+                        mma_ss2_w(acc, xeh_lo, xe_hiw, bh, hiw, idesc, kk ? 1u : 0u);
                         mma_ss2_w(acc, xel_lo, xe_hiw, bh, hiw, idesc, 1u);
                         mma_ss2_w(acc, xeh_lo, xe_hiw, bl, hiw, idesc, 1u);
                     } else {
                         const uint32_t tcol = ab + (uint32_t)(kb * 32);
-                        mma_ts2_w(acc, tcol, bh, hiw, idesc, kb ? 1u : 0u);
+                        mma_ts2_w(acc, tcol, bh, hiw, idesc, kk ? 1u : 0u);
                         mma_ts2_w(acc, tcol + 8u, bh, hiw, idesc, 1u);
                         mma_ts2_w(acc, tcol + 16u, bh + KADV, hiw, idesc, 1u);
                         mma_ts2_w(acc, tcol + 24u, bh + KADV, hiw, idesc, 1u);
@@ -1140,6 +1138,27 @@ __global__ void __launch_bounds__(DEFER ? tc8::NTHR_DEFER : tc8::NTHR, 1) k_shad
                 if (l >= 1) ++c_pack;
                 mma_commit_w(l < 3 ? &sm.bar_acc_full : &sm.bar_final);
                 if (l == 0) mma_commit_w(&sm.bar_a1_free);
+            }
+        }
+    } else if (warp == W_LOAD) {
+        // ============================================================ weight ring: one K block (hi + lo image, 32 KB) per stage
+        if (lane == 0) {
+            const uint32_t total = (uint32_t)my_tiles * tc8::STAGES_PER_TILE;
+            uint32_t s = 0, ph = 0, j = 0;
+            for (uint32_t n = 0; n < total; ++n) {
+                if (!TW(0, mbar_wait(&sm.bar_empty[s], ph ^ 1u, p.err, 91))) break;
+                uint32_t blk = j < (uint32_t)tc8::NKB1 ? (uint32_t)tc8::KB1_FIRST + j : 9u + (j - (uint32_t)tc8::NKB1);
+                // XF: layer 3 (stages NKB1 + 8 .. NKB1 + 16 of a tile, weight blocks 17 .. 25) takes its extras block (25) FIRST
+                if (XF && j >= (uint32_t)tc8::NKB1 + 8u && j < (uint32_t)tc8::NKB1 + 17u) blk = j == (uint32_t)tc8::NKB1 + 8u ? 25u : blk - 1u;
+                if (p.dbg_no_weights) mbar_arrive(&sm.bar_full[s]);
+                else {
+                    mbar_arrive_expect_tx(&sm.bar_full[s], tc8::STAGE);
+                    const unsigned char* src = p.wimg + (size_t)blk * tc8::STAGE;
+                    bulk_g2s(sm.b[s], src, IMG, &sm.bar_full[s]);
+                    bulk_g2s(sm.b[s] + IMG, src + IMG, IMG, &sm.bar_full[s]);
+                }
+                if (++s == (uint32_t)NSTAGE) { s = 0; ph ^= 1u; }
+                if (++j == (uint32_t)tc8::STAGES_PER_TILE) j = 0;
             }
         }
     } else if (warp > W_ISSUE) {
@@ -1738,7 +1757,7 @@ extern "C" int pnb_shade_forward_tc(const pnb_query_t* q, const pnb_points_t* pt
             // 4-stage weight ring + coalesced gather of the hoisted table (variants measured: profiles/r02_tc8_experiments.log)
             // deferred last epilogue (default; dbg bit 3 = the non-deferred form, bit-identical results)
             // (schedules / prefetch depths measured: profiles/r02_tc8_experiments.log #10)
-            if (p.dbg_flags & 8) k_shade_tc8<4, true, false><<<n_sm, tc8::NTHR, smem_tc8, stream>>>(p);
+            if (p.dbg_flags & 8) k_shade_tc8<4, true, false><<<n_sm, tc8::NTHR, smem_tc8, stream>>>(p);                 // non-deferred last epilogue
             else k_shade_tc8<4, true, true, 2, 2><<<n_sm, tc8::NTHR_DEFER, smem_tc8, stream>>>(p);
         }
         else k_shade_tc7<<<n_sm, tc7::NTHR, smem_tc7, stream>>>(p);

@@ -95,6 +95,25 @@ __device__ __forceinline__ bool mbar_try_wait4(uint64_t* b0, uint32_t p0, uint64
         : "memory");
     return ok != 0;
 }
+// two-barrier form of the probe
+__device__ __forceinline__ bool mbar_try_wait2(uint64_t* b0, uint32_t p0, uint64_t* b1, uint32_t p1) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred q0, q1;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 q0, [%1], %3;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 q1, [%2], %4;\n\t"
+        "and.pred q0, q0, q1;\n\tselp.u32 %0, 1, 0, q0;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(b0)), "r"(smem_u32(b1)), "r"(p0), "r"(p1)
+        : "memory");
+    return ok != 0;
+}
+// Warp-uniformity for the issuing warp: every lane of the issuer executes the same code on the same values, but values that come from
+// memory (the TMEM base address, the tile count) or from per-lane barrier probes are not PROVABLY uniform, and ptxas then keeps the MMA
+// operands in ordinary registers and moves them to uniform registers for every single UTCHMMA (ELECT + ~8 R2UR.BROADCAST + VOTEU each).
+// A constant-lane shuffle / a vote makes them uniform by construction: the descriptors then live in uniform registers.
+__device__ __forceinline__ uint32_t uni32(uint32_t x) { return __shfl_sync(0xffffffffu, x, 0); }
+__device__ __forceinline__ bool uni(bool b) { return __all_sync(0xffffffffu, b) != 0; }
 __device__ __forceinline__ uint64_t globaltimer_ns_fwd() {
     uint64_t t;
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));

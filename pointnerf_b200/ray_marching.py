@@ -14,6 +14,7 @@ Only the shipped hot-path configuration (SURVEY.md section 8 head) is implemente
 value raises NotImplementedError (no silent fallback).
 """
 import math
+import os
 
 import torch
 import torch.nn as nn
@@ -363,7 +364,7 @@ def _init_state(mod):
     # (k_shade_tc8: the point-only inputs of block1.0 hoisted into a per-point table, rebuilt when points_embeding or
     # block1.0 change); 0 = always the general kernel (k_shade_tc7), which is what training steps use in either case.
     mod.frozen_ok = bool(int(getattr(opt, "pnb_frozen", 1)))
-    mod.dbg_flags = int(getattr(opt, "pnb_dbg_flags", 0))
+    mod.dbg_flags = int(getattr(opt, "pnb_dbg_flags", 0)) | int(os.environ.get("PNB_DBG_FLAGS_DEFAULT", "0"))   # (env: kernel experiments under the test-suite)
     mod.last = None
     mod._pnb_ready = True
 

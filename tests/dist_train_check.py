@@ -85,7 +85,8 @@ def main():
         res["train_sparse" if sparse else "train_dense"] = dict(max_gradient_diff_vs_unsharded_rel=err, parameters_moved_by=moved, loss=float(loss),
                                                                 replicas_bit_identical=True)
     # ---------------- 2. render: interleave-sharded frame + all-gather == single-rank frame
-    net, _, _ = harness.build_model(cfg, dev, alpha_bias=3.0)
+    # (a centre patch keeps ~22 valid samples per ray, more than the 10 the render_full() workspace heuristic starts from: size it for SR)
+    net, _, _ = harness.build_model(cfg, dev, alpha_bias=3.0, pnb_max_valid_per_ray=cfg.SR)
     full = scene.make_rays(cfg, scene.centre_patch(cfg, 300))
     rd = full["raydir"][0]
     R = rd.shape[0]

@@ -4,7 +4,7 @@ counts of the Blackwell tensor-core / tensor-memory / bulk-copy mnemonics in eve
     python tools/sass_summary.py > profiles/r02_sass_summary.txt
 
 UTCHMMA = tcgen05.mma (kind::f16), LDTM / STTM = tcgen05.ld / tcgen05.st, UTCBAR = tcgen05.commit (mbarrier arrive),
-UBLKCP = cp.async.bulk (TMA engine, 1-D bulk copy), UTMALDG = cp.async.bulk.tensor (tensor-map TMA), SYNCS = mbarrier ops,
+UBLKCP = cp.async.bulk (TMA engine, 1-D bulk copy), USETMAXREG = setmaxnreg (warpgroup register re-allocation), UTMALDG = cp.async.bulk.tensor (tensor-map TMA), SYNCS = mbarrier ops,
 HMMA = legacy mma.sync (must be 0 everywhere)."""
 import collections
 import os
@@ -14,7 +14,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "pointnerf_b200", "csrc", "libpnb200.so")
-MNEMONICS = ["UTCHMMA", "LDTM", "STTM", "UTCBAR", "UBLKCP", "UTMALDG", "SYNCS", "HMMA", "FFMA", "MUFU", "ATOM", "RED", "LDG", "STG", "SHFL"]
+MNEMONICS = ["UTCHMMA", "LDTM", "STTM", "UTCBAR", "UBLKCP", "UTMALDG", "USETMAXREG", "SYNCS", "HMMA", "FFMA", "MUFU", "ATOM", "RED", "LDG", "STG", "SHFL"]
 
 
 def main():

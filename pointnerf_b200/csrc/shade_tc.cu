@@ -405,12 +405,14 @@ __global__ void __launch_bounds__(256) k_pack_place(pnb_query_t q, int cap, cons
 // <= 8 lanes, first lane st); the last row of a sample (swrite) holds the sums and writes h-bar.
 // EARLY (v8): ALL chunks of this warp are read into registers first and `drain_bar` is signalled right away - the accumulator region
 // is then free for layer 2 of the next tile ~2 k cycles after the last MMA instead of after the whole reduction (~10 k).
-template <int NG, int NCHUNK, bool EARLY = false>
+// O1: agg_intrp_order == 1 as a COMPILE-TIME flag (as a run-time flag ptxas if-converted the order-1 dot product: 16 extra loads + FMAs per
+// chunk executed speculatively on the shipped order-2 path, seen in the ncu source page).
+template <int NG, int NCHUNK, bool EARLY = false, bool O1 = false>
 __device__ __forceinline__ float last_chunks_packed(const ShadeTcParams& p, uint32_t accb, int G, float wrow, int st, bool swrite, int sidx, int lane,
                                                     uint64_t* drain_bar = nullptr) {
     using namespace tc;
     const float* bias = p.bias[3];
-    const bool order1 = p.o.agg_intrp_order == 1;
+    constexpr bool order1 = O1;
     float apart = 0.f;
     uint32_t vv[EARLY ? NCHUNK : 2][16];
     if (EARLY) {
@@ -475,11 +477,12 @@ __device__ __forceinline__ float last_chunks_packed(const ShadeTcParams& p, uint
 }
 // One 16-column chunk of the last epilogue from REGISTERS (the deferred form of last_chunks_packed<.., EARLY = true>: identical
 // arithmetic in identical order, so the two forms give bit-identical h-bar / alpha sums): columns c0 .. c0+15 of this lane's row in v.
+template <bool O1>
 __device__ __forceinline__ void last_chunk_from_regs(const ShadeTcParams& p, int c0, const uint32_t* v, float wrow, int st, bool swrite, int sidx, int lane,
                                                      float& apart) {
     using namespace tc;
     const float* bias = p.bias[3];
-    const bool order1 = p.o.agg_intrp_order == 1;
+    constexpr bool order1 = O1;
     float z[16];
 #pragma unroll
     for (int e4 = 0; e4 < 4; ++e4) {
@@ -542,6 +545,7 @@ __device__ __forceinline__ QuadRow quad_row(uint32_t head, int tot, int lane) {
     return r;
 }
 
+template <bool O1>
 __global__ void __launch_bounds__(tc7::NTHR, 1) k_shade_tc7(ShadeTcParams p) {
     using namespace tc;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -691,7 +695,7 @@ __global__ void __launch_bounds__(tc7::NTHR, 1) k_shade_tc7(ShadeTcParams p) {
                 const int sidx = qr.live ? (int)p.vorder[sm.qfirst[tf & 1][qw] + qr.j] : 0;
                 const bool swrite = qr.is_end && sidx < n_valid;
                 const float wrow = sm.wc[tf & 1][row];
-                const float apart = last_chunks_packed<4, 4>(p, tP + tlane, 2 + part, wrow, qr.st, swrite, sidx, lane);
+                const float apart = last_chunks_packed<4, 4, false, O1>(p, tP + tlane, 2 + part, wrow, qr.st, swrite, sidx, lane);
                 tc_fence_before();
                 sm.alpha_part[part][row] = apart;
                 named_bar_sync(2, tc7::NBUILD);
@@ -701,7 +705,7 @@ __global__ void __launch_bounds__(tc7::NTHR, 1) k_shade_tc7(ShadeTcParams p) {
                     sm.alpha_e[row] = 0.f;
                     const float sp = a > 20.f ? a : log1pf(expf(a));
                     // order 2: density per neighbour, weighted sum over the sample's rows; order 1: `a` is already the sample's value (its last row)
-                    const float zz = p.o.agg_intrp_order == 1 ? sp : seg_scan8(sp * wrow, lane, qr.st);
+                    const float zz = O1 ? sp : seg_scan8(sp * wrow, lane, qr.st);
                     if (swrite) p.sigma[sidx] = zz;
                 }
                 __syncwarp();
@@ -752,7 +756,7 @@ __global__ void __launch_bounds__(tc7::NTHR, 1) k_shade_tc7(ShadeTcParams p) {
                 tc_fence_after();
                 const QuadRow qr = quad_row(sm.qhead[t & 1][quad], (int)sm.qtotal[t & 1][quad], lane);
                 const int sidx = qr.live ? (int)p.vorder[sm.qfirst[t & 1][quad] + qr.j] : 0;
-                const float apart = last_chunks_packed<4, 4>(p, tP + tlane, grp, sm.wc[t & 1][erow], qr.st, qr.is_end && sidx < n_valid, sidx, lane);
+                const float apart = last_chunks_packed<4, 4, false, O1>(p, tP + tlane, grp, sm.wc[t & 1][erow], qr.st, qr.is_end && sidx < n_valid, sidx, lane);
                 tc_fence_before();
                 atomicAdd(&sm.alpha_e[erow], apart);
                 __syncwarp();
@@ -1016,7 +1020,7 @@ __device__ __forceinline__ void tc8_epi_layer(SmemT& sm, uint32_t accb, int grp,
 // XF: layers are queued back to back (tcgen05.mma execute in issue order: a layer's accumulator region is the previous layer's dead operand
 // region, so the issuer need not wait for the previous layer's completion barrier - only for the per-K-block operand barriers), and layer 3
 // issues its extras K block (operand from shared memory, independent of the layer-2 epilogue) FIRST, into the layer turn-around bubble.
-template <int NSTAGE, bool COOP, bool DEFER, int SCHED = 0, int PFN = 3, bool UNI = true, bool XF = true>
+template <int NSTAGE, bool COOP, bool DEFER, bool O1 = false, int SCHED = 0, int PFN = 3, bool UNI = true, bool XF = true>
 __global__ void __launch_bounds__(DEFER ? tc8::NTHR_DEFER : tc8::NTHR, 1) k_shade_tc8(ShadeTcParams p) {
     using SmemT = tc8::Smem<NSTAGE, COOP>;
     constexpr int NGRP = tc8::NGRP;
@@ -1179,7 +1183,7 @@ __global__ void __launch_bounds__(DEFER ? tc8::NTHR_DEFER : tc8::NTHR, 1) k_shad
             for (int gq = 0; gq < NGRP; ++gq) a += sm.alpha_part[tf & 1][gq][row];          // fixed order: deterministic
             a += __ldg(p.ba) - 1.0f;
             const float sp = a > 20.f ? a : log1pf(expf(a));
-            const float zz = p.o.agg_intrp_order == 1 ? sp : seg_scan8(sp * wrow, lane, st);      // (order 1: see k_shade_tc7)
+            const float zz = O1 ? sp : seg_scan8(sp * wrow, lane, st);      // (order 1: see k_shade_tc7)
             if (swrite) p.sigma[sidx] = zz;
             return true;
         };
@@ -1223,7 +1227,7 @@ __global__ void __launch_bounds__(DEFER ? tc8::NTHR_DEFER : tc8::NTHR, 1) k_shad
                 const int sidx = qr.live ? (int)p.vorder[sm.qfirst[tf & 1][qw] + qr.j] : 0;
                 const bool swrite = qr.is_end && sidx < n_valid;
                 const float wrow = sm.wc[tf & 1][row];
-                const float apart = last_chunks_packed<NG4, NCH4_B, true>(p, tP + tlane, 0, wrow, qr.st, swrite, sidx, lane, &sm.bar_drain);
+                const float apart = last_chunks_packed<NG4, NCH4_B, true, O1>(p, tP + tlane, 0, wrow, qr.st, swrite, sidx, lane, &sm.bar_drain);
                 TB(11);
                 if (!DEFER) {
                     if (!finish_sigma(tf, apart, wrow, qr.st, swrite, sidx)) { ok = false; break; }
@@ -1251,7 +1255,7 @@ __global__ void __launch_bounds__(DEFER ? tc8::NTHR_DEFER : tc8::NTHR, 1) k_shad
             if constexpr (DEFER) {
 #pragma unroll
                 for (int i = decltype(first)::value; i < decltype(first)::value + decltype(count)::value; ++i)
-                    last_chunk_from_regs(p, 16 * (1 + grp + NG4 * i), hv[i], d_wrow, d_st, d_sw, d_sidx, lane, d_apart);
+                    last_chunk_from_regs<O1>(p, 16 * (1 + grp + NG4 * i), hv[i], d_wrow, d_st, d_sw, d_sidx, lane, d_apart);
             }
         };
         auto held_done = [&](int tf) -> bool {             // the held tile is finished: publish this warp's alpha partial sum
@@ -1304,7 +1308,7 @@ __global__ void __launch_bounds__(DEFER ? tc8::NTHR_DEFER : tc8::NTHR, 1) k_shad
                 const QuadRow qr = quad_row(sm.qhead[t & 1][quad], (int)sm.qtotal[t & 1][quad], lane);
                 const int sidx = qr.live ? (int)p.vorder[sm.qfirst[t & 1][quad] + qr.j] : 0;
                 if constexpr (!DEFER) {
-                    const float apart = last_chunks_packed<NG4, NCH4_E, true>(p, tP + tlane, 1 + grp, sm.wc[t & 1][erow], qr.st, qr.is_end && sidx < n_valid, sidx,
+                    const float apart = last_chunks_packed<NG4, NCH4_E, true, O1>(p, tP + tlane, 1 + grp, sm.wc[t & 1][erow], qr.st, qr.is_end && sidx < n_valid, sidx,
                                                                               lane, &sm.bar_drain);
                     sm.alpha_part[t & 1][grp][erow] = apart;
                     __syncwarp();
@@ -1728,9 +1732,12 @@ extern "C" int pnb_shade_forward_tc(const pnb_query_t* q, const pnb_points_t* pt
     static_assert(sizeof(ctc2::Smem) + 128 <= kSmemMax, "colour kernel shared-memory carve-out exceeds the per-block limit");
     static_assert(tc7::NSTAGE == 4, "the v7 issuer assumes a 4-stage ring");
     if (!configured[dev]) {
-        PNB_CHECK_CUDA(cudaFuncSetAttribute(k_shade_tc7, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tc7));
-        PNB_CHECK_CUDA(cudaFuncSetAttribute(k_shade_tc8<4, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tc8));
-        PNB_CHECK_CUDA(cudaFuncSetAttribute(k_shade_tc8<4, true, true, 2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tc8));
+        PNB_CHECK_CUDA(cudaFuncSetAttribute(k_shade_tc7<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tc7));
+        PNB_CHECK_CUDA(cudaFuncSetAttribute(k_shade_tc7<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tc7));
+        PNB_CHECK_CUDA(cudaFuncSetAttribute(k_shade_tc8<4, true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tc8));
+        PNB_CHECK_CUDA(cudaFuncSetAttribute(k_shade_tc8<4, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tc8));
+        PNB_CHECK_CUDA(cudaFuncSetAttribute(k_shade_tc8<4, true, true, false, 2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tc8));
+        PNB_CHECK_CUDA(cudaFuncSetAttribute(k_shade_tc8<4, true, true, true, 2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tc8));
         PNB_CHECK_CUDA(cudaFuncSetAttribute(k_color_tc2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_ctc2));
         PNB_CHECK_CUDA(cudaDeviceGetAttribute(&n_sm_of[dev], cudaDevAttrMultiProcessorCount, dev));
         configured[dev] = 1;
@@ -1757,10 +1764,15 @@ extern "C" int pnb_shade_forward_tc(const pnb_query_t* q, const pnb_points_t* pt
             // 4-stage weight ring + coalesced gather of the hoisted table (variants measured: profiles/r02_tc8_experiments.log)
             // deferred last epilogue (default; dbg bit 3 = the non-deferred form, bit-identical results)
             // (schedules / prefetch depths measured: profiles/r02_tc8_experiments.log #10)
-            if (p.dbg_flags & 8) k_shade_tc8<4, true, false><<<n_sm, tc8::NTHR, smem_tc8, stream>>>(p);                 // non-deferred last epilogue
-            else k_shade_tc8<4, true, true, 2, 2><<<n_sm, tc8::NTHR_DEFER, smem_tc8, stream>>>(p);
+            const bool o1 = opts->agg_intrp_order == 1;          // a compile-time flag of the kernels (see last_chunks_packed)
+            if (p.dbg_flags & 8) {                                // non-deferred last epilogue
+                if (o1) k_shade_tc8<4, true, false, true><<<n_sm, tc8::NTHR, smem_tc8, stream>>>(p);
+                else k_shade_tc8<4, true, false, false><<<n_sm, tc8::NTHR, smem_tc8, stream>>>(p);
+            } else if (o1) k_shade_tc8<4, true, true, true, 2, 2><<<n_sm, tc8::NTHR_DEFER, smem_tc8, stream>>>(p);
+            else k_shade_tc8<4, true, true, false, 2, 2><<<n_sm, tc8::NTHR_DEFER, smem_tc8, stream>>>(p);
         }
-        else k_shade_tc7<<<n_sm, tc7::NTHR, smem_tc7, stream>>>(p);
+        else if (opts->agg_intrp_order == 1) k_shade_tc7<true><<<n_sm, tc7::NTHR, smem_tc7, stream>>>(p);
+        else k_shade_tc7<false><<<n_sm, tc7::NTHR, smem_tc7, stream>>>(p);
     }
     if (flags & PNB_TC_COLOR) {
         ColorTcParams ct;

@@ -2,7 +2,7 @@
 # One gpurun call: GPU tests, the bench line, the ncu launch list and one --set full capture of the hot kernels of the same command.
 # usage (build container): tools/gpurun_retry.sh 1500 -- 'bash tools/gpu_round.sh'
 mkdir -p gpurun_out
-python -m pytest tests -m gpu -x -q -rs > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/pytest_gpu.log
+python -m pytest tests -m gpu -q -rs -s > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?"; grep -v ref-kernel gpurun_out/pytest_gpu.log | tail -4
 python bench.py > gpurun_out/bench_1gpu.json 2> gpurun_out/bench_1gpu.err; echo "bench rc=$?"; cut -c1-600 gpurun_out/bench_1gpu.json
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv \
     python bench.py --steps 2 --warmup 3 --only main --no-cpu-baseline > gpurun_out/b_ncu.log 2>&1; echo "ncu launches rc=$?"
